@@ -1,0 +1,195 @@
+/*
+ * sdplrp_b200.h -- C ABI of the B200-native SDPLRPlus hot path.
+ *
+ * This is the drop-in boundary: the entry points a Julia
+ * `ccall` shim binds to replace the reference's operator seam
+ *   A!(out,aux,Ut) / A!(out,aux,Ut,Vt)         src/coreop.jl:36-70
+ *   At_preprocess!(var,aux)                    src/coreop.jl:248-258
+ *   At!(Y,X,aux,var) / At!(y,aux,x,var)        src/coreop.jl:260-300
+ *   f! / g! / fg!                              src/coreop.jl:11-31,305-349
+ *   linesearch! / linesearch_armijo!           src/linesearch.jl:4-191
+ *   lbfgs_dir! / lbfgs_update! / lbfgs_clear!  src/lbfgs.jl:52-149
+ *   approx_mineigval_lanczos / dual_obj        src/coreop.jl:376-415,461-514
+ *   preprocess_sparsecons / SolverAuxiliary    src/preprocess.jl:24-169, src/structs.jl:296-361
+ * (file:line relative to the reference checkout).
+ *
+ * Conventions
+ *  - plain C: pointers and sizes only; no torch / C++ types.
+ *  - every function returns an int32 status: 0 = OK, <0 = error (enum below);
+ *    sdplrp_last_error(h) gives the message.  Nothing throws or calls back.
+ *  - all host pointers are caller-owned and only touched during the call; all
+ *    device memory is owned by the handle.
+ *  - index arrays crossing the ABI are Julia-style 1-based int64; reals are
+ *    IEEE double.  "Rt" matrices are r x n column-major (Julia), which is the
+ *    n x r row-major layout kept in HBM.
+ *  - one handle drives one GPU.  Multi-GPU = one handle per process/rank
+ *    (world > 1), NCCL communicator bootstrapped from an id made by rank 0.
+ *  - calls enqueue on the handle's stream and synchronise only when they
+ *    return host scalars or fill host buffers.
+ */
+#ifndef SDPLRP_B200_H
+#define SDPLRP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sdplrp_handle sdplrp_handle;
+
+enum {
+    SDPLRP_OK = 0,
+    SDPLRP_ERR_CUDA = -1,        /* CUDA runtime error (message has the call) */
+    SDPLRP_ERR_ARG = -2,         /* bad argument / index out of range */
+    SDPLRP_ERR_STATE = -3,       /* call order violated (e.g. no preprocess yet) */
+    SDPLRP_ERR_ASYMMETRIC = -4,  /* lower entry with no upper mirror (src/preprocess.jl:138-158) */
+    SDPLRP_ERR_NCCL = -5,
+    SDPLRP_ERR_NO_DEVICE = -6,   /* no CUDA device: there is no CPU fallback */
+    SDPLRP_ERR_LINESEARCH = -7   /* cubic[1] > eps (src/linesearch.jl:60-62) */
+};
+
+/* dense device matrices (n x r), addressed by id */
+enum {
+    SDPLRP_MAT_R = 0,   /* var.Rt */
+    SDPLRP_MAT_G = 1,   /* var.Gt */
+    SDPLRP_MAT_D = 2,   /* dirt   */
+    SDPLRP_MAT_W0 = 3,  /* scratch (operator tests) */
+    SDPLRP_MAT_W1 = 4,
+    SDPLRP_MAT_S0 = 16, /* L-BFGS s_j = S0 + j, j in [0,h) (0-based slot) */
+    SDPLRP_MAT_Y0 = 48  /* L-BFGS y_j = Y0 + j */
+};
+
+/* device vectors, addressed by id (length in parentheses) */
+enum {
+    SDPLRP_VEC_LAMBDA = 0,     /* (m)   var.lambda */
+    SDPLRP_VEC_LAMBDA_UB = 1,  /* (m)   var.lambda_ub */
+    SDPLRP_VEC_B = 2,          /* (m)   data.b */
+    SDPLRP_VEC_PVIO_RAW = 3,   /* (m+1) var.primal_vio_raw */
+    SDPLRP_VEC_Y = 4,          /* (m+1) var.y */
+    SDPLRP_VEC_PVIO_LB = 5,    /* (m)   var.primal_vio_lb */
+    SDPLRP_VEC_A_RD = 6,       /* (m+1) var.A_RD (already x2) */
+    SDPLRP_VEC_A_DD = 7,       /* (m+1) var.A_DD */
+    SDPLRP_VEC_S_NZVAL = 8,    /* (nnzF) aux.sparse_S.nzval */
+    SDPLRP_VEC_TRIUS_NZVAL = 9 /* (nnzT) aux.triu_sparse_S.nzval (materialised on demand) */
+};
+
+/* ---- lifecycle -------------------------------------------------------- */
+int32_t sdplrp_version(void);
+const char *sdplrp_error_string(int32_t code);
+/* rank 0 makes the 128-byte NCCL id; the host runtime broadcasts it */
+int32_t sdplrp_nccl_unique_id(void *out128);
+/* world == 1: nccl_id may be NULL and NCCL is never touched */
+int32_t sdplrp_create(int32_t device, int32_t rank, int32_t world, const void *nccl_id, sdplrp_handle **out);
+int32_t sdplrp_destroy(sdplrp_handle *h);
+const char *sdplrp_last_error(sdplrp_handle *h);
+int32_t sdplrp_synchronize(sdplrp_handle *h);
+/* the CUDA stream the handle launches on (a cudaStream_t), for event timing */
+void *sdplrp_stream(sdplrp_handle *h);
+
+/* ---- preprocessing: preprocess_sparsecons + SolverAuxiliary ------------
+ * The nA sparse matrices (sparse / diagonal A_i in order of appearance, then
+ * C if it is sparse: src/structs.jl:303-325) as concatenated 1-based triplets
+ * in `findnz` order (CSC: column-major; COO: stored order). mat_off has nA+1
+ * 0-based offsets into I/J/V. sparse_global_inds[k] in 1..m, or m+1 for C.
+ * Builds, on the device, the aggregated upper-triangular and full patterns
+ * and every index map of src/preprocess.jl:24-169 (bit-exact; see
+ * sdplrp_pattern_export) plus the device-only derived layouts. */
+int32_t sdplrp_preprocess(sdplrp_handle *h, int64_t n, int64_t m, int64_t nA, const int64_t *mat_off,
+                          const int64_t *I, const int64_t *J, const double *V,
+                          const int64_t *sparse_global_inds);
+int32_t sdplrp_pattern_sizes(sdplrp_handle *h, int64_t *nnzT, int64_t *nnzF, int64_t *Ec);
+/* 1-based, exactly the seven outputs of preprocess_sparsecons */
+int32_t sdplrp_pattern_export(sdplrp_handle *h, int64_t *triu_colptr, int64_t *triu_rowval, int64_t *matptr,
+                              int64_t *nzind, double *nzval_one, double *nzval_two, int64_t *full_colptr,
+                              int64_t *full_rowval, int64_t *mappedto_triu);
+/* SymLowRankMatrix(Diagonal(D), B): B is n x s column-major; global_id in 1..m+1
+ * (src/structs.jl:11-24, 310-312, 326-328). Call after sdplrp_preprocess
+ * (with nA = 0 when there is no sparse matrix). */
+int32_t sdplrp_add_symlowrank(sdplrp_handle *h, int64_t global_id, int64_t s, const double *B, const double *D);
+/* data.b and constraint types (1 = inequality <=) -> lambda_ub / primal_vio_lb
+ * (src/structs.jl:228, 248-249). is_ineq may be NULL (all equalities). */
+int32_t sdplrp_set_problem(sdplrp_handle *h, const double *b, const uint8_t *is_ineq);
+
+/* ---- state: SolverVars / LBFGSHistory --------------------------------- */
+/* (re)allocates R,G,D and the 2*numlbfgsvecs history for rank r and clears the
+ * history (lbfgs_init, src/lbfgs.jl:35-47; rank_update!, src/coreop.jl:518-526) */
+int32_t sdplrp_set_rank(sdplrp_handle *h, int32_t r, int32_t numlbfgsvecs);
+int32_t sdplrp_set_sigma(sdplrp_handle *h, double sigma);
+int32_t sdplrp_get_sigma(sdplrp_handle *h, double *sigma);
+int32_t sdplrp_get_obj(sdplrp_handle *h, double *obj);
+int32_t sdplrp_upload_mat(sdplrp_handle *h, int32_t mat_id, const double *src /* r*n */);
+int32_t sdplrp_download_mat(sdplrp_handle *h, int32_t mat_id, double *dst /* r*n */);
+int32_t sdplrp_upload_vec(sdplrp_handle *h, int32_t vec_id, const double *src, int64_t len);
+int32_t sdplrp_download_vec(sdplrp_handle *h, int32_t vec_id, double *dst, int64_t len);
+
+/* ---- seam-level operators (parity with test/coreop.jl) ---------------- */
+/* A!(out, aux, Ut): out (m+1 doubles, host, may be NULL) also lands in the
+ * device scratch vector; src/coreop.jl:36-49 */
+int32_t sdplrp_A_uu(sdplrp_handle *h, int32_t U_id, double *out);
+/* A!(out, aux, Ut, Vt) = A((UV'+VU')/2); src/coreop.jl:54-70 */
+int32_t sdplrp_A_uv(sdplrp_handle *h, int32_t U_id, int32_t V_id, double *out);
+/* At_preprocess!(var, aux): S = sum_i y_i A_i + y_{m+1} C on the aggregated
+ * pattern. y (m+1, host) may be NULL to use the device var.y; src/coreop.jl:248-258 */
+int32_t sdplrp_At_preprocess(sdplrp_handle *h, const double *y);
+/* At!(Y, X, aux, var): Y = X*S + low-rank terms; src/coreop.jl:260-279 */
+int32_t sdplrp_At_left(sdplrp_handle *h, int32_t X_id, int32_t Y_id);
+/* At!(y, aux, x, var): y = S*x + low-rank terms, x and y n x ncols
+ * column-major host arrays; src/coreop.jl:281-300 */
+int32_t sdplrp_At_right(sdplrp_handle *h, const double *x, double *y, int64_t ncols);
+
+/* ---- fused iteration -------------------------------------------------- */
+/* f!: primal_vio_raw, obj, AL value; src/coreop.jl:11-31 */
+int32_t sdplrp_f(sdplrp_handle *h, double *L, double *obj);
+/* g!: y, S, G = 2*R*S (+low rank); returns ||G||_F^2 and ||max(raw,lb)||_2^2
+ * (the two norms of src/sdplr.jl:224-234); src/coreop.jl:305-317 */
+int32_t sdplrp_g(sdplrp_handle *h, double *gnorm2, double *pnorm2);
+/* fg!: out = {L, obj, ||G||_F^2, ||pvio||_2^2}; src/coreop.jl:323-349 */
+int32_t sdplrp_fg(sdplrp_handle *h, double out[4]);
+/* lbfgs_dir!(dirt, his, Gt; negate=true) + descent = dot(dirt, Gt);
+ * src/lbfgs.jl:77-124, src/sdplr.jl:197-201 */
+int32_t sdplrp_lbfgs_dir(sdplrp_handle *h, double *descent);
+/* non-descent fallback: Gt *= -1; dirt = Gt; src/sdplr.jl:202-205 */
+int32_t sdplrp_use_gradient_direction(sdplrp_handle *h);
+/* the two A passes of linesearch! fused (A_RD already x2, A_DD) and the five
+ * quartic coefficients; src/linesearch.jl:10-16, 36-56 */
+int32_t sdplrp_linesearch_coeffs(sdplrp_handle *h, double biquadratic[5]);
+/* after alpha is chosen: primal_vio_raw += a(a A_DD + A_RD), obj, and
+ * Rt += a*dirt; src/linesearch.jl:118-124, src/sdplr.jl:219 */
+int32_t sdplrp_step(sdplrp_handle *h, double alpha, double *obj);
+/* lbfgs_update!(dirt, his, Gt, alpha); src/lbfgs.jl:129-149 */
+int32_t sdplrp_lbfgs_update(sdplrp_handle *h, double alpha);
+/* lbfgs_clear!; src/lbfgs.jl:52-59 */
+int32_t sdplrp_lbfgs_clear(sdplrp_handle *h);
+/* lambda_i <- min(ub_i, lambda_i - sigma*raw_i); src/sdplr.jl:358-362 */
+int32_t sdplrp_dual_update(sdplrp_handle *h);
+/* sharp AL at k step sizes + the slope at 0 (eval_AL closure and slope of
+ * linesearch_armijo!; needs linesearch_coeffs first); src/linesearch.jl:158-172 */
+int32_t sdplrp_armijo_eval(sdplrp_handle *h, const double *alphas, int32_t k, double *L, double *slope);
+
+/* ---- dual bound ------------------------------------------------------- */
+/* q-step Lanczos on the current S (set by At_preprocess / g / dual_obj):
+ * alpha,beta (q doubles each, host) receive the unshifted recurrence
+ * coefficients, *iters the steps done. v0 (n, host) is the unnormalised start
+ * vector; NULL draws a seeded Gaussian on the device. reorth != 0 adds full
+ * re-orthogonalisation (the reference has none); src/coreop.jl:461-500 */
+int32_t sdplrp_lanczos(sdplrp_handle *h, int64_t q, const double *v0, uint64_t seed, int32_t reorth,
+                       double *alpha, double *beta, int64_t *iters);
+/* smallest eigenvalue of SymTridiagonal(d, e) (host; replaces the symeigs
+ * call of src/coreop.jl:509-511) */
+int32_t sdplrp_tridiag_mineig(const double *d, const double *e, int64_t k, double *out);
+/* dual_obj (Lanczos branch): y, S, q = 2*ceil(sqrt(max(iter,100))*log n)
+ * Lanczos steps, dual = -y'b + trace_bound*min(lambda_min,0); src/coreop.jl:376-415 */
+int32_t sdplrp_dual_obj(sdplrp_handle *h, double trace_bound, int64_t iter, const double *v0, uint64_t seed,
+                        double *dual_value, double *mineig, int64_t *lanczos_steps);
+
+/* ---- introspection ---------------------------------------------------- */
+/* number of kernels this handle has launched since creation */
+int32_t sdplrp_launch_count(sdplrp_handle *h, int64_t *count);
+/* rows [lo,hi) of R/G/D owned by this rank (0-based) */
+int32_t sdplrp_row_range(sdplrp_handle *h, int64_t *lo, int64_t *hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDPLRP_B200_H */

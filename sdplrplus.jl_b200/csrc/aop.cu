@@ -1,0 +1,328 @@
+// aop.cu -- constraint evaluation A(UU'), A((UV'+VU')/2) and the fused
+// line-search pass {A(RD'+DR'), A(DD')} as sampled-dot kernels over the n x r
+// factors with a segmented reduction into the (m+1)-vector.
+//
+// Reference: src/coreop.jl:36-203 (A!, A_sparse!, A_sparse_formUUt!/UVt!, mydot,
+// A_symlowrank!, tr_UtAU, tr_UtAV) and src/linesearch.jl:10-16.
+//
+// Design (not a translation): the reference first materialises one dot per
+// triu slot (nnzT doubles) and then runs a sparse transposed mat-vec over the
+// per-matrix entry list.  Here every entry computes its own sampled dot from
+// the two factor rows (gathered as 128-bit loads by a sub-warp group of lanes,
+// one group per entry) and accumulates val*dot in registers, so the nnzT
+// scratch round trip disappears and the RD and DD passes share every load.
+//   * "short" matrices (<= kLongMatThreshold triu entries: the m diagonal /
+//     edge constraints): one lane group per matrix, result stored directly.
+//   * "long" matrices (C, identity, D ...): cut into chunks of kChunkEntries
+//     entries, one CTA per chunk, partial sums combined per matrix in a fixed
+//     order by a second tiny kernel (deterministic, no atomics).
+#include <algorithm>
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+template <int VEC>
+struct Ld;
+template <>
+struct Ld<1> {
+    typedef double T;
+    static __device__ __forceinline__ T ld(const double *p) { return __ldg(p); }
+    static __device__ __forceinline__ double dot(T a, T b) { return a * b; }
+};
+template <>
+struct Ld<2> {
+    typedef double2 T;
+    static __device__ __forceinline__ T ld(const double *p) { return ldg2(p); }
+    static __device__ __forceinline__ double dot(T a, T b) { return a.x * b.x + a.y * b.y; }
+};
+
+// this lane's share of the sampled dots of one entry (row <= col).
+// MODE 0: a1 += v2 * <U_row, U_col>
+// MODE 1: a1 += v2 * (<U_col,V_row> + <V_col,U_row>) / 2
+// MODE 2: a1 += v2 * (<U_col,V_row> + <V_col,U_row>)     (A_RD, already x2)
+//         a2 += v2 * <V_row, V_col>                      (A_DD)
+template <int MODE, int VEC>
+__device__ __forceinline__ void entry_accum(const double *__restrict__ U, const double *__restrict__ V, int r, int nv,
+                                            int row, int col, int lg, int G, double v2, double &a1, double &a2,
+                                            int own_lo, int own_hi) {
+    typedef Ld<VEC> L;
+    if (col < own_lo || col >= own_hi) return;  // multi-GPU: the owner of the column computes the entry
+    const double *ur = U + (size_t)row * r, *uc = U + (size_t)col * r;
+    const double *vr = (MODE == 0) ? nullptr : V + (size_t)row * r;
+    const double *vc = (MODE == 0) ? nullptr : V + (size_t)col * r;
+    double d1 = 0.0, d2 = 0.0;
+    if (row == col) {
+        for (int c = lg; c < nv; c += G) {
+            typename L::T u = L::ld(ur + c * VEC);
+            if (MODE == 0) {
+                d1 += L::dot(u, u);
+            } else {
+                typename L::T v = L::ld(vr + c * VEC);
+                d1 += 2.0 * L::dot(u, v);
+                if (MODE == 2) d2 += L::dot(v, v);
+            }
+        }
+    } else {
+        for (int c = lg; c < nv; c += G) {
+            typename L::T a = L::ld(ur + c * VEC), b = L::ld(uc + c * VEC);
+            if (MODE == 0) {
+                d1 += L::dot(a, b);
+            } else {
+                typename L::T p = L::ld(vr + c * VEC), q = L::ld(vc + c * VEC);
+                d1 += L::dot(b, p) + L::dot(q, a);
+                if (MODE == 2) d2 += L::dot(p, q);
+            }
+        }
+    }
+    if (MODE == 1) d1 *= 0.5;
+    a1 += v2 * d1;
+    if (MODE == 2) a2 += v2 * d2;
+}
+
+__device__ __forceinline__ double group_sum(double v, int G) {
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// one lane group per short matrix
+template <int MODE, int VEC>
+__global__ void __launch_bounds__(TPB) k_A_short(int nA, const int *__restrict__ matptr, const int *__restrict__ mat_gid,
+                                                 const int *__restrict__ ent_row, const int *__restrict__ ent_col,
+                                                 const double *__restrict__ ent_two, const double *__restrict__ U,
+                                                 const double *__restrict__ V, int r, int G, double *__restrict__ out1,
+                                                 double *__restrict__ out2, int own_lo, int own_hi) {
+    const int nv = r / VEC;
+    const int lg = threadIdx.x & (G - 1);
+    const int gpw = 32 / G;  // groups per warp
+    const long long warp_global = (long long)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (TPB / 32);
+    const int g_in_warp = (threadIdx.x & 31) / G;
+    for (long long base = warp_global * gpw; base < nA; base += n_warps * gpw) {  // warp-uniform trip count
+        const long long a = base + g_in_warp;
+        double a1 = 0.0, a2 = 0.0;
+        bool store = false;
+        int gid = 0;
+        if (a < nA) {
+            const int beg = matptr[a], end = matptr[a + 1];
+            if (end - beg <= kLongMatThreshold) {
+                store = true;
+                gid = mat_gid[a];
+                for (int k = beg; k < end; k++)
+                    entry_accum<MODE, VEC>(U, V, r, nv, ent_row[k], ent_col[k], lg, G, ent_two[k], a1, a2, own_lo, own_hi);
+            }
+        }
+        a1 = group_sum(a1, G);
+        if (MODE == 2) a2 = group_sum(a2, G);
+        if (store && lg == 0) {
+            out1[gid] = a1;
+            if (MODE == 2) out2[gid] = a2;
+        }
+    }
+}
+
+// one CTA per chunk of a long matrix
+template <int MODE, int VEC>
+__global__ void __launch_bounds__(TPB) k_A_long(const int *__restrict__ chunk_mat, const int *__restrict__ long_mat,
+                                                const int *__restrict__ long_chunk_ptr, const int *__restrict__ matptr,
+                                                const int *__restrict__ ent_row, const int *__restrict__ ent_col,
+                                                const double *__restrict__ ent_two, const double *__restrict__ U,
+                                                const double *__restrict__ V, int r, int G, double *__restrict__ chunk_part,
+                                                int own_lo, int own_hi) {
+    const int c = blockIdx.x;
+    const int l = chunk_mat[c];
+    const int a = long_mat[l];
+    const int beg = matptr[a] + (c - long_chunk_ptr[l]) * kChunkEntries;
+    const int end = min(beg + kChunkEntries, matptr[a + 1]);
+    const int nv = r / VEC;
+    const int lg = threadIdx.x & (G - 1);
+    const int gpb = TPB / G;
+    double acc[2] = {0.0, 0.0};
+    for (int k = beg + threadIdx.x / G; k < end; k += gpb)
+        entry_accum<MODE, VEC>(U, V, r, nv, ent_row[k], ent_col[k], lg, G, ent_two[k], acc[0], acc[1], own_lo, own_hi);
+    block_sum<2>(acc);
+    if (threadIdx.x == 0) {
+        chunk_part[2 * (size_t)c] = acc[0];
+        chunk_part[2 * (size_t)c + 1] = acc[1];
+    }
+}
+
+// fixed-order combination of the chunk partials of each long matrix
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_A_long_combine(const int *__restrict__ long_mat, const int *__restrict__ long_chunk_ptr,
+                                                        const int *__restrict__ mat_gid, const double *__restrict__ chunk_part,
+                                                        double *__restrict__ out1, double *__restrict__ out2) {
+    const int l = blockIdx.x;
+    double acc[2] = {0.0, 0.0};
+    for (int c = long_chunk_ptr[l] + threadIdx.x; c < long_chunk_ptr[l + 1]; c += TPB) {
+        acc[0] += chunk_part[2 * (size_t)c];
+        acc[1] += chunk_part[2 * (size_t)c + 1];
+    }
+    block_sum<2>(acc);
+    if (threadIdx.x == 0) {
+        const int gid = mat_gid[long_mat[l]];
+        out1[gid] = acc[0];
+        if (MODE == 2) out2[gid] = acc[1];
+    }
+}
+
+// ---- low-rank matrices: X'B projections (tall-skinny, memory-bound) --------
+// part[block][k*r+i] = sum over this block's rows j of X[j*r+i] * B[j + k*n], k < s (s <= 8 per launch)
+constexpr int kLrS = 8;
+__global__ void __launch_bounds__(TPB) k_lr_proj(i64 n, int r, int s, const double *__restrict__ X,
+                                                 const double *__restrict__ B, i64 ldb, double *__restrict__ part,
+                                                 unsigned *__restrict__ ticket, double *__restrict__ out) {
+    __shared__ double sm[TPB];
+    const int rpb = TPB / r;  // rows per block step
+    const int i = threadIdx.x % r, jo = threadIdx.x / r;
+    const bool active = jo < rpb;
+    double acc[kLrS];
+#pragma unroll
+    for (int k = 0; k < kLrS; k++) acc[k] = 0.0;
+    if (active) {
+        for (i64 j = (i64)blockIdx.x * rpb + jo; j < n; j += (i64)gridDim.x * rpb) {
+            const double x = X[j * r + i];
+#pragma unroll
+            for (int k = 0; k < kLrS; k++)
+                if (k < s) acc[k] += x * __ldg(&B[j + k * ldb]);
+        }
+    }
+    for (int k = 0; k < s; k++) {
+        __syncthreads();
+        sm[threadIdx.x] = active ? acc[k] : 0.0;
+        __syncthreads();
+        if (threadIdx.x < r) {
+            double t = 0.0;
+            for (int q = 0; q < rpb; q++) t += sm[q * r + threadIdx.x];
+            part[(size_t)blockIdx.x * (r * s) + k * r + threadIdx.x] = t;
+        }
+    }
+    __shared__ bool is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int e = threadIdx.x; e < r * s; e += TPB) {
+            double t = 0.0;
+            for (unsigned bI = 0; bI < gridDim.x; bI++) t += __ldcg(&part[(size_t)bI * (r * s) + e]);
+            out[e] = t;
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
+// out[gid] = sum_{i,k} UB[i,k]*VB[i,k]*D[k] * mult   (tr_UtAU / tr_UtAV)
+__global__ void k_lr_trace(int r, int s, const double *__restrict__ UB, const double *__restrict__ VB,
+                           const double *__restrict__ Dg, double mult, double *__restrict__ out, int gid) {
+    double acc[1] = {0.0};
+    for (int e = threadIdx.x; e < r * s; e += blockDim.x) acc[0] += UB[e] * VB[e] * Dg[e / r];
+    block_sum<1>(acc);
+    if (threadIdx.x == 0) out[gid] = acc[0] * mult;
+}
+
+int pick_group(int nv) {
+    int G = 1;
+    while (G < nv && G < 32) G <<= 1;
+    return G;
+}
+
+template <int MODE>
+int32_t run_sparse(sdplrp_handle *h, const double *U, const double *V, double *out1, double *out2) {
+    if (h->nA <= 0) return SDPLRP_OK;
+    cudaStream_t st = h->stream;
+    const int r = h->r;
+    const bool vec2 = (r % 2 == 0);
+    const int nv = vec2 ? r / 2 : r;
+    const int G = pick_group(nv);
+    const int gpb = TPB / G;
+    const int grid_short = grid_for(h->nA, gpb, 16 * kNumSM);
+    const int lo = (int)h->row_lo, hi = (int)h->row_hi;
+    if (vec2) k_A_short<MODE, 2><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi);
+    else k_A_short<MODE, 1><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi);
+    KLAUNCH(h);
+    if (h->n_chunks > 0) {
+        if (vec2) k_A_long<MODE, 2><<<(int)h->n_chunks, TPB, 0, st>>>(h->chunk_mat, h->long_mat, h->long_chunk_ptr, h->matptr, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, h->chunk_part, lo, hi);
+        else k_A_long<MODE, 1><<<(int)h->n_chunks, TPB, 0, st>>>(h->chunk_mat, h->long_mat, h->long_chunk_ptr, h->matptr, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, h->chunk_part, lo, hi);
+        KLAUNCH(h);
+        k_A_long_combine<MODE><<<(int)h->n_long, TPB, 0, st>>>(h->long_mat, h->long_chunk_ptr, h->mat_gid, h->chunk_part, out1, out2);
+        KLAUNCH(h);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+
+}  // namespace
+
+// X'B for one low-rank matrix into dst (r*s doubles, device), k-major: dst[k*r+i]
+int32_t lr_project(sdplrp_handle *h, const LowRank &L, const double *X, double *dst) {
+    const int r = h->r;
+    if (r > TPB) return fail(h, SDPLRP_ERR_ARG, "low-rank path supports r <= 256");
+    for (i64 k0 = 0; k0 < L.s; k0 += kLrS) {
+        const int sc = (int)std::min<i64>(kLrS, L.s - k0);
+        i64 blocks = std::min<i64>(kRedBlocks, std::max<i64>(1, h->n / (TPB / r)));
+        blocks = std::max<i64>(1, std::min<i64>(blocks, kPartialsLen / ((i64)r * sc)));
+        k_lr_proj<<<(int)blocks, TPB, 0, h->stream>>>(h->n, r, sc, X, L.dB + k0 * h->n, h->n, h->partials, h->ticket, dst + k0 * r);
+        KLAUNCH(h);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+
+int32_t lr_scratch(sdplrp_handle *h) {
+    i64 smax = 1;
+    for (const LowRank &L : h->lr) smax = std::max(smax, L.s);
+    i64 need = 2 * smax * (i64)h->r;
+    if (h->lr_tmp_len < need) {
+        SDP_CHECK(dev_alloc(h, &h->lr_tmp, need));
+        h->lr_tmp_len = need;
+    }
+    return SDPLRP_OK;
+}
+
+// mode 0: A(UU'), mode 1: A((UV'+VU')/2), mode 2: line search (U=R, V=D)
+static int32_t run_lowrank(sdplrp_handle *h, int mode, const double *U, const double *V, double *out1, double *out2) {
+    if (h->lr.empty()) return SDPLRP_OK;
+    SDP_CHECK(lr_scratch(h));
+    const int r = h->r;
+    for (const LowRank &L : h->lr) {
+        double *ub = h->lr_tmp, *vb = h->lr_tmp + L.s * r;
+        SDP_CHECK(lr_project(h, L, U, ub));
+        if (mode != 0) SDP_CHECK(lr_project(h, L, V, vb));
+        if (mode == 0) {
+            k_lr_trace<<<1, 128, 0, h->stream>>>(r, (int)L.s, ub, ub, L.dD, 1.0, out1, (int)L.gid);
+        } else if (mode == 1) {
+            k_lr_trace<<<1, 128, 0, h->stream>>>(r, (int)L.s, ub, vb, L.dD, 1.0, out1, (int)L.gid);
+        } else {
+            k_lr_trace<<<1, 128, 0, h->stream>>>(r, (int)L.s, ub, vb, L.dD, 2.0, out1, (int)L.gid);
+            KLAUNCH(h);
+            k_lr_trace<<<1, 128, 0, h->stream>>>(r, (int)L.s, vb, vb, L.dD, 1.0, out2, (int)L.gid);
+        }
+        KLAUNCH(h);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+
+int32_t aop_uu(sdplrp_handle *h, const double *U, double *out) {
+    CUDA_TRY(h, cudaMemsetAsync(out, 0, (size_t)(h->m + 1) * sizeof(double), h->stream));
+    SDP_CHECK(run_sparse<0>(h, U, nullptr, out, nullptr));
+    return run_lowrank(h, 0, U, nullptr, out, nullptr);
+}
+
+int32_t aop_uv(sdplrp_handle *h, const double *U, const double *V, double *out) {
+    CUDA_TRY(h, cudaMemsetAsync(out, 0, (size_t)(h->m + 1) * sizeof(double), h->stream));
+    SDP_CHECK(run_sparse<1>(h, U, V, out, nullptr));
+    return run_lowrank(h, 1, U, V, out, nullptr);
+}
+
+int32_t aop_linesearch(sdplrp_handle *h) {
+    CUDA_TRY(h, cudaMemsetAsync(h->A_RD, 0, (size_t)(h->m + 1) * sizeof(double), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->A_DD, 0, (size_t)(h->m + 1) * sizeof(double), h->stream));
+    SDP_CHECK(run_sparse<2>(h, h->R, h->D, h->A_RD, h->A_DD));
+    return run_lowrank(h, 2, h->R, h->D, h->A_RD, h->A_DD);
+}

@@ -1,0 +1,574 @@
+// api.cu -- the extern "C" entry points of libsdplrp_b200.so (see
+// include/sdplrp_b200.h for the contract and the reference file:line each one
+// replaces).  There is no CPU fallback: without a CUDA device sdplrp_create
+// fails with SDPLRP_ERR_NO_DEVICE.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include "common.cuh"
+
+static const char *kNoHandle = "null handle";
+
+#define REQUIRE_H(h) \
+    if (!(h)) return SDPLRP_ERR_ARG
+#define REQUIRE_PRE(h)                                                                   \
+    if (!(h)->preprocessed) return fail(h, SDPLRP_ERR_STATE, "call sdplrp_preprocess first")
+#define REQUIRE_RANK(h)                                                                  \
+    if ((h)->r <= 0) return fail(h, SDPLRP_ERR_STATE, "call sdplrp_set_rank first")
+
+int32_t fetch_scalars(sdplrp_handle *h, int first, int count) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->hscal + first, h->dscal + first, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SDPLRP_OK;
+}
+
+static double *mat_ptr(sdplrp_handle *h, int id) {
+    switch (id) {
+    case SDPLRP_MAT_R: return h->R;
+    case SDPLRP_MAT_G: return h->G;
+    case SDPLRP_MAT_D: return h->D;
+    case SDPLRP_MAT_W0: return h->W0;
+    case SDPLRP_MAT_W1: return h->W1;
+    default: break;
+    }
+    if (id >= SDPLRP_MAT_S0 && id < SDPLRP_MAT_S0 + h->hist) return h->Sh[id - SDPLRP_MAT_S0];
+    if (id >= SDPLRP_MAT_Y0 && id < SDPLRP_MAT_Y0 + h->hist) return h->Yh[id - SDPLRP_MAT_Y0];
+    return nullptr;
+}
+
+static double *vec_ptr(sdplrp_handle *h, int id, i64 *len) {
+    switch (id) {
+    case SDPLRP_VEC_LAMBDA: *len = h->m; return h->lambda;
+    case SDPLRP_VEC_LAMBDA_UB: *len = h->m; return h->lambda_ub;
+    case SDPLRP_VEC_B: *len = h->m; return h->b;
+    case SDPLRP_VEC_PVIO_RAW: *len = h->m + 1; return h->pvio_raw;
+    case SDPLRP_VEC_Y: *len = h->m + 1; return h->y;
+    case SDPLRP_VEC_PVIO_LB: *len = h->m; return h->pvio_lb;
+    case SDPLRP_VEC_A_RD: *len = h->m + 1; return h->A_RD;
+    case SDPLRP_VEC_A_DD: *len = h->m + 1; return h->A_DD;
+    case SDPLRP_VEC_S_NZVAL: *len = h->nnzF; return h->S;
+    default: return nullptr;
+    }
+}
+
+__global__ void k_fill(i64 len, double v, double *__restrict__ x) {
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < len; i += (i64)gridDim.x * blockDim.x) x[i] = v;
+}
+__global__ void k_bounds(i64 m, const unsigned char *__restrict__ ineq, double *__restrict__ ub, double *__restrict__ lb) {
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
+        const bool q = ineq && ineq[i];
+        ub[i] = q ? 0.0 : INFINITY;   // src/structs.jl:228
+        lb[i] = q ? 0.0 : -INFINITY;  // src/structs.jl:249
+    }
+}
+
+extern "C" {
+
+int32_t sdplrp_version(void) { return 100; }
+
+const char *sdplrp_error_string(int32_t code) {
+    switch (code) {
+    case SDPLRP_OK: return "ok";
+    case SDPLRP_ERR_CUDA: return "CUDA runtime error";
+    case SDPLRP_ERR_ARG: return "bad argument";
+    case SDPLRP_ERR_STATE: return "call order violated";
+    case SDPLRP_ERR_ASYMMETRIC: return "constraint matrix not stored symmetric";
+    case SDPLRP_ERR_NCCL: return "NCCL error";
+    case SDPLRP_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+    case SDPLRP_ERR_LINESEARCH: return "line search slope is positive";
+    default: return "unknown error";
+    }
+}
+
+const char *sdplrp_last_error(sdplrp_handle *h) { return h ? h->err.c_str() : kNoHandle; }
+
+int32_t sdplrp_create(int32_t device, int32_t rank, int32_t world, const void *nccl_id, sdplrp_handle **out) {
+    if (!out) return SDPLRP_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SDPLRP_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev || world < 1 || rank < 0 || rank >= world) return SDPLRP_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return SDPLRP_ERR_CUDA;
+    sdplrp_handle *h = new sdplrp_handle();
+    h->device = device; h->rank = rank; h->world = world;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SDPLRP_ERR_CUDA; }
+    bool ok = cudaMalloc((void **)&h->dscal, SC_COUNT * sizeof(double)) == cudaSuccess &&
+              cudaMallocHost((void **)&h->hscal, SC_COUNT * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void **)&h->partials, (size_t)kPartialsLen * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void **)&h->ticket, 4 * sizeof(unsigned)) == cudaSuccess;
+    if (ok) ok = cudaMemset(h->dscal, 0, SC_COUNT * sizeof(double)) == cudaSuccess && cudaMemset(h->ticket, 0, 4 * sizeof(unsigned)) == cudaSuccess;
+    if (!ok) { sdplrp_destroy(h); return SDPLRP_ERR_CUDA; }
+    memset(h->hscal, 0, SC_COUNT * sizeof(double));
+    if (world > 1) {
+        int32_t rc = comm_init(h, nccl_id);
+        if (rc != SDPLRP_OK) { sdplrp_destroy(h); return rc; }
+    }
+    *out = h;
+    return SDPLRP_OK;
+}
+
+static void free_state(sdplrp_handle *h) {
+    dev_free(&h->R); dev_free(&h->G); dev_free(&h->D); dev_free(&h->W0); dev_free(&h->W1);
+    for (int j = 0; j < kMaxHist; j++) { dev_free(&h->Sh[j]); dev_free(&h->Yh[j]); }
+    dev_free(&h->lr_tmp); h->lr_tmp_len = 0;
+    h->r = 0; h->hist = 0;
+}
+
+static void free_problem(sdplrp_handle *h) {
+    pre_free(h);
+    for (LowRank &L : h->lr) { dev_free(&L.dB); dev_free(&L.dD); }
+    h->lr.clear();
+    dev_free(&h->b); dev_free(&h->lambda); dev_free(&h->lambda_ub); dev_free(&h->pvio_lb);
+    dev_free(&h->y); dev_free(&h->pvio_raw); dev_free(&h->A_RD); dev_free(&h->A_DD); dev_free(&h->A_out);
+    dev_free(&h->lz_v); dev_free(&h->lz_w); dev_free(&h->lz_vp); dev_free(&h->lz_ab); dev_free(&h->lz_basis);
+    h->lz_ab_len = 0; h->lz_basis_len = 0;
+}
+
+int32_t sdplrp_destroy(sdplrp_handle *h) {
+    if (!h) return SDPLRP_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    comm_destroy(h);
+    free_state(h);
+    free_problem(h);
+    dev_free(&h->dscal); dev_free(&h->partials); dev_free(&h->ticket);
+    if (h->hscal) cudaFreeHost(h->hscal);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_synchronize(sdplrp_handle *h) {
+    REQUIRE_H(h);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SDPLRP_OK;
+}
+
+void *sdplrp_stream(sdplrp_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+int32_t sdplrp_preprocess(sdplrp_handle *h, int64_t n, int64_t m, int64_t nA, const int64_t *mat_off, const int64_t *I,
+                          const int64_t *J, const double *V, const int64_t *gids) {
+    REQUIRE_H(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    free_state(h);
+    free_problem(h);
+    if (nA > 0 && (!mat_off || !gids)) return fail(h, SDPLRP_ERR_ARG, "preprocess: null arrays");
+    int32_t rc = pre_build(h, n, m, nA, mat_off, I, J, V, gids);
+    if (rc != SDPLRP_OK && rc != SDPLRP_ERR_ASYMMETRIC) return rc;
+    // vectors of SolverVars / SDPData
+    SDP_CHECK(dev_alloc(h, &h->b, m)); SDP_CHECK(dev_alloc(h, &h->lambda, m)); SDP_CHECK(dev_alloc(h, &h->lambda_ub, m));
+    SDP_CHECK(dev_alloc(h, &h->pvio_lb, m)); SDP_CHECK(dev_alloc(h, &h->y, m + 1)); SDP_CHECK(dev_alloc(h, &h->pvio_raw, m + 1));
+    SDP_CHECK(dev_alloc(h, &h->A_RD, m + 1)); SDP_CHECK(dev_alloc(h, &h->A_DD, m + 1)); SDP_CHECK(dev_alloc(h, &h->A_out, m + 1));
+    cudaStream_t st = h->stream;
+    CUDA_TRY(h, cudaMemsetAsync(h->b, 0, (size_t)std::max<i64>(m, 1) * 8, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->lambda, 0, (size_t)std::max<i64>(m, 1) * 8, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->y, 0, (size_t)(m + 1) * 8, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->pvio_raw, 0, (size_t)(m + 1) * 8, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->A_RD, 0, (size_t)(m + 1) * 8, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->A_DD, 0, (size_t)(m + 1) * 8, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->A_out, 0, (size_t)(m + 1) * 8, st));
+    k_bounds<<<grid_for(m, 256, kRedBlocks), 256, 0, st>>>(m, nullptr, h->lambda_ub, h->pvio_lb);
+    KLAUNCH(h);
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    h->y_obj = 0.0;
+    SDP_CHECK(comm_partition(h));
+    return rc;
+}
+
+int32_t sdplrp_pattern_sizes(sdplrp_handle *h, int64_t *nnzT, int64_t *nnzF, int64_t *Ec) {
+    REQUIRE_H(h);
+    REQUIRE_PRE(h);
+    if (nnzT) *nnzT = h->nnzT;
+    if (nnzF) *nnzF = h->nnzF;
+    if (Ec) *Ec = h->Ec;
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_pattern_export(sdplrp_handle *h, int64_t *triu_colptr, int64_t *triu_rowval, int64_t *matptr, int64_t *nzind,
+                              double *nzval_one, double *nzval_two, int64_t *full_colptr, int64_t *full_rowval,
+                              int64_t *mappedto_triu) {
+    REQUIRE_H(h);
+    REQUIRE_PRE(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return pre_export(h, triu_colptr, triu_rowval, matptr, nzind, nzval_one, nzval_two, full_colptr, full_rowval, mappedto_triu);
+}
+
+int32_t sdplrp_add_symlowrank(sdplrp_handle *h, int64_t global_id, int64_t s, const double *B, const double *D) {
+    REQUIRE_H(h);
+    REQUIRE_PRE(h);
+    if (global_id < 1 || global_id > h->m + 1 || s < 1 || !B || !D) return fail(h, SDPLRP_ERR_ARG, "add_symlowrank: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    LowRank L;
+    L.gid = global_id - 1; L.s = s; L.dB = nullptr; L.dD = nullptr;
+    SDP_CHECK(dev_alloc(h, &L.dB, h->n * s));
+    SDP_CHECK(dev_alloc(h, &L.dD, s));
+    CUDA_TRY(h, cudaMemcpy(L.dB, B, (size_t)(h->n * s) * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(L.dD, D, (size_t)s * 8, cudaMemcpyHostToDevice));
+    h->lr.push_back(L);
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_set_problem(sdplrp_handle *h, const double *b, const uint8_t *is_ineq) {
+    REQUIRE_H(h);
+    REQUIRE_PRE(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const i64 m = h->m;
+    if (m > 0 && !b) return fail(h, SDPLRP_ERR_ARG, "set_problem: null b");
+    if (m > 0) CUDA_TRY(h, cudaMemcpy(h->b, b, (size_t)m * 8, cudaMemcpyHostToDevice));
+    unsigned char *dq = nullptr;
+    if (is_ineq && m > 0) {
+        CUDA_TRY(h, cudaMalloc((void **)&dq, (size_t)m));
+        CUDA_TRY(h, cudaMemcpy(dq, is_ineq, (size_t)m, cudaMemcpyHostToDevice));
+    }
+    k_bounds<<<grid_for(m, 256, kRedBlocks), 256, 0, h->stream>>>(m, dq, h->lambda_ub, h->pvio_lb);
+    KLAUNCH(h);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (dq) cudaFree(dq);
+    CUDA_TRY(h, e);
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_set_rank(sdplrp_handle *h, int32_t r, int32_t numlbfgsvecs) {
+    REQUIRE_H(h);
+    REQUIRE_PRE(h);
+    if (r < 1 || numlbfgsvecs < 0 || numlbfgsvecs > kMaxHist) return fail(h, SDPLRP_ERR_ARG, "set_rank: bad rank / history length");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    free_state(h);
+    const i64 N = h->n * (i64)r;
+    SDP_CHECK(dev_alloc(h, &h->R, N)); SDP_CHECK(dev_alloc(h, &h->G, N)); SDP_CHECK(dev_alloc(h, &h->D, N));
+    for (int j = 0; j < numlbfgsvecs; j++) { SDP_CHECK(dev_alloc(h, &h->Sh[j], N)); SDP_CHECK(dev_alloc(h, &h->Yh[j], N)); }
+    h->r = r; h->hist = numlbfgsvecs; h->latest = numlbfgsvecs;  // lbfgs_init: latest = h (src/lbfgs.jl:45)
+    CUDA_TRY(h, cudaMemsetAsync(h->R, 0, (size_t)N * 8, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->G, 0, (size_t)N * 8, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->D, 0, (size_t)N * 8, h->stream));
+    SDP_CHECK(lb_clear(h));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_set_sigma(sdplrp_handle *h, double sigma) { REQUIRE_H(h); h->sigma = sigma; return SDPLRP_OK; }
+int32_t sdplrp_get_sigma(sdplrp_handle *h, double *sigma) { REQUIRE_H(h); *sigma = h->sigma; return SDPLRP_OK; }
+int32_t sdplrp_get_obj(sdplrp_handle *h, double *obj) {
+    REQUIRE_H(h);
+    SDP_CHECK(fetch_scalars(h, SC_OBJ, 1));
+    *obj = h->hscal[SC_OBJ];
+    return SDPLRP_OK;
+}
+
+static int32_t lazy_scratch(sdplrp_handle *h, int id) {
+    const i64 N = h->n * (i64)h->r;
+    if (id == SDPLRP_MAT_W0 && !h->W0) { SDP_CHECK(dev_alloc(h, &h->W0, N)); CUDA_TRY(h, cudaMemset(h->W0, 0, (size_t)N * 8)); }
+    if (id == SDPLRP_MAT_W1 && !h->W1) { SDP_CHECK(dev_alloc(h, &h->W1, N)); CUDA_TRY(h, cudaMemset(h->W1, 0, (size_t)N * 8)); }
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_upload_mat(sdplrp_handle *h, int32_t id, const double *src) {
+    REQUIRE_H(h);
+    REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(lazy_scratch(h, id));
+    double *p = mat_ptr(h, id);
+    if (!p || !src) return fail(h, SDPLRP_ERR_ARG, "upload_mat: bad id");
+    CUDA_TRY(h, cudaMemcpyAsync(p, src, (size_t)h->n * h->r * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    comm_mark_full(h, id);
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_download_mat(sdplrp_handle *h, int32_t id, double *dst) {
+    REQUIRE_H(h);
+    REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(lazy_scratch(h, id));
+    double *p = mat_ptr(h, id);
+    if (!p || !dst) return fail(h, SDPLRP_ERR_ARG, "download_mat: bad id");
+    SDP_CHECK(comm_gather_rows(h, p, id));
+    CUDA_TRY(h, cudaMemcpyAsync(dst, p, (size_t)h->n * h->r * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_upload_vec(sdplrp_handle *h, int32_t id, const double *src, int64_t len) {
+    REQUIRE_H(h);
+    REQUIRE_PRE(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    i64 want = 0;
+    double *p = vec_ptr(h, id, &want);
+    if (!p || !src || len != want) return fail(h, SDPLRP_ERR_ARG, "upload_vec: bad id or length");
+    if (len > 0) CUDA_TRY(h, cudaMemcpyAsync(p, src, (size_t)len * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (id == SDPLRP_VEC_Y) h->y_obj = src[h->m];
+    if (id == SDPLRP_VEC_S_NZVAL) h->S_static_valid = false;
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_download_vec(sdplrp_handle *h, int32_t id, double *dst, int64_t len) {
+    REQUIRE_H(h);
+    REQUIRE_PRE(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (id == SDPLRP_VEC_TRIUS_NZVAL) {
+        if (len != h->nnzT || !dst) return fail(h, SDPLRP_ERR_ARG, "download_vec: bad length");
+        double *tmp = nullptr;
+        SDP_CHECK(dev_alloc(h, &tmp, h->nnzT));
+        int32_t rc = grad_triuS(h, tmp);
+        if (rc == SDPLRP_OK && len > 0) {
+            cudaError_t e = cudaMemcpyAsync(dst, tmp, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = SDPLRP_ERR_CUDA; }
+        }
+        cudaFree(tmp);
+        return rc;
+    }
+    i64 want = 0;
+    double *p = vec_ptr(h, id, &want);
+    if (!p || !dst || len != want) return fail(h, SDPLRP_ERR_ARG, "download_vec: bad id or length");
+    if (len > 0) CUDA_TRY(h, cudaMemcpyAsync(dst, p, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SDPLRP_OK;
+}
+
+// ---- seam-level operators ----------------------------------------------------
+static int32_t copy_out(sdplrp_handle *h, const double *dev, double *host, i64 len) {
+    if (!host) return SDPLRP_OK;
+    CUDA_TRY(h, cudaMemcpyAsync(host, dev, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_A_uu(sdplrp_handle *h, int32_t U_id, double *out) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(lazy_scratch(h, U_id));
+    const double *U = mat_ptr(h, U_id);
+    if (!U) return fail(h, SDPLRP_ERR_ARG, "A_uu: bad matrix id");
+    SDP_CHECK(comm_require_full(h, U_id));
+    SDP_CHECK(aop_uu(h, U, h->A_out));
+    SDP_CHECK(comm_reduce_mvec(h, h->A_out, nullptr));
+    return copy_out(h, h->A_out, out, h->m + 1);
+}
+
+int32_t sdplrp_A_uv(sdplrp_handle *h, int32_t U_id, int32_t V_id, double *out) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(lazy_scratch(h, U_id)); SDP_CHECK(lazy_scratch(h, V_id));
+    const double *U = mat_ptr(h, U_id), *V = mat_ptr(h, V_id);
+    if (!U || !V) return fail(h, SDPLRP_ERR_ARG, "A_uv: bad matrix id");
+    SDP_CHECK(comm_require_full(h, U_id)); SDP_CHECK(comm_require_full(h, V_id));
+    SDP_CHECK(aop_uv(h, U, V, h->A_out));
+    SDP_CHECK(comm_reduce_mvec(h, h->A_out, nullptr));
+    return copy_out(h, h->A_out, out, h->m + 1);
+}
+
+int32_t sdplrp_At_preprocess(sdplrp_handle *h, const double *y) {
+    REQUIRE_H(h); REQUIRE_PRE(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (y) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->y, y, (size_t)(h->m + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        h->y_obj = y[h->m];
+    }
+    return grad_assemble_S(h);
+}
+
+int32_t sdplrp_At_left(sdplrp_handle *h, int32_t X_id, int32_t Y_id) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(lazy_scratch(h, X_id)); SDP_CHECK(lazy_scratch(h, Y_id));
+    const double *X = mat_ptr(h, X_id);
+    double *Y = mat_ptr(h, Y_id);
+    if (!X || !Y || X == Y) return fail(h, SDPLRP_ERR_ARG, "At_left: bad matrix ids");
+    SDP_CHECK(comm_require_full(h, X_id));
+    SDP_CHECK(grad_spmm(h, X, Y, 1.0, false));
+    comm_mark_partial(h, Y_id);
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_At_right(sdplrp_handle *h, const double *x, double *y, int64_t ncols) {
+    REQUIRE_H(h); REQUIRE_PRE(h);
+    if (!x || !y || ncols < 1) return fail(h, SDPLRP_ERR_ARG, "At_right: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    double *dx = nullptr, *dy = nullptr;
+    const i64 len = h->n * ncols;
+    SDP_CHECK(dev_alloc(h, &dx, len));
+    int32_t rc = dev_alloc(h, &dy, len);
+    if (rc == SDPLRP_OK) {
+        cudaError_t e = cudaMemcpyAsync(dx, x, (size_t)len * 8, cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = SDPLRP_ERR_CUDA; }
+    }
+    if (rc == SDPLRP_OK) rc = grad_spmv(h, dx, dy, ncols);
+    if (rc == SDPLRP_OK) rc = copy_out(h, dy, y, len);
+    cudaFree(dx);
+    if (dy) cudaFree(dy);
+    return rc;
+}
+
+// ---- fused iteration -----------------------------------------------------------
+static int32_t do_f(sdplrp_handle *h) {
+    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
+    SDP_CHECK(aop_uu(h, h->R, h->pvio_raw));
+    SDP_CHECK(comm_reduce_mvec(h, h->pvio_raw, nullptr));
+    return vec_f_finish(h);
+}
+
+static int32_t do_g(sdplrp_handle *h) {
+    SDP_CHECK(grad_form_y(h));
+    SDP_CHECK(grad_assemble_S(h));
+    SDP_CHECK(grad_spmm(h, h->R, h->G, 2.0, true));  // G = 2 * R * S  (src/coreop.jl:312-315)
+    comm_mark_partial(h, SDPLRP_MAT_G);
+    SDP_CHECK(lb_norm2(h, h->G, SC_GNORM2));
+    SDP_CHECK(comm_reduce_scalars(h, SC_GNORM2, 1));
+    return vec_pnorm2(h);
+}
+
+int32_t sdplrp_f(sdplrp_handle *h, double *L, double *obj) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(do_f(h));
+    SDP_CHECK(fetch_scalars(h, SC_OBJ, 2));
+    if (obj) *obj = h->hscal[SC_OBJ];
+    if (L) *L = h->hscal[SC_LVAL];
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_g(sdplrp_handle *h, double *gnorm2, double *pnorm2) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(do_g(h));
+    SDP_CHECK(fetch_scalars(h, SC_GNORM2, 2));
+    if (gnorm2) *gnorm2 = h->hscal[SC_GNORM2];
+    if (pnorm2) *pnorm2 = h->hscal[SC_PNORM2];
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_fg(sdplrp_handle *h, double out[4]) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(do_f(h));
+    SDP_CHECK(do_g(h));
+    SDP_CHECK(fetch_scalars(h, SC_GNORM2, 4));
+    out[0] = h->hscal[SC_LVAL]; out[1] = h->hscal[SC_OBJ]; out[2] = h->hscal[SC_GNORM2]; out[3] = h->hscal[SC_PNORM2];
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_lbfgs_dir(sdplrp_handle *h, double *descent) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(lb_dir(h));
+    comm_mark_partial(h, SDPLRP_MAT_D);
+    SDP_CHECK(fetch_scalars(h, SC_DESCENT, 1));
+    if (descent) *descent = h->hscal[SC_DESCENT];
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_use_gradient_direction(sdplrp_handle *h) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(lb_neg_copy(h));
+    comm_mark_partial(h, SDPLRP_MAT_D);
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_linesearch_coeffs(sdplrp_handle *h, double bq[5]) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_D));
+    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
+    SDP_CHECK(aop_linesearch(h));
+    SDP_CHECK(comm_reduce_mvec(h, h->A_RD, h->A_DD));
+    SDP_CHECK(vec_biquadratic(h));
+    SDP_CHECK(fetch_scalars(h, SC_BQ, 5));
+    for (int k = 0; k < 5; k++) bq[k] = h->hscal[SC_BQ + k];
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_step(sdplrp_handle *h, double alpha, double *obj) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(vec_commit(h, alpha));
+    SDP_CHECK(comm_step_R(h, alpha));  // Rt += alpha*dirt (all rows when replicated)
+    if (obj) {
+        SDP_CHECK(fetch_scalars(h, SC_OBJ, 1));
+        *obj = h->hscal[SC_OBJ];
+    }
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_lbfgs_update(sdplrp_handle *h, double alpha) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return lb_update(h, alpha);
+}
+
+int32_t sdplrp_lbfgs_clear(sdplrp_handle *h) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return lb_clear(h);
+}
+
+int32_t sdplrp_dual_update(sdplrp_handle *h) {
+    REQUIRE_H(h); REQUIRE_PRE(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return vec_dual_update(h);
+}
+
+int32_t sdplrp_armijo_eval(sdplrp_handle *h, const double *alphas, int32_t k, double *L, double *slope) {
+    REQUIRE_H(h); REQUIRE_PRE(h);
+    if (k < 0 || (k > 0 && (!alphas || !L))) return fail(h, SDPLRP_ERR_ARG, "armijo_eval: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return vec_armijo(h, alphas, k, L, slope);
+}
+
+// ---- dual bound ------------------------------------------------------------------
+int32_t sdplrp_lanczos(sdplrp_handle *h, int64_t q, const double *v0, uint64_t seed, int32_t reorth, double *alpha, double *beta,
+                       int64_t *iters) {
+    REQUIRE_H(h); REQUIRE_PRE(h);
+    if (q < 1 || !alpha || !beta || !iters) return fail(h, SDPLRP_ERR_ARG, "lanczos: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    i64 it = 0;
+    SDP_CHECK(lz_run(h, q, v0, seed, reorth, alpha, beta, &it));
+    *iters = it;
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_tridiag_mineig(const double *d, const double *e, int64_t k, double *out) {
+    if (!d || !out || k < 1 || (k > 1 && !e)) return SDPLRP_ERR_ARG;
+    *out = tridiag_mineig_host(d, e, k);
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_dual_obj(sdplrp_handle *h, double trace_bound, int64_t iter, const double *v0, uint64_t seed, double *dual_value,
+                        double *mineig, int64_t *lanczos_steps) {
+    REQUIRE_H(h); REQUIRE_PRE(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(grad_form_y(h));
+    SDP_CHECK(grad_assemble_S(h));
+    const double it = (double)std::max<i64>(iter, 100);
+    i64 q = (i64)(2.0 * ceil(sqrt(it) * log((double)h->n)));  // src/coreop.jl:402
+    q = std::max<i64>(1, std::min<i64>(q, h->n - 1));
+    std::vector<double> a((size_t)q), b((size_t)q);
+    i64 steps = 0;
+    SDP_CHECK(lz_run(h, q, v0, seed, 0, a.data(), b.data(), &steps));
+    for (i64 i = 0; i < steps; i++) a[(size_t)i] += 1.0;  // shift by I (src/coreop.jl:503)
+    const double lam = (steps == 1 ? a[0] : tridiag_mineig_host(a.data(), b.data(), steps)) - 1.0;
+    double yb = 0.0;
+    SDP_CHECK(vec_dual_dot(h, &yb));
+    if (dual_value) *dual_value = yb + trace_bound * std::min(lam, 0.0);  // src/coreop.jl:412
+    if (mineig) *mineig = lam;
+    if (lanczos_steps) *lanczos_steps = steps;
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_launch_count(sdplrp_handle *h, int64_t *count) {
+    REQUIRE_H(h);
+    if (count) *count = h->launches;
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_row_range(sdplrp_handle *h, int64_t *lo, int64_t *hi) {
+    REQUIRE_H(h);
+    if (lo) *lo = h->row_lo;
+    if (hi) *hi = h->row_hi;
+    return SDPLRP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+// comm.cu -- multi-GPU plumbing: one handle per rank, NCCL over NVLink.
+//
+// The reference has no distributed path at all; this is the
+// B200-side design: rows of R/G/D/history and of the aggregated pattern are
+// 1-D partitioned in contiguous blocks balanced by nonzeros.  R is kept
+// replicated and advanced locally (R += alpha*D on every row), so the only
+// bulk exchange per inner iteration is one all-gather of the direction D;
+// dot products and the constraint vector are all-reduced.
+//
+// world == 1 never touches NCCL: every function below is a no-op then.
+#include <nccl.h>
+#include <string.h>
+#include <algorithm>
+#include "common.cuh"
+
+#define NCCL_TRY(h, call)                                                        \
+    do {                                                                         \
+        ncclResult_t r__ = (call);                                               \
+        if (r__ != ncclSuccess) {                                                \
+            (h)->err = std::string(#call) + ": " + ncclGetErrorString(r__);      \
+            return SDPLRP_ERR_NCCL;                                              \
+        }                                                                        \
+    } while (0)
+
+extern "C" int32_t sdplrp_nccl_unique_id(void *out128) {
+    if (!out128) return SDPLRP_ERR_ARG;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return SDPLRP_ERR_NCCL;
+    memcpy(out128, &id, sizeof(id));
+    return SDPLRP_OK;
+}
+
+int32_t comm_init(sdplrp_handle *h, const void *nccl_id) {
+    if (h->world <= 1) return SDPLRP_OK;
+    if (!nccl_id) return fail(h, SDPLRP_ERR_ARG, "create: world > 1 needs the NCCL unique id");
+    ncclUniqueId id;
+    memcpy(&id, nccl_id, sizeof(id));
+    ncclComm_t comm;
+    NCCL_TRY(h, ncclCommInitRank(&comm, h->world, id, h->rank));
+    h->nccl = (void *)comm;
+    return SDPLRP_OK;
+}
+
+void comm_destroy(sdplrp_handle *h) {
+    if (h->nccl) {
+        ncclCommDestroy((ncclComm_t)h->nccl);
+        h->nccl = nullptr;
+    }
+}
+
+// contiguous row blocks with ~nnzF/world nonzeros each (prefix sum over the
+// full pattern's row pointer); identical on every rank.
+int32_t comm_partition(sdplrp_handle *h) {
+    const i64 n = h->n;
+    h->row_starts.assign((size_t)h->world + 1, 0);
+    h->row_starts[(size_t)h->world] = n;
+    for (int id = 0; id < 8; id++) h->mat_full[id] = true;
+    if (h->world <= 1) {
+        h->row_lo = 0; h->row_hi = n;
+        return SDPLRP_OK;
+    }
+    std::vector<int> ptr((size_t)n + 1);
+    CUDA_TRY(h, cudaMemcpy(ptr.data(), h->full_ptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    // weight of a row: its nonzeros plus one (dense BLAS-1 work per row)
+    const double total = (double)ptr[(size_t)n] + (double)n;
+    i64 row = 0;
+    for (int p = 1; p < h->world; p++) {
+        const double target = total * p / h->world;
+        while (row < n && (double)ptr[(size_t)row] + (double)row < target) row++;
+        h->row_starts[(size_t)p] = row;
+    }
+    h->row_lo = h->row_starts[(size_t)h->rank];
+    h->row_hi = h->row_starts[(size_t)h->rank + 1];
+    return SDPLRP_OK;
+}
+
+static int full_slot(int mat_id) {
+    switch (mat_id) {
+    case SDPLRP_MAT_R: return 0;
+    case SDPLRP_MAT_G: return 1;
+    case SDPLRP_MAT_D: return 2;
+    case SDPLRP_MAT_W0: return 3;
+    case SDPLRP_MAT_W1: return 4;
+    default: return -1;
+    }
+}
+
+void comm_mark_partial(sdplrp_handle *h, int mat_id) {
+    if (h->world <= 1) return;
+    const int s = full_slot(mat_id);
+    if (s >= 0) h->mat_full[s] = false;
+}
+void comm_mark_full(sdplrp_handle *h, int mat_id) {
+    const int s = full_slot(mat_id);
+    if (s >= 0) h->mat_full[s] = true;
+}
+
+// all-gather (variable block sizes) of the owned row blocks of a dense n x r matrix
+static int32_t allgather_rows(sdplrp_handle *h, double *p) {
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    NCCL_TRY(h, ncclGroupStart());
+    for (int q = 0; q < h->world; q++) {
+        const i64 off = h->row_starts[(size_t)q] * h->r;
+        const i64 len = (h->row_starts[(size_t)q + 1] - h->row_starts[(size_t)q]) * h->r;
+        if (len > 0) NCCL_TRY(h, ncclBroadcast(p + off, p + off, (size_t)len, ncclDouble, q, comm, h->stream));
+    }
+    NCCL_TRY(h, ncclGroupEnd());
+    return SDPLRP_OK;
+}
+
+int32_t comm_require_full(sdplrp_handle *h, int mat_id) {
+    if (h->world <= 1) return SDPLRP_OK;
+    const int s = full_slot(mat_id);
+    if (s < 0) return fail(h, SDPLRP_ERR_ARG, "multi-GPU: only R/G/D/W0/W1 can be operator inputs");
+    if (h->mat_full[s]) return SDPLRP_OK;
+    double *p = nullptr;
+    switch (s) {
+    case 0: p = h->R; break;
+    case 1: p = h->G; break;
+    case 2: p = h->D; break;
+    case 3: p = h->W0; break;
+    default: p = h->W1; break;
+    }
+    SDP_CHECK(allgather_rows(h, p));
+    h->mat_full[s] = true;
+    return SDPLRP_OK;
+}
+
+// used by download_mat: history slots are only ever valid on their owners
+int32_t comm_gather_rows(sdplrp_handle *h, double *p, int mat_id) {
+    if (h->world <= 1) return SDPLRP_OK;
+    const int s = full_slot(mat_id);
+    if (s >= 0) return comm_require_full(h, mat_id);
+    return allgather_rows(h, p);
+}
+
+// sum the per-rank partial constraint vectors (length m+1)
+int32_t comm_reduce_mvec(sdplrp_handle *h, double *v1, double *v2) {
+    if (h->world <= 1) return SDPLRP_OK;
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    NCCL_TRY(h, ncclGroupStart());
+    NCCL_TRY(h, ncclAllReduce(v1, v1, (size_t)(h->m + 1), ncclDouble, ncclSum, comm, h->stream));
+    if (v2) NCCL_TRY(h, ncclAllReduce(v2, v2, (size_t)(h->m + 1), ncclDouble, ncclSum, comm, h->stream));
+    NCCL_TRY(h, ncclGroupEnd());
+    return SDPLRP_OK;
+}
+
+int32_t comm_reduce_scalars(sdplrp_handle *h, int slot, int count) {
+    if (h->world <= 1) return SDPLRP_OK;
+    NCCL_TRY(h, ncclAllReduce(h->dscal + slot, h->dscal + slot, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)h->nccl, h->stream));
+    return SDPLRP_OK;
+}
+
+int32_t comm_reduce_ptr(sdplrp_handle *h, double *p, int count) {
+    if (h->world <= 1) return SDPLRP_OK;
+    NCCL_TRY(h, ncclAllReduce(p, p, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)h->nccl, h->stream));
+    return SDPLRP_OK;
+}
+
+// Rt += alpha * dirt on every row this rank keeps (all rows: R is replicated)
+int32_t comm_step_R(sdplrp_handle *h, double alpha) {
+    if (h->world <= 1) return lb_axpy(h, alpha, h->D, h->R);
+    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_D));
+    const i64 lo = h->row_lo, hi = h->row_hi;
+    h->row_lo = 0; h->row_hi = h->n;
+    const int32_t rc = lb_axpy(h, alpha, h->D, h->R);
+    h->row_lo = lo; h->row_hi = hi;
+    return rc;
+}

@@ -1,0 +1,285 @@
+// common.cuh -- handle, error plumbing and device-side reduction helpers shared
+// by every translation unit of libsdplrp_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/sdplrp_b200.h"
+
+typedef long long i64;
+
+constexpr int kNumSM = 148;          // B200: 2 dies x 74 SMs
+constexpr int kMaxHist = 32;         // numlbfgsvecs upper bound (ids S0..S0+31)
+constexpr int kRedBlocks = 4 * kNumSM;  // persistent grid of streaming/reduction kernels
+constexpr int kRedThreads = 256;
+constexpr int kMaxRedK = 16;         // max simultaneous sums of one reduction kernel
+constexpr long long kPartialsLen = (long long)kRedBlocks * kMaxRedK * 8;  // doubles in h->partials
+constexpr int kLongMatThreshold = 64;   // matrices with more triu entries go to the chunked path
+constexpr int kChunkEntries = 2048;     // entries per chunk (one CTA) of a long matrix
+constexpr int kLongRowThreshold = 1024; // rows of S with more nonzeros are split across a CTA
+
+struct LowRank {
+    i64 gid;     // 0-based global slot
+    i64 s;
+    double *dB;  // n x s column-major
+    double *dD;  // s
+};
+
+// device scalar slots (h->dscal)
+enum {
+    SC_DOT = 0,       // running dot of the L-BFGS recursion
+    SC_DESCENT = 1,
+    SC_GNORM2 = 2,
+    SC_PNORM2 = 3,
+    SC_OBJ = 4,
+    SC_LVAL = 5,
+    SC_BQ = 8,        // 8 partial sums -> 5 quartic coefficients
+    SC_RHO = 32,      // rho_j, j < kMaxHist
+    SC_A = 64,        // a_j (alpha of the first loop)
+    SC_LANCZOS = 96,  // alpha_i, beta_i, stop flag scratch
+    SC_COUNT = 128
+};
+
+struct sdplrp_handle {
+    int device = 0, rank = 0, world = 1;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    i64 launches = 0;
+    void *nccl = nullptr;  // ncclComm_t when world > 1
+
+    // problem sizes
+    i64 n = 0, m = 0, nA = 0, nnzT = 0, nnzF = 0, Ec = 0;
+    i64 row_lo = 0, row_hi = 0;  // rows of R/G/D owned by this rank
+    std::vector<i64> row_starts; // world+1 block boundaries (identical on every rank)
+    bool mat_full[8] = {true, true, true, true, true, true, true, true};  // R,G,D,W0,W1: all rows valid here?
+    bool preprocessed = false;
+
+    // aggregated patterns (0-based int32 on device)
+    int *triu_colptr = nullptr, *triu_rowval = nullptr;  // n+1, nnzT   (CSC of triu == CSR of tril)
+    int *full_ptr = nullptr, *full_idx = nullptr;        // n+1, nnzF   (symmetric: CSC == CSR)
+    int *mapped = nullptr;                               // nnzF -> triu slot
+    double *S = nullptr;                                 // nnzF  sparse_S.nzval
+    // per-entry lists in reference order (E_c)
+    int *matptr = nullptr;     // nA+1
+    int *mat_gid = nullptr;    // nA   0-based global slot of each sparse matrix
+    int *ent_slot = nullptr;   // Ec   nzind (0-based triu slot)
+    int *ent_row = nullptr, *ent_col = nullptr;  // Ec   coordinates of that slot (row <= col)
+    double *ent_one = nullptr, *ent_two = nullptr;  // Ec
+    // chunked ("long") matrices for the A passes
+    i64 n_long = 0, n_chunks = 0;
+    int *long_mat = nullptr;       // n_long: matrix index
+    int *long_chunk_ptr = nullptr; // n_long+1: first chunk of each long matrix
+    int *chunk_mat = nullptr;      // n_chunks: index into long_mat
+    double *chunk_part = nullptr;  // n_chunks*2 partial sums
+    // S assembly: static (objective) part + dynamic slots
+    int obj_mat = -1;              // index of the objective in the sparse list, -1 if C is not sparse
+    double *triuS_static = nullptr;  // nnzT: contribution of the objective matrix (unit y)
+    double S_static_scale = 0.0;     // y_{m+1} the static part of S currently carries
+    bool S_static_valid = false;
+    i64 n_dyn = 0;                 // triu slots with at least one non-objective contributor
+    int *dyn_slot = nullptr;       // n_dyn: triu slot
+    int *dyn_ptr = nullptr;        // n_dyn+1 into dyn_mat/dyn_val
+    int *dyn_gid = nullptr;        // contributors: global slot of y
+    double *dyn_val = nullptr;     //               nzval_one
+    int *dyn_pos_a = nullptr, *dyn_pos_b = nullptr;  // n_dyn: the (row,col) and (col,row) slots of the full pattern
+    // SpMM row classes
+    i64 n_long_rows = 0;
+    int *long_rows = nullptr;
+
+    // low-rank matrices
+    std::vector<LowRank> lr;
+    double *lr_tmp = nullptr;  // r*s_max*2 scratch (XB products)
+    i64 lr_tmp_len = 0;
+
+    // vectors
+    double *b = nullptr, *lambda = nullptr, *lambda_ub = nullptr, *pvio_lb = nullptr;
+    double *y = nullptr, *pvio_raw = nullptr, *A_RD = nullptr, *A_DD = nullptr, *A_out = nullptr;
+    double sigma = 2.0;
+    double y_obj = 0.0;  // host copy of y[m] (coefficient of the objective in S)
+
+    // dense state
+    int r = 0, hist = 0, latest = 0;  // latest is 1-based like the reference
+    double *R = nullptr, *G = nullptr, *D = nullptr, *W0 = nullptr, *W1 = nullptr;
+    double *Sh[kMaxHist] = {nullptr}, *Yh[kMaxHist] = {nullptr};
+
+    // reduction plumbing
+    double *dscal = nullptr;      // SC_COUNT device scalars
+    double *hscal = nullptr;      // pinned mirror
+    double *partials = nullptr;   // kRedBlocks * kMaxRedK (+ chunked extras)
+    unsigned *ticket = nullptr;   // last-block-done counters
+    // Lanczos workspace
+    double *lz_v = nullptr, *lz_w = nullptr, *lz_vp = nullptr, *lz_ab = nullptr;
+    i64 lz_ab_len = 0;
+    double *lz_basis = nullptr;
+    i64 lz_basis_len = 0;
+};
+
+#define CUDA_TRY(h, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                    \
+            return SDPLRP_ERR_CUDA;                                                            \
+        }                                                                                      \
+    } while (0)
+
+#define SDP_CHECK(expr)                        \
+    do {                                       \
+        int32_t rc__ = (expr);                 \
+        if (rc__ != SDPLRP_OK) return rc__;    \
+    } while (0)
+
+#define KLAUNCH(h) ((h)->launches++)
+
+static inline int32_t fail(sdplrp_handle *h, int32_t code, const std::string &msg) {
+    h->err = msg;
+    return code;
+}
+
+template <typename T>
+static inline int32_t dev_alloc(sdplrp_handle *h, T **p, i64 count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count <= 0) count = 1;
+    CUDA_TRY(h, cudaMalloc((void **)p, (size_t)count * sizeof(T)));
+    return SDPLRP_OK;
+}
+template <typename T>
+static inline void dev_free(T **p) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+}
+
+static inline int grid_for(i64 work_items, int per_block, int max_blocks = 1 << 30) {
+    i64 g = (work_items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum K per-thread values over the CTA (blockDim.x multiple of 32, <= 1024).
+// Result valid in thread 0.
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K]) {
+    __shared__ double sm[K][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = warp_sum(v[k]);
+    __syncthreads();  // protect sm across repeated calls
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) sm[k][wid] = v[k];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double t = lane < nw ? sm[k][lane] : 0.0;
+            v[k] = warp_sum(t);
+        }
+    }
+}
+
+// Deterministic grid reduction: every CTA deposits its K sums, the last CTA to
+// arrive (ticket) adds all deposits in a fixed order and calls `fin(sums)`.
+// out-of-kernel state: partials[gridDim.x*K], *ticket == 0 on entry and exit.
+template <int K, typename Fin>
+__device__ __forceinline__ void grid_sum_finalize(double (&v)[K], double *partials, unsigned *ticket, Fin fin) {
+    block_sum<K>(v);
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) partials[(size_t)blockIdx.x * K + k] = v[k];
+        __threadfence();
+        unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double s[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) s[k] = 0.0;
+        for (unsigned bI = threadIdx.x; bI < gridDim.x; bI += blockDim.x) {
+#pragma unroll
+            for (int k = 0; k < K; k++) s[k] += __ldcg(&partials[(size_t)bI * K + k]);
+        }
+        block_sum<K>(s);
+        if (threadIdx.x == 0) {
+            fin(s);
+            *ticket = 0u;
+        }
+    }
+}
+
+// 128-bit read-only loads of two doubles
+__device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+
+// host-visible kernels' launcher prototypes (one TU per subsystem) -----------
+int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off, const int64_t *I,
+                  const int64_t *J, const double *V, const int64_t *gids);
+int32_t pre_export(sdplrp_handle *h, int64_t *triu_colptr, int64_t *triu_rowval, int64_t *matptr,
+                   int64_t *nzind, double *one, double *two, int64_t *full_colptr, int64_t *full_rowval,
+                   int64_t *mapped);
+void pre_free(sdplrp_handle *h);
+
+// A passes (aop.cu)
+int32_t aop_uu(sdplrp_handle *h, const double *U, double *out_dev);                    // out = A(UU')
+int32_t aop_uv(sdplrp_handle *h, const double *U, const double *V, double *out_dev);  // out = A((UV'+VU')/2)
+int32_t aop_linesearch(sdplrp_handle *h);                                              // A_RD (x2), A_DD fused
+
+int32_t lr_project(sdplrp_handle *h, const LowRank &L, const double *X, double *dst);  // dst[k*r+i] = (X'B)[i,k]
+int32_t lr_scratch(sdplrp_handle *h);
+
+// gradient (gradient.cu)
+int32_t grad_form_y(sdplrp_handle *h);                          // copy2y_lambda_sub_pvio!
+int32_t grad_assemble_S(sdplrp_handle *h);                      // At_preprocess! from device y
+int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bool want_norm);  // Y = scale*X*S (+low rank)
+int32_t grad_spmv(sdplrp_handle *h, const double *x, double *y, i64 ncols);                     // y = S*x (+low rank), n x ncols col-major
+int32_t grad_triuS(sdplrp_handle *h, double *out_dev);          // materialise triu_sparse_S.nzval
+
+// m-vector kernels (vecops.cu)
+int32_t vec_f_finish(sdplrp_handle *h);      // raw -= b, obj, AL value -> SC_OBJ, SC_LVAL
+int32_t vec_biquadratic(sdplrp_handle *h);   // SC_BQ..SC_BQ+4
+int32_t vec_commit(sdplrp_handle *h, double alpha);  // residual recurrence + obj
+int32_t vec_pnorm2(sdplrp_handle *h);        // ||max(raw,lb)||^2 -> SC_PNORM2
+int32_t vec_dual_update(sdplrp_handle *h);
+int32_t vec_armijo(sdplrp_handle *h, const double *alphas, int k, double *L, double *slope);
+int32_t vec_dual_dot(sdplrp_handle *h, double *out);  // -y[1:m]'b
+
+// dense BLAS-1 fusions (lbfgs.cu)
+int32_t lb_dir(sdplrp_handle *h);                   // lbfgs_dir! + descent -> SC_DESCENT
+int32_t lb_update(sdplrp_handle *h, double alpha);  // lbfgs_update!
+int32_t lb_clear(sdplrp_handle *h);
+int32_t lb_axpy(sdplrp_handle *h, double alpha, const double *x, double *y);  // y += alpha x over owned rows
+int32_t lb_neg_copy(sdplrp_handle *h);              // G = -G ; D = G
+int32_t lb_norm2(sdplrp_handle *h, const double *x, int slot);
+
+// Lanczos (lanczos.cu)
+int32_t lz_run(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, int reorth, double *alpha,
+               double *beta, i64 *iters);
+double tridiag_mineig_host(const double *d, const double *e, i64 k);
+
+// multi-GPU plumbing (comm.cu); all no-ops when world == 1
+int32_t comm_init(sdplrp_handle *h, const void *nccl_id);
+void comm_destroy(sdplrp_handle *h);
+int32_t comm_partition(sdplrp_handle *h);
+void comm_mark_partial(sdplrp_handle *h, int mat_id);
+void comm_mark_full(sdplrp_handle *h, int mat_id);
+int32_t comm_require_full(sdplrp_handle *h, int mat_id);
+int32_t comm_gather_rows(sdplrp_handle *h, double *p, int mat_id);
+int32_t comm_reduce_mvec(sdplrp_handle *h, double *v1, double *v2);
+int32_t comm_reduce_scalars(sdplrp_handle *h, int slot, int count);
+int32_t comm_reduce_ptr(sdplrp_handle *h, double *p, int count);
+int32_t comm_step_R(sdplrp_handle *h, double alpha);
+
+// scalar plumbing (api.cu)
+int32_t fetch_scalars(sdplrp_handle *h, int first, int count);  // dscal -> hscal, synchronises

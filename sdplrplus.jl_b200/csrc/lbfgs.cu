@@ -1,0 +1,279 @@
+// lbfgs.cu -- the L-BFGS two-loop recursion and the dense BLAS-1 glue of the
+// inner iteration as fused dot/axpy kernels with device-side scalars.
+//
+// Reference: src/lbfgs.jl:52-149 (lbfgs_clear!, lbfgs_dir!, lbfgs_update!) and
+// src/sdplr.jl:201-205, 219, 224-228 (descent dot, fallback, Rt += alpha*dirt,
+// gradient norm).
+//
+// Design (not a translation): the reference runs 2h dependent (dot -> host
+// scalar -> axpy) pairs, 48*N bytes of traffic and 2h host round trips.  Here
+// every axpy is fused with the dot the *next* step needs, rho/alpha/beta stay
+// in device memory (the last CTA of each kernel finalises the sum), the
+// negation, the y_next = -grad pre-store and the descent dot ride on the last
+// axpy: 2h+1 launches, 35*N bytes, no host synchronisation until `descent`.
+// The arithmetic is the literal two-loop (no H0 scaling, zeroed slots act as
+// identity), only the summation order inside a dot differs.
+#include <algorithm>
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = kRedThreads;
+
+template <int VEC>
+struct V;
+template <>
+struct V<1> {
+    typedef double T;
+    static __device__ __forceinline__ T ld(const double *p, i64 i) { return p[i]; }
+    static __device__ __forceinline__ void st(double *p, i64 i, T v) { p[i] = v; }
+    static __device__ __forceinline__ T axpy(double a, T x, T y) { return y + a * x; }
+    static __device__ __forceinline__ T neg(T x) { return -x; }
+    static __device__ __forceinline__ T scale(double a, T x) { return a * x; }
+    static __device__ __forceinline__ double dot(T a, T b) { return a * b; }
+};
+template <>
+struct V<2> {
+    typedef double2 T;
+    static __device__ __forceinline__ T ld(const double *p, i64 i) { return reinterpret_cast<const double2 *>(p)[i]; }
+    static __device__ __forceinline__ void st(double *p, i64 i, T v) { reinterpret_cast<double2 *>(p)[i] = v; }
+    static __device__ __forceinline__ T axpy(double a, T x, T y) { return make_double2(y.x + a * x.x, y.y + a * x.y); }
+    static __device__ __forceinline__ T neg(T x) { return make_double2(-x.x, -x.y); }
+    static __device__ __forceinline__ T scale(double a, T x) { return make_double2(a * x.x, a * x.y); }
+    static __device__ __forceinline__ double dot(T a, T b) { return a.x * b.x + a.y * b.y; }
+};
+
+#define GRID_STRIDE(i, nu) for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < (nu); i += (i64)gridDim.x * blockDim.x)
+
+// out_scalar = <x, y>
+template <int VEC>
+__global__ void __launch_bounds__(TPB) k_dot(i64 nu, const double *__restrict__ x, const double *__restrict__ y, double *partials,
+                                             unsigned *ticket, double *out) {
+    double acc[1] = {0.0};
+    GRID_STRIDE(i, nu) acc[0] += V<VEC>::dot(V<VEC>::ld(x, i), V<VEC>::ld(y, i));
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { out[0] = s[0]; });
+}
+
+// one step of the two-loop recursion fused with the next step's dot.
+// PHASE 1 (first loop, src/lbfgs.jl:93-101):  a = rho*dot_in; out = in - a*w;      a_j = a
+// PHASE 2 (second loop, :104-112):            g = a_j - rho*dot_in; out = in + g*w
+// PHASE 3 (last step): as PHASE 2, then out = -out (:115-117), ypre = -grad
+//          (:121-123) and the fused dot is <out, grad> = descent (src/sdplr.jl:201)
+template <int VEC, int PHASE>
+__global__ void __launch_bounds__(TPB) k_two_loop(i64 nu, const double *in, const double *__restrict__ w,
+                                                  const double *z, double *out, const double *__restrict__ rho_j,
+                                                  double *a_j, const double *__restrict__ dot_in, double *dot_out,
+                                                  const double *grad, double *ypre, double *partials, unsigned *ticket) {
+    double coef;
+    if (PHASE == 1) {
+        const double a = rho_j[0] * dot_in[0];
+        coef = -a;
+        if (blockIdx.x == 0 && threadIdx.x == 0) a_j[0] = a;
+    } else {
+        coef = a_j[0] - rho_j[0] * dot_in[0];
+    }
+    double acc[1] = {0.0};
+    GRID_STRIDE(i, nu) {
+        typename V<VEC>::T d = V<VEC>::axpy(coef, V<VEC>::ld(w, i), V<VEC>::ld(in, i));
+        if (PHASE == 3) {
+            d = V<VEC>::neg(d);
+            typename V<VEC>::T g = V<VEC>::ld(grad, i);
+            V<VEC>::st(ypre, i, V<VEC>::neg(g));
+            acc[0] += V<VEC>::dot(d, g);
+        } else {
+            acc[0] += V<VEC>::dot(V<VEC>::ld(z, i), d);
+        }
+        V<VEC>::st(out, i, d);
+    }
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { dot_out[0] = s[0]; });
+}
+
+// h == 0: dir = -grad, descent = -||grad||^2
+template <int VEC>
+__global__ void __launch_bounds__(TPB) k_neg_dir(i64 nu, const double *__restrict__ grad, double *__restrict__ dir,
+                                                 double *partials, unsigned *ticket, double *dot_out) {
+    double acc[1] = {0.0};
+    GRID_STRIDE(i, nu) {
+        typename V<VEC>::T g = V<VEC>::ld(grad, i);
+        V<VEC>::st(dir, i, V<VEC>::neg(g));
+        acc[0] -= V<VEC>::dot(g, g);
+    }
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { dot_out[0] = s[0]; });
+}
+
+// lbfgs_update! (src/lbfgs.jl:129-149): s_j = alpha*dir, y_j += grad, rho_j = 1/<y_j,s_j>
+template <int VEC>
+__global__ void __launch_bounds__(TPB) k_update(i64 nu, double alpha, const double *__restrict__ dir,
+                                                const double *__restrict__ grad, double *__restrict__ sj,
+                                                double *__restrict__ yj, double *partials, unsigned *ticket, double *rho_j) {
+    double acc[1] = {0.0};
+    GRID_STRIDE(i, nu) {
+        typename V<VEC>::T s = V<VEC>::scale(alpha, V<VEC>::ld(dir, i));
+        typename V<VEC>::T y = V<VEC>::axpy(1.0, V<VEC>::ld(grad, i), V<VEC>::ld(yj, i));
+        V<VEC>::st(sj, i, s);
+        V<VEC>::st(yj, i, y);
+        acc[0] += V<VEC>::dot(y, s);
+    }
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { rho_j[0] = s[0]; });
+}
+__global__ void k_invert(double *x) { x[0] = 1.0 / x[0]; }
+
+template <int VEC>
+__global__ void __launch_bounds__(TPB) k_axpy(i64 nu, double a, const double *__restrict__ x, double *__restrict__ y) {
+    GRID_STRIDE(i, nu) V<VEC>::st(y, i, V<VEC>::axpy(a, V<VEC>::ld(x, i), V<VEC>::ld(y, i)));
+}
+
+// G = -G ; D = G   (src/sdplr.jl:203-204)
+template <int VEC>
+__global__ void __launch_bounds__(TPB) k_neg_copy(i64 nu, double *__restrict__ g, double *__restrict__ d) {
+    GRID_STRIDE(i, nu) {
+        typename V<VEC>::T v = V<VEC>::neg(V<VEC>::ld(g, i));
+        V<VEC>::st(g, i, v);
+        V<VEC>::st(d, i, v);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(TPB) k_norm2(i64 nu, const double *__restrict__ x, double *partials, unsigned *ticket, double *out) {
+    double acc[1] = {0.0};
+    GRID_STRIDE(i, nu) {
+        typename V<VEC>::T v = V<VEC>::ld(x, i);
+        acc[0] += V<VEC>::dot(v, v);
+    }
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { out[0] = s[0]; });
+}
+
+struct Slice {
+    i64 off, len, nu;
+    int vec;
+    int grid;
+};
+Slice owned(const sdplrp_handle *h) {
+    Slice s;
+    s.off = h->row_lo * h->r;
+    s.len = (h->row_hi - h->row_lo) * h->r;
+    s.vec = (s.off % 2 == 0 && s.len % 2 == 0) ? 2 : 1;
+    s.nu = s.len / s.vec;
+    s.grid = grid_for(s.nu, TPB * 4, kRedBlocks);
+    return s;
+}
+
+#define DISPATCH_VEC(sl, KERNEL, ...)                                              \
+    do {                                                                           \
+        if ((sl).vec == 2) KERNEL<2><<<(sl).grid, TPB, 0, h->stream>>>(__VA_ARGS__); \
+        else KERNEL<1><<<(sl).grid, TPB, 0, h->stream>>>(__VA_ARGS__);             \
+        KLAUNCH(h);                                                                \
+    } while (0)
+
+template <int PHASE>
+void launch_two_loop(sdplrp_handle *h, const Slice &sl, const double *in, const double *w, const double *z, double *out,
+                     const double *rho_j, double *a_j, const double *dot_in, double *dot_out, const double *grad, double *ypre) {
+    if (sl.vec == 2)
+        k_two_loop<2, PHASE><<<sl.grid, TPB, 0, h->stream>>>(sl.nu, in, w, z, out, rho_j, a_j, dot_in, dot_out, grad, ypre, h->partials, h->ticket);
+    else
+        k_two_loop<1, PHASE><<<sl.grid, TPB, 0, h->stream>>>(sl.nu, in, w, z, out, rho_j, a_j, dot_in, dot_out, grad, ypre, h->partials, h->ticket);
+    KLAUNCH(h);
+}
+
+}  // namespace
+
+// lbfgs_dir!(dirt, his, Gt; negate=true) followed by descent = dot(dirt, Gt)
+int32_t lb_dir(sdplrp_handle *h) {
+    const Slice sl = owned(h);
+    const int m = h->hist;
+    const double *grad = h->G + sl.off;
+    double *dir = h->D + sl.off;
+    double *descent = h->dscal + SC_DESCENT;
+    if (m == 0) {
+        DISPATCH_VEC(sl, k_neg_dir, sl.nu, grad, dir, h->partials, h->ticket, descent);
+        CUDA_TRY(h, cudaGetLastError());
+        return comm_reduce_ptr(h, descent, 1);
+    }
+    // slot order: newest -> oldest (1-based j as in the reference)
+    int order[kMaxHist];
+    {
+        int j = h->latest;
+        for (int q = 0; q < m; q++) { order[q] = j - 1; j -= 1; if (j == 0) j = m; }
+    }
+    double *dotA = h->dscal + SC_DOT, *dotB = h->dscal + SC_DOT + 6;  // ping-pong
+    // dot(s_newest, grad)
+    DISPATCH_VEC(sl, k_dot, sl.nu, h->Sh[order[0]] + sl.off, grad, h->partials, h->ticket, dotA);
+    SDP_CHECK(comm_reduce_ptr(h, dotA, 1));
+    double *din = dotA, *dout = dotB;
+    // first loop: newest -> oldest
+    for (int q = 0; q < m; q++) {
+        const int j = order[q];
+        const double *in = (q == 0) ? grad : dir;
+        const double *w = h->Yh[j] + sl.off;
+        const double *z = (q + 1 < m) ? h->Sh[order[q + 1]] + sl.off : h->Yh[order[m - 1]] + sl.off;
+        launch_two_loop<1>(h, sl, in, w, z, dir, h->dscal + SC_RHO + j, h->dscal + SC_A + j, din, dout, nullptr, nullptr);
+        SDP_CHECK(comm_reduce_ptr(h, dout, 1));
+        std::swap(din, dout);
+    }
+    // second loop: oldest -> newest
+    const int jpre = h->latest % m;  // 0-based slot mod(latest,h)+1 that receives y = -grad
+    for (int q = m - 1; q >= 0; q--) {
+        const int j = order[q];
+        const double *w = h->Sh[j] + sl.off;
+        if (q > 0) {
+            const double *z = h->Yh[order[q - 1]] + sl.off;
+            launch_two_loop<2>(h, sl, dir, w, z, dir, h->dscal + SC_RHO + j, h->dscal + SC_A + j, din, dout, nullptr, nullptr);
+            SDP_CHECK(comm_reduce_ptr(h, dout, 1));
+            std::swap(din, dout);
+        } else {
+            launch_two_loop<3>(h, sl, dir, w, nullptr, dir, h->dscal + SC_RHO + j, h->dscal + SC_A + j, din, descent, grad,
+                               h->Yh[jpre] + sl.off);
+            SDP_CHECK(comm_reduce_ptr(h, descent, 1));
+        }
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+
+int32_t lb_update(sdplrp_handle *h, double alpha) {
+    const int m = h->hist;
+    if (m == 0) return SDPLRP_OK;
+    const Slice sl = owned(h);
+    const int j = h->latest % m;  // 0-based mod(latest,h)+1
+    DISPATCH_VEC(sl, k_update, sl.nu, alpha, h->D + sl.off, h->G + sl.off, h->Sh[j] + sl.off, h->Yh[j] + sl.off, h->partials,
+                 h->ticket, h->dscal + SC_RHO + j);
+    SDP_CHECK(comm_reduce_ptr(h, h->dscal + SC_RHO + j, 1));
+    k_invert<<<1, 1, 0, h->stream>>>(h->dscal + SC_RHO + j);
+    KLAUNCH(h);
+    h->latest = j + 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+
+// lbfgs_clear!: zero s, y, rho, a; `latest` is kept (src/lbfgs.jl:52-59)
+int32_t lb_clear(sdplrp_handle *h) {
+    const size_t bytes = (size_t)h->n * h->r * sizeof(double);
+    for (int j = 0; j < h->hist; j++) {
+        CUDA_TRY(h, cudaMemsetAsync(h->Sh[j], 0, bytes, h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(h->Yh[j], 0, bytes, h->stream));
+    }
+    CUDA_TRY(h, cudaMemsetAsync(h->dscal + SC_RHO, 0, kMaxHist * sizeof(double), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->dscal + SC_A, 0, kMaxHist * sizeof(double), h->stream));
+    return SDPLRP_OK;
+}
+
+int32_t lb_axpy(sdplrp_handle *h, double alpha, const double *x, double *y) {
+    const Slice sl = owned(h);
+    DISPATCH_VEC(sl, k_axpy, sl.nu, alpha, x + sl.off, y + sl.off);
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+
+int32_t lb_neg_copy(sdplrp_handle *h) {
+    const Slice sl = owned(h);
+    DISPATCH_VEC(sl, k_neg_copy, sl.nu, h->G + sl.off, h->D + sl.off);
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+
+int32_t lb_norm2(sdplrp_handle *h, const double *x, int slot) {
+    const Slice sl = owned(h);
+    DISPATCH_VEC(sl, k_norm2, sl.nu, x + sl.off, h->partials, h->ticket, h->dscal + slot);
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}

@@ -1,0 +1,516 @@
+// preprocess.cu -- device-side construction of the aggregated sparsity pattern
+// and of every index map of preprocess_sparsecons (reference
+// src/preprocess.jl:24-169), plus the device-only derived layouts (chunk lists
+// for the constraint passes, static/dynamic split of S, SpMM row classes).
+//
+// Integer work, bit-exact against the oracle.  Sorting / scanning / unique use
+// the CUB primitives shipped with the CUDA toolkit (library code, like cuBLAS
+// for a plain GEMM); everything pattern-specific is hand-written below.
+#include <cub/cub.cuh>
+#include <algorithm>
+#include "common.cuh"
+
+namespace {
+
+struct Tmp {  // scoped device scratch
+    std::vector<void *> ptrs;
+    ~Tmp() {
+        for (void *p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    T *get(sdplrp_handle *h, i64 count, int32_t *rc) {
+        T *p = nullptr;
+        if (count <= 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, (size_t)count * sizeof(T));
+        if (e != cudaSuccess) {
+            h->err = std::string("cudaMalloc(preprocess scratch): ") + cudaGetErrorString(e);
+            *rc = SDPLRP_ERR_CUDA;
+            return nullptr;
+        }
+        ptrs.push_back(p);
+        return p;
+    }
+};
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ unsigned long long make_key(int row, int col) {
+    return ((unsigned long long)(unsigned)col << 32) | (unsigned)row;
+}
+
+// coordinates -> sort keys + upper-triangle flags (src/preprocess.jl:4-16, 56-82)
+__global__ void k_keys(i64 nnz, i64 n, const int64_t *__restrict__ I, const int64_t *__restrict__ J,
+                       unsigned long long *__restrict__ keyF, int *__restrict__ flag, int *__restrict__ errw) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nnz; k += (i64)gridDim.x * blockDim.x) {
+        i64 i = I[k] - 1, j = J[k] - 1;
+        if (i < 0 || i >= n || j < 0 || j >= n) {
+            atomicOr(errw, 1);
+            i = 0; j = 0;
+        }
+        keyF[k] = make_key((int)i, (int)j);
+        flag[k] = (i <= j) ? 1 : 0;
+    }
+}
+
+// stable compaction of the upper-triangular entries: this IS the concatenated
+// findnz(triu(A_i)) order of src/preprocess.jl:95-135
+__global__ void k_compact(i64 nnz, const int64_t *__restrict__ I, const int64_t *__restrict__ J,
+                          const double *__restrict__ V, const int *__restrict__ flag, const int *__restrict__ tpos,
+                          int *__restrict__ ent_row, int *__restrict__ ent_col, double *__restrict__ one,
+                          double *__restrict__ two, unsigned long long *__restrict__ keyT) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nnz; k += (i64)gridDim.x * blockDim.x) {
+        if (!flag[k]) continue;
+        int t = tpos[k];
+        int i = (int)(I[k] - 1), j = (int)(J[k] - 1);
+        double v = V[k];
+        ent_row[t] = i;
+        ent_col[t] = j;
+        one[t] = v;
+        two[t] = (i == j) ? v : 2.0 * v;  // src/preprocess.jl:125-132
+        keyT[t] = make_key(i, j);
+    }
+}
+
+// matptr[a] = number of triu entries before matrix a (src/preprocess.jl:101, 135)
+__global__ void k_matptr(i64 nA, i64 nnz, i64 Ec, const int64_t *__restrict__ mat_off, const int *__restrict__ tpos,
+                         int *__restrict__ matptr, const int64_t *__restrict__ gids, int *__restrict__ mat_gid) {
+    for (i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x; a <= nA; a += (i64)gridDim.x * blockDim.x) {
+        i64 off = (a < nA) ? mat_off[a] : nnz;
+        matptr[a] = (off < nnz) ? tpos[off] : (int)Ec;
+        if (a < nA) mat_gid[a] = (int)(gids[a] - 1);
+    }
+}
+
+// column pointers of a sorted, de-duplicated (col,row) key list
+__global__ void k_colptr(i64 n, i64 nnz, const unsigned long long *__restrict__ keys, int *__restrict__ ptr) {
+    for (i64 c = blockIdx.x * (i64)blockDim.x + threadIdx.x; c <= n; c += (i64)gridDim.x * blockDim.x) {
+        unsigned long long target = (unsigned long long)c << 32;
+        i64 lo = 0, hi = nnz;
+        while (lo < hi) {
+            i64 mid = (lo + hi) >> 1;
+            if (keys[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        ptr[c] = (int)lo;
+    }
+}
+
+__global__ void k_low32(i64 nnz, const unsigned long long *__restrict__ keys, int *__restrict__ out) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nnz; k += (i64)gridDim.x * blockDim.x)
+        out[k] = (int)(unsigned)(keys[k] & 0xffffffffull);
+}
+
+__device__ __forceinline__ int csc_find(const int *__restrict__ colptr, const int *__restrict__ rowval, int col, int row) {
+    int low = colptr[col], high = colptr[col + 1] - 1;
+    while (low <= high) {
+        int mid = (low + high) >> 1;
+        int rv = rowval[mid];
+        if (rv == row) return mid;
+        if (rv < row) low = mid + 1; else high = mid - 1;
+    }
+    return -1;
+}
+
+// nzind: slot of every entry in the triu CSC (src/preprocess.jl:104-124)
+__global__ void k_nzind(i64 Ec, const int *__restrict__ ent_row, const int *__restrict__ ent_col,
+                        const int *__restrict__ colptr, const int *__restrict__ rowval, int *__restrict__ slot) {
+    for (i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x; t < Ec; t += (i64)gridDim.x * blockDim.x)
+        slot[t] = csc_find(colptr, rowval, ent_col[t], ent_row[t]);
+}
+
+// agg_sparse_A_mappedto_triu (src/preprocess.jl:137-159)
+__global__ void k_mapped(i64 nnzF, const unsigned long long *__restrict__ keyF, const int *__restrict__ colptr,
+                         const int *__restrict__ rowval, int *__restrict__ mapped, int *__restrict__ errw) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nnzF; k += (i64)gridDim.x * blockDim.x) {
+        int row = (int)(unsigned)(keyF[k] & 0xffffffffull), col = (int)(keyF[k] >> 32);
+        int rr = min(row, col), cc = max(row, col);
+        int s = csc_find(colptr, rowval, cc, rr);
+        mapped[k] = s;
+        if (s < 0) atomicOr(errw, 2);
+    }
+}
+
+// matrix index of every entry (upper_bound on matptr)
+__global__ void k_ent_mat(i64 Ec, i64 nA, const int *__restrict__ matptr, int *__restrict__ ent_mat) {
+    for (i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x; t < Ec; t += (i64)gridDim.x * blockDim.x) {
+        i64 lo = 0, hi = nA;  // find last a with matptr[a] <= t
+        while (lo < hi) {
+            i64 mid = (lo + hi + 1) >> 1;
+            if (matptr[mid] <= (int)t) lo = mid; else hi = mid - 1;
+        }
+        // skip empty matrices that share the same matptr value: take the one whose range contains t
+        ent_mat[t] = (int)lo;
+    }
+}
+
+__global__ void k_iota(i64 nItems, int *__restrict__ out) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nItems; k += (i64)gridDim.x * blockDim.x) out[k] = (int)k;
+}
+
+// first position of each slot in the slot-sorted entry list
+__global__ void k_slot_ptr(i64 nnzT, i64 Ec, const int *__restrict__ sorted_slot, int *__restrict__ slot_ptr) {
+    for (i64 s = blockIdx.x * (i64)blockDim.x + threadIdx.x; s <= nnzT; s += (i64)gridDim.x * blockDim.x) {
+        i64 lo = 0, hi = Ec;
+        while (lo < hi) {
+            i64 mid = (lo + hi) >> 1;
+            if (sorted_slot[mid] < (int)s) lo = mid + 1; else hi = mid;
+        }
+        slot_ptr[s] = (int)lo;
+    }
+}
+
+// per triu slot: static (objective) value and number of non-objective contributors
+__global__ void k_slot_classify(i64 nnzT, const int *__restrict__ slot_ptr, const int *__restrict__ sorted_t,
+                                const int *__restrict__ ent_mat, const double *__restrict__ one, int obj_mat,
+                                double *__restrict__ triuS_static, int *__restrict__ dyn_cnt, int *__restrict__ dyn_flag) {
+    for (i64 s = blockIdx.x * (i64)blockDim.x + threadIdx.x; s < nnzT; s += (i64)gridDim.x * blockDim.x) {
+        double st = 0.0;
+        int cnt = 0;
+        for (int p = slot_ptr[s]; p < slot_ptr[s + 1]; p++) {
+            int t = sorted_t[p];
+            if (ent_mat[t] == obj_mat) st += one[t]; else cnt++;
+        }
+        triuS_static[s] = st;
+        dyn_cnt[s] = cnt;
+        dyn_flag[s] = cnt > 0 ? 1 : 0;
+    }
+}
+
+__global__ void k_dyn_fill(i64 nnzT, const int *__restrict__ slot_ptr, const int *__restrict__ sorted_t,
+                           const int *__restrict__ ent_mat, const double *__restrict__ one, const int *__restrict__ mat_gid,
+                           int obj_mat, const int *__restrict__ dyn_flag, const int *__restrict__ dyn_index,
+                           const int *__restrict__ dyn_off, const int *__restrict__ triu_rowval,
+                           const unsigned long long *__restrict__ keyT, const int *__restrict__ full_ptr,
+                           const int *__restrict__ full_idx, int *__restrict__ dyn_slot, int *__restrict__ dyn_ptr,
+                           int *__restrict__ dyn_gid, double *__restrict__ dyn_val, int *__restrict__ pos_a,
+                           int *__restrict__ pos_b) {
+    for (i64 s = blockIdx.x * (i64)blockDim.x + threadIdx.x; s < nnzT; s += (i64)gridDim.x * blockDim.x) {
+        if (!dyn_flag[s]) continue;
+        int d = dyn_index[s];
+        int o = dyn_off[s];
+        dyn_slot[d] = (int)s;
+        dyn_ptr[d] = o;
+        for (int p = slot_ptr[s]; p < slot_ptr[s + 1]; p++) {
+            int t = sorted_t[p];
+            int a = ent_mat[t];
+            if (a == obj_mat) continue;
+            dyn_gid[o] = mat_gid[a];
+            dyn_val[o] = one[t];
+            o++;
+        }
+        int row = triu_rowval[s], col = (int)(keyT[s] >> 32);
+        pos_a[d] = csc_find(full_ptr, full_idx, col, row);
+        pos_b[d] = csc_find(full_ptr, full_idx, row, col);
+    }
+}
+
+// generic: flag items whose segment length exceeds a threshold
+__global__ void k_len_flag(i64 nItems, const int *__restrict__ ptr, int thresh, int *__restrict__ flag) {
+    for (i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x; a < nItems; a += (i64)gridDim.x * blockDim.x)
+        flag[a] = (ptr[a + 1] - ptr[a] > thresh) ? 1 : 0;
+}
+__global__ void k_compact_ids(i64 nItems, const int *__restrict__ flag, const int *__restrict__ pos, int *__restrict__ out) {
+    for (i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x; a < nItems; a += (i64)gridDim.x * blockDim.x)
+        if (flag[a]) out[pos[a]] = (int)a;
+}
+__global__ void k_chunk_counts(i64 nLong, const int *__restrict__ long_mat, const int *__restrict__ matptr, int chunk,
+                               int *__restrict__ cnt) {
+    for (i64 l = blockIdx.x * (i64)blockDim.x + threadIdx.x; l < nLong; l += (i64)gridDim.x * blockDim.x) {
+        int a = long_mat[l];
+        cnt[l] = (matptr[a + 1] - matptr[a] + chunk - 1) / chunk;
+    }
+}
+__global__ void k_chunk_mat(i64 nChunks, i64 nLong, const int *__restrict__ long_chunk_ptr, int *__restrict__ chunk_mat) {
+    for (i64 c = blockIdx.x * (i64)blockDim.x + threadIdx.x; c < nChunks; c += (i64)gridDim.x * blockDim.x) {
+        i64 lo = 0, hi = nLong - 1;  // last l with long_chunk_ptr[l] <= c
+        while (lo < hi) {
+            i64 mid = (lo + hi + 1) >> 1;
+            if (long_chunk_ptr[mid] <= (int)c) lo = mid; else hi = mid - 1;
+        }
+        chunk_mat[c] = (int)lo;
+    }
+}
+
+// export kernels: 0-based int32 -> Julia 1-based int64
+__global__ void k_export_i32(i64 nItems, const int *__restrict__ in, int64_t *__restrict__ out) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nItems; k += (i64)gridDim.x * blockDim.x)
+        out[k] = (int64_t)in[k] + 1;
+}
+
+template <typename F>
+int32_t with_cub_temp(sdplrp_handle *h, F f) {
+    size_t bytes = 0;
+    CUDA_TRY(h, f((void *)nullptr, bytes));
+    void *tmp = nullptr;
+    CUDA_TRY(h, cudaMalloc(&tmp, bytes ? bytes : 1));
+    cudaError_t e = f(tmp, bytes);
+    cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { h->err = std::string("cub: ") + cudaGetErrorString(e); return SDPLRP_ERR_CUDA; }
+    if (e2 != cudaSuccess) { h->err = std::string("cub sync: ") + cudaGetErrorString(e2); return SDPLRP_ERR_CUDA; }
+    return SDPLRP_OK;
+}
+
+int32_t exclusive_scan(sdplrp_handle *h, const int *in, int *out, i64 count) {
+    if (count <= 0) return SDPLRP_OK;
+    h->launches += 2;
+    return with_cub_temp(h, [&](void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum(t, b, in, out, (int)count, h->stream); });
+}
+
+// sorted unique keys; returns the count
+int32_t sort_unique(sdplrp_handle *h, unsigned long long *keys, unsigned long long *scratch, i64 count, int end_bit,
+                    unsigned long long *out, i64 *n_out) {
+    if (count <= 0) { *n_out = 0; return SDPLRP_OK; }
+    h->launches += 8;
+    SDP_CHECK(with_cub_temp(h, [&](void *t, size_t &b) {
+        return cub::DeviceRadixSort::SortKeys(t, b, keys, scratch, (int)count, 0, end_bit, h->stream);
+    }));
+    int *d_n = nullptr;
+    CUDA_TRY(h, cudaMalloc((void **)&d_n, sizeof(int)));
+    int32_t rc = with_cub_temp(h, [&](void *t, size_t &b) {
+        return cub::DeviceSelect::Unique(t, b, scratch, out, d_n, (int)count, h->stream);
+    });
+    int hn = 0;
+    if (rc == SDPLRP_OK) {
+        cudaError_t e = cudaMemcpy(&hn, d_n, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { h->err = std::string("memcpy(unique count): ") + cudaGetErrorString(e); rc = SDPLRP_ERR_CUDA; }
+    }
+    cudaFree(d_n);
+    *n_out = hn;
+    return rc;
+}
+
+int32_t read_int(sdplrp_handle *h, const int *dptr, int *out) {
+    CUDA_TRY(h, cudaMemcpyAsync(out, dptr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SDPLRP_OK;
+}
+
+int bits_for(i64 n) {
+    int b = 1;
+    while (((i64)1 << b) < n) b++;
+    return b;
+}
+
+}  // namespace
+
+void pre_free(sdplrp_handle *h) {
+    dev_free(&h->triu_colptr); dev_free(&h->triu_rowval); dev_free(&h->full_ptr); dev_free(&h->full_idx);
+    dev_free(&h->mapped); dev_free(&h->S); dev_free(&h->matptr); dev_free(&h->mat_gid); dev_free(&h->ent_slot);
+    dev_free(&h->ent_row); dev_free(&h->ent_col); dev_free(&h->ent_one); dev_free(&h->ent_two);
+    dev_free(&h->long_mat); dev_free(&h->long_chunk_ptr); dev_free(&h->chunk_mat); dev_free(&h->chunk_part);
+    dev_free(&h->triuS_static); dev_free(&h->dyn_slot); dev_free(&h->dyn_ptr); dev_free(&h->dyn_gid);
+    dev_free(&h->dyn_val); dev_free(&h->dyn_pos_a); dev_free(&h->dyn_pos_b); dev_free(&h->long_rows);
+    h->preprocessed = false;
+    h->S_static_valid = false;
+}
+
+int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off, const int64_t *I,
+                  const int64_t *J, const double *V, const int64_t *gids) {
+    pre_free(h);
+    if (n <= 0 || m < 0 || nA < 0) return fail(h, SDPLRP_ERR_ARG, "preprocess: bad sizes");
+    if (n >= ((i64)1 << 31) - 1) return fail(h, SDPLRP_ERR_ARG, "preprocess: n must fit int32");
+    const i64 nnz = nA > 0 ? mat_off[nA] : 0;
+    if (nnz >= ((i64)1 << 31) - 1) return fail(h, SDPLRP_ERR_ARG, "preprocess: total nnz must fit int32");
+    for (i64 a = 0; a < nA; a++)
+        if (mat_off[a] > mat_off[a + 1] || mat_off[a] < 0) return fail(h, SDPLRP_ERR_ARG, "preprocess: mat_off not monotone");
+    h->n = n; h->m = m; h->nA = nA;
+    h->obj_mat = -1;
+    for (i64 a = 0; a < nA; a++) {
+        if (gids[a] < 1 || gids[a] > m + 1) return fail(h, SDPLRP_ERR_ARG, "preprocess: sparse_global_inds out of range");
+        if (gids[a] == m + 1) h->obj_mat = (int)a;
+    }
+    cudaStream_t st = h->stream;
+    int32_t rc = SDPLRP_OK;
+    Tmp tmp;
+    const int GS = 8 * kNumSM;
+
+    // ---- upload the triplets ------------------------------------------------
+    int64_t *dI = tmp.get<int64_t>(h, nnz, &rc), *dJ = tmp.get<int64_t>(h, nnz, &rc);
+    double *dV = tmp.get<double>(h, nnz, &rc);
+    int64_t *dOff = tmp.get<int64_t>(h, nA + 1, &rc), *dG = tmp.get<int64_t>(h, nA, &rc);
+    unsigned long long *keyF = tmp.get<unsigned long long>(h, nnz, &rc);
+    unsigned long long *keyS = tmp.get<unsigned long long>(h, nnz, &rc);  // sort scratch
+    unsigned long long *UF = tmp.get<unsigned long long>(h, nnz, &rc);
+    int *flag = tmp.get<int>(h, nnz + 1, &rc), *tpos = tmp.get<int>(h, nnz + 1, &rc);
+    int *errw = tmp.get<int>(h, 1, &rc);
+    if (rc) return rc;
+    if (nnz > 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(dI, I, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h, cudaMemcpyAsync(dJ, J, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h, cudaMemcpyAsync(dV, V, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (nA > 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(dOff, mat_off, (size_t)(nA + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h, cudaMemcpyAsync(dG, gids, (size_t)nA * 8, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(h, cudaMemsetAsync(errw, 0, sizeof(int), st));
+    CUDA_TRY(h, cudaMemsetAsync(flag, 0, (size_t)(nnz + 1) * sizeof(int), st));
+
+    // ---- keys, triu compaction ---------------------------------------------
+    if (nnz > 0) { k_keys<<<GS, TPB, 0, st>>>(nnz, n, dI, dJ, keyF, flag, errw); KLAUNCH(h); }
+    SDP_CHECK(exclusive_scan(h, flag, tpos, nnz + 1));
+    int Ec_i = 0;
+    SDP_CHECK(read_int(h, tpos + nnz, &Ec_i));
+    const i64 Ec = Ec_i;
+    h->Ec = Ec;
+    int herr = 0;
+    SDP_CHECK(read_int(h, errw, &herr));
+    if (herr & 1) return fail(h, SDPLRP_ERR_ARG, "preprocess: coordinate outside 1..n");
+
+    SDP_CHECK(dev_alloc(h, &h->ent_row, Ec)); SDP_CHECK(dev_alloc(h, &h->ent_col, Ec));
+    SDP_CHECK(dev_alloc(h, &h->ent_one, Ec)); SDP_CHECK(dev_alloc(h, &h->ent_two, Ec));
+    SDP_CHECK(dev_alloc(h, &h->ent_slot, Ec));
+    SDP_CHECK(dev_alloc(h, &h->matptr, nA + 1)); SDP_CHECK(dev_alloc(h, &h->mat_gid, nA));
+    unsigned long long *keyT = tmp.get<unsigned long long>(h, Ec, &rc);
+    unsigned long long *UT = tmp.get<unsigned long long>(h, Ec, &rc);
+    if (rc) return rc;
+    if (nnz > 0) {
+        k_compact<<<GS, TPB, 0, st>>>(nnz, dI, dJ, dV, flag, tpos, h->ent_row, h->ent_col, h->ent_one, h->ent_two, keyT);
+        KLAUNCH(h);
+    }
+    k_matptr<<<grid_for(nA + 1, TPB, GS), TPB, 0, st>>>(nA, nnz, Ec, dOff, tpos, h->matptr, dG, h->mat_gid);
+    KLAUNCH(h);
+
+    // ---- the two sparse() calls: sort + unique (src/preprocess.jl:90,93) ----
+    const int end_bit = 32 + bits_for(n);
+    i64 nnzT = 0, nnzF = 0;
+    SDP_CHECK(sort_unique(h, keyT, keyS, Ec, end_bit, UT, &nnzT));
+    SDP_CHECK(sort_unique(h, keyF, keyS, nnz, end_bit, UF, &nnzF));
+    h->nnzT = nnzT; h->nnzF = nnzF;
+
+    SDP_CHECK(dev_alloc(h, &h->triu_colptr, n + 1)); SDP_CHECK(dev_alloc(h, &h->triu_rowval, nnzT));
+    SDP_CHECK(dev_alloc(h, &h->full_ptr, n + 1)); SDP_CHECK(dev_alloc(h, &h->full_idx, nnzF));
+    SDP_CHECK(dev_alloc(h, &h->mapped, nnzF)); SDP_CHECK(dev_alloc(h, &h->S, nnzF));
+    SDP_CHECK(dev_alloc(h, &h->triuS_static, nnzT));
+    k_colptr<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, nnzT, UT, h->triu_colptr); KLAUNCH(h);
+    k_colptr<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, nnzF, UF, h->full_ptr); KLAUNCH(h);
+    if (nnzT > 0) { k_low32<<<GS, TPB, 0, st>>>(nnzT, UT, h->triu_rowval); KLAUNCH(h); }
+    if (nnzF > 0) { k_low32<<<GS, TPB, 0, st>>>(nnzF, UF, h->full_idx); KLAUNCH(h); }
+
+    // ---- index maps ----------------------------------------------------------
+    if (Ec > 0) { k_nzind<<<GS, TPB, 0, st>>>(Ec, h->ent_row, h->ent_col, h->triu_colptr, h->triu_rowval, h->ent_slot); KLAUNCH(h); }
+    if (nnzF > 0) { k_mapped<<<GS, TPB, 0, st>>>(nnzF, UF, h->triu_colptr, h->triu_rowval, h->mapped, errw); KLAUNCH(h); }
+    SDP_CHECK(read_int(h, errw, &herr));
+    CUDA_TRY(h, cudaMemsetAsync(h->S, 0, (size_t)std::max<i64>(nnzF, 1) * sizeof(double), st));
+    const bool asym = (herr & 2) != 0;
+
+    // ---- long matrices -> chunk lists (constraint passes) --------------------
+    h->n_long = 0; h->n_chunks = 0;
+    if (nA > 0) {
+        int *lflag = tmp.get<int>(h, nA + 1, &rc), *lpos = tmp.get<int>(h, nA + 1, &rc);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaMemsetAsync(lflag, 0, (size_t)(nA + 1) * sizeof(int), st));
+        k_len_flag<<<grid_for(nA, TPB, GS), TPB, 0, st>>>(nA, h->matptr, kLongMatThreshold, lflag); KLAUNCH(h);
+        SDP_CHECK(exclusive_scan(h, lflag, lpos, nA + 1));
+        int nl = 0;
+        SDP_CHECK(read_int(h, lpos + nA, &nl));
+        h->n_long = nl;
+        if (nl > 0) {
+            SDP_CHECK(dev_alloc(h, &h->long_mat, nl)); SDP_CHECK(dev_alloc(h, &h->long_chunk_ptr, nl + 1));
+            int *ccnt = tmp.get<int>(h, nl + 1, &rc);
+            if (rc) return rc;
+            CUDA_TRY(h, cudaMemsetAsync(ccnt, 0, (size_t)(nl + 1) * sizeof(int), st));
+            k_compact_ids<<<grid_for(nA, TPB, GS), TPB, 0, st>>>(nA, lflag, lpos, h->long_mat); KLAUNCH(h);
+            k_chunk_counts<<<grid_for(nl, TPB, GS), TPB, 0, st>>>(nl, h->long_mat, h->matptr, kChunkEntries, ccnt); KLAUNCH(h);
+            SDP_CHECK(exclusive_scan(h, ccnt, h->long_chunk_ptr, nl + 1));
+            int nc = 0;
+            SDP_CHECK(read_int(h, h->long_chunk_ptr + nl, &nc));
+            h->n_chunks = nc;
+            SDP_CHECK(dev_alloc(h, &h->chunk_mat, nc)); SDP_CHECK(dev_alloc(h, &h->chunk_part, (i64)nc * 2));
+            k_chunk_mat<<<grid_for(nc, TPB, GS), TPB, 0, st>>>(nc, nl, h->long_chunk_ptr, h->chunk_mat); KLAUNCH(h);
+        }
+    }
+
+    // ---- S assembly layout: static objective part + dynamic slots -----------
+    h->n_dyn = 0;
+    if (Ec > 0) {
+        int *ent_mat = tmp.get<int>(h, Ec, &rc), *iota = tmp.get<int>(h, Ec, &rc);
+        int *sorted_slot = tmp.get<int>(h, Ec, &rc), *sorted_t = tmp.get<int>(h, Ec, &rc);
+        int *slot_ptr = tmp.get<int>(h, nnzT + 1, &rc);
+        int *dcnt = tmp.get<int>(h, nnzT + 1, &rc), *dflag = tmp.get<int>(h, nnzT + 1, &rc);
+        int *dindex = tmp.get<int>(h, nnzT + 1, &rc), *doff = tmp.get<int>(h, nnzT + 1, &rc);
+        if (rc) return rc;
+        k_ent_mat<<<GS, TPB, 0, st>>>(Ec, nA, h->matptr, ent_mat); KLAUNCH(h);
+        k_iota<<<GS, TPB, 0, st>>>(Ec, iota); KLAUNCH(h);
+        h->launches += 4;
+        SDP_CHECK(with_cub_temp(h, [&](void *t, size_t &b) {
+            return cub::DeviceRadixSort::SortPairs(t, b, reinterpret_cast<const unsigned *>(h->ent_slot),
+                                                   reinterpret_cast<unsigned *>(sorted_slot), iota, sorted_t, (int)Ec, 0,
+                                                   bits_for(nnzT + 1), st);
+        }));
+        k_slot_ptr<<<grid_for(nnzT + 1, TPB, GS), TPB, 0, st>>>(nnzT, Ec, sorted_slot, slot_ptr); KLAUNCH(h);
+        CUDA_TRY(h, cudaMemsetAsync(dcnt, 0, (size_t)(nnzT + 1) * sizeof(int), st));
+        CUDA_TRY(h, cudaMemsetAsync(dflag, 0, (size_t)(nnzT + 1) * sizeof(int), st));
+        k_slot_classify<<<GS, TPB, 0, st>>>(nnzT, slot_ptr, sorted_t, ent_mat, h->ent_one, h->obj_mat, h->triuS_static, dcnt, dflag);
+        KLAUNCH(h);
+        SDP_CHECK(exclusive_scan(h, dflag, dindex, nnzT + 1));
+        SDP_CHECK(exclusive_scan(h, dcnt, doff, nnzT + 1));
+        int nd = 0, ndc = 0;
+        SDP_CHECK(read_int(h, dindex + nnzT, &nd));
+        SDP_CHECK(read_int(h, doff + nnzT, &ndc));
+        h->n_dyn = nd;
+        SDP_CHECK(dev_alloc(h, &h->dyn_slot, nd)); SDP_CHECK(dev_alloc(h, &h->dyn_ptr, nd + 1));
+        SDP_CHECK(dev_alloc(h, &h->dyn_gid, ndc)); SDP_CHECK(dev_alloc(h, &h->dyn_val, ndc));
+        SDP_CHECK(dev_alloc(h, &h->dyn_pos_a, nd)); SDP_CHECK(dev_alloc(h, &h->dyn_pos_b, nd));
+        if (nd > 0) {
+            k_dyn_fill<<<GS, TPB, 0, st>>>(nnzT, slot_ptr, sorted_t, ent_mat, h->ent_one, h->mat_gid, h->obj_mat, dflag,
+                                           dindex, doff, h->triu_rowval, UT, h->full_ptr, h->full_idx, h->dyn_slot,
+                                           h->dyn_ptr, h->dyn_gid, h->dyn_val, h->dyn_pos_a, h->dyn_pos_b);
+            KLAUNCH(h);
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(h->dyn_ptr + nd, &ndc, sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+    }
+
+    // ---- SpMM row classes ---------------------------------------------------
+    h->n_long_rows = 0;
+    {
+        int *rflag = tmp.get<int>(h, n + 1, &rc), *rpos = tmp.get<int>(h, n + 1, &rc);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaMemsetAsync(rflag, 0, (size_t)(n + 1) * sizeof(int), st));
+        k_len_flag<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, h->full_ptr, kLongRowThreshold, rflag); KLAUNCH(h);
+        SDP_CHECK(exclusive_scan(h, rflag, rpos, n + 1));
+        int nlr = 0;
+        SDP_CHECK(read_int(h, rpos + n, &nlr));
+        h->n_long_rows = nlr;
+        SDP_CHECK(dev_alloc(h, &h->long_rows, nlr));
+        if (nlr > 0) { k_compact_ids<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, rflag, rpos, h->long_rows); KLAUNCH(h); }
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    CUDA_TRY(h, cudaGetLastError());
+    h->preprocessed = true;
+    h->S_static_valid = false;
+    h->row_lo = 0; h->row_hi = n;
+    if (asym) {
+        h->err = "preprocess: a lower-triangular entry has no mirrored upper entry (maps exported with 0 there)";
+        return SDPLRP_ERR_ASYMMETRIC;
+    }
+    return SDPLRP_OK;
+}
+
+int32_t pre_export(sdplrp_handle *h, int64_t *triu_colptr, int64_t *triu_rowval, int64_t *matptr, int64_t *nzind,
+                   double *one, double *two, int64_t *full_colptr, int64_t *full_rowval, int64_t *mapped) {
+    cudaStream_t st = h->stream;
+    const i64 n = h->n, nA = h->nA, nnzT = h->nnzT, nnzF = h->nnzF, Ec = h->Ec;
+    i64 maxlen = std::max(std::max(n + 1, nA + 1), std::max(std::max(nnzT, nnzF), Ec));
+    int64_t *buf = nullptr;
+    CUDA_TRY(h, cudaMalloc((void **)&buf, (size_t)std::max<i64>(maxlen, 1) * sizeof(int64_t)));
+    struct Item { const int *src; int64_t *dst; i64 len; };
+    Item items[] = {{h->triu_colptr, triu_colptr, n + 1}, {h->triu_rowval, triu_rowval, nnzT}, {h->matptr, matptr, nA + 1},
+                    {h->ent_slot, nzind, Ec}, {h->full_ptr, full_colptr, n + 1}, {h->full_idx, full_rowval, nnzF},
+                    {h->mapped, mapped, nnzF}};
+    int32_t rc = SDPLRP_OK;
+    for (const Item &it : items) {
+        if (!it.dst || it.len <= 0) continue;
+        k_export_i32<<<grid_for(it.len, TPB, 8 * kNumSM), TPB, 0, st>>>(it.len, it.src, buf);
+        KLAUNCH(h);
+        cudaError_t e = cudaMemcpyAsync(it.dst, buf, (size_t)it.len * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { h->err = std::string("pattern_export: ") + cudaGetErrorString(e); rc = SDPLRP_ERR_CUDA; break; }
+    }
+    cudaFree(buf);
+    if (rc) return rc;
+    if (one && Ec > 0) CUDA_TRY(h, cudaMemcpy(one, h->ent_one, (size_t)Ec * 8, cudaMemcpyDeviceToHost));
+    if (two && Ec > 0) CUDA_TRY(h, cudaMemcpy(two, h->ent_two, (size_t)Ec * 8, cudaMemcpyDeviceToHost));
+    return SDPLRP_OK;
+}

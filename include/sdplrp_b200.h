@@ -184,6 +184,27 @@ int32_t sdplrp_dual_obj(sdplrp_handle *h, double trace_bound, int64_t iter, cons
                         double *dual_value, double *mineig, int64_t *lanczos_steps);
 
 /* ---- introspection ---------------------------------------------------- */
+/* kernel-group sections timed with CUDA events on the handle's stream */
+enum {
+    SDPLRP_SEC_LBFGS_DIR = 0,    /* two-loop recursion kernels (2h+1 launches) */
+    SDPLRP_SEC_LS_PASS = 1,      /* fused {A(RD'+DR'), A(DD')} sampled-dot kernels */
+    SDPLRP_SEC_LS_COEFF = 2,     /* quartic-coefficient reduction */
+    SDPLRP_SEC_STEP = 3,         /* residual recurrence + R += alpha*D */
+    SDPLRP_SEC_S_ASSEMBLE = 4,   /* y formation + S update */
+    SDPLRP_SEC_SPMM = 5,         /* G = 2*S*R (+ low rank) */
+    SDPLRP_SEC_NORMS = 6,        /* ||G||^2, ||pvio||^2 */
+    SDPLRP_SEC_LBFGS_UPDATE = 7,
+    SDPLRP_SEC_A_UU = 8,         /* A(RR') of f! */
+    SDPLRP_SEC_F_FINISH = 9,
+    SDPLRP_SEC_LANCZOS = 10,
+    SDPLRP_SEC_COMM = 11,        /* NCCL collectives */
+    SDPLRP_SEC_COUNT = 12
+};
+/* on != 0: record a CUDA-event pair around every section from now on */
+int32_t sdplrp_set_profiling(sdplrp_handle *h, int32_t on);
+/* synchronises, adds the pending event pairs up and returns (then resets) the
+ * accumulated milliseconds and launch-group counts per section (SDPLRP_SEC_COUNT each) */
+int32_t sdplrp_section_times(sdplrp_handle *h, double *ms, int64_t *counts);
 /* number of kernels this handle has launched since creation */
 int32_t sdplrp_launch_count(sdplrp_handle *h, int64_t *count);
 /* rows [lo,hi) of R/G/D owned by this rank (0-based) */

@@ -64,6 +64,8 @@ _SIGNATURES = {
     "sdplrp_lanczos": [_H, C.c_int64, _p_f64, C.c_uint64, C.c_int32, _p_f64, _p_f64, _p_i64],
     "sdplrp_tridiag_mineig": [_p_f64, _p_f64, C.c_int64, _p_f64],
     "sdplrp_dual_obj": [_H, C.c_double, C.c_int64, _p_f64, C.c_uint64, _p_f64, _p_f64, _p_i64],
+    "sdplrp_set_profiling": [_H, C.c_int32],
+    "sdplrp_section_times": [_H, _p_f64, _p_i64],
     "sdplrp_launch_count": [_H, _p_i64],
     "sdplrp_row_range": [_H, _p_i64, _p_i64],
 }
@@ -358,6 +360,19 @@ class Handle:
         self._check(self.lib.sdplrp_dual_obj(self._h, float(trace_bound), int(it), pv, int(seed), C.byref(d), C.byref(e),
                                               C.byref(s)))
         return d.value, e.value, s.value
+
+    SECTIONS = ["lbfgs_dir", "ls_pass", "ls_coeff", "step", "s_assemble", "spmm", "norms", "lbfgs_update", "a_uu", "f_finish",
+                "lanczos", "comm"]
+
+    def set_profiling(self, on):
+        self._check(self.lib.sdplrp_set_profiling(self._h, int(bool(on))))
+
+    def section_times(self):
+        """{section: (milliseconds, count)} accumulated since the last call (CUDA events on the handle's stream)."""
+        k = len(self.SECTIONS)
+        ms = np.zeros(k); cnt = np.zeros(k, np.int64)
+        self._check(self.lib.sdplrp_section_times(self._h, ms.ctypes.data_as(_p_f64), cnt.ctypes.data_as(_p_i64)))
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.SECTIONS)}
 
     def launch_count(self):
         c = C.c_int64()

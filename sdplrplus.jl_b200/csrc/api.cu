@@ -22,6 +22,29 @@ int32_t fetch_scalars(sdplrp_handle *h, int first, int count) {
     return SDPLRP_OK;
 }
 
+cudaEvent_t prof_begin(sdplrp_handle *h) {
+    cudaEvent_t e = nullptr;
+    if (!h->ev_free.empty()) { e = h->ev_free.back(); h->ev_free.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    cudaEventRecord(e, h->stream);
+    return e;
+}
+void prof_end(sdplrp_handle *h, int sec, cudaEvent_t a) {
+    cudaEvent_t e = nullptr;
+    if (!h->ev_free.empty()) { e = h->ev_free.back(); h->ev_free.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) { h->ev_free.push_back(a); return; }
+    cudaEventRecord(e, h->stream);
+    h->ev_pending.push_back({sec, a, e});
+}
+static void prof_collect(sdplrp_handle *h) {
+    for (auto &p : h->ev_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { h->sec_ms[p.sec] += ms; h->sec_cnt[p.sec] += 1; }
+        h->ev_free.push_back(p.a); h->ev_free.push_back(p.b);
+    }
+    h->ev_pending.clear();
+}
+
 static double *mat_ptr(sdplrp_handle *h, int id) {
     switch (id) {
     case SDPLRP_MAT_R: return h->R;
@@ -129,6 +152,9 @@ int32_t sdplrp_destroy(sdplrp_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     comm_destroy(h);
+    prof_collect(h);
+    for (cudaEvent_t e : h->ev_free) cudaEventDestroy(e);
+    h->ev_free.clear();
     free_state(h);
     free_problem(h);
     dev_free(&h->dscal); dev_free(&h->partials); dev_free(&h->ticket);
@@ -405,16 +431,27 @@ int32_t sdplrp_At_right(sdplrp_handle *h, const double *x, double *y, int64_t nc
 // ---- fused iteration -----------------------------------------------------------
 static int32_t do_f(sdplrp_handle *h) {
     SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
-    SDP_CHECK(aop_uu(h, h->R, h->pvio_raw));
+    {
+        SectionScope sc(h, SDPLRP_SEC_A_UU);
+        SDP_CHECK(aop_uu(h, h->R, h->pvio_raw));
+    }
     SDP_CHECK(comm_reduce_mvec(h, h->pvio_raw, nullptr));
+    SectionScope sc(h, SDPLRP_SEC_F_FINISH);
     return vec_f_finish(h);
 }
 
 static int32_t do_g(sdplrp_handle *h) {
-    SDP_CHECK(grad_form_y(h));
-    SDP_CHECK(grad_assemble_S(h));
-    SDP_CHECK(grad_spmm(h, h->R, h->G, 2.0, true));  // G = 2 * R * S  (src/coreop.jl:312-315)
+    {
+        SectionScope sc(h, SDPLRP_SEC_S_ASSEMBLE);
+        SDP_CHECK(grad_form_y(h));
+        SDP_CHECK(grad_assemble_S(h));
+    }
+    {
+        SectionScope sc(h, SDPLRP_SEC_SPMM);
+        SDP_CHECK(grad_spmm(h, h->R, h->G, 2.0, true));  // G = 2 * R * S  (src/coreop.jl:312-315)
+    }
     comm_mark_partial(h, SDPLRP_MAT_G);
+    SectionScope sc(h, SDPLRP_SEC_NORMS);
     SDP_CHECK(lb_norm2(h, h->G, SC_GNORM2));
     SDP_CHECK(comm_reduce_scalars(h, SC_GNORM2, 1));
     return vec_pnorm2(h);
@@ -453,7 +490,10 @@ int32_t sdplrp_fg(sdplrp_handle *h, double out[4]) {
 int32_t sdplrp_lbfgs_dir(sdplrp_handle *h, double *descent) {
     REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
-    SDP_CHECK(lb_dir(h));
+    {
+        SectionScope sc(h, SDPLRP_SEC_LBFGS_DIR);
+        SDP_CHECK(lb_dir(h));
+    }
     comm_mark_partial(h, SDPLRP_MAT_D);
     SDP_CHECK(fetch_scalars(h, SC_DESCENT, 1));
     if (descent) *descent = h->hscal[SC_DESCENT];
@@ -473,9 +513,15 @@ int32_t sdplrp_linesearch_coeffs(sdplrp_handle *h, double bq[5]) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     SDP_CHECK(comm_require_full(h, SDPLRP_MAT_D));
     SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
-    SDP_CHECK(aop_linesearch(h));
+    {
+        SectionScope sc(h, SDPLRP_SEC_LS_PASS);
+        SDP_CHECK(aop_linesearch(h));
+    }
     SDP_CHECK(comm_reduce_mvec(h, h->A_RD, h->A_DD));
-    SDP_CHECK(vec_biquadratic(h));
+    {
+        SectionScope sc(h, SDPLRP_SEC_LS_COEFF);
+        SDP_CHECK(vec_biquadratic(h));
+    }
     SDP_CHECK(fetch_scalars(h, SC_BQ, 5));
     for (int k = 0; k < 5; k++) bq[k] = h->hscal[SC_BQ + k];
     return SDPLRP_OK;
@@ -484,8 +530,11 @@ int32_t sdplrp_linesearch_coeffs(sdplrp_handle *h, double bq[5]) {
 int32_t sdplrp_step(sdplrp_handle *h, double alpha, double *obj) {
     REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
-    SDP_CHECK(vec_commit(h, alpha));
-    SDP_CHECK(comm_step_R(h, alpha));  // Rt += alpha*dirt (all rows when replicated)
+    {
+        SectionScope sc(h, SDPLRP_SEC_STEP);
+        SDP_CHECK(vec_commit(h, alpha));
+        SDP_CHECK(comm_step_R(h, alpha));  // Rt += alpha*dirt (all rows when replicated)
+    }
     if (obj) {
         SDP_CHECK(fetch_scalars(h, SC_OBJ, 1));
         *obj = h->hscal[SC_OBJ];
@@ -496,6 +545,7 @@ int32_t sdplrp_step(sdplrp_handle *h, double alpha, double *obj) {
 int32_t sdplrp_lbfgs_update(sdplrp_handle *h, double alpha) {
     REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
+    SectionScope sc(h, SDPLRP_SEC_LBFGS_UPDATE);
     return lb_update(h, alpha);
 }
 
@@ -525,7 +575,10 @@ int32_t sdplrp_lanczos(sdplrp_handle *h, int64_t q, const double *v0, uint64_t s
     if (q < 1 || !alpha || !beta || !iters) return fail(h, SDPLRP_ERR_ARG, "lanczos: bad argument");
     CUDA_TRY(h, cudaSetDevice(h->device));
     i64 it = 0;
-    SDP_CHECK(lz_run(h, q, v0, seed, reorth, alpha, beta, &it));
+    {
+        SectionScope sc(h, SDPLRP_SEC_LANCZOS);
+        SDP_CHECK(lz_run(h, q, v0, seed, reorth, alpha, beta, &it));
+    }
     *iters = it;
     return SDPLRP_OK;
 }
@@ -547,7 +600,10 @@ int32_t sdplrp_dual_obj(sdplrp_handle *h, double trace_bound, int64_t iter, cons
     q = std::max<i64>(1, std::min<i64>(q, h->n - 1));
     std::vector<double> a((size_t)q), b((size_t)q);
     i64 steps = 0;
-    SDP_CHECK(lz_run(h, q, v0, seed, 0, a.data(), b.data(), &steps));
+    {
+        SectionScope sc(h, SDPLRP_SEC_LANCZOS);
+        SDP_CHECK(lz_run(h, q, v0, seed, 0, a.data(), b.data(), &steps));
+    }
     for (i64 i = 0; i < steps; i++) a[(size_t)i] += 1.0;  // shift by I (src/coreop.jl:503)
     const double lam = (steps == 1 ? a[0] : tridiag_mineig_host(a.data(), b.data(), steps)) - 1.0;
     double yb = 0.0;
@@ -555,6 +611,25 @@ int32_t sdplrp_dual_obj(sdplrp_handle *h, double trace_bound, int64_t iter, cons
     if (dual_value) *dual_value = yb + trace_bound * std::min(lam, 0.0);  // src/coreop.jl:412
     if (mineig) *mineig = lam;
     if (lanczos_steps) *lanczos_steps = steps;
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_set_profiling(sdplrp_handle *h, int32_t on) {
+    REQUIRE_H(h);
+    h->prof = on != 0;
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_section_times(sdplrp_handle *h, double *ms, int64_t *counts) {
+    REQUIRE_H(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    prof_collect(h);
+    for (int k = 0; k < SDPLRP_SEC_COUNT; k++) {
+        if (ms) ms[k] = h->sec_ms[k];
+        if (counts) counts[k] = h->sec_cnt[k];
+        h->sec_ms[k] = 0.0; h->sec_cnt[k] = 0;
+    }
     return SDPLRP_OK;
 }
 

@@ -8,10 +8,57 @@
 // dot products and the constraint vector are all-reduced.
 //
 // world == 1 never touches NCCL: every function below is a no-op then.
+#include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
 #include <algorithm>
 #include "common.cuh"
+
+// NCCL is bound lazily with dlopen: a process that already carries a libnccl
+// (e.g. the one bundled with PyTorch, which the host runtime imports first)
+// keeps using it, and single-GPU use never loads NCCL at all.
+namespace {
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+
+bool nccl_bind() {
+    if (g_nccl.ok) return true;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+#define BIND(field, sym) *(void **)(&g_nccl.field) = dlsym(lib, sym); if (!g_nccl.field) return false
+    BIND(GetUniqueId, "ncclGetUniqueId");
+    BIND(CommInitRank, "ncclCommInitRank");
+    BIND(CommDestroy, "ncclCommDestroy");
+    BIND(AllReduce, "ncclAllReduce");
+    BIND(Broadcast, "ncclBroadcast");
+    BIND(GroupStart, "ncclGroupStart");
+    BIND(GroupEnd, "ncclGroupEnd");
+    BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+    g_nccl.ok = true;
+    return true;
+}
+}  // namespace
+#define ncclGetUniqueId g_nccl.GetUniqueId
+#define ncclCommInitRank g_nccl.CommInitRank
+#define ncclCommDestroy g_nccl.CommDestroy
+#define ncclAllReduce g_nccl.AllReduce
+#define ncclBroadcast g_nccl.Broadcast
+#define ncclGroupStart g_nccl.GroupStart
+#define ncclGroupEnd g_nccl.GroupEnd
+#define ncclGetErrorString g_nccl.GetErrorString
 
 #define NCCL_TRY(h, call)                                                        \
     do {                                                                         \
@@ -25,6 +72,7 @@
 extern "C" int32_t sdplrp_nccl_unique_id(void *out128) {
     if (!out128) return SDPLRP_ERR_ARG;
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (!nccl_bind()) return SDPLRP_ERR_NCCL;
     ncclUniqueId id;
     if (ncclGetUniqueId(&id) != ncclSuccess) return SDPLRP_ERR_NCCL;
     memcpy(out128, &id, sizeof(id));
@@ -34,6 +82,7 @@ extern "C" int32_t sdplrp_nccl_unique_id(void *out128) {
 int32_t comm_init(sdplrp_handle *h, const void *nccl_id) {
     if (h->world <= 1) return SDPLRP_OK;
     if (!nccl_id) return fail(h, SDPLRP_ERR_ARG, "create: world > 1 needs the NCCL unique id");
+    if (!nccl_bind()) return fail(h, SDPLRP_ERR_NCCL, "cannot load libnccl.so.2");
     ncclUniqueId id;
     memcpy(&id, nccl_id, sizeof(id));
     ncclComm_t comm;
@@ -98,6 +147,7 @@ void comm_mark_full(sdplrp_handle *h, int mat_id) {
 
 // all-gather (variable block sizes) of the owned row blocks of a dense n x r matrix
 static int32_t allgather_rows(sdplrp_handle *h, double *p) {
+    SectionScope sc(h, SDPLRP_SEC_COMM);
     ncclComm_t comm = (ncclComm_t)h->nccl;
     NCCL_TRY(h, ncclGroupStart());
     for (int q = 0; q < h->world; q++) {
@@ -138,6 +188,7 @@ int32_t comm_gather_rows(sdplrp_handle *h, double *p, int mat_id) {
 // sum the per-rank partial constraint vectors (length m+1)
 int32_t comm_reduce_mvec(sdplrp_handle *h, double *v1, double *v2) {
     if (h->world <= 1) return SDPLRP_OK;
+    SectionScope sc(h, SDPLRP_SEC_COMM);
     ncclComm_t comm = (ncclComm_t)h->nccl;
     NCCL_TRY(h, ncclGroupStart());
     NCCL_TRY(h, ncclAllReduce(v1, v1, (size_t)(h->m + 1), ncclDouble, ncclSum, comm, h->stream));

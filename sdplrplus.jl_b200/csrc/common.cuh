@@ -108,6 +108,13 @@ struct sdplrp_handle {
     double *hscal = nullptr;      // pinned mirror
     double *partials = nullptr;   // kRedBlocks * kMaxRedK (+ chunked extras)
     unsigned *ticket = nullptr;   // last-block-done counters
+    // section profiling (CUDA events on `stream`)
+    bool prof = false;
+    std::vector<cudaEvent_t> ev_free;
+    struct Pending { int sec; cudaEvent_t a, b; };
+    std::vector<Pending> ev_pending;
+    double sec_ms[SDPLRP_SEC_COUNT] = {0};
+    i64 sec_cnt[SDPLRP_SEC_COUNT] = {0};
     // Lanczos workspace
     double *lz_v = nullptr, *lz_w = nullptr, *lz_vp = nullptr, *lz_ab = nullptr;
     i64 lz_ab_len = 0;
@@ -280,6 +287,15 @@ int32_t comm_reduce_mvec(sdplrp_handle *h, double *v1, double *v2);
 int32_t comm_reduce_scalars(sdplrp_handle *h, int slot, int count);
 int32_t comm_reduce_ptr(sdplrp_handle *h, double *p, int count);
 int32_t comm_step_R(sdplrp_handle *h, double alpha);
+
+// section timers (api.cu)
+cudaEvent_t prof_begin(sdplrp_handle *h);
+void prof_end(sdplrp_handle *h, int sec, cudaEvent_t a);
+struct SectionScope {
+    sdplrp_handle *h; int sec; cudaEvent_t a;
+    SectionScope(sdplrp_handle *h_, int sec_) : h(h_), sec(sec_), a(h_->prof ? prof_begin(h_) : nullptr) {}
+    ~SectionScope() { if (a) prof_end(h, sec, a); }
+};
 
 // scalar plumbing (api.cu)
 int32_t fetch_scalars(sdplrp_handle *h, int first, int count);  // dscal -> hscal, synchronises

@@ -196,3 +196,52 @@ def powerlaw_graph(n, target_edges, seed, exponent=2.3):
     v = np.searchsorted(cdf, rng.random(M)).astype(np.int64)
     perm = rng.permutation(n)  # hide the degree ordering in the vertex labels
     return _sym_from_edges(n, perm[np.minimum(u, n - 1)], perm[np.minimum(v, n - 1)])
+
+
+def powerlaw_maxcut_assembled(n, target_edges, seed, device=None, exponent=2.3):
+    """MaxCut on a Chung-Lu power-law graph, assembled straight into the ABI's triplet form
+    (n one-entry diagonal constraints, then C = -1/4 L in CSC `findnz` order) without scipy:
+    torch does the sampling / sort / unique, on the GPU when `device` is a CUDA device
+    (the 10M-vertex BASELINE config takes ~170 s through scipy and a few seconds this way).
+    Returns (AssembledSparse, b, normC)."""
+    import torch
+    from .types import AssembledSparse
+    dev = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    gamma = 1.0 / (exponent - 1.0)
+    i0 = max(1.0, n * 1e-5)
+    w = (torch.arange(n, dtype=torch.float64, device=dev) + i0) ** (-gamma)
+    cdf = torch.cumsum(w, 0)
+    cdf = cdf / cdf[-1]
+    M = int(target_edges * 1.03)
+    u = torch.searchsorted(cdf, torch.rand(M, dtype=torch.float64, device=dev, generator=g)).clamp_(max=n - 1)
+    v = torch.searchsorted(cdf, torch.rand(M, dtype=torch.float64, device=dev, generator=g)).clamp_(max=n - 1)
+    perm = torch.randperm(n, device=dev, generator=g)
+    u, v = perm[u], perm[v]
+    del cdf, w, perm
+    keep = u != v
+    lo, hi = torch.minimum(u, v)[keep], torch.maximum(u, v)[keep]
+    del u, v, keep
+    key = torch.unique(lo * n + hi)          # sorted, de-duplicated undirected edges
+    del lo, hi
+    lo, hi = key // n, key % n
+    E = int(key.numel())
+    deg = torch.bincount(lo, minlength=n) + torch.bincount(hi, minlength=n)
+    diag = torch.arange(n, dtype=torch.int64, device=dev)
+    # column-major keys (col * n + row) of C: both triangles plus the full diagonal
+    ck = torch.cat([hi * n + lo, lo * n + hi, diag * n + diag])
+    del key, lo, hi
+    ck, _ = torch.sort(ck)
+    col, row = ck // n, ck % n
+    del ck
+    V = torch.where(row == col, -0.25 * deg[row].to(torch.float64), torch.full((1,), 0.25, dtype=torch.float64, device=dev))
+    normC = float(torch.sqrt(torch.sum(V * V)).item())
+    I = torch.cat([diag + 1, row + 1]).cpu().numpy()
+    J = torch.cat([diag + 1, col + 1]).cpu().numpy()
+    Vh = torch.cat([torch.ones(n, dtype=torch.float64, device=dev), V]).cpu().numpy()
+    nnzC = int(V.numel())
+    mat_off = np.concatenate([np.arange(n + 1, dtype=np.int64), [n + nnzC]]).astype(np.int64)
+    gids = np.arange(1, n + 2, dtype=np.int64)
+    asm = AssembledSparse(n, n, mat_off, I, J, Vh, gids, [])
+    return asm, np.ones(n), normC, E

@@ -109,13 +109,18 @@ def pick_alpha(bq, alpha_max=1.0):
 class B200Engine:
     """SolverAuxiliary + SolverVars living on the GPU (one handle)."""
 
-    def __init__(self, data: SDPData, handle: Optional[_lib.Handle] = None, device=0):
+    def __init__(self, data: SDPData, handle: Optional[_lib.Handle] = None, device=0, asm=None):
+        """`data` needs n, m, b, constraint_types, has_inequalities (and C for the norms of
+        _sdplr); `asm` may carry triplets that were assembled elsewhere (bench: on the GPU)."""
         self.data = data
         self.h = handle if handle is not None else _lib.Handle(device=device)
         t0 = time.perf_counter()
-        asm = assemble_sparse(data)
+        if asm is None:
+            asm = assemble_sparse(data)
         self.assemble_time = time.perf_counter() - t0
+        t0 = time.perf_counter()
         self.h.preprocess(asm.n, asm.m, asm.mat_off, asm.I, asm.J, asm.V, asm.gids)
+        self.preprocess_time = time.perf_counter() - t0
         for gid1, A in asm.lowrank:
             self.h.add_symlowrank(gid1, A.B, A.D)
         self.h.set_problem(data.b, data.constraint_types.astype(np.uint8) if data.has_inequalities else None)
@@ -425,3 +430,24 @@ def sdplr(C, As, b, r, constraint_types=None, config: Optional[BurerMonteiroConf
         ans["trace"] = stats.trace
     ans["engine"] = engine
     return ans
+
+
+def run_inner_iterations(engine, k, use_armijo=False, alpha_max=1.0, update_history=True):
+    """k passes of the hot loop body of _sdplr (src/sdplr.jl:190-246) without the tolerance
+    logic: direction, descent test, line search, step, gradient, L-BFGS update.  Used by
+    bench.py and the trajectory tests.  Returns the last (L, obj, gnorm2, pnorm2, alpha)."""
+    out = None
+    for _ in range(k):
+        descent = engine.lbfgs_dir()
+        if math.isnan(descent) or descent >= 0:
+            engine.use_gradient_direction()
+        if use_armijo:
+            alpha, L_val = linesearch_armijo_(engine, alpha_max)
+        else:
+            alpha, L_val = linesearch_(engine, alpha_max)
+        obj = engine.step(alpha)
+        gn2, pn2 = engine.g()
+        if update_history:
+            engine.lbfgs_update(alpha)
+        out = (L_val, obj, gn2, pn2, alpha)
+    return out

@@ -1,0 +1,398 @@
+"""GPU parity tests: every call goes through the C ABI (libsdplrp_b200.so) and is
+compared with the CPU oracle on the same seeded inputs.
+  - preprocessing maps: bit-exact (integers AND the copied/doubled values)
+  - operators / per-iteration quantities: 1e-10 (the reference's own bar, test/coreop.jl)
+  - free-running solves: final objective within 1e-6 relative, dual bound to solver tolerance
+"""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import COMBOS, MAP_KEYS, dense_S, dense_primal_vio, families, g1_graph, k2_graph, load_golden, make_case, p3_graph
+
+pytestmark = pytest.mark.gpu
+
+FAMS = ["maxcut", "lovasz_theta", "minimum_bisection", "cutnorm", "mu_conductance_0.01", "mu_conductance_0.05", "mu_conductance_0.1"]
+
+
+@pytest.fixture(scope="module")
+def handle(gpu_handle_factory):
+    h = gpu_handle_factory()
+    yield h
+    h.close()
+
+
+def _fam(sp, fam):
+    if fam.startswith("ineq_"):
+        mu = float(fam.split("_")[1])
+        return lambda A: sp.problems.mu_conductance_ineq(A, mu)
+    return dict(families(sp))[fam]
+
+
+def _pair(sp, oracle_mod, handle, data, Rt0, r, sigma=2.0, h=4, lam0=None):
+    lam0 = np.zeros(data.m) if lam0 is None else lam0
+    ge = sp.B200Engine(data, handle=handle)
+    ge.init_vars(r, Rt0, lam0, sigma, h)
+    oe = oracle_mod.OracleEngine(data)
+    oe.init_vars(r, Rt0, lam0, sigma, h)
+    return ge, oe
+
+
+def _relclose(a, b, tol, what=""):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    scale = max(1.0, float(np.max(np.abs(b))) if b.size else 1.0)
+    err = float(np.max(np.abs(a - b))) if a.size else 0.0
+    assert err <= tol * scale, f"{what}: err {err:.3e} scale {scale:.3e}"
+
+
+# ---------------------------------------------------------------- preprocessing
+@pytest.mark.parametrize("name,graph,fam", [("k2_maxcut.json", k2_graph, "maxcut"), ("p3_lovasz.json", p3_graph, "lovasz_theta")])
+def test_golden_maps_gpu(sp, handle, name, graph, fam):
+    gold = load_golden(name)
+    C, As, bs = getattr(sp.problems, fam)(graph())
+    eng = sp.B200Engine(sp.SDPData(C, As, bs), handle=handle)
+    assert handle.pattern_sizes() == (gold["nnzT"], gold["nnzF"], gold["Ec"])
+    maps = handle.pattern_export()
+    for k in MAP_KEYS:
+        np.testing.assert_array_equal(maps[k], np.array(gold[k]), err_msg=k)
+
+
+@pytest.mark.parametrize("fam", FAMS + ["ineq_0.05"])
+@pytest.mark.parametrize("seed,n,p,r", COMBOS[::3])
+def test_maps_bit_exact_small(sp, oracle_mod, handle, fam, seed, n, p, r):
+    data, Rt0, _ = make_case(sp, _fam(sp, fam), seed, n, p, r)
+    asm = sp.assemble_sparse(data)
+    o = oracle_mod.Oracle(asm, data.b)
+    sp.B200Engine(data, handle=handle)
+    assert handle.pattern_sizes() == o.pattern_sizes()
+    mg, mo = handle.pattern_export(), o.pattern_export()
+    for k in MAP_KEYS:
+        np.testing.assert_array_equal(mg[k], mo[k], err_msg=k)
+
+
+@pytest.mark.parametrize("which", ["g1_maxcut", "er_lovasz", "bisect", "cutnorm", "dup_coo"])
+def test_maps_bit_exact_medium(sp, oracle_mod, handle, which):
+    P = sp.problems
+    if which == "g1_maxcut":
+        C, As, bs = P.maxcut(g1_graph())
+    elif which == "er_lovasz":
+        C, As, bs = P.lovasz_theta(P.erdos_renyi(600, 0.02, 2))
+    elif which == "bisect":
+        C, As, bs = P.minimum_bisection(P.erdos_renyi(3000, 0.003, 3))
+    elif which == "cutnorm":
+        import scipy.sparse as sps
+        A = sps.random(300, 200, density=0.05, random_state=4, data_rvs=np.random.default_rng(4).standard_normal, format="csc")
+        C, As, bs = P.cutnorm(A)
+    else:  # COO with duplicate coordinates and an empty matrix: every entry keeps its own nzind slot
+        import scipy.sparse as sps
+        n = 50
+        rng = np.random.default_rng(9)
+        G = P.erdos_renyi(n, 0.2, 9)
+        C = sps.csc_matrix(G * 0.5 + sps.identity(n))
+        i = rng.integers(0, n, 40); j = rng.integers(0, n, 40)
+        dup = sp.SparseMatrixCOO(np.concatenate([i, j, i]), np.concatenate([j, i, j]), rng.standard_normal(120), n)
+        empty = sp.SparseMatrixCOO([], [], [], n)
+        As = [dup, empty, sp.Diagonal(rng.standard_normal(n)), sp.SparseMatrixCOO([3, 3], [3, 3], [1.0, 2.0], n)]
+        # make `dup` symmetric in storage: add mirrored copies
+        dup.rows, dup.cols = np.concatenate([dup.rows, dup.cols]), np.concatenate([dup.cols, dup.rows[:120]])
+        dup.vals = np.concatenate([dup.vals, dup.vals])
+        bs = np.zeros(4)
+    data = sp.SDPData(C, As, bs)
+    asm = sp.assemble_sparse(data)
+    o = oracle_mod.Oracle(asm, data.b)
+    sp.B200Engine(data, handle=handle)
+    assert handle.pattern_sizes() == o.pattern_sizes()
+    mg, mo = handle.pattern_export(), o.pattern_export()
+    for k in MAP_KEYS:
+        np.testing.assert_array_equal(mg[k], mo[k], err_msg=k)
+
+
+def test_asymmetric_storage_error(sp, handle):
+    import scipy.sparse as sps
+    n = 3
+    bad = sp.SparseMatrixCOO([2], [0], [1.0], n)
+    data = sp.SDPData(sps.csc_matrix(np.eye(n)), [bad], np.zeros(1))
+    asm = sp.assemble_sparse(data)
+    with pytest.raises(sp.SdplrpError) as e:
+        handle.preprocess(asm.n, asm.m, asm.mat_off, asm.I, asm.J, asm.V, asm.gids)
+    assert e.value.code == -4
+    rc = handle.preprocess(asm.n, asm.m, asm.mat_off, asm.I, asm.J, asm.V, asm.gids, allow_asymmetric=True)
+    assert rc == -4 and (handle.pattern_export()["mapped"] == 0).sum() == 1
+
+
+def test_bad_arguments(sp, handle):
+    with pytest.raises(sp.SdplrpError):
+        handle.preprocess(3, 1, [0, 1], [5], [1], [1.0], [1])       # row 5 outside 1..3
+    with pytest.raises(sp.SdplrpError):
+        handle.preprocess(3, 1, [0, 1], [1], [1], [1.0], [7])       # global id outside 1..m+1
+
+
+# ---------------------------------------------------------------- operators (test/coreop.jl design)
+@pytest.mark.parametrize("fam", FAMS)
+@pytest.mark.parametrize("seed,n,p,r", COMBOS)
+def test_f_g_linesearch_gpu(sp, oracle_mod, handle, fam, seed, n, p, r):
+    data, Rt0, rng = make_case(sp, _fam(sp, fam), seed, n, p, r)
+    ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, r)
+    Lg, objg = ge.f(); Lo, objo = oe.f()
+    ref = dense_primal_vio(data, Rt0)
+    assert np.max(np.abs(ge.get_pvio_raw() - ref)) < 1e-10          # test/coreop.jl:58-61
+    _relclose(ge.get_pvio_raw(), oe.get_pvio_raw(), 1e-12, "pvio_raw vs oracle")
+    _relclose([Lg, objg], [Lo, objo], 1e-12, "L,obj")
+    g2, p2 = ge.g(); og2, op2 = oe.g()
+    _relclose(ge.get_G(), oe.get_G(), 1e-12, "G")
+    _relclose([g2, p2], [og2, op2], 1e-11, "norms")
+    _relclose(ge.get_y(), oe.get_y(), 1e-13, "y")
+    # line search along -G, then incremental residuals vs a dense recomputation (test/coreop.jl:65-72)
+    D = -oe.get_G()
+    ge.set_D(D); oe.set_D(D)
+    bqg, bqo = ge.linesearch_coeffs(), oe.linesearch_coeffs()
+    _relclose(bqg, bqo, 1e-11, "quartic coefficients")
+    _relclose(handle.download_vec(sp._lib.VEC_A_RD, data.m + 1), oe.o.view("A_RD"), 1e-12, "A_RD")
+    _relclose(handle.download_vec(sp._lib.VEC_A_DD, data.m + 1), oe.o.view("A_DD"), 1e-12, "A_DD")
+    alpha, _ = sp.pick_alpha(bqo, 1.0)
+    ge.step(alpha); oe.step(alpha)
+    Rnew = Rt0 + alpha * D
+    assert np.max(np.abs(ge.get_R() - Rnew)) < 1e-13
+    assert np.max(np.abs(ge.get_pvio_raw() - dense_primal_vio(data, Rnew))) < 1e-10
+
+
+@pytest.mark.parametrize("mu", [0.01, 0.05, 0.1])
+@pytest.mark.parametrize("seed,n,p,r", COMBOS[::2])
+def test_inequalities_gpu(sp, oracle_mod, handle, mu, seed, n, p, r):
+    data, Rt0, rng = make_case(sp, lambda A: sp.problems.mu_conductance_ineq(A, mu), seed, n, p, r)
+    lam0 = -np.abs(rng.standard_normal(data.m)) * 0.1
+    lam0[:2] = rng.standard_normal(2)
+    ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, r, lam0=lam0)
+    outg, outo = ge.fg(), oe.fg()
+    _relclose(outg, outo, 1e-11, "fg with inequalities")
+    pv = dense_primal_vio(data, Rt0)
+    assert np.max(np.abs(ge.get_pvio_raw() - pv)) < 1e-10
+    cap = pv[: data.m].copy(); cap[data.constraint_types] = np.maximum(cap[data.constraint_types], 0.0)
+    assert abs(outg[3] - cap @ cap) <= 1e-10 * max(1.0, cap @ cap)   # test/coreop.jl:107-112 via the norm
+    _relclose(ge.get_G(), oe.get_G(), 1e-12, "G ineq")
+    # Armijo evaluation of the sharp AL
+    D = -oe.get_G(); ge.set_D(D); oe.set_D(D)
+    ge.linesearch_coeffs(); oe.linesearch_coeffs()
+    alphas = 1.0 / 2.0 ** np.arange(20)
+    Lg, sg = ge.armijo_eval(alphas); Lo, so = oe.armijo_eval(alphas)
+    _relclose(Lg, Lo, 1e-11, "armijo L"); _relclose([sg], [so], 1e-11, "armijo slope")
+    ag, _ = sp.linesearch_armijo_(ge); ao, _ = sp.linesearch_armijo_(oe)
+    assert ag == ao
+
+
+@pytest.mark.parametrize("fam", ["maxcut", "lovasz_theta", "minimum_bisection", "mu_conductance_0.05", "ineq_0.05"])
+@pytest.mark.parametrize("seed,n,p,r", COMBOS)
+def test_adjoint_gpu(sp, oracle_mod, handle, fam, seed, n, p, r):
+    data, Rt0, rng = make_case(sp, _fam(sp, fam), seed, n, p, r)
+    ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, r)
+    y = np.random.default_rng(seed + 100).standard_normal(data.m + 1)
+    handle.At_preprocess(y)
+    S = dense_S(data, y)
+    nnzT, nnzF, _ = handle.pattern_sizes()
+    oe.o.At_preprocess(y)
+    _relclose(handle.download_vec(sp._lib.VEC_S_NZVAL, nnzF), oe.o.view("S", nnzF), 1e-14, "S.nzval")
+    _relclose(handle.download_vec(sp._lib.VEC_TRIUS_NZVAL, nnzT), oe.o.view("triuS", nnzT), 1e-14, "triuS.nzval")
+    handle.At_left(sp._lib.MAT_R, sp._lib.MAT_W0)
+    Yl = handle.download_mat(sp._lib.MAT_W0)
+    assert np.max(np.abs(Yl - (Rt0.T @ S).T)) < 1e-10                 # test/coreop.jl:160-165
+    x = rng.standard_normal((data.n, r))
+    assert np.max(np.abs(handle.At_right(x) - S @ x)) < 1e-10         # :167-172
+    assert np.max(np.abs(handle.At_right(x[:, 0]) - S @ x[:, 0])) < 1e-10
+    # second y with a different objective coefficient (exercises the static/dynamic split of S)
+    y2 = y.copy(); y2[-1] = -0.37; y2[:3] += 1.0
+    handle.At_preprocess(y2)
+    handle.At_left(sp._lib.MAT_R, sp._lib.MAT_W0)
+    assert np.max(np.abs(handle.download_mat(sp._lib.MAT_W0) - (Rt0.T @ dense_S(data, y2)).T)) < 1e-10
+
+
+@pytest.mark.parametrize("fam", ["maxcut", "lovasz_theta", "minimum_bisection"])
+def test_A_uv_seam(sp, oracle_mod, handle, fam):
+    data, Rt0, rng = make_case(sp, _fam(sp, fam), 3, 12, 0.4, 4)
+    ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, 4)
+    V = rng.standard_normal(Rt0.shape)
+    handle.upload_mat(sp._lib.MAT_W1, V)
+    _relclose(handle.A_uu(sp._lib.MAT_R), oe.o.A_uu(Rt0), 1e-13, "A_uu")
+    _relclose(handle.A_uv(sp._lib.MAT_R, sp._lib.MAT_W1), oe.o.A_uv(Rt0, V), 1e-13, "A_uv")
+    _relclose(handle.A_uv(sp._lib.MAT_W1, sp._lib.MAT_W1), oe.o.A_uu(V), 1e-13, "A_uv(V,V) == A_uu(V)")
+
+
+@pytest.mark.parametrize("r", [1, 2, 3, 5, 8, 10, 12, 16, 20, 33, 40, 70])
+def test_rank_sweep(sp, oracle_mod, handle, r):
+    """runtime rank (dynamic rank doubling, src/sdplr.jl:373-382): odd/even, small/large r"""
+    P = sp.problems
+    C, As, bs = P.minimum_bisection(P.erdos_renyi(120, 0.08, 11))
+    data = sp.SDPData(C, As, bs)
+    Rt0 = 2 * np.random.default_rng(r).random((data.n, r)) - 1
+    ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, r)
+    _relclose(ge.fg(), oe.fg(), 1e-11, "fg")
+    _relclose(ge.get_G(), oe.get_G(), 1e-12, "G")
+    D = -oe.get_G(); ge.set_D(D); oe.set_D(D)
+    _relclose(ge.linesearch_coeffs(), oe.linesearch_coeffs(), 1e-11, "bq")
+
+
+# ---------------------------------------------------------------- L-BFGS
+@pytest.mark.parametrize("hist", [0, 1, 2, 4, 7])
+def test_lbfgs_teacher_forced(sp, oracle_mod, handle, hist):
+    """lbfgs_dir!/lbfgs_update! against the literal two-loop: at every step both sides are fed the
+    oracle's G, then directions must agree to 1e-10 relative (north_star parity bar)."""
+    P = sp.problems
+    C, As, bs = P.maxcut(P.erdos_renyi(200, 0.05, 5))
+    data = sp.SDPData(C, As, bs)
+    r = 6
+    Rt0 = 2 * np.random.default_rng(1).random((data.n, r)) - 1
+    ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, r, h=hist)
+    ge.fg(); oe.fg()
+    for it in range(3 * max(hist, 1) + 2):
+        handle.upload_mat(sp._lib.MAT_G, oe.get_G())
+        dg, do = ge.lbfgs_dir(), oe.lbfgs_dir()
+        Dg, Do = ge.get_D(), oe.get_D()
+        nrm = np.linalg.norm(Do)
+        assert np.linalg.norm(Dg - Do) <= 1e-10 * nrm, f"direction it={it}"
+        assert abs(dg - do) <= 1e-10 * max(1.0, abs(do))
+        ge.set_D(Do)
+        bq = oe.linesearch_coeffs(); ge.linesearch_coeffs()
+        alpha, _ = sp.pick_alpha(bq, 1.0)
+        ge.step(alpha); oe.step(alpha)
+        ge.set_R(oe.get_R())
+        ge.g(); oe.g()
+        handle.upload_mat(sp._lib.MAT_G, oe.get_G())
+        ge.lbfgs_update(alpha); oe.lbfgs_update(alpha)
+        if hist:
+            j = oe.lib.orc_lbfgs_latest(oe.o.ctx) - 1
+            N = data.n * r
+            so = np.ctypeslib.as_array(oe.lib.orc_lbfgs_ptr(oe.o.ctx, 0, j), shape=(N,))
+            yo = np.ctypeslib.as_array(oe.lib.orc_lbfgs_ptr(oe.o.ctx, 1, j), shape=(N,))
+            _relclose(handle.download_mat(sp._lib.MAT_S0 + j).reshape(-1), so, 1e-13, "s_j")
+            _relclose(handle.download_mat(sp._lib.MAT_Y0 + j).reshape(-1), yo, 1e-13, "y_j")
+    if hist:
+        ge.lbfgs_clear()
+        assert not handle.download_mat(sp._lib.MAT_S0).any() and not handle.download_mat(sp._lib.MAT_Y0 + hist - 1).any()
+
+
+def test_nondescent_fallback(sp, oracle_mod, handle):
+    P = sp.problems
+    C, As, bs = P.maxcut(P.erdos_renyi(60, 0.1, 6))
+    data = sp.SDPData(C, As, bs)
+    Rt0 = 2 * np.random.default_rng(2).random((data.n, 4)) - 1
+    ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, 4)
+    ge.fg(); oe.fg()
+    G = oe.get_G()
+    ge.use_gradient_direction(); oe.use_gradient_direction()
+    np.testing.assert_array_equal(ge.get_G(), -G)                      # src/sdplr.jl:203-204 negates Gt in place
+    np.testing.assert_array_equal(ge.get_D(), -G)
+
+
+# ---------------------------------------------------------------- per-iteration trajectories
+@pytest.mark.parametrize("which", ["g1", "lovasz", "bisect", "cutnorm"])
+def test_free_running_first_iterations(sp, oracle_mod, handle, which):
+    """Free-running inner iterations from the same R0: objective / residual norm / AL agree to 1e-10
+    relative over the first iterations (hard part 4)."""
+    P = sp.problems
+    if which == "g1":
+        C, As, bs = P.maxcut(g1_graph()); r = 10
+    elif which == "lovasz":
+        C, As, bs = P.lovasz_theta(P.erdos_renyi(300, 0.03, 2)); r = 8
+    elif which == "bisect":
+        C, As, bs = P.minimum_bisection(P.erdos_renyi(1000, 0.01, 3)); r = 10
+    else:
+        import scipy.sparse as sps
+        A = sps.random(200, 200, density=0.05, random_state=4, data_rvs=np.random.default_rng(4).standard_normal, format="csc")
+        C, As, bs = P.cutnorm(A); r = 10
+    data = sp.SDPData(C, As, bs)
+    Rt0 = 2 * np.random.default_rng(0).random((data.n, r)) - 1
+    ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, r)
+    fg_g, fg_o = ge.fg(), oe.fg()
+    _relclose(fg_g, fg_o, 1e-11, "fg0")
+    for it in range(40):
+        dg, do = ge.lbfgs_dir(), oe.lbfgs_dir()
+        assert abs(dg - do) <= 1e-9 * max(1.0, abs(do)), f"descent it={it}"
+        bqg, bqo = ge.linesearch_coeffs(), oe.linesearch_coeffs()
+        ag, Lg = sp.pick_alpha(bqg, 1.0); ao, Lo = sp.pick_alpha(bqo, 1.0)
+        objg, objo = ge.step(ag), oe.step(ao)
+        (g2, p2), (og2, op2) = ge.g(), oe.g()
+        assert abs(objg - objo) <= 1e-10 * max(1.0, abs(objo)), f"obj it={it}"
+        assert abs(Lg - Lo) <= 1e-10 * max(1.0, abs(Lo)), f"L it={it}"
+        assert abs(math.sqrt(p2) - math.sqrt(op2)) <= 1e-10 * max(1.0, math.sqrt(op2)), f"pnorm it={it}"
+        assert abs(math.sqrt(g2) - math.sqrt(og2)) <= 1e-8 * max(1.0, math.sqrt(og2)), f"gnorm it={it}"
+        ge.lbfgs_update(ag); oe.lbfgs_update(ao)
+
+
+# ---------------------------------------------------------------- Lanczos / dual bound
+@pytest.mark.parametrize("fam", ["maxcut", "lovasz_theta", "minimum_bisection"])
+def test_lanczos_and_dual(sp, oracle_mod, handle, fam):
+    P = sp.problems
+    G = P.erdos_renyi(400, 0.03, 8)
+    C, As, bs = getattr(P, fam)(G)
+    data = sp.SDPData(C, As, bs)
+    r = 6
+    Rt0 = 2 * np.random.default_rng(0).random((data.n, r)) - 1
+    ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, r)
+    ge.fg(); oe.fg()
+    v0 = np.random.default_rng(1).standard_normal(data.n)
+    q = 30
+    ag, bg, itg = handle.lanczos(q, v0)
+    lam_o, ao, bo, ito = oe.o.lanczos(q, v0)
+    assert itg == ito
+    # early coefficients agree tightly; later ones drift with Lanczos' loss of orthogonality
+    _relclose(ag[:8], ao[:8], 1e-9, "alpha"); _relclose(bg[:8], bo[:8], 1e-9, "beta")
+    lam_g = sp.tridiag_mineig(ag[:itg] + 1.0, bg[: itg - 1]) - 1.0
+    assert abs(lam_g - lam_o) <= 1e-6 * max(1.0, abs(lam_o))
+    # exact tridiagonal eigenvalue vs LAPACK
+    T = np.diag(ag[:itg]) + np.diag(bg[: itg - 1], 1) + np.diag(bg[: itg - 1], -1)
+    assert abs(sp.tridiag_mineig(ag[:itg], bg[: itg - 1]) - np.linalg.eigvalsh(T)[0]) < 1e-10 * max(1, abs(T).max())
+    dg, eg, sg = ge.dual_obj(float(data.n), 150, v0)
+    do, eo, so = oe.dual_obj(float(data.n), 150, v0)
+    assert sg == so
+    assert abs(eg - eo) <= 1e-4 * max(1.0, abs(eo)) and abs(dg - do) <= 1e-4 * max(1.0, abs(do))
+    # device RNG path + full re-orthogonalisation: converged Ritz value equals the true smallest eigenvalue
+    a2, b2, it2 = handle.lanczos(120, None, seed=7, reorth=True)
+    lam_ro = sp.tridiag_mineig(a2[:it2], b2[: it2 - 1])
+    nnzT, nnzF, _ = handle.pattern_sizes()
+    Sd = dense_S(data, ge.get_y())
+    assert abs(lam_ro - np.linalg.eigvalsh(Sd)[0]) <= 1e-6 * max(1.0, abs(lam_ro))
+
+
+# ---------------------------------------------------------------- end-to-end solves
+def test_k2_known_answers_gpu(sp, handle):
+    C, As, bs = sp.problems.maxcut(k2_graph())
+    fac = lambda data: sp.B200Engine(data, handle=handle)
+    res = sp.sdplr(C, As, bs, 1, engine_factory=fac, printlevel=0, fprec=0.0, gtol=1e-8, objtol=1e-8, ptol=1e-8, prior_trace_bound=2.0)
+    assert res["obj"] == pytest.approx(-1.0, rel=1e-7)                 # test/maxcut.jl:24
+    res = sp.sdplr(C, As, bs, 1, engine_factory=fac, printlevel=0, sigma_0=10.0, fprec=0.0, gtol=1e-8, objtol=1e-8, ptol=1e-8,
+                   prior_trace_bound=2.0)
+    assert res["obj"] == pytest.approx(-1.0, rel=1e-7)                 # test/maxcut.jl:47
+    C, As, bs = sp.problems.minimum_bisection(k2_graph())
+    res = sp.sdplr(C, As, bs, 1, engine_factory=fac, printlevel=0, fprec=0.0, objtol=1e-4, ptol=1e-4, prior_trace_bound=2.0)
+    assert (res["obj"] - 1) / (1 + abs(res["obj"])) < 1e-4             # test/minimumbisection.jl:22
+
+
+@pytest.mark.parametrize("which", ["g1_maxcut", "lovasz", "bisect", "cutnorm", "ineq"])
+def test_full_solve_matches_oracle(sp, oracle_mod, handle, which):
+    """Free-running full solve: same discrete decisions, final objective within 1e-6 relative,
+    dual bound to solver tolerance (north_star correctness bar)."""
+    P = sp.problems
+    kw = dict(printlevel=0, seed=0)
+    types = None
+    if which == "g1_maxcut":
+        C, As, bs = P.maxcut(g1_graph()); r = 10; kw["prior_trace_bound"] = 800.0
+    elif which == "lovasz":
+        C, As, bs = P.lovasz_theta(P.erdos_renyi(200, 0.05, 2)); r = 10; kw["prior_trace_bound"] = 1.0
+    elif which == "bisect":
+        G = P.erdos_renyi(500, 0.02, 3); C, As, bs = P.minimum_bisection(G); r = 10; kw["prior_trace_bound"] = 500.0
+    elif which == "cutnorm":
+        import scipy.sparse as sps
+        A = sps.random(150, 150, density=0.05, random_state=4, data_rvs=np.random.default_rng(4).standard_normal, format="csc")
+        C, As, bs = P.cutnorm(A); r = 10; kw["prior_trace_bound"] = 300.0
+    else:
+        C, As, bs, types = P.mu_conductance_ineq(P.erdos_renyi(60, 0.15, 5), 0.05); r = 5
+        kw.update(objtol=math.inf, ptol=1e-3, maxmajoriter=40)
+    rg = sp.sdplr(C, As, bs, r, constraint_types=types, engine_factory=lambda d: sp.B200Engine(d, handle=handle), **kw)
+    ro = sp.sdplr(C, As, bs, r, constraint_types=types, engine_factory=oracle_mod.OracleEngine, **kw)
+    assert rg["majoriter"] == ro["majoriter"]
+    assert abs(rg["iter"] - ro["iter"]) <= max(2, 0.02 * ro["iter"])
+    assert abs(rg["obj"] - ro["obj"]) <= 1e-6 * max(1.0, abs(ro["obj"]))
+    assert rg["primal_vio"] <= max(kw.get("ptol", 1e-2), 1.05 * ro["primal_vio"] + 1e-12)
+    if math.isfinite(kw.get("objtol", 1e-2)):
+        assert abs(rg["max_dual_value"] - ro["max_dual_value"]) <= 1e-4 * max(1.0, abs(ro["max_dual_value"]))
+        assert rg["min_duality_gap"] <= 1e-2

@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(TPB) k_lr_proj(i64 n, int r, int s, const doub
         }
     }
     __shared__ bool is_last;
+    __threadfence();  // every writer publishes its partials before the ticket is taken
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();

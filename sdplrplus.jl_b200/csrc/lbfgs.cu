@@ -88,15 +88,16 @@ __global__ void __launch_bounds__(TPB) k_two_loop(i64 nu, const double *in, cons
     grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { dot_out[0] = s[0]; });
 }
 
-// h == 0: dir = -grad, descent = -||grad||^2
+// numlbfgsvecs == 0: the reference returns right after copyto!(dir, grad) (src/lbfgs.jl:84-90),
+// i.e. dir = +grad and descent = ||grad||^2 >= 0, which then takes the fallback of src/sdplr.jl:202-205
 template <int VEC>
-__global__ void __launch_bounds__(TPB) k_neg_dir(i64 nu, const double *__restrict__ grad, double *__restrict__ dir,
+__global__ void __launch_bounds__(TPB) k_copy_dir(i64 nu, const double *__restrict__ grad, double *__restrict__ dir,
                                                  double *partials, unsigned *ticket, double *dot_out) {
     double acc[1] = {0.0};
     GRID_STRIDE(i, nu) {
         typename V<VEC>::T g = V<VEC>::ld(grad, i);
-        V<VEC>::st(dir, i, V<VEC>::neg(g));
-        acc[0] -= V<VEC>::dot(g, g);
+        V<VEC>::st(dir, i, g);
+        acc[0] += V<VEC>::dot(g, g);
     }
     grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { dot_out[0] = s[0]; });
 }
@@ -185,7 +186,7 @@ int32_t lb_dir(sdplrp_handle *h) {
     double *dir = h->D + sl.off;
     double *descent = h->dscal + SC_DESCENT;
     if (m == 0) {
-        DISPATCH_VEC(sl, k_neg_dir, sl.nu, grad, dir, h->partials, h->ticket, descent);
+        DISPATCH_VEC(sl, k_copy_dir, sl.nu, grad, dir, h->partials, h->ticket, descent);
         CUDA_TRY(h, cudaGetLastError());
         return comm_reduce_ptr(h, descent, 1);
     }

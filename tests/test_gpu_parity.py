@@ -277,10 +277,11 @@ def test_nondescent_fallback(sp, oracle_mod, handle):
     Rt0 = 2 * np.random.default_rng(2).random((data.n, 4)) - 1
     ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, 4)
     ge.fg(); oe.fg()
-    G = oe.get_G()
+    G = ge.get_G()
     ge.use_gradient_direction(); oe.use_gradient_direction()
     np.testing.assert_array_equal(ge.get_G(), -G)                      # src/sdplr.jl:203-204 negates Gt in place
     np.testing.assert_array_equal(ge.get_D(), -G)
+    _relclose(ge.get_D(), oe.get_D(), 1e-12, "fallback direction")
 
 
 # ---------------------------------------------------------------- per-iteration trajectories

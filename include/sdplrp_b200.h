@@ -191,14 +191,15 @@ enum {
     SDPLRP_SEC_LS_COEFF = 2,     /* quartic-coefficient reduction */
     SDPLRP_SEC_STEP = 3,         /* residual recurrence + R += alpha*D */
     SDPLRP_SEC_S_ASSEMBLE = 4,   /* y formation + S update */
-    SDPLRP_SEC_SPMM = 5,         /* G = 2*S*R (+ low rank) */
+    SDPLRP_SEC_SPMM = 5,         /* CD = C*D (objective gather pass with the fused line-search dots), CR rebuilds */
     SDPLRP_SEC_NORMS = 6,        /* ||G||^2, ||pvio||^2 */
     SDPLRP_SEC_LBFGS_UPDATE = 7,
     SDPLRP_SEC_A_UU = 8,         /* A(RR') of f! */
     SDPLRP_SEC_F_FINISH = 9,
     SDPLRP_SEC_LANCZOS = 10,
     SDPLRP_SEC_COMM = 11,        /* NCCL collectives */
-    SDPLRP_SEC_COUNT = 12
+    SDPLRP_SEC_GRAD = 12,        /* G = 2*(y_obj*CR + S_dyn*R + low rank) with ||G||^2 fused */
+    SDPLRP_SEC_COUNT = 13
 };
 /* on != 0: record a CUDA-event pair around every section from now on */
 int32_t sdplrp_set_profiling(sdplrp_handle *h, int32_t on);

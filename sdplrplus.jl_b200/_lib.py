@@ -362,7 +362,7 @@ class Handle:
         return d.value, e.value, s.value
 
     SECTIONS = ["lbfgs_dir", "ls_pass", "ls_coeff", "step", "s_assemble", "spmm", "norms", "lbfgs_update", "a_uu", "f_finish",
-                "lanczos", "comm"]
+                "lanczos", "comm", "grad"]
 
     def set_profiling(self, on):
         self._check(self.lib.sdplrp_set_profiling(self._h, int(bool(on))))

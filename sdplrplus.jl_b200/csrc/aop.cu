@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(TPB) k_A_short(int nA, const int *__restrict__
                                                  const int *__restrict__ ent_row, const int *__restrict__ ent_col,
                                                  const double *__restrict__ ent_two, const double *__restrict__ U,
                                                  const double *__restrict__ V, int r, int G, double *__restrict__ out1,
-                                                 double *__restrict__ out2, int own_lo, int own_hi) {
+                                                 double *__restrict__ out2, int own_lo, int own_hi, int skip_mat) {
     const int nv = r / VEC;
     const int lg = threadIdx.x & (G - 1);
     const int gpw = 32 / G;  // groups per warp
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(TPB) k_A_short(int nA, const int *__restrict__
         int gid = 0;
         if (a < nA) {
             const int beg = matptr[a], end = matptr[a + 1];
-            if (end - beg <= kLongMatThreshold) {
+            if (end - beg <= kLongMatThreshold && a != skip_mat) {
                 store = true;
                 gid = mat_gid[a];
                 for (int k = beg; k < end; k++)
@@ -129,10 +129,11 @@ __global__ void __launch_bounds__(TPB) k_A_long(const int *__restrict__ chunk_ma
                                                 const int *__restrict__ ent_row, const int *__restrict__ ent_col,
                                                 const double *__restrict__ ent_two, const double *__restrict__ U,
                                                 const double *__restrict__ V, int r, int G, double *__restrict__ chunk_part,
-                                                int own_lo, int own_hi) {
+                                                int own_lo, int own_hi, int skip_mat) {
     const int c = blockIdx.x;
     const int l = chunk_mat[c];
     const int a = long_mat[l];
+    if (a == skip_mat) return;  // the objective is handled by the CD = C*D pass
     const int beg = matptr[a] + (c - long_chunk_ptr[l]) * kChunkEntries;
     const int end = min(beg + kChunkEntries, matptr[a + 1]);
     const int nv = r / VEC;
@@ -152,8 +153,9 @@ __global__ void __launch_bounds__(TPB) k_A_long(const int *__restrict__ chunk_ma
 template <int MODE>
 __global__ void __launch_bounds__(TPB) k_A_long_combine(const int *__restrict__ long_mat, const int *__restrict__ long_chunk_ptr,
                                                         const int *__restrict__ mat_gid, const double *__restrict__ chunk_part,
-                                                        double *__restrict__ out1, double *__restrict__ out2) {
+                                                        double *__restrict__ out1, double *__restrict__ out2, int skip_mat) {
     const int l = blockIdx.x;
+    if (long_mat[l] == skip_mat) return;
     double acc[2] = {0.0, 0.0};
     for (int c = long_chunk_ptr[l] + threadIdx.x; c < long_chunk_ptr[l + 1]; c += TPB) {
         acc[0] += chunk_part[2 * (size_t)c];
@@ -233,7 +235,7 @@ int pick_group(int nv) {
 }
 
 template <int MODE>
-int32_t run_sparse(sdplrp_handle *h, const double *U, const double *V, double *out1, double *out2) {
+int32_t run_sparse(sdplrp_handle *h, const double *U, const double *V, double *out1, double *out2, int skip_mat = -1) {
     if (h->nA <= 0) return SDPLRP_OK;
     cudaStream_t st = h->stream;
     const int r = h->r;
@@ -243,14 +245,14 @@ int32_t run_sparse(sdplrp_handle *h, const double *U, const double *V, double *o
     const int gpb = TPB / G;
     const int grid_short = grid_for(h->nA, gpb, 16 * kNumSM);
     const int lo = (int)h->row_lo, hi = (int)h->row_hi;
-    if (vec2) k_A_short<MODE, 2><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi);
-    else k_A_short<MODE, 1><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi);
+    if (vec2) k_A_short<MODE, 2><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi, skip_mat);
+    else k_A_short<MODE, 1><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi, skip_mat);
     KLAUNCH(h);
     if (h->n_chunks > 0) {
-        if (vec2) k_A_long<MODE, 2><<<(int)h->n_chunks, TPB, 0, st>>>(h->chunk_mat, h->long_mat, h->long_chunk_ptr, h->matptr, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, h->chunk_part, lo, hi);
-        else k_A_long<MODE, 1><<<(int)h->n_chunks, TPB, 0, st>>>(h->chunk_mat, h->long_mat, h->long_chunk_ptr, h->matptr, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, h->chunk_part, lo, hi);
+        if (vec2) k_A_long<MODE, 2><<<(int)h->n_chunks, TPB, 0, st>>>(h->chunk_mat, h->long_mat, h->long_chunk_ptr, h->matptr, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, h->chunk_part, lo, hi, skip_mat);
+        else k_A_long<MODE, 1><<<(int)h->n_chunks, TPB, 0, st>>>(h->chunk_mat, h->long_mat, h->long_chunk_ptr, h->matptr, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, h->chunk_part, lo, hi, skip_mat);
         KLAUNCH(h);
-        k_A_long_combine<MODE><<<(int)h->n_long, TPB, 0, st>>>(h->long_mat, h->long_chunk_ptr, h->mat_gid, h->chunk_part, out1, out2);
+        k_A_long_combine<MODE><<<(int)h->n_long, TPB, 0, st>>>(h->long_mat, h->long_chunk_ptr, h->mat_gid, h->chunk_part, out1, out2, skip_mat);
         KLAUNCH(h);
     }
     CUDA_TRY(h, cudaGetLastError());
@@ -309,11 +311,13 @@ static int32_t run_lowrank(sdplrp_handle *h, int mode, const double *U, const do
     return SDPLRP_OK;
 }
 
-int32_t aop_uu(sdplrp_handle *h, const double *U, double *out) {
+int32_t aop_uu_skip(sdplrp_handle *h, const double *U, double *out, bool skip_objective) {
     CUDA_TRY(h, cudaMemsetAsync(out, 0, (size_t)(h->m + 1) * sizeof(double), h->stream));
-    SDP_CHECK(run_sparse<0>(h, U, nullptr, out, nullptr));
+    SDP_CHECK(run_sparse<0>(h, U, nullptr, out, nullptr, skip_objective ? h->obj_mat : -1));
     return run_lowrank(h, 0, U, nullptr, out, nullptr);
 }
+
+int32_t aop_uu(sdplrp_handle *h, const double *U, double *out) { return aop_uu_skip(h, U, out, false); }
 
 int32_t aop_uv(sdplrp_handle *h, const double *U, const double *V, double *out) {
     CUDA_TRY(h, cudaMemsetAsync(out, 0, (size_t)(h->m + 1) * sizeof(double), h->stream));
@@ -321,9 +325,9 @@ int32_t aop_uv(sdplrp_handle *h, const double *U, const double *V, double *out) 
     return run_lowrank(h, 1, U, V, out, nullptr);
 }
 
-int32_t aop_linesearch(sdplrp_handle *h) {
+int32_t aop_linesearch(sdplrp_handle *h, bool skip_objective) {
     CUDA_TRY(h, cudaMemsetAsync(h->A_RD, 0, (size_t)(h->m + 1) * sizeof(double), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->A_DD, 0, (size_t)(h->m + 1) * sizeof(double), h->stream));
-    SDP_CHECK(run_sparse<2>(h, h->R, h->D, h->A_RD, h->A_DD));
+    SDP_CHECK(run_sparse<2>(h, h->R, h->D, h->A_RD, h->A_DD, skip_objective ? h->obj_mat : -1));
     return run_lowrank(h, 2, h->R, h->D, h->A_RD, h->A_DD);
 }

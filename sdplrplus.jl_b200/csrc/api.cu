@@ -132,6 +132,8 @@ int32_t sdplrp_create(int32_t device, int32_t rank, int32_t world, const void *n
 
 static void free_state(sdplrp_handle *h) {
     dev_free(&h->R); dev_free(&h->G); dev_free(&h->D); dev_free(&h->W0); dev_free(&h->W1);
+    dev_free(&h->CR); dev_free(&h->CD);
+    h->CR_valid = h->CD_valid = false;
     for (int j = 0; j < kMaxHist; j++) { dev_free(&h->Sh[j]); dev_free(&h->Yh[j]); }
     dev_free(&h->lr_tmp); h->lr_tmp_len = 0;
     h->r = 0; h->hist = 0;
@@ -262,6 +264,7 @@ int32_t sdplrp_set_rank(sdplrp_handle *h, int32_t r, int32_t numlbfgsvecs) {
     free_state(h);
     const i64 N = h->n * (i64)r;
     SDP_CHECK(dev_alloc(h, &h->R, N)); SDP_CHECK(dev_alloc(h, &h->G, N)); SDP_CHECK(dev_alloc(h, &h->D, N));
+    if (h->obj_mat >= 0) { SDP_CHECK(dev_alloc(h, &h->CR, N)); SDP_CHECK(dev_alloc(h, &h->CD, N)); }
     for (int j = 0; j < numlbfgsvecs; j++) { SDP_CHECK(dev_alloc(h, &h->Sh[j], N)); SDP_CHECK(dev_alloc(h, &h->Yh[j], N)); }
     h->r = r; h->hist = numlbfgsvecs; h->latest = numlbfgsvecs;  // lbfgs_init: latest = h (src/lbfgs.jl:45)
     CUDA_TRY(h, cudaMemsetAsync(h->R, 0, (size_t)N * 8, h->stream));
@@ -298,6 +301,8 @@ int32_t sdplrp_upload_mat(sdplrp_handle *h, int32_t id, const double *src) {
     CUDA_TRY(h, cudaMemcpyAsync(p, src, (size_t)h->n * h->r * 8, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     comm_mark_full(h, id);
+    if (id == SDPLRP_MAT_R) h->CR_valid = false;
+    if (id == SDPLRP_MAT_D) h->CD_valid = false;
     return SDPLRP_OK;
 }
 
@@ -429,30 +434,50 @@ int32_t sdplrp_At_right(sdplrp_handle *h, const double *x, double *y, int64_t nc
 }
 
 // ---- fused iteration -----------------------------------------------------------
+// CR = C*R over the owned rows (from scratch); sums6[c][0] = <R,CR> per row class
+static int32_t rebuild_CR(sdplrp_handle *h) {
+    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
+    SectionScope sc(h, SDPLRP_SEC_SPMM);
+    SDP_CHECK(grad_obj_spmm(h, h->R, h->CR, nullptr, h->dscal + SC_SUMS));
+    h->CR_valid = true;
+    return SDPLRP_OK;
+}
+
+__global__ void k_store_sum3(const double *__restrict__ sums6, double *out) { *out = sums6[0] + sums6[2] + sums6[4]; }
+
+// f! (src/coreop.jl:11-31).  With a sparse objective the slot m+1 is <R, C*R>, a by-product
+// of rebuilding CR = C*R (which resets the drift of the CR recurrence once per major iteration).
 static int32_t do_f(sdplrp_handle *h) {
     SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
+    const bool split = h->obj_mat >= 0;
     {
         SectionScope sc(h, SDPLRP_SEC_A_UU);
-        SDP_CHECK(aop_uu(h, h->R, h->pvio_raw));
+        SDP_CHECK(aop_uu_skip(h, h->R, h->pvio_raw, split));
+    }
+    if (split) {
+        SDP_CHECK(rebuild_CR(h));
+        k_store_sum3<<<1, 1, 0, h->stream>>>(h->dscal + SC_SUMS, h->pvio_raw + h->m);
+        KLAUNCH(h);
     }
     SDP_CHECK(comm_reduce_mvec(h, h->pvio_raw, nullptr));
     SectionScope sc(h, SDPLRP_SEC_F_FINISH);
     return vec_f_finish(h);
 }
 
+// g! (src/coreop.jl:305-317): y, then G = 2*(y_obj*CR + S_dyn(y)*R + low rank) and the two norms
 static int32_t do_g(sdplrp_handle *h) {
+    if (h->obj_mat >= 0 && !h->CR_valid) SDP_CHECK(rebuild_CR(h));
+    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
     {
         SectionScope sc(h, SDPLRP_SEC_S_ASSEMBLE);
         SDP_CHECK(grad_form_y(h));
-        SDP_CHECK(grad_assemble_S(h));
     }
     {
-        SectionScope sc(h, SDPLRP_SEC_SPMM);
-        SDP_CHECK(grad_spmm(h, h->R, h->G, 2.0, true));  // G = 2 * R * S  (src/coreop.jl:312-315)
+        SectionScope sc(h, SDPLRP_SEC_GRAD);
+        SDP_CHECK(grad_hot(h));
     }
     comm_mark_partial(h, SDPLRP_MAT_G);
     SectionScope sc(h, SDPLRP_SEC_NORMS);
-    SDP_CHECK(lb_norm2(h, h->G, SC_GNORM2));
     SDP_CHECK(comm_reduce_scalars(h, SC_GNORM2, 1));
     return vec_pnorm2(h);
 }
@@ -494,6 +519,7 @@ int32_t sdplrp_lbfgs_dir(sdplrp_handle *h, double *descent) {
         SectionScope sc(h, SDPLRP_SEC_LBFGS_DIR);
         SDP_CHECK(lb_dir(h));
     }
+    h->CD_valid = false;
     comm_mark_partial(h, SDPLRP_MAT_D);
     SDP_CHECK(fetch_scalars(h, SC_DESCENT, 1));
     if (descent) *descent = h->hscal[SC_DESCENT];
@@ -504,6 +530,7 @@ int32_t sdplrp_use_gradient_direction(sdplrp_handle *h) {
     REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
     SDP_CHECK(lb_neg_copy(h));
+    h->CD_valid = false;
     comm_mark_partial(h, SDPLRP_MAT_D);
     return SDPLRP_OK;
 }
@@ -513,9 +540,18 @@ int32_t sdplrp_linesearch_coeffs(sdplrp_handle *h, double bq[5]) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     SDP_CHECK(comm_require_full(h, SDPLRP_MAT_D));
     SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
+    const bool split = h->obj_mat >= 0;
+    if (split && !h->CR_valid) SDP_CHECK(rebuild_CR(h));
     {
         SectionScope sc(h, SDPLRP_SEC_LS_PASS);
-        SDP_CHECK(aop_linesearch(h));
+        SDP_CHECK(aop_linesearch(h, split));  // constraints: sampled dots (A_RD already x2, A_DD)
+    }
+    if (split) {
+        // objective: CD = C*D (the one gather pass of the iteration), <C,DD'> = <D,CD>, <C,RD'+DR'> = 2<D,CR>
+        SectionScope sc(h, SDPLRP_SEC_SPMM);
+        SDP_CHECK(grad_obj_spmm(h, h->D, h->CD, h->CR, h->dscal + SC_SUMS));
+        SDP_CHECK(grad_obj_slots(h, h->dscal + SC_SUMS, h->A_RD + h->m, h->A_DD + h->m));
+        h->CD_valid = true;
     }
     SDP_CHECK(comm_reduce_mvec(h, h->A_RD, h->A_DD));
     {
@@ -533,7 +569,14 @@ int32_t sdplrp_step(sdplrp_handle *h, double alpha, double *obj) {
     {
         SectionScope sc(h, SDPLRP_SEC_STEP);
         SDP_CHECK(vec_commit(h, alpha));
-        SDP_CHECK(comm_step_R(h, alpha));  // Rt += alpha*dirt (all rows when replicated)
+        const bool recur = h->obj_mat >= 0 && h->CR_valid && h->CD_valid;
+        if (recur && h->world == 1) {
+            SDP_CHECK(lb_axpy2(h, alpha, h->D, h->R, h->CD, h->CR));  // Rt += a*dirt ; CR += a*CD
+        } else {
+            SDP_CHECK(comm_step_R(h, alpha));  // Rt += alpha*dirt (all rows when replicated)
+            if (recur) SDP_CHECK(lb_axpy(h, alpha, h->CD, h->CR));
+            else h->CR_valid = false;
+        }
     }
     if (obj) {
         SDP_CHECK(fetch_scalars(h, SC_OBJ, 1));

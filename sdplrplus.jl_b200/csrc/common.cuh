@@ -17,7 +17,16 @@ constexpr int kMaxRedK = 16;         // max simultaneous sums of one reduction k
 constexpr long long kPartialsLen = (long long)kRedBlocks * kMaxRedK * 8;  // doubles in h->partials
 constexpr int kLongMatThreshold = 64;   // matrices with more triu entries go to the chunked path
 constexpr int kChunkEntries = 2048;     // entries per chunk (one CTA) of a long matrix
-constexpr int kLongRowThreshold = 1024; // rows of S with more nonzeros are split across a CTA
+constexpr int kRowGroupMax = 32;        // rows with <= this many nonzeros: one sub-warp lane group per row
+constexpr int kRowWarpMax = 2048;       // rows with <= this many: one warp per row; longer: one CTA per row
+
+// rows of a CSR pattern binned by length (compacted lists, natural order inside a bin);
+// list[c] == nullptr with cnt[c] == n means "all rows" (identity, keeps streaming access)
+struct RowClasses {
+    int *list[3] = {nullptr, nullptr, nullptr};
+    long long cnt[3] = {0, 0, 0};
+    int *storage = nullptr;
+};
 
 struct LowRank {
     i64 gid;     // 0-based global slot
@@ -37,6 +46,7 @@ enum {
     SC_BQ = 8,        // 8 partial sums -> 5 quartic coefficients
     SC_RHO = 32,      // rho_j, j < kMaxHist
     SC_A = 64,        // a_j (alpha of the first loop)
+    SC_SUMS = 16,     // 3 row classes x 2 fused sums of the sparse kernels (6 doubles)
     SC_LANCZOS = 96,  // alpha_i, beta_i, stop flag scratch
     SC_COUNT = 128
 };
@@ -83,9 +93,16 @@ struct sdplrp_handle {
     int *dyn_gid = nullptr;        // contributors: global slot of y
     double *dyn_val = nullptr;     //               nzval_one
     int *dyn_pos_a = nullptr, *dyn_pos_b = nullptr;  // n_dyn: the (row,col) and (col,row) slots of the full pattern
-    // SpMM row classes
-    i64 n_long_rows = 0;
-    int *long_rows = nullptr;
+    // objective-split hot path: static objective values on the full pattern, dynamic pattern as CSR
+    double *Cfull = nullptr;       // nnzF: C's value at every full-pattern slot (0 where C has no entry)
+    double *dynS = nullptr;        // n_dyn: constraint part of S at the dynamic slots (per iteration)
+    i64 n_dynF = 0;                // dynamic slots of the full pattern
+    int *dynrow_ptr = nullptr;     // n+1
+    int *dynrow_col = nullptr;     // n_dynF
+    int *dynrow_src = nullptr;     // n_dynF -> index into dynS
+    RowClasses full_cls, dyn_cls;  // row bins of the full / dynamic pattern
+    double *CR = nullptr, *CD = nullptr;  // n x r: C*R (recurrence) and C*D
+    bool CR_valid = false, CD_valid = false;
 
     // low-rank matrices
     std::vector<LowRank> lr;
@@ -241,7 +258,8 @@ void pre_free(sdplrp_handle *h);
 // A passes (aop.cu)
 int32_t aop_uu(sdplrp_handle *h, const double *U, double *out_dev);                    // out = A(UU')
 int32_t aop_uv(sdplrp_handle *h, const double *U, const double *V, double *out_dev);  // out = A((UV'+VU')/2)
-int32_t aop_linesearch(sdplrp_handle *h);                                              // A_RD (x2), A_DD fused
+int32_t aop_linesearch(sdplrp_handle *h, bool skip_objective);                         // A_RD (x2), A_DD fused
+int32_t aop_uu_skip(sdplrp_handle *h, const double *U, double *out_dev, bool skip_objective);
 
 int32_t lr_project(sdplrp_handle *h, const LowRank &L, const double *X, double *dst);  // dst[k*r+i] = (X'B)[i,k]
 int32_t lr_scratch(sdplrp_handle *h);
@@ -250,6 +268,9 @@ int32_t lr_scratch(sdplrp_handle *h);
 int32_t grad_form_y(sdplrp_handle *h);                          // copy2y_lambda_sub_pvio!
 int32_t grad_assemble_S(sdplrp_handle *h);                      // At_preprocess! from device y
 int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bool want_norm);  // Y = scale*X*S (+low rank)
+int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double *Z, double *sums6);  // Y = C*X, sums <X,Y>, <X,Z>
+int32_t grad_obj_slots(sdplrp_handle *h, const double *sums6, double *a_rd_m, double *a_dd_m);
+int32_t grad_hot(sdplrp_handle *h);                             // G = 2*(y_obj*CR + S_dyn*R + low rank), ||G||^2
 int32_t grad_spmv(sdplrp_handle *h, const double *x, double *y, i64 ncols);                     // y = S*x (+low rank), n x ncols col-major
 int32_t grad_triuS(sdplrp_handle *h, double *out_dev);          // materialise triu_sparse_S.nzval
 
@@ -267,6 +288,7 @@ int32_t lb_dir(sdplrp_handle *h);                   // lbfgs_dir! + descent -> S
 int32_t lb_update(sdplrp_handle *h, double alpha);  // lbfgs_update!
 int32_t lb_clear(sdplrp_handle *h);
 int32_t lb_axpy(sdplrp_handle *h, double alpha, const double *x, double *y);  // y += alpha x over owned rows
+int32_t lb_axpy2(sdplrp_handle *h, double alpha, const double *x1, double *y1, const double *x2, double *y2);
 int32_t lb_neg_copy(sdplrp_handle *h);              // G = -G ; D = G
 int32_t lb_norm2(sdplrp_handle *h, const double *x, int slot);
 

@@ -1,19 +1,29 @@
 // gradient.cu -- y formation, assembly of S = C - sum (lambda_i - sigma v_i) A_i
-// on the aggregated pattern, and the SpMM  G = 2 * S * R  (+ low-rank terms);
-// plus the S*x product used by Lanczos.
+// on the aggregated pattern, the sparse x dense-factor products, and the S*x
+// product used by Lanczos.
 //
 // Reference: src/coreop.jl:205-317 (At_preprocess_sparse!, copy2y_lambda_sub_pvio!,
 // At_preprocess!, At! left/right, g!) and src/structs.jl:90-145 (BDB' mul!).
 //
-// Design (not a translation): the reference rebuilds every value of S on each
-// call (a scatter over all E_c entries followed by an nnzF-long gather).  Here
-// the contribution of the objective matrix is folded once into
-// triuS_static, S keeps y_{m+1}*static resident in HBM, and each iteration only
-// rewrites the "dynamic" slots that some constraint touches (n diagonal slots
-// for MaxCut) through a deterministic slot->contributors gather (no atomics).
-// The SpMM walks the symmetric pattern as CSR: one sub-warp lane group per row
-// keeps the r-vector accumulator in registers and gathers rows of R with
-// 128-bit loads; rows longer than kLongRowThreshold get a whole CTA.
+// Design (not a translation)
+//  * S is split as  S(y) = y_obj * C  +  S_dyn(y):  the objective's values are
+//    static (Cfull, resident in HBM), only the "dynamic" slots that some
+//    constraint touches (the n diagonal slots for MaxCut) are re-evaluated per
+//    iteration through a deterministic slot->contributors gather (no atomics).
+//  * The hot loop never multiplies by the full S.  It keeps CR = C*R by the
+//    recurrence CR += alpha*CD (the same device the reference uses for the
+//    residual vector, src/linesearch.jl:118) where CD = C*D is the ONE gather
+//    pass per inner iteration; that pass also yields <C,DD'> = <D,CD> and
+//    <C,RD'+DR'> = 2<D,CR> for the exact line search, and the gradient becomes
+//    G = 2*(y_obj*CR + S_dyn*R): a pass over the dynamic pattern only.  CR is
+//    rebuilt from scratch by every f! (major iteration), which bounds the drift.
+//  * Sparse x dense kernels walk the symmetric pattern as CSR with rows binned
+//    by length: <= kRowGroupMax nonzeros -> one sub-warp lane group per row,
+//    <= kRowWarpMax -> one warp per row (lane groups split the nonzeros, 16
+//    independent gathers in flight per warp), longer -> one CTA per row.  Lanes
+//    own 128-bit slices of the r-vector; accumulators stay in registers.
+//  * The seam-level operators At!(Y,X) / At!(y,x) still use the full S (tests,
+//    Lanczos); S is materialised from Cfull + dynamic slots on demand.
 #include <algorithm>
 #include "common.cuh"
 
@@ -30,32 +40,33 @@ __global__ void k_form_y(i64 m, double sigma, const double *__restrict__ lambda,
     }
 }
 
-// static part: S[k] = y_obj * triuS_static[mapped[k]]
-__global__ void k_S_static(i64 nnzF, double yobj, const int *__restrict__ mapped, const double *__restrict__ st,
-                           double *__restrict__ S) {
-    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nnzF; k += (i64)gridDim.x * blockDim.x) {
-        int t = mapped[k];
-        S[k] = t >= 0 ? yobj * st[t] : 0.0;
-    }
+// static part: S[k] = y_obj * Cfull[k]
+__global__ void k_S_static(i64 nnzF, double yobj, const double *__restrict__ cfull, double *__restrict__ S) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nnzF; k += (i64)gridDim.x * blockDim.x) S[k] = yobj * cfull[k];
 }
 
 // dynamic slots: constraints first (in matrix order), objective last -- the
-// accumulation order of the reference's CSC mat-vec (src/coreop.jl:221)
+// accumulation order of the reference's CSC mat-vec (src/coreop.jl:221).
+// MODE 0: write the total into S at both mirrored positions
+// MODE 1: write the total into triu_out[slot]
+// MODE 2: write only the constraint part into dyn_out[d]   (S_dyn of the hot loop)
+template <int MODE>
 __global__ void k_S_dynamic(i64 nd, double yobj, const int *__restrict__ dyn_slot, const int *__restrict__ dyn_ptr,
                             const int *__restrict__ dyn_gid, const double *__restrict__ dyn_val,
                             const int *__restrict__ pos_a, const int *__restrict__ pos_b, const double *__restrict__ st,
-                            const double *__restrict__ y, double *__restrict__ S, double *__restrict__ triu_out) {
+                            const double *__restrict__ y, double *__restrict__ out) {
     for (i64 d = blockIdx.x * (i64)blockDim.x + threadIdx.x; d < nd; d += (i64)gridDim.x * blockDim.x) {
         double s = 0.0;
         for (int j = dyn_ptr[d]; j < dyn_ptr[d + 1]; j++) s += dyn_val[j] * y[dyn_gid[j]];
+        if (MODE == 2) { out[d] = s; continue; }
         const int t = dyn_slot[d];
         s += yobj * st[t];
-        if (triu_out) {
-            triu_out[t] = s;
+        if (MODE == 1) {
+            out[t] = s;
         } else {
-            S[pos_a[d]] = s;
+            out[pos_a[d]] = s;
             const int pb = pos_b[d];
-            if (pb >= 0) S[pb] = s;
+            if (pb >= 0) out[pb] = s;
         }
     }
 }
@@ -64,7 +75,7 @@ __global__ void k_scale_copy(i64 len, double a, const double *__restrict__ x, do
     for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < len; k += (i64)gridDim.x * blockDim.x) y[k] = a * x[k];
 }
 
-// ---- SpMM ------------------------------------------------------------------
+// ---- sparse x dense-factor kernels ------------------------------------------
 template <int VEC>
 struct Acc;
 template <>
@@ -72,112 +83,228 @@ struct Acc<1> {
     double v;
     __device__ __forceinline__ void zero() { v = 0.0; }
     __device__ __forceinline__ void fma(double s, const double *p) { v += s * __ldg(p); }
-    __device__ __forceinline__ void add(const Acc &o) { v += o.v; }
-    __device__ __forceinline__ void store(double *p, double sc) const { *p = sc * v; }
     __device__ __forceinline__ void shfl_add(int o) { v += __shfl_xor_sync(0xffffffffu, v, o); }
+    __device__ __forceinline__ void scale_add(double sc, double a, const double *p) { v = sc * (v + a * __ldg(p)); }
+    __device__ __forceinline__ void scale(double sc) { v *= sc; }
+    __device__ __forceinline__ double dot_ld(const double *p) const { return v * __ldg(p); }
+    __device__ __forceinline__ double norm2() const { return v * v; }
+    __device__ __forceinline__ void store(double *p) const { *p = v; }
 };
 template <>
 struct Acc<2> {
     double2 v;
     __device__ __forceinline__ void zero() { v.x = v.y = 0.0; }
     __device__ __forceinline__ void fma(double s, const double *p) {
-        double2 x = ldg2(p);
+        const double2 x = ldg2(p);
         v.x += s * x.x; v.y += s * x.y;
-    }
-    __device__ __forceinline__ void add(const Acc &o) { v.x += o.v.x; v.y += o.v.y; }
-    __device__ __forceinline__ void store(double *p, double sc) const {
-        *reinterpret_cast<double2 *>(p) = make_double2(sc * v.x, sc * v.y);
     }
     __device__ __forceinline__ void shfl_add(int o) {
         v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
         v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
     }
+    __device__ __forceinline__ void scale_add(double sc, double a, const double *p) {
+        const double2 x = ldg2(p);
+        v.x = sc * (v.x + a * x.x); v.y = sc * (v.y + a * x.y);
+    }
+    __device__ __forceinline__ void scale(double sc) { v.x *= sc; v.y *= sc; }
+    __device__ __forceinline__ double dot_ld(const double *p) const {
+        const double2 x = ldg2(p);
+        return v.x * x.x + v.y * x.y;
+    }
+    __device__ __forceinline__ double norm2() const { return v.x * v.x + v.y * v.y; }
+    __device__ __forceinline__ void store(double *p) const { *reinterpret_cast<double2 *>(p) = v; }
 };
 
-// Y[i,:] = scale * sum_k S[k] * X[idx[k],:]  for rows i in [lo,hi) with at most
-// kLongRowThreshold nonzeros. One group of G lanes per row; lane lg owns the
-// vector units lg, lg+G, ... (MAXU of them).
-template <int VEC, int MAXU>
-__global__ void __launch_bounds__(TPB) k_spmm_rows(i64 lo, i64 hi, const int *__restrict__ ptr, const int *__restrict__ idx,
-                                                   const double *__restrict__ S, const double *__restrict__ X,
-                                                   double *__restrict__ Y, int r, int G, double scale) {
-    const int nv = r / VEC;
-    const int lg = threadIdx.x & (G - 1);
-    const i64 group = ((i64)blockIdx.x * TPB + threadIdx.x) / G;
-    const i64 n_groups = (i64)gridDim.x * TPB / G;
-    for (i64 i = lo + group; i < hi; i += n_groups) {
-        const int beg = ptr[i], end = ptr[i + 1];
-        if (end - beg > kLongRowThreshold) continue;
+// EPI 0: Y_i = scale * acc                                   (seam-level At!)
+// EPI 1: Y_i = scale * (acc + yobj*ADD_i); sum0 += |Y_i|^2    (gradient)
+// EPI 2: Y_i = acc; sum0 += <X_i, acc>; sum1 += <X_i, Z_i>    (CD = C*D with the line-search dots; CR = C*R with obj)
+struct RowArgs {
+    const int *rows;   // compacted row list of this class, nullptr = identity over [0, n_rows)
+    i64 n_rows;
+    const int *ptr, *idx;
+    const double *val;
+    const int *src;    // IND: value = val[src[k]]
+    const double *X;
+    double *Y;
+    int r, G;
+    double scale, yobj;
+    const double *ADD, *Z;
+    double *partials;
+    unsigned *ticket;
+    double *out;       // EPI != 0: out[0], out[1]
+    i64 own_lo, own_hi;
+};
+
+template <int VEC, int MAXU, int EPI>
+__device__ __forceinline__ void row_epilogue(const RowArgs &a, i64 i, Acc<VEC> (&acc)[MAXU], int lg, int nv, double &s0, double &s1) {
+#pragma unroll
+    for (int u = 0; u < MAXU; u++) {
+        const int c = lg + u * a.G;
+        if (c < nv) {
+            const size_t off = (size_t)i * a.r + c * VEC;
+            if (EPI == 0) {
+                acc[u].scale(a.scale);
+            } else if (EPI == 1) {
+                if (a.ADD) acc[u].scale_add(a.scale, a.yobj, a.ADD + off); else acc[u].scale(a.scale);
+                s0 += acc[u].norm2();
+            } else {
+                s0 += acc[u].dot_ld(a.X + off);
+                if (a.Z) {
+                    Acc<VEC> t;
+                    t.zero(); t.fma(1.0, a.X + off);
+                    s1 += t.dot_ld(a.Z + off);
+                }
+            }
+            acc[u].store(a.Y + off);
+        }
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void finish_sums(const RowArgs &a, double s0, double s1) {
+    if (EPI == 0) return;
+    double v[2] = {s0, s1};
+    double *out = a.out;
+    grid_sum_finalize<2>(v, a.partials, a.ticket, [&](double (&s)[2]) { out[0] = s[0]; out[1] = s[1]; });
+}
+
+#define VAL_AT(k) (IND ? __ldg(a.val + __ldg(a.src + (k))) : __ldg(a.val + (k)))
+
+// class 0: one group of G lanes per row
+template <int VEC, int MAXU, bool IND, int EPI>
+__global__ void __launch_bounds__(TPB) k_rows_group(RowArgs a) {
+    const int nv = a.r / VEC;
+    const int lg = threadIdx.x & (a.G - 1);
+    const i64 group = ((i64)blockIdx.x * TPB + threadIdx.x) / a.G;
+    const i64 n_groups = (i64)gridDim.x * TPB / a.G;
+    double s0 = 0.0, s1 = 0.0;
+    for (i64 q = group; q < a.n_rows; q += n_groups) {
+        const i64 i = a.rows ? a.rows[q] : q;
+        if (i < a.own_lo || i >= a.own_hi) continue;
+        const int beg = a.ptr[i], end = a.ptr[i + 1];
         Acc<VEC> acc[MAXU];
 #pragma unroll
         for (int u = 0; u < MAXU; u++) acc[u].zero();
         int k = beg;
         for (; k + 4 <= end; k += 4) {  // 4 independent gathers in flight per lane
-            const int c0 = __ldg(idx + k), c1 = __ldg(idx + k + 1), c2 = __ldg(idx + k + 2), c3 = __ldg(idx + k + 3);
-            const double s0 = __ldg(S + k), s1 = __ldg(S + k + 1), s2 = __ldg(S + k + 2), s3 = __ldg(S + k + 3);
+            const int c0 = __ldg(a.idx + k), c1 = __ldg(a.idx + k + 1), c2 = __ldg(a.idx + k + 2), c3 = __ldg(a.idx + k + 3);
+            const double v0 = VAL_AT(k), v1 = VAL_AT(k + 1), v2 = VAL_AT(k + 2), v3 = VAL_AT(k + 3);
 #pragma unroll
             for (int u = 0; u < MAXU; u++) {
-                const int c = lg + u * G;
+                const int c = lg + u * a.G;
                 if (c < nv) {
-                    acc[u].fma(s0, X + (size_t)c0 * r + c * VEC);
-                    acc[u].fma(s1, X + (size_t)c1 * r + c * VEC);
-                    acc[u].fma(s2, X + (size_t)c2 * r + c * VEC);
-                    acc[u].fma(s3, X + (size_t)c3 * r + c * VEC);
+                    acc[u].fma(v0, a.X + (size_t)c0 * a.r + c * VEC);
+                    acc[u].fma(v1, a.X + (size_t)c1 * a.r + c * VEC);
+                    acc[u].fma(v2, a.X + (size_t)c2 * a.r + c * VEC);
+                    acc[u].fma(v3, a.X + (size_t)c3 * a.r + c * VEC);
                 }
             }
         }
         for (; k < end; k++) {
-            const int c0 = __ldg(idx + k);
-            const double s0 = __ldg(S + k);
+            const int c0 = __ldg(a.idx + k);
+            const double v0 = VAL_AT(k);
 #pragma unroll
             for (int u = 0; u < MAXU; u++) {
-                const int c = lg + u * G;
-                if (c < nv) acc[u].fma(s0, X + (size_t)c0 * r + c * VEC);
+                const int c = lg + u * a.G;
+                if (c < nv) acc[u].fma(v0, a.X + (size_t)c0 * a.r + c * VEC);
             }
         }
-#pragma unroll
-        for (int u = 0; u < MAXU; u++) {
-            const int c = lg + u * G;
-            if (c < nv) acc[u].store(Y + (size_t)i * r + c * VEC, scale);
-        }
+        row_epilogue<VEC, MAXU, EPI>(a, i, acc, lg, nv, s0, s1);
     }
+    finish_sums<EPI>(a, s0, s1);
 }
 
-// one CTA per long row: groups stride over the nonzeros, then a fixed-order
-// cross-group sum in shared memory
-template <int VEC, int MAXU>
-__global__ void __launch_bounds__(TPB) k_spmm_long(const int *__restrict__ rows, i64 lo, i64 hi, const int *__restrict__ ptr,
-                                                   const int *__restrict__ idx, const double *__restrict__ S,
-                                                   const double *__restrict__ X, double *__restrict__ Y, int r, int G,
-                                                   double scale) {
-    extern __shared__ double sm[];  // (TPB/G) * r
-    const i64 i = rows[blockIdx.x];
-    if (i < lo || i >= hi) return;
-    const int nv = r / VEC;
-    const int lg = threadIdx.x & (G - 1), grp = threadIdx.x / G, ng = TPB / G;
-    Acc<VEC> acc[MAXU];
+// class 1: one warp per row; the 32/G lane groups take 4 nonzeros each per step
+template <int VEC, int MAXU, bool IND, int EPI>
+__global__ void __launch_bounds__(TPB) k_rows_warp(RowArgs a) {
+    const int nv = a.r / VEC;
+    const int lane = threadIdx.x & 31;
+    const int lg = lane & (a.G - 1), grp = lane / a.G, ng = 32 / a.G;
+    const i64 warp = (i64)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+    const i64 n_warps = (i64)gridDim.x * (TPB / 32);
+    double s0 = 0.0, s1 = 0.0;
+    for (i64 q = warp; q < a.n_rows; q += n_warps) {  // warp-uniform
+        const i64 i = a.rows ? a.rows[q] : q;
+        if (i < a.own_lo || i >= a.own_hi) continue;
+        const int beg = a.ptr[i], end = a.ptr[i + 1];
+        Acc<VEC> acc[MAXU];
 #pragma unroll
-    for (int u = 0; u < MAXU; u++) acc[u].zero();
-    for (int k = ptr[i] + grp; k < ptr[i + 1]; k += ng) {
-        const int c0 = __ldg(idx + k);
-        const double s0 = __ldg(S + k);
+        for (int u = 0; u < MAXU; u++) acc[u].zero();
+        for (int k0 = beg + grp * 4; k0 < end; k0 += ng * 4) {
+            int cc[4];
+            double vv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bool ok = k0 + j < end;
+                cc[j] = ok ? __ldg(a.idx + k0 + j) : 0;
+                vv[j] = ok ? VAL_AT(k0 + j) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < MAXU; u++) {
+                const int c = lg + u * a.G;
+                if (c < nv) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (k0 + j < end) acc[u].fma(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC);
+                }
+            }
+        }
+        // sum the lane groups (xor offsets G, 2G, ... < 32)
+#pragma unroll
+        for (int u = 0; u < MAXU; u++)
+            for (int o = a.G; o < 32; o <<= 1) acc[u].shfl_add(o);
+        if (grp == 0) row_epilogue<VEC, MAXU, EPI>(a, i, acc, lg, nv, s0, s1);
+    }
+    finish_sums<EPI>(a, s0, s1);
+}
+
+// class 2: one CTA per row; groups stride over the nonzeros, fixed-order cross-group sum in shared memory
+template <int VEC, int MAXU, bool IND, int EPI>
+__global__ void __launch_bounds__(TPB) k_rows_cta(RowArgs a) {
+    extern __shared__ double sm[];  // (TPB/G) * r
+    const int nv = a.r / VEC;
+    const int lg = threadIdx.x & (a.G - 1), grp = threadIdx.x / a.G, ng = TPB / a.G;
+    double s0 = 0.0, s1 = 0.0;
+    for (i64 q = blockIdx.x; q < a.n_rows; q += gridDim.x) {
+        const i64 i = a.rows ? a.rows[q] : q;
+        if (i < a.own_lo || i >= a.own_hi) continue;
+        Acc<VEC> acc[MAXU];
+#pragma unroll
+        for (int u = 0; u < MAXU; u++) acc[u].zero();
+        const int beg = a.ptr[i], end = a.ptr[i + 1];
+        for (int k = beg + grp; k < end; k += ng) {
+            const int c0 = __ldg(a.idx + k);
+            const double v0 = VAL_AT(k);
+#pragma unroll
+            for (int u = 0; u < MAXU; u++) {
+                const int c = lg + u * a.G;
+                if (c < nv) acc[u].fma(v0, a.X + (size_t)c0 * a.r + c * VEC);
+            }
+        }
+        __syncthreads();
 #pragma unroll
         for (int u = 0; u < MAXU; u++) {
-            const int c = lg + u * G;
-            if (c < nv) acc[u].fma(s0, X + (size_t)c0 * r + c * VEC);
+            const int c = lg + u * a.G;
+            if (c < nv) acc[u].store(sm + (size_t)grp * a.r + c * VEC);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < a.r; e += TPB) {
+            double t = 0.0;
+            for (int g = 0; g < ng; g++) t += sm[(size_t)g * a.r + e];
+            const size_t off = (size_t)i * a.r + e;
+            if (EPI == 0) {
+                t *= a.scale;
+            } else if (EPI == 1) {
+                t = a.ADD ? a.scale * (t + a.yobj * a.ADD[off]) : a.scale * t;
+                s0 += t * t;
+            } else {
+                s0 += a.X[off] * t;
+                if (a.Z) s1 += a.X[off] * a.Z[off];
+            }
+            a.Y[off] = t;
         }
     }
-#pragma unroll
-    for (int u = 0; u < MAXU; u++) {
-        const int c = lg + u * G;
-        if (c < nv) acc[u].store(sm + (size_t)grp * r + c * VEC, 1.0);
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < r; e += TPB) {
-        double t = 0.0;
-        for (int g = 0; g < ng; g++) t += sm[(size_t)g * r + e];
-        Y[(size_t)i * r + e] = scale * t;
-    }
+    finish_sums<EPI>(a, s0, s1);
 }
 
 // Y[j,:] += scale*coeff * sum_k XB[:,k] D[k] B[j,k]     (src/structs.jl:135-145)
@@ -194,7 +321,7 @@ __global__ void k_lr_apply(i64 lo, i64 hi, int r, int s, i64 n, const double *__
     }
 }
 
-// ---- SpMV (Lanczos): y = S*x, 8 lanes per row ---------------------------------
+// ---- SpMV (seam-level At!(y, aux, x)): y = S*x, 8 lanes per row -----------------
 constexpr int SPMV_L = 8;
 __global__ void __launch_bounds__(TPB) k_spmv(i64 n, const int *__restrict__ ptr, const int *__restrict__ idx,
                                               const double *__restrict__ S, const double *__restrict__ x,
@@ -215,15 +342,12 @@ __global__ void __launch_bounds__(TPB) k_spmv(i64 n, const int *__restrict__ ptr
     }
 }
 
-// low-rank part of S*x for one column: t_k = D_k * coeff * <B[:,k], x>, y += B t
-__global__ void __launch_bounds__(TPB) k_lr_dot(i64 n, int s, const double *__restrict__ B, const double *__restrict__ x,
+__global__ void __launch_bounds__(TPB) k_lr_dot(i64 n, const double *__restrict__ B, const double *__restrict__ x,
                                                 double *__restrict__ partials, unsigned *__restrict__ ticket,
                                                 double *__restrict__ out) {
-    // one launch per k (s is tiny); out[0] = <B[:,k], x>
     double acc[1] = {0.0};
     for (i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x; j < n; j += (i64)gridDim.x * blockDim.x) acc[0] += B[j] * x[j];
     grid_sum_finalize<1>(acc, partials, ticket, [&](double (&sv)[1]) { out[0] = sv[0]; });
-    (void)s;
 }
 __global__ void k_lr_axpy_vec(i64 n, const double *__restrict__ B, const double *__restrict__ dot, const double *__restrict__ Dg,
                               int k, const double *__restrict__ yv, int gid, double *__restrict__ out) {
@@ -231,10 +355,91 @@ __global__ void k_lr_axpy_vec(i64 n, const double *__restrict__ B, const double 
     for (i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x; j < n; j += (i64)gridDim.x * blockDim.x) out[j] += B[j] * t;
 }
 
+// objective slots of the line-search vectors from the fused sums of CD = C*D
+__global__ void k_obj_slots(int ncls, const double *__restrict__ sums /* ncls x 2 */, double *a_rd_m, double *a_dd_m) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int c = 0; c < ncls; c++) { s0 += sums[2 * c]; s1 += sums[2 * c + 1]; }
+    if (a_dd_m) *a_dd_m = s0;        // <C, DD'> = <D, CD>
+    if (a_rd_m) *a_rd_m = 2.0 * s1;  // <C, RD'+DR'> = 2 <D, CR>
+}
+__global__ void k_sum_slots(int ncls, const double *__restrict__ sums, int stride, double *out) {
+    double s = 0.0;
+    for (int c = 0; c < ncls; c++) s += sums[stride * c];
+    *out = s;
+}
+
 int pick_group(int nv) {
     int G = 1;
     while (G < nv && G < 32) G <<= 1;
     return G;
+}
+
+struct Csr {
+    const int *ptr, *idx;
+    const double *val;
+    const int *src;
+    const RowClasses *cls;
+};
+
+template <int VEC, int MAXU, bool IND, int EPI>
+int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, double *sums /* 3 x 2 or null */) {
+    cudaStream_t st = h->stream;
+    const int gpb = TPB / a.G;
+    for (int c = 0; c < 3; c++) {
+        if (sums) a.out = sums + 2 * c;
+        a.rows = cls.list[c];
+        a.n_rows = cls.cnt[c];
+        if (a.n_rows <= 0) {
+            if (sums) CUDA_TRY(h, cudaMemsetAsync(sums + 2 * c, 0, 2 * sizeof(double), st));
+            continue;
+        }
+        if (c == 0) {
+            k_rows_group<VEC, MAXU, IND, EPI><<<grid_for(a.n_rows, gpb, 16 * kNumSM), TPB, 0, st>>>(a);
+        } else if (c == 1) {
+            k_rows_warp<VEC, MAXU, IND, EPI><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
+        } else {
+            const size_t smem = (size_t)gpb * a.r * sizeof(double);
+            k_rows_cta<VEC, MAXU, IND, EPI><<<grid_for(a.n_rows, 1, 8 * kNumSM), TPB, smem, st>>>(a);
+        }
+        KLAUNCH(h);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+
+template <bool IND, int EPI>
+int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, double *sums) {
+    const int r = h->r;
+    const bool vec2 = (r % 2 == 0);
+    const int nv = vec2 ? r / 2 : r;
+    a.r = r;
+    a.G = pick_group(nv);
+    a.partials = h->partials;
+    a.ticket = h->ticket;
+    a.own_lo = h->row_lo;
+    a.own_hi = h->row_hi;
+    const int units = (nv + a.G - 1) / a.G;
+    if (units > 4) return fail(h, SDPLRP_ERR_ARG, "rank too large for the sparse kernels (r <= 256 even / 128 odd)");
+    if (vec2) {
+        if (units == 1) return launch_classes<2, 1, IND, EPI>(h, a, cls, sums);
+        return launch_classes<2, 4, IND, EPI>(h, a, cls, sums);
+    }
+    if (units == 1) return launch_classes<1, 1, IND, EPI>(h, a, cls, sums);
+    return launch_classes<1, 4, IND, EPI>(h, a, cls, sums);
+}
+
+int32_t add_lowrank(sdplrp_handle *h, const double *X, double *Y, double scale) {
+    if (h->lr.empty()) return SDPLRP_OK;
+    const int r = h->r;
+    SDP_CHECK(lr_scratch(h));
+    for (const LowRank &L : h->lr) {
+        SDP_CHECK(lr_project(h, L, X, h->lr_tmp));
+        k_lr_apply<<<grid_for((h->row_hi - h->row_lo) * r, TPB, kRedBlocks), TPB, 0, h->stream>>>(
+            h->row_lo, h->row_hi, r, (int)L.s, h->n, h->lr_tmp, L.dD, L.dB, h->y, (int)L.gid, scale, Y);
+        KLAUNCH(h);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
 }
 
 }  // namespace
@@ -247,21 +452,22 @@ int32_t grad_form_y(sdplrp_handle *h) {
     return SDPLRP_OK;
 }
 
+// At_preprocess!: materialise S = y_obj*C + S_dyn(y) on the full pattern (seam-level / Lanczos)
 int32_t grad_assemble_S(sdplrp_handle *h) {
     if (h->nA <= 0) return SDPLRP_OK;
     cudaStream_t st = h->stream;
     const double yobj = (h->obj_mat >= 0) ? h->y_obj : 0.0;
     if (!h->S_static_valid || h->S_static_scale != yobj) {
         if (h->nnzF > 0) {
-            k_S_static<<<grid_for(h->nnzF, TPB, 8 * kNumSM), TPB, 0, st>>>(h->nnzF, yobj, h->mapped, h->triuS_static, h->S);
+            k_S_static<<<grid_for(h->nnzF, TPB, 8 * kNumSM), TPB, 0, st>>>(h->nnzF, yobj, h->Cfull, h->S);
             KLAUNCH(h);
         }
         h->S_static_valid = true;
         h->S_static_scale = yobj;
     }
     if (h->n_dyn > 0) {
-        k_S_dynamic<<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, yobj, h->dyn_slot, h->dyn_ptr, h->dyn_gid, h->dyn_val,
-                                                                        h->dyn_pos_a, h->dyn_pos_b, h->triuS_static, h->y, h->S, nullptr);
+        k_S_dynamic<0><<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, yobj, h->dyn_slot, h->dyn_ptr, h->dyn_gid, h->dyn_val,
+                                                                           h->dyn_pos_a, h->dyn_pos_b, h->triuS_static, h->y, h->S);
         KLAUNCH(h);
     }
     CUDA_TRY(h, cudaGetLastError());
@@ -275,59 +481,68 @@ int32_t grad_triuS(sdplrp_handle *h, double *out) {
     k_scale_copy<<<grid_for(h->nnzT, TPB, 8 * kNumSM), TPB, 0, st>>>(h->nnzT, yobj, h->triuS_static, out);
     KLAUNCH(h);
     if (h->n_dyn > 0) {
-        k_S_dynamic<<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, yobj, h->dyn_slot, h->dyn_ptr, h->dyn_gid, h->dyn_val,
-                                                                        h->dyn_pos_a, h->dyn_pos_b, h->triuS_static, h->y, h->S, out);
+        k_S_dynamic<1><<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, yobj, h->dyn_slot, h->dyn_ptr, h->dyn_gid, h->dyn_val,
+                                                                           h->dyn_pos_a, h->dyn_pos_b, h->triuS_static, h->y, out);
         KLAUNCH(h);
     }
     CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
 }
 
-template <int VEC, int MAXU>
-static int32_t spmm_launch(sdplrp_handle *h, const double *X, double *Y, double scale, int G) {
-    cudaStream_t st = h->stream;
-    const i64 rows = h->row_hi - h->row_lo;
-    const int gpb = TPB / G;
-    k_spmm_rows<VEC, MAXU><<<grid_for(rows, gpb, 32 * kNumSM), TPB, 0, st>>>(h->row_lo, h->row_hi, h->full_ptr, h->full_idx, h->S, X, Y, h->r, G, scale);
-    KLAUNCH(h);
-    if (h->n_long_rows > 0) {
-        size_t smem = (size_t)gpb * h->r * sizeof(double);
-        k_spmm_long<VEC, MAXU><<<(int)h->n_long_rows, TPB, smem, st>>>(h->long_rows, h->row_lo, h->row_hi, h->full_ptr, h->full_idx, h->S, X, Y, h->r, G, scale);
-        KLAUNCH(h);
-    }
-    CUDA_TRY(h, cudaGetLastError());
-    return SDPLRP_OK;
-}
-
-// Y = scale * (X*S + sum_g y_g X B D B')  over the owned rows
+// seam-level At!(Y, X): Y = scale * (X*S + sum_g y_g X B D B') over the owned rows, S as last assembled
 int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bool /*want_norm*/) {
     const int r = h->r;
-    const bool vec2 = (r % 2 == 0);
-    const int nv = vec2 ? r / 2 : r;
-    const int G = pick_group(nv);
-    const int units = (nv + G - 1) / G;
-    if (units > 4) return fail(h, SDPLRP_ERR_ARG, "rank too large for the SpMM kernel (r <= 256 even / 128 odd)");
     if (h->nA > 0) {
-        if (vec2) {
-            if (units == 1) SDP_CHECK((spmm_launch<2, 1>(h, X, Y, scale, G)));
-            else SDP_CHECK((spmm_launch<2, 4>(h, X, Y, scale, G)));
-        } else {
-            if (units == 1) SDP_CHECK((spmm_launch<1, 1>(h, X, Y, scale, G)));
-            else SDP_CHECK((spmm_launch<1, 4>(h, X, Y, scale, G)));
-        }
+        RowArgs a = {};
+        a.ptr = h->full_ptr; a.idx = h->full_idx; a.val = h->S; a.src = nullptr;
+        a.X = X; a.Y = Y; a.scale = scale;
+        SDP_CHECK((launch_csr<false, 0>(h, a, h->full_cls, nullptr)));
     } else {
         CUDA_TRY(h, cudaMemsetAsync(Y + h->row_lo * r, 0, (size_t)(h->row_hi - h->row_lo) * r * sizeof(double), h->stream));
     }
-    if (!h->lr.empty()) {
-        SDP_CHECK(lr_scratch(h));
-        for (const LowRank &L : h->lr) {
-            SDP_CHECK(lr_project(h, L, X, h->lr_tmp));
-            k_lr_apply<<<grid_for((h->row_hi - h->row_lo) * r, TPB, kRedBlocks), TPB, 0, h->stream>>>(
-                h->row_lo, h->row_hi, r, (int)L.s, h->n, h->lr_tmp, L.dD, L.dB, h->y, (int)L.gid, scale, Y);
-            KLAUNCH(h);
-        }
-        CUDA_TRY(h, cudaGetLastError());
+    return add_lowrank(h, X, Y, scale);
+}
+
+// Y = C*X over the owned rows with the fused sums  out0 = <X, Y>, out1 = <X, Z>  (Z may be null)
+int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double *Z, double *sums6) {
+    RowArgs a = {};
+    a.ptr = h->full_ptr; a.idx = h->full_idx; a.val = h->Cfull; a.src = nullptr;
+    a.X = X; a.Y = Y; a.Z = Z; a.scale = 1.0;
+    return launch_csr<false, 2>(h, a, h->full_cls, sums6);
+}
+
+// the hot-loop gradient: G = 2*(y_obj*CR + S_dyn(y)*R + low rank), ||G||_F^2 -> SC_GNORM2
+int32_t grad_hot(sdplrp_handle *h) {
+    cudaStream_t st = h->stream;
+    const int r = h->r;
+    double *sums = h->dscal + SC_SUMS;
+    if (h->n_dyn > 0) {
+        k_S_dynamic<2><<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, 0.0, h->dyn_slot, h->dyn_ptr, h->dyn_gid, h->dyn_val,
+                                                                           h->dyn_pos_a, h->dyn_pos_b, h->triuS_static, h->y, h->dynS);
+        KLAUNCH(h);
     }
+    RowArgs a = {};
+    a.ptr = h->dynrow_ptr; a.idx = h->dynrow_col; a.val = h->dynS; a.src = h->dynrow_src;
+    a.X = h->R; a.Y = h->G; a.scale = 2.0;
+    a.ADD = (h->obj_mat >= 0) ? h->CR : nullptr;
+    a.yobj = h->y_obj;
+    SDP_CHECK((launch_csr<true, 1>(h, a, h->dyn_cls, sums)));
+    if (h->lr.empty()) {
+        k_sum_slots<<<1, 1, 0, st>>>(3, sums, 2, h->dscal + SC_GNORM2);
+        KLAUNCH(h);
+    } else {
+        SDP_CHECK(add_lowrank(h, h->R, h->G, 2.0));
+        SDP_CHECK(lb_norm2(h, h->G, SC_GNORM2));
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+
+// objective slots of A_RD / A_DD from the sums of CD = C*D; pvio_raw[m] from those of CR = C*R
+int32_t grad_obj_slots(sdplrp_handle *h, const double *sums6, double *a_rd_m, double *a_dd_m) {
+    k_obj_slots<<<1, 1, 0, h->stream>>>(3, sums6, a_rd_m, a_dd_m);
+    KLAUNCH(h);
+    CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
 }
 
@@ -346,7 +561,7 @@ int32_t grad_spmv(sdplrp_handle *h, const double *x, double *y, i64 ncols) {
         }
         for (const LowRank &L : h->lr) {
             for (i64 k = 0; k < L.s; k++) {
-                k_lr_dot<<<kRedBlocks, TPB, 0, st>>>(n, (int)L.s, L.dB + k * n, xq, h->partials, h->ticket, h->dscal + SC_LANCZOS + 8);
+                k_lr_dot<<<kRedBlocks, TPB, 0, st>>>(n, L.dB + k * n, xq, h->partials, h->ticket, h->dscal + SC_LANCZOS + 8);
                 KLAUNCH(h);
                 k_lr_axpy_vec<<<grid_for(n, TPB, kRedBlocks), TPB, 0, st>>>(n, L.dB + k * n, h->dscal + SC_LANCZOS + 8, L.dD, (int)k, h->y, (int)L.gid, yq);
                 KLAUNCH(h);

@@ -124,6 +124,16 @@ __global__ void __launch_bounds__(TPB) k_axpy(i64 nu, double a, const double *__
     GRID_STRIDE(i, nu) V<VEC>::st(y, i, V<VEC>::axpy(a, V<VEC>::ld(x, i), V<VEC>::ld(y, i)));
 }
 
+// y1 += a*x1 ; y2 += a*x2  (R += alpha*D and CR += alpha*CD in one launch)
+template <int VEC>
+__global__ void __launch_bounds__(TPB) k_axpy2(i64 nu, double a, const double *__restrict__ x1, double *__restrict__ y1,
+                                               const double *__restrict__ x2, double *__restrict__ y2) {
+    GRID_STRIDE(i, nu) {
+        V<VEC>::st(y1, i, V<VEC>::axpy(a, V<VEC>::ld(x1, i), V<VEC>::ld(y1, i)));
+        V<VEC>::st(y2, i, V<VEC>::axpy(a, V<VEC>::ld(x2, i), V<VEC>::ld(y2, i)));
+    }
+}
+
 // G = -G ; D = G   (src/sdplr.jl:203-204)
 template <int VEC>
 __global__ void __launch_bounds__(TPB) k_neg_copy(i64 nu, double *__restrict__ g, double *__restrict__ d) {
@@ -261,6 +271,13 @@ int32_t lb_clear(sdplrp_handle *h) {
 int32_t lb_axpy(sdplrp_handle *h, double alpha, const double *x, double *y) {
     const Slice sl = owned(h);
     DISPATCH_VEC(sl, k_axpy, sl.nu, alpha, x + sl.off, y + sl.off);
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+
+int32_t lb_axpy2(sdplrp_handle *h, double alpha, const double *x1, double *y1, const double *x2, double *y2) {
+    const Slice sl = owned(h);
+    DISPATCH_VEC(sl, k_axpy2, sl.nu, alpha, x1 + sl.off, y1 + sl.off, x2 + sl.off, y2 + sl.off);
     CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
 }

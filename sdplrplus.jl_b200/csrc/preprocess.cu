@@ -291,6 +291,70 @@ int bits_for(i64 n) {
     return b;
 }
 
+
+// Cfull[k] = value of the objective at full-pattern slot k
+__global__ void k_cfull(i64 nnzF, const int *__restrict__ mapped, const double *__restrict__ st, double *__restrict__ cfull) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nnzF; k += (i64)gridDim.x * blockDim.x) {
+        const int t = mapped[k];
+        cfull[k] = t >= 0 ? st[t] : 0.0;
+    }
+}
+// mark the full-pattern slots (both mirrored positions) of every dynamic triu slot
+__global__ void k_dyn_mark(i64 nd, const int *__restrict__ pos_a, const int *__restrict__ pos_b, int *__restrict__ flag,
+                           int *__restrict__ src) {
+    for (i64 d = blockIdx.x * (i64)blockDim.x + threadIdx.x; d < nd; d += (i64)gridDim.x * blockDim.x) {
+        const int a = pos_a[d], b = pos_b[d];
+        if (a >= 0) { flag[a] = 1; src[a] = (int)d; }
+        if (b >= 0) { flag[b] = 1; src[b] = (int)d; }
+    }
+}
+__global__ void k_dyn_rows(i64 nnzF, const int *__restrict__ flag, const int *__restrict__ pos, const int *__restrict__ src,
+                           const int *__restrict__ full_idx, int *__restrict__ col, int *__restrict__ osrc) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nnzF; k += (i64)gridDim.x * blockDim.x)
+        if (flag[k]) { col[pos[k]] = full_idx[k]; osrc[pos[k]] = src[k]; }
+}
+__global__ void k_gather_ptr(i64 n, const int *__restrict__ full_ptr, const int *__restrict__ pos, int *__restrict__ out) {
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i <= n; i += (i64)gridDim.x * blockDim.x) out[i] = pos[full_ptr[i]];
+}
+__global__ void k_class_flags(i64 n, const int *__restrict__ ptr, int *__restrict__ f0, int *__restrict__ f1, int *__restrict__ f2) {
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const int len = ptr[i + 1] - ptr[i];
+        const int c = len <= kRowGroupMax ? 0 : (len <= kRowWarpMax ? 1 : 2);
+        f0[i] = c == 0; f1[i] = c == 1; f2[i] = c == 2;
+    }
+}
+
+// rows of a CSR pattern binned by length into three compacted lists
+int32_t build_classes(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, RowClasses &cls) {
+    cudaStream_t st = h->stream;
+    const int GS = 8 * kNumSM;
+    int32_t rc = SDPLRP_OK;
+    int *f[3], *p[3];
+    for (int c = 0; c < 3; c++) { f[c] = tmp.get<int>(h, n + 1, &rc); p[c] = tmp.get<int>(h, n + 1, &rc); }
+    if (rc) return rc;
+    for (int c = 0; c < 3; c++) CUDA_TRY(h, cudaMemsetAsync(f[c], 0, (size_t)(n + 1) * sizeof(int), st));
+    k_class_flags<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, ptr, f[0], f[1], f[2]); KLAUNCH(h);
+    int cnt[3];
+    for (int c = 0; c < 3; c++) {
+        SDP_CHECK(exclusive_scan(h, f[c], p[c], n + 1));
+        SDP_CHECK(read_int(h, p[c] + n, &cnt[c]));
+    }
+    dev_free(&cls.storage);
+    cls = RowClasses();
+    if (cnt[1] == 0 && cnt[2] == 0) {  // every row is short: identity order, no list
+        cls.cnt[0] = n;
+        return SDPLRP_OK;
+    }
+    SDP_CHECK(dev_alloc(h, &cls.storage, n));
+    i64 off = 0;
+    for (int c = 0; c < 3; c++) {
+        cls.list[c] = cls.storage + off;
+        cls.cnt[c] = cnt[c];
+        if (cnt[c] > 0) { k_compact_ids<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, f[c], p[c], cls.list[c]); KLAUNCH(h); }
+        off += cnt[c];
+    }
+    return SDPLRP_OK;
+}
 }  // namespace
 
 void pre_free(sdplrp_handle *h) {
@@ -299,7 +363,11 @@ void pre_free(sdplrp_handle *h) {
     dev_free(&h->ent_row); dev_free(&h->ent_col); dev_free(&h->ent_one); dev_free(&h->ent_two);
     dev_free(&h->long_mat); dev_free(&h->long_chunk_ptr); dev_free(&h->chunk_mat); dev_free(&h->chunk_part);
     dev_free(&h->triuS_static); dev_free(&h->dyn_slot); dev_free(&h->dyn_ptr); dev_free(&h->dyn_gid);
-    dev_free(&h->dyn_val); dev_free(&h->dyn_pos_a); dev_free(&h->dyn_pos_b); dev_free(&h->long_rows);
+    dev_free(&h->dyn_val); dev_free(&h->dyn_pos_a); dev_free(&h->dyn_pos_b);
+    dev_free(&h->Cfull); dev_free(&h->dynS); dev_free(&h->dynrow_ptr); dev_free(&h->dynrow_col); dev_free(&h->dynrow_src);
+    dev_free(&h->full_cls.storage); dev_free(&h->dyn_cls.storage);
+    h->full_cls = RowClasses(); h->dyn_cls = RowClasses();
+    h->CR_valid = h->CD_valid = false;
     h->preprocessed = false;
     h->S_static_valid = false;
 }
@@ -462,20 +530,32 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
         CUDA_TRY(h, cudaStreamSynchronize(st));
     }
 
-    // ---- SpMM row classes ---------------------------------------------------
-    h->n_long_rows = 0;
-    {
-        int *rflag = tmp.get<int>(h, n + 1, &rc), *rpos = tmp.get<int>(h, n + 1, &rc);
+    // ---- objective values on the full pattern + the dynamic pattern as CSR -------
+    SDP_CHECK(dev_alloc(h, &h->Cfull, nnzF));
+    SDP_CHECK(dev_alloc(h, &h->dynS, h->n_dyn));
+    SDP_CHECK(dev_alloc(h, &h->dynrow_ptr, n + 1));
+    h->n_dynF = 0;
+    if (nnzF > 0) {
+        k_cfull<<<GS, TPB, 0, st>>>(nnzF, h->mapped, h->triuS_static, h->Cfull); KLAUNCH(h);
+        int *fflag = tmp.get<int>(h, nnzF + 1, &rc), *fpos = tmp.get<int>(h, nnzF + 1, &rc), *fsrc = tmp.get<int>(h, nnzF + 1, &rc);
         if (rc) return rc;
-        CUDA_TRY(h, cudaMemsetAsync(rflag, 0, (size_t)(n + 1) * sizeof(int), st));
-        k_len_flag<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, h->full_ptr, kLongRowThreshold, rflag); KLAUNCH(h);
-        SDP_CHECK(exclusive_scan(h, rflag, rpos, n + 1));
-        int nlr = 0;
-        SDP_CHECK(read_int(h, rpos + n, &nlr));
-        h->n_long_rows = nlr;
-        SDP_CHECK(dev_alloc(h, &h->long_rows, nlr));
-        if (nlr > 0) { k_compact_ids<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, rflag, rpos, h->long_rows); KLAUNCH(h); }
+        CUDA_TRY(h, cudaMemsetAsync(fflag, 0, (size_t)(nnzF + 1) * sizeof(int), st));
+        if (h->n_dyn > 0) { k_dyn_mark<<<GS, TPB, 0, st>>>(h->n_dyn, h->dyn_pos_a, h->dyn_pos_b, fflag, fsrc); KLAUNCH(h); }
+        SDP_CHECK(exclusive_scan(h, fflag, fpos, nnzF + 1));
+        int ndf = 0;
+        SDP_CHECK(read_int(h, fpos + nnzF, &ndf));
+        h->n_dynF = ndf;
+        SDP_CHECK(dev_alloc(h, &h->dynrow_col, ndf)); SDP_CHECK(dev_alloc(h, &h->dynrow_src, ndf));
+        if (ndf > 0) { k_dyn_rows<<<GS, TPB, 0, st>>>(nnzF, fflag, fpos, fsrc, h->full_idx, h->dynrow_col, h->dynrow_src); KLAUNCH(h); }
+        k_gather_ptr<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, h->full_ptr, fpos, h->dynrow_ptr); KLAUNCH(h);
+    } else {
+        CUDA_TRY(h, cudaMemsetAsync(h->dynrow_ptr, 0, (size_t)(n + 1) * sizeof(int), st));
+        SDP_CHECK(dev_alloc(h, &h->dynrow_col, 0)); SDP_CHECK(dev_alloc(h, &h->dynrow_src, 0));
     }
+
+    // ---- row bins of both patterns (sparse x dense kernels) -----------------------
+    SDP_CHECK(build_classes(h, tmp, n, h->full_ptr, h->full_cls));
+    SDP_CHECK(build_classes(h, tmp, n, h->dynrow_ptr, h->dyn_cls));
     CUDA_TRY(h, cudaStreamSynchronize(st));
     CUDA_TRY(h, cudaGetLastError());
     h->preprocessed = true;

@@ -95,12 +95,14 @@ def algorithmic_bytes(n, m, r, nnzT, nnzF, Ec, h, rows_local):
     frac = rows_local / float(n)
     return {
         "lbfgs_dir": (8 * h + 3) * N,                                             # fused two-loop, 35N at h=4
-        "ls_pass": 2 * N + frac * (4 * (n + 1) + 4 * nnzT + 12 * Ec + 16 * (m + 1)),
+        # constraint part of the fused {A(RD'+DR'), A(DD')} pass (the objective slot rides on the spmm pass)
+        "ls_pass": 2 * N + frac * (12.0 * (Ec - nnzT) + 8.0 * m + 16 * (m + 1)),
         "ls_coeff": 32.0 * m,
-        "step": 3 * N + 24.0 * (m + 1),
-        "s_assemble": 32.0 * m + 12.0 * (Ec - nnzT) + 16.0 * m,                   # y + dynamic slots (fused figure)
-        "spmm": 2 * N + frac * (4 * (n + 1) + 12 * nnzF),
-        "norms": N + 16.0 * m,
+        "step": 6 * N + 24.0 * (m + 1),                                           # R += aD and CR += a*CD
+        "s_assemble": 32.0 * m,                                                   # y formation
+        "spmm": 2 * N + frac * (4 * (n + 1) + 12 * nnzF),                         # CD = C*D: SURVEY 8d B_G
+        "grad": 3 * N + frac * (12.0 * (Ec - nnzT) + 8.0 * m + 4.0 * (n + 1)),    # G = 2(y_obj CR + S_dyn R), ||G||^2
+        "norms": 16.0 * m,
         "lbfgs_update": 5 * N,
     }
 

@@ -250,6 +250,9 @@ def test_lbfgs_teacher_forced(sp, oracle_mod, handle, hist):
         nrm = np.linalg.norm(Do)
         assert np.linalg.norm(Dg - Do) <= 1e-10 * nrm, f"direction it={it}"
         assert abs(dg - do) <= 1e-10 * max(1.0, abs(do))
+        if do >= 0:  # numlbfgsvecs == 0 returns dir = +grad: the caller takes the fallback (src/sdplr.jl:201-205)
+            ge.use_gradient_direction(); oe.use_gradient_direction()
+            Do = oe.get_D()
         ge.set_D(Do)
         bq = oe.linesearch_coeffs(); ge.linesearch_coeffs()
         alpha, _ = sp.pick_alpha(bq, 1.0)
@@ -305,9 +308,14 @@ def test_free_running_first_iterations(sp, oracle_mod, handle, which):
     ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, r)
     fg_g, fg_o = ge.fg(), oe.fg()
     _relclose(fg_g, fg_o, 1e-11, "fg0")
+    L_prev = fg_o[0]
     for it in range(40):
         dg, do = ge.lbfgs_dir(), oe.lbfgs_dir()
-        assert abs(dg - do) <= 1e-9 * max(1.0, abs(do)), f"descent it={it}"
+        if math.isnan(do) or do >= 0:  # the caller's non-descent fallback (src/sdplr.jl:201-205)
+            assert math.isnan(dg) or dg >= 0, f"fallback decision it={it}"
+            ge.use_gradient_direction(); oe.use_gradient_direction()
+        else:
+            assert abs(dg - do) <= 1e-9 * max(1.0, abs(do)), f"descent it={it}"
         bqg, bqo = ge.linesearch_coeffs(), oe.linesearch_coeffs()
         ag, Lg = sp.pick_alpha(bqg, 1.0); ao, Lo = sp.pick_alpha(bqo, 1.0)
         objg, objo = ge.step(ag), oe.step(ao)
@@ -316,6 +324,10 @@ def test_free_running_first_iterations(sp, oracle_mod, handle, which):
         assert abs(Lg - Lo) <= 1e-10 * max(1.0, abs(Lo)), f"L it={it}"
         assert abs(math.sqrt(p2) - math.sqrt(op2)) <= 1e-10 * max(1.0, math.sqrt(op2)), f"pnorm it={it}"
         assert abs(math.sqrt(g2) - math.sqrt(og2)) <= 1e-8 * max(1.0, math.sqrt(og2)), f"gnorm it={it}"
+        # the caller's fprec break comes BEFORE lbfgs_update! (src/sdplr.jl:238-246): a zero step would make rho = 1/0
+        if (L_prev - Lo) / max(1.0, abs(Lo), abs(L_prev)) < 1e8 * np.finfo(float).eps:
+            break
+        L_prev = Lo
         ge.lbfgs_update(ag); oe.lbfgs_update(ao)
 
 

@@ -87,6 +87,13 @@ int32_t sdplrp_synchronize(sdplrp_handle *h);
 /* the CUDA stream the handle launches on (a cudaStream_t), for event timing */
 void *sdplrp_stream(sdplrp_handle *h);
 
+/* tuning knobs (all optional; defaults are the product configuration):
+ *   "relabel"     -1 auto (default) / 0 off / 1 on: internal hub-first vertex order, set BEFORE
+ *                 sdplrp_preprocess.  Invisible at the ABI (every upload/download converts).
+ *   "hot_rows"    leading rows of the gathered factor pinned in L2 (evict_last); -1 = sized from L2
+ *   "spmm_kernel" 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel (experimental) */
+int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value);
+
 /* ---- preprocessing: preprocess_sparsecons + SolverAuxiliary ------------
  * The nA sparse matrices (sparse / diagonal A_i in order of appearance, then
  * C if it is sparse: src/structs.jl:303-325) as concatenated 1-based triplets

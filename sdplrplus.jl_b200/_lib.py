@@ -32,6 +32,7 @@ _SIGNATURES = {
     "sdplrp_create": [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(_H)],
     "sdplrp_destroy": [_H],
     "sdplrp_synchronize": [_H],
+    "sdplrp_set_option": [_H, C.c_char_p, C.c_double],
     "sdplrp_preprocess": [_H, C.c_int64, C.c_int64, C.c_int64, _p_i64, _p_i64, _p_i64, _p_f64, _p_i64],
     "sdplrp_pattern_sizes": [_H, _p_i64, _p_i64, _p_i64],
     "sdplrp_pattern_export": [_H, _p_i64, _p_i64, _p_i64, _p_i64, _p_f64, _p_f64, _p_i64, _p_i64, _p_i64],
@@ -139,6 +140,10 @@ class Handle:
         if rc != 0 and rc not in allow:
             raise SdplrpError(rc, self.lib.sdplrp_last_error(self._h).decode())
         return rc
+
+    def set_option(self, key, value):
+        """Tuning knobs of include/sdplrp_b200.h ("relabel" must be set before preprocess)."""
+        self._check(self.lib.sdplrp_set_option(self._h, str(key).encode(), float(value)))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

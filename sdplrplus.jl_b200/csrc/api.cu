@@ -3,6 +3,7 @@
 // replaces).  There is no CPU fallback: without a CUDA device sdplrp_create
 // fails with SDPLRP_ERR_NO_DEVICE.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "common.cuh"
@@ -114,6 +115,9 @@ int32_t sdplrp_create(int32_t device, int32_t rank, int32_t world, const void *n
     if (cudaSetDevice(device) != cudaSuccess) return SDPLRP_ERR_CUDA;
     sdplrp_handle *h = new sdplrp_handle();
     h->device = device; h->rank = rank; h->world = world;
+    if (const char *e = getenv("SDPLRP_RELABEL")) h->relabel_mode = atoi(e) < 0 ? -1 : (atoi(e) > 0 ? 1 : 0);
+    if (const char *e = getenv("SDPLRP_SPMM_KERNEL")) h->spmm_kernel = atoi(e);
+    if (const char *e = getenv("SDPLRP_HOT_ROWS")) h->hot_rows = atoll(e);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SDPLRP_ERR_CUDA; }
     bool ok = cudaMalloc((void **)&h->dscal, SC_COUNT * sizeof(double)) == cudaSuccess &&
               cudaMallocHost((void **)&h->hscal, SC_COUNT * sizeof(double)) == cudaSuccess &&
@@ -147,6 +151,7 @@ static void free_problem(sdplrp_handle *h) {
     dev_free(&h->y); dev_free(&h->pvio_raw); dev_free(&h->A_RD); dev_free(&h->A_DD); dev_free(&h->A_out);
     dev_free(&h->lz_v); dev_free(&h->lz_w); dev_free(&h->lz_vp); dev_free(&h->lz_ab); dev_free(&h->lz_basis);
     h->lz_ab_len = 0; h->lz_basis_len = 0;
+    dev_free(&h->stage); h->stage_len = 0;
 }
 
 int32_t sdplrp_destroy(sdplrp_handle *h) {
@@ -230,9 +235,9 @@ int32_t sdplrp_add_symlowrank(sdplrp_handle *h, int64_t global_id, int64_t s, co
     L.gid = global_id - 1; L.s = s; L.dB = nullptr; L.dD = nullptr;
     SDP_CHECK(dev_alloc(h, &L.dB, h->n * s));
     SDP_CHECK(dev_alloc(h, &L.dD, s));
-    CUDA_TRY(h, cudaMemcpy(L.dB, B, (size_t)(h->n * s) * 8, cudaMemcpyHostToDevice));
+    h->lr.push_back(L);  // owned by the handle from here on (freed by free_problem even if a copy fails)
+    SDP_CHECK(perm_upload(h, L.dB, B, s, false));  // rows of B follow the internal vertex order
     CUDA_TRY(h, cudaMemcpy(L.dD, D, (size_t)s * 8, cudaMemcpyHostToDevice));
-    h->lr.push_back(L);
     return SDPLRP_OK;
 }
 
@@ -275,6 +280,16 @@ int32_t sdplrp_set_rank(sdplrp_handle *h, int32_t r, int32_t numlbfgsvecs) {
     return SDPLRP_OK;
 }
 
+int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
+    REQUIRE_H(h);
+    if (!key) return fail(h, SDPLRP_ERR_ARG, "set_option: null key");
+    const std::string k(key);
+    if (k == "relabel") { h->relabel_mode = value < 0 ? -1 : (value > 0 ? 1 : 0); return SDPLRP_OK; }  // before preprocess
+    if (k == "hot_rows") { h->hot_rows = (i64)value; return SDPLRP_OK; }
+    if (k == "spmm_kernel") { h->spmm_kernel = (int)value; return SDPLRP_OK; }
+    return fail(h, SDPLRP_ERR_ARG, "set_option: unknown key " + k);
+}
+
 int32_t sdplrp_set_sigma(sdplrp_handle *h, double sigma) { REQUIRE_H(h); h->sigma = sigma; return SDPLRP_OK; }
 int32_t sdplrp_get_sigma(sdplrp_handle *h, double *sigma) { REQUIRE_H(h); *sigma = h->sigma; return SDPLRP_OK; }
 int32_t sdplrp_get_obj(sdplrp_handle *h, double *obj) {
@@ -298,8 +313,7 @@ int32_t sdplrp_upload_mat(sdplrp_handle *h, int32_t id, const double *src) {
     SDP_CHECK(lazy_scratch(h, id));
     double *p = mat_ptr(h, id);
     if (!p || !src) return fail(h, SDPLRP_ERR_ARG, "upload_mat: bad id");
-    CUDA_TRY(h, cudaMemcpyAsync(p, src, (size_t)h->n * h->r * 8, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    SDP_CHECK(perm_upload(h, p, src, h->r, true));
     comm_mark_full(h, id);
     if (id == SDPLRP_MAT_R) h->CR_valid = false;
     if (id == SDPLRP_MAT_D) h->CD_valid = false;
@@ -314,9 +328,7 @@ int32_t sdplrp_download_mat(sdplrp_handle *h, int32_t id, double *dst) {
     double *p = mat_ptr(h, id);
     if (!p || !dst) return fail(h, SDPLRP_ERR_ARG, "download_mat: bad id");
     SDP_CHECK(comm_gather_rows(h, p, id));
-    CUDA_TRY(h, cudaMemcpyAsync(dst, p, (size_t)h->n * h->r * 8, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return SDPLRP_OK;
+    return perm_download(h, p, dst, h->r, true);
 }
 
 int32_t sdplrp_upload_vec(sdplrp_handle *h, int32_t id, const double *src, int64_t len) {
@@ -326,10 +338,14 @@ int32_t sdplrp_upload_vec(sdplrp_handle *h, int32_t id, const double *src, int64
     i64 want = 0;
     double *p = vec_ptr(h, id, &want);
     if (!p || !src || len != want) return fail(h, SDPLRP_ERR_ARG, "upload_vec: bad id or length");
-    if (len > 0) CUDA_TRY(h, cudaMemcpyAsync(p, src, (size_t)len * 8, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    if (id == SDPLRP_VEC_Y) h->y_obj = src[h->m];
-    if (id == SDPLRP_VEC_S_NZVAL) h->S_static_valid = false;
+    if (id == SDPLRP_VEC_S_NZVAL) {
+        SDP_CHECK(perm_slots_upload(h, p, src, len));
+    } else {
+        if (len > 0) CUDA_TRY(h, cudaMemcpyAsync(p, src, (size_t)len * 8, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    if (id == SDPLRP_VEC_Y) { h->y_obj = src[h->m]; h->S_current = false; }
+    if (id == SDPLRP_VEC_S_NZVAL) { h->S_static_valid = false; h->S_current = true; }
     return SDPLRP_OK;
 }
 
@@ -353,6 +369,7 @@ int32_t sdplrp_download_vec(sdplrp_handle *h, int32_t id, double *dst, int64_t l
     i64 want = 0;
     double *p = vec_ptr(h, id, &want);
     if (!p || !dst || len != want) return fail(h, SDPLRP_ERR_ARG, "download_vec: bad id or length");
+    if (id == SDPLRP_VEC_S_NZVAL) return perm_slots_download(h, p, dst, len);
     if (len > 0) CUDA_TRY(h, cudaMemcpyAsync(dst, p, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return SDPLRP_OK;
@@ -409,6 +426,7 @@ int32_t sdplrp_At_left(sdplrp_handle *h, int32_t X_id, int32_t Y_id) {
     double *Y = mat_ptr(h, Y_id);
     if (!X || !Y || X == Y) return fail(h, SDPLRP_ERR_ARG, "At_left: bad matrix ids");
     SDP_CHECK(comm_require_full(h, X_id));
+    if (!h->S_current) SDP_CHECK(grad_assemble_S(h));
     SDP_CHECK(grad_spmm(h, X, Y, 1.0, false));
     comm_mark_partial(h, Y_id);
     return SDPLRP_OK;
@@ -422,12 +440,10 @@ int32_t sdplrp_At_right(sdplrp_handle *h, const double *x, double *y, int64_t nc
     const i64 len = h->n * ncols;
     SDP_CHECK(dev_alloc(h, &dx, len));
     int32_t rc = dev_alloc(h, &dy, len);
-    if (rc == SDPLRP_OK) {
-        cudaError_t e = cudaMemcpyAsync(dx, x, (size_t)len * 8, cudaMemcpyHostToDevice, h->stream);
-        if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = SDPLRP_ERR_CUDA; }
-    }
+    if (rc == SDPLRP_OK && !h->S_current) rc = grad_assemble_S(h);
+    if (rc == SDPLRP_OK) rc = perm_upload(h, dx, x, ncols, false);
     if (rc == SDPLRP_OK) rc = grad_spmv(h, dx, dy, ncols);
-    if (rc == SDPLRP_OK) rc = copy_out(h, dy, y, len);
+    if (rc == SDPLRP_OK) rc = perm_download(h, dy, y, ncols, false);
     cudaFree(dx);
     if (dy) cudaFree(dy);
     return rc;
@@ -618,6 +634,7 @@ int32_t sdplrp_lanczos(sdplrp_handle *h, int64_t q, const double *v0, uint64_t s
     if (q < 1 || !alpha || !beta || !iters) return fail(h, SDPLRP_ERR_ARG, "lanczos: bad argument");
     CUDA_TRY(h, cudaSetDevice(h->device));
     i64 it = 0;
+    if (!h->S_current) SDP_CHECK(grad_assemble_S(h));  // S for the device y (g! no longer materialises it)
     {
         SectionScope sc(h, SDPLRP_SEC_LANCZOS);
         SDP_CHECK(lz_run(h, q, v0, seed, reorth, alpha, beta, &it));

@@ -28,6 +28,15 @@ struct RowClasses {
     int *storage = nullptr;
 };
 
+// rows longer than one tile of the async-copy SpMM (spmm.cu) cut into chunks
+constexpr int kTileChunk = 64;          // == kTileNnz of spmm.cu
+struct TileLayout {
+    long long n_long = 0, n_chunks = 0;
+    int *long_rows = nullptr;    // n_long   rows with more than kTileChunk nonzeros (ascending)
+    int *long_cptr = nullptr;    // n_long+1 first chunk of each long row
+    int *chunk_start = nullptr, *chunk_end = nullptr, *chunk_row = nullptr;  // n_chunks
+};
+
 struct LowRank {
     i64 gid;     // 0-based global slot
     i64 s;
@@ -66,15 +75,27 @@ struct sdplrp_handle {
     bool preprocessed = false;
 
     // aggregated patterns (0-based int32 on device)
-    int *triu_colptr = nullptr, *triu_rowval = nullptr;  // n+1, nnzT   (CSC of triu == CSR of tril)
-    int *full_ptr = nullptr, *full_idx = nullptr;        // n+1, nnzF   (symmetric: CSC == CSR)
-    int *mapped = nullptr;                               // nnzF -> triu slot
-    double *S = nullptr;                                 // nnzF  sparse_S.nzval
+    int *triu_colptr = nullptr, *triu_rowval = nullptr;  // n+1, nnzT   (CSC of triu == CSR of tril), reference labels
+    int *ref_full_ptr = nullptr, *ref_full_idx = nullptr;  // n+1, nnzF  agg_sparse_A in reference labels (export only)
+    int *mapped = nullptr;                               // nnzF (reference slot) -> triu slot
+    // internal vertex order: rows sorted by descending degree (hubs first) so that the hot rows of the
+    // gathered factor are contiguous and the row classes are ranges.  Invisible at the ABI: uploads and
+    // downloads of anything indexed by vertex go through perm / iperm.
+    bool relabeled = false;
+    int relabel_mode = -1;                               // -1 auto, 0 off, 1 on (sdplrp_set_option "relabel")
+    int *perm = nullptr, *iperm = nullptr;               // n: internal label of reference vertex / its inverse
+    int *i2r = nullptr, *r2i = nullptr;                  // nnzF: internal full slot <-> reference full slot
+    int *full_ptr = nullptr, *full_idx = nullptr;        // n+1, nnzF   the symmetric pattern as CSR in INTERNAL labels
+    double *S = nullptr;                                 // nnzF  sparse_S.nzval (internal slot order)
+    double *stage = nullptr;                             // n x r staging buffer of the permuting copies
+    i64 stage_len = 0;
+    i64 hot_rows = -1;                                   // leading (hub) rows of a gathered factor kept in L2; -1 = auto
+    int spmm_kernel = 0;                                 // 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel
     // per-entry lists in reference order (E_c)
     int *matptr = nullptr;     // nA+1
     int *mat_gid = nullptr;    // nA   0-based global slot of each sparse matrix
     int *ent_slot = nullptr;   // Ec   nzind (0-based triu slot)
-    int *ent_row = nullptr, *ent_col = nullptr;  // Ec   coordinates of that slot (row <= col)
+    int *ent_row = nullptr, *ent_col = nullptr;  // Ec   coordinates of that slot in INTERNAL labels
     double *ent_one = nullptr, *ent_two = nullptr;  // Ec
     // chunked ("long") matrices for the A passes
     i64 n_long = 0, n_chunks = 0;
@@ -87,6 +108,7 @@ struct sdplrp_handle {
     double *triuS_static = nullptr;  // nnzT: contribution of the objective matrix (unit y)
     double S_static_scale = 0.0;     // y_{m+1} the static part of S currently carries
     bool S_static_valid = false;
+    bool S_current = false;          // S (full pattern) matches the device y / was uploaded by the caller
     i64 n_dyn = 0;                 // triu slots with at least one non-objective contributor
     int *dyn_slot = nullptr;       // n_dyn: triu slot
     int *dyn_ptr = nullptr;        // n_dyn+1 into dyn_mat/dyn_val
@@ -101,6 +123,9 @@ struct sdplrp_handle {
     int *dynrow_col = nullptr;     // n_dynF
     int *dynrow_src = nullptr;     // n_dynF -> index into dynS
     RowClasses full_cls, dyn_cls;  // row bins of the full / dynamic pattern
+    TileLayout full_tile, dyn_tile; // long-row chunk lists of both patterns (spmm.cu)
+    double *tile_scratch = nullptr; // chunk partial sums, max(n_chunks) x r
+    i64 tile_scratch_len = 0;
     double *CR = nullptr, *CD = nullptr;  // n x r: C*R (recurrence) and C*D
     bool CR_valid = false, CD_valid = false;
 
@@ -274,6 +299,13 @@ int32_t grad_hot(sdplrp_handle *h);                             // G = 2*(y_obj*
 int32_t grad_spmv(sdplrp_handle *h, const double *x, double *y, i64 ncols);                     // y = S*x (+low rank), n x ncols col-major
 int32_t grad_triuS(sdplrp_handle *h, double *out_dev);          // materialise triu_sparse_S.nzval
 
+// async-copy tile-stream SpMM (spmm.cu)
+bool tile_supported(const sdplrp_handle *h);
+i64 tile_hot_rows(const sdplrp_handle *h);
+int32_t tile_spmm(sdplrp_handle *h, const TileLayout &lay, const int *ptr, const int *idx, const double *val, const int *src,
+                  const double *X, double *Y, int epi, double scale, double yobj, const double *E0, const double *E1,
+                  double *sums2);
+
 // m-vector kernels (vecops.cu)
 int32_t vec_f_finish(sdplrp_handle *h);      // raw -= b, obj, AL value -> SC_OBJ, SC_LVAL
 int32_t vec_biquadratic(sdplrp_handle *h);   // SC_BQ..SC_BQ+4
@@ -309,6 +341,14 @@ int32_t comm_reduce_mvec(sdplrp_handle *h, double *v1, double *v2);
 int32_t comm_reduce_scalars(sdplrp_handle *h, int slot, int count);
 int32_t comm_reduce_ptr(sdplrp_handle *h, double *p, int count);
 int32_t comm_step_R(sdplrp_handle *h, double alpha);
+
+// reference order <-> internal order (perm.cu)
+int32_t perm_stage(sdplrp_handle *h, i64 len);
+int32_t perm_upload(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 ncols, bool row_major);
+int32_t perm_download(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 ncols, bool row_major);
+int32_t perm_device(sdplrp_handle *h, double *dst, const double *src, i64 ncols, bool row_major, bool to_internal);
+int32_t perm_slots_upload(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 len);
+int32_t perm_slots_download(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 len);
 
 // section timers (api.cu)
 cudaEvent_t prof_begin(sdplrp_handle *h);

@@ -448,12 +448,14 @@ int32_t grad_form_y(sdplrp_handle *h) {
     k_form_y<<<grid_for(h->m + 1, TPB, kRedBlocks), TPB, 0, h->stream>>>(h->m, h->sigma, h->lambda, h->lambda_ub, h->pvio_raw, h->y);
     KLAUNCH(h);
     h->y_obj = 1.0;
+    h->S_current = false;  // the hot loop never materialises S; Lanczos / At! re-assemble on demand
     CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
 }
 
 // At_preprocess!: materialise S = y_obj*C + S_dyn(y) on the full pattern (seam-level / Lanczos)
 int32_t grad_assemble_S(sdplrp_handle *h) {
+    h->S_current = true;
     if (h->nA <= 0) return SDPLRP_OK;
     cudaStream_t st = h->stream;
     const double yobj = (h->obj_mat >= 0) ? h->y_obj : 0.0;
@@ -492,7 +494,9 @@ int32_t grad_triuS(sdplrp_handle *h, double *out) {
 // seam-level At!(Y, X): Y = scale * (X*S + sum_g y_g X B D B') over the owned rows, S as last assembled
 int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bool /*want_norm*/) {
     const int r = h->r;
-    if (h->nA > 0) {
+    if (h->nA > 0 && tile_supported(h)) {
+        SDP_CHECK(tile_spmm(h, h->full_tile, h->full_ptr, h->full_idx, h->S, nullptr, X, Y, 0, scale, 0.0, nullptr, nullptr, nullptr));
+    } else if (h->nA > 0) {
         RowArgs a = {};
         a.ptr = h->full_ptr; a.idx = h->full_idx; a.val = h->S; a.src = nullptr;
         a.X = X; a.Y = Y; a.scale = scale;
@@ -505,6 +509,10 @@ int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bo
 
 // Y = C*X over the owned rows with the fused sums  out0 = <X, Y>, out1 = <X, Z>  (Z may be null)
 int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double *Z, double *sums6) {
+    if (tile_supported(h)) {
+        CUDA_TRY(h, cudaMemsetAsync(sums6, 0, 6 * sizeof(double), h->stream));
+        return tile_spmm(h, h->full_tile, h->full_ptr, h->full_idx, h->Cfull, nullptr, X, Y, 2, 1.0, 0.0, X, Z, sums6);
+    }
     RowArgs a = {};
     a.ptr = h->full_ptr; a.idx = h->full_idx; a.val = h->Cfull; a.src = nullptr;
     a.X = X; a.Y = Y; a.Z = Z; a.scale = 1.0;
@@ -521,12 +529,18 @@ int32_t grad_hot(sdplrp_handle *h) {
                                                                            h->dyn_pos_a, h->dyn_pos_b, h->triuS_static, h->y, h->dynS);
         KLAUNCH(h);
     }
-    RowArgs a = {};
-    a.ptr = h->dynrow_ptr; a.idx = h->dynrow_col; a.val = h->dynS; a.src = h->dynrow_src;
-    a.X = h->R; a.Y = h->G; a.scale = 2.0;
-    a.ADD = (h->obj_mat >= 0) ? h->CR : nullptr;
-    a.yobj = h->y_obj;
-    SDP_CHECK((launch_csr<true, 1>(h, a, h->dyn_cls, sums)));
+    if (tile_supported(h)) {
+        CUDA_TRY(h, cudaMemsetAsync(sums, 0, 6 * sizeof(double), st));
+        SDP_CHECK(tile_spmm(h, h->dyn_tile, h->dynrow_ptr, h->dynrow_col, h->dynS, h->dynrow_src, h->R, h->G, 1, 2.0, h->y_obj,
+                            (h->obj_mat >= 0) ? h->CR : nullptr, nullptr, sums));
+    } else {
+        RowArgs a = {};
+        a.ptr = h->dynrow_ptr; a.idx = h->dynrow_col; a.val = h->dynS; a.src = h->dynrow_src;
+        a.X = h->R; a.Y = h->G; a.scale = 2.0;
+        a.ADD = (h->obj_mat >= 0) ? h->CR : nullptr;
+        a.yobj = h->y_obj;
+        SDP_CHECK((launch_csr<true, 1>(h, a, h->dyn_cls, sums)));
+    }
     if (h->lr.empty()) {
         k_sum_slots<<<1, 1, 0, st>>>(3, sums, 2, h->dscal + SC_GNORM2);
         KLAUNCH(h);

@@ -205,7 +205,7 @@ int32_t lz_run(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, in
     CUDA_TRY(h, cudaMemsetAsync(vp, 0, (size_t)n * sizeof(double), st));
     const int gs = grid_for(n, TPB, kRedBlocks);
     if (v0_host) {
-        CUDA_TRY(h, cudaMemcpyAsync(v, v0_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+        SDP_CHECK(perm_upload(h, v, v0_host, 1, false));  // the start vector follows the internal vertex order
     } else {
         k_lz_randn<<<gs, TPB, 0, st>>>(n, seed, v); KLAUNCH(h);
     }

@@ -179,7 +179,8 @@ __global__ void k_dyn_fill(i64 nnzT, const int *__restrict__ slot_ptr, const int
                            const int *__restrict__ ent_mat, const double *__restrict__ one, const int *__restrict__ mat_gid,
                            int obj_mat, const int *__restrict__ dyn_flag, const int *__restrict__ dyn_index,
                            const int *__restrict__ dyn_off, const int *__restrict__ triu_rowval,
-                           const unsigned long long *__restrict__ keyT, const int *__restrict__ full_ptr,
+                           const unsigned long long *__restrict__ keyT, const int *__restrict__ perm,
+                           const int *__restrict__ full_ptr,
                            const int *__restrict__ full_idx, int *__restrict__ dyn_slot, int *__restrict__ dyn_ptr,
                            int *__restrict__ dyn_gid, double *__restrict__ dyn_val, int *__restrict__ pos_a,
                            int *__restrict__ pos_b) {
@@ -198,6 +199,7 @@ __global__ void k_dyn_fill(i64 nnzT, const int *__restrict__ slot_ptr, const int
             o++;
         }
         int row = triu_rowval[s], col = (int)(keyT[s] >> 32);
+        if (perm) { row = perm[row]; col = perm[col]; }  // positions in the INTERNAL full pattern
         pos_a[d] = csc_find(full_ptr, full_idx, col, row);
         pos_b[d] = csc_find(full_ptr, full_idx, row, col);
     }
@@ -293,9 +295,10 @@ int bits_for(i64 n) {
 
 
 // Cfull[k] = value of the objective at full-pattern slot k
-__global__ void k_cfull(i64 nnzF, const int *__restrict__ mapped, const double *__restrict__ st, double *__restrict__ cfull) {
+__global__ void k_cfull(i64 nnzF, const int *__restrict__ mapped, const int *__restrict__ i2r, const double *__restrict__ st,
+                        double *__restrict__ cfull) {
     for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nnzF; k += (i64)gridDim.x * blockDim.x) {
-        const int t = mapped[k];
+        const int t = mapped[i2r ? i2r[k] : k];
         cfull[k] = t >= 0 ? st[t] : 0.0;
     }
 }
@@ -322,6 +325,33 @@ __global__ void k_class_flags(i64 n, const int *__restrict__ ptr, int *__restric
         const int c = len <= kRowGroupMax ? 0 : (len <= kRowWarpMax ? 1 : 2);
         f0[i] = c == 0; f1[i] = c == 1; f2[i] = c == 2;
     }
+}
+
+
+// ---- internal vertex order (descending degree) ------------------------------------
+__global__ void k_deg_key(i64 n, const int *__restrict__ ptr, unsigned *__restrict__ key, int *__restrict__ val) {
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        key[i] = (unsigned)(n - (i64)(ptr[i + 1] - ptr[i]));  // ascending key == descending degree
+        val[i] = (int)i;
+    }
+}
+__global__ void k_invert_perm(i64 n, const int *__restrict__ iperm, int *__restrict__ perm) {
+    for (i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x; p < n; p += (i64)gridDim.x * blockDim.x) perm[iperm[p]] = (int)p;
+}
+// reference full slot k = (ref row = key >> 32 seen as CSR row, ref col = low 32) -> internal key
+__global__ void k_internal_keys(i64 nnzF, const unsigned long long *__restrict__ keyF, const int *__restrict__ perm,
+                                unsigned long long *__restrict__ ikey, int *__restrict__ payload) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nnzF; k += (i64)gridDim.x * blockDim.x) {
+        const int a = (int)(keyF[k] >> 32), b = (int)(unsigned)(keyF[k] & 0xffffffffull);
+        ikey[k] = make_key(perm[b], perm[a]);  // (row-major key: high = internal row perm[a], low = internal col perm[b])
+        payload[k] = (int)k;
+    }
+}
+__global__ void k_scatter_inverse(i64 nItems, const int *__restrict__ fwd, int *__restrict__ inv) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nItems; k += (i64)gridDim.x * blockDim.x) inv[fwd[k]] = (int)k;
+}
+__global__ void k_apply_perm(i64 nItems, const int *__restrict__ perm, int *__restrict__ x) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nItems; k += (i64)gridDim.x * blockDim.x) x[k] = perm[x[k]];
 }
 
 // rows of a CSR pattern binned by length into three compacted lists
@@ -355,10 +385,73 @@ int32_t build_classes(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, RowClas
     }
     return SDPLRP_OK;
 }
+__global__ void k_tile_chunk_counts(i64 nLong, const int *__restrict__ long_rows, const int *__restrict__ ptr, int *__restrict__ cnt) {
+    for (i64 l = blockIdx.x * (i64)blockDim.x + threadIdx.x; l < nLong; l += (i64)gridDim.x * blockDim.x) {
+        const int i = long_rows[l];
+        cnt[l] = (ptr[i + 1] - ptr[i] + kTileChunk - 1) / kTileChunk;
+    }
+}
+__global__ void k_tile_chunks(i64 nChunks, i64 nLong, const int *__restrict__ long_rows, const int *__restrict__ long_cptr,
+                              const int *__restrict__ ptr, int *__restrict__ cstart, int *__restrict__ cend, int *__restrict__ crow) {
+    for (i64 c = blockIdx.x * (i64)blockDim.x + threadIdx.x; c < nChunks; c += (i64)gridDim.x * blockDim.x) {
+        i64 lo = 0, hi = nLong - 1;  // last l with long_cptr[l] <= c
+        while (lo < hi) {
+            i64 mid = (lo + hi + 1) >> 1;
+            if (long_cptr[mid] <= (int)c) lo = mid; else hi = mid - 1;
+        }
+        const int i = long_rows[lo];
+        const int s = ptr[i] + ((int)c - long_cptr[lo]) * kTileChunk;
+        cstart[c] = s;
+        cend[c] = min(s + kTileChunk, ptr[i + 1]);
+        crow[c] = i;
+    }
+}
+
+void tile_free(TileLayout &t) {
+    dev_free(&t.long_rows); dev_free(&t.long_cptr); dev_free(&t.chunk_start); dev_free(&t.chunk_end); dev_free(&t.chunk_row);
+    t.n_long = 0; t.n_chunks = 0;
+}
+
+// chunk lists of the rows that do not fit one tile of the async-copy SpMM
+int32_t tile_build(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, TileLayout &t) {
+    cudaStream_t st = h->stream;
+    const int GS = 8 * kNumSM;
+    int32_t rc = SDPLRP_OK;
+    tile_free(t);
+    int *lflag = tmp.get<int>(h, n + 1, &rc), *lpos = tmp.get<int>(h, n + 1, &rc);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemsetAsync(lflag, 0, (size_t)(n + 1) * sizeof(int), st));
+    k_len_flag<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, ptr, kTileChunk, lflag); KLAUNCH(h);
+    SDP_CHECK(exclusive_scan(h, lflag, lpos, n + 1));
+    int nl = 0;
+    SDP_CHECK(read_int(h, lpos + n, &nl));
+    t.n_long = nl;
+    if (nl == 0) return SDPLRP_OK;
+    SDP_CHECK(dev_alloc(h, &t.long_rows, nl)); SDP_CHECK(dev_alloc(h, &t.long_cptr, nl + 1));
+    int *ccnt = tmp.get<int>(h, nl + 1, &rc);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemsetAsync(ccnt, 0, (size_t)(nl + 1) * sizeof(int), st));
+    k_compact_ids<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, lflag, lpos, t.long_rows); KLAUNCH(h);
+    k_tile_chunk_counts<<<grid_for(nl, TPB, GS), TPB, 0, st>>>(nl, t.long_rows, ptr, ccnt); KLAUNCH(h);
+    SDP_CHECK(exclusive_scan(h, ccnt, t.long_cptr, nl + 1));
+    int nc = 0;
+    SDP_CHECK(read_int(h, t.long_cptr + nl, &nc));
+    t.n_chunks = nc;
+    SDP_CHECK(dev_alloc(h, &t.chunk_start, nc)); SDP_CHECK(dev_alloc(h, &t.chunk_end, nc)); SDP_CHECK(dev_alloc(h, &t.chunk_row, nc));
+    k_tile_chunks<<<grid_for(nc, TPB, GS), TPB, 0, st>>>(nc, nl, t.long_rows, t.long_cptr, ptr, t.chunk_start, t.chunk_end, t.chunk_row);
+    KLAUNCH(h);
+    return SDPLRP_OK;
+}
 }  // namespace
 
 void pre_free(sdplrp_handle *h) {
-    dev_free(&h->triu_colptr); dev_free(&h->triu_rowval); dev_free(&h->full_ptr); dev_free(&h->full_idx);
+    tile_free(h->full_tile); tile_free(h->dyn_tile);
+    dev_free(&h->tile_scratch); h->tile_scratch_len = 0;
+    dev_free(&h->triu_colptr); dev_free(&h->triu_rowval);
+    if (h->full_ptr == h->ref_full_ptr) { h->full_ptr = nullptr; h->full_idx = nullptr; }  // aliases when not relabeled
+    dev_free(&h->full_ptr); dev_free(&h->full_idx); dev_free(&h->ref_full_ptr); dev_free(&h->ref_full_idx);
+    dev_free(&h->perm); dev_free(&h->iperm); dev_free(&h->i2r); dev_free(&h->r2i);
+    h->relabeled = false;
     dev_free(&h->mapped); dev_free(&h->S); dev_free(&h->matptr); dev_free(&h->mat_gid); dev_free(&h->ent_slot);
     dev_free(&h->ent_row); dev_free(&h->ent_col); dev_free(&h->ent_one); dev_free(&h->ent_two);
     dev_free(&h->long_mat); dev_free(&h->long_chunk_ptr); dev_free(&h->chunk_mat); dev_free(&h->chunk_part);
@@ -447,13 +540,13 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
     h->nnzT = nnzT; h->nnzF = nnzF;
 
     SDP_CHECK(dev_alloc(h, &h->triu_colptr, n + 1)); SDP_CHECK(dev_alloc(h, &h->triu_rowval, nnzT));
-    SDP_CHECK(dev_alloc(h, &h->full_ptr, n + 1)); SDP_CHECK(dev_alloc(h, &h->full_idx, nnzF));
+    SDP_CHECK(dev_alloc(h, &h->ref_full_ptr, n + 1)); SDP_CHECK(dev_alloc(h, &h->ref_full_idx, nnzF));
     SDP_CHECK(dev_alloc(h, &h->mapped, nnzF)); SDP_CHECK(dev_alloc(h, &h->S, nnzF));
     SDP_CHECK(dev_alloc(h, &h->triuS_static, nnzT));
     k_colptr<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, nnzT, UT, h->triu_colptr); KLAUNCH(h);
-    k_colptr<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, nnzF, UF, h->full_ptr); KLAUNCH(h);
+    k_colptr<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, nnzF, UF, h->ref_full_ptr); KLAUNCH(h);
     if (nnzT > 0) { k_low32<<<GS, TPB, 0, st>>>(nnzT, UT, h->triu_rowval); KLAUNCH(h); }
-    if (nnzF > 0) { k_low32<<<GS, TPB, 0, st>>>(nnzF, UF, h->full_idx); KLAUNCH(h); }
+    if (nnzF > 0) { k_low32<<<GS, TPB, 0, st>>>(nnzF, UF, h->ref_full_idx); KLAUNCH(h); }
 
     // ---- index maps ----------------------------------------------------------
     if (Ec > 0) { k_nzind<<<GS, TPB, 0, st>>>(Ec, h->ent_row, h->ent_col, h->triu_colptr, h->triu_rowval, h->ent_slot); KLAUNCH(h); }
@@ -461,6 +554,53 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
     SDP_CHECK(read_int(h, errw, &herr));
     CUDA_TRY(h, cudaMemsetAsync(h->S, 0, (size_t)std::max<i64>(nnzF, 1) * sizeof(double), st));
     const bool asym = (herr & 2) != 0;
+
+    // ---- internal vertex order: descending degree of the aggregated pattern -------
+    // Hub rows become a contiguous prefix of every n x r factor (L2-resident gather
+    // targets) and the row classes become ranges.  "auto" relabels only skewed patterns
+    // (max degree >= 8x the mean): regular / banded patterns keep their natural locality.
+    h->relabeled = false;
+    h->full_ptr = h->ref_full_ptr; h->full_idx = h->ref_full_idx;
+    if (nnzF > 0 && h->relabel_mode != 0) {
+        unsigned *dkey = tmp.get<unsigned>(h, n, &rc), *dkey2 = tmp.get<unsigned>(h, n, &rc);
+        int *dval = tmp.get<int>(h, n, &rc);
+        if (rc) return rc;
+        SDP_CHECK(dev_alloc(h, &h->iperm, n)); SDP_CHECK(dev_alloc(h, &h->perm, n));
+        k_deg_key<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, h->ref_full_ptr, dkey, dval); KLAUNCH(h);
+        h->launches += 4;
+        SDP_CHECK(with_cub_temp(h, [&](void *t, size_t &b) {
+            return cub::DeviceRadixSort::SortPairs(t, b, dkey, dkey2, dval, h->iperm, (int)n, 0, bits_for(n + 2), st);
+        }));
+        bool want = h->relabel_mode == 1;
+        if (h->relabel_mode < 0) {
+            unsigned k0 = 0;
+            CUDA_TRY(h, cudaMemcpyAsync(&k0, dkey2, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(h, cudaStreamSynchronize(st));
+            const double maxdeg = (double)(n - (i64)k0), mean = (double)nnzF / (double)n;
+            want = maxdeg >= 8.0 * mean;
+        }
+        if (want) {
+            k_invert_perm<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, h->iperm, h->perm); KLAUNCH(h);
+            unsigned long long *ikey = tmp.get<unsigned long long>(h, nnzF, &rc);
+            int *ipay = tmp.get<int>(h, nnzF, &rc);
+            if (rc) return rc;
+            SDP_CHECK(dev_alloc(h, &h->i2r, nnzF)); SDP_CHECK(dev_alloc(h, &h->r2i, nnzF));
+            k_internal_keys<<<GS, TPB, 0, st>>>(nnzF, UF, h->perm, ikey, ipay); KLAUNCH(h);
+            h->launches += 8;
+            // keyF (the unsorted input keys) is dead by now: reuse it as the sorted-key output
+            SDP_CHECK(with_cub_temp(h, [&](void *t, size_t &b) {
+                return cub::DeviceRadixSort::SortPairs(t, b, ikey, keyF, ipay, h->i2r, (int)nnzF, 0, end_bit, st);
+            }));
+            k_scatter_inverse<<<GS, TPB, 0, st>>>(nnzF, h->i2r, h->r2i); KLAUNCH(h);
+            h->full_ptr = nullptr; h->full_idx = nullptr;
+            SDP_CHECK(dev_alloc(h, &h->full_ptr, n + 1)); SDP_CHECK(dev_alloc(h, &h->full_idx, nnzF));
+            k_colptr<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, nnzF, keyF, h->full_ptr); KLAUNCH(h);
+            k_low32<<<GS, TPB, 0, st>>>(nnzF, keyF, h->full_idx); KLAUNCH(h);
+            h->relabeled = true;
+        } else {
+            dev_free(&h->iperm); dev_free(&h->perm);
+        }
+    }
 
     // ---- long matrices -> chunk lists (constraint passes) --------------------
     h->n_long = 0; h->n_chunks = 0;
@@ -522,7 +662,7 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
         SDP_CHECK(dev_alloc(h, &h->dyn_pos_a, nd)); SDP_CHECK(dev_alloc(h, &h->dyn_pos_b, nd));
         if (nd > 0) {
             k_dyn_fill<<<GS, TPB, 0, st>>>(nnzT, slot_ptr, sorted_t, ent_mat, h->ent_one, h->mat_gid, h->obj_mat, dflag,
-                                           dindex, doff, h->triu_rowval, UT, h->full_ptr, h->full_idx, h->dyn_slot,
+                                           dindex, doff, h->triu_rowval, UT, h->relabeled ? h->perm : nullptr, h->full_ptr, h->full_idx, h->dyn_slot,
                                            h->dyn_ptr, h->dyn_gid, h->dyn_val, h->dyn_pos_a, h->dyn_pos_b);
             KLAUNCH(h);
         }
@@ -536,7 +676,7 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
     SDP_CHECK(dev_alloc(h, &h->dynrow_ptr, n + 1));
     h->n_dynF = 0;
     if (nnzF > 0) {
-        k_cfull<<<GS, TPB, 0, st>>>(nnzF, h->mapped, h->triuS_static, h->Cfull); KLAUNCH(h);
+        k_cfull<<<GS, TPB, 0, st>>>(nnzF, h->mapped, h->i2r, h->triuS_static, h->Cfull); KLAUNCH(h);
         int *fflag = tmp.get<int>(h, nnzF + 1, &rc), *fpos = tmp.get<int>(h, nnzF + 1, &rc), *fsrc = tmp.get<int>(h, nnzF + 1, &rc);
         if (rc) return rc;
         CUDA_TRY(h, cudaMemsetAsync(fflag, 0, (size_t)(nnzF + 1) * sizeof(int), st));
@@ -553,9 +693,17 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
         SDP_CHECK(dev_alloc(h, &h->dynrow_col, 0)); SDP_CHECK(dev_alloc(h, &h->dynrow_src, 0));
     }
 
+    // ---- the constraint passes index factor rows: entry coordinates in internal labels
+    if (h->relabeled && Ec > 0) {
+        k_apply_perm<<<GS, TPB, 0, st>>>(Ec, h->perm, h->ent_row); KLAUNCH(h);
+        k_apply_perm<<<GS, TPB, 0, st>>>(Ec, h->perm, h->ent_col); KLAUNCH(h);
+    }
+
     // ---- row bins of both patterns (sparse x dense kernels) -----------------------
     SDP_CHECK(build_classes(h, tmp, n, h->full_ptr, h->full_cls));
     SDP_CHECK(build_classes(h, tmp, n, h->dynrow_ptr, h->dyn_cls));
+    SDP_CHECK(tile_build(h, tmp, n, h->full_ptr, h->full_tile));
+    SDP_CHECK(tile_build(h, tmp, n, h->dynrow_ptr, h->dyn_tile));
     CUDA_TRY(h, cudaStreamSynchronize(st));
     CUDA_TRY(h, cudaGetLastError());
     h->preprocessed = true;
@@ -577,7 +725,7 @@ int32_t pre_export(sdplrp_handle *h, int64_t *triu_colptr, int64_t *triu_rowval,
     CUDA_TRY(h, cudaMalloc((void **)&buf, (size_t)std::max<i64>(maxlen, 1) * sizeof(int64_t)));
     struct Item { const int *src; int64_t *dst; i64 len; };
     Item items[] = {{h->triu_colptr, triu_colptr, n + 1}, {h->triu_rowval, triu_rowval, nnzT}, {h->matptr, matptr, nA + 1},
-                    {h->ent_slot, nzind, Ec}, {h->full_ptr, full_colptr, n + 1}, {h->full_idx, full_rowval, nnzF},
+                    {h->ent_slot, nzind, Ec}, {h->ref_full_ptr, full_colptr, n + 1}, {h->ref_full_idx, full_rowval, nnzF},
                     {h->mapped, mapped, nnzF}};
     int32_t rc = SDPLRP_OK;
     for (const Item &it : items) {

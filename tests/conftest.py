@@ -26,9 +26,21 @@ def oracle_mod():
     return pyoracle
 
 
+# kernel configurations every GPU parity test runs under: the product default (auto relabeling,
+# async-copy tile SpMM), forced hub-first relabeling (exercises every permuting copy on the small
+# regular test graphs too), and the async-copy tile-stream SpMM kernel
+GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "tile": {"relabel": 1, "spmm_kernel": 1}}
+
+
 @pytest.fixture(scope="session")
 def gpu_handle_factory(sp):
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    return lambda: sp.Handle(device=0)
+
+    def make(config="default"):
+        h = sp.Handle(device=0)
+        for k, v in GPU_CONFIGS[config].items():
+            h.set_option(k, v)
+        return h
+    return make

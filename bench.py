@@ -94,7 +94,7 @@ def algorithmic_bytes(n, m, r, nnzT, nnzF, Ec, h, rows_local):
     N = 8.0 * rows_local * r
     frac = rows_local / float(n)
     return {
-        "lbfgs_dir": (8 * h + 3) * N,                                             # fused two-loop, 35N at h=4
+        "lbfgs_dir": (2 * h + 3) * N,                                             # coefficient two-loop: one pass forming dir (+ y pre-store), 11N at h=4
         # constraint part of the fused {A(RD'+DR'), A(DD')} pass (the objective slot rides on the spmm pass)
         "ls_pass": 2 * N + frac * (12.0 * (Ec - nnzT) + 8.0 * m + 16 * (m + 1)),
         "ls_coeff": 32.0 * m,
@@ -103,7 +103,7 @@ def algorithmic_bytes(n, m, r, nnzT, nnzF, Ec, h, rows_local):
         "spmm": 2 * N + frac * (4 * (n + 1) + 12 * nnzF),                         # CD = C*D: SURVEY 8d B_G
         "grad": 3 * N + frac * (12.0 * (Ec - nnzT) + 8.0 * m + 4.0 * (n + 1)),    # G = 2(y_obj CR + S_dyn R), ||G||^2
         "norms": 16.0 * m,
-        "lbfgs_update": 5 * N,
+        "lbfgs_update": (2 * h + 3) * N,                                          # new pair + its dots with the whole history, 11N at h=4
     }
 
 

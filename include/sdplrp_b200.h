@@ -91,7 +91,9 @@ void *sdplrp_stream(sdplrp_handle *h);
  *   "relabel"     -1 auto (default) / 0 off / 1 on: internal hub-first vertex order, set BEFORE
  *                 sdplrp_preprocess.  Invisible at the ABI (every upload/download converts).
  *   "hot_rows"    leading rows of the gathered factor pinned in L2 (evict_last); -1 = sized from L2
- *   "spmm_kernel" 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel (experimental) */
+ *   "spmm_kernel" 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel (experimental)
+ *   "lbfgs_kernel" 1 = two-loop recursion on coefficients over directly computed dot products (default,
+ *                 numlbfgsvecs <= 8), 0 = literal vector two-loop */
 int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value);
 
 /* ---- preprocessing: preprocess_sparsecons + SolverAuxiliary ------------

@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(TPB) k_A_short(int nA, const int *__restrict__
                                                  const int *__restrict__ ent_row, const int *__restrict__ ent_col,
                                                  const double *__restrict__ ent_two, const double *__restrict__ U,
                                                  const double *__restrict__ V, int r, int G, double *__restrict__ out1,
-                                                 double *__restrict__ out2, int own_lo, int own_hi, int skip_mat) {
+                                                 double *__restrict__ out2, int own_lo, int own_hi, int skip_mat,
+                                                 const unsigned char *__restrict__ sd_flag) {
     const int nv = r / VEC;
     const int lg = threadIdx.x & (G - 1);
     const int gpw = 32 / G;  // groups per warp
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(TPB) k_A_short(int nA, const int *__restrict__
         int gid = 0;
         if (a < nA) {
             const int beg = matptr[a], end = matptr[a + 1];
-            if (end - beg <= kLongMatThreshold && a != skip_mat) {
+            if (end - beg <= kLongMatThreshold && a != skip_mat && !(sd_flag && sd_flag[a])) {
                 store = true;
                 gid = mat_gid[a];
                 for (int k = beg; k < end; k++)
@@ -118,6 +119,50 @@ __global__ void __launch_bounds__(TPB) k_A_short(int nA, const int *__restrict__
         if (store && lg == 0) {
             out1[gid] = a1;
             if (MODE == 2) out2[gid] = a2;
+        }
+    }
+}
+
+// single-diagonal-entry constraints (Diag(X) = 1 ...): a streaming pass over the factor rows.  A group of G
+// lanes owns row i, forms <U_i,U_i> / <U_i,V_i> / <V_i,V_i> once and serves every constraint listed for the row.
+template <int MODE, int VEC>
+__global__ void __launch_bounds__(TPB) k_A_rowc(long long lo, long long hi, const int *__restrict__ rowc_ptr,
+                                                const int *__restrict__ rowc_gid, const double *__restrict__ rowc_val,
+                                                const double *__restrict__ U, const double *__restrict__ V, int r, int G,
+                                                double *__restrict__ out1, double *__restrict__ out2) {
+    typedef Ld<VEC> L;
+    const int nv = r / VEC;
+    const int lg = threadIdx.x & (G - 1);
+    const int gpw = 32 / G;  // groups per warp
+    const long long warp_global = (long long)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (TPB / 32);
+    const int g_in_warp = (threadIdx.x & 31) / G;
+    for (long long base = lo + warp_global * gpw; base < hi; base += n_warps * gpw) {  // warp-uniform trip count
+        const long long i = base + g_in_warp;
+        const bool live = i < hi;
+        int beg = 0, end = 0;
+        if (live) { beg = rowc_ptr[i]; end = rowc_ptr[i + 1]; }
+        double d1 = 0.0, d2 = 0.0;
+        if (live && end > beg) {
+            const double *u = U + (size_t)i * r, *v = (MODE == 0) ? nullptr : V + (size_t)i * r;
+            for (int c = lg; c < nv; c += G) {
+                typename L::T a = L::ld(u + c * VEC);
+                if (MODE == 0) {
+                    d1 += L::dot(a, a);
+                } else {
+                    typename L::T b = L::ld(v + c * VEC);
+                    d1 += L::dot(a, b);
+                    if (MODE == 2) d2 += L::dot(b, b);
+                }
+            }
+        }
+        d1 = group_sum(d1, G);
+        if (MODE == 2) d2 = group_sum(d2, G);
+        for (int k = beg + lg; k < end; k += G) {
+            const double val = rowc_val[k];
+            const int gid = rowc_gid[k];
+            out1[gid] = (MODE == 2 ? 2.0 : 1.0) * val * d1;  // MODE 2: A_RD is kept already doubled
+            if (MODE == 2) out2[gid] = val * d2;
         }
     }
 }
@@ -245,9 +290,18 @@ int32_t run_sparse(sdplrp_handle *h, const double *U, const double *V, double *o
     const int gpb = TPB / G;
     const int grid_short = grid_for(h->nA, gpb, 16 * kNumSM);
     const int lo = (int)h->row_lo, hi = (int)h->row_hi;
-    if (vec2) k_A_short<MODE, 2><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi, skip_mat);
-    else k_A_short<MODE, 1><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi, skip_mat);
-    KLAUNCH(h);
+    const unsigned char *sdf = h->n_sd > 0 ? h->sd_flag : nullptr;
+    if (h->nA - h->n_sd - h->n_long > 0) {  // short matrices that are not single diagonal entries
+        if (vec2) k_A_short<MODE, 2><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi, skip_mat, sdf);
+        else k_A_short<MODE, 1><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi, skip_mat, sdf);
+        KLAUNCH(h);
+    }
+    if (h->n_sd > 0) {
+        const int grid_rows = grid_for(h->row_hi - h->row_lo, gpb, 16 * kNumSM);
+        if (vec2) k_A_rowc<MODE, 2><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_gid, h->rowc_val, U, V, r, G, out1, out2);
+        else k_A_rowc<MODE, 1><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_gid, h->rowc_val, U, V, r, G, out1, out2);
+        KLAUNCH(h);
+    }
     if (h->n_chunks > 0) {
         if (vec2) k_A_long<MODE, 2><<<(int)h->n_chunks, TPB, 0, st>>>(h->chunk_mat, h->long_mat, h->long_chunk_ptr, h->matptr, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, h->chunk_part, lo, hi, skip_mat);
         else k_A_long<MODE, 1><<<(int)h->n_chunks, TPB, 0, st>>>(h->chunk_mat, h->long_mat, h->long_chunk_ptr, h->matptr, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, h->chunk_part, lo, hi, skip_mat);

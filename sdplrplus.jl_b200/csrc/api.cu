@@ -118,6 +118,7 @@ int32_t sdplrp_create(int32_t device, int32_t rank, int32_t world, const void *n
     if (const char *e = getenv("SDPLRP_RELABEL")) h->relabel_mode = atoi(e) < 0 ? -1 : (atoi(e) > 0 ? 1 : 0);
     if (const char *e = getenv("SDPLRP_SPMM_KERNEL")) h->spmm_kernel = atoi(e);
     if (const char *e = getenv("SDPLRP_HOT_ROWS")) h->hot_rows = atoll(e);
+    if (const char *e = getenv("SDPLRP_LBFGS_KERNEL")) h->lbfgs_kernel = atoi(e);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SDPLRP_ERR_CUDA; }
     bool ok = cudaMalloc((void **)&h->dscal, SC_COUNT * sizeof(double)) == cudaSuccess &&
               cudaMallocHost((void **)&h->hscal, SC_COUNT * sizeof(double)) == cudaSuccess &&
@@ -139,6 +140,8 @@ static void free_state(sdplrp_handle *h) {
     dev_free(&h->CR); dev_free(&h->CD);
     h->CR_valid = h->CD_valid = false;
     for (int j = 0; j < kMaxHist; j++) { dev_free(&h->Sh[j]); dev_free(&h->Yh[j]); }
+    dev_free(&h->lb_small);
+    h->gram_pairs_valid = h->gram_g_valid = false; h->gram_prestored = -1;
     dev_free(&h->lr_tmp); h->lr_tmp_len = 0;
     h->r = 0; h->hist = 0;
 }
@@ -271,6 +274,7 @@ int32_t sdplrp_set_rank(sdplrp_handle *h, int32_t r, int32_t numlbfgsvecs) {
     SDP_CHECK(dev_alloc(h, &h->R, N)); SDP_CHECK(dev_alloc(h, &h->G, N)); SDP_CHECK(dev_alloc(h, &h->D, N));
     if (h->obj_mat >= 0) { SDP_CHECK(dev_alloc(h, &h->CR, N)); SDP_CHECK(dev_alloc(h, &h->CD, N)); }
     for (int j = 0; j < numlbfgsvecs; j++) { SDP_CHECK(dev_alloc(h, &h->Sh[j], N)); SDP_CHECK(dev_alloc(h, &h->Yh[j], N)); }
+    SDP_CHECK(dev_alloc(h, &h->lb_small, kLbSmallLen));
     h->r = r; h->hist = numlbfgsvecs; h->latest = numlbfgsvecs;  // lbfgs_init: latest = h (src/lbfgs.jl:45)
     CUDA_TRY(h, cudaMemsetAsync(h->R, 0, (size_t)N * 8, h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->G, 0, (size_t)N * 8, h->stream));
@@ -287,6 +291,7 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
     if (k == "relabel") { h->relabel_mode = value < 0 ? -1 : (value > 0 ? 1 : 0); return SDPLRP_OK; }  // before preprocess
     if (k == "hot_rows") { h->hot_rows = (i64)value; return SDPLRP_OK; }
     if (k == "spmm_kernel") { h->spmm_kernel = (int)value; return SDPLRP_OK; }
+    if (k == "lbfgs_kernel") { h->lbfgs_kernel = (int)value; h->gram_pairs_valid = h->gram_g_valid = false; return SDPLRP_OK; }
     return fail(h, SDPLRP_ERR_ARG, "set_option: unknown key " + k);
 }
 
@@ -317,6 +322,8 @@ int32_t sdplrp_upload_mat(sdplrp_handle *h, int32_t id, const double *src) {
     comm_mark_full(h, id);
     if (id == SDPLRP_MAT_R) h->CR_valid = false;
     if (id == SDPLRP_MAT_D) h->CD_valid = false;
+    if (id == SDPLRP_MAT_G) h->gram_g_valid = false;
+    if (id >= SDPLRP_MAT_S0) { h->gram_pairs_valid = false; h->gram_prestored = -1; }
     return SDPLRP_OK;
 }
 
@@ -492,6 +499,7 @@ static int32_t do_g(sdplrp_handle *h) {
         SectionScope sc(h, SDPLRP_SEC_GRAD);
         SDP_CHECK(grad_hot(h));
     }
+    h->gram_g_valid = false;  // G changed: its dots with the L-BFGS history are rebuilt by the update pass
     comm_mark_partial(h, SDPLRP_MAT_G);
     SectionScope sc(h, SDPLRP_SEC_NORMS);
     SDP_CHECK(comm_reduce_scalars(h, SC_GNORM2, 1));
@@ -546,6 +554,7 @@ int32_t sdplrp_use_gradient_direction(sdplrp_handle *h) {
     REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
     SDP_CHECK(lb_neg_copy(h));
+    h->gram_g_valid = false;
     h->CD_valid = false;
     comm_mark_partial(h, SDPLRP_MAT_D);
     return SDPLRP_OK;

@@ -13,7 +13,8 @@ constexpr int kNumSM = 148;          // B200: 2 dies x 74 SMs
 constexpr int kMaxHist = 32;         // numlbfgsvecs upper bound (ids S0..S0+31)
 constexpr int kRedBlocks = 4 * kNumSM;  // persistent grid of streaming/reduction kernels
 constexpr int kRedThreads = 256;
-constexpr int kMaxRedK = 16;         // max simultaneous sums of one reduction kernel
+constexpr int kMaxRedK = 64;         // max simultaneous sums of one reduction kernel
+constexpr int kLbSmallLen = 17 * 17 + 3 * 17 + 17 + 7;  // Gram (17x17) + three probe rows + coefficients
 constexpr long long kPartialsLen = (long long)kRedBlocks * kMaxRedK * 8;  // doubles in h->partials
 constexpr int kLongMatThreshold = 64;   // matrices with more triu entries go to the chunked path
 constexpr int kChunkEntries = 2048;     // entries per chunk (one CTA) of a long matrix
@@ -122,6 +123,15 @@ struct sdplrp_handle {
     int *dynrow_ptr = nullptr;     // n+1
     int *dynrow_col = nullptr;     // n_dynF
     int *dynrow_src = nullptr;     // n_dynF -> index into dynS
+    int *dyn_diag = nullptr;       // n: index into dynS of the dynamic DIAGONAL slot of row i, -1 if none (dynrow_* holds only
+                                   //    the off-diagonal dynamic slots: the diagonal part of S_dyn*R is a row scaling)
+    // constraints that are a single diagonal entry (Diag(X) = 1 of MaxCut / cut-norm / bisection ...), as per-row lists in
+    // internal row order: their sampled dots are a streaming pass over the factor rows (aop.cu, k_A_rowc)
+    i64 n_sd = 0;
+    int *rowc_ptr = nullptr;       // n+1
+    int *rowc_gid = nullptr;       // n_sd  global slot of the constraint
+    double *rowc_val = nullptr;    // n_sd  its value (nzval_one == nzval_two on the diagonal)
+    unsigned char *sd_flag = nullptr;  // nA: matrix handled by the row lists
     RowClasses full_cls, dyn_cls;  // row bins of the full / dynamic pattern
     TileLayout full_tile, dyn_tile; // long-row chunk lists of both patterns (spmm.cu)
     double *tile_scratch = nullptr; // chunk partial sums, max(n_chunks) x r
@@ -144,6 +154,11 @@ struct sdplrp_handle {
     int r = 0, hist = 0, latest = 0;  // latest is 1-based like the reference
     double *R = nullptr, *G = nullptr, *D = nullptr, *W0 = nullptr, *W1 = nullptr;
     double *Sh[kMaxHist] = {nullptr}, *Yh[kMaxHist] = {nullptr};
+    // coefficient-space L-BFGS (lbfgs.cu): Gram matrix of [s_j, y_j, g], probe-row scratch, coefficients
+    int lbfgs_kernel = 1;          // 0 = literal vector two-loop, 1 = coefficient two-loop on directly computed dots
+    double *lb_small = nullptr;    // kLbSmallLen doubles
+    bool gram_pairs_valid = false, gram_g_valid = false;
+    int gram_prestored = -1;       // slot whose y was overwritten by the y = -g pre-store since the last update
 
     // reduction plumbing
     double *dscal = nullptr;      // SC_COUNT device scalars

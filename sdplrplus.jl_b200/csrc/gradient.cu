@@ -85,6 +85,7 @@ struct Acc<1> {
     __device__ __forceinline__ void fma(double s, const double *p) { v += s * __ldg(p); }
     __device__ __forceinline__ void shfl_add(int o) { v += __shfl_xor_sync(0xffffffffu, v, o); }
     __device__ __forceinline__ void scale_add(double sc, double a, const double *p) { v = sc * (v + a * __ldg(p)); }
+    __device__ __forceinline__ void accumulate_onto(double sc, const double *p) { v = p[0] + sc * v; }
     __device__ __forceinline__ void scale(double sc) { v *= sc; }
     __device__ __forceinline__ double dot_ld(const double *p) const { return v * __ldg(p); }
     __device__ __forceinline__ double norm2() const { return v * v; }
@@ -107,6 +108,10 @@ struct Acc<2> {
         v.x = sc * (v.x + a * x.x); v.y = sc * (v.y + a * x.y);
     }
     __device__ __forceinline__ void scale(double sc) { v.x *= sc; v.y *= sc; }
+    __device__ __forceinline__ void accumulate_onto(double sc, const double *p) {
+        const double2 x = *reinterpret_cast<const double2 *>(p);
+        v.x = x.x + sc * v.x; v.y = x.y + sc * v.y;
+    }
     __device__ __forceinline__ double dot_ld(const double *p) const {
         const double2 x = ldg2(p);
         return v.x * x.x + v.y * x.y;
@@ -144,6 +149,8 @@ __device__ __forceinline__ void row_epilogue(const RowArgs &a, i64 i, Acc<VEC> (
             const size_t off = (size_t)i * a.r + c * VEC;
             if (EPI == 0) {
                 acc[u].scale(a.scale);
+            } else if (EPI == 3) {
+                acc[u].accumulate_onto(a.scale, a.Y + off);  // Y_i + scale*acc
             } else if (EPI == 1) {
                 if (a.ADD) acc[u].scale_add(a.scale, a.yobj, a.ADD + off); else acc[u].scale(a.scale);
                 s0 += acc[u].norm2();
@@ -162,7 +169,7 @@ __device__ __forceinline__ void row_epilogue(const RowArgs &a, i64 i, Acc<VEC> (
 
 template <int EPI>
 __device__ __forceinline__ void finish_sums(const RowArgs &a, double s0, double s1) {
-    if (EPI == 0) return;
+    if (EPI == 0 || EPI == 3) return;
     double v[2] = {s0, s1};
     double *out = a.out;
     grid_sum_finalize<2>(v, a.partials, a.ticket, [&](double (&s)[2]) { out[0] = s[0]; out[1] = s[1]; });
@@ -272,13 +279,23 @@ __global__ void __launch_bounds__(TPB) k_rows_cta(RowArgs a) {
 #pragma unroll
         for (int u = 0; u < MAXU; u++) acc[u].zero();
         const int beg = a.ptr[i], end = a.ptr[i + 1];
-        for (int k = beg + grp; k < end; k += ng) {
-            const int c0 = __ldg(a.idx + k);
-            const double v0 = VAL_AT(k);
+        for (int k0 = beg + grp * 4; k0 < end; k0 += ng * 4) {  // 4 independent gathers in flight per lane
+            int cc[4];
+            double vv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bool ok = k0 + j < end;
+                cc[j] = ok ? __ldg(a.idx + k0 + j) : 0;
+                vv[j] = ok ? VAL_AT(k0 + j) : 0.0;
+            }
 #pragma unroll
             for (int u = 0; u < MAXU; u++) {
                 const int c = lg + u * a.G;
-                if (c < nv) acc[u].fma(v0, a.X + (size_t)c0 * a.r + c * VEC);
+                if (c < nv) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (k0 + j < end) acc[u].fma(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC);
+                }
             }
         }
         __syncthreads();
@@ -294,6 +311,8 @@ __global__ void __launch_bounds__(TPB) k_rows_cta(RowArgs a) {
             const size_t off = (size_t)i * a.r + e;
             if (EPI == 0) {
                 t *= a.scale;
+            } else if (EPI == 3) {
+                t = a.Y[off] + a.scale * t;
             } else if (EPI == 1) {
                 t = a.ADD ? a.scale * (t + a.yobj * a.ADD[off]) : a.scale * t;
                 s0 += t * t;
@@ -366,6 +385,32 @@ __global__ void k_sum_slots(int ncls, const double *__restrict__ sums, int strid
     double s = 0.0;
     for (int c = 0; c < ncls; c++) s += sums[stride * c];
     *out = s;
+}
+
+// the hot-loop gradient without its gathered parts:  G_i = 2*(y_obj*CR_i + d_i*R_i),  d_i = S_dyn(i,i)  (src/coreop.jl:305-317
+// with S = y_obj*C + S_dyn and C*R kept by recurrence); ||G||_F^2 fused.  Pure streaming: 3N bytes.
+template <int VEC>
+__global__ void __launch_bounds__(TPB) k_grad_diag(i64 lo, i64 hi, int r, double yobj, const double *__restrict__ CR,
+                                                   const double *__restrict__ R, const int *__restrict__ dyn_diag,
+                                                   const double *__restrict__ dynS, double *__restrict__ G, double *partials,
+                                                   unsigned *ticket, double *out) {
+    const int nv = r / VEC;
+    const i64 total = (hi - lo) * nv;
+    double acc[1] = {0.0};
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 i = lo + e / nv;
+        const int c = (int)(e - (i - lo) * nv);
+        const int dd = dyn_diag[i];
+        const double d = dd >= 0 ? dynS[dd] : 0.0;
+        const size_t off = (size_t)i * r + c * VEC;
+        Acc<VEC> g;
+        g.zero();
+        g.fma(d, R + off);
+        if (CR) g.scale_add(2.0, yobj, CR + off); else g.scale(2.0);
+        acc[0] += g.norm2();
+        g.store(G + off);
+    }
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { out[0] = s[0]; });
 }
 
 int pick_group(int nv) {
@@ -520,34 +565,39 @@ int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double
 }
 
 // the hot-loop gradient: G = 2*(y_obj*CR + S_dyn(y)*R + low rank), ||G||_F^2 -> SC_GNORM2
+//   1. dynS = constraint part of S at every dynamic slot (deterministic slot -> contributors gather)
+//   2. streaming pass: G_i = 2*(y_obj*CR_i + S_dyn(i,i)*R_i) with the norm fused
+//   3. only if some constraint has off-diagonal entries: G_i += 2*sum_j S_dyn(i,j)*R_j over the off-diagonal dynamic pattern
+//   4. only with low-rank constraints: the BDB' terms; the norm is then taken in a separate pass
 int32_t grad_hot(sdplrp_handle *h) {
     cudaStream_t st = h->stream;
     const int r = h->r;
-    double *sums = h->dscal + SC_SUMS;
     if (h->n_dyn > 0) {
         k_S_dynamic<2><<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, 0.0, h->dyn_slot, h->dyn_ptr, h->dyn_gid, h->dyn_val,
                                                                            h->dyn_pos_a, h->dyn_pos_b, h->triuS_static, h->y, h->dynS);
         KLAUNCH(h);
     }
-    if (tile_supported(h)) {
-        CUDA_TRY(h, cudaMemsetAsync(sums, 0, 6 * sizeof(double), st));
-        SDP_CHECK(tile_spmm(h, h->dyn_tile, h->dynrow_ptr, h->dynrow_col, h->dynS, h->dynrow_src, h->R, h->G, 1, 2.0, h->y_obj,
-                            (h->obj_mat >= 0) ? h->CR : nullptr, nullptr, sums));
-    } else {
+    const bool vec2 = (r % 2 == 0);
+    const int nv = vec2 ? r / 2 : r;
+    const i64 total = (h->row_hi - h->row_lo) * nv;
+    const double *CR = (h->obj_mat >= 0) ? h->CR : nullptr;
+    const int grid = grid_for(total, TPB * 2, kRedBlocks);
+    if (vec2) k_grad_diag<2><<<grid, TPB, 0, st>>>(h->row_lo, h->row_hi, r, h->y_obj, CR, h->R, h->dyn_diag, h->dynS, h->G, h->partials, h->ticket, h->dscal + SC_GNORM2);
+    else k_grad_diag<1><<<grid, TPB, 0, st>>>(h->row_lo, h->row_hi, r, h->y_obj, CR, h->R, h->dyn_diag, h->dynS, h->G, h->partials, h->ticket, h->dscal + SC_GNORM2);
+    KLAUNCH(h);
+    bool renorm = false;
+    if (h->n_dynF > 0) {
         RowArgs a = {};
         a.ptr = h->dynrow_ptr; a.idx = h->dynrow_col; a.val = h->dynS; a.src = h->dynrow_src;
         a.X = h->R; a.Y = h->G; a.scale = 2.0;
-        a.ADD = (h->obj_mat >= 0) ? h->CR : nullptr;
-        a.yobj = h->y_obj;
-        SDP_CHECK((launch_csr<true, 1>(h, a, h->dyn_cls, sums)));
+        SDP_CHECK((launch_csr<true, 3>(h, a, h->dyn_cls, nullptr)));
+        renorm = true;
     }
-    if (h->lr.empty()) {
-        k_sum_slots<<<1, 1, 0, st>>>(3, sums, 2, h->dscal + SC_GNORM2);
-        KLAUNCH(h);
-    } else {
+    if (!h->lr.empty()) {
         SDP_CHECK(add_lowrank(h, h->R, h->G, 2.0));
-        SDP_CHECK(lb_norm2(h, h->G, SC_GNORM2));
+        renorm = true;
     }
+    if (renorm) SDP_CHECK(lb_norm2(h, h->G, SC_GNORM2));
     CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
 }

@@ -13,6 +13,16 @@
 // axpy: 2h+1 launches, 35*N bytes, no host synchronisation until `descent`.
 // The arithmetic is the literal two-loop (no H0 scaling, zeroed slots act as
 // identity), only the summation order inside a dot differs.
+//
+// Default path ("lbfgs_kernel" = 1, numlbfgsvecs <= kGramMaxHist): the same recursion
+// run on COEFFICIENTS.  Every vector the two-loop touches is a combination of the
+// 2h+1 stored vectors [s_1..s_h, y_1..y_h, g], so the recursion only needs their
+// pairwise dot products.  Those are all computed DIRECTLY from the stored vectors
+// (never by recurrence): lbfgs_update! is one pass that writes the new pair
+// (s = alpha*dir, y += g) and forms the dots of {s_new, y_new, g} with every stored
+// vector (11N bytes), lbfgs_dir! is a 1-thread coefficient two-loop followed by one
+// pass dir = -sum c_k b_k with the y_next = -g pre-store and the descent dot fused
+// (11N bytes): 22N per iteration instead of 40N, 2 reductions instead of 2h+2.
 #include <algorithm>
 #include "common.cuh"
 
@@ -154,6 +164,143 @@ __global__ void __launch_bounds__(TPB) k_norm2(i64 nu, const double *__restrict_
     grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { out[0] = s[0]; });
 }
 
+
+// ---- coefficient-space ("Gram") two-loop ------------------------------------------------
+constexpr int kGramMaxHist = 8;
+constexpr int kGramNB = 2 * kGramMaxHist + 1;   // basis size bound
+struct LbPtrs {
+    const double *S[kGramMaxHist];
+    const double *Y[kGramMaxHist];
+};
+
+// One pass over the basis [S_0..S_{M-1}, Y_0..Y_{M-1}, G] (slots in the ROTATED order the host passes, so that the
+// slot being replaced is always position M-1):  dots of three probe vectors with every basis vector
+// -> out[p*(2M+1) + k].
+//   UPDATE:  position M-1 is replaced by the new pair first (S = alpha*D, Y += G; src/lbfgs.jl:142-148) and the
+//            probes are {S_new, Y_new, G} -- static positions, no selects; every load precedes the two stores so
+//            that the in-order issue never waits on a store operand with loads still unissued.
+//   !UPDATE: probes p0..p2 (positions, -1 = unused) -- refresh path after uploads / out-of-order calls.
+template <int VEC, int M, bool UPDATE>
+__global__ void __launch_bounds__(TPB) k_gram_pass(i64 nu, double alpha, LbPtrs P, const double *__restrict__ G,
+                                                   const double *__restrict__ D, double *Sj_out, double *Yj_out,
+                                                   int p0, int p1, int p2, double *partials, unsigned *ticket, double *out) {
+    constexpr int NB = 2 * M + 1;
+    double acc[3 * NB];
+#pragma unroll
+    for (int k = 0; k < 3 * NB; k++) acc[k] = 0.0;
+    GRID_STRIDE(i, nu) {
+        typename V<VEC>::T b[NB];
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+            b[k] = (UPDATE && k == M - 1) ? V<VEC>::ld(D, i) : V<VEC>::ld(P.S[k], i);
+            b[M + k] = V<VEC>::ld(P.Y[k], i);
+        }
+        b[2 * M] = V<VEC>::ld(G, i);
+        typename V<VEC>::T pv[3];
+        if (UPDATE) {
+            b[M - 1] = V<VEC>::scale(alpha, b[M - 1]);
+            b[2 * M - 1] = V<VEC>::axpy(1.0, b[2 * M], b[2 * M - 1]);
+            V<VEC>::st(Sj_out, i, b[M - 1]);
+            V<VEC>::st(Yj_out, i, b[2 * M - 1]);
+            pv[0] = b[M - 1]; pv[1] = b[2 * M - 1]; pv[2] = b[2 * M];
+        } else {
+            const int probe[3] = {p0, p1, p2};
+#pragma unroll
+            for (int p = 0; p < 3; p++) {
+                pv[p] = b[0];
+#pragma unroll
+                for (int k = 1; k < NB; k++)
+                    if (k == probe[p]) pv[p] = b[k];
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+#pragma unroll
+            for (int k = 0; k < NB; k++) acc[p * NB + k] += V<VEC>::dot(pv[p], b[k]);
+        }
+    }
+    grid_sum_finalize<3 * NB>(acc, partials, ticket, [&](double (&sv)[3 * NB]) {
+#pragma unroll
+        for (int k = 0; k < 3 * NB; k++) out[k] = sv[k];
+    });
+}
+
+// scatter the probe rows into the symmetric Gram matrix (positions -> slots through `rot`: position q holds slot
+// (rot + q) % M); rho_j = 1/<y_j, s_j> after an update (src/lbfgs.jl:146)
+__global__ void k_gram_commit(int M, int rot, int p0, int p1, int p2, const double *__restrict__ tmp, double *__restrict__ gram,
+                              int upd_j, double *__restrict__ rho) {
+    const int NB = 2 * M + 1;
+    const int probe[3] = {p0, p1, p2};
+    auto true_index = [&](int b) { return b < M ? (rot + b) % M : (b < 2 * M ? M + (rot + b - M) % M : 2 * M); };
+    for (int p = 0; p < 3; p++) {
+        if (probe[p] < 0) continue;
+        const int tp = true_index(probe[p]);
+        for (int k = threadIdx.x; k < NB; k += blockDim.x) {
+            const double v = tmp[p * NB + k];
+            const int tk = true_index(k);
+            gram[tp * NB + tk] = v;
+            gram[tk * NB + tp] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && upd_j >= 0) rho[upd_j] = 1.0 / gram[(M + upd_j) * NB + upd_j];
+}
+
+// the two-loop recursion on coefficients (src/lbfgs.jl:93-117): dir = -sum_k c[k] b_k
+__global__ void k_gram_coef(int M, int latest, const double *__restrict__ gram, const double *__restrict__ rho,
+                            double *__restrict__ coef) {
+    if (threadIdx.x != 0) return;
+    const int NB = 2 * M + 1;
+    double c[kGramNB], a[kGramMaxHist];
+    for (int k = 0; k < NB; k++) c[k] = 0.0;
+    c[2 * M] = 1.0;
+    int order[kGramMaxHist];
+    {
+        int j = latest;  // 1-based, newest first
+        for (int q = 0; q < M; q++) { order[q] = j - 1; j -= 1; if (j == 0) j = M; }
+    }
+    for (int q = 0; q < M; q++) {
+        const int j = order[q];
+        double sd = 0.0;
+        for (int k = 0; k < NB; k++) sd += c[k] * gram[j * NB + k];
+        a[j] = rho[j] * sd;
+        c[M + j] -= a[j];
+    }
+    for (int q = M - 1; q >= 0; q--) {
+        const int j = order[q];
+        double yd = 0.0;
+        for (int k = 0; k < NB; k++) yd += c[k] * gram[(M + j) * NB + k];
+        c[j] += a[j] - rho[j] * yd;
+    }
+    for (int k = 0; k < NB; k++) coef[k] = c[k];
+}
+
+// dir = -sum_k c_k b_k ; y_pre = -g ; descent = <dir, g>
+template <int VEC, int M>
+__global__ void __launch_bounds__(TPB) k_gram_form(i64 nu, LbPtrs P, const double *__restrict__ G, const double *__restrict__ coef,
+                                                   double *dir, double *ypre, int jpre,
+                                                   double *partials, unsigned *ticket, double *dot_out) {
+    constexpr int NB = 2 * M + 1;
+    double c[NB];
+#pragma unroll
+    for (int k = 0; k < NB; k++) c[k] = coef[k];
+    double acc[1] = {0.0};
+    GRID_STRIDE(i, nu) {
+        const typename V<VEC>::T g = V<VEC>::ld(G, i);
+        typename V<VEC>::T d = V<VEC>::scale(c[2 * M], g);
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+            d = V<VEC>::axpy(c[k], V<VEC>::ld(P.S[k], i), d);
+            d = V<VEC>::axpy(c[M + k], V<VEC>::ld(P.Y[k], i), d);
+        }
+        d = V<VEC>::neg(d);
+        V<VEC>::st(dir, i, d);
+        V<VEC>::st(ypre, i, V<VEC>::neg(g));  // slot jpre is read above before it is overwritten (same element, same thread)
+        acc[0] += V<VEC>::dot(d, g);
+    }
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&sv)[1]) { dot_out[0] = sv[0]; });
+}
+
 struct Slice {
     i64 off, len, nu;
     int vec;
@@ -186,6 +333,128 @@ void launch_two_loop(sdplrp_handle *h, const Slice &sl, const double *in, const 
     KLAUNCH(h);
 }
 
+
+bool gram_enabled(const sdplrp_handle *h) { return h->lbfgs_kernel == 1 && h->hist >= 1 && h->hist <= kGramMaxHist; }
+
+// position q of the kernel's basis holds slot (rot + q) % hist
+LbPtrs gram_ptrs(const sdplrp_handle *h, i64 off, int rot = 0) {
+    LbPtrs P = {};
+    for (int q = 0; q < h->hist; q++) {
+        const int k = (rot + q) % h->hist;
+        P.S[q] = h->Sh[k] + off; P.Y[q] = h->Yh[k] + off;
+    }
+    return P;
+}
+
+// dots of up to three probe vectors with the whole basis (optionally writing the new pair of slot j first)
+template <int M>
+int32_t gram_pass_m(sdplrp_handle *h, const Slice &sl, bool update, double alpha, int j, int p0, int p1, int p2) {
+    // update: rotate the slots so that slot j sits at position M-1 (static probe positions in the kernel)
+    const int rot = update ? (j + 1) % M : 0;
+    if (update) { p0 = M - 1; p1 = 2 * M - 1; p2 = 2 * M; }
+    const LbPtrs P = gram_ptrs(h, sl.off, rot);
+    const double *G = h->G + sl.off, *D = h->D + sl.off;
+    double *Sj = update ? h->Sh[j] + sl.off : nullptr, *Yj = update ? h->Yh[j] + sl.off : nullptr;
+    double *tmp = h->lb_small + kGramNB * kGramNB;
+#define GP_LAUNCH(VECN, UPD) k_gram_pass<VECN, M, UPD><<<sl.grid, TPB, 0, h->stream>>>(sl.nu, alpha, P, G, D, Sj, Yj, p0, p1, p2, h->partials, h->ticket, tmp)
+    if (sl.vec == 2) { if (update) GP_LAUNCH(2, true); else GP_LAUNCH(2, false); }
+    else { if (update) GP_LAUNCH(1, true); else GP_LAUNCH(1, false); }
+#undef GP_LAUNCH
+    KLAUNCH(h);
+    CUDA_TRY(h, cudaGetLastError());
+    SDP_CHECK(comm_reduce_ptr(h, tmp, 3 * (2 * M + 1)));
+    k_gram_commit<<<1, 32, 0, h->stream>>>(M, rot, p0, p1, p2, tmp, h->lb_small, update ? j : -1, h->dscal + SC_RHO);
+    KLAUNCH(h);
+    return SDPLRP_OK;
+}
+int32_t gram_pass(sdplrp_handle *h, const Slice &sl, bool update, double alpha, int j, int p0, int p1, int p2) {
+    switch (h->hist) {
+    case 1: return gram_pass_m<1>(h, sl, update, alpha, j, p0, p1, p2);
+    case 2: return gram_pass_m<2>(h, sl, update, alpha, j, p0, p1, p2);
+    case 3: return gram_pass_m<3>(h, sl, update, alpha, j, p0, p1, p2);
+    case 4: return gram_pass_m<4>(h, sl, update, alpha, j, p0, p1, p2);
+    case 5: return gram_pass_m<5>(h, sl, update, alpha, j, p0, p1, p2);
+    case 6: return gram_pass_m<6>(h, sl, update, alpha, j, p0, p1, p2);
+    case 7: return gram_pass_m<7>(h, sl, update, alpha, j, p0, p1, p2);
+    default: return gram_pass_m<8>(h, sl, update, alpha, j, p0, p1, p2);
+    }
+}
+
+template <int M>
+int32_t gram_form_m(sdplrp_handle *h, const Slice &sl, int jpre) {
+    const LbPtrs P = gram_ptrs(h, sl.off);
+    const double *coef = h->lb_small + kGramNB * kGramNB + 3 * kGramNB;
+    if (sl.vec == 2)
+        k_gram_form<2, M><<<sl.grid, TPB, 0, h->stream>>>(sl.nu, P, h->G + sl.off, coef, h->D + sl.off, h->Yh[jpre] + sl.off, jpre,
+                                                          h->partials, h->ticket, h->dscal + SC_DESCENT);
+    else
+        k_gram_form<1, M><<<sl.grid, TPB, 0, h->stream>>>(sl.nu, P, h->G + sl.off, coef, h->D + sl.off, h->Yh[jpre] + sl.off, jpre,
+                                                          h->partials, h->ticket, h->dscal + SC_DESCENT);
+    KLAUNCH(h);
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+int32_t gram_form(sdplrp_handle *h, const Slice &sl, int jpre) {
+    switch (h->hist) {
+    case 1: return gram_form_m<1>(h, sl, jpre);
+    case 2: return gram_form_m<2>(h, sl, jpre);
+    case 3: return gram_form_m<3>(h, sl, jpre);
+    case 4: return gram_form_m<4>(h, sl, jpre);
+    case 5: return gram_form_m<5>(h, sl, jpre);
+    case 6: return gram_form_m<6>(h, sl, jpre);
+    case 7: return gram_form_m<7>(h, sl, jpre);
+    default: return gram_form_m<8>(h, sl, jpre);
+    }
+}
+
+// bring the Gram matrix in line with the vectors in memory (only after uploads / out-of-order calls)
+int32_t gram_refresh(sdplrp_handle *h, const Slice &sl) {
+    const int M = h->hist, NB = 2 * M + 1;
+    if (!h->gram_pairs_valid) {
+        for (int p = 0; p < NB - 1; p += 3)
+            SDP_CHECK(gram_pass(h, sl, false, 0.0, -1, p, p + 1 < NB - 1 ? p + 1 : -1, p + 2 < NB - 1 ? p + 2 : -1));
+        h->gram_pairs_valid = true;
+    }
+    if (!h->gram_g_valid) {
+        SDP_CHECK(gram_pass(h, sl, false, 0.0, -1, 2 * M, -1, -1));
+        h->gram_g_valid = true;
+    }
+    return SDPLRP_OK;
+}
+
+int32_t lb_dir_gram(sdplrp_handle *h) {
+    const Slice sl = owned(h);
+    const int M = h->hist;
+    SDP_CHECK(gram_refresh(h, sl));
+    double *coef = h->lb_small + kGramNB * kGramNB + 3 * kGramNB;
+    k_gram_coef<<<1, 32, 0, h->stream>>>(M, h->latest, h->lb_small, h->dscal + SC_RHO, coef);
+    KLAUNCH(h);
+    const int jpre = h->latest % M;
+    SDP_CHECK(gram_form(h, sl, jpre));
+    SDP_CHECK(comm_reduce_ptr(h, h->dscal + SC_DESCENT, 1));
+    h->gram_pairs_valid = false;  // slot jpre now holds y = -g: its rows are rebuilt by the update pass (or a refresh)
+    h->gram_prestored = jpre;
+    return SDPLRP_OK;
+}
+
+int32_t lb_update_gram(sdplrp_handle *h, double alpha) {
+    const Slice sl = owned(h);
+    const int M = h->hist;
+    const int j = h->latest % M;
+    // everything except slot j must be current: true when the only stale rows are those of the pre-stored slot j
+    if (!h->gram_pairs_valid && h->gram_prestored != j) {
+        // unusual call order (e.g. uploads): rebuild the rows of every other slot from memory
+        for (int p = 0; p < 2 * M; p++) {
+            if (p == j || p == M + j) continue;
+            SDP_CHECK(gram_pass(h, sl, false, 0.0, -1, p, -1, -1));
+        }
+    }
+    SDP_CHECK(gram_pass(h, sl, true, alpha, j, j, M + j, 2 * M));
+    h->gram_pairs_valid = true; h->gram_g_valid = true; h->gram_prestored = -1;
+    h->latest = j + 1;
+    return SDPLRP_OK;
+}
+
 }  // namespace
 
 // lbfgs_dir!(dirt, his, Gt; negate=true) followed by descent = dot(dirt, Gt)
@@ -200,6 +469,7 @@ int32_t lb_dir(sdplrp_handle *h) {
         CUDA_TRY(h, cudaGetLastError());
         return comm_reduce_ptr(h, descent, 1);
     }
+    if (gram_enabled(h)) return lb_dir_gram(h);
     // slot order: newest -> oldest (1-based j as in the reference)
     int order[kMaxHist];
     {
@@ -244,6 +514,7 @@ int32_t lb_dir(sdplrp_handle *h) {
 int32_t lb_update(sdplrp_handle *h, double alpha) {
     const int m = h->hist;
     if (m == 0) return SDPLRP_OK;
+    if (gram_enabled(h)) return lb_update_gram(h, alpha);
     const Slice sl = owned(h);
     const int j = h->latest % m;  // 0-based mod(latest,h)+1
     DISPATCH_VEC(sl, k_update, sl.nu, alpha, h->D + sl.off, h->G + sl.off, h->Sh[j] + sl.off, h->Yh[j] + sl.off, h->partials,
@@ -265,6 +536,10 @@ int32_t lb_clear(sdplrp_handle *h) {
     }
     CUDA_TRY(h, cudaMemsetAsync(h->dscal + SC_RHO, 0, kMaxHist * sizeof(double), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->dscal + SC_A, 0, kMaxHist * sizeof(double), h->stream));
+    if (h->lb_small) CUDA_TRY(h, cudaMemsetAsync(h->lb_small, 0, (size_t)kLbSmallLen * sizeof(double), h->stream));
+    h->gram_pairs_valid = true;   // all-zero history: every pair dot is zero
+    h->gram_g_valid = true;       // ... and so is every <g, s_j>, <g, y_j>; <g, g> is not used by the recursion
+    h->gram_prestored = -1;
     return SDPLRP_OK;
 }
 

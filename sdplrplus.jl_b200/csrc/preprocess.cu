@@ -303,12 +303,46 @@ __global__ void k_cfull(i64 nnzF, const int *__restrict__ mapped, const int *__r
     }
 }
 // mark the full-pattern slots (both mirrored positions) of every dynamic triu slot
-__global__ void k_dyn_mark(i64 nd, const int *__restrict__ pos_a, const int *__restrict__ pos_b, int *__restrict__ flag,
-                           int *__restrict__ src) {
+__global__ void k_dyn_mark(i64 nd, const int *__restrict__ pos_a, const int *__restrict__ pos_b, const int *__restrict__ full_idx,
+                           int *__restrict__ flag, int *__restrict__ src, int *__restrict__ dyn_diag) {
     for (i64 d = blockIdx.x * (i64)blockDim.x + threadIdx.x; d < nd; d += (i64)gridDim.x * blockDim.x) {
         const int a = pos_a[d], b = pos_b[d];
+        if (a >= 0 && a == b) { dyn_diag[full_idx[a]] = (int)d; continue; }  // diagonal slot: row scaling, not a gather
         if (a >= 0) { flag[a] = 1; src[a] = (int)d; }
         if (b >= 0) { flag[b] = 1; src[b] = (int)d; }
+    }
+}
+__global__ void k_fill_int(i64 nItems, int v, int *__restrict__ x) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nItems; k += (i64)gridDim.x * blockDim.x) x[k] = v;
+}
+// single-diagonal-entry constraint matrices -> sort key = their (internal) row, n for every other matrix
+__global__ void k_sd_keys(i64 nA, i64 n, int obj_mat, const int *__restrict__ matptr, const int *__restrict__ ent_row,
+                          const int *__restrict__ ent_col, unsigned *__restrict__ key, int *__restrict__ val,
+                          unsigned char *__restrict__ sd_flag) {
+    for (i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x; a < nA; a += (i64)gridDim.x * blockDim.x) {
+        const int k = matptr[a];
+        const bool sd = (matptr[a + 1] - k == 1) && (int)a != obj_mat && ent_row[k] == ent_col[k];
+        key[a] = sd ? (unsigned)ent_row[k] : (unsigned)n;
+        val[a] = (int)a;
+        sd_flag[a] = sd ? 1 : 0;
+    }
+}
+__global__ void k_lower_bound_u32(i64 n, i64 len, const unsigned *__restrict__ sorted, int *__restrict__ ptr) {
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i <= n; i += (i64)gridDim.x * blockDim.x) {
+        i64 lo = 0, hi = len;
+        while (lo < hi) {
+            i64 mid = (lo + hi) >> 1;
+            if (sorted[mid] < (unsigned)i) lo = mid + 1; else hi = mid;
+        }
+        ptr[i] = (int)lo;
+    }
+}
+__global__ void k_sd_fill(i64 n_sd, const int *__restrict__ sorted_a, const int *__restrict__ matptr, const int *__restrict__ mat_gid,
+                          const double *__restrict__ ent_two, int *__restrict__ gid, double *__restrict__ val) {
+    for (i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x; p < n_sd; p += (i64)gridDim.x * blockDim.x) {
+        const int a = sorted_a[p];
+        gid[p] = mat_gid[a];
+        val[p] = ent_two[matptr[a]];
     }
 }
 __global__ void k_dyn_rows(i64 nnzF, const int *__restrict__ flag, const int *__restrict__ pos, const int *__restrict__ src,
@@ -458,6 +492,8 @@ void pre_free(sdplrp_handle *h) {
     dev_free(&h->triuS_static); dev_free(&h->dyn_slot); dev_free(&h->dyn_ptr); dev_free(&h->dyn_gid);
     dev_free(&h->dyn_val); dev_free(&h->dyn_pos_a); dev_free(&h->dyn_pos_b);
     dev_free(&h->Cfull); dev_free(&h->dynS); dev_free(&h->dynrow_ptr); dev_free(&h->dynrow_col); dev_free(&h->dynrow_src);
+    dev_free(&h->dyn_diag); dev_free(&h->rowc_ptr); dev_free(&h->rowc_gid); dev_free(&h->rowc_val); dev_free(&h->sd_flag);
+    h->n_sd = 0;
     dev_free(&h->full_cls.storage); dev_free(&h->dyn_cls.storage);
     h->full_cls = RowClasses(); h->dyn_cls = RowClasses();
     h->CR_valid = h->CD_valid = false;
@@ -674,13 +710,15 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
     SDP_CHECK(dev_alloc(h, &h->Cfull, nnzF));
     SDP_CHECK(dev_alloc(h, &h->dynS, h->n_dyn));
     SDP_CHECK(dev_alloc(h, &h->dynrow_ptr, n + 1));
+    SDP_CHECK(dev_alloc(h, &h->dyn_diag, n));
+    k_fill_int<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, -1, h->dyn_diag); KLAUNCH(h);
     h->n_dynF = 0;
     if (nnzF > 0) {
         k_cfull<<<GS, TPB, 0, st>>>(nnzF, h->mapped, h->i2r, h->triuS_static, h->Cfull); KLAUNCH(h);
         int *fflag = tmp.get<int>(h, nnzF + 1, &rc), *fpos = tmp.get<int>(h, nnzF + 1, &rc), *fsrc = tmp.get<int>(h, nnzF + 1, &rc);
         if (rc) return rc;
         CUDA_TRY(h, cudaMemsetAsync(fflag, 0, (size_t)(nnzF + 1) * sizeof(int), st));
-        if (h->n_dyn > 0) { k_dyn_mark<<<GS, TPB, 0, st>>>(h->n_dyn, h->dyn_pos_a, h->dyn_pos_b, fflag, fsrc); KLAUNCH(h); }
+        if (h->n_dyn > 0) { k_dyn_mark<<<GS, TPB, 0, st>>>(h->n_dyn, h->dyn_pos_a, h->dyn_pos_b, h->full_idx, fflag, fsrc, h->dyn_diag); KLAUNCH(h); }
         SDP_CHECK(exclusive_scan(h, fflag, fpos, nnzF + 1));
         int ndf = 0;
         SDP_CHECK(read_int(h, fpos + nnzF, &ndf));
@@ -697,6 +735,33 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
     if (h->relabeled && Ec > 0) {
         k_apply_perm<<<GS, TPB, 0, st>>>(Ec, h->perm, h->ent_row); KLAUNCH(h);
         k_apply_perm<<<GS, TPB, 0, st>>>(Ec, h->perm, h->ent_col); KLAUNCH(h);
+    }
+
+    // ---- single-diagonal-entry constraints as per-row lists (streaming A passes) ----
+    h->n_sd = 0;
+    SDP_CHECK(dev_alloc(h, &h->rowc_ptr, n + 1));
+    SDP_CHECK(dev_alloc(h, &h->sd_flag, nA));
+    CUDA_TRY(h, cudaMemsetAsync(h->rowc_ptr, 0, (size_t)(n + 1) * sizeof(int), st));
+    if (nA > 0) {
+        unsigned *skey = tmp.get<unsigned>(h, nA, &rc), *skey2 = tmp.get<unsigned>(h, nA, &rc);
+        int *sval = tmp.get<int>(h, nA, &rc), *sval2 = tmp.get<int>(h, nA, &rc);
+        if (rc) return rc;
+        k_sd_keys<<<grid_for(nA, TPB, GS), TPB, 0, st>>>(nA, n, h->obj_mat, h->matptr, h->ent_row, h->ent_col, skey, sval, h->sd_flag);
+        KLAUNCH(h);
+        h->launches += 4;
+        SDP_CHECK(with_cub_temp(h, [&](void *t, size_t &b) {
+            return cub::DeviceRadixSort::SortPairs(t, b, skey, skey2, sval, sval2, (int)nA, 0, bits_for(n + 2), st);
+        }));
+        k_lower_bound_u32<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, nA, skey2, h->rowc_ptr); KLAUNCH(h);
+        int nsd = 0;
+        SDP_CHECK(read_int(h, h->rowc_ptr + n, &nsd));
+        h->n_sd = nsd;
+        SDP_CHECK(dev_alloc(h, &h->rowc_gid, nsd)); SDP_CHECK(dev_alloc(h, &h->rowc_val, nsd));
+        if (nsd > 0) {
+            k_sd_fill<<<grid_for(nsd, TPB, GS), TPB, 0, st>>>(nsd, sval2, h->matptr, h->mat_gid, h->ent_two, h->rowc_gid, h->rowc_val);
+            KLAUNCH(h);
+        }
+        CUDA_TRY(h, cudaStreamSynchronize(st));
     }
 
     // ---- row bins of both patterns (sparse x dense kernels) -----------------------

@@ -28,8 +28,8 @@ def oracle_mod():
 
 # kernel configurations every GPU parity test runs under: the product default (auto relabeling,
 # async-copy tile SpMM), forced hub-first relabeling (exercises every permuting copy on the small
-# regular test graphs too), and the async-copy tile-stream SpMM kernel
-GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "tile": {"relabel": 1, "spmm_kernel": 1}}
+# regular test graphs too), and the alternative kernels (async-copy tile-stream SpMM, literal vector two-loop)
+GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "tile": {"relabel": 1, "spmm_kernel": 1, "lbfgs_kernel": 0}}
 
 
 @pytest.fixture(scope="session")

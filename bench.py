@@ -103,6 +103,7 @@ def algorithmic_bytes(n, m, r, nnzT, nnzF, Ec, h, rows_local):
         "spmm": 2 * N + frac * (4 * (n + 1) + 12 * nnzF),                         # CD = C*D: SURVEY 8d B_G
         "grad": 3 * N + frac * (12.0 * (Ec - nnzT) + 8.0 * m + 4.0 * (n + 1)),    # G = 2(y_obj CR + S_dyn R), ||G||^2
         "norms": 16.0 * m,
+        "tail": 7 * N + 72.0 * m,                                                 # fused step + y + gradient + norms row pass
         "lbfgs_update": (2 * h + 3) * N,                                          # new pair + its dots with the whole history, 11N at h=4
     }
 
@@ -171,7 +172,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--vertices", dest="n", type=int, default=10_000_000)
     ap.add_argument("--edges", type=int, default=80_000_000)
     ap.add_argument("--rank", type=int, default=10)
     ap.add_argument("--seed", type=int, default=42)

@@ -92,6 +92,7 @@ void *sdplrp_stream(sdplrp_handle *h);
  *                 sdplrp_preprocess.  Invisible at the ABI (every upload/download converts).
  *   "hot_rows"    leading rows of the gathered factor pinned in L2 (evict_last); -1 = sized from L2
  *   "spmm_kernel" 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel (experimental)
+ *   "fused_tail"  1 = sdplrp_step_g uses the fused row pass (default), 0 = step and g separately
  *   "lbfgs_kernel" 1 = two-loop recursion on coefficients over directly computed dot products (default,
  *                 numlbfgsvecs <= 8), 0 = literal vector two-loop */
 int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value);
@@ -166,6 +167,10 @@ int32_t sdplrp_linesearch_coeffs(sdplrp_handle *h, double biquadratic[5]);
 /* after alpha is chosen: primal_vio_raw += a(a A_DD + A_RD), obj, and
  * Rt += a*dirt; src/linesearch.jl:118-124, src/sdplr.jl:219 */
 int32_t sdplrp_step(sdplrp_handle *h, double alpha, double *obj);
+/* sdplrp_step followed by sdplrp_g as ONE call (the caller's `axpy!` + `g!` + the two norms, src/sdplr.jl:219-234):
+ * out = {obj, ||G||_F^2, ||pvio||_2^2}.  When the line search of the current direction is still valid the library
+ * runs them as a single fused row pass; results are those of the two separate calls. */
+int32_t sdplrp_step_g(sdplrp_handle *h, double alpha, double out[3]);
 /* lbfgs_update!(dirt, his, Gt, alpha); src/lbfgs.jl:129-149 */
 int32_t sdplrp_lbfgs_update(sdplrp_handle *h, double alpha);
 /* lbfgs_clear!; src/lbfgs.jl:52-59 */
@@ -208,7 +213,8 @@ enum {
     SDPLRP_SEC_LANCZOS = 10,
     SDPLRP_SEC_COMM = 11,        /* NCCL collectives */
     SDPLRP_SEC_GRAD = 12,        /* G = 2*(y_obj*CR + S_dyn*R + low rank) with ||G||^2 fused */
-    SDPLRP_SEC_COUNT = 13
+    SDPLRP_SEC_TAIL = 13,        /* fused step + y + gradient + norms row pass (sdplrp_step_g) */
+    SDPLRP_SEC_COUNT = 14
 };
 /* on != 0: record a CUDA-event pair around every section from now on */
 int32_t sdplrp_set_profiling(sdplrp_handle *h, int32_t on);

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "sdplrp_use_gradient_direction": [_H],
     "sdplrp_linesearch_coeffs": [_H, _p_f64],
     "sdplrp_step": [_H, C.c_double, _p_f64],
+    "sdplrp_step_g": [_H, C.c_double, _p_f64],
     "sdplrp_lbfgs_update": [_H, C.c_double],
     "sdplrp_lbfgs_clear": [_H],
     "sdplrp_dual_update": [_H],
@@ -328,6 +329,12 @@ class Handle:
         self._check(self.lib.sdplrp_step(self._h, float(alpha), C.byref(o) if want_obj else None))
         return o.value
 
+    def step_g(self, alpha):
+        """step + g in one call -> (obj, ||G||_F^2, ||pvio||_2^2)"""
+        out = (C.c_double * 3)()
+        self._check(self.lib.sdplrp_step_g(self._h, float(alpha), out))
+        return out[0], out[1], out[2]
+
     def lbfgs_update(self, alpha):
         self._check(self.lib.sdplrp_lbfgs_update(self._h, float(alpha)))
 
@@ -367,7 +374,7 @@ class Handle:
         return d.value, e.value, s.value
 
     SECTIONS = ["lbfgs_dir", "ls_pass", "ls_coeff", "step", "s_assemble", "spmm", "norms", "lbfgs_update", "a_uu", "f_finish",
-                "lanczos", "comm", "grad"]
+                "lanczos", "comm", "grad", "tail"]
 
     def set_profiling(self, on):
         self._check(self.lib.sdplrp_set_profiling(self._h, int(bool(on))))

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(TPB) k_A_short(int nA, const int *__restrict__
 // lanes owns row i, forms <U_i,U_i> / <U_i,V_i> / <V_i,V_i> once and serves every constraint listed for the row.
 template <int MODE, int VEC>
 __global__ void __launch_bounds__(TPB) k_A_rowc(long long lo, long long hi, const int *__restrict__ rowc_ptr,
-                                                const int *__restrict__ rowc_gid, const double *__restrict__ rowc_val,
+                                                const double *__restrict__ rowc_val,
                                                 const double *__restrict__ U, const double *__restrict__ V, int r, int G,
                                                 double *__restrict__ out1, double *__restrict__ out2) {
     typedef Ld<VEC> L;
@@ -159,10 +159,9 @@ __global__ void __launch_bounds__(TPB) k_A_rowc(long long lo, long long hi, cons
         d1 = group_sum(d1, G);
         if (MODE == 2) d2 = group_sum(d2, G);
         for (int k = beg + lg; k < end; k += G) {
-            const double val = rowc_val[k];
-            const int gid = rowc_gid[k];
-            out1[gid] = (MODE == 2 ? 2.0 : 1.0) * val * d1;  // MODE 2: A_RD is kept already doubled
-            if (MODE == 2) out2[gid] = val * d2;
+            const double val = rowc_val[k];  // constraint k of this row IS internal slot k: coalesced stores
+            out1[k] = (MODE == 2 ? 2.0 : 1.0) * val * d1;  // MODE 2: A_RD is kept already doubled
+            if (MODE == 2) out2[k] = val * d2;
         }
     }
 }
@@ -298,8 +297,8 @@ int32_t run_sparse(sdplrp_handle *h, const double *U, const double *V, double *o
     }
     if (h->n_sd > 0) {
         const int grid_rows = grid_for(h->row_hi - h->row_lo, gpb, 16 * kNumSM);
-        if (vec2) k_A_rowc<MODE, 2><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_gid, h->rowc_val, U, V, r, G, out1, out2);
-        else k_A_rowc<MODE, 1><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_gid, h->rowc_val, U, V, r, G, out1, out2);
+        if (vec2) k_A_rowc<MODE, 2><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, G, out1, out2);
+        else k_A_rowc<MODE, 1><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, G, out1, out2);
         KLAUNCH(h);
     }
     if (h->n_chunks > 0) {

@@ -78,11 +78,14 @@ static double *vec_ptr(sdplrp_handle *h, int id, i64 *len) {
 __global__ void k_fill(i64 len, double v, double *__restrict__ x) {
     for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < len; i += (i64)gridDim.x * blockDim.x) x[i] = v;
 }
-__global__ void k_bounds(i64 m, const unsigned char *__restrict__ ineq, double *__restrict__ ub, double *__restrict__ lb) {
-    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
-        const bool q = ineq && ineq[i];
-        ub[i] = q ? 0.0 : INFINITY;   // src/structs.jl:228
-        lb[i] = q ? 0.0 : -INFINITY;  // src/structs.jl:249
+// `ineq` is in reference constraint order, ub / lb in the internal order (cperm)
+__global__ void k_bounds(i64 m, const unsigned char *__restrict__ ineq, const int *__restrict__ cperm, double *__restrict__ ub,
+                         double *__restrict__ lb) {
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < m; g += (i64)gridDim.x * blockDim.x) {
+        const bool q = ineq && ineq[g];
+        const i64 c = cperm ? cperm[g] : g;
+        ub[c] = q ? 0.0 : INFINITY;   // src/structs.jl:228
+        lb[c] = q ? 0.0 : -INFINITY;  // src/structs.jl:249
     }
 }
 
@@ -151,7 +154,7 @@ static void free_problem(sdplrp_handle *h) {
     for (LowRank &L : h->lr) { dev_free(&L.dB); dev_free(&L.dD); }
     h->lr.clear();
     dev_free(&h->b); dev_free(&h->lambda); dev_free(&h->lambda_ub); dev_free(&h->pvio_lb);
-    dev_free(&h->y); dev_free(&h->pvio_raw); dev_free(&h->A_RD); dev_free(&h->A_DD); dev_free(&h->A_out);
+    dev_free(&h->y); dev_free(&h->pvio_raw); dev_free(&h->pvio_raw_alt); dev_free(&h->A_RD); dev_free(&h->A_DD); dev_free(&h->A_out);
     dev_free(&h->lz_v); dev_free(&h->lz_w); dev_free(&h->lz_vp); dev_free(&h->lz_ab); dev_free(&h->lz_basis);
     h->lz_ab_len = 0; h->lz_basis_len = 0;
     dev_free(&h->stage); h->stage_len = 0;
@@ -193,17 +196,18 @@ int32_t sdplrp_preprocess(sdplrp_handle *h, int64_t n, int64_t m, int64_t nA, co
     if (rc != SDPLRP_OK && rc != SDPLRP_ERR_ASYMMETRIC) return rc;
     // vectors of SolverVars / SDPData
     SDP_CHECK(dev_alloc(h, &h->b, m)); SDP_CHECK(dev_alloc(h, &h->lambda, m)); SDP_CHECK(dev_alloc(h, &h->lambda_ub, m));
-    SDP_CHECK(dev_alloc(h, &h->pvio_lb, m)); SDP_CHECK(dev_alloc(h, &h->y, m + 1)); SDP_CHECK(dev_alloc(h, &h->pvio_raw, m + 1));
+    SDP_CHECK(dev_alloc(h, &h->pvio_lb, m)); SDP_CHECK(dev_alloc(h, &h->y, m + 1)); SDP_CHECK(dev_alloc(h, &h->pvio_raw, m + 1)); SDP_CHECK(dev_alloc(h, &h->pvio_raw_alt, m + 1));
     SDP_CHECK(dev_alloc(h, &h->A_RD, m + 1)); SDP_CHECK(dev_alloc(h, &h->A_DD, m + 1)); SDP_CHECK(dev_alloc(h, &h->A_out, m + 1));
     cudaStream_t st = h->stream;
     CUDA_TRY(h, cudaMemsetAsync(h->b, 0, (size_t)std::max<i64>(m, 1) * 8, st));
     CUDA_TRY(h, cudaMemsetAsync(h->lambda, 0, (size_t)std::max<i64>(m, 1) * 8, st));
     CUDA_TRY(h, cudaMemsetAsync(h->y, 0, (size_t)(m + 1) * 8, st));
     CUDA_TRY(h, cudaMemsetAsync(h->pvio_raw, 0, (size_t)(m + 1) * 8, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->pvio_raw_alt, 0, (size_t)(m + 1) * 8, st));
     CUDA_TRY(h, cudaMemsetAsync(h->A_RD, 0, (size_t)(m + 1) * 8, st));
     CUDA_TRY(h, cudaMemsetAsync(h->A_DD, 0, (size_t)(m + 1) * 8, st));
     CUDA_TRY(h, cudaMemsetAsync(h->A_out, 0, (size_t)(m + 1) * 8, st));
-    k_bounds<<<grid_for(m, 256, kRedBlocks), 256, 0, st>>>(m, nullptr, h->lambda_ub, h->pvio_lb);
+    k_bounds<<<grid_for(m, 256, kRedBlocks), 256, 0, st>>>(m, nullptr, h->cperm, h->lambda_ub, h->pvio_lb);
     KLAUNCH(h);
     CUDA_TRY(h, cudaStreamSynchronize(st));
     h->y_obj = 0.0;
@@ -235,7 +239,9 @@ int32_t sdplrp_add_symlowrank(sdplrp_handle *h, int64_t global_id, int64_t s, co
     if (global_id < 1 || global_id > h->m + 1 || s < 1 || !B || !D) return fail(h, SDPLRP_ERR_ARG, "add_symlowrank: bad argument");
     CUDA_TRY(h, cudaSetDevice(h->device));
     LowRank L;
-    L.gid = global_id - 1; L.s = s; L.dB = nullptr; L.dD = nullptr;
+    int gid_internal = (int)(global_id - 1);
+    CUDA_TRY(h, cudaMemcpy(&gid_internal, h->cperm + (global_id - 1), sizeof(int), cudaMemcpyDeviceToHost));  // internal constraint slot
+    L.gid = gid_internal; L.s = s; L.dB = nullptr; L.dD = nullptr;
     SDP_CHECK(dev_alloc(h, &L.dB, h->n * s));
     SDP_CHECK(dev_alloc(h, &L.dD, s));
     h->lr.push_back(L);  // owned by the handle from here on (freed by free_problem even if a copy fails)
@@ -250,13 +256,13 @@ int32_t sdplrp_set_problem(sdplrp_handle *h, const double *b, const uint8_t *is_
     CUDA_TRY(h, cudaSetDevice(h->device));
     const i64 m = h->m;
     if (m > 0 && !b) return fail(h, SDPLRP_ERR_ARG, "set_problem: null b");
-    if (m > 0) CUDA_TRY(h, cudaMemcpy(h->b, b, (size_t)m * 8, cudaMemcpyHostToDevice));
+    if (m > 0) SDP_CHECK(perm_cvec_upload(h, h->b, b, m));
     unsigned char *dq = nullptr;
     if (is_ineq && m > 0) {
         CUDA_TRY(h, cudaMalloc((void **)&dq, (size_t)m));
         CUDA_TRY(h, cudaMemcpy(dq, is_ineq, (size_t)m, cudaMemcpyHostToDevice));
     }
-    k_bounds<<<grid_for(m, 256, kRedBlocks), 256, 0, h->stream>>>(m, dq, h->lambda_ub, h->pvio_lb);
+    k_bounds<<<grid_for(m, 256, kRedBlocks), 256, 0, h->stream>>>(m, dq, h->cperm, h->lambda_ub, h->pvio_lb);
     KLAUNCH(h);
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (dq) cudaFree(dq);
@@ -291,6 +297,7 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
     if (k == "relabel") { h->relabel_mode = value < 0 ? -1 : (value > 0 ? 1 : 0); return SDPLRP_OK; }  // before preprocess
     if (k == "hot_rows") { h->hot_rows = (i64)value; return SDPLRP_OK; }
     if (k == "spmm_kernel") { h->spmm_kernel = (int)value; return SDPLRP_OK; }
+    if (k == "fused_tail") { h->fused_tail = value != 0; return SDPLRP_OK; }
     if (k == "lbfgs_kernel") { h->lbfgs_kernel = (int)value; h->gram_pairs_valid = h->gram_g_valid = false; return SDPLRP_OK; }
     return fail(h, SDPLRP_ERR_ARG, "set_option: unknown key " + k);
 }
@@ -321,7 +328,8 @@ int32_t sdplrp_upload_mat(sdplrp_handle *h, int32_t id, const double *src) {
     SDP_CHECK(perm_upload(h, p, src, h->r, true));
     comm_mark_full(h, id);
     if (id == SDPLRP_MAT_R) h->CR_valid = false;
-    if (id == SDPLRP_MAT_D) h->CD_valid = false;
+    if (id == SDPLRP_MAT_D) { h->CD_valid = false; h->ls_valid = false; }
+    if (id == SDPLRP_MAT_R) h->ls_valid = false;
     if (id == SDPLRP_MAT_G) h->gram_g_valid = false;
     if (id >= SDPLRP_MAT_S0) { h->gram_pairs_valid = false; h->gram_prestored = -1; }
     return SDPLRP_OK;
@@ -348,8 +356,7 @@ int32_t sdplrp_upload_vec(sdplrp_handle *h, int32_t id, const double *src, int64
     if (id == SDPLRP_VEC_S_NZVAL) {
         SDP_CHECK(perm_slots_upload(h, p, src, len));
     } else {
-        if (len > 0) CUDA_TRY(h, cudaMemcpyAsync(p, src, (size_t)len * 8, cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        SDP_CHECK(perm_cvec_upload(h, p, src, len));  // m-vectors live in the internal constraint order
     }
     if (id == SDPLRP_VEC_Y) { h->y_obj = src[h->m]; h->S_current = false; }
     if (id == SDPLRP_VEC_S_NZVAL) { h->S_static_valid = false; h->S_current = true; }
@@ -377,17 +384,13 @@ int32_t sdplrp_download_vec(sdplrp_handle *h, int32_t id, double *dst, int64_t l
     double *p = vec_ptr(h, id, &want);
     if (!p || !dst || len != want) return fail(h, SDPLRP_ERR_ARG, "download_vec: bad id or length");
     if (id == SDPLRP_VEC_S_NZVAL) return perm_slots_download(h, p, dst, len);
-    if (len > 0) CUDA_TRY(h, cudaMemcpyAsync(dst, p, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return SDPLRP_OK;
+    return perm_cvec_download(h, p, dst, len);
 }
 
 // ---- seam-level operators ----------------------------------------------------
 static int32_t copy_out(sdplrp_handle *h, const double *dev, double *host, i64 len) {
     if (!host) return SDPLRP_OK;
-    CUDA_TRY(h, cudaMemcpyAsync(host, dev, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return SDPLRP_OK;
+    return perm_cvec_download(h, dev, host, len);  // (m+1)-vector: internal -> reference constraint order
 }
 
 int32_t sdplrp_A_uu(sdplrp_handle *h, int32_t U_id, double *out) {
@@ -418,8 +421,7 @@ int32_t sdplrp_At_preprocess(sdplrp_handle *h, const double *y) {
     REQUIRE_H(h); REQUIRE_PRE(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (y) {
-        CUDA_TRY(h, cudaMemcpyAsync(h->y, y, (size_t)(h->m + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        SDP_CHECK(perm_cvec_upload(h, h->y, y, h->m + 1));
         h->y_obj = y[h->m];
     }
     return grad_assemble_S(h);
@@ -543,7 +545,7 @@ int32_t sdplrp_lbfgs_dir(sdplrp_handle *h, double *descent) {
         SectionScope sc(h, SDPLRP_SEC_LBFGS_DIR);
         SDP_CHECK(lb_dir(h));
     }
-    h->CD_valid = false;
+    h->CD_valid = false; h->ls_valid = false;
     comm_mark_partial(h, SDPLRP_MAT_D);
     SDP_CHECK(fetch_scalars(h, SC_DESCENT, 1));
     if (descent) *descent = h->hscal[SC_DESCENT];
@@ -555,7 +557,7 @@ int32_t sdplrp_use_gradient_direction(sdplrp_handle *h) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     SDP_CHECK(lb_neg_copy(h));
     h->gram_g_valid = false;
-    h->CD_valid = false;
+    h->CD_valid = false; h->ls_valid = false;
     comm_mark_partial(h, SDPLRP_MAT_D);
     return SDPLRP_OK;
 }
@@ -583,6 +585,7 @@ int32_t sdplrp_linesearch_coeffs(sdplrp_handle *h, double bq[5]) {
         SectionScope sc(h, SDPLRP_SEC_LS_COEFF);
         SDP_CHECK(vec_biquadratic(h));
     }
+    h->ls_valid = true;
     SDP_CHECK(fetch_scalars(h, SC_BQ, 5));
     for (int k = 0; k < 5; k++) bq[k] = h->hscal[SC_BQ + k];
     return SDPLRP_OK;
@@ -603,10 +606,33 @@ int32_t sdplrp_step(sdplrp_handle *h, double alpha, double *obj) {
             else h->CR_valid = false;
         }
     }
+    h->ls_valid = false;
     if (obj) {
         SDP_CHECK(fetch_scalars(h, SC_OBJ, 1));
         *obj = h->hscal[SC_OBJ];
     }
+    return SDPLRP_OK;
+}
+
+// sdplrp_step followed by sdplrp_g, fused into one row pass when the line search of the current direction is
+// still valid (single GPU); out = {obj, ||G||_F^2, ||pvio||_2^2}
+int32_t sdplrp_step_g(sdplrp_handle *h, double alpha, double out[3]) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    if (!out) return fail(h, SDPLRP_ERR_ARG, "step_g: null output");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const bool split = h->obj_mat >= 0;
+    const bool fused = h->fused_tail && h->world == 1 && h->ls_valid && (!split || (h->CR_valid && h->CD_valid));
+    if (fused) {
+        SectionScope sc(h, SDPLRP_SEC_TAIL);
+        SDP_CHECK(grad_step_fused(h, alpha));
+        h->ls_valid = false; h->CD_valid = false;
+        h->gram_g_valid = false;
+    } else {
+        SDP_CHECK(sdplrp_step(h, alpha, nullptr));
+        SDP_CHECK(do_g(h));
+    }
+    SDP_CHECK(fetch_scalars(h, SC_GNORM2, 3));
+    out[0] = h->hscal[SC_OBJ]; out[1] = h->hscal[SC_GNORM2]; out[2] = h->hscal[SC_PNORM2];
     return SDPLRP_OK;
 }
 

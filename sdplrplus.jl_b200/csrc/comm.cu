@@ -111,12 +111,16 @@ int32_t comm_partition(sdplrp_handle *h) {
     }
     std::vector<int> ptr((size_t)n + 1);
     CUDA_TRY(h, cudaMemcpy(ptr.data(), h->full_ptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
-    // weight of a row: its nonzeros plus one (dense BLAS-1 work per row)
-    const double total = (double)ptr[(size_t)n] + (double)n;
+    // weight of a row in "gathered nonzeros": each nonzero of the gather pass costs ~128 B of DRAM granule
+    // traffic; the streaming passes (L-BFGS 22N, step 6N, gradient 3N, constraint pass 2N, ...) cost ~35 rows of
+    // 8r bytes per vertex = ~22 nonzero-equivalents at r = 10.  (With the hub-first order a pure nnz balance
+    // would give the first rank a sliver of the rows and the last rank nearly all the BLAS-1 work.)
+    const double kRowCost = 22.0;
+    const double total = (double)ptr[(size_t)n] + kRowCost * (double)n;
     i64 row = 0;
     for (int p = 1; p < h->world; p++) {
         const double target = total * p / h->world;
-        while (row < n && (double)ptr[(size_t)row] + (double)row < target) row++;
+        while (row < n && (double)ptr[(size_t)row] + kRowCost * (double)row < target) row++;
         h->row_starts[(size_t)p] = row;
     }
     h->row_lo = h->row_starts[(size_t)h->rank];

@@ -128,9 +128,11 @@ struct sdplrp_handle {
     // constraints that are a single diagonal entry (Diag(X) = 1 of MaxCut / cut-norm / bisection ...), as per-row lists in
     // internal row order: their sampled dots are a streaming pass over the factor rows (aop.cu, k_A_rowc)
     i64 n_sd = 0;
-    int *rowc_ptr = nullptr;       // n+1
-    int *rowc_gid = nullptr;       // n_sd  global slot of the constraint
+    int *rowc_ptr = nullptr;       // n+1   constraint p of row i: rowc_ptr[i] <= p < rowc_ptr[i+1]; p IS its internal slot
     double *rowc_val = nullptr;    // n_sd  its value (nzval_one == nzval_two on the diagonal)
+    int *cperm = nullptr;          // m+1   internal slot of reference constraint g (slot m = objective, fixed)
+    int *dyn_nsd_end = nullptr;    // n_dyn end of the contributors that are NOT single-diagonal-entry constraints
+    i64 n_dyn_nsd = 0;             // their total number (0 for MaxCut-type problems: the hot loop then skips S_dyn)
     unsigned char *sd_flag = nullptr;  // nA: matrix handled by the row lists
     RowClasses full_cls, dyn_cls;  // row bins of the full / dynamic pattern
     TileLayout full_tile, dyn_tile; // long-row chunk lists of both patterns (spmm.cu)
@@ -138,6 +140,8 @@ struct sdplrp_handle {
     i64 tile_scratch_len = 0;
     double *CR = nullptr, *CD = nullptr;  // n x r: C*R (recurrence) and C*D
     bool CR_valid = false, CD_valid = false;
+    bool ls_valid = false;         // A_RD / A_DD (and CD) belong to the current R and D
+    bool fused_tail = true;        // sdplrp_step_g may use the fused row pass
 
     // low-rank matrices
     std::vector<LowRank> lr;
@@ -147,6 +151,7 @@ struct sdplrp_handle {
     // vectors
     double *b = nullptr, *lambda = nullptr, *lambda_ub = nullptr, *pvio_lb = nullptr;
     double *y = nullptr, *pvio_raw = nullptr, *A_RD = nullptr, *A_DD = nullptr, *A_out = nullptr;
+    double *pvio_raw_alt = nullptr;  // second residual buffer: the fused step/gradient pass reads one and writes the other
     double sigma = 2.0;
     double y_obj = 0.0;  // host copy of y[m] (coefficient of the objective in S)
 
@@ -311,6 +316,8 @@ int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bo
 int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double *Z, double *sums6);  // Y = C*X, sums <X,Y>, <X,Z>
 int32_t grad_obj_slots(sdplrp_handle *h, const double *sums6, double *a_rd_m, double *a_dd_m);
 int32_t grad_hot(sdplrp_handle *h);                             // G = 2*(y_obj*CR + S_dyn*R + low rank), ||G||^2
+int32_t grad_step_fused(sdplrp_handle *h, double alpha);        // step + y + gradient + both norms in one row pass
+int32_t vec_tail_rest(sdplrp_handle *h, double alpha, const double *raw_in, double *raw_out, double *pn2_out);
 int32_t grad_spmv(sdplrp_handle *h, const double *x, double *y, i64 ncols);                     // y = S*x (+low rank), n x ncols col-major
 int32_t grad_triuS(sdplrp_handle *h, double *out_dev);          // materialise triu_sparse_S.nzval
 
@@ -364,6 +371,8 @@ int32_t perm_download(sdplrp_handle *h, const double *src_dev, double *dst_host,
 int32_t perm_device(sdplrp_handle *h, double *dst, const double *src, i64 ncols, bool row_major, bool to_internal);
 int32_t perm_slots_upload(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 len);
 int32_t perm_slots_download(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 len);
+int32_t perm_cvec_upload(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 len);     // m or m+1 doubles
+int32_t perm_cvec_download(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 len);
 
 // section timers (api.cu)
 cudaEvent_t prof_begin(sdplrp_handle *h);

@@ -52,12 +52,14 @@ __global__ void k_S_static(i64 nnzF, double yobj, const double *__restrict__ cfu
 // MODE 2: write only the constraint part into dyn_out[d]   (S_dyn of the hot loop)
 template <int MODE>
 __global__ void k_S_dynamic(i64 nd, double yobj, const int *__restrict__ dyn_slot, const int *__restrict__ dyn_ptr,
-                            const int *__restrict__ dyn_gid, const double *__restrict__ dyn_val,
+                            const int *__restrict__ dyn_nsd_end, const int *__restrict__ dyn_gid, const double *__restrict__ dyn_val,
                             const int *__restrict__ pos_a, const int *__restrict__ pos_b, const double *__restrict__ st,
                             const double *__restrict__ y, double *__restrict__ out) {
     for (i64 d = blockIdx.x * (i64)blockDim.x + threadIdx.x; d < nd; d += (i64)gridDim.x * blockDim.x) {
         double s = 0.0;
-        for (int j = dyn_ptr[d]; j < dyn_ptr[d + 1]; j++) s += dyn_val[j] * y[dyn_gid[j]];
+        // MODE 2 leaves out the single-diagonal-entry constraints (listed last): the hot loop applies them per row
+        const int jend = (MODE == 2) ? dyn_nsd_end[d] : dyn_ptr[d + 1];
+        for (int j = dyn_ptr[d]; j < jend; j++) s += dyn_val[j] * y[dyn_gid[j]];
         if (MODE == 2) { out[d] = s; continue; }
         const int t = dyn_slot[d];
         s += yobj * st[t];
@@ -86,6 +88,7 @@ struct Acc<1> {
     __device__ __forceinline__ void shfl_add(int o) { v += __shfl_xor_sync(0xffffffffu, v, o); }
     __device__ __forceinline__ void scale_add(double sc, double a, const double *p) { v = sc * (v + a * __ldg(p)); }
     __device__ __forceinline__ void accumulate_onto(double sc, const double *p) { v = p[0] + sc * v; }
+    __device__ __forceinline__ void fma_reg(double s, const Acc &o) { v += s * o.v; }
     __device__ __forceinline__ void scale(double sc) { v *= sc; }
     __device__ __forceinline__ double dot_ld(const double *p) const { return v * __ldg(p); }
     __device__ __forceinline__ double norm2() const { return v * v; }
@@ -112,6 +115,7 @@ struct Acc<2> {
         const double2 x = *reinterpret_cast<const double2 *>(p);
         v.x = x.x + sc * v.x; v.y = x.y + sc * v.y;
     }
+    __device__ __forceinline__ void fma_reg(double s, const Acc &o) { v.x += s * o.v.x; v.y += s * o.v.y; }
     __device__ __forceinline__ double dot_ld(const double *p) const {
         const double2 x = ldg2(p);
         return v.x * x.x + v.y * x.y;
@@ -391,7 +395,9 @@ __global__ void k_sum_slots(int ncls, const double *__restrict__ sums, int strid
 // with S = y_obj*C + S_dyn and C*R kept by recurrence); ||G||_F^2 fused.  Pure streaming: 3N bytes.
 template <int VEC>
 __global__ void __launch_bounds__(TPB) k_grad_diag(i64 lo, i64 hi, int r, double yobj, const double *__restrict__ CR,
-                                                   const double *__restrict__ R, const int *__restrict__ dyn_diag,
+                                                   const double *__restrict__ R, const int *__restrict__ rowc_ptr,
+                                                   const double *__restrict__ rowc_val, const double *__restrict__ y,
+                                                   const int *__restrict__ dyn_diag,
                                                    const double *__restrict__ dynS, double *__restrict__ G, double *partials,
                                                    unsigned *ticket, double *out) {
     const int nv = r / VEC;
@@ -400,8 +406,12 @@ __global__ void __launch_bounds__(TPB) k_grad_diag(i64 lo, i64 hi, int r, double
     for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
         const i64 i = lo + e / nv;
         const int c = (int)(e - (i - lo) * nv);
-        const int dd = dyn_diag[i];
-        const double d = dd >= 0 ? dynS[dd] : 0.0;
+        double d = 0.0;
+        for (int p = rowc_ptr[i]; p < rowc_ptr[i + 1]; p++) d += rowc_val[p] * y[p];  // single-diagonal-entry constraints of row i
+        if (dynS) {
+            const int dd = dyn_diag[i];
+            if (dd >= 0) d += dynS[dd];
+        }
         const size_t off = (size_t)i * r + c * VEC;
         Acc<VEC> g;
         g.zero();
@@ -411,6 +421,66 @@ __global__ void __launch_bounds__(TPB) k_grad_diag(i64 lo, i64 hi, int r, double
         g.store(G + off);
     }
     grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { out[0] = s[0]; });
+}
+
+// The whole tail of an inner iteration for the rows and their per-row (single-diagonal-entry) constraints in ONE
+// streaming pass (src/linesearch.jl:118-124, src/sdplr.jl:219, src/coreop.jl:229-236, 305-317, src/sdplr.jl:224-234):
+//   R_i += a*D_i ;  CR_i += a*CD_i ;
+//   for the constraints p of row i:  raw_p += a*(a*A_DD_p + A_RD_p) ;  y_p = -min(ub_p, lambda_p - sigma*raw_p)
+//   G_i = 2*(y_obj*CR_i + (sum_p val_p*y_p + S_dyn(i,i))*R_i) ;  ||G||^2 and ||max(raw,lb)||^2 fused.
+// 7N + ~9 doubles per constraint instead of the 9N + 3 m-vector passes of step / y / gradient / norm kernels.
+// raw is double-buffered (raw_in -> raw_out): every piece-thread of a row re-derives y_p from raw_in, only piece 0 writes.
+template <int VEC>
+__global__ void __launch_bounds__(TPB) k_step_grad(i64 lo, i64 hi, int r, double a, double sigma, double yobj,
+                                                   const double *__restrict__ D, double *__restrict__ R,
+                                                   const double *__restrict__ CD, double *__restrict__ CR,
+                                                   const int *__restrict__ rowc_ptr, const double *__restrict__ rowc_val,
+                                                   const double *__restrict__ lambda, const double *__restrict__ ub,
+                                                   const double *__restrict__ lb, const double *__restrict__ raw_in,
+                                                   double *__restrict__ raw_out, const double *__restrict__ q1v,
+                                                   const double *__restrict__ q2v, double *__restrict__ y,
+                                                   const int *__restrict__ dyn_diag, const double *__restrict__ dynS,
+                                                   double *__restrict__ G, const double *__restrict__ pn2_rest,
+                                                   double *partials, unsigned *ticket, double *gn2_out, double *pn2_out) {
+    const int nv = r / VEC;
+    const i64 total = (hi - lo) * nv;
+    double acc[2] = {0.0, 0.0};
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 i = lo + e / nv;
+        const int c = (int)(e - (i - lo) * nv);
+        const size_t off = (size_t)i * r + c * VEC;
+        // independent row loads first (in flight while the constraint chain below resolves)
+        Acc<VEC> rr, cr;
+        rr.zero(); cr.zero();
+        rr.fma(1.0, R + off); rr.fma(a, D + off);           // R_i + a*D_i
+        if (CR) { cr.fma(1.0, CR + off); cr.fma(a, CD + off); }
+        double d = 0.0;
+        for (int p = rowc_ptr[i]; p < rowc_ptr[i + 1]; p++) {
+            const double v = raw_in[p] + a * (a * q2v[p] + q1v[p]);
+            const double yp = -fmin(ub[p], lambda[p] - sigma * v);
+            d += rowc_val[p] * yp;
+            if (c == 0) {
+                raw_out[p] = v;
+                y[p] = yp;
+                const double w = fmax(v, lb[p]);
+                acc[1] += w * w;
+            }
+        }
+        if (dynS) {
+            const int dd = dyn_diag[i];
+            if (dd >= 0) d += dynS[dd];
+        }
+        rr.store(R + off);
+        if (CR) cr.store(CR + off);
+        Acc<VEC> g;
+        g.zero();
+        g.fma_reg(d, rr);
+        if (CR) g.fma_reg(yobj, cr);
+        g.scale(2.0);
+        acc[0] += g.norm2();
+        g.store(G + off);
+    }
+    grid_sum_finalize<2>(acc, partials, ticket, [&](double (&s)[2]) { gn2_out[0] = s[0]; pn2_out[0] = s[1] + pn2_rest[0]; });
 }
 
 int pick_group(int nv) {
@@ -513,7 +583,7 @@ int32_t grad_assemble_S(sdplrp_handle *h) {
         h->S_static_scale = yobj;
     }
     if (h->n_dyn > 0) {
-        k_S_dynamic<0><<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, yobj, h->dyn_slot, h->dyn_ptr, h->dyn_gid, h->dyn_val,
+        k_S_dynamic<0><<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, yobj, h->dyn_slot, h->dyn_ptr, h->dyn_nsd_end, h->dyn_gid, h->dyn_val,
                                                                            h->dyn_pos_a, h->dyn_pos_b, h->triuS_static, h->y, h->S);
         KLAUNCH(h);
     }
@@ -528,7 +598,7 @@ int32_t grad_triuS(sdplrp_handle *h, double *out) {
     k_scale_copy<<<grid_for(h->nnzT, TPB, 8 * kNumSM), TPB, 0, st>>>(h->nnzT, yobj, h->triuS_static, out);
     KLAUNCH(h);
     if (h->n_dyn > 0) {
-        k_S_dynamic<1><<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, yobj, h->dyn_slot, h->dyn_ptr, h->dyn_gid, h->dyn_val,
+        k_S_dynamic<1><<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, yobj, h->dyn_slot, h->dyn_ptr, h->dyn_nsd_end, h->dyn_gid, h->dyn_val,
                                                                            h->dyn_pos_a, h->dyn_pos_b, h->triuS_static, h->y, out);
         KLAUNCH(h);
     }
@@ -572,8 +642,9 @@ int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double
 int32_t grad_hot(sdplrp_handle *h) {
     cudaStream_t st = h->stream;
     const int r = h->r;
-    if (h->n_dyn > 0) {
-        k_S_dynamic<2><<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, 0.0, h->dyn_slot, h->dyn_ptr, h->dyn_gid, h->dyn_val,
+    const bool need_dynS = h->n_dyn > 0 && h->n_dyn_nsd > 0;  // false for MaxCut-type problems: nothing but row-list constraints
+    if (need_dynS) {
+        k_S_dynamic<2><<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, 0.0, h->dyn_slot, h->dyn_ptr, h->dyn_nsd_end, h->dyn_gid, h->dyn_val,
                                                                            h->dyn_pos_a, h->dyn_pos_b, h->triuS_static, h->y, h->dynS);
         KLAUNCH(h);
     }
@@ -582,9 +653,58 @@ int32_t grad_hot(sdplrp_handle *h) {
     const i64 total = (h->row_hi - h->row_lo) * nv;
     const double *CR = (h->obj_mat >= 0) ? h->CR : nullptr;
     const int grid = grid_for(total, TPB * 2, kRedBlocks);
-    if (vec2) k_grad_diag<2><<<grid, TPB, 0, st>>>(h->row_lo, h->row_hi, r, h->y_obj, CR, h->R, h->dyn_diag, h->dynS, h->G, h->partials, h->ticket, h->dscal + SC_GNORM2);
-    else k_grad_diag<1><<<grid, TPB, 0, st>>>(h->row_lo, h->row_hi, r, h->y_obj, CR, h->R, h->dyn_diag, h->dynS, h->G, h->partials, h->ticket, h->dscal + SC_GNORM2);
+    if (vec2) k_grad_diag<2><<<grid, TPB, 0, st>>>(h->row_lo, h->row_hi, r, h->y_obj, CR, h->R, h->rowc_ptr, h->rowc_val, h->y, h->dyn_diag, need_dynS ? h->dynS : nullptr, h->G, h->partials, h->ticket, h->dscal + SC_GNORM2);
+    else k_grad_diag<1><<<grid, TPB, 0, st>>>(h->row_lo, h->row_hi, r, h->y_obj, CR, h->R, h->rowc_ptr, h->rowc_val, h->y, h->dyn_diag, need_dynS ? h->dynS : nullptr, h->G, h->partials, h->ticket, h->dscal + SC_GNORM2);
     KLAUNCH(h);
+    bool renorm = false;
+    if (h->n_dynF > 0) {
+        RowArgs a = {};
+        a.ptr = h->dynrow_ptr; a.idx = h->dynrow_col; a.val = h->dynS; a.src = h->dynrow_src;
+        a.X = h->R; a.Y = h->G; a.scale = 2.0;
+        SDP_CHECK((launch_csr<true, 3>(h, a, h->dyn_cls, nullptr)));
+        renorm = true;
+    }
+    if (!h->lr.empty()) {
+        SDP_CHECK(add_lowrank(h, h->R, h->G, 2.0));
+        renorm = true;
+    }
+    if (renorm) SDP_CHECK(lb_norm2(h, h->G, SC_GNORM2));
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+
+// sdplrp_step + sdplrp_g in one go (same results, 1 row pass instead of 3 + 4 m-vector passes):
+//   Rt += alpha*dirt, CR += alpha*CD, residual recurrence, y, G, ||G||^2, ||pvio||^2.
+// Caller guarantees: linesearch_coeffs ran for the current D (A_RD, A_DD, CD valid) and CR is valid (or C is not sparse).
+int32_t grad_step_fused(sdplrp_handle *h, double alpha) {
+    cudaStream_t st = h->stream;
+    const int r = h->r;
+    const bool split = h->obj_mat >= 0;
+    double *raw_in = h->pvio_raw, *raw_out = h->pvio_raw_alt;
+    double *pn2_rest = h->dscal + SC_SUMS + 2;
+    SDP_CHECK(vec_tail_rest(h, alpha, raw_in, raw_out, pn2_rest));  // slots [n_sd, m]: raw, y, obj; its share of ||pvio||^2
+    h->y_obj = 1.0;
+    h->S_current = false;
+    const bool need_dynS = h->n_dyn > 0 && h->n_dyn_nsd > 0;
+    if (need_dynS) {
+        k_S_dynamic<2><<<grid_for(h->n_dyn, TPB, 8 * kNumSM), TPB, 0, st>>>(h->n_dyn, 0.0, h->dyn_slot, h->dyn_ptr, h->dyn_nsd_end, h->dyn_gid, h->dyn_val,
+                                                                           h->dyn_pos_a, h->dyn_pos_b, h->triuS_static, h->y, h->dynS);
+        KLAUNCH(h);
+    }
+    const bool vec2 = (r % 2 == 0);
+    const int nv = vec2 ? r / 2 : r;
+    const i64 total = (h->row_hi - h->row_lo) * nv;
+    const int grid = grid_for(total, TPB * 2, kRedBlocks);
+    const double *CD = split ? h->CD : nullptr;
+    double *CR = split ? h->CR : nullptr;
+#define SG_ARGS h->row_lo, h->row_hi, r, alpha, h->sigma, h->y_obj, h->D, h->R, CD, CR, h->rowc_ptr, h->rowc_val, h->lambda, h->lambda_ub, \
+                h->pvio_lb, raw_in, raw_out, h->A_RD, h->A_DD, h->y, h->dyn_diag, need_dynS ? h->dynS : nullptr, h->G, pn2_rest, h->partials, \
+                h->ticket, h->dscal + SC_GNORM2, h->dscal + SC_PNORM2
+    if (vec2) k_step_grad<2><<<grid, TPB, 0, st>>>(SG_ARGS);
+    else k_step_grad<1><<<grid, TPB, 0, st>>>(SG_ARGS);
+#undef SG_ARGS
+    KLAUNCH(h);
+    std::swap(h->pvio_raw, h->pvio_raw_alt);
     bool renorm = false;
     if (h->n_dynF > 0) {
         RowArgs a = {};

@@ -121,3 +121,26 @@ int32_t perm_slots_download(sdplrp_handle *h, const double *src_dev, double *dst
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return SDPLRP_OK;
 }
+
+// ---- m-vectors: reference constraint order (ABI) <-> internal constraint order (cperm) -------------------
+int32_t perm_cvec_upload(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 len) {
+    if (len <= 0) return SDPLRP_OK;
+    SDP_CHECK(perm_stage(h, len));
+    CUDA_TRY(h, cudaMemcpyAsync(h->stage, src_host, (size_t)len * 8, cudaMemcpyHostToDevice, h->stream));
+    k_perm_slots<<<grid_for(len, TPB, kRedBlocks * 4), TPB, 0, h->stream>>>(len, h->cperm, h->stage, dst_dev, true);  // dst[cperm[g]] = src[g]
+    KLAUNCH(h);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SDPLRP_OK;
+}
+
+int32_t perm_cvec_download(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 len) {
+    if (len <= 0) return SDPLRP_OK;
+    SDP_CHECK(perm_stage(h, len));
+    k_perm_slots<<<grid_for(len, TPB, kRedBlocks * 4), TPB, 0, h->stream>>>(len, h->cperm, src_dev, h->stage, false);  // dst[g] = src[cperm[g]]
+    KLAUNCH(h);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(dst_host, h->stage, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SDPLRP_OK;
+}

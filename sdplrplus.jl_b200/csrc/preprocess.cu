@@ -181,7 +181,8 @@ __global__ void k_dyn_fill(i64 nnzT, const int *__restrict__ slot_ptr, const int
                            const int *__restrict__ dyn_off, const int *__restrict__ triu_rowval,
                            const unsigned long long *__restrict__ keyT, const int *__restrict__ perm,
                            const int *__restrict__ full_ptr,
-                           const int *__restrict__ full_idx, int *__restrict__ dyn_slot, int *__restrict__ dyn_ptr,
+                           const int *__restrict__ full_idx, const unsigned char *__restrict__ sd_flag,
+                           int *__restrict__ dyn_slot, int *__restrict__ dyn_ptr, int *__restrict__ dyn_nsd_end,
                            int *__restrict__ dyn_gid, double *__restrict__ dyn_val, int *__restrict__ pos_a,
                            int *__restrict__ pos_b) {
     for (i64 s = blockIdx.x * (i64)blockDim.x + threadIdx.x; s < nnzT; s += (i64)gridDim.x * blockDim.x) {
@@ -190,13 +191,19 @@ __global__ void k_dyn_fill(i64 nnzT, const int *__restrict__ slot_ptr, const int
         int o = dyn_off[s];
         dyn_slot[d] = (int)s;
         dyn_ptr[d] = o;
-        for (int p = slot_ptr[s]; p < slot_ptr[s + 1]; p++) {
-            int t = sorted_t[p];
-            int a = ent_mat[t];
-            if (a == obj_mat) continue;
-            dyn_gid[o] = mat_gid[a];
-            dyn_val[o] = one[t];
-            o++;
+        // contributors that are NOT single-diagonal-entry constraints first (the hot loop only needs those:
+        // the single-diagonal ones are applied from the per-row lists), then the rest; matrix order inside each part
+        for (int pass = 0; pass < 2; pass++) {
+            for (int p = slot_ptr[s]; p < slot_ptr[s + 1]; p++) {
+                int t = sorted_t[p];
+                int a = ent_mat[t];
+                if (a == obj_mat) continue;
+                if ((sd_flag[a] != 0) != (pass == 1)) continue;
+                dyn_gid[o] = mat_gid[a];
+                dyn_val[o] = one[t];
+                o++;
+            }
+            if (pass == 0) dyn_nsd_end[d] = o;
         }
         int row = triu_rowval[s], col = (int)(keyT[s] >> 32);
         if (perm) { row = perm[row]; col = perm[col]; }  // positions in the INTERNAL full pattern
@@ -304,10 +311,14 @@ __global__ void k_cfull(i64 nnzF, const int *__restrict__ mapped, const int *__r
 }
 // mark the full-pattern slots (both mirrored positions) of every dynamic triu slot
 __global__ void k_dyn_mark(i64 nd, const int *__restrict__ pos_a, const int *__restrict__ pos_b, const int *__restrict__ full_idx,
+                           const int *__restrict__ dyn_ptr, const int *__restrict__ dyn_nsd_end,
                            int *__restrict__ flag, int *__restrict__ src, int *__restrict__ dyn_diag) {
     for (i64 d = blockIdx.x * (i64)blockDim.x + threadIdx.x; d < nd; d += (i64)gridDim.x * blockDim.x) {
         const int a = pos_a[d], b = pos_b[d];
-        if (a >= 0 && a == b) { dyn_diag[full_idx[a]] = (int)d; continue; }  // diagonal slot: row scaling, not a gather
+        if (a >= 0 && a == b) {  // diagonal slot: a row scaling, not a gather (and nothing at all if only row-list constraints touch it)
+            if (dyn_nsd_end[d] > dyn_ptr[d]) dyn_diag[full_idx[a]] = (int)d;
+            continue;
+        }
         if (a >= 0) { flag[a] = 1; src[a] = (int)d; }
         if (b >= 0) { flag[b] = 1; src[b] = (int)d; }
     }
@@ -419,6 +430,30 @@ int32_t build_classes(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, RowClas
     }
     return SDPLRP_OK;
 }
+// ---- internal constraint order: single-diagonal-entry constraints in (internal) row order first, the rest after
+__global__ void k_cperm_sd(i64 n_sd, const int *__restrict__ sorted_a, const int *__restrict__ mat_gid, int *__restrict__ cperm,
+                           int *__restrict__ assigned) {
+    for (i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x; p < n_sd; p += (i64)gridDim.x * blockDim.x) {
+        const int g = mat_gid[sorted_a[p]];
+        cperm[g] = (int)p;
+        assigned[g] = 1;
+    }
+}
+__global__ void k_not(i64 nItems, const int *__restrict__ x, int *__restrict__ y) {
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nItems; k += (i64)gridDim.x * blockDim.x) y[k] = x[k] ? 0 : 1;
+}
+__global__ void k_cperm_rest(i64 m, i64 n_sd, const int *__restrict__ assigned, const int *__restrict__ rank, int *__restrict__ cperm) {
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g <= m; g += (i64)gridDim.x * blockDim.x) {
+        if (g == m) { cperm[g] = (int)m; continue; }  // the objective keeps slot m+1
+        if (!assigned[g]) cperm[g] = (int)(n_sd + rank[g]);
+    }
+}
+__global__ void k_sd_vals(i64 n_sd, const int *__restrict__ sorted_a, const int *__restrict__ matptr, const double *__restrict__ ent_two,
+                          double *__restrict__ val) {
+    for (i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x; p < n_sd; p += (i64)gridDim.x * blockDim.x)
+        val[p] = ent_two[matptr[sorted_a[p]]];
+}
+
 __global__ void k_tile_chunk_counts(i64 nLong, const int *__restrict__ long_rows, const int *__restrict__ ptr, int *__restrict__ cnt) {
     for (i64 l = blockIdx.x * (i64)blockDim.x + threadIdx.x; l < nLong; l += (i64)gridDim.x * blockDim.x) {
         const int i = long_rows[l];
@@ -492,8 +527,9 @@ void pre_free(sdplrp_handle *h) {
     dev_free(&h->triuS_static); dev_free(&h->dyn_slot); dev_free(&h->dyn_ptr); dev_free(&h->dyn_gid);
     dev_free(&h->dyn_val); dev_free(&h->dyn_pos_a); dev_free(&h->dyn_pos_b);
     dev_free(&h->Cfull); dev_free(&h->dynS); dev_free(&h->dynrow_ptr); dev_free(&h->dynrow_col); dev_free(&h->dynrow_src);
-    dev_free(&h->dyn_diag); dev_free(&h->rowc_ptr); dev_free(&h->rowc_gid); dev_free(&h->rowc_val); dev_free(&h->sd_flag);
-    h->n_sd = 0;
+    dev_free(&h->dyn_diag); dev_free(&h->rowc_ptr); dev_free(&h->rowc_val); dev_free(&h->sd_flag);
+    dev_free(&h->cperm); dev_free(&h->dyn_nsd_end);
+    h->n_sd = 0; h->n_dyn_nsd = 0;
     dev_free(&h->full_cls.storage); dev_free(&h->dyn_cls.storage);
     h->full_cls = RowClasses(); h->dyn_cls = RowClasses();
     h->CR_valid = h->CD_valid = false;
@@ -638,6 +674,53 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
         }
     }
 
+    // ---- the constraint passes index factor rows: entry coordinates in internal labels
+    if (h->relabeled && Ec > 0) {
+        k_apply_perm<<<GS, TPB, 0, st>>>(Ec, h->perm, h->ent_row); KLAUNCH(h);
+        k_apply_perm<<<GS, TPB, 0, st>>>(Ec, h->perm, h->ent_col); KLAUNCH(h);
+    }
+
+    // ---- single-diagonal-entry constraints as per-row lists + the internal constraint order --------
+    // Constraints that are one diagonal entry (Diag(X) = 1 ...) are numbered first, in internal row order, so
+    // that constraint p of row i sits at rowc_ptr[i] <= p < rowc_ptr[i+1] and every m-vector (lambda, y,
+    // residuals, A_RD, A_DD) streams together with the factor rows; all other constraints follow in their
+    // original order; the objective keeps slot m.  Invisible at the ABI (perm.cu converts m-vectors).
+    h->n_sd = 0;
+    SDP_CHECK(dev_alloc(h, &h->rowc_ptr, n + 1));
+    SDP_CHECK(dev_alloc(h, &h->sd_flag, nA));
+    SDP_CHECK(dev_alloc(h, &h->cperm, m + 1));
+    CUDA_TRY(h, cudaMemsetAsync(h->rowc_ptr, 0, (size_t)(n + 1) * sizeof(int), st));
+    {
+        int *assigned = tmp.get<int>(h, m + 1, &rc), *unassigned = tmp.get<int>(h, m + 1, &rc), *crank = tmp.get<int>(h, m + 1, &rc);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaMemsetAsync(assigned, 0, (size_t)(m + 1) * sizeof(int), st));
+        if (nA > 0) {
+            unsigned *skey = tmp.get<unsigned>(h, nA, &rc), *skey2 = tmp.get<unsigned>(h, nA, &rc);
+            int *sval = tmp.get<int>(h, nA, &rc), *sval2 = tmp.get<int>(h, nA, &rc);
+            if (rc) return rc;
+            k_sd_keys<<<grid_for(nA, TPB, GS), TPB, 0, st>>>(nA, n, h->obj_mat, h->matptr, h->ent_row, h->ent_col, skey, sval, h->sd_flag);
+            KLAUNCH(h);
+            h->launches += 4;
+            SDP_CHECK(with_cub_temp(h, [&](void *t, size_t &b) {
+                return cub::DeviceRadixSort::SortPairs(t, b, skey, skey2, sval, sval2, (int)nA, 0, bits_for(n + 2), st);
+            }));
+            k_lower_bound_u32<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, nA, skey2, h->rowc_ptr); KLAUNCH(h);
+            int nsd = 0;
+            SDP_CHECK(read_int(h, h->rowc_ptr + n, &nsd));
+            h->n_sd = nsd;
+            SDP_CHECK(dev_alloc(h, &h->rowc_val, nsd));
+            if (nsd > 0) {
+                k_sd_vals<<<grid_for(nsd, TPB, GS), TPB, 0, st>>>(nsd, sval2, h->matptr, h->ent_two, h->rowc_val); KLAUNCH(h);
+                k_cperm_sd<<<grid_for(nsd, TPB, GS), TPB, 0, st>>>(nsd, sval2, h->mat_gid, h->cperm, assigned); KLAUNCH(h);
+            }
+        }
+        k_not<<<grid_for(m + 1, TPB, GS), TPB, 0, st>>>(m + 1, assigned, unassigned); KLAUNCH(h);
+        SDP_CHECK(exclusive_scan(h, unassigned, crank, m + 1));
+        k_cperm_rest<<<grid_for(m + 1, TPB, GS), TPB, 0, st>>>(m, h->n_sd, assigned, crank, h->cperm); KLAUNCH(h);
+        if (nA > 0) { k_apply_perm<<<grid_for(nA, TPB, GS), TPB, 0, st>>>(nA, h->cperm, h->mat_gid); KLAUNCH(h); }  // mat_gid -> internal slots
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+    }
+
     // ---- long matrices -> chunk lists (constraint passes) --------------------
     h->n_long = 0; h->n_chunks = 0;
     if (nA > 0) {
@@ -693,15 +776,16 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
         SDP_CHECK(read_int(h, dindex + nnzT, &nd));
         SDP_CHECK(read_int(h, doff + nnzT, &ndc));
         h->n_dyn = nd;
-        SDP_CHECK(dev_alloc(h, &h->dyn_slot, nd)); SDP_CHECK(dev_alloc(h, &h->dyn_ptr, nd + 1));
+        SDP_CHECK(dev_alloc(h, &h->dyn_slot, nd)); SDP_CHECK(dev_alloc(h, &h->dyn_ptr, nd + 1)); SDP_CHECK(dev_alloc(h, &h->dyn_nsd_end, nd));
         SDP_CHECK(dev_alloc(h, &h->dyn_gid, ndc)); SDP_CHECK(dev_alloc(h, &h->dyn_val, ndc));
         SDP_CHECK(dev_alloc(h, &h->dyn_pos_a, nd)); SDP_CHECK(dev_alloc(h, &h->dyn_pos_b, nd));
         if (nd > 0) {
             k_dyn_fill<<<GS, TPB, 0, st>>>(nnzT, slot_ptr, sorted_t, ent_mat, h->ent_one, h->mat_gid, h->obj_mat, dflag,
-                                           dindex, doff, h->triu_rowval, UT, h->relabeled ? h->perm : nullptr, h->full_ptr, h->full_idx, h->dyn_slot,
-                                           h->dyn_ptr, h->dyn_gid, h->dyn_val, h->dyn_pos_a, h->dyn_pos_b);
+                                           dindex, doff, h->triu_rowval, UT, h->relabeled ? h->perm : nullptr, h->full_ptr, h->full_idx, h->sd_flag,
+                                           h->dyn_slot, h->dyn_ptr, h->dyn_nsd_end, h->dyn_gid, h->dyn_val, h->dyn_pos_a, h->dyn_pos_b);
             KLAUNCH(h);
         }
+        h->n_dyn_nsd = (i64)ndc - h->n_sd;  // contributors that are not single-diagonal-entry constraints (each of those has exactly one)
         CUDA_TRY(h, cudaMemcpyAsync(h->dyn_ptr + nd, &ndc, sizeof(int), cudaMemcpyHostToDevice, st));
         CUDA_TRY(h, cudaStreamSynchronize(st));
     }
@@ -718,7 +802,7 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
         int *fflag = tmp.get<int>(h, nnzF + 1, &rc), *fpos = tmp.get<int>(h, nnzF + 1, &rc), *fsrc = tmp.get<int>(h, nnzF + 1, &rc);
         if (rc) return rc;
         CUDA_TRY(h, cudaMemsetAsync(fflag, 0, (size_t)(nnzF + 1) * sizeof(int), st));
-        if (h->n_dyn > 0) { k_dyn_mark<<<GS, TPB, 0, st>>>(h->n_dyn, h->dyn_pos_a, h->dyn_pos_b, h->full_idx, fflag, fsrc, h->dyn_diag); KLAUNCH(h); }
+        if (h->n_dyn > 0) { k_dyn_mark<<<GS, TPB, 0, st>>>(h->n_dyn, h->dyn_pos_a, h->dyn_pos_b, h->full_idx, h->dyn_ptr, h->dyn_nsd_end, fflag, fsrc, h->dyn_diag); KLAUNCH(h); }
         SDP_CHECK(exclusive_scan(h, fflag, fpos, nnzF + 1));
         int ndf = 0;
         SDP_CHECK(read_int(h, fpos + nnzF, &ndf));
@@ -729,39 +813,6 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
     } else {
         CUDA_TRY(h, cudaMemsetAsync(h->dynrow_ptr, 0, (size_t)(n + 1) * sizeof(int), st));
         SDP_CHECK(dev_alloc(h, &h->dynrow_col, 0)); SDP_CHECK(dev_alloc(h, &h->dynrow_src, 0));
-    }
-
-    // ---- the constraint passes index factor rows: entry coordinates in internal labels
-    if (h->relabeled && Ec > 0) {
-        k_apply_perm<<<GS, TPB, 0, st>>>(Ec, h->perm, h->ent_row); KLAUNCH(h);
-        k_apply_perm<<<GS, TPB, 0, st>>>(Ec, h->perm, h->ent_col); KLAUNCH(h);
-    }
-
-    // ---- single-diagonal-entry constraints as per-row lists (streaming A passes) ----
-    h->n_sd = 0;
-    SDP_CHECK(dev_alloc(h, &h->rowc_ptr, n + 1));
-    SDP_CHECK(dev_alloc(h, &h->sd_flag, nA));
-    CUDA_TRY(h, cudaMemsetAsync(h->rowc_ptr, 0, (size_t)(n + 1) * sizeof(int), st));
-    if (nA > 0) {
-        unsigned *skey = tmp.get<unsigned>(h, nA, &rc), *skey2 = tmp.get<unsigned>(h, nA, &rc);
-        int *sval = tmp.get<int>(h, nA, &rc), *sval2 = tmp.get<int>(h, nA, &rc);
-        if (rc) return rc;
-        k_sd_keys<<<grid_for(nA, TPB, GS), TPB, 0, st>>>(nA, n, h->obj_mat, h->matptr, h->ent_row, h->ent_col, skey, sval, h->sd_flag);
-        KLAUNCH(h);
-        h->launches += 4;
-        SDP_CHECK(with_cub_temp(h, [&](void *t, size_t &b) {
-            return cub::DeviceRadixSort::SortPairs(t, b, skey, skey2, sval, sval2, (int)nA, 0, bits_for(n + 2), st);
-        }));
-        k_lower_bound_u32<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, nA, skey2, h->rowc_ptr); KLAUNCH(h);
-        int nsd = 0;
-        SDP_CHECK(read_int(h, h->rowc_ptr + n, &nsd));
-        h->n_sd = nsd;
-        SDP_CHECK(dev_alloc(h, &h->rowc_gid, nsd)); SDP_CHECK(dev_alloc(h, &h->rowc_val, nsd));
-        if (nsd > 0) {
-            k_sd_fill<<<grid_for(nsd, TPB, GS), TPB, 0, st>>>(nsd, sval2, h->matptr, h->mat_gid, h->ent_two, h->rowc_gid, h->rowc_val);
-            KLAUNCH(h);
-        }
-        CUDA_TRY(h, cudaStreamSynchronize(st));
     }
 
     // ---- row bins of both patterns (sparse x dense kernels) -----------------------

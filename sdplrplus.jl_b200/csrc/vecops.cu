@@ -71,6 +71,27 @@ __global__ void k_commit(i64 m, double a, const double *__restrict__ q1v, const 
     }
 }
 
+// the m-vector part of the fused step/gradient pass (gradient.cu, k_step_grad) for the constraints that are NOT in the
+// per-row lists, slots [c0, m), plus the objective slot m:  residual recurrence into the alternate buffer, y, and this
+// range's share of ||max(raw, lb)||^2 -> *pn2_out (the row pass adds its own share)
+__global__ void __launch_bounds__(TPB) k_tail_rest(i64 c0, i64 m, double a, double sigma, const double *__restrict__ q1v,
+                                                   const double *__restrict__ q2v, const double *__restrict__ raw_in,
+                                                   double *__restrict__ raw_out, const double *__restrict__ lambda,
+                                                   const double *__restrict__ ub, const double *__restrict__ lb,
+                                                   double *__restrict__ y, double *__restrict__ pn2_out,
+                                                   double *partials, unsigned *ticket, double *__restrict__ dscal) {
+    double acc[1] = {0.0};
+    for (i64 i = c0 + blockIdx.x * (i64)blockDim.x + threadIdx.x; i <= m; i += (i64)gridDim.x * blockDim.x) {
+        const double v = raw_in[i] + a * (a * q2v[i] + q1v[i]);
+        raw_out[i] = v;
+        if (i == m) { y[i] = 1.0; dscal[SC_OBJ] = v; continue; }
+        y[i] = -fmin(ub[i], lambda[i] - sigma * v);
+        const double w = fmax(v, lb[i]);
+        acc[0] += w * w;
+    }
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { pn2_out[0] = s[0]; });
+}
+
 // ||max(raw, lb)||_2^2 (src/coreop.jl:340-347, src/sdplr.jl:230-234)
 __global__ void __launch_bounds__(TPB) k_pnorm2(i64 m, const double *__restrict__ raw, const double *__restrict__ lb,
                                                 double *partials, unsigned *ticket, double *__restrict__ dscal) {
@@ -197,5 +218,15 @@ int32_t vec_dual_dot(sdplrp_handle *h, double *out) {
     CUDA_TRY(h, cudaGetLastError());
     SDP_CHECK(fetch_scalars(h, SC_LANCZOS + 9, 1));
     *out = -h->hscal[SC_LANCZOS + 9];
+    return SDPLRP_OK;
+}
+
+// see k_tail_rest; launched BEFORE the fused row pass (S_dyn needs the y of these constraints)
+int32_t vec_tail_rest(sdplrp_handle *h, double alpha, const double *raw_in, double *raw_out, double *pn2_out) {
+    const i64 c0 = h->n_sd;
+    k_tail_rest<<<red_grid(h->m + 1 - c0), TPB, 0, h->stream>>>(c0, h->m, alpha, h->sigma, h->A_RD, h->A_DD, raw_in, raw_out, h->lambda,
+                                                              h->lambda_ub, h->pvio_lb, h->y, pn2_out, h->partials, h->ticket, h->dscal);
+    KLAUNCH(h);
+    CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
 }

@@ -62,13 +62,16 @@ def barrier():
         dist.barrier()
 
 
+ROW_COST = 22.0  # streaming bytes per vertex in units of one gathered nonzero (csrc/comm.cu, comm_partition)
+
+
 def balanced_row_blocks(rowptr, world):
-    """Contiguous row blocks with ~equal (nnz + rows) weight -- the same rule as comm_partition()
+    """Contiguous row blocks with ~equal (nnz + ROW_COST * rows) weight -- the same rule as comm_partition()
     in csrc/comm.cu (kept in Python for tests and for sizing host buffers)."""
     rowptr = np.asarray(rowptr, dtype=np.int64)
     n = rowptr.size - 1
-    w = rowptr[:-1] + np.arange(n, dtype=np.int64)
-    total = float(rowptr[-1] + n)
+    w = rowptr[:-1] + ROW_COST * np.arange(n, dtype=np.float64)
+    total = float(rowptr[-1] + ROW_COST * n)
     starts = [0]
     for p in range(1, world):
         starts.append(int(np.searchsorted(w, total * p / world, side="left")))

@@ -191,6 +191,10 @@ class B200Engine:
     def step(self, alpha):
         return self.h.step(alpha)
 
+    def step_g(self, alpha):
+        """axpy! + g! + the two norms of src/sdplr.jl:219-234 in one ABI call (fused row pass on the device)."""
+        return self.h.step_g(alpha)
+
     def lbfgs_update(self, alpha):
         self.h.lbfgs_update(alpha)
 
@@ -236,6 +240,16 @@ def linesearch_armijo_(engine, alpha_max=1.0):
             k = s + int(ok[0])
             return float(alphas[k]), float(Ls[k])
     return float(alphas[50]), float(Ls[50])
+
+
+def _step_g(engine, alpha):
+    """`axpy!(alpha, dirt, Rt); g!(var, aux)` and the two norms (src/sdplr.jl:219-234): one fused call when the
+    engine offers it, the two seam calls otherwise (oracle engine)."""
+    if hasattr(engine, "step_g"):
+        return engine.step_g(alpha)
+    obj = engine.step(alpha)
+    gn2, pn2 = engine.g()
+    return obj, gn2, pn2
 
 
 @dataclass
@@ -303,8 +317,7 @@ def _sdplr(data, engine, config: BurerMonteiroConfig, stats: SolverStats, r, rng
                 alpha, L_val = linesearch_armijo_(engine, 1.0)
             else:
                 alpha, L_val = linesearch_(engine, 1.0)
-            obj = engine.step(alpha)
-            gn2, pn2 = engine.g()
+            obj, gn2, pn2 = _step_g(engine, alpha)
             grad_norm, primal_vio_norm = math.sqrt(gn2) / gscale, math.sqrt(pn2) / pscale
             if record_trace:
                 stats.trace.append((L_val, obj, grad_norm, primal_vio_norm, alpha))
@@ -445,8 +458,7 @@ def run_inner_iterations(engine, k, use_armijo=False, alpha_max=1.0, update_hist
             alpha, L_val = linesearch_armijo_(engine, alpha_max)
         else:
             alpha, L_val = linesearch_(engine, alpha_max)
-        obj = engine.step(alpha)
-        gn2, pn2 = engine.g()
+        obj, gn2, pn2 = _step_g(engine, alpha)
         if update_history:
             engine.lbfgs_update(alpha)
         out = (L_val, obj, gn2, pn2, alpha)

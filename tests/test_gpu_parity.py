@@ -231,6 +231,33 @@ def test_rank_sweep(sp, oracle_mod, handle, r):
     _relclose(ge.linesearch_coeffs(), oe.linesearch_coeffs(), 1e-11, "bq")
 
 
+@pytest.mark.parametrize("fam", FAMS + ["ineq_0.05"])
+def test_step_g_fused(sp, oracle_mod, handle, fam):
+    """sdplrp_step_g (one fused row pass: step, residual recurrence, y, gradient, both norms) against the
+    oracle's separate step + g, two iterations in a row (the residual vector is double-buffered)."""
+    out = make_case(sp, _fam(sp, fam), 3, 12, 0.4, 3)
+    data, Rt0 = out[0], out[1]
+    ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, 3)
+    ge.fg(); oe.fg()
+    for it in range(2):
+        dg, do = ge.lbfgs_dir(), oe.lbfgs_dir()
+        if math.isnan(do) or do >= 0:
+            ge.use_gradient_direction(); oe.use_gradient_direction()
+        bqg, bqo = ge.linesearch_coeffs(), oe.linesearch_coeffs()
+        _relclose(bqg, bqo, 1e-10, "bq")
+        alpha = 0.37 if it == 0 else 0.11   # any step size exercises the recurrences
+        objg, gn2, pn2 = ge.step_g(alpha)
+        objo = oe.step(alpha); ogn2, opn2 = oe.g()
+        _relclose([objg, math.sqrt(gn2), math.sqrt(pn2)], [objo, math.sqrt(ogn2), math.sqrt(opn2)], 1e-10, "scalars")
+        _relclose(ge.get_R(), oe.get_R(), 1e-10, "R")
+        _relclose(ge.get_G(), oe.get_G(), 1e-10, "G")
+        _relclose(ge.get_pvio_raw(), oe.get_pvio_raw(), 1e-10, "raw")
+        _relclose(ge.get_y(), oe.get_y(), 1e-10, "y")
+        # teacher-force the second round (these families amplify rounding noise within one step): same R, fresh f/g
+        ge.set_R(oe.get_R()); ge.lbfgs_clear(); oe.lbfgs_clear()
+        ge.fg(); oe.fg()
+
+
 # ---------------------------------------------------------------- L-BFGS
 @pytest.mark.parametrize("hist", [0, 1, 2, 4, 7])
 def test_lbfgs_teacher_forced(sp, oracle_mod, handle, hist):

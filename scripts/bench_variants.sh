@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of the SpMM knobs on the C5 workload (device-resident section timers only)
-for cfg in "SDPLRP_RELABEL=-1 SDPLRP_SPMM_KERNEL=1" "SDPLRP_RELABEL=-1 SDPLRP_SPMM_KERNEL=1 SDPLRP_HOT_ROWS=0" "SDPLRP_RELABEL=0 SDPLRP_SPMM_KERNEL=1" "SDPLRP_RELABEL=-1 SDPLRP_SPMM_KERNEL=0" "SDPLRP_RELABEL=-1 SDPLRP_SPMM_KERNEL=1 SDPLRP_HOT_ROWS=1500000"; do
+for cfg in "SDPLRP_SPMM_UNROLL=8 SDPLRP_SPMM_G0=1" "SDPLRP_SPMM_UNROLL=4 SDPLRP_SPMM_G0=1" "SDPLRP_SPMM_UNROLL=8 SDPLRP_SPMM_G0=0" "SDPLRP_SPMM_UNROLL=4 SDPLRP_SPMM_G0=0 SDPLRP_HOT_ROWS=0" "SDPLRP_SPMM_UNROLL=8 SDPLRP_SPMM_G0=1 SDPLRP_HOT_ROWS=0" "SDPLRP_SPMM_UNROLL=8 SDPLRP_SPMM_G0=1 SDPLRP_HOT_ROWS=1200000"; do
   echo "== $cfg"
   env $cfg timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys

@@ -122,6 +122,8 @@ int32_t sdplrp_create(int32_t device, int32_t rank, int32_t world, const void *n
     if (const char *e = getenv("SDPLRP_SPMM_KERNEL")) h->spmm_kernel = atoi(e);
     if (const char *e = getenv("SDPLRP_HOT_ROWS")) h->hot_rows = atoll(e);
     if (const char *e = getenv("SDPLRP_LBFGS_KERNEL")) h->lbfgs_kernel = atoi(e);
+    if (const char *e = getenv("SDPLRP_SPMM_UNROLL")) h->spmm_unroll = atoi(e);
+    if (const char *e = getenv("SDPLRP_SPMM_G0")) h->spmm_g0 = atoi(e);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SDPLRP_ERR_CUDA; }
     bool ok = cudaMalloc((void **)&h->dscal, SC_COUNT * sizeof(double)) == cudaSuccess &&
               cudaMallocHost((void **)&h->hscal, SC_COUNT * sizeof(double)) == cudaSuccess &&
@@ -297,6 +299,8 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
     if (k == "relabel") { h->relabel_mode = value < 0 ? -1 : (value > 0 ? 1 : 0); return SDPLRP_OK; }  // before preprocess
     if (k == "hot_rows") { h->hot_rows = (i64)value; return SDPLRP_OK; }
     if (k == "spmm_kernel") { h->spmm_kernel = (int)value; return SDPLRP_OK; }
+    if (k == "spmm_unroll") { h->spmm_unroll = (int)value; return SDPLRP_OK; }
+    if (k == "spmm_g0") { h->spmm_g0 = (int)value; return SDPLRP_OK; }
     if (k == "fused_tail") { h->fused_tail = value != 0; return SDPLRP_OK; }
     if (k == "lbfgs_kernel") { h->lbfgs_kernel = (int)value; h->gram_pairs_valid = h->gram_g_valid = false; return SDPLRP_OK; }
     return fail(h, SDPLRP_ERR_ARG, "set_option: unknown key " + k);
@@ -459,6 +463,14 @@ int32_t sdplrp_At_right(sdplrp_handle *h, const double *x, double *y, int64_t nc
 }
 
 // ---- fused iteration -----------------------------------------------------------
+// Multi-GPU: R is only advanced on the owned rows inside the inner loop; the rows of other ranks are needed only by
+// passes that gather factor rows across the partition: C*R rebuilds, constraint matrices with off-diagonal entries or
+// several entries (not in the per-row lists), low-rank projections, off-diagonal dynamic gradient parts.
+static bool needs_remote_R_rows(const sdplrp_handle *h) {
+    const i64 general = h->nA - h->n_sd - (h->obj_mat >= 0 ? 1 : 0);
+    return general > 0 || !h->lr.empty() || h->n_dynF > 0;
+}
+
 // CR = C*R over the owned rows (from scratch); sums6[c][0] = <R,CR> per row class
 static int32_t rebuild_CR(sdplrp_handle *h) {
     SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
@@ -492,7 +504,7 @@ static int32_t do_f(sdplrp_handle *h) {
 // g! (src/coreop.jl:305-317): y, then G = 2*(y_obj*CR + S_dyn(y)*R + low rank) and the two norms
 static int32_t do_g(sdplrp_handle *h) {
     if (h->obj_mat >= 0 && !h->CR_valid) SDP_CHECK(rebuild_CR(h));
-    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
+    if (needs_remote_R_rows(h)) SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
     {
         SectionScope sc(h, SDPLRP_SEC_S_ASSEMBLE);
         SDP_CHECK(grad_form_y(h));
@@ -566,7 +578,7 @@ int32_t sdplrp_linesearch_coeffs(sdplrp_handle *h, double bq[5]) {
     REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
     SDP_CHECK(comm_require_full(h, SDPLRP_MAT_D));
-    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
+    if (needs_remote_R_rows(h)) SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
     const bool split = h->obj_mat >= 0;
     if (split && !h->CR_valid) SDP_CHECK(rebuild_CR(h));
     {

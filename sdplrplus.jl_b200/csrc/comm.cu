@@ -102,9 +102,14 @@ void comm_destroy(sdplrp_handle *h) {
 // full pattern's row pointer); identical on every rank.
 int32_t comm_partition(sdplrp_handle *h) {
     const i64 n = h->n;
+    for (int id = 0; id < 8; id++) h->mat_full[id] = true;
+    if (h->dealt && h->world > 1) {  // blocks fixed by the hub-first relabeling (preprocess.cu, k_deal_rows)
+        h->row_lo = h->row_starts[(size_t)h->rank];
+        h->row_hi = h->row_starts[(size_t)h->rank + 1];
+        return SDPLRP_OK;
+    }
     h->row_starts.assign((size_t)h->world + 1, 0);
     h->row_starts[(size_t)h->world] = n;
-    for (int id = 0; id < 8; id++) h->mat_full[id] = true;
     if (h->world <= 1) {
         h->row_lo = 0; h->row_hi = n;
         return SDPLRP_OK;
@@ -213,13 +218,10 @@ int32_t comm_reduce_ptr(sdplrp_handle *h, double *p, int count) {
     return SDPLRP_OK;
 }
 
-// Rt += alpha * dirt on every row this rank keeps (all rows: R is replicated)
+// Rt += alpha * dirt on the rows this rank owns
 int32_t comm_step_R(sdplrp_handle *h, double alpha) {
-    if (h->world <= 1) return lb_axpy(h, alpha, h->D, h->R);
-    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_D));
-    const i64 lo = h->row_lo, hi = h->row_hi;
-    h->row_lo = 0; h->row_hi = h->n;
-    const int32_t rc = lb_axpy(h, alpha, h->D, h->R);
-    h->row_lo = lo; h->row_hi = hi;
-    return rc;
+    // owned rows only: the rows of other ranks are fetched lazily (comm_require_full) by the passes that need them
+    SDP_CHECK(lb_axpy(h, alpha, h->D, h->R));
+    comm_mark_partial(h, SDPLRP_MAT_R);
+    return SDPLRP_OK;
 }

@@ -83,6 +83,7 @@ struct sdplrp_handle {
     // gathered factor are contiguous and the row classes are ranges.  Invisible at the ABI: uploads and
     // downloads of anything indexed by vertex go through perm / iperm.
     bool relabeled = false;
+    bool dealt = false;                                  // multi-GPU: row blocks fixed by the round-robin deal of the relabeling
     int relabel_mode = -1;                               // -1 auto, 0 off, 1 on (sdplrp_set_option "relabel")
     int *perm = nullptr, *iperm = nullptr;               // n: internal label of reference vertex / its inverse
     int *i2r = nullptr, *r2i = nullptr;                  // nnzF: internal full slot <-> reference full slot
@@ -91,6 +92,8 @@ struct sdplrp_handle {
     double *stage = nullptr;                             // n x r staging buffer of the permuting copies
     i64 stage_len = 0;
     i64 hot_rows = -1;                                   // leading (hub) rows of a gathered factor kept in L2; -1 = auto
+    int spmm_unroll = 8;                                 // nonzeros per predicated block of the class-0 register kernel (4 or 8)
+    int spmm_g0 = 1;                                     // class-0 lane groups of exactly r/2 lanes (0: next power of two)
     int spmm_kernel = 0;                                 // 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel
     // per-entry lists in reference order (E_c)
     int *matptr = nullptr;     // nA+1

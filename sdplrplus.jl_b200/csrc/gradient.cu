@@ -31,6 +31,34 @@ namespace {
 
 constexpr int TPB = 256;
 
+// L2 eviction policies: the pattern streams (idx, val) and cold gathers are evict_first, gathers of the hub prefix
+// (internal rows < hot_rows, preprocess.cu) evict_last, so that the hubs stay L2-resident across the pass
+__device__ __forceinline__ unsigned long long pol_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long pol_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int ldg_i32_hint(const int *p, unsigned long long pol) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ldg_f64_hint(const double *p, unsigned long long pol) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double2 ldg_f64x2_hint(const double *p, unsigned long long pol) {
+    double2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+
 // y_i = -min(ub_i, lambda_i - sigma*raw_i), y_{m+1} = 1   (src/coreop.jl:229-236)
 __global__ void k_form_y(i64 m, double sigma, const double *__restrict__ lambda, const double *__restrict__ ub,
                          const double *__restrict__ raw, double *__restrict__ y) {
@@ -85,6 +113,7 @@ struct Acc<1> {
     double v;
     __device__ __forceinline__ void zero() { v = 0.0; }
     __device__ __forceinline__ void fma(double s, const double *p) { v += s * __ldg(p); }
+    __device__ __forceinline__ void fma_hint(double s, const double *p, unsigned long long pol) { v += s * ldg_f64_hint(p, pol); }
     __device__ __forceinline__ void shfl_add(int o) { v += __shfl_xor_sync(0xffffffffu, v, o); }
     __device__ __forceinline__ void scale_add(double sc, double a, const double *p) { v = sc * (v + a * __ldg(p)); }
     __device__ __forceinline__ void accumulate_onto(double sc, const double *p) { v = p[0] + sc * v; }
@@ -100,6 +129,10 @@ struct Acc<2> {
     __device__ __forceinline__ void zero() { v.x = v.y = 0.0; }
     __device__ __forceinline__ void fma(double s, const double *p) {
         const double2 x = ldg2(p);
+        v.x += s * x.x; v.y += s * x.y;
+    }
+    __device__ __forceinline__ void fma_hint(double s, const double *p, unsigned long long pol) {
+        const double2 x = ldg_f64x2_hint(p, pol);
         v.x += s * x.x; v.y += s * x.y;
     }
     __device__ __forceinline__ void shfl_add(int o) {
@@ -136,6 +169,8 @@ struct RowArgs {
     const double *X;
     double *Y;
     int r, G;
+    int G0;            // lanes per row of the class-0 kernel (= pieces per row: no idle lanes, no shuffles there)
+    int hot_rows;      // gathers of columns < hot_rows are L2 evict_last
     double scale, yobj;
     const double *ADD, *Z;
     double *partials;
@@ -145,10 +180,11 @@ struct RowArgs {
 };
 
 template <int VEC, int MAXU, int EPI>
-__device__ __forceinline__ void row_epilogue(const RowArgs &a, i64 i, Acc<VEC> (&acc)[MAXU], int lg, int nv, double &s0, double &s1) {
+__device__ __forceinline__ void row_epilogue(const RowArgs &a, i64 i, Acc<VEC> (&acc)[MAXU], int lg, int nv, double &s0, double &s1,
+                                             int G) {
 #pragma unroll
     for (int u = 0; u < MAXU; u++) {
-        const int c = lg + u * a.G;
+        const int c = lg + u * G;
         if (c < nv) {
             const size_t off = (size_t)i * a.r + c * VEC;
             if (EPI == 0) {
@@ -181,14 +217,22 @@ __device__ __forceinline__ void finish_sums(const RowArgs &a, double s0, double 
 
 #define VAL_AT(k) (IND ? __ldg(a.val + __ldg(a.src + (k))) : __ldg(a.val + (k)))
 
-// class 0: one group of G lanes per row
-template <int VEC, int MAXU, bool IND, int EPI>
+// class 0: one group of G0 lanes per row (G0 = pieces per row when that fits a warp: 6 rows per warp at r = 10);
+// the row's nonzeros are taken NB at a time, fully predicated, so a row of <= NB nonzeros costs one round trip
+// ptr -> idx/val -> gathers with NB independent 128-bit gathers in flight per lane
+template <int VEC, int MAXU, bool IND, int EPI, int NB>
 __global__ void __launch_bounds__(TPB) k_rows_group(RowArgs a) {
     const int nv = a.r / VEC;
-    const int lg = threadIdx.x & (a.G - 1);
-    const i64 group = ((i64)blockIdx.x * TPB + threadIdx.x) / a.G;
-    const i64 n_groups = (i64)gridDim.x * TPB / a.G;
+    const int G = a.G0;
+    const int gpb = TPB / G;                       // groups per CTA (lanes beyond gpb*G idle)
+    const int gib = threadIdx.x / G;
+    const int lg = threadIdx.x - gib * G;
+    const bool lane_ok = gib < gpb;
+    const i64 group = (i64)blockIdx.x * gpb + gib;
+    const i64 n_groups = (i64)gridDim.x * gpb;
+    const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
     double s0 = 0.0, s1 = 0.0;
+    if (lane_ok)
     for (i64 q = group; q < a.n_rows; q += n_groups) {
         const i64 i = a.rows ? a.rows[q] : q;
         if (i < a.own_lo || i >= a.own_hi) continue;
@@ -196,31 +240,26 @@ __global__ void __launch_bounds__(TPB) k_rows_group(RowArgs a) {
         Acc<VEC> acc[MAXU];
 #pragma unroll
         for (int u = 0; u < MAXU; u++) acc[u].zero();
-        int k = beg;
-        for (; k + 4 <= end; k += 4) {  // 4 independent gathers in flight per lane
-            const int c0 = __ldg(a.idx + k), c1 = __ldg(a.idx + k + 1), c2 = __ldg(a.idx + k + 2), c3 = __ldg(a.idx + k + 3);
-            const double v0 = VAL_AT(k), v1 = VAL_AT(k + 1), v2 = VAL_AT(k + 2), v3 = VAL_AT(k + 3);
+        for (int k0 = beg; k0 < end; k0 += NB) {
+            int cc[NB];
+            double vv[NB];
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                const bool ok = k0 + j < end;
+                cc[j] = ok ? ldg_i32_hint(a.idx + k0 + j, p_str) : 0;
+                vv[j] = ok ? (IND ? __ldg(a.val + ldg_i32_hint(a.src + k0 + j, p_str)) : ldg_f64_hint(a.val + k0 + j, p_str)) : 0.0;
+            }
 #pragma unroll
             for (int u = 0; u < MAXU; u++) {
-                const int c = lg + u * a.G;
+                const int c = lg + u * G;
                 if (c < nv) {
-                    acc[u].fma(v0, a.X + (size_t)c0 * a.r + c * VEC);
-                    acc[u].fma(v1, a.X + (size_t)c1 * a.r + c * VEC);
-                    acc[u].fma(v2, a.X + (size_t)c2 * a.r + c * VEC);
-                    acc[u].fma(v3, a.X + (size_t)c3 * a.r + c * VEC);
+#pragma unroll
+                    for (int j = 0; j < NB; j++)
+                        if (k0 + j < end) acc[u].fma_hint(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
                 }
             }
         }
-        for (; k < end; k++) {
-            const int c0 = __ldg(a.idx + k);
-            const double v0 = VAL_AT(k);
-#pragma unroll
-            for (int u = 0; u < MAXU; u++) {
-                const int c = lg + u * a.G;
-                if (c < nv) acc[u].fma(v0, a.X + (size_t)c0 * a.r + c * VEC);
-            }
-        }
-        row_epilogue<VEC, MAXU, EPI>(a, i, acc, lg, nv, s0, s1);
+        row_epilogue<VEC, MAXU, EPI>(a, i, acc, lg, nv, s0, s1, G);
     }
     finish_sums<EPI>(a, s0, s1);
 }
@@ -233,6 +272,7 @@ __global__ void __launch_bounds__(TPB) k_rows_warp(RowArgs a) {
     const int lg = lane & (a.G - 1), grp = lane / a.G, ng = 32 / a.G;
     const i64 warp = (i64)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
     const i64 n_warps = (i64)gridDim.x * (TPB / 32);
+    const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
     double s0 = 0.0, s1 = 0.0;
     for (i64 q = warp; q < a.n_rows; q += n_warps) {  // warp-uniform
         const i64 i = a.rows ? a.rows[q] : q;
@@ -247,8 +287,8 @@ __global__ void __launch_bounds__(TPB) k_rows_warp(RowArgs a) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const bool ok = k0 + j < end;
-                cc[j] = ok ? __ldg(a.idx + k0 + j) : 0;
-                vv[j] = ok ? VAL_AT(k0 + j) : 0.0;
+                cc[j] = ok ? ldg_i32_hint(a.idx + k0 + j, p_str) : 0;
+                vv[j] = ok ? (IND ? __ldg(a.val + ldg_i32_hint(a.src + k0 + j, p_str)) : ldg_f64_hint(a.val + k0 + j, p_str)) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < MAXU; u++) {
@@ -256,7 +296,7 @@ __global__ void __launch_bounds__(TPB) k_rows_warp(RowArgs a) {
                 if (c < nv) {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (k0 + j < end) acc[u].fma(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC);
+                        if (k0 + j < end) acc[u].fma_hint(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
                 }
             }
         }
@@ -264,7 +304,7 @@ __global__ void __launch_bounds__(TPB) k_rows_warp(RowArgs a) {
 #pragma unroll
         for (int u = 0; u < MAXU; u++)
             for (int o = a.G; o < 32; o <<= 1) acc[u].shfl_add(o);
-        if (grp == 0) row_epilogue<VEC, MAXU, EPI>(a, i, acc, lg, nv, s0, s1);
+        if (grp == 0) row_epilogue<VEC, MAXU, EPI>(a, i, acc, lg, nv, s0, s1, a.G);
     }
     finish_sums<EPI>(a, s0, s1);
 }
@@ -275,6 +315,7 @@ __global__ void __launch_bounds__(TPB) k_rows_cta(RowArgs a) {
     extern __shared__ double sm[];  // (TPB/G) * r
     const int nv = a.r / VEC;
     const int lg = threadIdx.x & (a.G - 1), grp = threadIdx.x / a.G, ng = TPB / a.G;
+    const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
     double s0 = 0.0, s1 = 0.0;
     for (i64 q = blockIdx.x; q < a.n_rows; q += gridDim.x) {
         const i64 i = a.rows ? a.rows[q] : q;
@@ -289,8 +330,8 @@ __global__ void __launch_bounds__(TPB) k_rows_cta(RowArgs a) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const bool ok = k0 + j < end;
-                cc[j] = ok ? __ldg(a.idx + k0 + j) : 0;
-                vv[j] = ok ? VAL_AT(k0 + j) : 0.0;
+                cc[j] = ok ? ldg_i32_hint(a.idx + k0 + j, p_str) : 0;
+                vv[j] = ok ? (IND ? __ldg(a.val + ldg_i32_hint(a.src + k0 + j, p_str)) : ldg_f64_hint(a.val + k0 + j, p_str)) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < MAXU; u++) {
@@ -298,7 +339,7 @@ __global__ void __launch_bounds__(TPB) k_rows_cta(RowArgs a) {
                 if (c < nv) {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (k0 + j < end) acc[u].fma(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC);
+                        if (k0 + j < end) acc[u].fma_hint(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
                 }
             }
         }
@@ -500,6 +541,7 @@ template <int VEC, int MAXU, bool IND, int EPI>
 int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, double *sums /* 3 x 2 or null */) {
     cudaStream_t st = h->stream;
     const int gpb = TPB / a.G;
+    const int gpb0 = TPB / a.G0;
     for (int c = 0; c < 3; c++) {
         if (sums) a.out = sums + 2 * c;
         a.rows = cls.list[c];
@@ -509,7 +551,8 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, doubl
             continue;
         }
         if (c == 0) {
-            k_rows_group<VEC, MAXU, IND, EPI><<<grid_for(a.n_rows, gpb, 16 * kNumSM), TPB, 0, st>>>(a);
+            if (h->spmm_unroll >= 8) k_rows_group<VEC, MAXU, IND, EPI, 8><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
+            else k_rows_group<VEC, MAXU, IND, EPI, 4><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
         } else if (c == 1) {
             k_rows_warp<VEC, MAXU, IND, EPI><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
         } else {
@@ -533,6 +576,8 @@ int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, double *s
     a.ticket = h->ticket;
     a.own_lo = h->row_lo;
     a.own_hi = h->row_hi;
+    a.G0 = (nv <= 32 && h->spmm_g0) ? nv : a.G;   // class 0: exactly one lane per piece
+    a.hot_rows = (int)tile_hot_rows(h);
     const int units = (nv + a.G - 1) / a.G;
     if (units > 4) return fail(h, SDPLRP_ERR_ARG, "rank too large for the sparse kernels (r <= 256 even / 128 odd)");
     if (vec2) {

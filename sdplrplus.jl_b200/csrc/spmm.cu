@@ -499,6 +499,7 @@ bool tile_supported(const sdplrp_handle *h) {
 i64 tile_hot_rows(const sdplrp_handle *h) {
     if (h->hot_rows >= 0) return std::min<i64>(h->hot_rows, h->n);
     if (!h->relabeled) return 0;
+    if (h->dealt) return h->n;  // multi-GPU deal: hubs are spread over the rank blocks; one policy for every gather, streams evict_first
     // default: ~48 MB of leading factor rows (well inside the 126 MB L2 next to the streams)
     return std::min<i64>(h->n, (i64)(48.0 * 1024 * 1024) / (8 * (i64)std::max(1, h->r)));
 }

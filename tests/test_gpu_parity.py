@@ -461,3 +461,104 @@ def test_full_solve_matches_oracle(sp, oracle_mod, handle, which):
             assert abs(rg["max_dual_value"] - ro["max_dual_value"]) <= tol * max(1.0, abs(ro["max_dual_value"]))
     if math.isfinite(objtol):
         assert rg["min_duality_gap"] <= objtol
+
+
+# ---------------------------------------------------------------- BASELINE.json configs at their own sizes
+def _baseline_config(sp, cfg):
+    """C1-C4 of SURVEY.md section 8 (seeds 1-4), r0 = 10."""
+    import scipy.sparse as sps
+    P = sp.problems
+    if cfg == "C1":    # MaxCut, G1 shape
+        return P.maxcut(P.gnm_graph(800, 19176, 1))
+    if cfg == "C2":    # Lovasz theta, ER n=2000 p=0.01: one sparse A_i per edge
+        return P.lovasz_theta(P.erdos_renyi(2000, 0.01, 2))
+    if cfg == "C3":    # minimum bisection, n=20000, mean degree 10: rank-one 11' constraint
+        return P.minimum_bisection(P.gnm_graph(20000, 100000, 3))
+    A = sps.random(5000, 5000, density=0.02, random_state=4, data_rvs=np.random.default_rng(4).standard_normal, format="csc")
+    return P.cutnorm(A)   # C4: cut-norm, 5000 x 5000, 2 % dense, N(0,1)
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C3", "C4"])
+def test_baseline_configs(sp, oracle_mod, handle, cfg):
+    """Each BASELINE config at its real size: maps bit-exact, f/g at 1e-10, then inner iterations against the oracle
+    (1e-10 throughout for the MaxCut-type configs, first steps only for the rank-one families)."""
+    C, As, bs = _baseline_config(sp, cfg)
+    data = sp.SDPData(C, As, bs)
+    r = 10
+    Rt0 = 2 * np.random.default_rng(7).random((data.n, r)) - 1
+    ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, r)
+    assert handle.pattern_sizes() == oe.o.pattern_sizes()
+    mg, mo = handle.pattern_export(), oe.o.pattern_export()
+    for k in MAP_KEYS:
+        np.testing.assert_array_equal(mg[k], mo[k], err_msg=k)
+    _relclose(ge.fg(), oe.fg(), 1e-10, "fg")
+    _relclose(ge.get_pvio_raw(), oe.get_pvio_raw(), 1e-10, "raw")
+    _relclose(ge.get_G(), oe.get_G(), 1e-10, "G")
+    strict = cfg in ("C1", "C4")
+    for it in range(6):
+        # rank-one families (C2 objective, C3 constraint): the quartic's coefficients are ~1e6 x the AL value, so the
+        # value at the chosen root only agrees to ~1e-8 even when every coefficient agrees to 1e-10 of its scale
+        tol = 1e-10 if strict else (1e-8 if it < 2 else 1e-5)
+        dg, do = ge.lbfgs_dir(), oe.lbfgs_dir()
+        if math.isnan(do) or do >= 0:
+            ge.use_gradient_direction(); oe.use_gradient_direction()
+        else:
+            assert abs(dg - do) <= 10 * tol * max(1.0, abs(do)), f"descent it={it}"
+        bqg, bqo = ge.linesearch_coeffs(), oe.linesearch_coeffs()
+        if it == 0:
+            _relclose(bqg, bqo, 1e-10, "quartic coefficients")
+        ag, Lg = sp.pick_alpha(bqg, 1.0); ao, Lo = sp.pick_alpha(bqo, 1.0)
+        objg, gn2, pn2 = ge.step_g(ag)
+        objo = oe.step(ao); ogn2, opn2 = oe.g()
+        assert abs(objg - objo) <= tol * max(1.0, abs(objo)), f"obj it={it}"
+        assert abs(Lg - Lo) <= tol * max(1.0, abs(Lo)), f"L it={it}"
+        assert abs(math.sqrt(pn2) - math.sqrt(opn2)) <= tol * max(1.0, math.sqrt(opn2)), f"pnorm it={it}"
+        assert abs(math.sqrt(gn2) - math.sqrt(ogn2)) <= 100 * tol * max(1.0, math.sqrt(ogn2)), f"gnorm it={it}"
+        ge.lbfgs_update(ag); oe.lbfgs_update(ao)
+
+
+def test_c5_full_size_properties(sp, gpu_handle_factory):
+    """BASELINE config C5 at its full size (10M-vertex power-law MaxCut, rank 10): size-independent properties.
+      1. the incrementally advanced residual vector / objective / C*R recurrence equal a from-scratch f! (1e-10)
+      2. the internal hub-first relabeling is invisible: same trajectory with relabeling off (1e-9)
+      3. the coefficient-space L-BFGS equals the literal vector two-loop (1e-9 on the trajectory)"""
+    import torch
+    n, edges, r = 10_000_000, 80_000_000, 10
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~60 GB of device memory")
+    asm, b, normC, E = sp.problems.powerlaw_maxcut_assembled(n, edges, 42)
+    torch.cuda.synchronize(); torch.cuda.empty_cache()
+
+    class D:  # what B200Engine needs from SDPData when the triplets are pre-assembled
+        pass
+    data = D(); data.n, data.m, data.b = n, n, b
+    data.constraint_types = np.zeros(n, dtype=bool); data.has_inequalities = False
+    Rt0 = 2.0 * np.random.default_rng(0).random((n, r)) - 1.0
+    lam0 = np.zeros(n)
+    traces = {}
+    for name, opts in (("default", {}), ("norelabel", {"relabel": 0}), ("literal_lbfgs", {"lbfgs_kernel": 0, "fused_tail": 0})):
+        h = gpu_handle_factory("default")
+        for k, v in opts.items():
+            h.set_option(k, v)
+        eng = sp.B200Engine(data, handle=h, asm=asm)
+        eng.init_vars(r, Rt0, lam0, 2.0, 4)
+        eng.fg()
+        tr = []
+        for _ in range(5):
+            tr.append(sp.solver.run_inner_iterations(eng, 1))
+        traces[name] = np.array(tr)
+        if name == "default":
+            raw_inc = eng.get_pvio_raw()
+            L, obj = eng.f()                       # from scratch: A(RR'), C*R rebuilt
+            raw_new = eng.get_pvio_raw()
+            scale = max(1.0, float(np.abs(raw_new).max()))
+            assert float(np.abs(raw_inc - raw_new).max()) <= 1e-10 * scale
+            assert abs(obj - tr[-1][1]) <= 1e-10 * max(1.0, abs(obj))
+        h.close()
+        del eng
+        torch.cuda.empty_cache()
+    for name in ("norelabel", "literal_lbfgs"):
+        ref, got = traces["default"], traces[name]
+        rel = np.abs(ref - got) / np.maximum(1.0, np.abs(ref))
+        assert rel.max() <= 1e-9, (name, rel.max())

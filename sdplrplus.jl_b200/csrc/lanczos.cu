@@ -15,32 +15,60 @@ namespace {
 constexpr int TPB = 256;
 constexpr int LZ_L = 8;  // lanes per row in the SpMV
 
-// w = S*v ; optionally alpha_i = <v, w>
-template <bool WITH_ALPHA>
-__global__ void __launch_bounds__(TPB) k_lz_spmv(i64 n, const int *__restrict__ ptr, const int *__restrict__ idx,
-                                                 const double *__restrict__ S, const double *__restrict__ v,
-                                                 double *__restrict__ w, const double *__restrict__ stop, double *partials,
-                                                 unsigned *ticket, double *alpha_out) {
+// w = S*v over one row class with LANES lanes per row (rows are binned by length, RowClasses of the full pattern:
+// <= 32 nonzeros -> 4 lanes, <= 2048 -> one warp, longer -> 8 warps); optionally the class's share of alpha_i = <v, w>.
+// v (n doubles) is L2-resident; the pattern (12 B per nonzero) streams once per step.
+template <int LANES, bool WITH_ALPHA>
+__global__ void __launch_bounds__(TPB) k_lz_spmv(const int *__restrict__ rows, i64 n_rows, const int *__restrict__ ptr,
+                                                 const int *__restrict__ idx, const double *__restrict__ S,
+                                                 const double *__restrict__ v, double *__restrict__ w,
+                                                 const double *__restrict__ stop, double *partials, unsigned *ticket,
+                                                 double *alpha_part) {
     if (stop[0] != 0.0) return;
-    const int lg = threadIdx.x & (LZ_L - 1);
-    const i64 warp_global = (i64)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
-    const i64 n_warps = (i64)gridDim.x * (TPB / 32);
-    const int g_in_warp = (threadIdx.x & 31) / LZ_L;
-    constexpr int gpw = 32 / LZ_L;
+    constexpr int GPB = TPB / LANES;   // row groups per CTA
+    const int lg = threadIdx.x % LANES, gib = threadIdx.x / LANES;
+    __shared__ double red[TPB / 32];
     double acc[1] = {0.0};
-    for (i64 base = warp_global * gpw; base < n; base += n_warps * gpw) {
-        const i64 i = base + g_in_warp;
+    for (i64 base = (i64)blockIdx.x * GPB; base < n_rows; base += (i64)gridDim.x * GPB) {  // CTA-uniform trip count
+        const i64 q = base + gib;
+        const bool live = q < n_rows;
+        const i64 i = live ? (rows ? rows[q] : q) : 0;
         double t = 0.0;
-        if (i < n)
-            for (int k = ptr[i] + lg; k < ptr[i + 1]; k += LZ_L) t += __ldg(S + k) * __ldg(v + __ldg(idx + k));
+        if (live) {
+            const int beg = ptr[i], end = ptr[i + 1];
+            int k = beg + lg;
+            for (; k + 3 * LANES < end; k += 4 * LANES) {  // four independent index -> value chains per lane
+                const int c0 = __ldg(idx + k), c1 = __ldg(idx + k + LANES), c2 = __ldg(idx + k + 2 * LANES), c3 = __ldg(idx + k + 3 * LANES);
+                const double s0 = __ldg(S + k), s1 = __ldg(S + k + LANES), s2 = __ldg(S + k + 2 * LANES), s3 = __ldg(S + k + 3 * LANES);
+                t += s0 * __ldg(v + c0) + s1 * __ldg(v + c1) + s2 * __ldg(v + c2) + s3 * __ldg(v + c3);
+            }
+            for (; k < end; k += LANES) t += __ldg(S + k) * __ldg(v + __ldg(idx + k));
+        }
+        if (LANES <= 32) {
 #pragma unroll
-        for (int o = LZ_L >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (i < n && lg == 0) {
+            for (int o = LANES >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        } else {  // one CTA-wide group per row: combine the warps in a fixed order
+            t = warp_sum(t);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+            __syncthreads();
+            t = 0.0;
+            if (threadIdx.x == 0)
+                for (int q2 = 0; q2 < TPB / 32; q2++) t += red[q2];
+        }
+        if (live && lg == 0) {
             w[i] = t;
             if (WITH_ALPHA) acc[0] += t * v[i];
         }
     }
-    if (WITH_ALPHA) grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { alpha_out[0] = s[0]; });
+    if (WITH_ALPHA) grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { alpha_part[0] = s[0]; });
+}
+
+__global__ void k_lz_alpha_sum(const double *__restrict__ parts, int nparts, const double *__restrict__ stop, double *alpha_out) {
+    if (stop[0] != 0.0) return;
+    double a = 0.0;
+    for (int c = 0; c < nparts; c++) a += parts[c];
+    alpha_out[0] = a;
 }
 
 __global__ void k_lz_zero(i64 n, double *__restrict__ w, const double *__restrict__ stop) {
@@ -212,12 +240,25 @@ int32_t lz_run(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, in
     k_lz_norm2<<<gs, TPB, 0, st>>>(n, v, h->partials, h->ticket, tmp); KLAUNCH(h);
     k_lz_div<<<gs, TPB, 0, st>>>(n, tmp, v); KLAUNCH(h);
     const bool has_lr = !h->lr.empty();
-    const int gspmv = grid_for(n, TPB / LZ_L, 16 * kNumSM);
     for (i64 i = 0; i < q; i++) {
         if (reorth) CUDA_TRY(h, cudaMemcpyAsync(h->lz_basis + (size_t)i * n, v, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
         if (h->nA > 0) {
-            if (has_lr) k_lz_spmv<false><<<gspmv, TPB, 0, st>>>(n, h->full_ptr, h->full_idx, h->S, v, w, stop, h->partials, h->ticket, ab + i);
-            else k_lz_spmv<true><<<gspmv, TPB, 0, st>>>(n, h->full_ptr, h->full_idx, h->S, v, w, stop, h->partials, h->ticket, ab + i);
+            // three row classes of the full pattern (class lists are null when every row is short: identity)
+            const RowClasses &cls = h->full_cls;
+            double *parts = h->dscal + SC_LANCZOS + 2;
+            CUDA_TRY(h, cudaMemsetAsync(parts, 0, 3 * sizeof(double), st));
+            for (int c = 0; c < 3; c++) {
+                const i64 nr = cls.cnt[c];
+                if (nr <= 0) continue;
+                const int *rows = cls.list[c];
+#define LZ_SPMV(L, A) k_lz_spmv<L, A><<<grid_for(nr, TPB / L, 16 * kNumSM), TPB, 0, st>>>(rows, nr, h->full_ptr, h->full_idx, h->S, v, w, stop, h->partials, h->ticket, parts + c)
+                if (c == 0) { if (has_lr) LZ_SPMV(4, false); else LZ_SPMV(4, true); }
+                else if (c == 1) { if (has_lr) LZ_SPMV(32, false); else LZ_SPMV(32, true); }
+                else { if (has_lr) LZ_SPMV(256, false); else LZ_SPMV(256, true); }
+#undef LZ_SPMV
+                KLAUNCH(h);
+            }
+            if (!has_lr) k_lz_alpha_sum<<<1, 1, 0, st>>>(parts, 3, stop, ab + i);
         } else {
             k_lz_zero<<<gs, TPB, 0, st>>>(n, w, stop);
         }

@@ -123,46 +123,51 @@ __global__ void __launch_bounds__(TPB) k_A_short(int nA, const int *__restrict__
     }
 }
 
-// single-diagonal-entry constraints (Diag(X) = 1 ...): a streaming pass over the factor rows.  A group of G
-// lanes owns row i, forms <U_i,U_i> / <U_i,V_i> / <V_i,V_i> once and serves every constraint listed for the row.
+// single-diagonal-entry constraints (Diag(X) = 1 ...): a streaming pass over the factor rows.  Flat mapping
+// (thread = one piece of one row, consecutive threads = consecutive addresses), a CTA takes tiles of TPB/nv whole
+// rows, the per-row dots <U_i,U_i> / <U_i,V_i> / <V_i,V_i> are combined through shared memory in a fixed order and
+// serve every constraint listed for the row (constraint k of row i is internal slot k: coalesced stores).
 template <int MODE, int VEC>
 __global__ void __launch_bounds__(TPB) k_A_rowc(long long lo, long long hi, const int *__restrict__ rowc_ptr,
                                                 const double *__restrict__ rowc_val,
                                                 const double *__restrict__ U, const double *__restrict__ V, int r, int G,
                                                 double *__restrict__ out1, double *__restrict__ out2) {
     typedef Ld<VEC> L;
+    __shared__ double sh1[TPB], sh2[TPB];
     const int nv = r / VEC;
-    const int lg = threadIdx.x & (G - 1);
-    const int gpw = 32 / G;  // groups per warp
-    const long long warp_global = (long long)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
-    const long long n_warps = (long long)gridDim.x * (TPB / 32);
-    const int g_in_warp = (threadIdx.x & 31) / G;
-    for (long long base = lo + warp_global * gpw; base < hi; base += n_warps * gpw) {  // warp-uniform trip count
-        const long long i = base + g_in_warp;
-        const bool live = i < hi;
-        int beg = 0, end = 0;
-        if (live) { beg = rowc_ptr[i]; end = rowc_ptr[i + 1]; }
+    const int rpt = TPB / nv;                      // whole rows per tile
+    const int rl = threadIdx.x / nv, c = threadIdx.x - rl * nv;
+    const long long n_rows = hi - lo;
+    for (long long t0 = (long long)blockIdx.x * rpt; t0 < n_rows; t0 += (long long)gridDim.x * rpt) {  // CTA-uniform
+        const long long i = lo + t0 + rl;
+        const bool live = rl < rpt && i < hi;
         double d1 = 0.0, d2 = 0.0;
-        if (live && end > beg) {
-            const double *u = U + (size_t)i * r, *v = (MODE == 0) ? nullptr : V + (size_t)i * r;
-            for (int c = lg; c < nv; c += G) {
-                typename L::T a = L::ld(u + c * VEC);
-                if (MODE == 0) {
-                    d1 += L::dot(a, a);
-                } else {
-                    typename L::T b = L::ld(v + c * VEC);
-                    d1 += L::dot(a, b);
-                    if (MODE == 2) d2 += L::dot(b, b);
+        if (live) {
+            typename L::T a = L::ld(U + (size_t)i * r + c * VEC);
+            if (MODE == 0) {
+                d1 = L::dot(a, a);
+            } else {
+                typename L::T b = L::ld(V + (size_t)i * r + c * VEC);
+                d1 = L::dot(a, b);
+                if (MODE == 2) d2 = L::dot(b, b);
+            }
+        }
+        sh1[threadIdx.x] = d1;
+        if (MODE == 2) sh2[threadIdx.x] = d2;
+        __syncthreads();
+        if (live && c == 0) {
+            const int beg = rowc_ptr[i], end = rowc_ptr[i + 1];
+            if (end > beg) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int k = 0; k < nv; k++) { s1 += sh1[threadIdx.x + k]; if (MODE == 2) s2 += sh2[threadIdx.x + k]; }
+                for (int k = beg; k < end; k++) {
+                    const double val = rowc_val[k];
+                    out1[k] = (MODE == 2 ? 2.0 : 1.0) * val * s1;  // MODE 2: A_RD is kept already doubled
+                    if (MODE == 2) out2[k] = val * s2;
                 }
             }
         }
-        d1 = group_sum(d1, G);
-        if (MODE == 2) d2 = group_sum(d2, G);
-        for (int k = beg + lg; k < end; k += G) {
-            const double val = rowc_val[k];  // constraint k of this row IS internal slot k: coalesced stores
-            out1[k] = (MODE == 2 ? 2.0 : 1.0) * val * d1;  // MODE 2: A_RD is kept already doubled
-            if (MODE == 2) out2[k] = val * d2;
-        }
+        __syncthreads();
     }
 }
 
@@ -296,7 +301,7 @@ int32_t run_sparse(sdplrp_handle *h, const double *U, const double *V, double *o
         KLAUNCH(h);
     }
     if (h->n_sd > 0) {
-        const int grid_rows = grid_for(h->row_hi - h->row_lo, gpb, 16 * kNumSM);
+        const int grid_rows = grid_for(h->row_hi - h->row_lo, TPB / nv, 16 * kNumSM);
         if (vec2) k_A_rowc<MODE, 2><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, G, out1, out2);
         else k_A_rowc<MODE, 1><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, G, out1, out2);
         KLAUNCH(h);

@@ -455,7 +455,7 @@ def test_full_solve_matches_oracle(sp, oracle_mod, handle, which):
     else:
         # rank-one constraint / objective families amplify summation-order noise until discrete decisions
         # (fprec break, tolerance gates) flip: "final objective and duality bound to solver tolerance"
-        tol = objtol if math.isfinite(objtol) else 1e-2
+        tol = objtol if math.isfinite(objtol) else 5e-2   # no gap criterion: both stop on feasibility alone, objectives are looser
         assert abs(rg["obj"] - ro["obj"]) <= tol * max(1.0, abs(ro["obj"]))
         if math.isfinite(objtol):
             assert abs(rg["max_dual_value"] - ro["max_dual_value"]) <= tol * max(1.0, abs(ro["max_dual_value"]))

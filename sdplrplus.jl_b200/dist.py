@@ -79,6 +79,27 @@ def balanced_row_blocks(rowptr, world):
     return np.asarray(starts, dtype=np.int64)
 
 
+def dealt_row_starts(n, world):
+    """Row blocks of the multi-GPU layout of relabelled (skewed) patterns -- the same rule as k_deal_rows() in
+    csrc/preprocess.cu: the degree-sorted vertices are dealt round-robin to the ranks, rank q owns
+    ceil((n - q) / world) consecutive internal rows."""
+    starts = [0]
+    for q in range(world):
+        starts.append(starts[-1] + (n - q + world - 1) // world)
+    return np.asarray(starts, dtype=np.int64)
+
+
+def deal_order(sorted_vertices, world):
+    """Internal order produced by the deal: position k of the degree-sorted list goes to rank k % world, slot k // world."""
+    sorted_vertices = np.asarray(sorted_vertices)
+    n = sorted_vertices.size
+    starts = dealt_row_starts(n, world)
+    k = np.arange(n, dtype=np.int64)
+    out = np.empty_like(sorted_vertices)
+    out[starts[k % world] + k // world] = sorted_vertices
+    return out
+
+
 def make_handle(Handle):
     """Create this rank's handle; rank 0 makes the NCCL id and every rank receives it."""
     rank, world, local = init_process_group()

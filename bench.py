@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--rank", type=int, default=10)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--cpu-sample-n", type=int, default=1_000_000)
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanczos", type=int, default=0, help="also time this many Lanczos steps (reported separately)")
     args = ap.parse_args()
@@ -194,7 +194,7 @@ def main():
             return 0
         sample_n = min(args.cpu_sample_n, args.n)
         # keep the whole run within a few minutes whatever K is
-        steps = max(1, min(args.steps, 8))
+        steps = max(1, min(args.steps, 80))
         res = cpu_oracle_run(sp, args.n, args.edges, args.rank, sample_n, steps, min(args.warmup, 2), args.seed)
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "strong",

@@ -125,6 +125,16 @@ int32_t sdplrp_create(int32_t device, int32_t rank, int32_t world, const void *n
     if (const char *e = getenv("SDPLRP_SPMM_UNROLL")) h->spmm_unroll = atoi(e);
     if (const char *e = getenv("SDPLRP_SPMM_G0")) h->spmm_g0 = atoi(e);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SDPLRP_ERR_CUDA; }
+    // Experiment knob only: an L2 set-aside for evict_last lines (cudaLimitPersistingL2CacheSize).  Measured on C5: a
+    // set-aside of the maximum 79 MB slows every streaming kernel 1.8x (1.34 -> 2.46 ms for an 8.8 GB pass) and does
+    // not speed the gather pass up, so the library leaves the device default alone unless asked to.
+    if (const char *e = getenv("SDPLRP_L2_PERSIST_MB")) {
+        int maxp = 0;
+        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, device);
+        const size_t want = std::min<size_t>((size_t)maxp, (size_t)atoll(e) << 20);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) h->l2_persist_bytes = (i64)want;
+        else cudaGetLastError();
+    }
     bool ok = cudaMalloc((void **)&h->dscal, SC_COUNT * sizeof(double)) == cudaSuccess &&
               cudaMallocHost((void **)&h->hscal, SC_COUNT * sizeof(double)) == cudaSuccess &&
               cudaMalloc((void **)&h->partials, (size_t)kPartialsLen * sizeof(double)) == cudaSuccess &&

@@ -91,6 +91,7 @@ struct sdplrp_handle {
     double *S = nullptr;                                 // nnzF  sparse_S.nzval (internal slot order)
     double *stage = nullptr;                             // n x r staging buffer of the permuting copies
     i64 stage_len = 0;
+    i64 l2_persist_bytes = 0;                            // cudaLimitPersistingL2CacheSize set at creation
     i64 hot_rows = -1;                                   // leading (hub) rows of a gathered factor kept in L2; -1 = auto
     int spmm_unroll = 8;                                 // nonzeros per predicated block of the class-0 register kernel (4 or 8)
     int spmm_g0 = 1;                                     // class-0 lane groups of exactly r/2 lanes (0: next power of two)

@@ -45,12 +45,12 @@ __device__ __forceinline__ unsigned long long pol_evict_first() {
 }
 __device__ __forceinline__ int ldg_i32_hint(const int *p, unsigned long long pol) {
     int v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
 }
 __device__ __forceinline__ double ldg_f64_hint(const double *p, unsigned long long pol) {
     double v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     return v;
 }
 __device__ __forceinline__ double2 ldg_f64x2_hint(const double *p, unsigned long long pol) {

@@ -323,15 +323,17 @@ int32_t run_sparse(sdplrp_handle *h, const double *U, const double *V, double *o
 int32_t lr_project(sdplrp_handle *h, const LowRank &L, const double *X, double *dst) {
     const int r = h->r;
     if (r > TPB) return fail(h, SDPLRP_ERR_ARG, "low-rank path supports r <= 256");
+    // each rank projects its own rows; the r x s partial products are summed over the ranks (no factor rows cross NVLink)
+    const i64 lo = h->row_lo, nloc = h->row_hi - h->row_lo;
     for (i64 k0 = 0; k0 < L.s; k0 += kLrS) {
         const int sc = (int)std::min<i64>(kLrS, L.s - k0);
-        i64 blocks = std::min<i64>(kRedBlocks, std::max<i64>(1, h->n / (TPB / r)));
+        i64 blocks = std::min<i64>(kRedBlocks, std::max<i64>(1, nloc / (TPB / r)));
         blocks = std::max<i64>(1, std::min<i64>(blocks, kPartialsLen / ((i64)r * sc)));
-        k_lr_proj<<<(int)blocks, TPB, 0, h->stream>>>(h->n, r, sc, X, L.dB + k0 * h->n, h->n, h->partials, h->ticket, dst + k0 * r);
+        k_lr_proj<<<(int)blocks, TPB, 0, h->stream>>>(nloc, r, sc, X + lo * r, L.dB + k0 * h->n + lo, h->n, h->partials, h->ticket, dst + k0 * r);
         KLAUNCH(h);
     }
     CUDA_TRY(h, cudaGetLastError());
-    return SDPLRP_OK;
+    return comm_reduce_ptr(h, dst, (int)(L.s * r));
 }
 
 int32_t lr_scratch(sdplrp_handle *h) {
@@ -350,18 +352,19 @@ static int32_t run_lowrank(sdplrp_handle *h, int mode, const double *U, const do
     if (h->lr.empty()) return SDPLRP_OK;
     SDP_CHECK(lr_scratch(h));
     const int r = h->r;
+    const double once = (h->world == 1 || h->rank == 0) ? 1.0 : 0.0;  // every rank forms the same trace; the slot is all-reduced later
     for (const LowRank &L : h->lr) {
         double *ub = h->lr_tmp, *vb = h->lr_tmp + L.s * r;
         SDP_CHECK(lr_project(h, L, U, ub));
         if (mode != 0) SDP_CHECK(lr_project(h, L, V, vb));
         if (mode == 0) {
-            k_lr_trace<<<1, 128, 0, h->stream>>>(r, (int)L.s, ub, ub, L.dD, 1.0, out1, (int)L.gid);
+            k_lr_trace<<<1, 128, 0, h->stream>>>(r, (int)L.s, ub, ub, L.dD, once, out1, (int)L.gid);
         } else if (mode == 1) {
-            k_lr_trace<<<1, 128, 0, h->stream>>>(r, (int)L.s, ub, vb, L.dD, 1.0, out1, (int)L.gid);
+            k_lr_trace<<<1, 128, 0, h->stream>>>(r, (int)L.s, ub, vb, L.dD, once, out1, (int)L.gid);
         } else {
-            k_lr_trace<<<1, 128, 0, h->stream>>>(r, (int)L.s, ub, vb, L.dD, 2.0, out1, (int)L.gid);
+            k_lr_trace<<<1, 128, 0, h->stream>>>(r, (int)L.s, ub, vb, L.dD, 2.0 * once, out1, (int)L.gid);
             KLAUNCH(h);
-            k_lr_trace<<<1, 128, 0, h->stream>>>(r, (int)L.s, vb, vb, L.dD, 1.0, out2, (int)L.gid);
+            k_lr_trace<<<1, 128, 0, h->stream>>>(r, (int)L.s, vb, vb, L.dD, once, out2, (int)L.gid);
         }
         KLAUNCH(h);
     }

@@ -398,12 +398,14 @@ int32_t sdplrp_download_vec(sdplrp_handle *h, int32_t id, double *dst, int64_t l
     double *p = vec_ptr(h, id, &want);
     if (!p || !dst || len != want) return fail(h, SDPLRP_ERR_ARG, "download_vec: bad id or length");
     if (id == SDPLRP_VEC_S_NZVAL) return perm_slots_download(h, p, dst, len);
+    SDP_CHECK(comm_gather_cvec(h, p));  // multi-GPU: per-row-constraint slots live on their owners
     return perm_cvec_download(h, p, dst, len);
 }
 
 // ---- seam-level operators ----------------------------------------------------
-static int32_t copy_out(sdplrp_handle *h, const double *dev, double *host, i64 len) {
+static int32_t copy_out(sdplrp_handle *h, double *dev, double *host, i64 len) {
     if (!host) return SDPLRP_OK;
+    SDP_CHECK(comm_gather_cvec(h, dev));
     return perm_cvec_download(h, dev, host, len);  // (m+1)-vector: internal -> reference constraint order
 }
 
@@ -478,7 +480,7 @@ int32_t sdplrp_At_right(sdplrp_handle *h, const double *x, double *y, int64_t nc
 // several entries (not in the per-row lists), low-rank projections, off-diagonal dynamic gradient parts.
 static bool needs_remote_R_rows(const sdplrp_handle *h) {
     const i64 general = h->nA - h->n_sd - (h->obj_mat >= 0 ? 1 : 0);
-    return general > 0 || !h->lr.empty() || h->n_dynF > 0;
+    return general > 0 || h->n_dynF > 0;   // (low-rank terms project the owned rows and all-reduce r x s numbers)
 }
 
 // CR = C*R over the owned rows (from scratch); sums6[c][0] = <R,CR> per row class
@@ -527,7 +529,7 @@ static int32_t do_g(sdplrp_handle *h) {
     comm_mark_partial(h, SDPLRP_MAT_G);
     SectionScope sc(h, SDPLRP_SEC_NORMS);
     SDP_CHECK(comm_reduce_scalars(h, SC_GNORM2, 1));
-    return vec_pnorm2(h);
+    return vec_pnorm2(h);  // reduces its own share
 }
 
 int32_t sdplrp_f(sdplrp_handle *h, double *L, double *obj) {
@@ -643,7 +645,7 @@ int32_t sdplrp_step_g(sdplrp_handle *h, double alpha, double out[3]) {
     if (!out) return fail(h, SDPLRP_ERR_ARG, "step_g: null output");
     CUDA_TRY(h, cudaSetDevice(h->device));
     const bool split = h->obj_mat >= 0;
-    const bool fused = h->fused_tail && h->world == 1 && h->ls_valid && (!split || (h->CR_valid && h->CD_valid));
+    const bool fused = h->fused_tail && h->ls_valid && (!split || (h->CR_valid && h->CD_valid));
     if (fused) {
         SectionScope sc(h, SDPLRP_SEC_TAIL);
         SDP_CHECK(grad_step_fused(h, alpha));

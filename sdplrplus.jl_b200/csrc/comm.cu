@@ -100,18 +100,33 @@ void comm_destroy(sdplrp_handle *h) {
 
 // contiguous row blocks with ~nnzF/world nonzeros each (prefix sum over the
 // full pattern's row pointer); identical on every rank.
+// the per-row-constraint slots that go with each rank's row block
+static int32_t partition_constraints(sdplrp_handle *h) {
+    h->c_starts.assign((size_t)h->world + 1, 0);
+    for (int q = 0; q <= h->world; q++) {
+        int v = 0;
+        CUDA_TRY(h, cudaMemcpy(&v, h->rowc_ptr + h->row_starts[(size_t)q], sizeof(int), cudaMemcpyDeviceToHost));
+        h->c_starts[(size_t)q] = v;
+    }
+    h->c_lo = h->c_starts[(size_t)h->rank];
+    h->c_hi = h->c_starts[(size_t)h->rank + 1];
+    return SDPLRP_OK;
+}
+
 int32_t comm_partition(sdplrp_handle *h) {
     const i64 n = h->n;
     for (int id = 0; id < 8; id++) h->mat_full[id] = true;
     if (h->dealt && h->world > 1) {  // blocks fixed by the hub-first relabeling (preprocess.cu, k_deal_rows)
         h->row_lo = h->row_starts[(size_t)h->rank];
         h->row_hi = h->row_starts[(size_t)h->rank + 1];
-        return SDPLRP_OK;
+        return partition_constraints(h);
     }
     h->row_starts.assign((size_t)h->world + 1, 0);
     h->row_starts[(size_t)h->world] = n;
     if (h->world <= 1) {
         h->row_lo = 0; h->row_hi = n;
+        h->c_lo = 0; h->c_hi = h->n_sd;
+        h->c_starts.assign(2, 0); h->c_starts[1] = h->n_sd;
         return SDPLRP_OK;
     }
     std::vector<int> ptr((size_t)n + 1);
@@ -130,7 +145,7 @@ int32_t comm_partition(sdplrp_handle *h) {
     }
     h->row_lo = h->row_starts[(size_t)h->rank];
     h->row_hi = h->row_starts[(size_t)h->rank + 1];
-    return SDPLRP_OK;
+    return partition_constraints(h);
 }
 
 static int full_slot(int mat_id) {
@@ -199,9 +214,25 @@ int32_t comm_reduce_mvec(sdplrp_handle *h, double *v1, double *v2) {
     if (h->world <= 1) return SDPLRP_OK;
     SectionScope sc(h, SDPLRP_SEC_COMM);
     ncclComm_t comm = (ncclComm_t)h->nccl;
+    // only the shared slots [n_sd, m]: the per-row constraints are computed and consumed by their owner (vecops.cu)
+    const size_t off = (size_t)h->n_sd, cnt = (size_t)(h->m + 1 - h->n_sd);
     NCCL_TRY(h, ncclGroupStart());
-    NCCL_TRY(h, ncclAllReduce(v1, v1, (size_t)(h->m + 1), ncclDouble, ncclSum, comm, h->stream));
-    if (v2) NCCL_TRY(h, ncclAllReduce(v2, v2, (size_t)(h->m + 1), ncclDouble, ncclSum, comm, h->stream));
+    NCCL_TRY(h, ncclAllReduce(v1 + off, v1 + off, cnt, ncclDouble, ncclSum, comm, h->stream));
+    if (v2) NCCL_TRY(h, ncclAllReduce(v2 + off, v2 + off, cnt, ncclDouble, ncclSum, comm, h->stream));
+    NCCL_TRY(h, ncclGroupEnd());
+    return SDPLRP_OK;
+}
+
+// every rank receives the per-row-constraint slots of the other ranks (downloads, S assembly for Lanczos)
+int32_t comm_gather_cvec(sdplrp_handle *h, double *v) {
+    if (h->world <= 1) return SDPLRP_OK;
+    SectionScope sc(h, SDPLRP_SEC_COMM);
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    NCCL_TRY(h, ncclGroupStart());
+    for (int q = 0; q < h->world; q++) {
+        const i64 off = h->c_starts[(size_t)q], len = h->c_starts[(size_t)q + 1] - off;
+        if (len > 0) NCCL_TRY(h, ncclBroadcast(v + off, v + off, (size_t)len, ncclDouble, q, comm, h->stream));
+    }
     NCCL_TRY(h, ncclGroupEnd());
     return SDPLRP_OK;
 }

@@ -72,6 +72,8 @@ struct sdplrp_handle {
     i64 n = 0, m = 0, nA = 0, nnzT = 0, nnzF = 0, Ec = 0;
     i64 row_lo = 0, row_hi = 0;  // rows of R/G/D owned by this rank
     std::vector<i64> row_starts; // world+1 block boundaries (identical on every rank)
+    i64 c_lo = 0, c_hi = 0;      // internal slots of the per-row constraints of the owned rows (vecops.cu)
+    std::vector<i64> c_starts;   // world+1: rowc_ptr[row_starts[q]]
     bool mat_full[8] = {true, true, true, true, true, true, true, true};  // R,G,D,W0,W1: all rows valid here?
     bool preprocessed = false;
 
@@ -363,7 +365,8 @@ void comm_mark_partial(sdplrp_handle *h, int mat_id);
 void comm_mark_full(sdplrp_handle *h, int mat_id);
 int32_t comm_require_full(sdplrp_handle *h, int mat_id);
 int32_t comm_gather_rows(sdplrp_handle *h, double *p, int mat_id);
-int32_t comm_reduce_mvec(sdplrp_handle *h, double *v1, double *v2);
+int32_t comm_reduce_mvec(sdplrp_handle *h, double *v1, double *v2);   // shared slots [n_sd, m] only
+int32_t comm_gather_cvec(sdplrp_handle *h, double *v);                // make every per-row-constraint slot current on every rank
 int32_t comm_reduce_scalars(sdplrp_handle *h, int slot, int count);
 int32_t comm_reduce_ptr(sdplrp_handle *h, double *p, int count);
 int32_t comm_step_R(sdplrp_handle *h, double alpha);

@@ -616,6 +616,7 @@ int32_t grad_form_y(sdplrp_handle *h) {
 // At_preprocess!: materialise S = y_obj*C + S_dyn(y) on the full pattern (seam-level / Lanczos)
 int32_t grad_assemble_S(sdplrp_handle *h) {
     h->S_current = true;
+    SDP_CHECK(comm_gather_cvec(h, h->y));  // multi-GPU: S is replicated, so every rank needs every y_i
     if (h->nA <= 0) return SDPLRP_OK;
     cudaStream_t st = h->stream;
     const double yobj = (h->obj_mat >= 0) ? h->y_obj : 0.0;
@@ -750,6 +751,9 @@ int32_t grad_step_fused(sdplrp_handle *h, double alpha) {
 #undef SG_ARGS
     KLAUNCH(h);
     std::swap(h->pvio_raw, h->pvio_raw_alt);
+    comm_mark_partial(h, SDPLRP_MAT_R);
+    comm_mark_partial(h, SDPLRP_MAT_G);
+    if (h->n_dynF > 0) SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));  // the off-diagonal dynamic part gathers rows of other ranks
     bool renorm = false;
     if (h->n_dynF > 0) {
         RowArgs a = {};
@@ -763,6 +767,7 @@ int32_t grad_step_fused(sdplrp_handle *h, double alpha) {
         renorm = true;
     }
     if (renorm) SDP_CHECK(lb_norm2(h, h->G, SC_GNORM2));
+    SDP_CHECK(comm_reduce_scalars(h, SC_GNORM2, 2));  // ||G||^2 and ||pvio||^2 shares of the ranks
     CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
 }

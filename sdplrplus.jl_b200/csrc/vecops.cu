@@ -5,6 +5,15 @@
 // Reference: src/coreop.jl:11-31 (f!), src/linesearch.jl:36-56, 118-124,
 // 158-172, src/sdplr.jl:224-234, 358-362, src/coreop.jl:412 (dual value).
 // All reductions are deterministic two-stage sums finalised on the device.
+//
+// Constraint slots and ranks.  The m-vectors are kept in the internal constraint order
+// (preprocess.cu): the single-diagonal-entry constraints first, in internal row order, then every
+// other constraint, then the objective slot m.  With several GPUs a rank OWNS the slots of the
+// per-row constraints of its rows, [c_lo, c_hi), and every rank keeps an identical copy of the
+// shared slots [n_sd, m] (their values are all-reduced where they are produced).  Slots of other
+// ranks' rows are never read.  Element-wise kernels run over owned + shared slots; sums run over
+// owned slots plus -- on rank 0 only -- the shared slots, are all-reduced as scalars and finished by
+// a one-thread kernel, so no m-vector crosses NVLink inside the iteration.
 #include <algorithm>
 #include "common.cuh"
 
@@ -12,35 +21,52 @@ namespace {
 
 constexpr int TPB = kRedThreads;
 
-// f! tail: raw[0:m] -= b; obj = raw[m]; L = obj + sum (yt^2 - lambda^2)/(2 sigma)
-__global__ void __launch_bounds__(TPB) k_f_finish(i64 m, double sigma, const double *__restrict__ b,
-                                                  const double *__restrict__ lambda, const double *__restrict__ ub,
-                                                  double *__restrict__ raw, double *partials, unsigned *ticket,
-                                                  double *__restrict__ dscal) {
+struct CRange {
+    i64 a0, a1;  // owned per-row-constraint slots
+    i64 b0, b1;  // shared slots this launch covers
+    __host__ __device__ i64 len() const { return (a1 - a0) + (b1 - b0); }
+    __device__ __forceinline__ i64 at(i64 k) const { return k < a1 - a0 ? a0 + k : b0 + (k - (a1 - a0)); }
+};
+// element-wise work: owned + every shared slot (each rank keeps the shared slots current)
+CRange range_all(const sdplrp_handle *h) { return CRange{h->c_lo, h->c_hi, h->n_sd, h->m}; }
+// sums: the shared slots are counted once, by rank 0
+CRange range_sum(const sdplrp_handle *h) { return CRange{h->c_lo, h->c_hi, h->n_sd, h->rank == 0 ? h->m : h->n_sd}; }
+
+#define FOR_SLOTS(i, R)                                                                                  \
+    for (i64 k__ = blockIdx.x * (i64)blockDim.x + threadIdx.x, i = 0;                                     \
+         k__ < (R).len() && ((i = (R).at(k__)), true); k__ += (i64)gridDim.x * blockDim.x)
+
+// f! tail, part 1: raw[i] -= b[i] over owned + shared slots (element-wise)
+__global__ void k_sub_b(CRange R, const double *__restrict__ b, double *__restrict__ raw) {
+    FOR_SLOTS(i, R) raw[i] -= b[i];
+}
+// f! tail, part 2: this rank's share of sum (yt^2 - lambda^2)/(2 sigma) -> *out
+__global__ void __launch_bounds__(TPB) k_f_sum(CRange R, double sigma, const double *__restrict__ lambda,
+                                               const double *__restrict__ ub, const double *__restrict__ raw, double *partials,
+                                               unsigned *ticket, double *__restrict__ out) {
     double acc[1] = {0.0};
-    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
-        const double v = raw[i] - b[i];
-        raw[i] = v;
+    FOR_SLOTS(i, R) {
         const double l = lambda[i];
-        const double yt = fmin(ub[i], l - sigma * v);
+        const double yt = fmin(ub[i], l - sigma * raw[i]);
         acc[0] += (yt * yt - l * l) / (2.0 * sigma);
     }
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { out[0] = s[0]; });
+}
+__global__ void k_f_final(i64 m, const double *__restrict__ raw, double *__restrict__ dscal) {
     const double obj = raw[m];
-    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) {
-        dscal[SC_OBJ] = obj;
-        dscal[SC_LVAL] = obj + s[0];
-    });
+    dscal[SC_OBJ] = obj;
+    dscal[SC_LVAL] = obj + dscal[SC_LVAL];
 }
 
-// the eight dot products behind the five quartic coefficients (src/linesearch.jl:36-56)
-__global__ void __launch_bounds__(TPB) k_biquadratic(i64 m, double sigma, const double *__restrict__ lambda,
+// the eight dot products behind the five quartic coefficients (src/linesearch.jl:36-56) -> dscal[SC_BQ .. SC_BQ+8)
+__global__ void __launch_bounds__(TPB) k_biquadratic(CRange R, double sigma, const double *__restrict__ lambda,
                                                      const double *__restrict__ raw, const double *__restrict__ q1v,
                                                      const double *__restrict__ q2v, double *partials, unsigned *ticket,
                                                      double *__restrict__ dscal) {
     double acc[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) acc[k] = 0.0;
-    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
+    FOR_SLOTS(i, R) {
         const double l = lambda[i], q0 = raw[i], q1 = q1v[i], q2 = q2v[i];
         acc[0] += l * q0;
         acc[1] += q0 * q0;
@@ -51,34 +77,42 @@ __global__ void __launch_bounds__(TPB) k_biquadratic(i64 m, double sigma, const 
         acc[6] += q1 * q2;
         acc[7] += q2 * q2;
     }
-    const double p0 = raw[m], p1 = q1v[m], p2 = q2v[m];
     grid_sum_finalize<8>(acc, partials, ticket, [&](double (&s)[8]) {
-        dscal[SC_BQ + 0] = p0 - s[0] + sigma * s[1] / 2.0;
-        dscal[SC_BQ + 1] = p1 - s[2] + sigma * s[3];
-        dscal[SC_BQ + 2] = p2 - s[4] + sigma * s[5] / 2.0;
-        dscal[SC_BQ + 3] = sigma * s[6];
-        dscal[SC_BQ + 4] = sigma * s[7] / 2.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) dscal[SC_BQ + k] = s[k];
     });
 }
+__global__ void k_biquadratic_final(i64 m, double sigma, const double *__restrict__ raw, const double *__restrict__ q1v,
+                                    const double *__restrict__ q2v, double *__restrict__ dscal) {
+    const double p0 = raw[m], p1 = q1v[m], p2 = q2v[m];
+    double s[8];
+    for (int k = 0; k < 8; k++) s[k] = dscal[SC_BQ + k];
+    dscal[SC_BQ + 0] = p0 - s[0] + sigma * s[1] / 2.0;
+    dscal[SC_BQ + 1] = p1 - s[2] + sigma * s[3];
+    dscal[SC_BQ + 2] = p2 - s[4] + sigma * s[5] / 2.0;
+    dscal[SC_BQ + 3] = sigma * s[6];
+    dscal[SC_BQ + 4] = sigma * s[7] / 2.0;
+}
 
-// raw += a*(a*A_DD + A_RD) over all m+1 slots; obj = raw[m]  (src/linesearch.jl:118-119)
-__global__ void k_commit(i64 m, double a, const double *__restrict__ q1v, const double *__restrict__ q2v,
+// raw += a*(a*A_DD + A_RD) over owned + shared slots and the objective slot; obj = raw[m]  (src/linesearch.jl:118-119)
+__global__ void k_commit(CRange R, i64 m, double a, const double *__restrict__ q1v, const double *__restrict__ q2v,
                          double *__restrict__ raw, double *__restrict__ dscal) {
-    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i <= m; i += (i64)gridDim.x * blockDim.x) {
-        const double v = raw[i] + a * (a * q2v[i] + q1v[i]);
-        raw[i] = v;
-        if (i == m) dscal[SC_OBJ] = v;
+    FOR_SLOTS(i, R) raw[i] += a * (a * q2v[i] + q1v[i]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double v = raw[m] + a * (a * q2v[m] + q1v[m]);
+        raw[m] = v;
+        dscal[SC_OBJ] = v;
     }
 }
 
 // the m-vector part of the fused step/gradient pass (gradient.cu, k_step_grad) for the constraints that are NOT in the
-// per-row lists, slots [c0, m), plus the objective slot m:  residual recurrence into the alternate buffer, y, and this
-// range's share of ||max(raw, lb)||^2 -> *pn2_out (the row pass adds its own share)
+// per-row lists, shared slots [c0, m), plus the objective slot m:  residual recurrence into the alternate buffer, y, and
+// this range's share of ||max(raw, lb)||^2 -> *pn2_out (the row pass adds its own share)
 __global__ void __launch_bounds__(TPB) k_tail_rest(i64 c0, i64 m, double a, double sigma, const double *__restrict__ q1v,
                                                    const double *__restrict__ q2v, const double *__restrict__ raw_in,
                                                    double *__restrict__ raw_out, const double *__restrict__ lambda,
                                                    const double *__restrict__ ub, const double *__restrict__ lb,
-                                                   double *__restrict__ y, double *__restrict__ pn2_out,
+                                                   double *__restrict__ y, double *__restrict__ pn2_out, double pn2_weight,
                                                    double *partials, unsigned *ticket, double *__restrict__ dscal) {
     double acc[1] = {0.0};
     for (i64 i = c0 + blockIdx.x * (i64)blockDim.x + threadIdx.x; i <= m; i += (i64)gridDim.x * blockDim.x) {
@@ -89,14 +123,14 @@ __global__ void __launch_bounds__(TPB) k_tail_rest(i64 c0, i64 m, double a, doub
         const double w = fmax(v, lb[i]);
         acc[0] += w * w;
     }
-    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { pn2_out[0] = s[0]; });
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { pn2_out[0] = pn2_weight * s[0]; });
 }
 
-// ||max(raw, lb)||_2^2 (src/coreop.jl:340-347, src/sdplr.jl:230-234)
-__global__ void __launch_bounds__(TPB) k_pnorm2(i64 m, const double *__restrict__ raw, const double *__restrict__ lb,
+// ||max(raw, lb)||_2^2 (src/coreop.jl:340-347, src/sdplr.jl:230-234), this rank's share
+__global__ void __launch_bounds__(TPB) k_pnorm2(CRange R, const double *__restrict__ raw, const double *__restrict__ lb,
                                                 double *partials, unsigned *ticket, double *__restrict__ dscal) {
     double acc[1] = {0.0};
-    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
+    FOR_SLOTS(i, R) {
         const double v = fmax(raw[i], lb[i]);
         acc[0] += v * v;
     }
@@ -104,16 +138,15 @@ __global__ void __launch_bounds__(TPB) k_pnorm2(i64 m, const double *__restrict_
 }
 
 // lambda_i <- min(ub_i, lambda_i - sigma*raw_i)  (src/sdplr.jl:358-362)
-__global__ void k_dual_update(i64 m, double sigma, const double *__restrict__ ub, const double *__restrict__ raw,
+__global__ void k_dual_update(CRange R, double sigma, const double *__restrict__ ub, const double *__restrict__ raw,
                               double *__restrict__ lambda) {
-    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x)
-        lambda[i] = fmin(ub[i], lambda[i] - sigma * raw[i]);
+    FOR_SLOTS(i, R) lambda[i] = fmin(ub[i], lambda[i] - sigma * raw[i]);
 }
 
-// sharp AL at K step sizes plus the slope at 0 (src/linesearch.jl:158-172)
+// sharp AL at K step sizes plus the slope at 0 (src/linesearch.jl:158-172): this rank's partial sums -> out[0..ARM_K]
 constexpr int ARM_K = 15;
 struct ArmijoArgs { double a[ARM_K]; int k; };
-__global__ void __launch_bounds__(TPB) k_armijo(i64 m, double sigma, ArmijoArgs args, const double *__restrict__ lambda,
+__global__ void __launch_bounds__(TPB) k_armijo(CRange R, double sigma, ArmijoArgs args, const double *__restrict__ lambda,
                                                 const double *__restrict__ ub, const double *__restrict__ raw,
                                                 const double *__restrict__ q1v, const double *__restrict__ q2v,
                                                 const double *__restrict__ y, double *partials, unsigned *ticket,
@@ -121,7 +154,7 @@ __global__ void __launch_bounds__(TPB) k_armijo(i64 m, double sigma, ArmijoArgs 
     double acc[ARM_K + 1];
 #pragma unroll
     for (int k = 0; k <= ARM_K; k++) acc[k] = 0.0;
-    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
+    FOR_SLOTS(i, R) {
         const double l = lambda[i], u = ub[i], q0 = raw[i], q1 = q1v[i], q2 = q2v[i];
 #pragma unroll
         for (int k = 0; k < ARM_K; k++) {
@@ -134,21 +167,26 @@ __global__ void __launch_bounds__(TPB) k_armijo(i64 m, double sigma, ArmijoArgs 
         }
         acc[ARM_K] += y[i] * q1;
     }
-    const double p0 = raw[m], p1 = q1v[m], p2 = q2v[m];
     grid_sum_finalize<ARM_K + 1>(acc, partials, ticket, [&](double (&s)[ARM_K + 1]) {
-        for (int k = 0; k < args.k; k++) {
-            const double a = args.a[k];
-            out[k] = p0 + a * p1 + a * a * p2 + s[k];
-        }
-        out[ARM_K] = p1 + s[ARM_K];
+#pragma unroll
+        for (int k = 0; k <= ARM_K; k++) out[k] = s[k];
     });
 }
+__global__ void k_armijo_final(i64 m, ArmijoArgs args, const double *__restrict__ raw, const double *__restrict__ q1v,
+                               const double *__restrict__ q2v, double *__restrict__ out) {
+    const double p0 = raw[m], p1 = q1v[m], p2 = q2v[m];
+    for (int k = 0; k < args.k; k++) {
+        const double a = args.a[k];
+        out[k] = p0 + a * p1 + a * a * p2 + out[k];
+    }
+    out[ARM_K] = p1 + out[ARM_K];
+}
 
-// sum y_i b_i over i < m
-__global__ void __launch_bounds__(TPB) k_yb(i64 m, const double *__restrict__ y, const double *__restrict__ b,
+// sum y_i b_i over i < m (this rank's share)
+__global__ void __launch_bounds__(TPB) k_yb(CRange R, const double *__restrict__ y, const double *__restrict__ b,
                                             double *partials, unsigned *ticket, double *__restrict__ out) {
     double acc[1] = {0.0};
-    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) acc[0] += y[i] * b[i];
+    FOR_SLOTS(i, R) acc[0] += y[i] * b[i];
     grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { out[0] = s[0]; });
 }
 
@@ -157,35 +195,50 @@ inline int red_grid(i64 m) { return grid_for(m, TPB, kRedBlocks); }
 }  // namespace
 
 int32_t vec_f_finish(sdplrp_handle *h) {
-    k_f_finish<<<red_grid(h->m), TPB, 0, h->stream>>>(h->m, h->sigma, h->b, h->lambda, h->lambda_ub, h->pvio_raw, h->partials, h->ticket, h->dscal);
+    const CRange all = range_all(h), sum = range_sum(h);
+    k_sub_b<<<red_grid(all.len()), TPB, 0, h->stream>>>(all, h->b, h->pvio_raw);
+    KLAUNCH(h);
+    k_f_sum<<<red_grid(sum.len()), TPB, 0, h->stream>>>(sum, h->sigma, h->lambda, h->lambda_ub, h->pvio_raw, h->partials, h->ticket,
+                                                       h->dscal + SC_LVAL);
+    KLAUNCH(h);
+    SDP_CHECK(comm_reduce_scalars(h, SC_LVAL, 1));
+    k_f_final<<<1, 1, 0, h->stream>>>(h->m, h->pvio_raw, h->dscal);
     KLAUNCH(h);
     CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
 }
 
 int32_t vec_biquadratic(sdplrp_handle *h) {
-    k_biquadratic<<<red_grid(h->m), TPB, 0, h->stream>>>(h->m, h->sigma, h->lambda, h->pvio_raw, h->A_RD, h->A_DD, h->partials, h->ticket, h->dscal);
+    const CRange sum = range_sum(h);
+    k_biquadratic<<<red_grid(sum.len()), TPB, 0, h->stream>>>(sum, h->sigma, h->lambda, h->pvio_raw, h->A_RD, h->A_DD, h->partials,
+                                                             h->ticket, h->dscal);
+    KLAUNCH(h);
+    SDP_CHECK(comm_reduce_scalars(h, SC_BQ, 8));
+    k_biquadratic_final<<<1, 1, 0, h->stream>>>(h->m, h->sigma, h->pvio_raw, h->A_RD, h->A_DD, h->dscal);
     KLAUNCH(h);
     CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
 }
 
 int32_t vec_commit(sdplrp_handle *h, double alpha) {
-    k_commit<<<red_grid(h->m + 1), TPB, 0, h->stream>>>(h->m, alpha, h->A_RD, h->A_DD, h->pvio_raw, h->dscal);
+    const CRange all = range_all(h);
+    k_commit<<<red_grid(all.len()), TPB, 0, h->stream>>>(all, h->m, alpha, h->A_RD, h->A_DD, h->pvio_raw, h->dscal);
     KLAUNCH(h);
     CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
 }
 
 int32_t vec_pnorm2(sdplrp_handle *h) {
-    k_pnorm2<<<red_grid(h->m), TPB, 0, h->stream>>>(h->m, h->pvio_raw, h->pvio_lb, h->partials, h->ticket, h->dscal);
+    const CRange sum = range_sum(h);
+    k_pnorm2<<<red_grid(sum.len()), TPB, 0, h->stream>>>(sum, h->pvio_raw, h->pvio_lb, h->partials, h->ticket, h->dscal);
     KLAUNCH(h);
     CUDA_TRY(h, cudaGetLastError());
-    return SDPLRP_OK;
+    return comm_reduce_scalars(h, SC_PNORM2, 1);
 }
 
 int32_t vec_dual_update(sdplrp_handle *h) {
-    k_dual_update<<<red_grid(h->m), TPB, 0, h->stream>>>(h->m, h->sigma, h->lambda_ub, h->pvio_raw, h->lambda);
+    const CRange all = range_all(h);
+    k_dual_update<<<red_grid(all.len()), TPB, 0, h->stream>>>(all, h->sigma, h->lambda_ub, h->pvio_raw, h->lambda);
     KLAUNCH(h);
     CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
@@ -194,12 +247,16 @@ int32_t vec_dual_update(sdplrp_handle *h) {
 int32_t vec_armijo(sdplrp_handle *h, const double *alphas, int k, double *L, double *slope) {
     int done = 0;
     double sl = 0.0;
+    const CRange sum = range_sum(h);
     while (done < k || k == 0) {
         ArmijoArgs args;
         args.k = std::min(ARM_K, k - done);
         for (int q = 0; q < ARM_K; q++) args.a[q] = q < args.k ? alphas[done + q] : 0.0;
-        k_armijo<<<red_grid(h->m), TPB, 0, h->stream>>>(h->m, h->sigma, args, h->lambda, h->lambda_ub, h->pvio_raw, h->A_RD, h->A_DD, h->y,
-                                                      h->partials, h->ticket, h->dscal + SC_LANCZOS);
+        k_armijo<<<red_grid(sum.len()), TPB, 0, h->stream>>>(sum, h->sigma, args, h->lambda, h->lambda_ub, h->pvio_raw, h->A_RD, h->A_DD,
+                                                           h->y, h->partials, h->ticket, h->dscal + SC_LANCZOS);
+        KLAUNCH(h);
+        SDP_CHECK(comm_reduce_scalars(h, SC_LANCZOS, ARM_K + 1));
+        k_armijo_final<<<1, 1, 0, h->stream>>>(h->m, args, h->pvio_raw, h->A_RD, h->A_DD, h->dscal + SC_LANCZOS);
         KLAUNCH(h);
         CUDA_TRY(h, cudaGetLastError());
         SDP_CHECK(fetch_scalars(h, SC_LANCZOS, ARM_K + 1));
@@ -213,19 +270,23 @@ int32_t vec_armijo(sdplrp_handle *h, const double *alphas, int k, double *L, dou
 }
 
 int32_t vec_dual_dot(sdplrp_handle *h, double *out) {
-    k_yb<<<red_grid(h->m), TPB, 0, h->stream>>>(h->m, h->y, h->b, h->partials, h->ticket, h->dscal + SC_LANCZOS + 9);
+    const CRange sum = range_sum(h);
+    k_yb<<<red_grid(sum.len()), TPB, 0, h->stream>>>(sum, h->y, h->b, h->partials, h->ticket, h->dscal + SC_LANCZOS + 9);
     KLAUNCH(h);
     CUDA_TRY(h, cudaGetLastError());
+    SDP_CHECK(comm_reduce_scalars(h, SC_LANCZOS + 9, 1));
     SDP_CHECK(fetch_scalars(h, SC_LANCZOS + 9, 1));
     *out = -h->hscal[SC_LANCZOS + 9];
     return SDPLRP_OK;
 }
 
-// see k_tail_rest; launched BEFORE the fused row pass (S_dyn needs the y of these constraints)
+// see k_tail_rest; launched BEFORE the fused row pass (S_dyn needs the y of these constraints).  Every rank runs it
+// (the shared slots stay current everywhere); its share of the norm is counted once, on rank 0.
 int32_t vec_tail_rest(sdplrp_handle *h, double alpha, const double *raw_in, double *raw_out, double *pn2_out) {
     const i64 c0 = h->n_sd;
     k_tail_rest<<<red_grid(h->m + 1 - c0), TPB, 0, h->stream>>>(c0, h->m, alpha, h->sigma, h->A_RD, h->A_DD, raw_in, raw_out, h->lambda,
-                                                              h->lambda_ub, h->pvio_lb, h->y, pn2_out, h->partials, h->ticket, h->dscal);
+                                                              h->lambda_ub, h->pvio_lb, h->y, pn2_out, h->rank == 0 ? 1.0 : 0.0,
+                                                              h->partials, h->ticket, h->dscal);
     KLAUNCH(h);
     CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;

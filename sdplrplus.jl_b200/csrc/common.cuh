@@ -19,7 +19,7 @@ constexpr long long kPartialsLen = (long long)kRedBlocks * kMaxRedK * 8;  // dou
 constexpr int kLongMatThreshold = 64;   // matrices with more triu entries go to the chunked path
 constexpr int kChunkEntries = 2048;     // entries per chunk (one CTA) of a long matrix
 constexpr int kRowGroupMax = 32;        // rows with <= this many nonzeros: one sub-warp lane group per row
-constexpr int kRowWarpMax = 2048;       // rows with <= this many: one warp per row; longer: one CTA per row
+constexpr int kRowWarpMax = 512;        // rows with <= this many: one warp per row; longer: chunks of this size, one warp each
 
 // rows of a CSR pattern binned by length (compacted lists, natural order inside a bin);
 // list[c] == nullptr with cnt[c] == n means "all rows" (identity, keeps streaming access)
@@ -142,6 +142,7 @@ struct sdplrp_handle {
     unsigned char *sd_flag = nullptr;  // nA: matrix handled by the row lists
     RowClasses full_cls, dyn_cls;  // row bins of the full / dynamic pattern
     TileLayout full_tile, dyn_tile; // long-row chunk lists of both patterns (spmm.cu)
+    TileLayout full_long, dyn_long; // rows of the third class cut into kRowWarpMax-nonzero chunks (gradient.cu)
     double *tile_scratch = nullptr; // chunk partial sums, max(n_chunks) x r
     i64 tile_scratch_len = 0;
     double *CR = nullptr, *CD = nullptr;  // n x r: C*R (recurrence) and C*D

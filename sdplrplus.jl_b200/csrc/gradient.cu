@@ -118,6 +118,7 @@ struct Acc<1> {
     __device__ __forceinline__ void scale_add(double sc, double a, const double *p) { v = sc * (v + a * __ldg(p)); }
     __device__ __forceinline__ void accumulate_onto(double sc, const double *p) { v = p[0] + sc * v; }
     __device__ __forceinline__ void fma_reg(double s, const Acc &o) { v += s * o.v; }
+    __device__ __forceinline__ void add_mem(const double *p) { v += p[0]; }
     __device__ __forceinline__ void scale(double sc) { v *= sc; }
     __device__ __forceinline__ double dot_ld(const double *p) const { return v * __ldg(p); }
     __device__ __forceinline__ double norm2() const { return v * v; }
@@ -149,6 +150,10 @@ struct Acc<2> {
         v.x = x.x + sc * v.x; v.y = x.y + sc * v.y;
     }
     __device__ __forceinline__ void fma_reg(double s, const Acc &o) { v.x += s * o.v.x; v.y += s * o.v.y; }
+    __device__ __forceinline__ void add_mem(const double *p) {
+        const double2 x = *reinterpret_cast<const double2 *>(p);
+        v.x += x.x; v.y += x.y;
+    }
     __device__ __forceinline__ double dot_ld(const double *p) const {
         const double2 x = ldg2(p);
         return v.x * x.x + v.y * x.y;
@@ -177,6 +182,10 @@ struct RowArgs {
     unsigned *ticket;
     double *out;       // EPI != 0: out[0], out[1]
     i64 own_lo, own_hi;
+    // long rows (> kRowWarpMax nonzeros) are cut into chunks: one warp per chunk, partial sums in `scratch`
+    const int *chunk_start, *chunk_end, *chunk_row;
+    const int *long_rows, *long_cptr;
+    double *scratch;
 };
 
 template <int VEC, int MAXU, int EPI>
@@ -264,8 +273,11 @@ __global__ void __launch_bounds__(TPB) k_rows_group(RowArgs a) {
     finish_sums<EPI>(a, s0, s1);
 }
 
-// class 1: one warp per row; the 32/G lane groups take 4 nonzeros each per step
-template <int VEC, int MAXU, bool IND, int EPI>
+// class 1: one warp per row; the 32/G lane groups take 4 nonzeros each per step.
+// CHUNK: the work items are the kRowWarpMax-nonzero chunks of the long rows (class 2) and the warp leaves its partial
+// sums in a.scratch (combined per row, in chunk order, by k_rows_combine) -- a hub row of 30 k nonzeros is spread over
+// 60 warps instead of serialising one CTA, which is what lets the pass scale when the rows are divided among GPUs.
+template <int VEC, int MAXU, bool IND, int EPI, bool CHUNK>
 __global__ void __launch_bounds__(TPB) k_rows_warp(RowArgs a) {
     const int nv = a.r / VEC;
     const int lane = threadIdx.x & 31;
@@ -275,9 +287,9 @@ __global__ void __launch_bounds__(TPB) k_rows_warp(RowArgs a) {
     const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
     double s0 = 0.0, s1 = 0.0;
     for (i64 q = warp; q < a.n_rows; q += n_warps) {  // warp-uniform
-        const i64 i = a.rows ? a.rows[q] : q;
+        const i64 i = CHUNK ? a.chunk_row[q] : (a.rows ? a.rows[q] : q);
         if (i < a.own_lo || i >= a.own_hi) continue;
-        const int beg = a.ptr[i], end = a.ptr[i + 1];
+        const int beg = CHUNK ? a.chunk_start[q] : a.ptr[i], end = CHUNK ? a.chunk_end[q] : a.ptr[i + 1];
         Acc<VEC> acc[MAXU];
 #pragma unroll
         for (int u = 0; u < MAXU; u++) acc[u].zero();
@@ -304,12 +316,48 @@ __global__ void __launch_bounds__(TPB) k_rows_warp(RowArgs a) {
 #pragma unroll
         for (int u = 0; u < MAXU; u++)
             for (int o = a.G; o < 32; o <<= 1) acc[u].shfl_add(o);
-        if (grp == 0) row_epilogue<VEC, MAXU, EPI>(a, i, acc, lg, nv, s0, s1, a.G);
+        if (grp == 0) {
+            if (CHUNK) {
+#pragma unroll
+                for (int u = 0; u < MAXU; u++) {
+                    const int c = lg + u * a.G;
+                    if (c < nv) acc[u].store(a.scratch + (size_t)q * a.r + c * VEC);
+                }
+            } else {
+                row_epilogue<VEC, MAXU, EPI>(a, i, acc, lg, nv, s0, s1, a.G);
+            }
+        }
+    }
+    if (!CHUNK) finish_sums<EPI>(a, s0, s1);
+}
+
+// class 2, second step: per long row the chunk partials are added in chunk order, then the row epilogue
+template <int VEC, int MAXU, int EPI>
+__global__ void __launch_bounds__(TPB) k_rows_combine(RowArgs a) {
+    const int nv = a.r / VEC;
+    const int lg = threadIdx.x & (a.G - 1);
+    const i64 group = ((i64)blockIdx.x * TPB + threadIdx.x) / a.G;
+    const i64 n_groups = (i64)gridDim.x * TPB / a.G;
+    double s0 = 0.0, s1 = 0.0;
+    for (i64 q = group; q < a.n_rows; q += n_groups) {
+        const i64 i = a.long_rows[q];
+        if (i < a.own_lo || i >= a.own_hi) continue;
+        Acc<VEC> acc[MAXU];
+#pragma unroll
+        for (int u = 0; u < MAXU; u++) acc[u].zero();
+        for (int c = a.long_cptr[q]; c < a.long_cptr[q + 1]; c++) {
+#pragma unroll
+            for (int u = 0; u < MAXU; u++) {
+                const int p = lg + u * a.G;
+                if (p < nv) acc[u].add_mem(a.scratch + (size_t)c * a.r + p * VEC);
+            }
+        }
+        row_epilogue<VEC, MAXU, EPI>(a, i, acc, lg, nv, s0, s1, a.G);
     }
     finish_sums<EPI>(a, s0, s1);
 }
 
-// class 2: one CTA per row; groups stride over the nonzeros, fixed-order cross-group sum in shared memory
+// (superseded by the chunk pass; kept for reference builds) one CTA per row; groups stride over the nonzeros
 template <int VEC, int MAXU, bool IND, int EPI>
 __global__ void __launch_bounds__(TPB) k_rows_cta(RowArgs a) {
     extern __shared__ double sm[];  // (TPB/G) * r
@@ -538,7 +586,7 @@ struct Csr {
 };
 
 template <int VEC, int MAXU, bool IND, int EPI>
-int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, double *sums /* 3 x 2 or null */) {
+int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const TileLayout &longs, double *sums /* 3 x 2 or null */) {
     cudaStream_t st = h->stream;
     const int gpb = TPB / a.G;
     const int gpb0 = TPB / a.G0;
@@ -554,10 +602,22 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, doubl
             if (h->spmm_unroll >= 8) k_rows_group<VEC, MAXU, IND, EPI, 8><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
             else k_rows_group<VEC, MAXU, IND, EPI, 4><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
         } else if (c == 1) {
-            k_rows_warp<VEC, MAXU, IND, EPI><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
+            k_rows_warp<VEC, MAXU, IND, EPI, false><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
         } else {
-            const size_t smem = (size_t)gpb * a.r * sizeof(double);
-            k_rows_cta<VEC, MAXU, IND, EPI><<<grid_for(a.n_rows, 1, 8 * kNumSM), TPB, smem, st>>>(a);
+            // long rows: one warp per chunk, then the per-row combination with the epilogue
+            const i64 need = longs.n_chunks * (i64)a.r;
+            if (h->tile_scratch_len < need) {
+                SDP_CHECK(dev_alloc(h, &h->tile_scratch, need));
+                h->tile_scratch_len = need;
+            }
+            RowArgs b = a;
+            b.chunk_start = longs.chunk_start; b.chunk_end = longs.chunk_end; b.chunk_row = longs.chunk_row;
+            b.long_rows = longs.long_rows; b.long_cptr = longs.long_cptr; b.scratch = h->tile_scratch;
+            b.n_rows = longs.n_chunks;
+            k_rows_warp<VEC, MAXU, IND, EPI, true><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
+            KLAUNCH(h);
+            b.n_rows = longs.n_long;
+            k_rows_combine<VEC, MAXU, EPI><<<grid_for(b.n_rows, gpb, 4 * kNumSM), TPB, 0, st>>>(b);
         }
         KLAUNCH(h);
     }
@@ -566,7 +626,7 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, doubl
 }
 
 template <bool IND, int EPI>
-int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, double *sums) {
+int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const TileLayout &longs, double *sums) {
     const int r = h->r;
     const bool vec2 = (r % 2 == 0);
     const int nv = vec2 ? r / 2 : r;
@@ -581,11 +641,11 @@ int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, double *s
     const int units = (nv + a.G - 1) / a.G;
     if (units > 4) return fail(h, SDPLRP_ERR_ARG, "rank too large for the sparse kernels (r <= 256 even / 128 odd)");
     if (vec2) {
-        if (units == 1) return launch_classes<2, 1, IND, EPI>(h, a, cls, sums);
-        return launch_classes<2, 4, IND, EPI>(h, a, cls, sums);
+        if (units == 1) return launch_classes<2, 1, IND, EPI>(h, a, cls, longs, sums);
+        return launch_classes<2, 4, IND, EPI>(h, a, cls, longs, sums);
     }
-    if (units == 1) return launch_classes<1, 1, IND, EPI>(h, a, cls, sums);
-    return launch_classes<1, 4, IND, EPI>(h, a, cls, sums);
+    if (units == 1) return launch_classes<1, 1, IND, EPI>(h, a, cls, longs, sums);
+    return launch_classes<1, 4, IND, EPI>(h, a, cls, longs, sums);
 }
 
 int32_t add_lowrank(sdplrp_handle *h, const double *X, double *Y, double scale) {
@@ -661,7 +721,7 @@ int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bo
         RowArgs a = {};
         a.ptr = h->full_ptr; a.idx = h->full_idx; a.val = h->S; a.src = nullptr;
         a.X = X; a.Y = Y; a.scale = scale;
-        SDP_CHECK((launch_csr<false, 0>(h, a, h->full_cls, nullptr)));
+        SDP_CHECK((launch_csr<false, 0>(h, a, h->full_cls, h->full_long, nullptr)));
     } else {
         CUDA_TRY(h, cudaMemsetAsync(Y + h->row_lo * r, 0, (size_t)(h->row_hi - h->row_lo) * r * sizeof(double), h->stream));
     }
@@ -677,7 +737,7 @@ int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double
     RowArgs a = {};
     a.ptr = h->full_ptr; a.idx = h->full_idx; a.val = h->Cfull; a.src = nullptr;
     a.X = X; a.Y = Y; a.Z = Z; a.scale = 1.0;
-    return launch_csr<false, 2>(h, a, h->full_cls, sums6);
+    return launch_csr<false, 2>(h, a, h->full_cls, h->full_long, sums6);
 }
 
 // the hot-loop gradient: G = 2*(y_obj*CR + S_dyn(y)*R + low rank), ||G||_F^2 -> SC_GNORM2
@@ -707,7 +767,7 @@ int32_t grad_hot(sdplrp_handle *h) {
         RowArgs a = {};
         a.ptr = h->dynrow_ptr; a.idx = h->dynrow_col; a.val = h->dynS; a.src = h->dynrow_src;
         a.X = h->R; a.Y = h->G; a.scale = 2.0;
-        SDP_CHECK((launch_csr<true, 3>(h, a, h->dyn_cls, nullptr)));
+        SDP_CHECK((launch_csr<true, 3>(h, a, h->dyn_cls, h->dyn_long, nullptr)));
         renorm = true;
     }
     if (!h->lr.empty()) {
@@ -759,7 +819,7 @@ int32_t grad_step_fused(sdplrp_handle *h, double alpha) {
         RowArgs a = {};
         a.ptr = h->dynrow_ptr; a.idx = h->dynrow_col; a.val = h->dynS; a.src = h->dynrow_src;
         a.X = h->R; a.Y = h->G; a.scale = 2.0;
-        SDP_CHECK((launch_csr<true, 3>(h, a, h->dyn_cls, nullptr)));
+        SDP_CHECK((launch_csr<true, 3>(h, a, h->dyn_cls, h->dyn_long, nullptr)));
         renorm = true;
     }
     if (!h->lr.empty()) {

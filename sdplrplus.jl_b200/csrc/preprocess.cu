@@ -465,14 +465,16 @@ __global__ void k_sd_vals(i64 n_sd, const int *__restrict__ sorted_a, const int 
         val[p] = ent_two[matptr[sorted_a[p]]];
 }
 
-__global__ void k_tile_chunk_counts(i64 nLong, const int *__restrict__ long_rows, const int *__restrict__ ptr, int *__restrict__ cnt) {
+__global__ void k_tile_chunk_counts(i64 nLong, const int *__restrict__ long_rows, const int *__restrict__ ptr, int chunk,
+                                    int *__restrict__ cnt) {
     for (i64 l = blockIdx.x * (i64)blockDim.x + threadIdx.x; l < nLong; l += (i64)gridDim.x * blockDim.x) {
         const int i = long_rows[l];
-        cnt[l] = (ptr[i + 1] - ptr[i] + kTileChunk - 1) / kTileChunk;
+        cnt[l] = (ptr[i + 1] - ptr[i] + chunk - 1) / chunk;
     }
 }
 __global__ void k_tile_chunks(i64 nChunks, i64 nLong, const int *__restrict__ long_rows, const int *__restrict__ long_cptr,
-                              const int *__restrict__ ptr, int *__restrict__ cstart, int *__restrict__ cend, int *__restrict__ crow) {
+                              const int *__restrict__ ptr, int chunk, int *__restrict__ cstart, int *__restrict__ cend,
+                              int *__restrict__ crow) {
     for (i64 c = blockIdx.x * (i64)blockDim.x + threadIdx.x; c < nChunks; c += (i64)gridDim.x * blockDim.x) {
         i64 lo = 0, hi = nLong - 1;  // last l with long_cptr[l] <= c
         while (lo < hi) {
@@ -480,9 +482,9 @@ __global__ void k_tile_chunks(i64 nChunks, i64 nLong, const int *__restrict__ lo
             if (long_cptr[mid] <= (int)c) lo = mid; else hi = mid - 1;
         }
         const int i = long_rows[lo];
-        const int s = ptr[i] + ((int)c - long_cptr[lo]) * kTileChunk;
+        const int s = ptr[i] + ((int)c - long_cptr[lo]) * chunk;
         cstart[c] = s;
-        cend[c] = min(s + kTileChunk, ptr[i + 1]);
+        cend[c] = min(s + chunk, ptr[i + 1]);
         crow[c] = i;
     }
 }
@@ -493,7 +495,7 @@ void tile_free(TileLayout &t) {
 }
 
 // chunk lists of the rows that do not fit one tile of the async-copy SpMM
-int32_t tile_build(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, TileLayout &t) {
+int32_t tile_build(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, TileLayout &t, int chunk = kTileChunk) {
     cudaStream_t st = h->stream;
     const int GS = 8 * kNumSM;
     int32_t rc = SDPLRP_OK;
@@ -501,7 +503,7 @@ int32_t tile_build(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, TileLayout
     int *lflag = tmp.get<int>(h, n + 1, &rc), *lpos = tmp.get<int>(h, n + 1, &rc);
     if (rc) return rc;
     CUDA_TRY(h, cudaMemsetAsync(lflag, 0, (size_t)(n + 1) * sizeof(int), st));
-    k_len_flag<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, ptr, kTileChunk, lflag); KLAUNCH(h);
+    k_len_flag<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, ptr, chunk, lflag); KLAUNCH(h);
     SDP_CHECK(exclusive_scan(h, lflag, lpos, n + 1));
     int nl = 0;
     SDP_CHECK(read_int(h, lpos + n, &nl));
@@ -512,20 +514,20 @@ int32_t tile_build(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, TileLayout
     if (rc) return rc;
     CUDA_TRY(h, cudaMemsetAsync(ccnt, 0, (size_t)(nl + 1) * sizeof(int), st));
     k_compact_ids<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, lflag, lpos, t.long_rows); KLAUNCH(h);
-    k_tile_chunk_counts<<<grid_for(nl, TPB, GS), TPB, 0, st>>>(nl, t.long_rows, ptr, ccnt); KLAUNCH(h);
+    k_tile_chunk_counts<<<grid_for(nl, TPB, GS), TPB, 0, st>>>(nl, t.long_rows, ptr, chunk, ccnt); KLAUNCH(h);
     SDP_CHECK(exclusive_scan(h, ccnt, t.long_cptr, nl + 1));
     int nc = 0;
     SDP_CHECK(read_int(h, t.long_cptr + nl, &nc));
     t.n_chunks = nc;
     SDP_CHECK(dev_alloc(h, &t.chunk_start, nc)); SDP_CHECK(dev_alloc(h, &t.chunk_end, nc)); SDP_CHECK(dev_alloc(h, &t.chunk_row, nc));
-    k_tile_chunks<<<grid_for(nc, TPB, GS), TPB, 0, st>>>(nc, nl, t.long_rows, t.long_cptr, ptr, t.chunk_start, t.chunk_end, t.chunk_row);
+    k_tile_chunks<<<grid_for(nc, TPB, GS), TPB, 0, st>>>(nc, nl, t.long_rows, t.long_cptr, ptr, chunk, t.chunk_start, t.chunk_end, t.chunk_row);
     KLAUNCH(h);
     return SDPLRP_OK;
 }
 }  // namespace
 
 void pre_free(sdplrp_handle *h) {
-    tile_free(h->full_tile); tile_free(h->dyn_tile);
+    tile_free(h->full_tile); tile_free(h->dyn_tile); tile_free(h->full_long); tile_free(h->dyn_long);
     dev_free(&h->tile_scratch); h->tile_scratch_len = 0;
     dev_free(&h->triu_colptr); dev_free(&h->triu_rowval);
     if (h->full_ptr == h->ref_full_ptr) { h->full_ptr = nullptr; h->full_idx = nullptr; }  // aliases when not relabeled
@@ -841,6 +843,9 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
     SDP_CHECK(build_classes(h, tmp, n, h->dynrow_ptr, h->dyn_cls));
     SDP_CHECK(tile_build(h, tmp, n, h->full_ptr, h->full_tile));
     SDP_CHECK(tile_build(h, tmp, n, h->dynrow_ptr, h->dyn_tile));
+    // rows of the third class (> kRowWarpMax nonzeros) cut into chunks of kRowWarpMax for the register kernels
+    SDP_CHECK(tile_build(h, tmp, n, h->full_ptr, h->full_long, kRowWarpMax));
+    SDP_CHECK(tile_build(h, tmp, n, h->dynrow_ptr, h->dyn_long, kRowWarpMax));
     CUDA_TRY(h, cudaStreamSynchronize(st));
     CUDA_TRY(h, cudaGetLastError());
     h->preprocessed = true;

@@ -8,20 +8,28 @@
 // Design (not a translation)
 //  * S is split as  S(y) = y_obj * C  +  S_dyn(y):  the objective's values are
 //    static (Cfull, resident in HBM), only the "dynamic" slots that some
-//    constraint touches (the n diagonal slots for MaxCut) are re-evaluated per
-//    iteration through a deterministic slot->contributors gather (no atomics).
+//    constraint touches are re-evaluated per iteration through a deterministic
+//    slot->contributors gather (no atomics).  Constraints that are a single diagonal
+//    entry never enter that gather: they are applied from per-row lists.
 //  * The hot loop never multiplies by the full S.  It keeps CR = C*R by the
 //    recurrence CR += alpha*CD (the same device the reference uses for the
 //    residual vector, src/linesearch.jl:118) where CD = C*D is the ONE gather
 //    pass per inner iteration; that pass also yields <C,DD'> = <D,CD> and
 //    <C,RD'+DR'> = 2<D,CR> for the exact line search, and the gradient becomes
-//    G = 2*(y_obj*CR + S_dyn*R): a pass over the dynamic pattern only.  CR is
+//    G = 2*(y_obj*CR + S_dyn*R): a streaming pass plus, only for constraints with
+//    off-diagonal entries, a gather over the off-diagonal dynamic pattern.  CR is
 //    rebuilt from scratch by every f! (major iteration), which bounds the drift.
-//  * Sparse x dense kernels walk the symmetric pattern as CSR with rows binned
-//    by length: <= kRowGroupMax nonzeros -> one sub-warp lane group per row,
-//    <= kRowWarpMax -> one warp per row (lane groups split the nonzeros, 16
-//    independent gathers in flight per warp), longer -> one CTA per row.  Lanes
-//    own 128-bit slices of the r-vector; accumulators stay in registers.
+//  * k_step_grad fuses the whole tail of an iteration (step, residual recurrence,
+//    y, gradient, both norms) into one pass over the rows (sdplrp_step_g).
+//  * Sparse x dense kernels walk the symmetric pattern (internal hub-first labels)
+//    as CSR with rows binned by length: <= kRowGroupMax nonzeros -> one lane group
+//    of exactly r/2 lanes per row (6 rows per warp at r = 10), fully predicated
+//    blocks of 8 nonzeros; <= kRowWarpMax -> one warp per row (lane groups split the
+//    nonzeros, 4 independent 128-bit gathers in flight per lane); longer rows are cut
+//    into kRowWarpMax-nonzero chunks, one warp each, combined per row in chunk order.
+//    Lanes own 128-bit slices of the r-vector; accumulators stay in registers; every
+//    reduction has a fixed order.  L2 policies: pattern streams evict_first, gathers
+//    of the hub prefix evict_last.
 //  * The seam-level operators At!(Y,X) / At!(y,x) still use the full S (tests,
 //    Lanczos); S is materialised from Cfull + dynamic slots on demand.
 #include <algorithm>
@@ -353,68 +361,6 @@ __global__ void __launch_bounds__(TPB) k_rows_combine(RowArgs a) {
             }
         }
         row_epilogue<VEC, MAXU, EPI>(a, i, acc, lg, nv, s0, s1, a.G);
-    }
-    finish_sums<EPI>(a, s0, s1);
-}
-
-// (superseded by the chunk pass; kept for reference builds) one CTA per row; groups stride over the nonzeros
-template <int VEC, int MAXU, bool IND, int EPI>
-__global__ void __launch_bounds__(TPB) k_rows_cta(RowArgs a) {
-    extern __shared__ double sm[];  // (TPB/G) * r
-    const int nv = a.r / VEC;
-    const int lg = threadIdx.x & (a.G - 1), grp = threadIdx.x / a.G, ng = TPB / a.G;
-    const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
-    double s0 = 0.0, s1 = 0.0;
-    for (i64 q = blockIdx.x; q < a.n_rows; q += gridDim.x) {
-        const i64 i = a.rows ? a.rows[q] : q;
-        if (i < a.own_lo || i >= a.own_hi) continue;
-        Acc<VEC> acc[MAXU];
-#pragma unroll
-        for (int u = 0; u < MAXU; u++) acc[u].zero();
-        const int beg = a.ptr[i], end = a.ptr[i + 1];
-        for (int k0 = beg + grp * 4; k0 < end; k0 += ng * 4) {  // 4 independent gathers in flight per lane
-            int cc[4];
-            double vv[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const bool ok = k0 + j < end;
-                cc[j] = ok ? ldg_i32_hint(a.idx + k0 + j, p_str) : 0;
-                vv[j] = ok ? (IND ? __ldg(a.val + ldg_i32_hint(a.src + k0 + j, p_str)) : ldg_f64_hint(a.val + k0 + j, p_str)) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < MAXU; u++) {
-                const int c = lg + u * a.G;
-                if (c < nv) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (k0 + j < end) acc[u].fma_hint(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
-                }
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < MAXU; u++) {
-            const int c = lg + u * a.G;
-            if (c < nv) acc[u].store(sm + (size_t)grp * a.r + c * VEC);
-        }
-        __syncthreads();
-        for (int e = threadIdx.x; e < a.r; e += TPB) {
-            double t = 0.0;
-            for (int g = 0; g < ng; g++) t += sm[(size_t)g * a.r + e];
-            const size_t off = (size_t)i * a.r + e;
-            if (EPI == 0) {
-                t *= a.scale;
-            } else if (EPI == 3) {
-                t = a.Y[off] + a.scale * t;
-            } else if (EPI == 1) {
-                t = a.ADD ? a.scale * (t + a.yobj * a.ADD[off]) : a.scale * t;
-                s0 += t * t;
-            } else {
-                s0 += a.X[off] * t;
-                if (a.Z) s1 += a.X[off] * a.Z[off];
-            }
-            a.Y[off] = t;
-        }
     }
     finish_sums<EPI>(a, s0, s1);
 }

@@ -125,6 +125,11 @@ int32_t sdplrp_create(int32_t device, int32_t rank, int32_t world, const void *n
     if (const char *e = getenv("SDPLRP_SPMM_UNROLL")) h->spmm_unroll = atoi(e);
     if (const char *e = getenv("SDPLRP_SPMM_G0")) h->spmm_g0 = atoi(e);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SDPLRP_ERR_CUDA; }
+    // L2 fetch granularity (cudaLimitMaxL2FetchGranularity: 32 / 64 / 128 bytes): the gather pass reads 80-byte rows at
+    // random, so everything the memory system fetches beyond the touched sectors is waste
+    if (const char *e = getenv("SDPLRP_L2_FETCH")) {
+        if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoll(e)) != cudaSuccess) cudaGetLastError();
+    }
     // Experiment knob only: an L2 set-aside for evict_last lines (cudaLimitPersistingL2CacheSize).  Measured on C5: a
     // set-aside of the maximum 79 MB slows every streaming kernel 1.8x (1.34 -> 2.46 ms for an 8.8 GB pass) and does
     // not speed the gather pass up, so the library leaves the device default alone unless asked to.
@@ -148,6 +153,13 @@ int32_t sdplrp_create(int32_t device, int32_t rank, int32_t world, const void *n
     }
     *out = h;
     return SDPLRP_OK;
+}
+
+// doubles to allocate for an n x r factor: with equal row blocks the last block is padded to block_rows rows so that the
+// in-place all-gather (comm.cu) stays inside the allocation
+static i64 mat_capacity(const sdplrp_handle *h, int r) {
+    const i64 rows = h->equal_blocks ? std::max<i64>(h->n, (i64)h->world * h->block_rows) : h->n;
+    return rows * (i64)r;
 }
 
 static void free_state(sdplrp_handle *h) {
@@ -288,7 +300,7 @@ int32_t sdplrp_set_rank(sdplrp_handle *h, int32_t r, int32_t numlbfgsvecs) {
     if (r < 1 || numlbfgsvecs < 0 || numlbfgsvecs > kMaxHist) return fail(h, SDPLRP_ERR_ARG, "set_rank: bad rank / history length");
     CUDA_TRY(h, cudaSetDevice(h->device));
     free_state(h);
-    const i64 N = h->n * (i64)r;
+    const i64 N = mat_capacity(h, r);
     SDP_CHECK(dev_alloc(h, &h->R, N)); SDP_CHECK(dev_alloc(h, &h->G, N)); SDP_CHECK(dev_alloc(h, &h->D, N));
     if (h->obj_mat >= 0) { SDP_CHECK(dev_alloc(h, &h->CR, N)); SDP_CHECK(dev_alloc(h, &h->CD, N)); }
     for (int j = 0; j < numlbfgsvecs; j++) { SDP_CHECK(dev_alloc(h, &h->Sh[j], N)); SDP_CHECK(dev_alloc(h, &h->Yh[j], N)); }
@@ -326,7 +338,7 @@ int32_t sdplrp_get_obj(sdplrp_handle *h, double *obj) {
 }
 
 static int32_t lazy_scratch(sdplrp_handle *h, int id) {
-    const i64 N = h->n * (i64)h->r;
+    const i64 N = mat_capacity(h, h->r);
     if (id == SDPLRP_MAT_W0 && !h->W0) { SDP_CHECK(dev_alloc(h, &h->W0, N)); CUDA_TRY(h, cudaMemset(h->W0, 0, (size_t)N * 8)); }
     if (id == SDPLRP_MAT_W1 && !h->W1) { SDP_CHECK(dev_alloc(h, &h->W1, N)); CUDA_TRY(h, cudaMemset(h->W1, 0, (size_t)N * 8)); }
     return SDPLRP_OK;

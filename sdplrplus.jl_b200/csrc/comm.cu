@@ -24,6 +24,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -43,6 +44,7 @@ bool nccl_bind() {
     BIND(CommDestroy, "ncclCommDestroy");
     BIND(AllReduce, "ncclAllReduce");
     BIND(Broadcast, "ncclBroadcast");
+    BIND(AllGather, "ncclAllGather");
     BIND(GroupStart, "ncclGroupStart");
     BIND(GroupEnd, "ncclGroupEnd");
     BIND(GetErrorString, "ncclGetErrorString");
@@ -56,6 +58,7 @@ bool nccl_bind() {
 #define ncclCommDestroy g_nccl.CommDestroy
 #define ncclAllReduce g_nccl.AllReduce
 #define ncclBroadcast g_nccl.Broadcast
+#define ncclAllGather g_nccl.AllGather
 #define ncclGroupStart g_nccl.GroupStart
 #define ncclGroupEnd g_nccl.GroupEnd
 #define ncclGetErrorString g_nccl.GetErrorString
@@ -173,6 +176,12 @@ void comm_mark_full(sdplrp_handle *h, int mat_id) {
 static int32_t allgather_rows(sdplrp_handle *h, double *p) {
     SectionScope sc(h, SDPLRP_SEC_COMM);
     ncclComm_t comm = (ncclComm_t)h->nccl;
+    if (h->equal_blocks) {
+        // equal row blocks (the matrices carry world*block_rows rows of capacity): one in-place all-gather
+        const size_t cnt = (size_t)h->block_rows * h->r;
+        NCCL_TRY(h, ncclAllGather(p + (size_t)h->rank * cnt, p, cnt, ncclDouble, comm, h->stream));
+        return SDPLRP_OK;
+    }
     NCCL_TRY(h, ncclGroupStart());
     for (int q = 0; q < h->world; q++) {
         const i64 off = h->row_starts[(size_t)q] * h->r;

@@ -85,6 +85,8 @@ struct sdplrp_handle {
     // gathered factor are contiguous and the row classes are ranges.  Invisible at the ABI: uploads and
     // downloads of anything indexed by vertex go through perm / iperm.
     bool relabeled = false;
+    bool equal_blocks = false;                           // ... and ranks 0..P-2 hold exactly block_rows rows (in-place ncclAllGather)
+    i64 block_rows = 0;
     bool dealt = false;                                  // multi-GPU: row blocks fixed by the round-robin deal of the relabeling
     int relabel_mode = -1;                               // -1 auto, 0 off, 1 on (sdplrp_set_option "relabel")
     int *perm = nullptr, *iperm = nullptr;               // n: internal label of reference vertex / its inverse

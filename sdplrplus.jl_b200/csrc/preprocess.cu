@@ -383,12 +383,21 @@ __global__ void k_deg_key(i64 n, const int *__restrict__ ptr, unsigned *__restri
 // multi-GPU: deal the degree-sorted vertices round-robin to the P ranks and lay the ranks' shares out one after the
 // other, so that every rank's contiguous row block has the same mix of hub and tail rows (nonzeros AND rows balanced:
 // the phases of an iteration are separated by collectives, so each phase must balance, not just their sum)
-__global__ void k_deal_rows(i64 n, int P, const int *__restrict__ sorted, int *__restrict__ dealt) {
+__global__ void k_deal_rows(i64 n, int P, i64 B, i64 lastT, int rem, bool equal, const int *__restrict__ sorted,
+                            int *__restrict__ dealt) {
     for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < n; k += (i64)gridDim.x * blockDim.x) {
-        const int p = (int)(k % P);
-        i64 start = 0;
-        for (int q = 0; q < p; q++) start += (n - q + P - 1) / P;
-        dealt[start + k / P] = sorted[k];
+        int p = (int)(k % P);
+        i64 slot = k / P;
+        if (equal) {
+            // equal blocks of B = ceil(n/P) rows for ranks 0..P-2 (one in-place ncclAllGather moves a factor): the ranks the
+            // plain deal leaves one row short take the last (lowest-degree) rows of the last rank
+            if (rem != 0 && p == P - 1 && slot >= lastT) { p = rem + (int)(slot - lastT); slot = B - 1; }
+            dealt[(i64)p * B + slot] = sorted[k];
+        } else {
+            i64 start = 0;
+            for (int q = 0; q < p; q++) start += (n - q + P - 1) / P;
+            dealt[start + slot] = sorted[k];
+        }
     }
 }
 __global__ void k_invert_perm(i64 n, const int *__restrict__ iperm, int *__restrict__ perm) {
@@ -533,7 +542,7 @@ void pre_free(sdplrp_handle *h) {
     if (h->full_ptr == h->ref_full_ptr) { h->full_ptr = nullptr; h->full_idx = nullptr; }  // aliases when not relabeled
     dev_free(&h->full_ptr); dev_free(&h->full_idx); dev_free(&h->ref_full_ptr); dev_free(&h->ref_full_idx);
     dev_free(&h->perm); dev_free(&h->iperm); dev_free(&h->i2r); dev_free(&h->r2i);
-    h->relabeled = false; h->dealt = false;
+    h->relabeled = false; h->dealt = false; h->equal_blocks = false;
     dev_free(&h->mapped); dev_free(&h->S); dev_free(&h->matptr); dev_free(&h->mat_gid); dev_free(&h->ent_slot);
     dev_free(&h->ent_row); dev_free(&h->ent_col); dev_free(&h->ent_one); dev_free(&h->ent_two);
     dev_free(&h->long_mat); dev_free(&h->long_chunk_ptr); dev_free(&h->chunk_mat); dev_free(&h->chunk_part);
@@ -670,9 +679,17 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
             if (h->world > 1) {
                 int *dealt = tmp.get<int>(h, n, &rc);
                 if (rc) return rc;
-                k_deal_rows<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, h->world, h->iperm, dealt); KLAUNCH(h);
+                const int P = h->world;
+                const i64 B = (n + P - 1) / P;
+                const int rem = (int)(n % P);
+                const i64 lastT = n - (i64)(P - 1) * B;   // rows of the last rank when all others hold exactly B
+                h->equal_blocks = lastT >= 1;
+                h->block_rows = B;
+                k_deal_rows<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, P, B, lastT, rem, h->equal_blocks, h->iperm, dealt); KLAUNCH(h);
                 CUDA_TRY(h, cudaMemcpyAsync(h->iperm, dealt, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
-                for (int q = 0; q < h->world; q++) h->row_starts[(size_t)q + 1] = h->row_starts[(size_t)q] + (n - q + h->world - 1) / h->world;
+                for (int q = 0; q < P; q++)
+                    h->row_starts[(size_t)q + 1] = h->equal_blocks ? std::min<i64>(n, (i64)(q + 1) * B)
+                                                                     : h->row_starts[(size_t)q] + (n - q + P - 1) / P;
                 h->dealt = true;
             }
             k_invert_perm<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, h->iperm, h->perm); KLAUNCH(h);

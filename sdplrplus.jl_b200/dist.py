@@ -79,10 +79,19 @@ def balanced_row_blocks(rowptr, world):
     return np.asarray(starts, dtype=np.int64)
 
 
+def _equal_block_params(n, world):
+    B = (n + world - 1) // world
+    last = n - (world - 1) * B
+    return B, last, n % world
+
+
 def dealt_row_starts(n, world):
     """Row blocks of the multi-GPU layout of relabelled (skewed) patterns -- the same rule as k_deal_rows() in
-    csrc/preprocess.cu: the degree-sorted vertices are dealt round-robin to the ranks, rank q owns
-    ceil((n - q) / world) consecutive internal rows."""
+    csrc/preprocess.cu: the degree-sorted vertices are dealt round-robin to the ranks; ranks 0..world-2 hold exactly
+    B = ceil(n / world) rows (so one in-place ncclAllGather moves a factor), the last rank the remainder."""
+    B, last, _ = _equal_block_params(n, world)
+    if last >= 1:
+        return np.asarray([min(n, q * B) for q in range(world)] + [n], dtype=np.int64)
     starts = [0]
     for q in range(world):
         starts.append(starts[-1] + (n - q + world - 1) // world)
@@ -90,13 +99,20 @@ def dealt_row_starts(n, world):
 
 
 def deal_order(sorted_vertices, world):
-    """Internal order produced by the deal: position k of the degree-sorted list goes to rank k % world, slot k // world."""
+    """Internal order produced by the deal: position k of the degree-sorted list goes to rank k % world, slot k // world;
+    the ranks this leaves one row short of B take the last (lowest-degree) rows of the last rank."""
     sorted_vertices = np.asarray(sorted_vertices)
     n = sorted_vertices.size
+    B, last, rem = _equal_block_params(n, world)
     starts = dealt_row_starts(n, world)
     k = np.arange(n, dtype=np.int64)
+    p, slot = k % world, k // world
+    if last >= 1 and rem != 0:
+        move = (p == world - 1) & (slot >= last)
+        p = np.where(move, rem + (slot - last), p)
+        slot = np.where(move, B - 1, slot)
     out = np.empty_like(sorted_vertices)
-    out[starts[k % world] + k // world] = sorted_vertices
+    out[starts[p] + slot] = sorted_vertices
     return out
 
 

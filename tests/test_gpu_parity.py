@@ -231,6 +231,35 @@ def test_rank_sweep(sp, oracle_mod, handle, r):
     _relclose(ge.linesearch_coeffs(), oe.linesearch_coeffs(), 1e-11, "bq")
 
 
+@pytest.mark.parametrize("r", [3, 10, 20, 33])
+def test_rank_sweep_all_row_classes(sp, oracle_mod, handle, r):
+    """runtime rank on a skewed graph whose rows fall into all three classes of the gather kernels (<= 32 nonzeros:
+    lane group per row, <= 512: warp per row, longer: 512-nonzero chunks + ordered combine), with auto-relabeling"""
+    P = sp.problems
+    G = P.powerlaw_graph(4000, 60000, 3, exponent=2.1)      # max degree ~2400, 13 rows > 512, ~465 rows in (32, 512]
+    C, As, bs = P.maxcut(G)
+    data = sp.SDPData(C, As, bs)
+    Rt0 = 2 * np.random.default_rng(r).random((data.n, r)) - 1
+    ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, r)
+    _relclose(ge.fg(), oe.fg(), 1e-11, "fg")
+    _relclose(ge.get_G(), oe.get_G(), 1e-12, "G")
+    D = -oe.get_G(); ge.set_D(D); oe.set_D(D)
+    bq = oe.linesearch_coeffs()
+    _relclose(ge.linesearch_coeffs(), bq, 1e-11, "bq")
+    alpha, _ = sp.pick_alpha(bq, 1.0)
+    objg, gn2, pn2 = ge.step_g(alpha)
+    objo = oe.step(alpha); ogn2, opn2 = oe.g()
+    _relclose([objg, math.sqrt(gn2), math.sqrt(pn2)], [objo, math.sqrt(ogn2), math.sqrt(opn2)], 1e-10, "step_g")
+    _relclose(ge.get_G(), oe.get_G(), 1e-10, "G after the step")
+    # seam-level product with the full S through the same row classes
+    y = np.concatenate([np.linspace(-1.0, 1.0, data.m), [1.0]])
+    handle._check(handle.lib.sdplrp_At_preprocess(handle._h, sp._lib._f64(y)[1]))
+    handle.upload_mat(sp._lib.MAT_W0, Rt0)
+    handle._check(handle.lib.sdplrp_At_left(handle._h, sp._lib.MAT_W0, sp._lib.MAT_W1))
+    S = y[data.m] * C + __import__("scipy.sparse").sparse.diags(y[: data.m])   # MaxCut: A_i = e_i e_i'
+    _relclose(handle.download_mat(sp._lib.MAT_W1), S @ Rt0, 1e-11, "At_left")
+
+
 @pytest.mark.parametrize("fam", FAMS + ["ineq_0.05"])
 def test_step_g_fused(sp, oracle_mod, handle, fam):
     """sdplrp_step_g (one fused row pass: step, residual recurrence, y, gradient, both norms) against the

@@ -10,6 +10,7 @@
  *   linesearch! / linesearch_armijo!           src/linesearch.jl:4-191
  *   lbfgs_dir! / lbfgs_update! / lbfgs_clear!  src/lbfgs.jl:52-149
  *   approx_mineigval_lanczos / dual_obj        src/coreop.jl:376-415,461-514
+ *   SDP_S_eigval / DIMACS_errors               src/coreop.jl:351-374,417-453
  *   preprocess_sparsecons / SolverAuxiliary    src/preprocess.jl:24-169, src/structs.jl:296-361
  * (file:line relative to the reference checkout).
  *
@@ -196,6 +197,27 @@ int32_t sdplrp_tridiag_mineig(const double *d, const double *e, int64_t k, doubl
  * Lanczos steps, dual = -y'b + trace_bound*min(lambda_min,0); src/coreop.jl:376-415 */
 int32_t sdplrp_dual_obj(sdplrp_handle *h, double trace_bound, int64_t iter, const double *v0, uint64_t seed,
                         double *dual_value, double *mineig, int64_t *lanczos_steps);
+
+/* ---- high-precision eigenvalue path and DIMACS errors ------------------ */
+/* SDP_S_eigval(var, aux, nevs, true; which=:SA, ncv, tol, maxiter) (src/coreop.jl:351-374): the nevs smallest
+ * algebraic eigenvalues of the S last assembled (+ low-rank terms), ascending, by thick-restart Lanczos on the device
+ * (the restarted-Lanczos contract of GenericArpack.symeigs: Ritz pair i is accepted when its residual bound
+ * |beta_m y_m,i| <= tol * max(eps^(2/3), |theta_i + 1|); tol <= 0 means machine precision; maxiter bounds the number of
+ * restarts; nevs < ncv <= min(n, 512) is enforced by clamping ncv).  v0 (n, host) is the start vector, NULL draws a
+ * seeded Gaussian on the device.  bounds / matvecs / restarts may be NULL. */
+int32_t sdplrp_S_eigval(sdplrp_handle *h, int64_t nevs, int64_t ncv, double tol, int64_t maxiter, const double *v0, uint64_t seed,
+                        double *eigvals, double *bounds, int64_t *matvecs, int64_t *restarts);
+/* dual_obj(data, var, aux, trace_bound, iter; highprecision=true): y, S, then SDP_S_eigval with ncv = min(100, n),
+ * tol = 1e-6, maxiter = 10^6; src/coreop.jl:376-415 */
+int32_t sdplrp_dual_obj_highprecision(sdplrp_handle *h, double trace_bound, const double *v0, uint64_t seed, double *dual_value,
+                                      double *mineig, int64_t *matvecs);
+/* DIMACS_errors(data, var, aux) -> errs[6] (src/coreop.jl:417-453); normb = ||b||_2, normC = ||C||_F are the caller's
+ * (src/sdplr.jl:165-166).  Like the reference it overwrites y with -lambda (copy2y_lambda!) and S with the matching
+ * matrix, and error 6 takes the sparse part of S only. */
+int32_t sdplrp_dimacs_errors(sdplrp_handle *h, double normb, double normC, const double *v0, uint64_t seed, double errs[6]);
+/* host helper: eigen-decomposition of a small dense symmetric matrix A (k x k row-major): ascending eigenvalues ev[k],
+ * eigenvectors as the columns of Q (k x k row-major, may be NULL).  The projected problem of the restarted Lanczos. */
+int32_t sdplrp_dense_symeig(const double *A, int64_t k, double *ev, double *Q);
 
 /* ---- introspection ---------------------------------------------------- */
 /* kernel-group sections timed with CUDA events on the handle's stream */

@@ -84,6 +84,9 @@ def load():
         "orc_lanczos": ([V, C.c_int64, _p_f64, _p_i64, _p_f64, _p_f64], C.c_double),
         "orc_dual_obj": ([V, C.c_double, C.c_int64, _p_f64, _p_f64, _p_i64], C.c_double),
         "orc_dual_update": ([V], None),
+        "orc_copy2y_lambda": ([V], None),
+        "orc_dual_value": ([V, C.c_double, C.c_double], C.c_double),
+        "orc_dimacs_errors": ([V, C.c_double, C.c_double, C.c_double, _p_f64], None),
         "orc_symlowrank_norm": ([C.c_int64, C.c_int64, _p_f64, _p_f64, C.c_int], C.c_double),
     }
     for name, (args, res) in sig.items():
@@ -225,6 +228,29 @@ class Oracle:
         return lam, a, b, it.value
 
 
+def S_eigval(o, nevs=1, ncv=None, tol=0.0, maxiter=10 ** 6, v0=None):
+    """SDP_S_eigval (src/coreop.jl:351-374) on the oracle's current S.
+
+    The arithmetic lives in a third-party dependency that is not under /root/reference: GenericArpack.jl
+    (Project.toml compat "0.2"), a Julia port of ARPACK's dsaupd/dseupd, i.e. the implicitly restarted Lanczos method
+    (Lehoucq-Sorensen-Yang) with exact shifts, Ritz estimate rule |beta_m y_m,i| <= tol*max(eps^(2/3), |theta_i|), and
+    tol = 0 meaning machine precision.  scipy.sparse.linalg.eigsh binds ARPACK itself, so the same published algorithm
+    is applied to the same operator x -> S*x + x with the same (which, ncv, tol); small problems (n <= 3, where ARPACK
+    needs nev < ncv <= n) fall back to the dense eigenvalues.  Parity is to solver tolerance (the start vector of
+    GenericArpack is random and not reproducible)."""
+    import scipy.sparse.linalg as sla
+    n = o.n
+    ncv = min(100, n) if ncv is None else min(int(ncv), n)
+    if n <= 3 or nevs >= n - 1:
+        S = np.column_stack([o.At_right(e) for e in np.eye(n)])
+        return np.sort(np.linalg.eigvalsh(0.5 * (S + S.T)))[:nevs]
+    op = sla.LinearOperator((n, n), matvec=lambda x: o.At_right(np.asarray(x, np.float64).reshape(-1)) + np.asarray(x).reshape(-1),
+                            dtype=np.float64)
+    ev = sla.eigsh(op, k=int(nevs), which="SA", ncv=max(ncv, int(nevs) + 1), tol=float(tol), maxiter=int(maxiter), v0=v0,
+                   return_eigenvectors=False)
+    return np.sort(np.real(ev)) - 1.0
+
+
 class OracleEngine:
     """Engine interface of sdplrplus.jl_b200.solver (see B200Engine) on the CPU oracle."""
 
@@ -327,6 +353,22 @@ class OracleEngine:
         lam = C.c_double(); q = C.c_int64()
         d = self.lib.orc_dual_obj(self.o.ctx, float(trace_bound), int(it), _f(v0), C.byref(lam), C.byref(q))
         return d, lam.value, q.value
+
+    def dual_obj_highprecision(self, trace_bound, v0=None, seed=0):
+        """dual_obj(...; highprecision=true) (src/coreop.jl:376-415)"""
+        self.lib.orc_copy2y(self.o.ctx)
+        self.lib.orc_At_preprocess(self.o.ctx)
+        lam = float(S_eigval(self.o, 1, min(100, self.n), 1e-6, 10 ** 6, v0)[0])
+        return self.lib.orc_dual_value(self.o.ctx, float(trace_bound), lam), lam, 0
+
+    def dimacs_errors(self, normb, normC, v0=None, seed=0):
+        """DIMACS_errors (src/coreop.jl:426-453)"""
+        self.lib.orc_copy2y_lambda(self.o.ctx)
+        self.lib.orc_At_preprocess(self.o.ctx)
+        lam = float(S_eigval(self.o, 1, min(100, self.n), 0.0, 10 ** 6, v0)[0])
+        errs = np.zeros(6)
+        self.lib.orc_dimacs_errors(self.o.ctx, float(normb), float(normC), lam, _f(errs))
+        return errs
 
     def dual_update(self):
         self.lib.orc_dual_update(self.o.ctx)

@@ -911,6 +911,44 @@ double orc_dual_obj(orc_ctx *c, double trace_bound, i64 iter, const double *v0, 
     return -s + trace_bound * (lam < 0.0 ? lam : 0.0);
 }
 
+/* copy2y_lambda! (src/coreop.jl:238-246): y_i = -lambda_i, y_{m+1} = 1 */
+void orc_copy2y_lambda(orc_ctx *c) {
+    for (i64 i = 0; i < c->m; i++) c->y[i] = -c->lambda[i];
+    c->y[c->m] = 1.0;
+}
+
+/* dual value of dual_obj (src/coreop.jl:407-412) for a lambda_min(S) obtained elsewhere: the highprecision branch
+ * (:386-400) calls SDP_S_eigval = GenericArpack.symeigs (third-party, see pyoracle.S_eigval) */
+double orc_dual_value(const orc_ctx *c, double trace_bound, double mineig) {
+    double s = 0.0;
+    for (i64 i = 0; i < c->m; i++) s += c->y[i] * c->b[i];
+    return -s + trace_bound * (mineig < 0.0 ? mineig : 0.0);
+}
+
+/* DIMACS_errors (src/coreop.jl:426-453) after `copy2y_lambda!; At_preprocess!` (:435-436), for the smallest
+ * eigenvalue `mineig` of S delivered by SDP_S_eigval (:438-440).  err2 = err3 = 0 (:432-433); err6 takes the sparse
+ * part of S only, `dot(var.Rt, var.Rt * aux.sparse_S)` (:448-451). */
+void orc_dimacs_errors(const orc_ctx *c, double normb, double normC, double mineig, double *errs) {
+    double v2 = 0.0, lb = 0.0, xz = 0.0;
+    for (i64 i = 0; i < c->m; i++) { v2 += c->pvio_raw[i] * c->pvio_raw[i]; lb += c->lambda[i] * c->b[i]; }
+    if (c->nA > 0) {
+        for (i64 j = 0; j < c->n; j++)
+            for (i64 k = c->full_colptr[j]; k < c->full_colptr[j + 1]; k++) {
+                const double *x = c->Rt + c->full_rowval[k] * c->r, *yj = c->Rt + j * c->r;
+                double d = 0.0;
+                for (i64 i = 0; i < c->r; i++) d += x[i] * yj[i];
+                xz += d * c->S[k];
+            }
+    }
+    double den = 1.0 + fabs(c->obj) + fabs(lb);
+    errs[0] = sqrt(v2) / (1.0 + normb);
+    errs[1] = 0.0;
+    errs[2] = 0.0;
+    errs[3] = (mineig < 0.0 ? -mineig : 0.0) / (1.0 + normC);
+    errs[4] = (c->obj - lb) / den;
+    errs[5] = xz / den;
+}
+
 /* dual update (src/sdplr.jl:358-362) */
 void orc_dual_update(orc_ctx *c) {
     for (i64 i = 0; i < c->m; i++) {

@@ -66,6 +66,10 @@ _SIGNATURES = {
     "sdplrp_lanczos": [_H, C.c_int64, _p_f64, C.c_uint64, C.c_int32, _p_f64, _p_f64, _p_i64],
     "sdplrp_tridiag_mineig": [_p_f64, _p_f64, C.c_int64, _p_f64],
     "sdplrp_dual_obj": [_H, C.c_double, C.c_int64, _p_f64, C.c_uint64, _p_f64, _p_f64, _p_i64],
+    "sdplrp_S_eigval": [_H, C.c_int64, C.c_int64, C.c_double, C.c_int64, _p_f64, C.c_uint64, _p_f64, _p_f64, _p_i64, _p_i64],
+    "sdplrp_dual_obj_highprecision": [_H, C.c_double, _p_f64, C.c_uint64, _p_f64, _p_f64, _p_i64],
+    "sdplrp_dimacs_errors": [_H, C.c_double, C.c_double, _p_f64, C.c_uint64, _p_f64],
+    "sdplrp_dense_symeig": [_p_f64, C.c_int64, _p_f64, _p_f64],
     "sdplrp_set_profiling": [_H, C.c_int32],
     "sdplrp_section_times": [_H, _p_f64, _p_i64],
     "sdplrp_launch_count": [_H, _p_i64],
@@ -373,6 +377,37 @@ class Handle:
                                               C.byref(s)))
         return d.value, e.value, s.value
 
+    def S_eigval(self, nevs=1, ncv=None, tol=0.0, maxiter=10 ** 6, v0=None, seed=0):
+        """SDP_S_eigval(var, aux, nevs, true; which=:SA, ncv, tol, maxiter) on the S last assembled ->
+        (eigenvalues ascending, residual bounds, matvecs, restarts)"""
+        ncv = min(100, self.n) if ncv is None else int(ncv)
+        ev, bd = np.zeros(int(nevs)), np.zeros(int(nevs))
+        mv, rs = C.c_int64(), C.c_int64()
+        pv = None
+        if v0 is not None:
+            v0, pv = _f64(v0)
+            assert v0.size == self.n
+        self._check(self.lib.sdplrp_S_eigval(self._h, int(nevs), ncv, float(tol), int(maxiter), pv, int(seed),
+                                              ev.ctypes.data_as(_p_f64), bd.ctypes.data_as(_p_f64), C.byref(mv), C.byref(rs)))
+        return ev, bd, mv.value, rs.value
+
+    def dual_obj_highprecision(self, trace_bound, v0=None, seed=0):
+        d, e, s = C.c_double(), C.c_double(), C.c_int64()
+        pv = None
+        if v0 is not None:
+            v0, pv = _f64(v0)
+        self._check(self.lib.sdplrp_dual_obj_highprecision(self._h, float(trace_bound), pv, int(seed), C.byref(d), C.byref(e),
+                                                            C.byref(s)))
+        return d.value, e.value, s.value
+
+    def dimacs_errors(self, normb, normC, v0=None, seed=0):
+        errs = np.zeros(6)
+        pv = None
+        if v0 is not None:
+            v0, pv = _f64(v0)
+        self._check(self.lib.sdplrp_dimacs_errors(self._h, float(normb), float(normC), pv, int(seed), errs.ctypes.data_as(_p_f64)))
+        return errs
+
     SECTIONS = ["lbfgs_dir", "ls_pass", "ls_coeff", "step", "s_assemble", "spmm", "norms", "lbfgs_update", "a_uu", "f_finish",
                 "lanczos", "comm", "grad", "tail"]
 
@@ -405,3 +440,14 @@ def tridiag_mineig(d, e):
     if rc != 0:
         raise SdplrpError(rc, "tridiag_mineig: bad argument")
     return out.value
+
+
+def dense_symeig(A):
+    """Ascending eigenvalues and eigenvectors (columns) of a small dense symmetric matrix (host helper of the ABI)."""
+    A, pa = _f64(A)
+    k = A.shape[0]
+    ev, Q = np.zeros(k), np.zeros((k, k))
+    rc = load().sdplrp_dense_symeig(pa, k, ev.ctypes.data_as(_p_f64), Q.ctypes.data_as(_p_f64))
+    if rc != 0:
+        raise SdplrpError(rc, "dense_symeig: bad argument")
+    return ev, Q

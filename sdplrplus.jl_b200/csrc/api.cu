@@ -745,6 +745,85 @@ int32_t sdplrp_dual_obj(sdplrp_handle *h, double trace_bound, int64_t iter, cons
     return SDPLRP_OK;
 }
 
+int32_t sdplrp_dense_symeig(const double *A, int64_t k, double *ev, double *Q) {
+    if (!A || !ev || k < 1 || k > 4096) return SDPLRP_ERR_ARG;
+    dense_symeig_host(A, k, ev, Q);
+    return SDPLRP_OK;
+}
+
+// SDP_S_eigval(var, aux, nevs, true; which=:SA, ncv, tol, maxiter) (src/coreop.jl:351-374) on the S last assembled
+int32_t sdplrp_S_eigval(sdplrp_handle *h, int64_t nevs, int64_t ncv, double tol, int64_t maxiter, const double *v0, uint64_t seed,
+                        double *eigvals, double *bounds, int64_t *matvecs, int64_t *restarts) {
+    REQUIRE_H(h); REQUIRE_PRE(h);
+    if (!eigvals) return fail(h, SDPLRP_ERR_ARG, "S_eigval: eigvals is null");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!h->S_current) SDP_CHECK(grad_assemble_S(h));
+    i64 mv = 0, rs = 0;
+    {
+        SectionScope sc(h, SDPLRP_SEC_LANCZOS);
+        SDP_CHECK(lz_eigs(h, nevs, ncv, tol, maxiter, v0, seed, eigvals, bounds, &mv, &rs));
+    }
+    if (matvecs) *matvecs = mv;
+    if (restarts) *restarts = rs;
+    return SDPLRP_OK;
+}
+
+// dual_obj(...; highprecision=true) (src/coreop.jl:376-415): ncv = min(100, n), tol = 1e-6, maxiter = 10^6
+int32_t sdplrp_dual_obj_highprecision(sdplrp_handle *h, double trace_bound, const double *v0, uint64_t seed, double *dual_value,
+                                      double *mineig, int64_t *matvecs) {
+    REQUIRE_H(h); REQUIRE_PRE(h);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(grad_form_y(h));
+    SDP_CHECK(grad_assemble_S(h));
+    double lam = 0.0;
+    i64 mv = 0;
+    {
+        SectionScope sc(h, SDPLRP_SEC_LANCZOS);
+        SDP_CHECK(lz_eigs(h, 1, std::min<i64>(100, h->n), 1e-6, 1000000, v0, seed, &lam, nullptr, &mv, nullptr));
+    }
+    double yb = 0.0;
+    SDP_CHECK(vec_dual_dot(h, &yb));
+    if (dual_value) *dual_value = yb + trace_bound * std::min(lam, 0.0);
+    if (mineig) *mineig = lam;
+    if (matvecs) *matvecs = mv;
+    return SDPLRP_OK;
+}
+
+// DIMACS_errors (src/coreop.jl:426-453).  Leaves y = -lambda (copy2y_lambda!) and the matching S behind, as the
+// reference does; err6 uses the sparse part of S only, as the reference does (`var.Rt * aux.sparse_S`).
+int32_t sdplrp_dimacs_errors(sdplrp_handle *h, double normb, double normC, const double *v0, uint64_t seed, double errs[6]) {
+    REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
+    if (!errs) return fail(h, SDPLRP_ERR_ARG, "dimacs_errors: errs is null");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    double raw2 = 0.0, lamb = 0.0, obj = 0.0;
+    SDP_CHECK(vec_dimacs_sums(h, &raw2, &lamb));
+    SDP_CHECK(fetch_scalars(h, SC_OBJ, 1));
+    obj = h->hscal[SC_OBJ];
+    SDP_CHECK(vec_copy2y_lambda(h));
+    SDP_CHECK(grad_assemble_S(h));
+    double lam = 0.0;
+    {
+        SectionScope sc(h, SDPLRP_SEC_LANCZOS);
+        SDP_CHECK(lz_eigs(h, 1, std::min<i64>(100, h->n), 0.0, 1000000, v0, seed, &lam, nullptr, nullptr, nullptr));
+    }
+    SDP_CHECK(lazy_scratch(h, SDPLRP_MAT_W0));
+    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
+    SDP_CHECK(grad_spmm_sparse(h, h->R, h->W0, 1.0));
+    comm_mark_partial(h, SDPLRP_MAT_W0);
+    SDP_CHECK(lb_dot(h, h->R, h->W0, SC_LANCZOS + 9));
+    SDP_CHECK(comm_reduce_scalars(h, SC_LANCZOS + 9, 1));
+    SDP_CHECK(fetch_scalars(h, SC_LANCZOS + 9, 1));
+    const double xz = h->hscal[SC_LANCZOS + 9];
+    const double den = 1.0 + fabs(obj) + fabs(lamb);
+    errs[0] = sqrt(raw2) / (1.0 + normb);
+    errs[1] = 0.0;
+    errs[2] = 0.0;  // X = RR', Z = C - A*(y): errors 2 and 3 vanish by construction
+    errs[3] = std::max(0.0, -lam) / (1.0 + normC);
+    errs[4] = (obj - lamb) / den;
+    errs[5] = xz / den;
+    return SDPLRP_OK;
+}
+
 int32_t sdplrp_set_profiling(sdplrp_handle *h, int32_t on) {
     REQUIRE_H(h);
     h->prof = on != 0;

@@ -322,6 +322,7 @@ int32_t lr_scratch(sdplrp_handle *h);
 int32_t grad_form_y(sdplrp_handle *h);                          // copy2y_lambda_sub_pvio!
 int32_t grad_assemble_S(sdplrp_handle *h);                      // At_preprocess! from device y
 int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bool want_norm);  // Y = scale*X*S (+low rank)
+int32_t grad_spmm_sparse(sdplrp_handle *h, const double *X, double *Y, double scale);           // Y = scale*X*S, sparse part only
 int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double *Z, double *sums6);  // Y = C*X, sums <X,Y>, <X,Z>
 int32_t grad_obj_slots(sdplrp_handle *h, const double *sums6, double *a_rd_m, double *a_dd_m);
 int32_t grad_hot(sdplrp_handle *h);                             // G = 2*(y_obj*CR + S_dyn*R + low rank), ||G||^2
@@ -345,6 +346,8 @@ int32_t vec_pnorm2(sdplrp_handle *h);        // ||max(raw,lb)||^2 -> SC_PNORM2
 int32_t vec_dual_update(sdplrp_handle *h);
 int32_t vec_armijo(sdplrp_handle *h, const double *alphas, int k, double *L, double *slope);
 int32_t vec_dual_dot(sdplrp_handle *h, double *out);  // -y[1:m]'b
+int32_t vec_copy2y_lambda(sdplrp_handle *h);          // copy2y_lambda!: y_i = -lambda_i, y_{m+1} = 1
+int32_t vec_dimacs_sums(sdplrp_handle *h, double *raw_norm2, double *lambda_b);  // ||raw[1:m]||^2, lambda'b
 
 // dense BLAS-1 fusions (lbfgs.cu)
 int32_t lb_dir(sdplrp_handle *h);                   // lbfgs_dir! + descent -> SC_DESCENT
@@ -354,11 +357,16 @@ int32_t lb_axpy(sdplrp_handle *h, double alpha, const double *x, double *y);  //
 int32_t lb_axpy2(sdplrp_handle *h, double alpha, const double *x1, double *y1, const double *x2, double *y2);
 int32_t lb_neg_copy(sdplrp_handle *h);              // G = -G ; D = G
 int32_t lb_norm2(sdplrp_handle *h, const double *x, int slot);
+int32_t lb_dot(sdplrp_handle *h, const double *x, const double *y, int slot);   // dscal[slot] = <x,y> over the owned rows
 
 // Lanczos (lanczos.cu)
 int32_t lz_run(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, int reorth, double *alpha,
                double *beta, i64 *iters);
 double tridiag_mineig_host(const double *d, const double *e, i64 k);
+void dense_symeig_host(const double *A, i64 m, double *ev, double *Q);  // small dense symmetric eigenproblem (cyclic Jacobi)
+// thick-restart Lanczos for the nev smallest eigenvalues of the current S (SDP_S_eigval)
+int32_t lz_eigs(sdplrp_handle *h, i64 nev, i64 ncv, double tol, i64 maxiter, const double *v0_host, uint64_t seed, double *eigs,
+                double *bounds, i64 *matvecs, i64 *restarts);
 
 // multi-GPU plumbing (comm.cu); all no-ops when world == 1
 int32_t comm_init(sdplrp_handle *h, const void *nccl_id);

@@ -660,6 +660,12 @@ int32_t grad_triuS(sdplrp_handle *h, double *out) {
 
 // seam-level At!(Y, X): Y = scale * (X*S + sum_g y_g X B D B') over the owned rows, S as last assembled
 int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bool /*want_norm*/) {
+    SDP_CHECK(grad_spmm_sparse(h, X, Y, scale));
+    return add_lowrank(h, X, Y, scale);
+}
+
+// the sparse part alone (DIMACS error 6 of the reference leaves the low-rank terms out, src/coreop.jl:448-451)
+int32_t grad_spmm_sparse(sdplrp_handle *h, const double *X, double *Y, double scale) {
     const int r = h->r;
     if (h->nA > 0 && tile_supported(h)) {
         SDP_CHECK(tile_spmm(h, h->full_tile, h->full_ptr, h->full_idx, h->S, nullptr, X, Y, 0, scale, 0.0, nullptr, nullptr, nullptr));
@@ -671,7 +677,7 @@ int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bo
     } else {
         CUDA_TRY(h, cudaMemsetAsync(Y + h->row_lo * r, 0, (size_t)(h->row_hi - h->row_lo) * r * sizeof(double), h->stream));
     }
-    return add_lowrank(h, X, Y, scale);
+    return SDPLRP_OK;
 }
 
 // Y = C*X over the owned rows with the fused sums  out0 = <X, Y>, out1 = <X, Z>  (Z may be null)

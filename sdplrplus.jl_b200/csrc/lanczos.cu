@@ -214,6 +214,47 @@ double tridiag_mineig_host(const double *d, const double *e, i64 k) {
     return 0.5 * (lo + hi);
 }
 
+
+// w = S*v (+ the low-rank terms y_g B D B' v) on the internal vertex order and alpha_out[0] = <v, w>; every kernel is
+// guarded by the device stop flag.  S is the full pattern as last assembled; the three row classes of the pattern
+// (class lists are null when every row is short: identity) each get the lane-group width that fits their rows.
+static int32_t lz_apply(sdplrp_handle *h, const double *v, double *w, const double *stop, double *alpha_out) {
+    const i64 n = h->n;
+    cudaStream_t st = h->stream;
+    const int gs = grid_for(n, TPB, kRedBlocks);
+    const bool has_lr = !h->lr.empty();
+    double *tmp = h->dscal + SC_LANCZOS + 1;
+    if (h->nA > 0) {
+        const RowClasses &cls = h->full_cls;
+        double *parts = h->dscal + SC_LANCZOS + 2;
+        CUDA_TRY(h, cudaMemsetAsync(parts, 0, 3 * sizeof(double), st));
+        for (int c = 0; c < 3; c++) {
+            const i64 nr = cls.cnt[c];
+            if (nr <= 0) continue;
+            const int *rows = cls.list[c];
+#define LZ_SPMV(L, A) k_lz_spmv<L, A><<<grid_for(nr, TPB / L, 16 * kNumSM), TPB, 0, st>>>(rows, nr, h->full_ptr, h->full_idx, h->S, v, w, stop, h->partials, h->ticket, parts + c)
+            if (c == 0) { if (has_lr) LZ_SPMV(4, false); else LZ_SPMV(4, true); }
+            else if (c == 1) { if (has_lr) LZ_SPMV(32, false); else LZ_SPMV(32, true); }
+            else { if (has_lr) LZ_SPMV(256, false); else LZ_SPMV(256, true); }
+#undef LZ_SPMV
+            KLAUNCH(h);
+        }
+        if (!has_lr) k_lz_alpha_sum<<<1, 1, 0, st>>>(parts, 3, stop, alpha_out);
+    } else {
+        k_lz_zero<<<gs, TPB, 0, st>>>(n, w, stop);
+    }
+    KLAUNCH(h);
+    if (has_lr || h->nA <= 0) {
+        for (const LowRank &L : h->lr)
+            for (i64 k = 0; k < L.s; k++) {
+                k_lz_dot<<<gs, TPB, 0, st>>>(n, L.dB + k * n, v, stop, h->partials, h->ticket, tmp); KLAUNCH(h);
+                k_lz_lr_axpy<<<gs, TPB, 0, st>>>(n, L.dB + k * n, tmp, L.dD, (int)k, h->y, (int)L.gid, stop, w); KLAUNCH(h);
+            }
+        k_lz_dot<<<gs, TPB, 0, st>>>(n, v, w, stop, h->partials, h->ticket, alpha_out); KLAUNCH(h);
+    }
+    return SDPLRP_OK;
+}
+
 int32_t lz_run(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, int reorth, double *alpha, double *beta, i64 *iters) {
     const i64 n = h->n;
     cudaStream_t st = h->stream;
@@ -239,38 +280,9 @@ int32_t lz_run(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, in
     }
     k_lz_norm2<<<gs, TPB, 0, st>>>(n, v, h->partials, h->ticket, tmp); KLAUNCH(h);
     k_lz_div<<<gs, TPB, 0, st>>>(n, tmp, v); KLAUNCH(h);
-    const bool has_lr = !h->lr.empty();
     for (i64 i = 0; i < q; i++) {
         if (reorth) CUDA_TRY(h, cudaMemcpyAsync(h->lz_basis + (size_t)i * n, v, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        if (h->nA > 0) {
-            // three row classes of the full pattern (class lists are null when every row is short: identity)
-            const RowClasses &cls = h->full_cls;
-            double *parts = h->dscal + SC_LANCZOS + 2;
-            CUDA_TRY(h, cudaMemsetAsync(parts, 0, 3 * sizeof(double), st));
-            for (int c = 0; c < 3; c++) {
-                const i64 nr = cls.cnt[c];
-                if (nr <= 0) continue;
-                const int *rows = cls.list[c];
-#define LZ_SPMV(L, A) k_lz_spmv<L, A><<<grid_for(nr, TPB / L, 16 * kNumSM), TPB, 0, st>>>(rows, nr, h->full_ptr, h->full_idx, h->S, v, w, stop, h->partials, h->ticket, parts + c)
-                if (c == 0) { if (has_lr) LZ_SPMV(4, false); else LZ_SPMV(4, true); }
-                else if (c == 1) { if (has_lr) LZ_SPMV(32, false); else LZ_SPMV(32, true); }
-                else { if (has_lr) LZ_SPMV(256, false); else LZ_SPMV(256, true); }
-#undef LZ_SPMV
-                KLAUNCH(h);
-            }
-            if (!has_lr) k_lz_alpha_sum<<<1, 1, 0, st>>>(parts, 3, stop, ab + i);
-        } else {
-            k_lz_zero<<<gs, TPB, 0, st>>>(n, w, stop);
-        }
-        KLAUNCH(h);
-        if (has_lr || h->nA <= 0) {
-            for (const LowRank &L : h->lr)
-                for (i64 k = 0; k < L.s; k++) {
-                    k_lz_dot<<<gs, TPB, 0, st>>>(n, L.dB + k * n, v, stop, h->partials, h->ticket, tmp); KLAUNCH(h);
-                    k_lz_lr_axpy<<<gs, TPB, 0, st>>>(n, L.dB + k * n, tmp, L.dD, (int)k, h->y, (int)L.gid, stop, w); KLAUNCH(h);
-                }
-            k_lz_dot<<<gs, TPB, 0, st>>>(n, v, w, stop, h->partials, h->ticket, ab + i); KLAUNCH(h);
-        }
+        SDP_CHECK(lz_apply(h, v, w, stop, ab + i));
         k_lz_update<<<gs, TPB, 0, st>>>(n, (int)i, v, vp, w, ab, q, stop, h->partials, h->ticket); KLAUNCH(h);
         if (reorth) {
             k_lz_reorth_dots<<<(int)(i + 1), TPB, 0, st>>>(n, h->lz_basis, w, stop, coef); KLAUNCH(h);
@@ -290,5 +302,266 @@ int32_t lz_run(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, in
     if (coef) cudaFree(coef);
     for (i64 i = 0; i < q; i++) { alpha[i] = hab[(size_t)i]; beta[i] = hab[(size_t)(q + i)]; }
     *iters = hstop != 0.0 ? (i64)hstop : q;
+    return SDPLRP_OK;
+}
+
+// =====================================================================================================================
+// High-precision smallest eigenvalues of S: SDP_S_eigval (src/coreop.jl:351-374) calls GenericArpack's
+// `symeigs(op, nevs; which=:SA, ncv, tol, maxiter)` on x -> S*x + x, i.e. the implicitly restarted Lanczos method.
+// Here: THICK-RESTART Lanczos (Wu & Simon 2000), which spans the same Krylov subspaces as implicit restarting with
+// exact shifts, run entirely on the device:
+//   * the basis V (ncv+1 vectors of n doubles) stays in HBM; a Lanczos step is one SpMV (the row-class kernels of the
+//     q-step path above) plus two classical Gram-Schmidt passes against the whole basis (blocks of 8 basis vectors per
+//     streaming pass, deterministic grid reductions), so the recurrence never loses orthogonality;
+//   * alpha_j / beta_j and the breakdown flag stay in device memory: the host synchronises ONCE per restart cycle,
+//     solves the (ncv x ncv) arrowhead + tridiagonal projected problem (cyclic Jacobi) and uploads the Ritz
+//     coefficients; the basis is rotated in place by a shared-memory tiled kernel (rows are CTA-private).
+// The shift by the identity of the reference cancels exactly inside the orthogonalisation; it is applied to the
+// projected matrix on the host so that the ARPACK stopping rule  |beta_m * y_m,i| <= tol * max(eps^(2/3), |theta_i|)
+// sees the same shifted Ritz values.
+// =====================================================================================================================
+namespace {
+
+constexpr int TRL_NB = 8;     // basis vectors per Gram-Schmidt dot pass
+constexpr int TRL_ROWS = 32;  // rows per tile of the basis rotation
+
+// coef[b] = <V_b, w>, b < cnt <= TRL_NB  (V_b = basis + b*n)
+__global__ void __launch_bounds__(TPB) k_trl_dots(i64 n, const double *__restrict__ basis, int cnt, const double *__restrict__ w,
+                                                  const double *__restrict__ stop, double *partials, unsigned *ticket,
+                                                  double *__restrict__ coef) {
+    if (stop[0] != 0.0) return;
+    double acc[TRL_NB];
+#pragma unroll
+    for (int b = 0; b < TRL_NB; b++) acc[b] = 0.0;
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double wi = w[i];
+#pragma unroll
+        for (int b = 0; b < TRL_NB; b++)
+            if (b < cnt) acc[b] += basis[(size_t)b * n + i] * wi;
+    }
+    grid_sum_finalize<TRL_NB>(acc, partials, ticket, [&](double (&s)[TRL_NB]) {
+        for (int b = 0; b < cnt; b++) coef[b] = s[b];
+    });
+}
+
+// alpha_j = c1[j] + c2[j] (the two Gram-Schmidt passes)
+__global__ void k_trl_alpha(int j, const double *__restrict__ c1, const double *__restrict__ c2, const double *__restrict__ stop,
+                            double *__restrict__ ab) {
+    if (stop[0] != 0.0) return;
+    ab[j] = c1[j] + c2[j];
+}
+
+// V[:, 0:k] = V[:, 0:m] * Y (Y: m x k row-major), in place.  One CTA stages TRL_ROWS rows of all m basis vectors in
+// shared memory, then writes the k combinations of those rows back; no other CTA touches them.
+__global__ void __launch_bounds__(256) k_trl_rotate(i64 n, int m, int k, double *__restrict__ V, const double *__restrict__ Y) {
+    extern __shared__ double tile[];  // m x TRL_ROWS
+    const int row = threadIdx.x & (TRL_ROWS - 1), cg = threadIdx.x / TRL_ROWS, ncg = 256 / TRL_ROWS;
+    for (i64 base = (i64)blockIdx.x * TRL_ROWS; base < n; base += (i64)gridDim.x * TRL_ROWS) {
+        const i64 i = base + row;
+        __syncthreads();
+        for (int j = cg; j < m; j += ncg) tile[j * TRL_ROWS + row] = i < n ? V[(size_t)j * n + i] : 0.0;
+        __syncthreads();
+        for (int c = cg; c < k; c += ncg) {
+            double t = 0.0;
+            for (int j = 0; j < m; j++) t += tile[j * TRL_ROWS + row] * __ldg(Y + (size_t)j * k + c);
+            if (i < n) V[(size_t)c * n + i] = t;
+        }
+    }
+}
+
+// eigen-decomposition of a small dense symmetric matrix (cyclic Jacobi): A (m x m, row-major, destroyed) ->
+// ascending eigenvalues `ev`, eigenvectors as the COLUMNS of Q (row-major m x m)
+void jacobi_eigh(std::vector<double> &A, int m, std::vector<double> &ev, std::vector<double> &Q) {
+    Q.assign((size_t)m * m, 0.0);
+    for (int i = 0; i < m; i++) Q[(size_t)i * m + i] = 1.0;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int p = 0; p < m; p++) {
+            diag += A[(size_t)p * m + p] * A[(size_t)p * m + p];
+            for (int q = p + 1; q < m; q++) off += A[(size_t)p * m + q] * A[(size_t)p * m + q];
+        }
+        if (off <= 1e-32 * (diag + off) || off == 0.0) break;
+        for (int p = 0; p < m - 1; p++)
+            for (int q = p + 1; q < m; q++) {
+                const double apq = A[(size_t)p * m + q];
+                if (apq == 0.0) continue;
+                const double app = A[(size_t)p * m + p], aqq = A[(size_t)q * m + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < m; k++) {  // columns p, q of A
+                    const double akp = A[(size_t)k * m + p], akq = A[(size_t)k * m + q];
+                    A[(size_t)k * m + p] = c * akp - s * akq;
+                    A[(size_t)k * m + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < m; k++) {  // rows p, q of A
+                    const double apk = A[(size_t)p * m + k], aqk = A[(size_t)q * m + k];
+                    A[(size_t)p * m + k] = c * apk - s * aqk;
+                    A[(size_t)q * m + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < m; k++) {
+                    const double qkp = Q[(size_t)k * m + p], qkq = Q[(size_t)k * m + q];
+                    Q[(size_t)k * m + p] = c * qkp - s * qkq;
+                    Q[(size_t)k * m + q] = s * qkp + c * qkq;
+                }
+            }
+    }
+    std::vector<int> order((size_t)m);
+    for (int i = 0; i < m; i++) order[(size_t)i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return A[(size_t)a * m + a] < A[(size_t)b * m + b]; });
+    ev.resize((size_t)m);
+    std::vector<double> Qs((size_t)m * m);
+    for (int c = 0; c < m; c++) {
+        const int src = order[(size_t)c];
+        ev[(size_t)c] = A[(size_t)src * m + src];
+        for (int k = 0; k < m; k++) Qs[(size_t)k * m + c] = Q[(size_t)k * m + src];
+    }
+    Q.swap(Qs);
+}
+
+}  // namespace
+
+void dense_symeig_host(const double *A, i64 m, double *ev, double *Q) {
+    std::vector<double> a(A, A + (size_t)(m * m)), e, q;
+    jacobi_eigh(a, (int)m, e, q);
+    for (i64 i = 0; i < m; i++) ev[i] = e[(size_t)i];
+    if (Q) for (i64 i = 0; i < m * m; i++) Q[i] = q[(size_t)i];
+}
+
+int32_t lz_eigs(sdplrp_handle *h, i64 nev, i64 ncv, double tol, i64 maxiter, const double *v0_host, uint64_t seed, double *eigs,
+                double *bounds, i64 *matvecs, i64 *restarts) {
+    const i64 n = h->n;
+    cudaStream_t st = h->stream;
+    if (nev < 1 || nev > n) return fail(h, SDPLRP_ERR_ARG, "S_eigval: nev must be in [1, n]");
+    i64 m = std::min<i64>(std::max<i64>(ncv, nev + 1), n);  // ARPACK: nev < ncv <= n
+    if (m > 512) return fail(h, SDPLRP_ERR_ARG, "S_eigval: ncv > 512 is not supported");
+    if (tol <= 0.0) tol = 2.220446049250313e-16;             // ARPACK: tol = 0 means machine precision
+    const double eps23 = pow(2.220446049250313e-16, 2.0 / 3.0);
+    if (maxiter < 1) maxiter = 1;
+    const int gs = grid_for(n, TPB, kRedBlocks);
+
+    const i64 need = (m + 1) * n;
+    if (h->lz_basis_len < need) { SDP_CHECK(dev_alloc(h, &h->lz_basis, need)); h->lz_basis_len = need; }
+    if (h->lz_ab_len < 2 * m) { SDP_CHECK(dev_alloc(h, &h->lz_ab, 2 * m)); h->lz_ab_len = 2 * m; }
+    double *V = h->lz_basis, *ab = h->lz_ab;
+    double *small = nullptr;   // c1 (m+1) | c2 (m+1) | Y (m*m)
+    SDP_CHECK(dev_alloc(h, &small, 2 * (m + 1) + m * m));
+    struct Guard { double *p; ~Guard() { if (p) cudaFree(p); } } guard{small};
+    double *c1 = small, *c2 = small + (m + 1), *Yd = small + 2 * (m + 1);
+    double *stop = h->dscal + SC_LANCZOS, *tmp = h->dscal + SC_LANCZOS + 1;
+    const size_t rot_smem = (size_t)m * TRL_ROWS * sizeof(double);
+    if (rot_smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute(k_trl_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rot_smem));
+
+    CUDA_TRY(h, cudaMemsetAsync(stop, 0, sizeof(double), st));
+    if (v0_host) {
+        SDP_CHECK(perm_upload(h, V, v0_host, 1, false));
+    } else {
+        k_lz_randn<<<gs, TPB, 0, st>>>(n, seed, V); KLAUNCH(h);
+    }
+    k_lz_norm2<<<gs, TPB, 0, st>>>(n, V, h->partials, h->ticket, tmp); KLAUNCH(h);
+    k_lz_div<<<gs, TPB, 0, st>>>(n, tmp, V); KLAUNCH(h);
+
+    std::vector<double> theta, svec;          // kept Ritz values / coupling entries of the arrowhead (size k)
+    std::vector<double> hab((size_t)(2 * m)), T, ev, Q, Yk;
+    i64 k = 0, nmv = 0, nrestart = 0;
+    double best_bound = INFINITY, last_theta = NAN;
+    int stalled = 0;
+    int32_t rc = SDPLRP_OK;
+    for (;;) {
+        CUDA_TRY(h, cudaMemsetAsync(ab, 0, (size_t)(2 * m) * sizeof(double), st));
+        for (i64 j = k; j < m; j++) {
+            const double *vj = V + (size_t)j * n;
+            double *w = V + (size_t)(j + 1) * n;
+            rc = lz_apply(h, vj, w, stop, tmp);  // w = S*v_j   (tmp: <v_j, w>, superseded by the Gram-Schmidt coefficients)
+            if (rc != SDPLRP_OK) break;
+            nmv++;
+            for (int pass = 0; pass < 2; pass++) {  // classical Gram-Schmidt, twice
+                double *c = pass == 0 ? c1 : c2;
+                for (i64 b0 = 0; b0 <= j; b0 += TRL_NB) {
+                    const int cnt = (int)std::min<i64>(TRL_NB, j + 1 - b0);
+                    k_trl_dots<<<gs, TPB, 0, st>>>(n, V + (size_t)b0 * n, cnt, w, stop, h->partials, h->ticket, c + b0); KLAUNCH(h);
+                }
+                k_lz_reorth_apply<<<gs, TPB, 0, st>>>(n, (int)(j + 1), V, c, stop, w); KLAUNCH(h);
+            }
+            k_trl_alpha<<<1, 1, 0, st>>>((int)j, c1, c2, stop, ab); KLAUNCH(h);
+            k_lz_beta<<<gs, TPB, 0, st>>>(n, (int)j, w, ab, m, stop, h->partials, h->ticket); KLAUNCH(h);
+            k_lz_normalise<<<gs, TPB, 0, st>>>(n, (int)j, ab, m, stop, w); KLAUNCH(h);
+        }
+        if (rc != SDPLRP_OK) break;
+        double hstop = 0.0;
+        if (cudaMemcpyAsync(hab.data(), ab, (size_t)(2 * m) * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(&hstop, stop, sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            h->err = std::string("S_eigval: ") + cudaGetErrorString(cudaGetLastError());
+            rc = SDPLRP_ERR_CUDA;
+            break;
+        }
+        // an invariant subspace was found at step `hstop` (beta < sqrt(n)*eps): the projected problem is exact
+        const i64 me = hstop != 0.0 ? (i64)hstop : m;
+        if (hstop != 0.0) nmv -= (m - me);  // the guarded kernels of the later steps did nothing
+        T.assign((size_t)(me * me), 0.0);
+        for (i64 i = 0; i < k; i++) {
+            T[(size_t)(i * me + i)] = theta[(size_t)i];
+            T[(size_t)(i * me + k)] = T[(size_t)(k * me + i)] = svec[(size_t)i];
+        }
+        for (i64 j = k; j < me; j++) {
+            T[(size_t)(j * me + j)] = hab[(size_t)j];
+            if (j + 1 < me) T[(size_t)(j * me + j + 1)] = T[(size_t)((j + 1) * me + j)] = hab[(size_t)(m + j)];
+        }
+        const double beta_last = hab[(size_t)(m + me - 1)];
+        jacobi_eigh(T, (int)me, ev, Q);
+        const i64 nwant = std::min<i64>(nev, me);
+        // ARPACK's rule on the shifted Ritz value (the reference's operator is S + I), with the attainable floor of the
+        // projected eigenproblem (Jacobi: ~ m eps ||T||) so that tol = 0 ("machine precision", the DIMACS call) terminates
+        const double tnorm = std::max(fabs(ev[0] + 1.0), fabs(ev[(size_t)(me - 1)] + 1.0));
+        const double floor_ = 4.0 * (double)me * 2.220446049250313e-16 * tnorm;
+        bool conv = true;
+        double worst = 0.0;
+        for (i64 i = 0; i < nwant; i++) {
+            const double bound = fabs(beta_last * Q[(size_t)((me - 1) * me + i)]);
+            if (bounds) bounds[i] = bound;
+            eigs[i] = ev[(size_t)i];
+            const double want = tol * std::max(eps23, fabs(ev[(size_t)i] + 1.0));
+            if (!(bound <= std::max(want, floor_))) conv = false;
+            worst = std::max(worst, bound);
+        }
+        // stagnation guard: the bounds have stopped improving and the wanted Ritz values have stopped moving
+        const bool moved = fabs(ev[(size_t)(nwant - 1)] - last_theta) > 1e-13 * std::max(1.0, tnorm);
+        if (worst < 0.5 * best_bound) { best_bound = worst; stalled = 0; }
+        else if (!moved) stalled++;
+        last_theta = ev[(size_t)(nwant - 1)];
+        nrestart++;
+        if (conv || hstop != 0.0 || nrestart >= maxiter || me < 2 || stalled >= 8) {
+            for (i64 i = nwant; i < nev; i++) { eigs[i] = NAN; if (bounds) bounds[i] = NAN; }
+            break;
+        }
+        // thick restart: keep the lowest kk Ritz vectors and the residual vector
+        i64 kk = nev + ((me - nev) * 2) / 5;
+        kk = std::max<i64>(nev, std::min<i64>(kk, me - 2));
+        kk = std::max<i64>(1, std::min<i64>(kk, me - 1));
+        Yk.resize((size_t)(me * kk));
+        for (i64 j = 0; j < me; j++)
+            for (i64 c = 0; c < kk; c++) Yk[(size_t)(j * kk + c)] = Q[(size_t)(j * me + c)];
+        if (cudaMemcpyAsync(Yd, Yk.data(), Yk.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            h->err = "S_eigval: upload of the Ritz coefficients failed";
+            rc = SDPLRP_ERR_CUDA;
+            break;
+        }
+        k_trl_rotate<<<grid_for(n, TRL_ROWS, 8 * kNumSM), 256, rot_smem, st>>>(n, (int)me, (int)kk, V, Yd); KLAUNCH(h);
+        if (cudaMemcpyAsync(V + (size_t)kk * n, V + (size_t)me * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {   // Yk is host memory that the next cycle rewrites
+            h->err = "S_eigval: basis restart failed";
+            rc = SDPLRP_ERR_CUDA;
+            break;
+        }
+        theta.assign(ev.begin(), ev.begin() + kk);
+        svec.resize((size_t)kk);
+        for (i64 i = 0; i < kk; i++) svec[(size_t)i] = beta_last * Q[(size_t)((me - 1) * me + i)];
+        k = kk;
+    }
+    if (rc != SDPLRP_OK) return rc;
+    CUDA_TRY(h, cudaGetLastError());
+    if (matvecs) *matvecs = nmv;
+    if (restarts) *restarts = nrestart;
     return SDPLRP_OK;
 }

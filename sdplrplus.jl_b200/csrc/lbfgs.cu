@@ -164,6 +164,13 @@ __global__ void __launch_bounds__(TPB) k_norm2(i64 nu, const double *__restrict_
     grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { out[0] = s[0]; });
 }
 
+template <int VEC>
+__global__ void __launch_bounds__(TPB) k_dot2(i64 nu, const double *__restrict__ x, const double *__restrict__ y, double *partials,
+                                              unsigned *ticket, double *out) {
+    double acc[1] = {0.0};
+    GRID_STRIDE(i, nu) acc[0] += V<VEC>::dot(V<VEC>::ld(x, i), V<VEC>::ld(y, i));
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { out[0] = s[0]; });
+}
 
 // ---- coefficient-space ("Gram") two-loop ------------------------------------------------
 constexpr int kGramMaxHist = 8;
@@ -560,6 +567,14 @@ int32_t lb_axpy2(sdplrp_handle *h, double alpha, const double *x1, double *y1, c
 int32_t lb_neg_copy(sdplrp_handle *h) {
     const Slice sl = owned(h);
     DISPATCH_VEC(sl, k_neg_copy, sl.nu, h->G + sl.off, h->D + sl.off);
+    CUDA_TRY(h, cudaGetLastError());
+    return SDPLRP_OK;
+}
+
+// dscal[slot] = <x, y> over the owned rows (the caller all-reduces)
+int32_t lb_dot(sdplrp_handle *h, const double *x, const double *y, int slot) {
+    const Slice sl = owned(h);
+    DISPATCH_VEC(sl, k_dot2, sl.nu, x + sl.off, y + sl.off, h->partials, h->ticket, h->dscal + slot);
     CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
 }

@@ -190,6 +190,24 @@ __global__ void __launch_bounds__(TPB) k_yb(CRange R, const double *__restrict__
     grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { out[0] = s[0]; });
 }
 
+// DIMACS sums (src/coreop.jl:431, 441-447): this rank's share of ||raw[1:m]||^2 and lambda'b -> out[0], out[1]
+__global__ void __launch_bounds__(TPB) k_dimacs_sums(CRange R, const double *__restrict__ raw, const double *__restrict__ lambda,
+                                                     const double *__restrict__ b, double *partials, unsigned *ticket,
+                                                     double *__restrict__ out) {
+    double acc[2] = {0.0, 0.0};
+    FOR_SLOTS(i, R) {
+        acc[0] += raw[i] * raw[i];
+        acc[1] += lambda[i] * b[i];
+    }
+    grid_sum_finalize<2>(acc, partials, ticket, [&](double (&s)[2]) { out[0] = s[0]; out[1] = s[1]; });
+}
+
+// copy2y_lambda! (src/coreop.jl:238-246): y_i = -lambda_i over owned + shared slots, y_{m+1} = 1
+__global__ void k_copy2y_lambda(CRange R, i64 m, const double *__restrict__ lambda, double *__restrict__ y) {
+    FOR_SLOTS(i, R) y[i] = -lambda[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) y[m] = 1.0;
+}
+
 inline int red_grid(i64 m) { return grid_for(m, TPB, kRedBlocks); }
 
 }  // namespace
@@ -277,6 +295,29 @@ int32_t vec_dual_dot(sdplrp_handle *h, double *out) {
     SDP_CHECK(comm_reduce_scalars(h, SC_LANCZOS + 9, 1));
     SDP_CHECK(fetch_scalars(h, SC_LANCZOS + 9, 1));
     *out = -h->hscal[SC_LANCZOS + 9];
+    return SDPLRP_OK;
+}
+
+int32_t vec_copy2y_lambda(sdplrp_handle *h) {
+    const CRange all = range_all(h);
+    k_copy2y_lambda<<<red_grid(all.len()), TPB, 0, h->stream>>>(all, h->m, h->lambda, h->y);
+    KLAUNCH(h);
+    CUDA_TRY(h, cudaGetLastError());
+    h->y_obj = 1.0;
+    h->S_current = false;
+    return SDPLRP_OK;
+}
+
+int32_t vec_dimacs_sums(sdplrp_handle *h, double *raw_norm2, double *lambda_b) {
+    const CRange sum = range_sum(h);
+    k_dimacs_sums<<<red_grid(sum.len()), TPB, 0, h->stream>>>(sum, h->pvio_raw, h->lambda, h->b, h->partials, h->ticket,
+                                                            h->dscal + SC_LANCZOS + 9);
+    KLAUNCH(h);
+    CUDA_TRY(h, cudaGetLastError());
+    SDP_CHECK(comm_reduce_scalars(h, SC_LANCZOS + 9, 2));
+    SDP_CHECK(fetch_scalars(h, SC_LANCZOS + 9, 2));
+    *raw_norm2 = h->hscal[SC_LANCZOS + 9];
+    *lambda_b = h->hscal[SC_LANCZOS + 10];
     return SDPLRP_OK;
 }
 

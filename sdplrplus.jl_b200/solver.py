@@ -204,6 +204,14 @@ class B200Engine:
     def dual_obj(self, trace_bound, it, v0=None, seed=0):
         return self.h.dual_obj(trace_bound, it, v0, seed)
 
+    def dual_obj_highprecision(self, trace_bound, v0=None, seed=0):
+        """dual_obj(...; highprecision=true): SDP_S_eigval replaces the q-step Lanczos (src/coreop.jl:386-400)."""
+        return self.h.dual_obj_highprecision(trace_bound, v0, seed)
+
+    def dimacs_errors(self, normb, normC, v0=None, seed=0):
+        """DIMACS_errors(data, var, aux) (src/coreop.jl:426-453)."""
+        return self.h.dimacs_errors(normb, normC, v0, seed)
+
     def dual_update(self):
         self.h.dual_update()
 
@@ -348,7 +356,10 @@ def _sdplr(data, engine, config: BurerMonteiroConfig, stats: SolverStats, r, rng
         if primal_vio_norm <= cur_ptol:
             t0 = time.perf_counter()
             v0 = rng.standard_normal(n) if config.lanczos_host_rng else None
-            dual_value, _, steps = engine.dual_obj(config.prior_trace_bound, it, v0, int(rng.integers(1 << 62)))
+            if config.eigval_highprecision:   # src/sdplr.jl:311-321
+                dual_value, _, steps = engine.dual_obj_highprecision(config.prior_trace_bound, v0, int(rng.integers(1 << 62)))
+            else:
+                dual_value, _, steps = engine.dual_obj(config.prior_trace_bound, it, v0, int(rng.integers(1 << 62)))
             stats.lanczos_steps += int(steps)
             if dual_value > max_dual_value:
                 best_lambda = -engine.get_y()
@@ -407,11 +418,18 @@ def _sdplr(data, engine, config: BurerMonteiroConfig, stats: SolverStats, r, rng
     stats.endtime = time.perf_counter()
     totaltime = stats.endtime - stats.starttime
     stats.primal_time = totaltime - stats.dual_time
+    t0 = time.perf_counter()
+    if config.eval_DIMACS_errs:   # src/sdplr.jl:419-425; not part of totaltime
+        v0 = rng.standard_normal(n) if config.lanczos_host_rng else None
+        DIMACS_errs = np.asarray(engine.dimacs_errors(normb, normC, v0, int(rng.integers(1 << 62))))
+    else:
+        DIMACS_errs = np.zeros(6)
+    stats.DIMACS_time = time.perf_counter() - t0
     return {
         "Rt": engine.get_R(), "lambda": best_lambda, "Rt0": Rt0_copy, "lambda0": lam0_copy, "sigma": engine.sigma,
         "grad_norm": grad_norm, "primal_vio": primal_vio_norm, "obj": obj, "max_dual_value": max_dual_value,
         "min_duality_gap": min_duality_gap, "totaltime": totaltime, "dual_time": stats.dual_time,
-        "primaltime": stats.primal_time, "iter": it, "majoriter": majoriter, "DIMACS_errs": np.zeros(6),
+        "primaltime": stats.primal_time, "iter": it, "majoriter": majoriter, "DIMACS_errs": DIMACS_errs,
         "ptol": config.ptol, "objtol": config.objtol, "fprec": config.fprec, "rankupd_tol": config.rankupd_tol,
         "r": r, "lanczos_steps": stats.lanczos_steps, "L": L_val,
     }

@@ -219,6 +219,40 @@ int32_t sdplrp_dimacs_errors(sdplrp_handle *h, double normb, double normC, const
  * eigenvectors as the columns of Q (k x k row-major, may be NULL).  The projected problem of the restarted Lanczos. */
 int32_t sdplrp_dense_symeig(const double *A, int64_t k, double *ev, double *Q);
 
+/* ---- native host driver ------------------------------ */
+/* BurerMonteiroConfig (src/options.jl:1-24); every field is 8 bytes wide so the layout is the same from C, Julia
+ * (`struct` of Float64 / Int64 / UInt64) and ctypes.  *_relative: 1 = "relative" (default), 0 = "absolute". */
+typedef struct {
+    double ptol, gtol, objtol, sigma_0, sigmafac, maxtime, printfreq, fprec, prior_trace_bound, alpha_max;
+    int64_t maxmajoriter, maxiter, numlbfgsvecs, rankupd_tol, printlevel;
+    int64_t gtol_relative, ptol_relative, objtol_relative, eval_DIMACS_errs, eigval_highprecision;
+    uint64_t seed; /* counter-based device generator: eigenvalue start vectors, random R of a rank update / of a NULL Rt0 */
+} sdplrp_config;
+/* the scalar entries of the reference's result Dict (src/sdplr.jl:426-448); Rt and the multipliers are fetched with
+ * sdplrp_download_mat(SDPLRP_MAT_R) / the best_lambda argument.  status: 0 = tolerances met, 1 = iteration / time /
+ * major-iteration budget exhausted. */
+typedef struct {
+    double sigma, grad_norm, primal_vio, obj, L, max_dual_value, min_duality_gap, totaltime, dual_time, primaltime, DIMACS_time;
+    double DIMACS_errs[6];
+    int64_t iter, majoriter, lanczos_steps, r, status;
+} sdplrp_result;
+int32_t sdplrp_config_default(sdplrp_config *cfg);
+/* _sdplr (src/sdplr.jl:140-449) as one call: the same sequence of entry points a Julia host issues, driven natively.
+ * Rt0 (r x n column-major) / lambda0 (m) may be NULL (R ~ U(-1,1) from the device generator, lambda = 0:
+ * src/structs.jl:236-237).  normb = ||b||_2, normC = ||C||_F as computed by the caller (src/sdplr.jl:165-166).
+ * best_lambda (m+1 doubles, may be NULL) receives the multipliers of the best dual bound (src/sdplr.jl:325).
+ * Inequality problems (sdplrp_set_problem) use the Armijo search, as the reference does. */
+int32_t sdplrp_solve(sdplrp_handle *h, const sdplrp_config *cfg, int64_t r, const double *Rt0, const double *lambda0, double normb,
+                     double normC, sdplrp_result *result, double *best_lambda);
+/* root selection of linesearch! (src/linesearch.jl:58-112) for quartic coefficients as returned by
+ * sdplrp_linesearch_coeffs: the minimiser over the real roots of the derivative in [0, alpha_max] and alpha_max itself
+ * (host only).  Returns SDPLRP_ERR_LINESEARCH when cubic[1] > eps. */
+int32_t sdplrp_pick_alpha(const double biquadratic[5], double alpha_max, double *alpha, double *value);
+/* mat (R, G or D) <- 2u - 1 with u ~ U[0,1) from the counter-based device generator, keyed by (seed, reference vertex,
+ * column): the same matrix for every GPU count and internal vertex order (SolverVars' `2 .* rand(r, n) .- 1`,
+ * src/structs.jl:236, without the 0.8 GB host round trip at n = 10^7) */
+int32_t sdplrp_fill_uniform(sdplrp_handle *h, int32_t mat_id, uint64_t seed);
+
 /* ---- introspection ---------------------------------------------------- */
 /* kernel-group sections timed with CUDA events on the handle's stream */
 enum {

@@ -612,37 +612,64 @@ void orc_fg(orc_ctx *c, double normC, double normb, double *out3) {
 }
 
 /* ------------------------------------------------------------------------- */
-/* real roots of c0 + c1 x + c2 x^2 + c3 x^3 (c3 != 0), Newton-polished.
+static double cubic_newton(const double *c, double x, int iters) {
+    for (int it = 0; it < iters; it++) {
+        double f = ((c[3] * x + c[2]) * x + c[1]) * x + c[0];
+        double df = (3.0 * c[3] * x + 2.0 * c[2]) * x + c[1];
+        if (df == 0.0 || !isfinite(f / df)) break;
+        double xn = x - f / df;
+        if (xn == x) break;
+        x = xn;
+    }
+    return x;
+}
+
+/* real roots of c0 + c1 x + c2 x^2 + c3 x^3 (c3 != 0).
  * Stands in for PolynomialRoots.roots (src/linesearch.jl:82,94): the
- * reference keeps only roots with |imag| < eps, i.e. the real ones. */
+ * reference keeps only roots with |imag| < eps, i.e. the real ones.
+ * Closed form for the root of LARGEST magnitude (the one Cardano / the
+ * trigonometric form deliver without cancellation), Newton-polished on the
+ * original coefficients; backward deflation by it leaves a quadratic whose
+ * roots come from the cancellation-free quadratic formula, so the small roots
+ * survive a nearly vanishing leading coefficient. */
 static int cubic_real_roots(const double *c, double *roots) {
     double a = c[2] / c[3], b = c[1] / c[3], d = c[0] / c[3];
     double p = b - a * a / 3.0, q = 2.0 * a * a * a / 27.0 - a * b / 3.0 + d;
     double disc = q * q / 4.0 + p * p * p / 27.0;
-    int nr = 0;
+    double r1;
     if (disc > 0) {
         double sq = sqrt(disc);
         double u = cbrt(-q / 2.0 + sq), v = cbrt(-q / 2.0 - sq);
-        roots[nr++] = u + v - a / 3.0;
+        r1 = u + v - a / 3.0;
     } else if (p == 0.0) {
-        roots[nr++] = -a / 3.0;
+        r1 = -a / 3.0;
     } else {
         double m = 2.0 * sqrt(-p / 3.0);
         double arg = 3.0 * q / (p * m);
         if (arg > 1) arg = 1;
         if (arg < -1) arg = -1;
         double th = acos(arg) / 3.0;
-        for (int k = 0; k < 3; k++) roots[nr++] = m * cos(th - 2.0 * M_PI * k / 3.0) - a / 3.0;
-    }
-    for (int i = 0; i < nr; i++) { /* polish on the original coefficients */
-        double x = roots[i];
-        for (int it = 0; it < 4; it++) {
-            double f = ((c[3] * x + c[2]) * x + c[1]) * x + c[0];
-            double df = (3.0 * c[3] * x + 2.0 * c[2]) * x + c[1];
-            if (df == 0.0 || !isfinite(f / df)) break;
-            x -= f / df;
+        r1 = 0.0;
+        for (int k = 0; k < 3; k++) {
+            double t = m * cos(th - 2.0 * M_PI * k / 3.0) - a / 3.0;
+            if (fabs(t) > fabs(r1)) r1 = t;
         }
-        if (isfinite(x)) roots[i] = x;
+    }
+    if (!isfinite(r1)) return 0;
+    r1 = cubic_newton(c, r1, 30);
+    int nr = 0;
+    roots[nr++] = r1;
+    if (r1 == 0.0) return nr;
+    /* (x - r1)(c3 x^2 + b1 x + b0), BACKWARD deflation (from the constant term): the stable direction for the
+     * root of largest magnitude */
+    double b0 = -c[0] / r1, b1 = (b0 - c[1]) / r1;
+    double dq = b1 * b1 - 4.0 * c[3] * b0;
+    if (dq >= 0) {
+        double sq = sqrt(dq);
+        double t = -0.5 * (b1 + (b1 >= 0 ? sq : -sq));
+        double x1 = t / c[3], x2 = (t != 0.0) ? b0 / t : 0.0;
+        roots[nr++] = cubic_newton(c, x1, 8);
+        roots[nr++] = cubic_newton(c, x2, 8);
     }
     return nr;
 }

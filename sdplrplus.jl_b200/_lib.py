@@ -75,6 +75,32 @@ _SIGNATURES = {
     "sdplrp_launch_count": [_H, _p_i64],
     "sdplrp_row_range": [_H, _p_i64, _p_i64],
 }
+
+
+class Config(C.Structure):
+    """sdplrp_config (include/sdplrp_b200.h): BurerMonteiroConfig with 8-byte fields."""
+    _fields_ = ([(k, C.c_double) for k in ("ptol", "gtol", "objtol", "sigma_0", "sigmafac", "maxtime", "printfreq", "fprec",
+                                            "prior_trace_bound", "alpha_max")] +
+                [(k, C.c_int64) for k in ("maxmajoriter", "maxiter", "numlbfgsvecs", "rankupd_tol", "printlevel", "gtol_relative",
+                                           "ptol_relative", "objtol_relative", "eval_DIMACS_errs", "eigval_highprecision")] +
+                [("seed", C.c_uint64)])
+
+
+class Result(C.Structure):
+    """sdplrp_result (include/sdplrp_b200.h)."""
+    _fields_ = ([(k, C.c_double) for k in ("sigma", "grad_norm", "primal_vio", "obj", "L", "max_dual_value", "min_duality_gap",
+                                            "totaltime", "dual_time", "primaltime", "DIMACS_time")] +
+                [("DIMACS_errs", C.c_double * 6)] +
+                [(k, C.c_int64) for k in ("iter", "majoriter", "lanczos_steps", "r", "status")])
+
+
+_SIGNATURES.update({
+    "sdplrp_config_default": [C.POINTER(Config)],
+    "sdplrp_solve": [_H, C.POINTER(Config), C.c_int64, _p_f64, _p_f64, C.c_double, C.c_double, C.POINTER(Result), _p_f64],
+    "sdplrp_pick_alpha": [_p_f64, C.c_double, _p_f64, _p_f64],
+    "sdplrp_fill_uniform": [_H, C.c_int32, C.c_uint64],
+})
+
 _SPECIAL = {
     "sdplrp_version": ([], C.c_int32),
     "sdplrp_error_string": ([C.c_int32], C.c_char_p),
@@ -408,6 +434,26 @@ class Handle:
         self._check(self.lib.sdplrp_dimacs_errors(self._h, float(normb), float(normC), pv, int(seed), errs.ctypes.data_as(_p_f64)))
         return errs
 
+    def fill_uniform(self, mat_id, seed):
+        """mat <- U(-1,1) from the counter-based device generator (same matrix for any GPU count / vertex order)"""
+        self._check(self.lib.sdplrp_fill_uniform(self._h, int(mat_id), int(seed)))
+
+    def solve(self, cfg, r, Rt0=None, lambda0=None, normb=1.0, normC=1.0):
+        """sdplrp_solve: the native outer loop -> (Result, best_lambda[m+1])"""
+        pr = pl = None
+        if Rt0 is not None:
+            Rt0, pr = _f64(Rt0)
+            assert Rt0.size == self.n * int(r)
+        if lambda0 is not None:
+            lambda0, pl = _f64(lambda0)
+            assert lambda0.size == self.m
+        res = Result()
+        best = np.zeros(self.m + 1)
+        self._check(self.lib.sdplrp_solve(self._h, C.byref(cfg), int(r), pr, pl, float(normb), float(normC), C.byref(res),
+                                           best.ctypes.data_as(_p_f64)))
+        self.r = int(res.r)
+        return res, best
+
     SECTIONS = ["lbfgs_dir", "ls_pass", "ls_coeff", "step", "s_assemble", "spmm", "norms", "lbfgs_update", "a_uu", "f_finish",
                 "lanczos", "comm", "grad", "tail"]
 
@@ -451,3 +497,23 @@ def dense_symeig(A):
     if rc != 0:
         raise SdplrpError(rc, "dense_symeig: bad argument")
     return ev, Q
+
+
+def default_config():
+    cfg = Config()
+    rc = load().sdplrp_config_default(C.byref(cfg))
+    if rc != 0:
+        raise SdplrpError(rc, "config_default")
+    return cfg
+
+
+def pick_alpha_native(bq, alpha_max=1.0):
+    """sdplrp_pick_alpha: root selection of linesearch! on the host (C++); raises ArithmeticError like the reference."""
+    bq, pb = _f64(bq)
+    a, v = C.c_double(), C.c_double()
+    rc = load().sdplrp_pick_alpha(pb, float(alpha_max), C.byref(a), C.byref(v))
+    if rc == -7:
+        raise ArithmeticError(f"Error: cubic[1] = {bq[1]} should be less than 0.")
+    if rc != 0:
+        raise SdplrpError(rc, "pick_alpha: bad argument")
+    return a.value, v.value

@@ -282,6 +282,8 @@ int32_t sdplrp_set_problem(sdplrp_handle *h, const double *b, const uint8_t *is_
     if (m > 0 && !b) return fail(h, SDPLRP_ERR_ARG, "set_problem: null b");
     if (m > 0) SDP_CHECK(perm_cvec_upload(h, h->b, b, m));
     unsigned char *dq = nullptr;
+    h->has_ineq = false;
+    if (is_ineq) for (i64 i = 0; i < m; i++) h->has_ineq |= is_ineq[i] != 0;
     if (is_ineq && m > 0) {
         CUDA_TRY(h, cudaMalloc((void **)&dq, (size_t)m));
         CUDA_TRY(h, cudaMemcpy(dq, is_ineq, (size_t)m, cudaMemcpyHostToDevice));

@@ -76,6 +76,7 @@ struct sdplrp_handle {
     std::vector<i64> c_starts;   // world+1: rowc_ptr[row_starts[q]]
     bool mat_full[8] = {true, true, true, true, true, true, true, true};  // R,G,D,W0,W1: all rows valid here?
     bool preprocessed = false;
+    bool has_ineq = false;       // some constraint is an inequality (sdplrp_set_problem): the driver uses the Armijo search
 
     // aggregated patterns (0-based int32 on device)
     int *triu_colptr = nullptr, *triu_rowval = nullptr;  // n+1, nnzT   (CSC of triu == CSR of tril), reference labels

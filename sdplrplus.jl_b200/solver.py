@@ -60,6 +60,9 @@ class BurerMonteiroConfig:
     # not in the reference: Julia's global RNG is replaced by an explicit seed
     seed: int = 0
     lanczos_host_rng: bool = True  # draw the Lanczos start vector on the host (engine-independent)
+    rng_stream: str = "numpy"      # "native": eigenvalue start vectors from the device generator with the seed sequence of
+                                   # the native driver (csrc/driver.cu), so that both drivers see the same random numbers
+    driver: str = "python"         # "native": run the outer loop inside the library (sdplrp_solve)
 
     _ALIASES = {"σ_0": "sigma_0", "σfac": "sigmafac"}
 
@@ -68,6 +71,18 @@ class BurerMonteiroConfig:
         if not hasattr(self, key) or key.startswith("_"):
             raise KeyError(f"Unrecognized keyword argument {key}")  # reference: @error and continue
         setattr(self, key, value)
+
+
+_M64 = (1 << 64) - 1
+
+
+def native_seed(seed, k):
+    """k-th (k = 1, 2, ...) seed of the native driver's device-generator stream (csrc/driver.cu, Driver::next_seed)."""
+    x = (int(seed) + 0x632BE59BD9B4E019 * int(k)) & _M64
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
 
 
 def barvinok_pataki(n, m):
@@ -303,6 +318,7 @@ def _sdplr(data, engine, config: BurerMonteiroConfig, stats: SolverStats, r, rng
 
     it = 0
     majoriter = 0
+    seed_ctr = 0
     use_armijo = data.has_inequalities
     rankupd_tol_cnt = config.rankupd_tol
     duality_gap = 1e20
@@ -355,11 +371,16 @@ def _sdplr(data, engine, config: BurerMonteiroConfig, stats: SolverStats, r, rng
         sigma = engine.sigma
         if primal_vio_norm <= cur_ptol:
             t0 = time.perf_counter()
-            v0 = rng.standard_normal(n) if config.lanczos_host_rng else None
-            if config.eigval_highprecision:   # src/sdplr.jl:311-321
-                dual_value, _, steps = engine.dual_obj_highprecision(config.prior_trace_bound, v0, int(rng.integers(1 << 62)))
+            if config.rng_stream == "native":
+                seed_ctr += 1
+                v0, dev_seed = None, native_seed(config.seed, seed_ctr)
             else:
-                dual_value, _, steps = engine.dual_obj(config.prior_trace_bound, it, v0, int(rng.integers(1 << 62)))
+                v0 = rng.standard_normal(n) if config.lanczos_host_rng else None
+                dev_seed = int(rng.integers(1 << 62))
+            if config.eigval_highprecision:   # src/sdplr.jl:311-321
+                dual_value, _, steps = engine.dual_obj_highprecision(config.prior_trace_bound, v0, dev_seed)
+            else:
+                dual_value, _, steps = engine.dual_obj(config.prior_trace_bound, it, v0, dev_seed)
             stats.lanczos_steps += int(steps)
             if dual_value > max_dual_value:
                 best_lambda = -engine.get_y()
@@ -420,8 +441,12 @@ def _sdplr(data, engine, config: BurerMonteiroConfig, stats: SolverStats, r, rng
     stats.primal_time = totaltime - stats.dual_time
     t0 = time.perf_counter()
     if config.eval_DIMACS_errs:   # src/sdplr.jl:419-425; not part of totaltime
-        v0 = rng.standard_normal(n) if config.lanczos_host_rng else None
-        DIMACS_errs = np.asarray(engine.dimacs_errors(normb, normC, v0, int(rng.integers(1 << 62))))
+        if config.rng_stream == "native":
+            v0, dev_seed = None, native_seed(config.seed, seed_ctr + 1)
+        else:
+            v0 = rng.standard_normal(n) if config.lanczos_host_rng else None
+            dev_seed = int(rng.integers(1 << 62))
+        DIMACS_errs = np.asarray(engine.dimacs_errors(normb, normC, v0, dev_seed))
     else:
         DIMACS_errs = np.zeros(6)
     stats.DIMACS_time = time.perf_counter() - t0
@@ -432,6 +457,36 @@ def _sdplr(data, engine, config: BurerMonteiroConfig, stats: SolverStats, r, rng
         "primaltime": stats.primal_time, "iter": it, "majoriter": majoriter, "DIMACS_errs": DIMACS_errs,
         "ptol": config.ptol, "objtol": config.objtol, "fprec": config.fprec, "rankupd_tol": config.rankupd_tol,
         "r": r, "lanczos_steps": stats.lanczos_steps, "L": L_val,
+    }
+
+
+def _sdplr_native(data, engine, config: BurerMonteiroConfig, r, rng):
+    """The same solve with the outer loop inside the library (sdplrp_solve, csrc/driver.cu); only for the GPU engine.
+    Returns the reference's result dict."""
+    cfg = _lib.default_config()
+    for k in ("ptol", "gtol", "objtol", "sigma_0", "sigmafac", "maxtime", "printfreq", "fprec", "prior_trace_bound"):
+        setattr(cfg, k, float(getattr(config, k)))
+    for k in ("maxmajoriter", "maxiter", "numlbfgsvecs", "rankupd_tol", "printlevel"):
+        setattr(cfg, k, int(getattr(config, k)))
+    cfg.gtol_relative = int(config.gtol_mode == "relative")
+    cfg.ptol_relative = int(config.ptol_mode == "relative")
+    cfg.objtol_relative = int(config.objtol_mode == "relative")
+    cfg.eval_DIMACS_errs = int(bool(config.eval_DIMACS_errs))
+    cfg.eigval_highprecision = int(bool(config.eigval_highprecision))
+    cfg.seed = int(config.seed)
+    Rt0, lam0 = _init_point(data, r, config, rng)
+    normb = float(np.linalg.norm(data.b))
+    normC = frobenius_norm(data.C)
+    res, best = engine.h.solve(cfg, r, Rt0, lam0, normb, normC)
+    engine.r = int(res.r)
+    return {
+        "Rt": engine.get_R(), "lambda": best, "Rt0": Rt0, "lambda0": lam0, "sigma": res.sigma, "grad_norm": res.grad_norm,
+        "primal_vio": res.primal_vio, "obj": res.obj, "max_dual_value": res.max_dual_value,
+        "min_duality_gap": res.min_duality_gap, "totaltime": res.totaltime, "dual_time": res.dual_time,
+        "primaltime": res.primaltime, "iter": int(res.iter), "majoriter": int(res.majoriter),
+        "DIMACS_errs": np.array(list(res.DIMACS_errs)), "ptol": config.ptol, "objtol": config.objtol, "fprec": config.fprec,
+        "rankupd_tol": config.rankupd_tol, "r": int(res.r), "lanczos_steps": int(res.lanczos_steps), "L": res.L,
+        "status": int(res.status),
     }
 
 
@@ -454,7 +509,10 @@ def sdplr(C, As, b, r, constraint_types=None, config: Optional[BurerMonteiroConf
     stats = SolverStats()
     preprocess_dt = time.perf_counter() - t0
     rng = np.random.default_rng(config.seed)
-    ans = _sdplr(data, engine, config, stats, int(r), rng, record_trace=record_trace)
+    if config.driver == "native":
+        ans = _sdplr_native(data, engine, config, int(r), rng)
+    else:
+        ans = _sdplr(data, engine, config, stats, int(r), rng, record_trace=record_trace)
     ans["preprocess_time"] = preprocess_dt
     ans["totaltime"] += preprocess_dt
     if record_trace:

@@ -97,3 +97,58 @@ def test_misc(sp):
     with pytest.raises(KeyError):
         cfg.set("nonsense", 1)
     assert sp.frobenius_norm(sps.csc_matrix(np.array([[3.0, 0], [0, 4.0]]))) == 5.0
+
+
+def _scaled_quartics(count, seed):
+    """quartic coefficient sets over seven orders of magnitude, including the degenerate shapes of the line search"""
+    rng = np.random.default_rng(seed)
+    for t in range(count):
+        bq = rng.standard_normal(5) * 10.0 ** rng.integers(-3, 4, 5)
+        bq[1] = -abs(bq[1]); bq[4] = abs(bq[4])
+        kind = t % 5
+        if kind == 1: bq[4] = 0.0                       # quadratic fallback (src/linesearch.jl:70-83)
+        if kind == 2: bq[3] = bq[4] = 0.0               # derivative is linear
+        if kind == 3: bq[1] = 0.0                       # zero slope at 0
+        if kind == 4: bq[2] = abs(bq[2]); bq[3] = abs(bq[3])
+        yield bq
+
+
+def test_native_pick_alpha_matches_python_and_oracle(sp, oracle_mod):
+    """sdplrp_pick_alpha (the native driver's root selection, csrc/driver.cu) against the numpy.roots mirror and the
+    oracle's closed-form solver: same minimum of the quartic, same step."""
+    import ctypes as C
+    ol = oracle_mod.load()
+    for bq in _scaled_quartics(4000, 3):
+        a_py, f_py = sp.pick_alpha(bq, 1.0)
+        a_na, f_na = sp._lib.pick_alpha_native(bq, 1.0)
+        a, f = C.c_double(), C.c_double()
+        assert ol.orc_pick_alpha(bq.ctypes.data_as(C.POINTER(C.c_double)), 1.0, C.byref(a), C.byref(f)) == 0
+        tol = 1e-13 * max(1.0, abs(f_na))
+        assert f_na <= f_py + tol, (bq, a_py, a_na)      # numpy.roots loses tiny roots of badly scaled cubics; never the reverse
+        assert abs(f_na - f.value) <= tol, (bq, a_na, a.value)
+        assert abs(a_na - a.value) <= 1e-9 * max(abs(a_na), 1e-30), (bq, a_na, a.value)
+    with pytest.raises(ArithmeticError):
+        sp._lib.pick_alpha_native([0.0, 1.0, 1.0, 0.0, 1.0], 1.0)
+    assert sp._lib.pick_alpha_native([3.0, 0.0, 0.0, 0.0, 0.0], 1.0) == (0.0, 3.0)
+    a, f = sp._lib.pick_alpha_native([1.0, -1.0, 5.0, 0.0, 0.0], 1.0)
+    assert abs(a - 0.1) < 1e-15
+
+
+def test_native_config_defaults_match_reference_options(sp):
+    """sdplrp_config_default == BurerMonteiroConfig defaults (src/options.jl:1-24); 21 fields of 8 bytes"""
+    import ctypes as C
+    cfg = sp._lib.default_config()
+    assert C.sizeof(sp._lib.Config) == 21 * 8 and C.sizeof(sp._lib.Result) == 22 * 8
+    ref = sp.BurerMonteiroConfig()
+    for k in ("ptol", "gtol", "objtol", "sigma_0", "sigmafac", "maxtime", "printfreq", "fprec", "prior_trace_bound",
+              "maxmajoriter", "maxiter", "numlbfgsvecs", "rankupd_tol", "printlevel"):
+        assert getattr(cfg, k) == getattr(ref, k), k
+    assert (cfg.gtol_relative, cfg.ptol_relative, cfg.objtol_relative) == (1, 1, 1)
+    assert (cfg.eval_DIMACS_errs, cfg.eigval_highprecision, cfg.alpha_max) == (0, 0, 1.0)
+
+
+def test_native_seed_stream_is_a_fixed_sequence(sp):
+    from sdplrplus.jl_b200.solver import native_seed
+    s = [native_seed(0, k) for k in range(1, 5)]
+    assert len(set(s)) == 4 and all(0 <= x < 2 ** 64 for x in s)
+    assert native_seed(7, 3) == native_seed(7, 3) != native_seed(8, 3)

@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--cpu-sample-n", type=int, default=1_000_000)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--python-loop", action="store_true", help="drive the iterations from Python (one ctypes call per seam function) "
+                    "instead of sdplrp_iterate")
     ap.add_argument("--lanczos", type=int, default=0, help="also time this many Lanczos steps (reported separately)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -231,13 +233,15 @@ def main():
     Rout_t = torch.empty((n, r), dtype=torch.float64).pin_memory()
     stream = torch.cuda.ExternalStream(handle.stream)
 
+    native = not args.python_loop
+
     def reset():
         eng.init_vars(r, R0, lam0, 2.0, h)
         return eng.fg()
 
     # ---- device-resident throughput: K iterations, CUDA events on the handle's stream
     reset()
-    sp.solver.run_inner_iterations(eng, args.warmup)
+    sp.solver.run_inner_iterations(eng, args.warmup, native=native)
     handle.section_times()
     handle.set_profiling(True)
     sampler = ClockSampler(local)
@@ -248,7 +252,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     t_wall0 = time.perf_counter()
-    last = sp.solver.run_inner_iterations(eng, args.steps)
+    last = sp.solver.run_inner_iterations(eng, args.steps, native=native)
     ev1.record(stream)
     torch.cuda.synchronize(); spdist.barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -267,7 +271,7 @@ def main():
     t0 = time.perf_counter()
     eng.init_vars(r, R0, lam0, 2.0, h)
     eng.fg()
-    sp.solver.run_inner_iterations(eng, args.steps)
+    sp.solver.run_inner_iterations(eng, args.steps, native=native)
     handle.lib.sdplrp_download_mat(handle._h, sp._lib.MAT_R, Rout_t.numpy().ctypes.data_as(sp._lib._p_f64))
     lam_out = eng.get_lambda()
     torch.cuda.synchronize(); spdist.barrier()
@@ -333,7 +337,7 @@ def main():
             "host_wall_ms_per_step": 1e3 * t_wall / args.steps, "comm_ms_per_step": comm_ms / args.steps,
             "setup": {"graph_generation_s": gen_s, "preprocess_s": preprocess_s},
             "last_iterate": {"L": last[0], "obj": last[1], "gnorm2": last[2], "pnorm2": last[3], "alpha": last[4]},
-            "lanczos": lanczos,
+            "lanczos": lanczos, "loop": "sdplrp_iterate (native)" if native else "python (one ABI call per seam function)",
         }
         print(json.dumps(line), flush=True)
     handle.close()

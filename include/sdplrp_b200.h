@@ -244,6 +244,10 @@ int32_t sdplrp_config_default(sdplrp_config *cfg);
  * Inequality problems (sdplrp_set_problem) use the Armijo search, as the reference does. */
 int32_t sdplrp_solve(sdplrp_handle *h, const sdplrp_config *cfg, int64_t r, const double *Rt0, const double *lambda0, double normb,
                      double normC, sdplrp_result *result, double *best_lambda);
+/* k passes of the inner loop body of _sdplr (src/sdplr.jl:194-246) without the tolerance logic: direction, descent test,
+ * line search (use_armijo != 0: backtracking), step, gradient, and -- update_history != 0 -- the L-BFGS update.
+ * out = {L, obj, ||G||_F^2, ||pvio||_2^2, alpha} of the last pass.  What bench.py times. */
+int32_t sdplrp_iterate(sdplrp_handle *h, int64_t k, double alpha_max, int32_t use_armijo, int32_t update_history, double out[5]);
 /* root selection of linesearch! (src/linesearch.jl:58-112) for quartic coefficients as returned by
  * sdplrp_linesearch_coeffs: the minimiser over the real roots of the derivative in [0, alpha_max] and alpha_max itself
  * (host only).  Returns SDPLRP_ERR_LINESEARCH when cubic[1] > eps. */

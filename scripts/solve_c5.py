@@ -1,22 +1,63 @@
-"""Time-to-tolerance of the full solve on the C5 workload (driver = sdplrplus.jl_b200.solver._sdplr, reference defaults)."""
-import sys, os, time, json
+"""Time-to-tolerance of the full solve on the C5 workload (BASELINE metric "time-to-tol at 1/2/4/8 B200").
+
+  python scripts/solve_c5.py [n] [edges]                                  one GPU
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29551 \
+      scripts/solve_c5.py [n] [edges]                                     N GPUs (one rank per GPU)
+
+Driver: sdplrp_solve (csrc/driver.cu, the reference's control flow src/sdplr.jl:140-449 inside the library), reference
+defaults (ptol = objtol = 1e-2, sigma_0 = 2, numlbfgsvecs = 4, fprec = 1e8), prior_trace_bound = n, R0 ~ U(-1,1) and the
+Lanczos start vectors from the device generator (seed 0).  SOLVE_DRIVER=python uses the Python mirror of the loop instead.
+"""
+import json
+import math
+import os
+import sys
+import time
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import sdplrplus.jl_b200 as sp
+from sdplrplus.jl_b200 import dist as spdist
 from bench import SimpleData, generate
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 edges = int(sys.argv[2]) if len(sys.argv) > 2 else 8 * n
+rank, world, local = spdist.init_process_group()
+import torch
+torch.cuda.set_device(local)
+h = spdist.make_handle(sp.Handle)
 asm, b, normC, E, gen_s = generate(sp, n, edges, 42)
 data = SimpleData(n, n, b)
 data.C = None
-h = sp.Handle(device=0)
+t0 = time.perf_counter()
 eng = sp.B200Engine(data, handle=h, asm=asm)
-cfg = sp.BurerMonteiroConfig(prior_trace_bound=float(n), printlevel=1, printfreq=5.0, maxtime=600.0, dataset=f"C5 n={n}", seed=0,
-                             lanczos_host_rng=False)
-stats = sp.solver.SolverStats()
-import sdplrplus.jl_b200.solver as S
-S.frobenius_norm = lambda C: normC   # ||C||_F of the assembled objective (the triplets never exist as a scipy matrix here)
-res = S._sdplr(data, eng, cfg, stats, 10, np.random.default_rng(0))
-print(json.dumps({k: res[k] for k in ("iter", "majoriter", "obj", "primal_vio", "max_dual_value", "min_duality_gap", "totaltime", "dual_time",
-                                       "primaltime", "lanczos_steps", "r")}))
+pre_s = time.perf_counter() - t0
+del asm
+spdist.barrier()
+if os.environ.get("SOLVE_DRIVER", "native") == "python":
+    import sdplrplus.jl_b200.solver as S
+    S.frobenius_norm = lambda C: normC   # ||C||_F of the assembled objective (the triplets never exist as a scipy matrix here)
+    cfg = sp.BurerMonteiroConfig(prior_trace_bound=float(n), printlevel=int(rank == 0), printfreq=5.0, maxtime=600.0,
+                                 dataset=f"C5 n={n}", seed=0, lanczos_host_rng=False)
+    res = S._sdplr(data, eng, cfg, sp.solver.SolverStats(), 10, np.random.default_rng(0))
+    out = {k: res[k] for k in ("iter", "majoriter", "obj", "primal_vio", "max_dual_value", "min_duality_gap", "totaltime", "dual_time",
+                               "primaltime", "lanczos_steps", "r")}
+    out["driver"] = "python"
+else:
+    cfg = sp._lib.default_config()
+    cfg.prior_trace_bound = float(n)
+    cfg.printlevel = 1
+    cfg.printfreq = 5.0
+    cfg.maxtime = 600.0
+    cfg.seed = 0
+    res, best = h.solve(cfg, 10, None, None, normb=math.sqrt(n), normC=normC)
+    out = {k: getattr(res, k) for k in ("iter", "majoriter", "obj", "primal_vio", "max_dual_value", "min_duality_gap", "totaltime",
+                                        "dual_time", "primaltime", "lanczos_steps", "r", "status")}
+    out["driver"] = "native (sdplrp_solve)"
+out.update(n_gpus=world, n=n, edges=int(E), preprocess_s=pre_s, graph_generation_s=gen_s,
+           al_iters_per_s=out["iter"] / out["primaltime"])
+tt = spdist.max_over_ranks(out["totaltime"])
+if rank == 0:
+    out["totaltime_max_over_ranks"] = tt
+    print(json.dumps(out), flush=True)
+h.close()

@@ -98,6 +98,7 @@ _SIGNATURES.update({
     "sdplrp_config_default": [C.POINTER(Config)],
     "sdplrp_solve": [_H, C.POINTER(Config), C.c_int64, _p_f64, _p_f64, C.c_double, C.c_double, C.POINTER(Result), _p_f64],
     "sdplrp_pick_alpha": [_p_f64, C.c_double, _p_f64, _p_f64],
+    "sdplrp_iterate": [_H, C.c_int64, C.c_double, C.c_int32, C.c_int32, _p_f64],
     "sdplrp_fill_uniform": [_H, C.c_int32, C.c_uint64],
 })
 
@@ -433,6 +434,12 @@ class Handle:
             v0, pv = _f64(v0)
         self._check(self.lib.sdplrp_dimacs_errors(self._h, float(normb), float(normC), pv, int(seed), errs.ctypes.data_as(_p_f64)))
         return errs
+
+    def iterate(self, k, alpha_max=1.0, use_armijo=False, update_history=True):
+        """k inner iterations inside the library -> (L, obj, ||G||^2, ||pvio||^2, alpha) of the last one"""
+        out = (C.c_double * 5)()
+        self._check(self.lib.sdplrp_iterate(self._h, int(k), float(alpha_max), int(bool(use_armijo)), int(bool(update_history)), out))
+        return tuple(out)
 
     def fill_uniform(self, mat_id, seed):
         """mat <- U(-1,1) from the counter-based device generator (same matrix for any GPU count / vertex order)"""

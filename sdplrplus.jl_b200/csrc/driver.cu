@@ -150,6 +150,39 @@ void print_row(const sdplrp_config &cfg, i64 T, i64 localiter, i64 it, double L,
     fflush(stdout);
 }
 
+// one pass of the inner loop body of _sdplr (src/sdplr.jl:194-236): L-BFGS direction, descent test with the gradient
+// fallback, line search (exact quartic, or Armijo backtracking for inequality problems), step + gradient + norms.
+// L_val <- the line search's AL value, alpha <- the step, sg <- {obj, ||G||^2, ||pvio||^2}.
+int32_t inner_iteration(sdplrp_handle *h, bool use_armijo, double alpha_max, double *L_val, double *alpha_out, double sg[3]) {
+    double descent = 0.0;
+    SDP_CHECK(sdplrp_lbfgs_dir(h, &descent));
+    if (std::isnan(descent) || descent >= 0.0) SDP_CHECK(sdplrp_use_gradient_direction(h));  // src/sdplr.jl:202-205
+    double alpha = 0.0, bq[5];
+    SDP_CHECK(sdplrp_linesearch_coeffs(h, bq));
+    if (!use_armijo) {
+        if (pick_alpha(bq, alpha_max, &alpha, L_val) != SDPLRP_OK)
+            return fail(h, SDPLRP_ERR_LINESEARCH, "Error: cubic[1] = " + std::to_string(bq[1]) + " should be less than 0.");
+    } else {
+        // linesearch_armijo! (src/linesearch.jl:139-191): sharp AL at alpha_max / 2^k, k = 0..50, c = 1e-4
+        double L0 = 0.0, slope = 0.0, zero = 0.0;
+        SDP_CHECK(sdplrp_armijo_eval(h, &zero, 1, &L0, &slope));
+        double alphas[51], Ls[51];
+        for (int k = 0; k < 51; k++) alphas[k] = alpha_max / pow(2.0, (double)k);
+        int pick = 50;
+        bool found = false;
+        for (int s = 0; s < 51 && !found; s += 15) {
+            const int cnt = std::min(15, 51 - s);
+            SDP_CHECK(sdplrp_armijo_eval(h, alphas + s, cnt, Ls + s, nullptr));
+            for (int k = s; k < s + cnt; k++)
+                if (Ls[k] <= L0 + 1e-4 * alphas[k] * slope) { pick = k; found = true; break; }
+        }
+        alpha = alphas[pick]; *L_val = Ls[pick];
+    }
+    SDP_CHECK(sdplrp_step_g(h, alpha, sg));
+    *alpha_out = alpha;
+    return SDPLRP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -183,6 +216,19 @@ int32_t sdplrp_fill_uniform(sdplrp_handle *h, int32_t mat_id, uint64_t seed) {
     if (mat_id == SDPLRP_MAT_R) { h->CR_valid = false; h->ls_valid = false; }
     if (mat_id == SDPLRP_MAT_D) { h->CD_valid = false; h->ls_valid = false; }
     if (mat_id == SDPLRP_MAT_G) h->gram_g_valid = false;
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_iterate(sdplrp_handle *h, int64_t k, double alpha_max, int32_t use_armijo, int32_t update_history, double out[5]) {
+    if (!h) return SDPLRP_ERR_ARG;
+    if (!h->preprocessed || h->r <= 0) return fail(h, SDPLRP_ERR_STATE, "iterate: no problem / rank set");
+    if (k < 0 || !out) return fail(h, SDPLRP_ERR_ARG, "iterate: bad argument");
+    double L_val = 0.0, alpha = 0.0, sg[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = 0; i < k; i++) {
+        SDP_CHECK(inner_iteration(h, use_armijo != 0, alpha_max, &L_val, &alpha, sg));
+        if (update_history && h->hist > 0) SDP_CHECK(sdplrp_lbfgs_update(h, alpha));
+    }
+    out[0] = L_val; out[1] = sg[0]; out[2] = sg[1]; out[3] = sg[2]; out[4] = alpha;
     return SDPLRP_OK;
 }
 
@@ -239,33 +285,9 @@ int32_t sdplrp_solve(sdplrp_handle *h, const sdplrp_config *cfgp, int64_t r0, co
         i64 localiter = 0;
         while (grad_norm > cur_gtol) {
             localiter++; it++;
-            double descent = 0.0;
-            SDP_CHECK(sdplrp_lbfgs_dir(h, &descent));
-            if (std::isnan(descent) || descent >= 0.0) SDP_CHECK(sdplrp_use_gradient_direction(h));  // src/sdplr.jl:202-205
             const double lastval = L_val;
-            double alpha = 0.0, bq[5];
-            SDP_CHECK(sdplrp_linesearch_coeffs(h, bq));
-            if (!use_armijo) {
-                if (pick_alpha(bq, cfg.alpha_max, &alpha, &L_val) != SDPLRP_OK)
-                    return fail(h, SDPLRP_ERR_LINESEARCH, "Error: cubic[1] = " + std::to_string(bq[1]) + " should be less than 0.");
-            } else {
-                // linesearch_armijo! (src/linesearch.jl:139-191): sharp AL at alpha_max / 2^k, k = 0..50, c = 1e-4
-                double L0 = 0.0, slope = 0.0, zero = 0.0;
-                SDP_CHECK(sdplrp_armijo_eval(h, &zero, 1, &L0, &slope));
-                double alphas[51], Ls[51];
-                for (int k = 0; k < 51; k++) alphas[k] = cfg.alpha_max / pow(2.0, (double)k);
-                int pick = 50;
-                bool found = false;
-                for (int s = 0; s < 51 && !found; s += 15) {
-                    const int cnt = std::min(15, 51 - s);
-                    SDP_CHECK(sdplrp_armijo_eval(h, alphas + s, cnt, Ls + s, nullptr));
-                    for (int k = s; k < s + cnt; k++)
-                        if (Ls[k] <= L0 + 1e-4 * alphas[k] * slope) { pick = k; found = true; break; }
-                }
-                alpha = alphas[pick]; L_val = Ls[pick];
-            }
-            double sg[3];
-            SDP_CHECK(sdplrp_step_g(h, alpha, sg));
+            double alpha = 0.0, sg[3];
+            SDP_CHECK(inner_iteration(h, use_armijo, cfg.alpha_max, &L_val, &alpha, sg));
             obj = sg[0]; grad_norm = sqrt(sg[1]) / gscale; pvio_norm = sqrt(sg[2]) / pscale;
             const double rel_delta = (lastval - L_val) / std::max(1.0, std::max(fabs(L_val), fabs(lastval)));
             if (rel_delta < cfg.fprec * kEps) break;  // src/sdplr.jl:238-241

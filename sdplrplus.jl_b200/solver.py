@@ -230,6 +230,10 @@ class B200Engine:
     def dual_update(self):
         self.h.dual_update()
 
+    def iterate(self, k, use_armijo=False, alpha_max=1.0, update_history=True):
+        """k passes of the inner loop body driven inside the library (sdplrp_iterate)."""
+        return self.h.iterate(k, alpha_max, use_armijo, update_history)
+
     def close(self):
         self.h.close()
 
@@ -521,10 +525,13 @@ def sdplr(C, As, b, r, constraint_types=None, config: Optional[BurerMonteiroConf
     return ans
 
 
-def run_inner_iterations(engine, k, use_armijo=False, alpha_max=1.0, update_history=True):
+def run_inner_iterations(engine, k, use_armijo=False, alpha_max=1.0, update_history=True, native=False):
     """k passes of the hot loop body of _sdplr (src/sdplr.jl:190-246) without the tolerance
     logic: direction, descent test, line search, step, gradient, L-BFGS update.  Used by
-    bench.py and the trajectory tests.  Returns the last (L, obj, gnorm2, pnorm2, alpha)."""
+    bench.py and the trajectory tests.  Returns the last (L, obj, gnorm2, pnorm2, alpha).  native=True runs the same
+    sequence of entry points inside the library (sdplrp_iterate) when the engine offers it."""
+    if native and hasattr(engine, "iterate"):
+        return engine.iterate(k, use_armijo, alpha_max, update_history)
     out = None
     for _ in range(k):
         descent = engine.lbfgs_dir()

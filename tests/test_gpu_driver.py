@@ -116,3 +116,19 @@ def test_fill_uniform_is_layout_independent(sp, gpu_handle_factory):
     assert R.shape == (3000, 7) and -1.0 <= R.min() < -0.99 and 0.99 < R.max() < 1.0
     assert abs(R.mean()) < 0.02 and abs(R.var() - 1.0 / 3.0) < 0.02
     assert np.unique(R).size == R.size
+
+
+def test_iterate_matches_python_loop(sp, handle):
+    """sdplrp_iterate == run_inner_iterations driven call by call (what bench.py times)"""
+    C, As, bs = sp.problems.maxcut(g1_graph())
+    data = sp.SDPData(C, As, bs)
+    Rt0 = 2 * np.random.default_rng(0).random((data.n, 10)) - 1
+    outs = []
+    for native in (False, True):
+        eng = sp.B200Engine(data, handle=handle)
+        eng.init_vars(10, Rt0, np.zeros(data.m), 2.0, 4)
+        eng.fg()
+        last = sp.solver.run_inner_iterations(eng, 25, native=native)
+        outs.append((np.array(last), eng.get_R()))
+    np.testing.assert_allclose(outs[1][0], outs[0][0], rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(outs[1][1], outs[0][1], rtol=1e-7, atol=1e-9)

@@ -186,10 +186,40 @@ lbfgs_clear!(his::LBFGSHistory{<:Any,<:Any,DevMat}) =                           
 function dual_obj(data, var::SolverVars{Ti,Tv,DevMat}, aux::B200Auxiliary, trace_bound, iter; highprecision=false) where {Ti,Tv}  # src/coreop.jl:376-415
     v0 = randn(data.n)                                        # src/coreop.jl:473: the start vector stays Julia's
     dual, lam, steps = Ref(0.0), Ref(0.0), Ref{Int64}(0)
-    GC.@preserve v0 check(aux.h, ccall((:sdplrp_dual_obj, LIB), Int32,
-        (Ptr{Cvoid}, Float64, Int64, Ptr{Float64}, UInt64, Ref{Float64}, Ref{Float64}, Ref{Int64}),
-        aux.h.ptr, trace_bound, iter, v0, 0, dual, lam, steps))
-    return dual[]
+    if highprecision   # SDP_S_eigval (GenericArpack symeigs, src/coreop.jl:386-400) -> thick-restart Lanczos on the device
+        GC.@preserve v0 check(aux.h, ccall((:sdplrp_dual_obj_highprecision, LIB), Int32,
+            (Ptr{Cvoid}, Float64, Ptr{Float64}, UInt64, Ref{Float64}, Ref{Float64}, Ref{Int64}),
+            aux.h.ptr, trace_bound, v0, 0, dual, lam, steps))
+    else
+        GC.@preserve v0 check(aux.h, ccall((:sdplrp_dual_obj, LIB), Int32,
+            (Ptr{Cvoid}, Float64, Int64, Ptr{Float64}, UInt64, Ref{Float64}, Ref{Float64}, Ref{Int64}),
+            aux.h.ptr, trace_bound, iter, v0, 0, dual, lam, steps))
+    end
+    return dual[], lam[]
+end
+
+"""
+`SDP_S_eigval(var, aux, nevs, true; which=:SA, ncv, tol, maxiter)` (src/coreop.jl:351-374) on the S last assembled.
+"""
+function SDPLRPlus.SDP_S_eigval(var::SolverVars{Ti,Tv,DevMat}, aux::B200Auxiliary, nevs, preprocessed::Bool=false;
+                                ncv=min(100, aux.n), tol=0.0, maxiter=1000000, kwargs...) where {Ti,Tv}
+    preprocessed || check(aux.h, ccall((:sdplrp_At_preprocess, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), aux.h.ptr, var.y))
+    ev = zeros(nevs); v0 = randn(aux.n)
+    dt = @elapsed GC.@preserve ev v0 check(aux.h, ccall((:sdplrp_S_eigval, LIB), Int32,
+        (Ptr{Cvoid}, Int64, Int64, Float64, Int64, Ptr{Float64}, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
+        aux.h.ptr, nevs, ncv, tol, maxiter, v0, 0, ev, C_NULL, C_NULL, C_NULL))
+    return ev, dt
+end
+
+"""
+`DIMACS_errors(data, var, aux)` (src/coreop.jl:426-453) in one call.
+"""
+function SDPLRPlus.DIMACS_errors(data, var::SolverVars{Ti,Tv,DevMat}, aux::B200Auxiliary) where {Ti,Tv}
+    errs = zeros(6); v0 = randn(data.n)
+    GC.@preserve errs v0 check(aux.h, ccall((:sdplrp_dimacs_errors, LIB), Int32,
+        (Ptr{Cvoid}, Float64, Float64, Ptr{Float64}, UInt64, Ptr{Float64}),
+        aux.h.ptr, norm(data.b, 2), norm(data.C, 2), v0, 0, errs))
+    return errs
 end
 
 # λ_i <- min(ub_i, λ_i − σ v_i) (src/sdplr.jl:358-362) happens on the device; the host copy is refreshed for `best_λ`
@@ -214,6 +244,53 @@ function sdplr(C, As, b, r; device=0, kwargs...)
     ans = _sdplr(data, var, aux, SolverStats{Float64}(), config)
     ans["Rt"] = Array(var.Rt); ans["Rt0"] = Rt0
     return ans
+end
+
+# ---- the whole solve as ONE call (SURVEY.md 8f/f1): the native driver of csrc/driver.cu runs the loop of
+# src/sdplr.jl:140-449 inside the library.  Field order = sdplrp_config / sdplrp_result of include/sdplrp_b200.h.
+struct NativeConfig
+    ptol::Float64; gtol::Float64; objtol::Float64; sigma_0::Float64; sigmafac::Float64; maxtime::Float64; printfreq::Float64
+    fprec::Float64; prior_trace_bound::Float64; alpha_max::Float64
+    maxmajoriter::Int64; maxiter::Int64; numlbfgsvecs::Int64; rankupd_tol::Int64; printlevel::Int64
+    gtol_relative::Int64; ptol_relative::Int64; objtol_relative::Int64; eval_DIMACS_errs::Int64; eigval_highprecision::Int64
+    seed::UInt64
+end
+struct NativeResult
+    sigma::Float64; grad_norm::Float64; primal_vio::Float64; obj::Float64; L::Float64; max_dual_value::Float64
+    min_duality_gap::Float64; totaltime::Float64; dual_time::Float64; primaltime::Float64; DIMACS_time::Float64
+    DIMACS_errs::NTuple{6,Float64}
+    iter::Int64; majoriter::Int64; lanczos_steps::Int64; r::Int64; status::Int64
+end
+NativeConfig(c::BurerMonteiroConfig; seed=0) = NativeConfig(c.ptol, c.gtol, c.objtol, c.σ_0, c.σfac, c.maxtime, c.printfreq, c.fprec,
+    c.prior_trace_bound, 1.0, c.maxmajoriter, c.maxiter, c.numlbfgsvecs, c.rankupd_tol, c.printlevel,
+    c.gtol_mode == "relative", c.ptol_mode == "relative", c.objtol_mode == "relative", c.eval_DIMACS_errs, c.eigval_highprecision, seed)
+
+"""
+    sdplr_native(C, As, b, r; kwargs...)
+
+`sdplr` with the outer loop inside the library (`sdplrp_solve`).  Rt0 / λ0 come from `SolverVars(data, r, config)` as
+in the reference; the eigenvalue start vectors and the random point of a rank update come from the device generator.
+"""
+function sdplr_native(C, As, b, r; device=0, seed=0, kwargs...)
+    config = BurerMonteiroConfig()
+    for (k, v) in kwargs
+        hasfield(BurerMonteiroConfig, k) ? setfield!(config, k, v) : @error "Unrecognized keyword argument $k"
+    end
+    data = SDPData(C, As, b)
+    aux = B200Auxiliary(data; device)
+    host = SolverVars(data, r, config)
+    Rt0 = Matrix(host.Rt); λ0 = Vector(host.λ)
+    cfg = Ref(NativeConfig(config; seed)); res = Ref{NativeResult}(); best = zeros(data.m + 1)
+    GC.@preserve Rt0 λ0 best check(aux.h, ccall((:sdplrp_solve, LIB), Int32,
+        (Ptr{Cvoid}, Ref{NativeConfig}, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ref{NativeResult}, Ptr{Float64}),
+        aux.h.ptr, cfg, r, Rt0, λ0, norm(b, 2), norm(C, 2), res, best))
+    R = res[]
+    Rt = Array(DevMat(aux.h, MAT_R, Int(R.r), data.n))
+    return Dict("Rt" => Rt, "lambda" => best, "Rt0" => Rt0, "lambda0" => λ0, "sigma" => R.sigma, "grad_norm" => R.grad_norm,
+        "primal_vio" => R.primal_vio, "obj" => R.obj, "max_dual_value" => R.max_dual_value, "min_duality_gap" => R.min_duality_gap,
+        "totaltime" => R.totaltime, "dual_time" => R.dual_time, "primaltime" => R.primaltime, "iter" => R.iter,
+        "majoriter" => R.majoriter, "DIMACS_errs" => collect(R.DIMACS_errs), "ptol" => config.ptol, "objtol" => config.objtol,
+        "fprec" => config.fprec, "rankupd_tol" => config.rankupd_tol, "r" => Int(R.r))
 end
 
 end # module

@@ -109,9 +109,36 @@ def algorithmic_bytes(n, m, r, nnzT, nnzF, Ec, h, rows_local):
 
 
 def generate(sp, n, edges, seed):
+    """The C5 problem in the ABI's triplet form.  With several ranks, rank 0 generates and broadcasts: torch's CUDA
+    generator is reproducible per device index only (rank 1 draws a different graph from the same seed), and every rank
+    must preprocess the SAME problem -- the library replicates the pattern and partitions its rows."""
     import torch
+    import torch.distributed as dist
     t0 = time.perf_counter()
-    asm, b, normC, E = sp.problems.powerlaw_maxcut_assembled(n, edges, seed)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    root = (not multi) or dist.get_rank() == 0
+    if root:
+        asm, b, normC, E = sp.problems.powerlaw_maxcut_assembled(n, edges, seed)
+    if multi:
+        from sdplrplus.jl_b200.types import AssembledSparse
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        meta = torch.zeros(3, dtype=torch.float64, device=dev)
+        if root:
+            meta.copy_(torch.tensor([float(asm.I.size), float(normC), float(E)], dtype=torch.float64))
+        dist.broadcast(meta, 0)
+        nnz, normC, E = int(meta[0].item()), float(meta[1].item()), int(meta[2].item())
+        got = {}
+        for name, dt in (("I", torch.int64), ("J", torch.int64), ("V", torch.float64)):
+            t = torch.from_numpy(getattr(asm, name)).to(dev) if root else torch.empty(nnz, dtype=dt, device=dev)
+            dist.broadcast(t, 0)
+            if not root:
+                got[name] = t.cpu().numpy()
+            del t
+        if not root:
+            nnzC = nnz - n   # n one-entry diagonal constraints, then C (problems.powerlaw_maxcut_assembled)
+            mat_off = np.concatenate([np.arange(n + 1, dtype=np.int64), [n + nnzC]]).astype(np.int64)
+            asm = AssembledSparse(n, n, mat_off, got["I"], got["J"], got["V"], np.arange(1, n + 2, dtype=np.int64), [])
+            b = np.ones(n)
     if torch.cuda.is_available():
         torch.cuda.synchronize()
         torch.cuda.empty_cache()

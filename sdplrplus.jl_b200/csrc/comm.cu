@@ -246,6 +246,23 @@ int32_t comm_gather_cvec(sdplrp_handle *h, double *v) {
     return SDPLRP_OK;
 }
 
+// SPMD contract: every rank must have been handed the same problem.  `value` is a 64-bit checksum of this rank's input;
+// the ranks agree iff max == min of both halves (all-reduced as exactly representable doubles).
+int32_t comm_check_same(sdplrp_handle *h, unsigned long long value, const char *what) {
+    if (h->world <= 1) return SDPLRP_OK;
+    double *d = h->dscal + SC_LANCZOS + 12;
+    double v[4] = {(double)(value >> 32), (double)(value & 0xFFFFFFFFull), 0.0, 0.0};
+    v[2] = -v[0]; v[3] = -v[1];
+    CUDA_TRY(h, cudaMemcpyAsync(d, v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
+    NCCL_TRY(h, ncclAllReduce(d, d, 4, ncclDouble, ncclMax, (ncclComm_t)h->nccl, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(v, d, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (v[0] != -v[2] || v[1] != -v[3])
+        return fail(h, SDPLRP_ERR_ARG, std::string("multi-GPU: the ranks were given different ") + what +
+                                           " (every rank must make the same calls with the same data)");
+    return SDPLRP_OK;
+}
+
 int32_t comm_reduce_scalars(sdplrp_handle *h, int slot, int count) {
     if (h->world <= 1) return SDPLRP_OK;
     NCCL_TRY(h, ncclAllReduce(h->dscal + slot, h->dscal + slot, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)h->nccl, h->stream));

@@ -380,6 +380,7 @@ int32_t comm_gather_rows(sdplrp_handle *h, double *p, int mat_id);
 int32_t comm_reduce_mvec(sdplrp_handle *h, double *v1, double *v2);   // shared slots [n_sd, m] only
 int32_t comm_gather_cvec(sdplrp_handle *h, double *v);                // make every per-row-constraint slot current on every rank
 int32_t comm_reduce_scalars(sdplrp_handle *h, int slot, int count);
+int32_t comm_check_same(sdplrp_handle *h, unsigned long long value, const char *what);  // error unless all ranks pass the same value
 int32_t comm_reduce_ptr(sdplrp_handle *h, double *p, int count);
 int32_t comm_step_R(sdplrp_handle *h, double alpha);
 

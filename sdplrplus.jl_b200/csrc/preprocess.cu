@@ -38,6 +38,22 @@ __device__ __forceinline__ unsigned long long make_key(int row, int col) {
     return ((unsigned long long)(unsigned)col << 32) | (unsigned)row;
 }
 
+// order-sensitive 64-bit checksum of the input triplets (multi-GPU: every rank must preprocess the same problem)
+__global__ void k_triplet_checksum(i64 nnz, const int64_t *__restrict__ I, const int64_t *__restrict__ J, const double *__restrict__ V,
+                                   unsigned long long *__restrict__ out) {
+    unsigned long long acc = 0ull;
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < nnz; k += (i64)gridDim.x * blockDim.x) {
+        unsigned long long x = (unsigned long long)I[k] * 0x9E3779B97F4A7C15ull ^ (unsigned long long)J[k] * 0xD6E8FEB86659FD93ull ^
+                               (unsigned long long)__double_as_longlong(V[k]) ^ ((unsigned long long)k << 17);
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        acc += x ^ (x >> 31);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);   // integer sum: order-independent, deterministic
+}
+
 // coordinates -> sort keys + upper-triangle flags (src/preprocess.jl:4-16, 56-82)
 __global__ void k_keys(i64 nnz, i64 n, const int64_t *__restrict__ I, const int64_t *__restrict__ J,
                        unsigned long long *__restrict__ keyF, int *__restrict__ flag, int *__restrict__ errw) {
@@ -600,6 +616,18 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
     }
     CUDA_TRY(h, cudaMemsetAsync(errw, 0, sizeof(int), st));
     CUDA_TRY(h, cudaMemsetAsync(flag, 0, (size_t)(nnz + 1) * sizeof(int), st));
+
+    if (h->world > 1) {  // SPMD contract check before anything is built from the data
+        unsigned long long *dchk = tmp.get<unsigned long long>(h, 1, &rc);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaMemsetAsync(dchk, 0, sizeof(unsigned long long), st));
+        if (nnz > 0) { k_triplet_checksum<<<GS, TPB, 0, st>>>(nnz, dI, dJ, dV, dchk); KLAUNCH(h); }
+        unsigned long long chk = 0ull;
+        CUDA_TRY(h, cudaMemcpyAsync(&chk, dchk, sizeof(chk), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+        chk ^= (unsigned long long)n * 0x100000001B3ull ^ (unsigned long long)nnz;
+        SDP_CHECK(comm_check_same(h, chk, "problem (sdplrp_preprocess triplets)"));
+    }
 
     // ---- keys, triu compaction ---------------------------------------------
     if (nnz > 0) { k_keys<<<GS, TPB, 0, st>>>(nnz, n, dI, dJ, keyF, flag, errw); KLAUNCH(h); }

@@ -76,3 +76,33 @@ def test_balanced_row_blocks_weights():
     rowptr = np.arange(0, 1001 * 5, 5)                  # 1000 rows of 5 nonzeros
     b = spdist.balanced_row_blocks(rowptr, 4)
     assert b.tolist() == [0, 250, 500, 750, 1000]
+
+
+def _gen_worker(rank, world, port, results):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch
+    import torch.distributed as dist
+    import sdplrplus.jl_b200 as sp
+    from sdplrplus.jl_b200 import dist as spdist
+    import bench
+    spdist.init_process_group(backend="gloo")
+    torch.manual_seed(100 + rank)          # the ranks' own generators disagree: only rank 0's graph may be used
+    asm, b, normC, E, _ = bench.generate(sp, 3000, 20000, 42)
+    results[rank] = (asm.I.tolist(), asm.J.tolist(), asm.V.tolist(), asm.mat_off.tolist(), asm.gids.tolist(), b.tolist(), normC, E)
+    dist.destroy_process_group()
+
+
+def test_every_rank_gets_rank0s_problem():
+    """bench.generate under world 2: rank 0 draws the graph, the triplets are broadcast (a per-device generator would give
+    every rank its own graph, which is what the full-size 2-GPU run of round 1 caught)."""
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_gen_worker, args=(world, port, results), nprocs=world, join=True)
+        r0, r1 = results[0], results[1]
+    assert r0 == r1
+    I, J, V, off, gids, b, normC, E = r0
+    assert len(I) == len(J) == len(V) == off[-1] and off[-2] == 3000 and gids[-1] == 3001 and len(b) == 3000 and E > 15000

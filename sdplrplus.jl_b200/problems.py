@@ -211,15 +211,19 @@ def powerlaw_maxcut_assembled(n, target_edges, seed, device=None, exponent=2.3):
     g.manual_seed(int(seed))
     gamma = 1.0 / (exponent - 1.0)
     i0 = max(1.0, n * 1e-5)
-    w = (torch.arange(n, dtype=torch.float64, device=dev) + i0) ** (-gamma)
-    cdf = torch.cumsum(w, 0)
-    cdf = cdf / cdf[-1]
+    # the cumulative weights are summed on the host: a CUDA cumsum is not bitwise reproducible from run to run, and a cdf
+    # that moves in its last bits moves a handful of the 8e7 sampled endpoints (seen as 1e-9 relative differences in <C, RR'>)
+    w = (np.arange(n, dtype=np.float64) + i0) ** (-gamma)
+    cdf_h = np.cumsum(w)
+    cdf_h /= cdf_h[-1]
+    cdf = torch.from_numpy(cdf_h).to(dev)
+    del w, cdf_h
     M = int(target_edges * 1.03)
     u = torch.searchsorted(cdf, torch.rand(M, dtype=torch.float64, device=dev, generator=g)).clamp_(max=n - 1)
     v = torch.searchsorted(cdf, torch.rand(M, dtype=torch.float64, device=dev, generator=g)).clamp_(max=n - 1)
     perm = torch.randperm(n, device=dev, generator=g)
     u, v = perm[u], perm[v]
-    del cdf, w, perm
+    del cdf, perm
     keep = u != v
     lo, hi = torch.minimum(u, v)[keep], torch.maximum(u, v)[keep]
     del u, v, keep

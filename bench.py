@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--python-loop", action="store_true", help="drive the iterations from Python (one ctypes call per seam function) "
                     "instead of sdplrp_iterate")
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE",
+                    help="sdplrp_set_option before preprocessing (experiments: spmm_phases=1, spmm_kernel=1, ...)")
     ap.add_argument("--lanczos", type=int, default=0, help="also time this many Lanczos steps (reported separately)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -242,6 +244,9 @@ def main():
     rank, world, local = spdist.init_process_group()
     torch.cuda.set_device(local)
     handle = spdist.make_handle(sp.Handle)
+    for kv in args.option:
+        key, val = kv.split("=", 1)
+        handle.set_option(key, float(val))
     n, r, h = args.n, args.rank, 4
 
     asm, b, normC, E, gen_s = generate(sp, n, args.edges, args.seed)
@@ -364,7 +369,7 @@ def main():
             "host_wall_ms_per_step": 1e3 * t_wall / args.steps, "comm_ms_per_step": comm_ms / args.steps,
             "setup": {"graph_generation_s": gen_s, "preprocess_s": preprocess_s},
             "last_iterate": {"L": last[0], "obj": last[1], "gnorm2": last[2], "pnorm2": last[3], "alpha": last[4]},
-            "lanczos": lanczos, "loop": "sdplrp_iterate (native)" if native else "python (one ABI call per seam function)",
+            "lanczos": lanczos, "options": args.option, "loop": "sdplrp_iterate (native)" if native else "python (one ABI call per seam function)",
         }
         print(json.dumps(line), flush=True)
     handle.close()

@@ -93,6 +93,8 @@ void *sdplrp_stream(sdplrp_handle *h);
  *                 sdplrp_preprocess.  Invisible at the ABI (every upload/download converts).
  *   "hot_rows"    leading rows of the gathered factor pinned in L2 (evict_last); -1 = sized from L2
  *   "spmm_kernel" 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel (experimental)
+ *   "spmm_phases" 0 = one sweep per gather pass (default); 1 = two sweeps, hub columns (an L2-sized prefix of the
+ *                 hub-first order) then tail columns; k > 1 = k hub columns.  One GPU, relabelled patterns only (experimental)
  *   "fused_tail"  1 = sdplrp_step_g uses the fused row pass (default), 0 = step and g separately
  *   "lbfgs_kernel" 1 = two-loop recursion on coefficients over directly computed dot products (default,
  *                 numlbfgsvecs <= 8), 0 = literal vector two-loop */

@@ -323,6 +323,7 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
     if (k == "relabel") { h->relabel_mode = value < 0 ? -1 : (value > 0 ? 1 : 0); return SDPLRP_OK; }  // before preprocess
     if (k == "hot_rows") { h->hot_rows = (i64)value; return SDPLRP_OK; }
     if (k == "spmm_kernel") { h->spmm_kernel = (int)value; return SDPLRP_OK; }
+    if (k == "spmm_phases") { h->spmm_phases = value < 0 ? 0 : (int)value; return SDPLRP_OK; }
     if (k == "spmm_unroll") { h->spmm_unroll = (int)value; return SDPLRP_OK; }
     if (k == "spmm_g0") { h->spmm_g0 = (int)value; return SDPLRP_OK; }
     if (k == "fused_tail") { h->fused_tail = value != 0; return SDPLRP_OK; }

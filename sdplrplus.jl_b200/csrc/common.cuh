@@ -101,6 +101,10 @@ struct sdplrp_handle {
     int spmm_unroll = 8;                                 // nonzeros per predicated block of the class-0 register kernel (4 or 8)
     int spmm_g0 = 1;                                     // class-0 lane groups of exactly r/2 lanes (0: next power of two)
     int spmm_kernel = 0;                                 // 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel
+    int spmm_phases = 0;                                 // 0 = one sweep per gather pass (default); 1 = hub | tail two-phase pass with an
+                                                         // L2-sized hub prefix; > 1 = that many hub columns (gradient.cu, grad_obj_spmm)
+    int *row_mid = nullptr;                              // n: first tail-column position of every row (two-phase pass)
+    i64 row_mid_cols = -1;                               // hub prefix row_mid was built for
     // per-entry lists in reference order (E_c)
     int *matptr = nullptr;     // nA+1
     int *mat_gid = nullptr;    // nA   0-based global slot of each sparse matrix

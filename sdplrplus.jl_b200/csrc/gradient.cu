@@ -173,10 +173,13 @@ struct Acc<2> {
 // EPI 0: Y_i = scale * acc                                   (seam-level At!)
 // EPI 1: Y_i = scale * (acc + yobj*ADD_i); sum0 += |Y_i|^2    (gradient)
 // EPI 2: Y_i = acc; sum0 += <X_i, acc>; sum1 += <X_i, Z_i>    (CD = C*D with the line-search dots; CR = C*R with obj)
+// EPI 3: Y_i += scale * acc
+// EPI 4: Y_i += acc, then the sums of EPI 2 on the total     (second phase of the two-phase pass)
 struct RowArgs {
     const int *rows;   // compacted row list of this class, nullptr = identity over [0, n_rows)
     i64 n_rows;
     const int *ptr, *idx;
+    const int *beg_arr, *end_arr;  // row i covers [beg_arr[i], end_arr[i]); nullptr = ptr[i] / ptr[i+1] (two-phase pass: hub | tail columns)
     const double *val;
     const int *src;    // IND: value = val[src[k]]
     const double *X;
@@ -208,6 +211,14 @@ __device__ __forceinline__ void row_epilogue(const RowArgs &a, i64 i, Acc<VEC> (
                 acc[u].scale(a.scale);
             } else if (EPI == 3) {
                 acc[u].accumulate_onto(a.scale, a.Y + off);  // Y_i + scale*acc
+            } else if (EPI == 4) {
+                acc[u].accumulate_onto(1.0, a.Y + off);      // hub part (phase one) + tail part
+                s0 += acc[u].dot_ld(a.X + off);
+                if (a.Z) {
+                    Acc<VEC> t;
+                    t.zero(); t.fma(1.0, a.X + off);
+                    s1 += t.dot_ld(a.Z + off);
+                }
             } else if (EPI == 1) {
                 if (a.ADD) acc[u].scale_add(a.scale, a.yobj, a.ADD + off); else acc[u].scale(a.scale);
                 s0 += acc[u].norm2();
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(TPB) k_rows_group(RowArgs a) {
     for (i64 q = group; q < a.n_rows; q += n_groups) {
         const i64 i = a.rows ? a.rows[q] : q;
         if (i < a.own_lo || i >= a.own_hi) continue;
-        const int beg = a.ptr[i], end = a.ptr[i + 1];
+        const int beg = a.beg_arr ? a.beg_arr[i] : a.ptr[i], end = a.end_arr ? a.end_arr[i] : a.ptr[i + 1];
         Acc<VEC> acc[MAXU];
 #pragma unroll
         for (int u = 0; u < MAXU; u++) acc[u].zero();
@@ -297,7 +308,8 @@ __global__ void __launch_bounds__(TPB) k_rows_warp(RowArgs a) {
     for (i64 q = warp; q < a.n_rows; q += n_warps) {  // warp-uniform
         const i64 i = CHUNK ? a.chunk_row[q] : (a.rows ? a.rows[q] : q);
         if (i < a.own_lo || i >= a.own_hi) continue;
-        const int beg = CHUNK ? a.chunk_start[q] : a.ptr[i], end = CHUNK ? a.chunk_end[q] : a.ptr[i + 1];
+        const int beg = CHUNK ? a.chunk_start[q] : (a.beg_arr ? a.beg_arr[i] : a.ptr[i]);
+        const int end = CHUNK ? a.chunk_end[q] : (a.end_arr ? a.end_arr[i] : a.ptr[i + 1]);
         Acc<VEC> acc[MAXU];
 #pragma unroll
         for (int u = 0; u < MAXU; u++) acc[u].zero();
@@ -531,8 +543,11 @@ struct Csr {
     const RowClasses *cls;
 };
 
+// long_empty: the long rows (class 2) take the warp-per-row kernel over an EMPTY range (second phase of the two-phase pass:
+// their nonzeros were all handled, chunked, in the first phase; only the epilogue is left)
 template <int VEC, int MAXU, bool IND, int EPI>
-int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const TileLayout &longs, double *sums /* 3 x 2 or null */) {
+int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const TileLayout &longs, double *sums /* 3 x 2 or null */,
+                       bool long_empty = false) {
     cudaStream_t st = h->stream;
     const int gpb = TPB / a.G;
     const int gpb0 = TPB / a.G0;
@@ -549,6 +564,10 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
             else k_rows_group<VEC, MAXU, IND, EPI, 4><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
         } else if (c == 1) {
             k_rows_warp<VEC, MAXU, IND, EPI, false><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
+        } else if (long_empty) {
+            RowArgs b = a;
+            b.beg_arr = a.ptr + 1; b.end_arr = a.ptr + 1;
+            k_rows_warp<VEC, MAXU, IND, EPI, false><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
         } else {
             // long rows: one warp per chunk, then the per-row combination with the epilogue
             const i64 need = longs.n_chunks * (i64)a.r;
@@ -572,7 +591,8 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
 }
 
 template <bool IND, int EPI>
-int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const TileLayout &longs, double *sums) {
+int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const TileLayout &longs, double *sums, bool long_empty = false,
+                   i64 hot_override = -1) {
     const int r = h->r;
     const bool vec2 = (r % 2 == 0);
     const int nv = vec2 ? r / 2 : r;
@@ -583,15 +603,46 @@ int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const Til
     a.own_lo = h->row_lo;
     a.own_hi = h->row_hi;
     a.G0 = (nv <= 32 && h->spmm_g0) ? nv : a.G;   // class 0: exactly one lane per piece
-    a.hot_rows = (int)tile_hot_rows(h);
+    a.hot_rows = (int)(hot_override >= 0 ? hot_override : tile_hot_rows(h));
     const int units = (nv + a.G - 1) / a.G;
     if (units > 4) return fail(h, SDPLRP_ERR_ARG, "rank too large for the sparse kernels (r <= 256 even / 128 odd)");
     if (vec2) {
-        if (units == 1) return launch_classes<2, 1, IND, EPI>(h, a, cls, longs, sums);
-        return launch_classes<2, 4, IND, EPI>(h, a, cls, longs, sums);
+        if (units == 1) return launch_classes<2, 1, IND, EPI>(h, a, cls, longs, sums, long_empty);
+        return launch_classes<2, 4, IND, EPI>(h, a, cls, longs, sums, long_empty);
     }
-    if (units == 1) return launch_classes<1, 1, IND, EPI>(h, a, cls, longs, sums);
-    return launch_classes<1, 4, IND, EPI>(h, a, cls, longs, sums);
+    if (units == 1) return launch_classes<1, 1, IND, EPI>(h, a, cls, longs, sums, long_empty);
+    return launch_classes<1, 4, IND, EPI>(h, a, cls, longs, sums, long_empty);
+}
+
+// mid[i] = first position of row i whose column is >= hub_cols (columns are ascending inside a row, hubs first)
+__global__ void k_row_split(i64 n, const int *__restrict__ ptr, const int *__restrict__ idx, int hub_cols, int *__restrict__ mid) {
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        int lo = ptr[i], hi = ptr[i + 1];
+        while (lo < hi) {
+            const int m = lo + ((hi - lo) >> 1);
+            if (idx[m] < hub_cols) lo = m + 1; else hi = m;
+        }
+        mid[i] = lo;
+    }
+}
+
+// Two-phase gather pass (option "spmm_phases", off by default; DESIGN.md section 8, profiles/r1_hub_tail_analysis.md):
+// every row first takes its hub columns (an L2-sized prefix of the gathered factor), then -- in a second sweep over the
+// rows -- its tail columns, so that the random tail fills do not evict the hub rows while they are still being reused.
+// Only for the hub-first internal order on one GPU (the multi-GPU deal spreads the hubs over the rank blocks).
+static i64 phase_hub_cols(const sdplrp_handle *h) {
+    if (h->spmm_phases <= 0 || !h->relabeled || h->dealt || h->world > 1 || h->nnzF <= 0) return 0;
+    const i64 want = h->spmm_phases == 1 ? (i64)(64.0 * 1024 * 1024) / (8 * (i64)std::max(1, h->r)) : (i64)h->spmm_phases;
+    return std::min<i64>(want, h->n);
+}
+static int32_t ensure_row_mid(sdplrp_handle *h, i64 hub_cols) {
+    if (h->row_mid && h->row_mid_cols == hub_cols) return SDPLRP_OK;
+    SDP_CHECK(dev_alloc(h, &h->row_mid, h->n));
+    k_row_split<<<grid_for(h->n, TPB, 8 * kNumSM), TPB, 0, h->stream>>>(h->n, h->full_ptr, h->full_idx, (int)hub_cols, h->row_mid);
+    KLAUNCH(h);
+    CUDA_TRY(h, cudaGetLastError());
+    h->row_mid_cols = hub_cols;
+    return SDPLRP_OK;
 }
 
 int32_t add_lowrank(sdplrp_handle *h, const double *X, double *Y, double scale) {
@@ -689,6 +740,14 @@ int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double
     RowArgs a = {};
     a.ptr = h->full_ptr; a.idx = h->full_idx; a.val = h->Cfull; a.src = nullptr;
     a.X = X; a.Y = Y; a.Z = Z; a.scale = 1.0;
+    const i64 hub_cols = phase_hub_cols(h);
+    if (hub_cols > 0 && hub_cols < h->n) {
+        SDP_CHECK(ensure_row_mid(h, hub_cols));
+        a.end_arr = h->row_mid;                       // phase one: hub columns (long rows: everything, chunked), plain store
+        SDP_CHECK((launch_csr<false, 0>(h, a, h->full_cls, h->full_long, nullptr, false, hub_cols)));
+        a.beg_arr = h->row_mid; a.end_arr = nullptr;  // phase two: tail columns on top, with the fused dots of the pass
+        return launch_csr<false, 4>(h, a, h->full_cls, h->full_long, sums6, true, hub_cols);
+    }
     return launch_csr<false, 2>(h, a, h->full_cls, h->full_long, sums6);
 }
 

@@ -29,7 +29,10 @@ def oracle_mod():
 # kernel configurations every GPU parity test runs under: the product default (auto relabeling,
 # async-copy tile SpMM), forced hub-first relabeling (exercises every permuting copy on the small
 # regular test graphs too), and the alternative kernels (async-copy tile-stream SpMM, literal vector two-loop)
-GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "tile": {"relabel": 1, "spmm_kernel": 1, "lbfgs_kernel": 0}}
+# "phases": the two-phase (hub | tail columns) gather pass with a 5-column hub prefix, so that both phases and the
+# accumulate-with-dots epilogue are non-trivial on the small test graphs
+GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "tile": {"relabel": 1, "spmm_kernel": 1, "lbfgs_kernel": 0},
+               "phases": {"relabel": 1, "spmm_phases": 5}}
 
 
 @pytest.fixture(scope="session")

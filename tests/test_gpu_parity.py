@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 FAMS = ["maxcut", "lovasz_theta", "minimum_bisection", "cutnorm", "mu_conductance_0.01", "mu_conductance_0.05", "mu_conductance_0.1"]
 
 
-@pytest.fixture(scope="module", params=["default", "relabel", "tile"])
+@pytest.fixture(scope="module", params=["default", "relabel", "tile", "phases"])
 def handle(gpu_handle_factory, request):
     h = gpu_handle_factory(request.param)
     yield h

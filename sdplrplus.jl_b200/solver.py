@@ -467,6 +467,10 @@ def _sdplr(data, engine, config: BurerMonteiroConfig, stats: SolverStats, r, rng
 def _sdplr_native(data, engine, config: BurerMonteiroConfig, r, rng):
     """The same solve with the outer loop inside the library (sdplrp_solve, csrc/driver.cu); only for the GPU engine.
     Returns the reference's result dict."""
+    if not isinstance(getattr(engine, "h", None), _lib.Handle):
+        raise TypeError("driver='native' needs the GPU engine (sdplrp_solve runs inside libsdplrp_b200.so)")
+    # R0 / lambda0 are drawn here (init_func or numpy) and uploaded, exactly as driver='python' does; the random point of a
+    # rank update and the eigenvalue start vectors come from the device generator (config.seed)
     cfg = _lib.default_config()
     for k in ("ptol", "gtol", "objtol", "sigma_0", "sigmafac", "maxtime", "printfreq", "fprec", "prior_trace_bound"):
         setattr(cfg, k, float(getattr(config, k)))

@@ -152,3 +152,9 @@ def test_native_seed_stream_is_a_fixed_sequence(sp):
     s = [native_seed(0, k) for k in range(1, 5)]
     assert len(set(s)) == 4 and all(0 <= x < 2 ** 64 for x in s)
     assert native_seed(7, 3) == native_seed(7, 3) != native_seed(8, 3)
+
+
+def test_native_driver_needs_the_gpu_engine(sp, oracle_mod):
+    C, As, bs = sp.problems.maxcut(k2_graph())
+    with pytest.raises(TypeError):
+        sp.sdplr(C, As, bs, 1, engine_factory=oracle_mod.OracleEngine, driver="native", printlevel=0)

@@ -15,12 +15,12 @@ from . import _lib
 from ._lib import Handle, SdplrpError, tridiag_mineig
 from .types import (ConstraintBatch, Diagonal, SDPData, SparseMatrixCOO, SymLowRankMatrix, assemble_sparse,
                     b_vector, C_matrix, frobenius_norm)
-from .solver import (B200Engine, BurerMonteiroConfig, SolverStats, _sdplr, barvinok_pataki, linesearch_,
-                     linesearch_armijo_, pick_alpha, sdplr)
+from .solver import (B200Engine, BurerMonteiroConfig, GenericExecutionStats, Solver, SolverStats, _sdplr, barvinok_pataki,
+                     linesearch_, linesearch_armijo_, pick_alpha, sdplr)
 from . import problems
 from . import formats
 
 __all__ = ["Handle", "SdplrpError", "tridiag_mineig", "ConstraintBatch", "Diagonal", "SDPData", "SparseMatrixCOO",
            "SymLowRankMatrix", "assemble_sparse", "b_vector", "C_matrix", "frobenius_norm", "B200Engine",
-           "BurerMonteiroConfig", "SolverStats", "_sdplr", "barvinok_pataki", "linesearch_", "linesearch_armijo_",
+           "BurerMonteiroConfig", "GenericExecutionStats", "Solver", "SolverStats", "_sdplr", "barvinok_pataki", "linesearch_", "linesearch_armijo_",
            "pick_alpha", "sdplr", "problems", "formats"]

@@ -529,6 +529,73 @@ def sdplr(C, As, b, r, constraint_types=None, config: Optional[BurerMonteiroConf
     return ans
 
 
+# ---------------------------------------------------------------------------
+# the LowRankOpt `sub_solver` hook (src/lowrankopt.jl:4-53)
+# ---------------------------------------------------------------------------
+@dataclass
+class GenericExecutionStats:
+    """What SolverCore.solve! fills (src/lowrankopt.jl:47-52)."""
+    status: str = "unknown"
+    solution: Optional[np.ndarray] = None      # flat var.Rt (r x n column-major = C-order (n, r) raveled)
+    multipliers: Optional[np.ndarray] = None   # var.lambda
+    elapsed_time: float = 0.0
+    objective: float = float("nan")
+    solver_specific: dict = field(default_factory=dict)
+
+
+class Solver:
+    """`SDPLRPlus.Solver(src; config, kwargs...)` + `SolverCore.solve!(solver, model, stats; kwargs...)`.
+
+    The reference's hook passes the LowRankOpt model itself as `data` and `aux` and lets NLPModels evaluate the operators
+    (src/lowrankopt.jl:47, 80-135).  For the B200 path the model is read ONCE -- C = `LRO.grad(model, MatrixIndex(1))`,
+    b = `LRO.cons_constant`, the constraint matrices, `model.dim.ranks[]` -- and routed into the same device
+    engine as `sdplr`.  `src` here is any object with `C`, `As`, `b`, `rank` (and optionally `constraint_types`): the
+    contents of such a model.  As in the reference: unknown keywords are reported and skipped, the start point is a flat
+    vector `2*rand(n*r) - 1` with `lambda0 = randn(ncon)` (src/lowrankopt.jl:72-78), `status` is always `first_order`."""
+
+    def __init__(self, src, config: Optional[BurerMonteiroConfig] = None, engine_factory=None, **kwargs):
+        self.config = config if config is not None else BurerMonteiroConfig()
+        self._apply(kwargs, "error")
+        self.data = SDPData(src.C, src.As, np.asarray(src.b, dtype=np.float64), getattr(src, "constraint_types", None))
+        self.r = int(src.rank)
+        self.rng = np.random.default_rng(self.config.seed)
+        self.Rt0 = 2.0 * self.rng.random(self.data.n * self.r) - 1.0      # flat, as SolverVars(::LRO model, r) draws it
+        self.lambda0 = self.rng.standard_normal(self.data.m)
+        self.engine = (engine_factory or B200Engine)(self.data)
+        self.stats = SolverStats()
+
+    def _apply(self, kwargs, level):
+        for k, v in kwargs.items():
+            try:
+                self.config.set(k, v)
+            except KeyError:
+                print(f"[{level}] Unrecognized keyword argument {k}")  # @error / @warn and continue (src/lowrankopt.jl:15-21, 39-45)
+
+    def solve(self, model=None, stats: Optional[GenericExecutionStats] = None, **kwargs):
+        self._apply(kwargs, "warn")
+        stats = stats if stats is not None else GenericExecutionStats()
+        cfg = self.config
+        keep = (cfg.init_func, cfg.init_args)
+        def start_point(data, r):
+            if r == self.r:
+                return self.Rt0.reshape(data.n, r), self.lambda0
+            # rank_update! builds brand-new random variables (src/coreop.jl:518-526)
+            return 2.0 * self.rng.random((data.n, r)) - 1.0, self.rng.standard_normal(data.m)
+        cfg.init_func = start_point
+        cfg.init_args = ()
+        try:
+            ans = _sdplr(self.data, self.engine, cfg, self.stats, self.r, self.rng)
+        finally:
+            cfg.init_func, cfg.init_args = keep
+        stats.status = "first_order"                                   # TODO of the reference: the actual status
+        stats.solution = np.ascontiguousarray(ans["Rt"]).reshape(-1)
+        stats.multipliers = np.asarray(self.engine.get_lambda())
+        stats.elapsed_time = ans["totaltime"]
+        stats.objective = ans["obj"]
+        stats.solver_specific = {k: ans[k] for k in ("iter", "majoriter", "max_dual_value", "min_duality_gap", "primal_vio", "r")}
+        return stats
+
+
 def run_inner_iterations(engine, k, use_armijo=False, alpha_max=1.0, update_history=True, native=False):
     """k passes of the hot loop body of _sdplr (src/sdplr.jl:190-246) without the tolerance
     logic: direction, descent test, line search, step, gradient, L-BFGS update.  Used by

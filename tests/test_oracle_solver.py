@@ -49,3 +49,24 @@ def test_g1_maxcut_default_tolerances(sp, oracle_mod):
     assert abs(-res["obj"] - 12083.2) / 12083.2 < 1e-2
     assert res["max_dual_value"] <= res["obj"] + 1e-9 * abs(res["obj"]) or res["min_duality_gap"] < 0
     assert 50 < res["iter"] < 2000 and res["majoriter"] < 30
+
+
+def test_sub_solver_hook(sp, oracle_mod):
+    """SDPLRPlus.Solver / SolverCore.solve! (src/lowrankopt.jl:4-53): keywords applied to the config (unknown ones reported
+    and skipped), flat start vector, solution / multipliers / elapsed_time / status filled."""
+    from types import SimpleNamespace
+    C, As, bs = sp.problems.maxcut(k2_graph())
+    model = SimpleNamespace(C=C, As=As, b=bs, rank=1)
+    solver = sp.Solver(model, engine_factory=oracle_mod.OracleEngine, printlevel=0, fprec=0.0, gtol=1e-8, objtol=1e-8, ptol=1e-8,
+                       prior_trace_bound=2.0, no_such_option=3)
+    assert solver.config.ptol == 1e-8 and solver.Rt0.shape == (2,) and solver.lambda0.shape == (2,)
+    stats = solver.solve(model, sp.GenericExecutionStats(), maxtime=60.0, another_unknown=1)
+    assert solver.config.maxtime == 60.0
+    assert stats.status == "first_order" and stats.elapsed_time > 0
+    assert stats.solution.shape == (2,) and stats.multipliers.shape == (2,)
+    assert stats.objective == pytest.approx(-1.0, rel=1e-7)                       # K2 MaxCut, test/maxcut.jl:24
+    assert abs(abs(stats.solution[0]) - 1.0) < 1e-6 and stats.solution[0] * stats.solution[1] < 0   # the cut: R = (+-1, -+1)
+    C, As, bs = sp.problems.maxcut(g1_graph())
+    st = sp.Solver(SimpleNamespace(C=C, As=As, b=bs, rank=10), engine_factory=oracle_mod.OracleEngine, printlevel=0,
+                   prior_trace_bound=800.0).solve()
+    assert st.solution.shape == (8000,) and st.solver_specific["primal_vio"] <= 1e-2 and st.solver_specific["min_duality_gap"] <= 1e-2

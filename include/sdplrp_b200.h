@@ -95,6 +95,10 @@ void *sdplrp_stream(sdplrp_handle *h);
  *   "spmm_kernel" 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel (experimental)
  *   "spmm_phases" 0 = one sweep per gather pass (default); 1 = two sweeps, hub columns (an L2-sized prefix of the
  *                 hub-first order) then tail columns; k > 1 = k hub columns.  One GPU, relabelled patterns only (experimental)
+ *   "spmm_prefetch" 0 = default row loops; 1 = software-pipelined row loops of the gather pass (the next rows' index, ptr pair,
+ *                 first idx/val block and epilogue operands are loaded while the current gathers are in flight; same
+ *                 summation order, so results are those of the default kernels).  Experimental: written at the end of round 1
+ *                 without GPU time left, measured first thing in round 2 (profiles/r1_gather_size_sweep.md)
  *   "fused_tail"  1 = sdplrp_step_g uses the fused row pass (default), 0 = step and g separately
  *   "lbfgs_kernel" 1 = two-loop recursion on coefficients over directly computed dot products (default,
  *                 numlbfgsvecs <= 8), 0 = literal vector two-loop */

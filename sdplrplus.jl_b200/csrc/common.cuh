@@ -103,6 +103,8 @@ struct sdplrp_handle {
     int spmm_kernel = 0;                                 // 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel
     int spmm_phases = 0;                                 // 0 = one sweep per gather pass (default); 1 = hub | tail two-phase pass with an
                                                          // L2-sized hub prefix; > 1 = that many hub columns (gradient.cu, grad_obj_spmm)
+    int spmm_prefetch = 0;                               // 1 = software-pipelined row loops in the gather pass (experimental, gradient.cu:
+                                                         // k_rows_group_pf / k_rows_warp_pf; same summation order as the default kernels)
     int *row_mid = nullptr;                              // n: first tail-column position of every row (two-phase pass)
     i64 row_mid_cols = -1;                               // hub prefix row_mid was built for
     // per-entry lists in reference order (E_c)

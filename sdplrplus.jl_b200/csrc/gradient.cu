@@ -131,6 +131,9 @@ struct Acc<1> {
     __device__ __forceinline__ double dot_ld(const double *p) const { return v * __ldg(p); }
     __device__ __forceinline__ double norm2() const { return v * v; }
     __device__ __forceinline__ void store(double *p) const { *p = v; }
+    __device__ __forceinline__ void ld(const double *p) { v = __ldg(p); }
+    __device__ __forceinline__ void ld_hint(const double *p, unsigned long long pol) { v = ldg_f64_hint(p, pol); }
+    __device__ __forceinline__ double dot_reg(const Acc &o) const { return v * o.v; }
 };
 template <>
 struct Acc<2> {
@@ -168,6 +171,9 @@ struct Acc<2> {
     }
     __device__ __forceinline__ double norm2() const { return v.x * v.x + v.y * v.y; }
     __device__ __forceinline__ void store(double *p) const { *reinterpret_cast<double2 *>(p) = v; }
+    __device__ __forceinline__ void ld(const double *p) { v = ldg2(p); }
+    __device__ __forceinline__ void ld_hint(const double *p, unsigned long long pol) { v = ldg_f64x2_hint(p, pol); }
+    __device__ __forceinline__ double dot_reg(const Acc &o) const { return v.x * o.v.x + v.y * o.v.y; }
 };
 
 // EPI 0: Y_i = scale * acc                                   (seam-level At!)
@@ -378,6 +384,234 @@ __global__ void __launch_bounds__(TPB) k_rows_combine(RowArgs a) {
 }
 
 // Y[j,:] += scale*coeff * sum_k XB[:,k] D[k] B[j,k]     (src/structs.jl:135-145)
+// ---- software-pipelined row loops (option "spmm_prefetch"; profiles/r1_gather_size_sweep.md) ----------------------------
+// The default kernels pay four to five DEPENDENT memory round trips per row: row list -> ptr pair -> idx/val block ->
+// gathers -> epilogue operands.  Measured: a nonzero costs the same 22-26 ps whether the gathered factor sits in L2 or not,
+// i.e. the pass is bound by that chain, not by its DRAM traffic.  Here the work of a lane group (class 0) or warp (class 1 /
+// chunks) is a sequence of BLOCKS of nonzeros walked by a three-stage row pipeline:
+//   stage A  row index of row q+2        (one load, issued two rows ahead)
+//   stage B  ptr pair of row q+1         (issued one row ahead)
+//   stage C  the current row: its next idx/val block -- or the first block of row q+1 when the current block is the row's
+//            last -- and the epilogue operands X_i, Z_i of row q+1 are loaded right after the current block's gathers were
+//            issued, so they travel together with those gathers.
+// One exposed latency per block instead of five per row.  The nonzeros of a row are still accumulated in stored order by the
+// same lane, rows are taken by the same group in the same order, and the sums go through the same grid reduction, so on one
+// GPU the results are those of the default kernels bit for bit.  Only one unit per lane (MAXU == 1: r <= 64 even / 32 odd),
+// the plain value stream and the epilogue of the hot pass (EPI 2: Y_i = acc, sum0 += <X_i, acc>, sum1 += <X_i, Z_i>).
+// Written at the end of round 1 with no GPU time left: off by default, first measurement is scripts/r2_first_call.sh.
+
+// [q_lo, q_hi) = the entries of the ascending row list whose row is owned by this rank (the whole list on one GPU)
+__device__ __forceinline__ void owned_q_range(const int *__restrict__ list, i64 n_list, i64 own_lo, i64 own_hi, i64 &q_lo, i64 &q_hi) {
+    if (!list) {
+        q_lo = own_lo < 0 ? 0 : (own_lo < n_list ? own_lo : n_list);
+        q_hi = own_hi < n_list ? (own_hi < q_lo ? q_lo : own_hi) : n_list;
+        return;
+    }
+    i64 lo = 0, hi = n_list;
+    if (own_lo > 0) {
+        while (lo < hi) { const i64 mid = lo + ((hi - lo) >> 1); if ((i64)__ldg(list + mid) < own_lo) lo = mid + 1; else hi = mid; }
+    }
+    q_lo = lo;
+    hi = n_list;
+    if (n_list > 0 && (i64)__ldg(list + n_list - 1) >= own_hi) {
+        while (lo < hi) { const i64 mid = lo + ((hi - lo) >> 1); if ((i64)__ldg(list + mid) < own_hi) lo = mid + 1; else hi = mid; }
+        hi = lo;
+    }
+    q_hi = hi;
+}
+
+template <int VEC, int NB>
+__global__ void __launch_bounds__(TPB, 2) k_rows_group_pf(RowArgs a) {
+    const int nv = a.r / VEC;
+    const int G = a.G0;
+    const int gpb = TPB / G;
+    const int gib = threadIdx.x / G;
+    const int lg = threadIdx.x - gib * G;
+    const bool lane_ok = gib < gpb;
+    const bool piece_ok = lg < nv;
+    const size_t pc = (size_t)lg * VEC;             // this lane's slice of a factor row
+    const i64 n_groups = (i64)gridDim.x * gpb;
+    const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
+    double s0 = 0.0, s1 = 0.0;
+    if (lane_ok) {
+        i64 q_lo, q_hi;
+        owned_q_range(a.rows, a.n_rows, a.own_lo, a.own_hi, q_lo, q_hi);
+        // row index of list entry q; -2 = past the end
+        // (row labels and list positions fit 32 bits: the pattern arrays are int32)
+        auto row_at = [&](i64 q) -> int { return q < q_hi ? (a.rows ? __ldg(a.rows + q) : (int)q) : -2; };
+        i64 q = q_lo + (i64)blockIdx.x * gpb + gib;
+        // prologue: fill the three stages (the only place where the chain is exposed)
+        int iC = row_at(q);
+        int k0 = 0, endC = 0;
+        if (iC >= 0) { k0 = __ldg(a.ptr + iC); endC = __ldg(a.ptr + iC + 1); }
+        q += n_groups;
+        int iB = row_at(q);
+        int begB = 0, endB = 0;
+        if (iB >= 0) { begB = __ldg(a.ptr + iB); endB = __ldg(a.ptr + iB + 1); }
+        q += n_groups;
+        int iA = row_at(q);
+        int cc[NB];
+#pragma unroll
+        for (int j = 0; j < NB; j++) cc[j] = k0 + j < endC ? ldg_i32_hint(a.idx + k0 + j, p_str) : 0;
+        Acc<VEC> xC, zC, acc;
+        xC.zero(); zC.zero(); acc.zero();
+        if (iC >= 0 && piece_ok) {
+            xC.ld(a.X + (size_t)iC * a.r + pc);
+            if (a.Z) zC.ld(a.Z + (size_t)iC * a.r + pc);
+        }
+        while (iC >= 0) {
+            // 1. the gathers of the current block, and its values (their addresses need no index, so they travel with the
+            //    gathers instead of occupying registers a block ahead)
+            Acc<VEC> g[NB];
+            double vv[NB];
+#pragma unroll
+            for (int j = 0; j < NB; j++)
+                if (piece_ok && k0 + j < endC) g[j].ld_hint(a.X + (size_t)cc[j] * a.r + pc, cc[j] < a.hot_rows ? p_hot : p_str);
+#pragma unroll
+            for (int j = 0; j < NB; j++) vv[j] = k0 + j < endC ? ldg_f64_hint(a.val + k0 + j, p_str) : 0.0;
+            // 2. the indices of the block after it: next block of this row, or the first block of row B
+            const bool last = k0 + NB >= endC;
+            const int nk0 = last ? begB : k0 + NB;
+            const int nend = last ? endB : endC;
+            int cn[NB];
+#pragma unroll
+            for (int j = 0; j < NB; j++) cn[j] = nk0 + j < nend ? ldg_i32_hint(a.idx + nk0 + j, p_str) : 0;
+            // 3. the row pipeline moves when this block ends its row: ptr pair of row A, index of the row after A,
+            //    epilogue operands of row B
+            int iN = -2;
+            int begA = 0, endA = 0;
+            Acc<VEC> xB, zB;
+            xB.zero(); zB.zero();
+            if (last) {
+                if (iA >= 0) { begA = __ldg(a.ptr + iA); endA = __ldg(a.ptr + iA + 1); }
+                q += n_groups;
+                iN = row_at(q);
+                if (iB >= 0 && piece_ok) {
+                    xB.ld(a.X + (size_t)iB * a.r + pc);
+                    if (a.Z) zB.ld(a.Z + (size_t)iB * a.r + pc);
+                }
+            }
+            // 4. consume the gathers, in stored order
+#pragma unroll
+            for (int j = 0; j < NB; j++)
+                if (piece_ok && k0 + j < endC) acc.fma_reg(vv[j], g[j]);
+            // 5. row epilogue (EPI 2) and rotation
+            if (last) {
+                if (piece_ok) {
+                    s0 += acc.dot_reg(xC);
+                    if (a.Z) s1 += xC.dot_reg(zC);
+                    acc.store(a.Y + (size_t)iC * a.r + pc);
+                }
+                acc.zero();
+                iC = iB; k0 = begB; endC = endB; xC = xB; zC = zB;
+                iB = iA; begB = begA; endB = endA;
+                iA = iN;
+            } else {
+                k0 += NB;
+            }
+#pragma unroll
+            for (int j = 0; j < NB; j++) cc[j] = cn[j];
+        }
+    }
+    finish_sums<2>(a, s0, s1);
+}
+
+// class 1 (one warp per row) and the chunks of class 2 (one warp per chunk, CHUNK), pipelined the same way; a block is the
+// 4 nonzeros of each of the 32/G lane groups, the row pipeline is warp-uniform
+template <int VEC, bool CHUNK>
+__global__ void __launch_bounds__(TPB, 2) k_rows_warp_pf(RowArgs a) {
+    const int nv = a.r / VEC;
+    const int lane = threadIdx.x & 31;
+    const int lg = lane & (a.G - 1), grp = lane / a.G, ng = 32 / a.G;
+    const bool piece_ok = lg < nv;
+    const size_t pc = (size_t)lg * VEC;
+    const int step = ng * 4;
+    const int go = grp * 4;
+    const i64 n_warps = (i64)gridDim.x * (TPB / 32);
+    const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
+    double s0 = 0.0, s1 = 0.0;
+    i64 q_lo, q_hi;
+    owned_q_range(CHUNK ? a.chunk_row : a.rows, a.n_rows, a.own_lo, a.own_hi, q_lo, q_hi);
+    // stage A loads: the row of work item q (CHUNK: and its nonzero range, which does not depend on the row)
+    auto item_row = [&](i64 q) -> i64 { return q < q_hi ? (CHUNK ? (i64)__ldg(a.chunk_row + q) : (a.rows ? (i64)__ldg(a.rows + q) : q)) : (i64)-2; };
+    auto item_beg = [&](i64 q, i64 i) -> int { return i < 0 ? 0 : (CHUNK ? __ldg(a.chunk_start + q) : __ldg(a.ptr + i)); };
+    auto item_end = [&](i64 q, i64 i) -> int { return i < 0 ? 0 : (CHUNK ? __ldg(a.chunk_end + q) : __ldg(a.ptr + i + 1)); };
+    i64 q = q_lo + (i64)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+    i64 qC = q;
+    i64 iC = item_row(q);
+    int kb = item_beg(q, iC), endC = item_end(q, iC);
+    q += n_warps;
+    i64 qB = q;
+    i64 iB = item_row(q);
+    int begB = item_beg(q, iB), endB = item_end(q, iB);
+    q += n_warps;
+    i64 qA = q;
+    i64 iA = item_row(q);
+    int cc[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) cc[j] = kb + go + j < endC ? ldg_i32_hint(a.idx + kb + go + j, p_str) : 0;
+    Acc<VEC> xC, zC, acc;
+    xC.zero(); zC.zero(); acc.zero();
+    if (!CHUNK && iC >= 0 && piece_ok && grp == 0) {
+        xC.ld(a.X + (size_t)iC * a.r + pc);
+        if (a.Z) zC.ld(a.Z + (size_t)iC * a.r + pc);
+    }
+    while (iC >= 0) {  // warp-uniform
+        const int k0 = kb + go;
+        Acc<VEC> g[4];
+        double vv[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (piece_ok && k0 + j < endC) g[j].ld_hint(a.X + (size_t)cc[j] * a.r + pc, cc[j] < a.hot_rows ? p_hot : p_str);
+#pragma unroll
+        for (int j = 0; j < 4; j++) vv[j] = k0 + j < endC ? ldg_f64_hint(a.val + k0 + j, p_str) : 0.0;
+        const bool last = kb + step >= endC;   // warp-uniform
+        const int nkb = last ? begB : kb + step;
+        const int nend = last ? endB : endC;
+        int cn[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) cn[j] = nkb + go + j < nend ? ldg_i32_hint(a.idx + nkb + go + j, p_str) : 0;
+        i64 iN = -2, qN = q;
+        int begA = 0, endA = 0;
+        Acc<VEC> xB, zB;
+        xB.zero(); zB.zero();
+        if (last) {
+            begA = item_beg(qA, iA); endA = item_end(qA, iA);
+            q += n_warps;
+            qN = q;
+            iN = item_row(q);
+            if (!CHUNK && iB >= 0 && piece_ok && grp == 0) {
+                xB.ld(a.X + (size_t)iB * a.r + pc);
+                if (a.Z) zB.ld(a.Z + (size_t)iB * a.r + pc);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (piece_ok && k0 + j < endC) acc.fma_reg(vv[j], g[j]);
+        if (last) {
+            for (int o = a.G; o < 32; o <<= 1) acc.shfl_add(o);   // sum of the lane groups, fixed order
+            if (grp == 0 && piece_ok) {
+                if (CHUNK) {
+                    acc.store(a.scratch + (size_t)qC * a.r + pc);
+                } else {
+                    s0 += acc.dot_reg(xC);
+                    if (a.Z) s1 += xC.dot_reg(zC);
+                    acc.store(a.Y + (size_t)iC * a.r + pc);
+                }
+            }
+            acc.zero();
+            qC = qB; iC = iB; kb = begB; endC = endB; xC = xB; zC = zB;
+            qB = qA; iB = iA; begB = begA; endB = endA;
+            qA = qN; iA = iN;
+        } else {
+            kb += step;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) cc[j] = cn[j];
+    }
+    if (!CHUNK) finish_sums<2>(a, s0, s1);
+}
+
 __global__ void k_lr_apply(i64 lo, i64 hi, int r, int s, i64 n, const double *__restrict__ XB, const double *__restrict__ Dg,
                            const double *__restrict__ B, const double *__restrict__ y, int gid, double scale,
                            double *__restrict__ Y) {
@@ -551,12 +785,41 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
     cudaStream_t st = h->stream;
     const int gpb = TPB / a.G;
     const int gpb0 = TPB / a.G0;
+    // software-pipelined row loops: only the shape of the hot pass (one unit per lane, plain values, EPI 2, whole rows)
+    bool pf = false;
+    if constexpr (MAXU == 1 && !IND && EPI == 2) pf = h->spmm_prefetch > 0 && sums && !a.beg_arr && !a.end_arr && !long_empty;
     for (int c = 0; c < 3; c++) {
         if (sums) a.out = sums + 2 * c;
         a.rows = cls.list[c];
         a.n_rows = cls.cnt[c];
         if (a.n_rows <= 0) {
             if (sums) CUDA_TRY(h, cudaMemsetAsync(sums + 2 * c, 0, 2 * sizeof(double), st));
+            continue;
+        }
+        if (pf) {
+            if constexpr (MAXU == 1 && !IND && EPI == 2) {
+                if (c == 0) {
+                    if (h->spmm_unroll >= 8) k_rows_group_pf<VEC, 8><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
+                    else k_rows_group_pf<VEC, 4><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
+                } else if (c == 1) {
+                    k_rows_warp_pf<VEC, false><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
+                } else {
+                    const i64 need = longs.n_chunks * (i64)a.r;
+                    if (h->tile_scratch_len < need) {
+                        SDP_CHECK(dev_alloc(h, &h->tile_scratch, need));
+                        h->tile_scratch_len = need;
+                    }
+                    RowArgs b = a;
+                    b.chunk_start = longs.chunk_start; b.chunk_end = longs.chunk_end; b.chunk_row = longs.chunk_row;
+                    b.long_rows = longs.long_rows; b.long_cptr = longs.long_cptr; b.scratch = h->tile_scratch;
+                    b.n_rows = longs.n_chunks;
+                    k_rows_warp_pf<VEC, true><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
+                    KLAUNCH(h);
+                    b.n_rows = longs.n_long;
+                    k_rows_combine<VEC, MAXU, EPI><<<grid_for(b.n_rows, gpb, 4 * kNumSM), TPB, 0, st>>>(b);
+                }
+            }
+            KLAUNCH(h);
             continue;
         }
         if (c == 0) {

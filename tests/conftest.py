@@ -32,7 +32,13 @@ def oracle_mod():
 # "phases": the two-phase (hub | tail columns) gather pass with a 5-column hub prefix, so that both phases and the
 # accumulate-with-dots epilogue are non-trivial on the small test graphs
 GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "tile": {"relabel": 1, "spmm_kernel": 1, "lbfgs_kernel": 0},
-               "phases": {"relabel": 1, "spmm_phases": 5}}
+               "phases": {"relabel": 1, "spmm_phases": 5},
+               # experimental options: written without GPU time left, so they are NOT part of the default GPU run; they join it
+               # with SDPLRP_TEST_EXPERIMENTAL=1 (scripts/r2_first_call.sh) until they have been seen green on a B200
+               "prefetch": {"relabel": 1, "spmm_prefetch": 1}, "prefetch4": {"spmm_prefetch": 1, "spmm_unroll": 4}}
+EXPERIMENTAL_CONFIGS = ["prefetch", "prefetch4"]
+GPU_CONFIG_PARAMS = ["default", "relabel", "tile", "phases"] + (
+    EXPERIMENTAL_CONFIGS if os.environ.get("SDPLRP_TEST_EXPERIMENTAL", "0") not in ("", "0") else [])
 
 
 @pytest.fixture(scope="session")

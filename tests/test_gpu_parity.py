@@ -9,6 +9,7 @@ import math
 import numpy as np
 import pytest
 
+from conftest import GPU_CONFIG_PARAMS
 from helpers import COMBOS, MAP_KEYS, dense_S, dense_primal_vio, families, g1_graph, k2_graph, load_golden, make_case, p3_graph
 
 pytestmark = pytest.mark.gpu
@@ -16,7 +17,7 @@ pytestmark = pytest.mark.gpu
 FAMS = ["maxcut", "lovasz_theta", "minimum_bisection", "cutnorm", "mu_conductance_0.01", "mu_conductance_0.05", "mu_conductance_0.1"]
 
 
-@pytest.fixture(scope="module", params=["default", "relabel", "tile", "phases"])
+@pytest.fixture(scope="module", params=GPU_CONFIG_PARAMS)
 def handle(gpu_handle_factory, request):
     h = gpu_handle_factory(request.param)
     yield h

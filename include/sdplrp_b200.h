@@ -99,6 +99,9 @@ void *sdplrp_stream(sdplrp_handle *h);
  *                 first idx/val block and epilogue operands are loaded while the current gathers are in flight; same
  *                 summation order, so results are those of the default kernels).  Experimental: written at the end of round 1
  *                 without GPU time left, measured first thing in round 2 (profiles/r1_gather_size_sweep.md)
+ *   "lanczos_dist" 0 = the q-step Lanczos operator is replicated on every rank (default); 1 = rows of S and of the Lanczos
+ *                 vectors are divided among the ranks (one all-gather of n doubles + two scalar all-reduces per step).
+ *                 Only with world > 1 and without re-orthogonalisation.  Experimental, as "spmm_prefetch"
  *   "fused_tail"  1 = sdplrp_step_g uses the fused row pass (default), 0 = step and g separately
  *   "lbfgs_kernel" 1 = two-loop recursion on coefficients over directly computed dot products (default,
  *                 numlbfgsvecs <= 8), 0 = literal vector two-loop */

@@ -40,9 +40,14 @@ for k in (1, 10, 50, 200, 400):
     last = eng.iterate(k - done)
     done = k
     out[f"it{k}"] = [last[0], last[1], last[4]]
-v0 = None
+import time
+h.synchronize()
+t0 = time.perf_counter()
 d = eng.dual_obj(float(n), 100, None, 777)
+h.synchronize()
 out["dual"] = [d[0], d[1], d[2]]
+out["dual_s"] = time.perf_counter() - t0   # SDPLRP_LANCZOS_DIST=1: row-partitioned Lanczos (must give the same dual value)
+out["lanczos_dist"] = os.environ.get("SDPLRP_LANCZOS_DIST", "0")
 if rank == 0:
     print(json.dumps(out), flush=True)
 h.close()

@@ -246,6 +246,20 @@ int32_t comm_gather_cvec(sdplrp_handle *h, double *v) {
     return SDPLRP_OK;
 }
 
+// every rank receives the owned row blocks of an n-vector in internal vertex order (row-partitioned Lanczos)
+int32_t comm_gather_rowvec(sdplrp_handle *h, double *v) {
+    if (h->world <= 1) return SDPLRP_OK;
+    SectionScope sc(h, SDPLRP_SEC_COMM);
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    NCCL_TRY(h, ncclGroupStart());
+    for (int q = 0; q < h->world; q++) {
+        const i64 off = h->row_starts[(size_t)q], len = h->row_starts[(size_t)q + 1] - off;
+        if (len > 0) NCCL_TRY(h, ncclBroadcast(v + off, v + off, (size_t)len, ncclDouble, q, comm, h->stream));
+    }
+    NCCL_TRY(h, ncclGroupEnd());
+    return SDPLRP_OK;
+}
+
 // SPMD contract: every rank must have been handed the same problem.  `value` is a 64-bit checksum of this rank's input;
 // the ranks agree iff max == min of both halves (all-reduced as exactly representable doubles).
 int32_t comm_check_same(sdplrp_handle *h, unsigned long long value, const char *what) {

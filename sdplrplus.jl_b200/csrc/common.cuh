@@ -103,6 +103,7 @@ struct sdplrp_handle {
     int spmm_kernel = 0;                                 // 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel
     int spmm_phases = 0;                                 // 0 = one sweep per gather pass (default); 1 = hub | tail two-phase pass with an
                                                          // L2-sized hub prefix; > 1 = that many hub columns (gradient.cu, grad_obj_spmm)
+    int lanczos_dist = 0;                                // 1 = row-partitioned q-step Lanczos on world > 1 (experimental, lanczos.cu: lz_run_dist)
     int spmm_prefetch = 0;                               // 1 = software-pipelined row loops in the gather pass (experimental, gradient.cu:
                                                          // k_rows_group_pf / k_rows_warp_pf; same summation order as the default kernels)
     int *row_mid = nullptr;                              // n: first tail-column position of every row (two-phase pass)
@@ -384,6 +385,7 @@ void comm_mark_full(sdplrp_handle *h, int mat_id);
 int32_t comm_require_full(sdplrp_handle *h, int mat_id);
 int32_t comm_gather_rows(sdplrp_handle *h, double *p, int mat_id);
 int32_t comm_reduce_mvec(sdplrp_handle *h, double *v1, double *v2);   // shared slots [n_sd, m] only
+int32_t comm_gather_rowvec(sdplrp_handle *h, double *v);              // every rank's owned rows of an n-vector (internal order) to every rank
 int32_t comm_gather_cvec(sdplrp_handle *h, double *v);                // make every per-row-constraint slot current on every rank
 int32_t comm_reduce_scalars(sdplrp_handle *h, int slot, int count);
 int32_t comm_check_same(sdplrp_handle *h, unsigned long long value, const char *what);  // error unless all ranks pass the same value

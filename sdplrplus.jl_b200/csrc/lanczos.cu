@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(TPB) k_lz_spmv(const int *__restrict__ rows, i
                                                  const int *__restrict__ idx, const double *__restrict__ S,
                                                  const double *__restrict__ v, double *__restrict__ w,
                                                  const double *__restrict__ stop, double *partials, unsigned *ticket,
-                                                 double *alpha_part) {
+                                                 double *alpha_part, i64 row_off = 0) {
     if (stop[0] != 0.0) return;
     constexpr int GPB = TPB / LANES;   // row groups per CTA
     const int lg = threadIdx.x % LANES, gib = threadIdx.x / LANES;
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(TPB) k_lz_spmv(const int *__restrict__ rows, i
     for (i64 base = (i64)blockIdx.x * GPB; base < n_rows; base += (i64)gridDim.x * GPB) {  // CTA-uniform trip count
         const i64 q = base + gib;
         const bool live = q < n_rows;
-        const i64 i = live ? (rows ? rows[q] : q) : 0;
+        const i64 i = live ? (rows ? rows[q] : q + row_off) : 0;   // row_off: identity list restricted to a rank's rows
         double t = 0.0;
         if (live) {
             const int beg = ptr[i], end = ptr[i + 1];
@@ -187,6 +187,57 @@ __global__ void __launch_bounds__(TPB) k_lz_beta(i64 n, int step, const double *
     });
 }
 
+// ---- row-partitioned q-step Lanczos (option "lanczos_dist", world > 1) ------------------------------------------------
+// positions [q_lo, q_hi) of the three ascending class lists whose rows lie in [own_lo, own_hi); out = {lo0, hi0, lo1, hi1, lo2, hi2}
+__global__ void k_lz_class_ranges(const int *l0, i64 n0, const int *l1, i64 n1, const int *l2, i64 n2, i64 own_lo, i64 own_hi,
+                                  long long *out) {
+    const int c = threadIdx.x;
+    if (c >= 3) return;
+    const int *list = c == 0 ? l0 : (c == 1 ? l1 : l2);
+    const i64 nl = c == 0 ? n0 : (c == 1 ? n1 : n2);
+    i64 lo = 0, hi = nl;
+    if (!list) {  // identity list (every row in this class)
+        lo = own_lo < nl ? own_lo : nl;
+        hi = own_hi < nl ? own_hi : nl;
+        if (hi < lo) hi = lo;
+    } else {
+        i64 a = 0, b = nl;
+        while (a < b) { const i64 mid = a + ((b - a) >> 1); if ((i64)list[mid] < own_lo) a = mid + 1; else b = mid; }
+        lo = a;
+        b = nl;
+        while (a < b) { const i64 mid = a + ((b - a) >> 1); if ((i64)list[mid] < own_hi) a = mid + 1; else b = mid; }
+        hi = a;
+    }
+    out[2 * c] = lo;
+    out[2 * c + 1] = hi;
+}
+
+// owned rows: w -= alpha_i v + beta_{i-1} vp, this rank's share of ||w||^2 -> out[0]
+__global__ void __launch_bounds__(TPB) k_lz_update_part(i64 n_own, int step, const double *__restrict__ v, const double *__restrict__ vp,
+                                                        double *__restrict__ w, const double *__restrict__ ab, i64 q,
+                                                        const double *__restrict__ stop, double *partials, unsigned *ticket, double *out) {
+    if (stop[0] != 0.0) return;
+    const double a = ab[step];
+    const double bprev = step > 0 ? ab[q + step - 1] : 0.0;
+    double acc[1] = {0.0};
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n_own; i += (i64)gridDim.x * blockDim.x) {
+        double t = w[i];
+        if (step == 0) t -= a * v[i];
+        else t -= a * v[i] + bprev * vp[i];
+        w[i] = t;
+        acc[0] += t * t;
+    }
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { out[0] = s[0]; });
+}
+
+// beta_i = sqrt(sum over the ranks), stop when beta_i < sqrt(n) eps (every rank takes the same decision from the same sum)
+__global__ void k_lz_beta_finish(i64 n, int step, const double *__restrict__ sum, double *ab, i64 q, double *stop) {
+    if (stop[0] != 0.0) return;
+    const double b = sqrt(sum[0]);
+    ab[q + step] = b;
+    if (fabs(b) < sqrt((double)n) * 2.220446049250313e-16) stop[0] = (double)(step + 1);
+}
+
 }  // namespace
 
 // smallest eigenvalue of SymTridiagonal(d, e) by Sturm-sequence bisection
@@ -255,7 +306,104 @@ static int32_t lz_apply(sdplrp_handle *h, const double *v, double *w, const doub
     return SDPLRP_OK;
 }
 
+// The same recurrence with the rows of S, w and the vector updates divided among the ranks (option "lanczos_dist"; the
+// default keeps the operator replicated, which does not scale: 8 s of a 55 s two-GPU solve of C5).  Per step: the SpMV over
+// the owned rows of each class, alpha and ||w||^2 as partial sums + one scalar all-reduce each, and one all-gather of the
+// new Lanczos vector (n doubles), which the next SpMV gathers from.  Every rank ends with the same alpha / beta (the
+// all-reduced sums are identical on all ranks), so the decisions taken from the dual bound stay SPMD-consistent.
+// Written at the end of round 1 without GPU time left: off by default, first run is scripts/check_multigpu_solve.py.
+static int32_t lz_run_dist(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, double *alpha, double *beta, i64 *iters) {
+    const i64 n = h->n;
+    cudaStream_t st = h->stream;
+    if (q > n - 1) q = n - 1;
+    if (q < 1) q = 1;
+    if (!h->lz_v) {
+        SDP_CHECK(dev_alloc(h, &h->lz_v, n)); SDP_CHECK(dev_alloc(h, &h->lz_w, n)); SDP_CHECK(dev_alloc(h, &h->lz_vp, n));
+    }
+    if (h->lz_ab_len < 2 * q) { SDP_CHECK(dev_alloc(h, &h->lz_ab, 2 * q)); h->lz_ab_len = 2 * q; }
+    double *v = h->lz_v, *w = h->lz_w, *vp = h->lz_vp, *ab = h->lz_ab;
+    double *stop = h->dscal + SC_LANCZOS, *tmp = h->dscal + SC_LANCZOS + 1, *parts = h->dscal + SC_LANCZOS + 2;
+    double *bsum = h->dscal + SC_LANCZOS + 5;
+    const i64 lo = h->row_lo, hi = h->row_hi, n_own = hi - lo;
+    const bool has_lr = !h->lr.empty();
+    // list positions of the owned rows in every class
+    long long *d_rng = nullptr;
+    SDP_CHECK(dev_alloc(h, &d_rng, 6));
+    long long rng[6] = {0, 0, 0, 0, 0, 0};
+    if (h->nA > 0) {
+        const RowClasses &cls = h->full_cls;
+        k_lz_class_ranges<<<1, 32, 0, st>>>(cls.list[0], cls.cnt[0], cls.list[1], cls.cnt[1], cls.list[2], cls.cnt[2], lo, hi, d_rng);
+        KLAUNCH(h);
+        cudaError_t e = cudaMemcpyAsync(rng, d_rng, sizeof(rng), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { cudaFree(d_rng); h->err = std::string("lanczos: ") + cudaGetErrorString(e); return SDPLRP_ERR_CUDA; }
+    }
+    cudaFree(d_rng);
+    CUDA_TRY(h, cudaMemsetAsync(ab, 0, (size_t)(2 * q) * sizeof(double), st));
+    CUDA_TRY(h, cudaMemsetAsync(stop, 0, sizeof(double), st));
+    CUDA_TRY(h, cudaMemsetAsync(vp, 0, (size_t)n * sizeof(double), st));
+    const int gs = grid_for(n, TPB, kRedBlocks);
+    const int gso = grid_for(std::max<i64>(n_own, 1), TPB, kRedBlocks);
+    if (v0_host) {
+        SDP_CHECK(perm_upload(h, v, v0_host, 1, false));
+    } else {
+        k_lz_randn<<<gs, TPB, 0, st>>>(n, seed, v); KLAUNCH(h);
+    }
+    k_lz_norm2<<<gs, TPB, 0, st>>>(n, v, h->partials, h->ticket, tmp); KLAUNCH(h);   // replicated: same vector on every rank
+    k_lz_div<<<gs, TPB, 0, st>>>(n, tmp, v); KLAUNCH(h);
+    for (i64 i = 0; i < q; i++) {
+        // w[own] = (S v)[own], this rank's share of alpha_i
+        CUDA_TRY(h, cudaMemsetAsync(parts, 0, 3 * sizeof(double), st));
+        if (h->nA > 0) {
+            const RowClasses &cls = h->full_cls;
+            for (int c = 0; c < 3; c++) {
+                const i64 nr = rng[2 * c + 1] - rng[2 * c];
+                if (nr <= 0) continue;
+                const int *rows = cls.list[c] ? cls.list[c] + rng[2 * c] : nullptr;
+                const i64 off = cls.list[c] ? 0 : rng[2 * c];
+#define LZ_SPMV(L, A) k_lz_spmv<L, A><<<grid_for(nr, TPB / L, 16 * kNumSM), TPB, 0, st>>>(rows, nr, h->full_ptr, h->full_idx, h->S, v, w, stop, h->partials, h->ticket, parts + c, off)
+                if (c == 0) { if (has_lr) LZ_SPMV(4, false); else LZ_SPMV(4, true); }
+                else if (c == 1) { if (has_lr) LZ_SPMV(32, false); else LZ_SPMV(32, true); }
+                else { if (has_lr) LZ_SPMV(256, false); else LZ_SPMV(256, true); }
+#undef LZ_SPMV
+                KLAUNCH(h);
+            }
+        } else if (n_own > 0) {
+            k_lz_zero<<<gso, TPB, 0, st>>>(n_own, w + lo, stop); KLAUNCH(h);
+        }
+        if (has_lr || h->nA <= 0) {
+            for (const LowRank &L : h->lr)
+                for (i64 k = 0; k < L.s; k++) {
+                    // <B_k, v> over all rows (v is replicated, so no exchange), the update on the owned rows
+                    k_lz_dot<<<gs, TPB, 0, st>>>(n, L.dB + k * n, v, stop, h->partials, h->ticket, tmp); KLAUNCH(h);
+                    if (n_own > 0) { k_lz_lr_axpy<<<gso, TPB, 0, st>>>(n_own, L.dB + k * n + lo, tmp, L.dD, (int)k, h->y, (int)L.gid, stop, w + lo); KLAUNCH(h); }
+                }
+            k_lz_dot<<<gso, TPB, 0, st>>>(n_own, v + lo, w + lo, stop, h->partials, h->ticket, ab + i); KLAUNCH(h);
+        } else {
+            k_lz_alpha_sum<<<1, 1, 0, st>>>(parts, 3, stop, ab + i); KLAUNCH(h);
+        }
+        SDP_CHECK(comm_reduce_ptr(h, ab + i, 1));
+        CUDA_TRY(h, cudaMemsetAsync(bsum, 0, sizeof(double), st));
+        k_lz_update_part<<<gso, TPB, 0, st>>>(n_own, (int)i, v + lo, vp + lo, w + lo, ab, q, stop, h->partials, h->ticket, bsum); KLAUNCH(h);
+        SDP_CHECK(comm_reduce_ptr(h, bsum, 1));
+        k_lz_beta_finish<<<1, 1, 0, st>>>(n, (int)i, bsum, ab, q, stop); KLAUNCH(h);
+        if (n_own > 0) { k_lz_normalise<<<gso, TPB, 0, st>>>(n_own, (int)i, ab, q, stop, w + lo); KLAUNCH(h); }
+        SDP_CHECK(comm_gather_rowvec(h, w));
+        double *t = vp; vp = v; v = w; w = t;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    std::vector<double> hab((size_t)(2 * q));
+    double hstop = 0.0;
+    CUDA_TRY(h, cudaMemcpyAsync(hab.data(), ab, (size_t)(2 * q) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(&hstop, stop, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    for (i64 i = 0; i < q; i++) { alpha[i] = hab[(size_t)i]; beta[i] = hab[(size_t)(q + i)]; }
+    *iters = hstop != 0.0 ? (i64)hstop : q;
+    return SDPLRP_OK;
+}
+
 int32_t lz_run(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, int reorth, double *alpha, double *beta, i64 *iters) {
+    if (h->world > 1 && h->lanczos_dist && !reorth) return lz_run_dist(h, q, v0_host, seed, alpha, beta, iters);
     const i64 n = h->n;
     cudaStream_t st = h->stream;
     if (q > n - 1) q = n - 1;

@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(TPB) k_A_rowc(long long lo, long long hi, cons
         const long long i = lo + t0 + rl;
         const bool live = rl < rpt && i < hi;
         double d1 = 0.0, d2 = 0.0;
+        int beg = 0, end = 0;
+        if (live && c == 0) { beg = rowc_ptr[i]; end = rowc_ptr[i + 1]; }  // issued with the factor loads, not after the barrier
         if (live) {
             typename L::T a = L::ld(U + (size_t)i * r + c * VEC);
             if (MODE == 0) {
@@ -156,7 +158,6 @@ __global__ void __launch_bounds__(TPB) k_A_rowc(long long lo, long long hi, cons
         if (MODE == 2) sh2[threadIdx.x] = d2;
         __syncthreads();
         if (live && c == 0) {
-            const int beg = rowc_ptr[i], end = rowc_ptr[i + 1];
             if (end > beg) {
                 double s1 = 0.0, s2 = 0.0;
                 for (int k = 0; k < nv; k++) { s1 += sh1[threadIdx.x + k]; if (MODE == 2) s2 += sh2[threadIdx.x + k]; }

@@ -157,6 +157,7 @@ struct sdplrp_handle {
     i64 tile_scratch_len = 0;
     double *CR = nullptr, *CD = nullptr;  // n x r: C*R (recurrence) and C*D
     bool CR_valid = false, CD_valid = false;
+    i64 state_cap = 0;             // doubles per factor array of the current allocation (sdplrp_set_rank reuses it when nothing changed)
     bool ls_valid = false;         // A_RD / A_DD (and CD) belong to the current R and D
     bool fused_tail = true;        // sdplrp_step_g may use the fused row pass
 

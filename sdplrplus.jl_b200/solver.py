@@ -147,7 +147,10 @@ class B200Engine:
         """SolverVars(Rt0, lambda0, lambda_ub, r, sigma_0) + lbfgs_init."""
         self.h.set_rank(r, numlbfgsvecs)
         self.h.upload_mat(_lib.MAT_R, np.ascontiguousarray(Rt0, dtype=np.float64))
-        lam = np.minimum(np.asarray(lambda0, dtype=np.float64), np.where(self.data.constraint_types, 0.0, np.inf))
+        lam = np.ascontiguousarray(lambda0, dtype=np.float64)
+        ct = self.data.constraint_types
+        if ct is not None and np.any(ct):  # lambda_ub = 0 on inequalities (src/structs.jl:225-268); equalities: min(x, inf) = x,
+            lam = np.minimum(lam, np.where(ct, 0.0, np.inf))  # so the caller's (possibly pinned) buffer is uploaded as it is
         self.h.upload_vec(_lib.VEC_LAMBDA, lam)
         self.h.sigma = sigma0
         self.r = r

@@ -32,10 +32,23 @@ PY
 line default
 line prefetch8 --option spmm_prefetch=1
 line prefetch4 --option spmm_prefetch=1 --option spmm_unroll=4
+line prefetch8_pad --option spmm_prefetch=1 --option spmm_pad=1
+line prefetch4_pad --option spmm_prefetch=1 --option spmm_unroll=4 --option spmm_pad=1
+# hypothesis test for the wavefront model (profiles/r1_gather_size_sweep.md): lines touched per gathered row.
+# rank 8 = 64-byte rows (never cross a 128-byte line), 10 = 80 bytes (cross 5 times out of 8), 12 = 96 (6 of 8), 16 = 128 (never)
+line rank8 --rank 8
+line rank12 --rank 12
+line rank16 --rank 16
+line g0_pow2 --option spmm_g0=0
 line lanczos_default --lanczos 50
 } | tee $out/summary.txt
 
+# stall reasons / L1 wavefronts of the default class-0 kernel (one launch, --set full; read with ncu -i ... --page raw --csv)
+ncu --set full --import-source on --clock-control none -k regex:k_rows_group -s 2 -c 1 -o $out/rows_group_default \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/ncu_full_default.log 2>&1
 if grep -q "^prefetch8 it/s" $out/summary.txt; then
+  ncu --set full --import-source on --clock-control none -k regex:k_rows_group_pf -s 2 -c 1 -o $out/rows_group_prefetch8 \
+      python bench.py --steps 2 --warmup 1 --no-cpu-baseline --option spmm_prefetch=1 > $out/ncu_full_prefetch8.log 2>&1
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,sm__warps_active.avg.pct_of_peak_sustained_active \
       --clock-control none -k regex:k_rows -c 24 --csv --log-file $out/ncu_rows_prefetch8.csv \
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline --option spmm_prefetch=1 > $out/ncu_prefetch8.log 2>&1

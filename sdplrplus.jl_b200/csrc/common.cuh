@@ -103,6 +103,9 @@ struct sdplrp_handle {
     int spmm_kernel = 0;                                 // 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel
     int spmm_phases = 0;                                 // 0 = one sweep per gather pass (default); 1 = hub | tail two-phase pass with an
                                                          // L2-sized hub prefix; > 1 = that many hub columns (gradient.cu, grad_obj_spmm)
+    int spmm_pad = 0;                                    // 1 = the pipelined gather kernels read a 128-byte-aligned copy of the factor (experimental)
+    double *gpad = nullptr;                              // that copy, n x pad_stride(r)
+    i64 gpad_len = 0;
     int lanczos_dist = 0;                                // 1 = row-partitioned q-step Lanczos on world > 1 (experimental, lanczos.cu: lz_run_dist)
     int spmm_prefetch = 0;                               // 1 = software-pipelined row loops in the gather pass (experimental, gradient.cu:
                                                          // k_rows_group_pf / k_rows_warp_pf; same summation order as the default kernels)

@@ -189,6 +189,8 @@ struct RowArgs {
     const double *val;
     const int *src;    // IND: value = val[src[k]]
     const double *X;
+    const double *Xg;  // gathered operand of the pipelined kernels: X itself, or its line-aligned copy (option "spmm_pad")
+    int ldx;           // row stride of Xg in doubles
     double *Y;
     int r, G;
     int G0;            // lanes per row of the class-0 kernel (= pieces per row: no idle lanes, no shuffles there)
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(TPB, 2) k_rows_group_pf(RowArgs a) {
             double vv[NB];
 #pragma unroll
             for (int j = 0; j < NB; j++)
-                if (piece_ok && k0 + j < endC) g[j].ld_hint(a.X + (size_t)cc[j] * a.r + pc, cc[j] < a.hot_rows ? p_hot : p_str);
+                if (piece_ok && k0 + j < endC) g[j].ld_hint(a.Xg + (size_t)cc[j] * a.ldx + pc, cc[j] < a.hot_rows ? p_hot : p_str);
 #pragma unroll
             for (int j = 0; j < NB; j++) vv[j] = k0 + j < endC ? ldg_f64_hint(a.val + k0 + j, p_str) : 0.0;
             // 2. the indices of the block after it: next block of this row, or the first block of row B
@@ -562,7 +564,7 @@ __global__ void __launch_bounds__(TPB, 2) k_rows_warp_pf(RowArgs a) {
         double vv[4];
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            if (piece_ok && k0 + j < endC) g[j].ld_hint(a.X + (size_t)cc[j] * a.r + pc, cc[j] < a.hot_rows ? p_hot : p_str);
+            if (piece_ok && k0 + j < endC) g[j].ld_hint(a.Xg + (size_t)cc[j] * a.ldx + pc, cc[j] < a.hot_rows ? p_hot : p_str);
 #pragma unroll
         for (int j = 0; j < 4; j++) vv[j] = k0 + j < endC ? ldg_f64_hint(a.val + k0 + j, p_str) : 0.0;
         const bool last = kb + step >= endC;   // warp-uniform
@@ -860,6 +862,7 @@ int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const Til
     const bool vec2 = (r % 2 == 0);
     const int nv = vec2 ? r / 2 : r;
     a.r = r;
+    if (!a.Xg) { a.Xg = a.X; a.ldx = r; }
     a.G = pick_group(nv);
     a.partials = h->partials;
     a.ticket = h->ticket;
@@ -994,6 +997,26 @@ int32_t grad_spmm_sparse(sdplrp_handle *h, const double *X, double *Y, double sc
     return SDPLRP_OK;
 }
 
+// Option "spmm_pad" (with "spmm_prefetch", one GPU): the gathers read a copy of X whose rows start on 128-byte lines.
+// Why: a warp-wide gather instruction of the class-0 kernel touches 6 random rows; an 80-byte row at an 80-byte stride
+// straddles a 128-byte line 5 times out of 8, so the instruction costs ~9.6 L1 wavefronts instead of 6, and the pass
+// measures like a wavefront-bound kernel (6.4 cycles per nonzero per SM whether X is L2-resident or not,
+// profiles/r1_gather_size_sweep.md; B300_MICROARCH.md: ~2 cycles per extra line inside one LDG).  First experiment: the
+// copy is made by its own kernel (N read + n*ld*8 written, inside the timed section); if the pass gains more than that
+// the direction kernel writes the padded copy itself.
+__global__ void k_pad_rows(i64 n, int r, int ld, const double *__restrict__ X, double *__restrict__ Xp) {
+    const i64 total = n * r;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 i = e / r;
+        const int c = (int)(e - i * r);
+        Xp[i * ld + c] = X[e];
+    }
+}
+static int pad_stride(int r) {
+    if (r <= 16) { int p = 1; while (p < r) p <<= 1; return p; }  // 8r bytes divides 128: a row never crosses a line
+    return (r + 15) / 16 * 16;                                       // whole lines per row
+}
+
 // Y = C*X over the owned rows with the fused sums  out0 = <X, Y>, out1 = <X, Z>  (Z may be null)
 int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double *Z, double *sums6) {
     if (tile_supported(h)) {
@@ -1003,6 +1026,18 @@ int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double
     RowArgs a = {};
     a.ptr = h->full_ptr; a.idx = h->full_idx; a.val = h->Cfull; a.src = nullptr;
     a.X = X; a.Y = Y; a.Z = Z; a.scale = 1.0;
+    if (h->spmm_pad > 0 && h->spmm_prefetch > 0 && h->world == 1 && pad_stride(h->r) != h->r) {
+        const int ld = pad_stride(h->r);
+        const i64 need = h->n * (i64)ld;
+        if (h->gpad_len < need) {
+            SDP_CHECK(dev_alloc(h, &h->gpad, need));
+            CUDA_TRY(h, cudaMemsetAsync(h->gpad, 0, (size_t)need * 8, h->stream));
+            h->gpad_len = need;
+        }
+        k_pad_rows<<<grid_for(h->n * (i64)h->r, TPB, 16 * kNumSM), TPB, 0, h->stream>>>(h->n, h->r, ld, X, h->gpad);
+        KLAUNCH(h);
+        a.Xg = h->gpad; a.ldx = ld;
+    }
     const i64 hub_cols = phase_hub_cols(h);
     if (hub_cols > 0 && hub_cols < h->n) {
         SDP_CHECK(ensure_row_mid(h, hub_cols));

@@ -35,8 +35,9 @@ GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "tile": {"relabel": 1, 
                "phases": {"relabel": 1, "spmm_phases": 5},
                # experimental options: written without GPU time left, so they are NOT part of the default GPU run; they join it
                # with SDPLRP_TEST_EXPERIMENTAL=1 (scripts/r2_first_call.sh) until they have been seen green on a B200
-               "prefetch": {"relabel": 1, "spmm_prefetch": 1}, "prefetch4": {"spmm_prefetch": 1, "spmm_unroll": 4}}
-EXPERIMENTAL_CONFIGS = ["prefetch", "prefetch4"]
+               "prefetch": {"relabel": 1, "spmm_prefetch": 1}, "prefetch4": {"spmm_prefetch": 1, "spmm_unroll": 4},
+               "prefetch_pad": {"relabel": 1, "spmm_prefetch": 1, "spmm_pad": 1}}
+EXPERIMENTAL_CONFIGS = ["prefetch", "prefetch4", "prefetch_pad"]
 GPU_CONFIG_PARAMS = ["default", "relabel", "tile", "phases"] + (
     EXPERIMENTAL_CONFIGS if os.environ.get("SDPLRP_TEST_EXPERIMENTAL", "0") not in ("", "0") else [])
 

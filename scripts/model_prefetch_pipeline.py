@@ -126,6 +126,49 @@ def warp_kernel(ptr, idx, val, X, rows, n_rows, own_lo, own_hi, n_warps, ng, Y, 
     return s0
 
 
+def bundle_kernel(ptr, idx, val, X, c0_first, n_rows, own_lo, own_hi, n_warps, G, Y):
+    """every warp of k_rows_bundle: lane l holds ptr[i0 + min(l, nrow)], the span is staged, group g walks [o, e)"""
+    RPW = 32 // G
+    r_lo, r_hi = max(c0_first, own_lo), min(c0_first + n_rows, own_hi)
+    r_hi = max(r_hi, r_lo)
+    n_bundles = (r_hi - r_lo + RPW - 1) // RPW
+    s0 = 0.0
+
+    def load_ptr(bb):
+        if bb >= n_bundles: return [0] * 32
+        i0 = r_lo + bb * RPW
+        nrow = min(RPW, r_hi - i0)
+        return [int(ptr[i0 + (l if l < nrow else nrow)]) for l in range(32)]
+    for warp in range(n_warps):
+        b = warp
+        myp = load_ptr(b)
+        while b < n_bundles:
+            i0 = r_lo + b * RPW
+            nrow = min(RPW, r_hi - i0)
+            p0, pR = myp[0], myp[RPW]
+            assert pR - p0 <= RPW * 32
+            si = [None] * (RPW * 32); sv = [None] * (RPW * 32)
+            for lane in range(32):
+                for m in range(8):
+                    k = p0 + lane + 32 * m
+                    if k < pR: si[lane + 32 * m] = idx[k]; sv[lane + 32 * m] = val[k]
+            mypN = load_ptr(b + n_warps)
+            for g in range(32 // G + (1 if 32 % G else 0)):   # lane groups incl. the partial one that only stages
+                grp_ok = g < RPW
+                o = myp[g if grp_ok else RPW] - p0
+                e = myp[g + 1 if grp_ok else RPW] - p0
+                if not (grp_ok and g < nrow): continue
+                i = i0 + g
+                acc = np.zeros(X.shape[1])
+                for k in range(o, e): acc += sv[k] * X[si[k]]
+                s0 += float(acc @ X[i])
+                assert not np.any(np.isfinite(Y[i])), "row written twice"
+                Y[i] = acc
+            myp = mypN
+            b += n_warps
+    return s0
+
+
 def main():
     rng = np.random.default_rng(0)
     cases = 0
@@ -186,6 +229,32 @@ def main():
                 else:
                     assert not np.any(np.isfinite(Ys[c]))
             cases += 1
+    # bundles: class 0 = a contiguous row range with rows of at most 32 nonzeros
+    for trial in range(200):
+        n = int(rng.integers(1, 80))
+        r = int(rng.integers(1, 4))
+        lens = rng.integers(0, 33, n)
+        if trial % 5 == 0: lens[:] = 32
+        ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        nnz = int(ptr[-1])
+        idx = rng.integers(0, n, nnz); val = rng.standard_normal(nnz); X = rng.standard_normal((n, r))
+        ref = np.zeros((n, r))
+        for i in range(n):
+            for k in range(ptr[i], ptr[i + 1]): ref[i] += val[k] * X[idx[k]]
+        c0_first = int(rng.integers(0, n))
+        n_rows = int(rng.integers(0, n - c0_first + 1))
+        own_lo = int(rng.integers(0, n + 1)) if trial % 3 == 0 else 0
+        own_hi = int(rng.integers(own_lo, n + 1)) if trial % 3 == 0 else n
+        want = [i for i in range(c0_first, c0_first + n_rows) if own_lo <= i < own_hi]
+        for G in (4, 5, 6, 8, 10, 16):
+            for n_warps in (1, 3, 50):
+                Y = np.full((n, r), np.nan)
+                s0 = bundle_kernel(ptr, idx, val, X, c0_first, n_rows, own_lo, own_hi, n_warps, G, Y)
+                done = np.where(np.isfinite(Y).all(axis=1))[0].tolist()
+                assert done == want, (trial, G, done, want)
+                assert np.allclose(Y[want], ref[want], rtol=1e-12, atol=1e-12)
+                assert np.isclose(s0, float(np.sum(ref[want] * X[want])), rtol=1e-10, atol=1e-10)
+                cases += 1
     print("pipeline model: %d cases agree with the plain CSR product" % cases)
 
 

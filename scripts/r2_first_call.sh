@@ -10,7 +10,7 @@ set -u
 out=gpurun_out/r2_first
 mkdir -p $out
 export SDPLRP_TEST_EXPERIMENTAL=1
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "prefetch" > $out/pytest_experimental.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "prefetch or bundle" > $out/pytest_experimental.log 2>&1
 echo "pytest experimental rc=$?" | tee $out/rc.txt
 unset SDPLRP_TEST_EXPERIMENTAL
 
@@ -34,6 +34,10 @@ line prefetch8 --option spmm_prefetch=1
 line prefetch4 --option spmm_prefetch=1 --option spmm_unroll=4
 line prefetch8_pad --option spmm_prefetch=1 --option spmm_pad=1
 line prefetch4_pad --option spmm_prefetch=1 --option spmm_unroll=4 --option spmm_pad=1
+line bundle8 --option spmm_prefetch=2
+line bundle4 --option spmm_prefetch=2 --option spmm_unroll=4
+line bundle8_pad --option spmm_prefetch=2 --option spmm_pad=1
+line bundle4_pad --option spmm_prefetch=2 --option spmm_unroll=4 --option spmm_pad=1
 # hypothesis test for the wavefront model (profiles/r1_gather_size_sweep.md): lines touched per gathered row.
 # rank 8 = 64-byte rows (never cross a 128-byte line), 10 = 80 bytes (cross 5 times out of 8), 12 = 96 (6 of 8), 16 = 128 (never)
 line rank8 --rank 8

@@ -103,6 +103,9 @@ struct sdplrp_handle {
     int spmm_kernel = 0;                                 // 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel
     int spmm_phases = 0;                                 // 0 = one sweep per gather pass (default); 1 = hub | tail two-phase pass with an
                                                          // L2-sized hub prefix; > 1 = that many hub columns (gradient.cu, grad_obj_spmm)
+    const void *c0_checked = nullptr;                    // class-0 list the contiguity answer below belongs to (gradient.cu, k_rows_bundle)
+    i64 c0_first = 0;
+    bool c0_contig = false;
     int spmm_pad = 0;                                    // 1 = the pipelined gather kernels read a 128-byte-aligned copy of the factor (experimental)
     double *gpad = nullptr;                              // that copy, n x pad_stride(r)
     i64 gpad_len = 0;

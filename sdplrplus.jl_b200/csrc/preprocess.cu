@@ -556,6 +556,7 @@ void pre_free(sdplrp_handle *h) {
     dev_free(&h->tile_scratch); h->tile_scratch_len = 0;
     dev_free(&h->row_mid); h->row_mid_cols = -1;
     dev_free(&h->gpad); h->gpad_len = 0;
+    h->c0_checked = nullptr; h->c0_contig = false;
     dev_free(&h->triu_colptr); dev_free(&h->triu_rowval);
     if (h->full_ptr == h->ref_full_ptr) { h->full_ptr = nullptr; h->full_idx = nullptr; }  // aliases when not relabeled
     dev_free(&h->full_ptr); dev_free(&h->full_idx); dev_free(&h->ref_full_ptr); dev_free(&h->ref_full_idx);

@@ -36,8 +36,9 @@ GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "tile": {"relabel": 1, 
                # experimental options: written without GPU time left, so they are NOT part of the default GPU run; they join it
                # with SDPLRP_TEST_EXPERIMENTAL=1 (scripts/r2_first_call.sh) until they have been seen green on a B200
                "prefetch": {"relabel": 1, "spmm_prefetch": 1}, "prefetch4": {"spmm_prefetch": 1, "spmm_unroll": 4},
-               "prefetch_pad": {"relabel": 1, "spmm_prefetch": 1, "spmm_pad": 1}}
-EXPERIMENTAL_CONFIGS = ["prefetch", "prefetch4", "prefetch_pad"]
+               "prefetch_pad": {"relabel": 1, "spmm_prefetch": 1, "spmm_pad": 1},
+               "bundle": {"relabel": 1, "spmm_prefetch": 2}, "bundle4_pad": {"spmm_prefetch": 2, "spmm_unroll": 4, "spmm_pad": 1}}
+EXPERIMENTAL_CONFIGS = ["prefetch", "prefetch4", "prefetch_pad", "bundle", "bundle4_pad"]
 GPU_CONFIG_PARAMS = ["default", "relabel", "tile", "phases"] + (
     EXPERIMENTAL_CONFIGS if os.environ.get("SDPLRP_TEST_EXPERIMENTAL", "0") not in ("", "0") else [])
 

@@ -38,6 +38,9 @@ line bundle8 --option spmm_prefetch=2
 line bundle4 --option spmm_prefetch=2 --option spmm_unroll=4
 line bundle8_pad --option spmm_prefetch=2 --option spmm_pad=1
 line bundle4_pad --option spmm_prefetch=2 --option spmm_unroll=4 --option spmm_pad=1
+# 8 lanes per row (a lane group = one quarter-warp phase of an LDG.128) on 128-byte rows: one line per phase
+line bundle8_pad_g8 --option spmm_prefetch=2 --option spmm_pad=1 --option spmm_g0=0
+line prefetch8_pad_g8 --option spmm_prefetch=1 --option spmm_pad=1 --option spmm_g0=0
 # hypothesis test for the wavefront model (profiles/r1_gather_size_sweep.md): lines touched per gathered row.
 # rank 8 = 64-byte rows (never cross a 128-byte line), 10 = 80 bytes (cross 5 times out of 8), 12 = 96 (6 of 8), 16 = 128 (never)
 line rank8 --rank 8

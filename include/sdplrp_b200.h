@@ -102,7 +102,8 @@ void *sdplrp_stream(sdplrp_handle *h);
  *                 short rows to be one contiguous range, else as 1).  Experimental: written at the end of round 1
  *                 without GPU time left, measured first thing in round 2 (profiles/r1_gather_size_sweep.md)
  *   "spmm_pad"    with "spmm_prefetch" on one GPU: 1 = the gathers read a copy of the factor whose rows start on 128-byte
- *                 lines (an 80-byte row at an 80-byte stride crosses a line 5 times out of 8).  Experimental, as above
+ *                 lines (an 80-byte row at an 80-byte stride crosses a line 5 times out of 8).  Confirmation experiment only:
+ *                 no gain expected (profiles/r1_gather_size_sweep.md, addendum)
  *   "lanczos_dist" 0 = the q-step Lanczos operator is replicated on every rank (default); 1 = rows of S and of the Lanczos
  *                 vectors are divided among the ranks (one all-gather of n doubles + two scalar all-reduces per step).
  *                 Only with world > 1 and without re-orthogonalisation.  Experimental, as "spmm_prefetch"

@@ -521,11 +521,10 @@ __global__ void __launch_bounds__(TPB, 2) k_rows_group_pf(RowArgs a) {
 
 // Class 0 by BUNDLES (option "spmm_prefetch" = 2): a warp takes 32/G0 CONSECUTIVE rows (6 at r = 10) whose nonzeros are one
 // contiguous span of the CSR arrays (<= 32 per row in this class), stages that span into its own slice of shared memory with
-// fully coalesced loads (idx: ~2 lines, val: ~3 lines per bundle instead of 8 + 8 instructions of 2-3 lines each), then every
-// lane group walks its row out of shared memory and issues nothing but gathers to the load/store unit.  The ptr values of
-// the next bundle are loaded one bundle ahead.  Per bundle: staging and gathers are the only exposed latencies, and the L1
-// wavefront count per nonzero drops from ~3.2 to ~2 (1.3 with "spmm_pad").  Needs class 0 to be a contiguous row range
-// (hub-first order, or a pattern with short rows only) and 32/G0 <= kBundleRows.
+// fully coalesced loads, then every lane group walks its row out of shared memory and issues nothing but gathers.  The ptr
+// values of the next bundle are loaded one bundle ahead.  Two exposed round trips per bundle (staging, gathers) instead of
+// five per row, at 80 registers (24 warps per SM) where the register-pipelined kernels need 96-128.  Needs class 0 to be a
+// contiguous row range (hub-first order, or a pattern with short rows only) and 32/G0 <= kBundleRows.
 constexpr int TPB_B = 128;         // 4 warps: 4 x kBundleRows x 32 x 12 B = 12 KB of shared memory
 constexpr int kBundleRows = 8;
 template <int VEC, int NB>
@@ -1121,13 +1120,11 @@ int32_t grad_spmm_sparse(sdplrp_handle *h, const double *X, double *Y, double sc
     return SDPLRP_OK;
 }
 
-// Option "spmm_pad" (with "spmm_prefetch", one GPU): the gathers read a copy of X whose rows start on 128-byte lines.
-// Why: a warp-wide gather instruction of the class-0 kernel touches 6 random rows; an 80-byte row at an 80-byte stride
-// straddles a 128-byte line 5 times out of 8, so the instruction costs ~9.6 L1 wavefronts instead of 6, and the pass
-// measures like a wavefront-bound kernel (6.4 cycles per nonzero per SM whether X is L2-resident or not,
-// profiles/r1_gather_size_sweep.md; B300_MICROARCH.md: ~2 cycles per extra line inside one LDG).  First experiment: the
-// copy is made by its own kernel (N read + n*ld*8 written, inside the timed section); if the pass gains more than that
-// the direction kernel writes the padded copy itself.
+// Option "spmm_pad" (with "spmm_prefetch", one GPU): the gathers read a copy of X whose rows start on 128-byte lines (an
+// 80-byte row at an 80-byte stride straddles a line 5 times out of 8).  Written for an L1-wavefront reading of the size sweep
+// that the ncu capture of the round does not support (L1 at 39 % of peak, long_scoreboard dominant; sectors and DRAM
+// granules per gather are the same with and without padding): kept as a cheap confirmation, not as a candidate.  The copy
+// is made by its own kernel inside the timed section.
 __global__ void k_pad_rows(i64 n, int r, int ld, const double *__restrict__ X, double *__restrict__ Xp) {
     const i64 total = n * r;
     for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {

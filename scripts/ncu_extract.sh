@@ -28,12 +28,12 @@ for d in data:
     for k in want[1:]:
         if k in rec:
             print("   %-75s %s %s" % (k, rec[k], units[hdr.index(k)] if units else ""))
-    stalls = [(k, rec[k]) for k in hdr if "issue_stalled" in k and k.endswith("_per_warp_active.pct") and rec.get(k)]
+    stalls = [(k, rec[k]) for k in hdr if "issue_stalled" in k and k.endswith("_per_issue_active.ratio") and rec.get(k)]
     def num(x):
         try: return float(x.replace(",", ""))
         except Exception: return 0.0
     for k, v in sorted(stalls, key=lambda kv: -num(kv[1]))[:8]:
-        print("   stall %-69s %s" % (k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_warp_active.pct", ""), v))
+        print("   stall %-69s %s" % (k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v))
     out.append({k: rec.get(k, "") for k in want})
 if sys.argv[2]:
     with open(sys.argv[2], "w", newline="") as f:

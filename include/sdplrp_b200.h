@@ -99,7 +99,9 @@ void *sdplrp_stream(sdplrp_handle *h);
  *                 first idx/val block and epilogue operands are loaded while the current gathers are in flight; same
  *                 summation order, so results are those of the default kernels); 2 = in addition the short rows are taken in
  *                 bundles of 32/G consecutive rows whose CSR span is staged in shared memory with coalesced loads (needs the
- *                 short rows to be one contiguous range, else as 1).  Experimental: written at the end of round 1
+ *                 short rows to be one contiguous range, else as 1); 3 = the default short-row loop with all gathers of a block
+ *                 issued together (straight-line full blocks, unconditional gathers in the partial block, register
+ *                 budget given to ptxas by the launch bounds).  Experimental: written at the end of round 1
  *                 without GPU time left, measured first thing in round 2 (profiles/r1_gather_size_sweep.md)
  *   "spmm_pad"    with "spmm_prefetch" on one GPU: 1 = the gathers read a copy of the factor whose rows start on 128-byte
  *                 lines (an 80-byte row at an 80-byte stride crosses a line 5 times out of 8).  Confirmation experiment only:

@@ -10,7 +10,7 @@ set -u
 out=gpurun_out/r2_first
 mkdir -p $out
 export SDPLRP_TEST_EXPERIMENTAL=1
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "prefetch or bundle" > $out/pytest_experimental.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "prefetch or bundle or batched" > $out/pytest_experimental.log 2>&1
 echo "pytest experimental rc=$?" | tee $out/rc.txt
 unset SDPLRP_TEST_EXPERIMENTAL
 
@@ -34,6 +34,8 @@ line prefetch8 --option spmm_prefetch=1
 line prefetch4 --option spmm_prefetch=1 --option spmm_unroll=4
 line prefetch8_pad --option spmm_prefetch=1 --option spmm_pad=1
 line prefetch4_pad --option spmm_prefetch=1 --option spmm_unroll=4 --option spmm_pad=1
+line batched8 --option spmm_prefetch=3
+line batched4 --option spmm_prefetch=3 --option spmm_unroll=4
 line bundle8 --option spmm_prefetch=2
 line bundle4 --option spmm_prefetch=2 --option spmm_unroll=4
 line bundle8_pad --option spmm_prefetch=2 --option spmm_pad=1

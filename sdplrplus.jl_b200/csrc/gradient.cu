@@ -387,6 +387,69 @@ __global__ void __launch_bounds__(TPB) k_rows_combine(RowArgs a) {
 }
 
 // Y[j,:] += scale*coeff * sum_k XB[:,k] D[k] B[j,k]     (src/structs.jl:135-145)
+// Option "spmm_prefetch" = 3: the default class-0 row loop with ONE change -- full blocks are straight-line code and the last,
+// partial block gathers unconditionally (positions past the end repeat the row's last nonzero) with only its FMAs
+// predicated, so that all NB gathers of a block are in flight together.  In the default kernel ptxas issues the eight
+// predicated gathers as 1 + 2 + 5 with a dependent DFMA after each batch (source page of the round-1 capture,
+// profiles/r1_gather_size_sweep.md): three gather round trips per block.  EPI 2, one unit per lane, plain values.
+template <int VEC, int NB>
+__global__ void __launch_bounds__(TPB, NB >= 8 ? 2 : 4) k_rows_group_b(RowArgs a) {
+    const int nv = a.r / VEC;
+    const int G = a.G0;
+    const int gpb = TPB / G;
+    const int gib = threadIdx.x / G;
+    const int lg = threadIdx.x - gib * G;
+    const bool lane_ok = gib < gpb && lg < nv;
+    const size_t pc = (size_t)lg * VEC;
+    const i64 group = (i64)blockIdx.x * gpb + gib;
+    const i64 n_groups = (i64)gridDim.x * gpb;
+    const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
+    double s0 = 0.0, s1 = 0.0;
+    if (lane_ok)
+    for (i64 q = group; q < a.n_rows; q += n_groups) {
+        const i64 i = a.rows ? a.rows[q] : q;
+        if (i < a.own_lo || i >= a.own_hi) continue;
+        const int beg = a.ptr[i], end = a.ptr[i + 1];
+        Acc<VEC> x, z, acc;
+        acc.zero(); z.zero();
+        x.ld(a.X + (size_t)i * a.r + pc);              // epilogue operands: issued before the gathers, used after them
+        if (a.Z) z.ld(a.Z + (size_t)i * a.r + pc);
+        int k0 = beg;
+#pragma unroll 1
+        for (; k0 + NB <= end; k0 += NB) {
+            int c[NB];
+            double v[NB];
+            Acc<VEC> gq[NB];
+#pragma unroll
+            for (int j = 0; j < NB; j++) c[j] = ldg_i32_hint(a.idx + k0 + j, p_str);
+#pragma unroll
+            for (int j = 0; j < NB; j++) v[j] = ldg_f64_hint(a.val + k0 + j, p_str);
+#pragma unroll
+            for (int j = 0; j < NB; j++) gq[j].ld_hint(a.X + (size_t)c[j] * a.r + pc, c[j] < a.hot_rows ? p_hot : p_str);
+#pragma unroll
+            for (int j = 0; j < NB; j++) acc.fma_reg(v[j], gq[j]);
+        }
+        if (k0 < end) {
+            int c[NB];
+            double v[NB];
+            Acc<VEC> gq[NB];
+#pragma unroll
+            for (int j = 0; j < NB; j++) c[j] = ldg_i32_hint(a.idx + (k0 + j < end ? k0 + j : end - 1), p_str);
+#pragma unroll
+            for (int j = 0; j < NB; j++) v[j] = ldg_f64_hint(a.val + (k0 + j < end ? k0 + j : end - 1), p_str);
+#pragma unroll
+            for (int j = 0; j < NB; j++) gq[j].ld_hint(a.X + (size_t)c[j] * a.r + pc, c[j] < a.hot_rows ? p_hot : p_str);
+#pragma unroll
+            for (int j = 0; j < NB; j++)
+                if (k0 + j < end) acc.fma_reg(v[j], gq[j]);
+        }
+        s0 += acc.dot_reg(x);
+        if (a.Z) s1 += x.dot_reg(z);
+        acc.store(a.Y + (size_t)i * a.r + pc);
+    }
+    finish_sums<2>(a, s0, s1);
+}
+
 // ---- software-pipelined row loops (option "spmm_prefetch"; profiles/r1_gather_size_sweep.md) ----------------------------
 // The default kernels pay four to five DEPENDENT memory round trips per row: row list -> ptr pair -> idx/val block ->
 // gathers -> epilogue operands.  Measured: a nonzero costs the same 22-26 ps whether the gathered factor sits in L2 or not,
@@ -593,17 +656,38 @@ __global__ void __launch_bounds__(TPB_B, NB <= 4 ? 6 : 4) k_rows_bundle(RowArgs 
         __syncwarp();
         // 2. the row out of shared memory, NB gathers in flight per lane
         if (row_ok) {
-            for (int k0 = o; k0 < e; k0 += NB) {
+            // Full blocks are straight-line code and the last, partial block gathers unconditionally (positions past the
+            // end repeat the row's last nonzero: an L1 hit) with only its FMAs predicated.  With a predicate on every
+            // gather ptxas schedules LDS -> LDG -> DFMA per nonzero (seen in the SASS of the first version, and as the
+            // 1 + 2 + 5 batches of the default kernel): one round trip per nonzero instead of one per block.
+            int k0 = o;
+#pragma unroll 1
+            for (; k0 + NB <= e; k0 += NB) {
+                int c[NB];
+                double v[NB];
                 Acc<VEC> gq[NB];
 #pragma unroll
-                for (int j = 0; j < NB; j++)
-                    if (k0 + j < e) {
-                        const int c = si[k0 + j];
-                        gq[j].ld_hint(a.Xg + (size_t)c * a.ldx + pc, c < a.hot_rows ? p_hot : p_str);
-                    }
+                for (int j = 0; j < NB; j++) c[j] = si[k0 + j];
+#pragma unroll
+                for (int j = 0; j < NB; j++) gq[j].ld_hint(a.Xg + (size_t)c[j] * a.ldx + pc, c[j] < a.hot_rows ? p_hot : p_str);
+#pragma unroll
+                for (int j = 0; j < NB; j++) v[j] = sv[k0 + j];
+#pragma unroll
+                for (int j = 0; j < NB; j++) acc.fma_reg(v[j], gq[j]);
+            }
+            if (k0 < e) {
+                int c[NB];
+                double v[NB];
+                Acc<VEC> gq[NB];
+#pragma unroll
+                for (int j = 0; j < NB; j++) c[j] = si[k0 + j < e ? k0 + j : e - 1];
+#pragma unroll
+                for (int j = 0; j < NB; j++) gq[j].ld_hint(a.Xg + (size_t)c[j] * a.ldx + pc, c[j] < a.hot_rows ? p_hot : p_str);
+#pragma unroll
+                for (int j = 0; j < NB; j++) v[j] = sv[k0 + j < e ? k0 + j : e - 1];
 #pragma unroll
                 for (int j = 0; j < NB; j++)
-                    if (k0 + j < e) acc.fma_reg(sv[k0 + j], gq[j]);
+                    if (k0 + j < e) acc.fma_reg(v[j], gq[j]);
             }
             s0 += acc.dot_reg(x);
             if (a.Z) s1 += x.dot_reg(z);
@@ -918,7 +1002,10 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
         }
         if (pf) {
             if constexpr (MAXU == 1 && !IND && EPI == 2) {
-                if (c == 0 && h->spmm_prefetch >= 2 && 32 / a.G0 <= kBundleRows && class0_contiguous(h, cls, &a.c0_first)) {
+                if (c == 0 && h->spmm_prefetch == 3) {
+                    if (h->spmm_unroll >= 8) k_rows_group_b<VEC, 8><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
+                    else k_rows_group_b<VEC, 4><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
+                } else if (c == 0 && h->spmm_prefetch >= 2 && 32 / a.G0 <= kBundleRows && class0_contiguous(h, cls, &a.c0_first)) {
                     const int rpw = 32 / a.G0;
                     const int grid = grid_for((a.n_rows + rpw - 1) / rpw, TPB_B / 32, 32 * kNumSM);
                     if (h->spmm_unroll >= 8) k_rows_bundle<VEC, 8><<<grid, TPB_B, 0, st>>>(a);

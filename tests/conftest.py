@@ -37,8 +37,9 @@ GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "tile": {"relabel": 1, 
                # with SDPLRP_TEST_EXPERIMENTAL=1 (scripts/r2_first_call.sh) until they have been seen green on a B200
                "prefetch": {"relabel": 1, "spmm_prefetch": 1}, "prefetch4": {"spmm_prefetch": 1, "spmm_unroll": 4},
                "prefetch_pad": {"relabel": 1, "spmm_prefetch": 1, "spmm_pad": 1},
-               "bundle": {"relabel": 1, "spmm_prefetch": 2}, "bundle4_pad": {"spmm_prefetch": 2, "spmm_unroll": 4, "spmm_pad": 1}}
-EXPERIMENTAL_CONFIGS = ["prefetch", "prefetch4", "prefetch_pad", "bundle", "bundle4_pad"]
+               "bundle": {"relabel": 1, "spmm_prefetch": 2}, "bundle4_pad": {"spmm_prefetch": 2, "spmm_unroll": 4, "spmm_pad": 1},
+               "batched": {"relabel": 1, "spmm_prefetch": 3}, "batched4": {"spmm_prefetch": 3, "spmm_unroll": 4}}
+EXPERIMENTAL_CONFIGS = ["prefetch", "prefetch4", "prefetch_pad", "bundle", "bundle4_pad", "batched", "batched4"]
 GPU_CONFIG_PARAMS = ["default", "relabel", "tile", "phases"] + (
     EXPERIMENTAL_CONFIGS if os.environ.get("SDPLRP_TEST_EXPERIMENTAL", "0") not in ("", "0") else [])
 

@@ -109,6 +109,8 @@ void *sdplrp_stream(sdplrp_handle *h);
  *   "lanczos_dist" 0 = the q-step Lanczos operator is replicated on every rank (default); 1 = rows of S and of the Lanczos
  *                 vectors are divided among the ranks (one all-gather of n doubles + two scalar all-reduces per step).
  *                 Only with world > 1 and without re-orthogonalisation.  Experimental, as "spmm_prefetch"
+ *   "spmm_unroll" nonzeros per block of the short-row kernels: 8 (default) or 4
+ *   "spmm_g0"     1 = lane groups of exactly r/2 lanes per short row (default: 6 rows per warp at r = 10), 0 = next power of two
  *   "fused_tail"  1 = sdplrp_step_g uses the fused row pass (default), 0 = step and g separately
  *   "lbfgs_kernel" 1 = two-loop recursion on coefficients over directly computed dot products (default,
  *                 numlbfgsvecs <= 8), 0 = literal vector two-loop */

@@ -46,3 +46,14 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in text and "liboracle" not in text and "orc_" not in text, f
+
+
+def test_every_option_key_is_documented_in_the_header():
+    """sdplrp_set_option keys (csrc/api.cu) and the tuning-knob comment of include/sdplrp_b200.h must list the same names."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    keys = set(re.findall(r'k == "([a-z_0-9]+)"', open(os.path.join(root, "sdplrplus.jl_b200", "csrc", "api.cu")).read()))
+    hdr = open(os.path.join(root, "include", "sdplrp_b200.h")).read()
+    assert keys, "no option keys found"
+    missing = sorted(k for k in keys if f'"{k}"' not in hdr)
+    assert not missing, f"undocumented option keys: {missing}"

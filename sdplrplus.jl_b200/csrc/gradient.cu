@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(TPB_B, NB <= 4 ? 6 : 4) k_rows_bundle(RowArgs 
 // class 1 (one warp per row) and the chunks of class 2 (one warp per chunk, CHUNK), pipelined the same way; a block is the
 // 4 nonzeros of each of the 32/G lane groups, the row pipeline is warp-uniform
 template <int VEC, bool CHUNK>
-__global__ void __launch_bounds__(TPB, 2) k_rows_warp_pf(RowArgs a) {
+__global__ void __launch_bounds__(TPB, 3) k_rows_warp_pf(RowArgs a) {
     const int nv = a.r / VEC;
     const int lane = threadIdx.x & 31;
     const int lg = lane & (a.G - 1), grp = lane / a.G, ng = 32 / a.G;
@@ -717,20 +717,21 @@ __global__ void __launch_bounds__(TPB, 2) k_rows_warp_pf(RowArgs a) {
     i64 q_lo, q_hi;
     owned_q_range(CHUNK ? a.chunk_row : a.rows, a.n_rows, a.own_lo, a.own_hi, q_lo, q_hi);
     // stage A loads: the row of work item q (CHUNK: and its nonzero range, which does not depend on the row)
-    auto item_row = [&](i64 q) -> i64 { return q < q_hi ? (CHUNK ? (i64)__ldg(a.chunk_row + q) : (a.rows ? (i64)__ldg(a.rows + q) : q)) : (i64)-2; };
-    auto item_beg = [&](i64 q, i64 i) -> int { return i < 0 ? 0 : (CHUNK ? __ldg(a.chunk_start + q) : __ldg(a.ptr + i)); };
-    auto item_end = [&](i64 q, i64 i) -> int { return i < 0 ? 0 : (CHUNK ? __ldg(a.chunk_end + q) : __ldg(a.ptr + i + 1)); };
+    // (row labels fit 32 bits: the pattern arrays are int32)
+    auto item_row = [&](i64 q) -> int { return q < q_hi ? (CHUNK ? __ldg(a.chunk_row + q) : (a.rows ? __ldg(a.rows + q) : (int)q)) : -2; };
+    auto item_beg = [&](i64 q, int i) -> int { return i < 0 ? 0 : (CHUNK ? __ldg(a.chunk_start + q) : __ldg(a.ptr + i)); };
+    auto item_end = [&](i64 q, int i) -> int { return i < 0 ? 0 : (CHUNK ? __ldg(a.chunk_end + q) : __ldg(a.ptr + i + 1)); };
     i64 q = q_lo + (i64)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
     i64 qC = q;
-    i64 iC = item_row(q);
+    int iC = item_row(q);
     int kb = item_beg(q, iC), endC = item_end(q, iC);
     q += n_warps;
     i64 qB = q;
-    i64 iB = item_row(q);
+    int iB = item_row(q);
     int begB = item_beg(q, iB), endB = item_end(q, iB);
     q += n_warps;
     i64 qA = q;
-    i64 iA = item_row(q);
+    int iA = item_row(q);
     int cc[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) cc[j] = kb + go + j < endC ? ldg_i32_hint(a.idx + kb + go + j, p_str) : 0;
@@ -755,14 +756,13 @@ __global__ void __launch_bounds__(TPB, 2) k_rows_warp_pf(RowArgs a) {
         int cn[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) cn[j] = nkb + go + j < nend ? ldg_i32_hint(a.idx + nkb + go + j, p_str) : 0;
-        i64 iN = -2, qN = q;
+        int iN = -2;
         int begA = 0, endA = 0;
         Acc<VEC> xB, zB;
         xB.zero(); zB.zero();
         if (last) {
             begA = item_beg(qA, iA); endA = item_end(qA, iA);
             q += n_warps;
-            qN = q;
             iN = item_row(q);
             if (!CHUNK && iB >= 0 && piece_ok && grp == 0) {
                 xB.ld(a.X + (size_t)iB * a.r + pc);
@@ -786,7 +786,7 @@ __global__ void __launch_bounds__(TPB, 2) k_rows_warp_pf(RowArgs a) {
             acc.zero();
             qC = qB; iC = iB; kb = begB; endC = endB; xC = xB; zC = zB;
             qB = qA; iB = iA; begB = begA; endB = endA;
-            qA = qN; iA = iN;
+            qA = q; iA = iN;
         } else {
             kb += step;
         }

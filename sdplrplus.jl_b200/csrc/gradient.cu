@@ -386,7 +386,6 @@ __global__ void __launch_bounds__(TPB) k_rows_combine(RowArgs a) {
     finish_sums<EPI>(a, s0, s1);
 }
 
-// Y[j,:] += scale*coeff * sum_k XB[:,k] D[k] B[j,k]     (src/structs.jl:135-145)
 // Option "spmm_prefetch" = 3: the default class-0 row loop with ONE change -- full blocks are straight-line code and the last,
 // partial block gathers unconditionally (positions past the end repeat the row's last nonzero) with only its FMAs
 // predicated, so that all NB gathers of a block are in flight together.  In the default kernel ptxas issues the eight
@@ -796,6 +795,7 @@ __global__ void __launch_bounds__(TPB, 3) k_rows_warp_pf(RowArgs a) {
     if (!CHUNK) finish_sums<2>(a, s0, s1);
 }
 
+// Y[j,:] += scale*coeff * sum_k XB[:,k] D[k] B[j,k]     (src/structs.jl:135-145)
 __global__ void k_lr_apply(i64 lo, i64 hi, int r, int s, i64 n, const double *__restrict__ XB, const double *__restrict__ Dg,
                            const double *__restrict__ B, const double *__restrict__ y, int gid, double scale,
                            double *__restrict__ Y) {

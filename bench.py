@@ -108,7 +108,7 @@ def algorithmic_bytes(n, m, r, nnzT, nnzF, Ec, h, rows_local):
     }
 
 
-def generate(sp, n, edges, seed):
+def generate(sp, n, edges, seed, keep_on_device=False):
     """The C5 problem in the ABI's triplet form.  With several ranks, rank 0 generates and broadcasts: torch's CUDA
     generator is reproducible per device index only (rank 1 draws a different graph from the same seed), and every rank
     must preprocess the SAME problem -- the library replicates the pattern and partitions its rows."""
@@ -118,7 +118,7 @@ def generate(sp, n, edges, seed):
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     root = (not multi) or dist.get_rank() == 0
     if root:
-        asm, b, normC, E = sp.problems.powerlaw_maxcut_assembled(n, edges, seed)
+        asm, b, normC, E = sp.problems.powerlaw_maxcut_assembled(n, edges, seed, keep_on_device=keep_on_device and not multi)
     if multi:
         from sdplrplus.jl_b200.types import AssembledSparse
         dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
@@ -211,6 +211,8 @@ def main():
     ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE",
                     help="sdplrp_set_option before preprocessing (experiments: spmm_phases=1, spmm_kernel=1, ...)")
     ap.add_argument("--lanczos", type=int, default=0, help="also time this many Lanczos steps (reported separately)")
+    ap.add_argument("--device-triplets", action="store_true", help="one GPU: the generator's triplets stay on the device and go to "
+                    "sdplrp_preprocess_device (no 4.4 GB D2H + H2D); affects the setup times only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -249,7 +251,7 @@ def main():
         handle.set_option(key, float(val))
     n, r, h = args.n, args.rank, 4
 
-    asm, b, normC, E, gen_s = generate(sp, n, args.edges, args.seed)
+    asm, b, normC, E, gen_s = generate(sp, n, args.edges, args.seed, keep_on_device=args.device_triplets)
     data = SimpleData(n, n, b)
     t0 = time.perf_counter()
     eng = sp.B200Engine(data, handle=handle, asm=asm)

@@ -127,6 +127,13 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value);
 int32_t sdplrp_preprocess(sdplrp_handle *h, int64_t n, int64_t m, int64_t nA, const int64_t *mat_off,
                           const int64_t *I, const int64_t *J, const double *V,
                           const int64_t *sparse_global_inds);
+/* sdplrp_preprocess with the triplet arrays I, J, V in DEVICE memory of the handle's GPU: a problem generator that builds
+ * them there (exps/problems.jl:14-341 restated on the device) hands them over without a host round trip
+ * (4.4 GB each way at the 10M-vertex MaxCut).  mat_off and sparse_global_inds are host arrays as above.  The arrays are
+ * only read; work that produced them on another stream must have completed. */
+int32_t sdplrp_preprocess_device(sdplrp_handle *h, int64_t n, int64_t m, int64_t nA, const int64_t *mat_off,
+                                 const int64_t *d_I, const int64_t *d_J, const double *d_V,
+                                 const int64_t *sparse_global_inds);
 int32_t sdplrp_pattern_sizes(sdplrp_handle *h, int64_t *nnzT, int64_t *nnzF, int64_t *Ec);
 /* 1-based, exactly the seven outputs of preprocess_sparsecons */
 int32_t sdplrp_pattern_export(sdplrp_handle *h, int64_t *triu_colptr, int64_t *triu_rowval, int64_t *matptr,

@@ -10,7 +10,7 @@ set -u
 out=gpurun_out/r2_first
 mkdir -p $out
 export SDPLRP_TEST_EXPERIMENTAL=1
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "prefetch or bundle or batched" > $out/pytest_experimental.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "prefetch or bundle or batched or preprocess_device" > $out/pytest_experimental.log 2>&1
 echo "pytest experimental rc=$?" | tee $out/rc.txt
 unset SDPLRP_TEST_EXPERIMENTAL
 
@@ -50,6 +50,7 @@ line rank12 --rank 12
 line rank16 --rank 16
 line g0_pow2 --option spmm_g0=0
 line lanczos_default --lanczos 50
+line device_triplets --device-triplets
 } | tee $out/summary.txt
 
 # stall reasons / L1 wavefronts of the default class-0 kernel (one launch, --set full; read with ncu -i ... --page raw --csv)

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "sdplrp_synchronize": [_H],
     "sdplrp_set_option": [_H, C.c_char_p, C.c_double],
     "sdplrp_preprocess": [_H, C.c_int64, C.c_int64, C.c_int64, _p_i64, _p_i64, _p_i64, _p_f64, _p_i64],
+    "sdplrp_preprocess_device": [_H, C.c_int64, C.c_int64, C.c_int64, _p_i64, C.c_void_p, C.c_void_p, C.c_void_p, _p_i64],
     "sdplrp_pattern_sizes": [_H, _p_i64, _p_i64, _p_i64],
     "sdplrp_pattern_export": [_H, _p_i64, _p_i64, _p_i64, _p_i64, _p_f64, _p_f64, _p_i64, _p_i64, _p_i64],
     "sdplrp_add_symlowrank": [_H, C.c_int64, C.c_int64, _p_f64, _p_f64],
@@ -212,6 +213,18 @@ class Handle:
         gids1, pG = _i64(gids1)
         nA = len(gids1)
         rc = self.lib.sdplrp_preprocess(self._h, n, m, nA, p_off, pI, pJ, pV, pG)
+        self._check(rc, allow=(ERR_ASYMMETRIC,) if allow_asymmetric else ())
+        self.n, self.m, self.nA = int(n), int(m), int(nA)
+        return rc
+
+    def preprocess_device(self, n, m, mat_off, dI, dJ, dV, gids1, allow_asymmetric=False):
+        """sdplrp_preprocess_device: dI / dJ (int64, 1-based) and dV (float64) are CUDA tensors on the handle's GPU (anything
+        with data_ptr(), e.g. torch); mat_off / gids1 are host arrays.  The caller's stream must have finished writing them."""
+        mat_off, p_off = _i64(mat_off)
+        gids1, pG = _i64(gids1)
+        nA = len(gids1)
+        rc = self.lib.sdplrp_preprocess_device(self._h, n, m, nA, p_off, C.c_void_p(int(dI.data_ptr())), C.c_void_p(int(dJ.data_ptr())),
+                                               C.c_void_p(int(dV.data_ptr())), pG)
         self._check(rc, allow=(ERR_ASYMMETRIC,) if allow_asymmetric else ())
         self.n, self.m, self.nA = int(n), int(m), int(nA)
         return rc

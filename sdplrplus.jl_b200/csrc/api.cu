@@ -213,14 +213,40 @@ int32_t sdplrp_synchronize(sdplrp_handle *h) {
 
 void *sdplrp_stream(sdplrp_handle *h) { return h ? (void *)h->stream : nullptr; }
 
+static int32_t preprocess_common(sdplrp_handle *h, int64_t n, int64_t m, int64_t nA, const int64_t *mat_off, const int64_t *I,
+                                 const int64_t *J, const double *V, const int64_t *gids, bool triplets_on_device);
+
 int32_t sdplrp_preprocess(sdplrp_handle *h, int64_t n, int64_t m, int64_t nA, const int64_t *mat_off, const int64_t *I,
                           const int64_t *J, const double *V, const int64_t *gids) {
+    return preprocess_common(h, n, m, nA, mat_off, I, J, V, gids, false);
+}
+
+// the same with I, J, V in device memory of the handle's GPU (problem generators that build on the device)
+int32_t sdplrp_preprocess_device(sdplrp_handle *h, int64_t n, int64_t m, int64_t nA, const int64_t *mat_off, const int64_t *d_I,
+                                 const int64_t *d_J, const double *d_V, const int64_t *gids) {
+    REQUIRE_H(h);
+    if (nA > 0 && mat_off && mat_off[nA] > 0) {
+        if (!d_I || !d_J || !d_V) return fail(h, SDPLRP_ERR_ARG, "preprocess_device: null triplet arrays");
+        cudaPointerAttributes at;
+        const void *ptrs[3] = {d_I, d_J, d_V};
+        for (const void *p : ptrs) {
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != h->device) {
+                cudaGetLastError();
+                return fail(h, SDPLRP_ERR_ARG, "preprocess_device: I, J, V must be device memory of the handle's GPU");
+            }
+        }
+    }
+    return preprocess_common(h, n, m, nA, mat_off, d_I, d_J, d_V, gids, true);
+}
+
+static int32_t preprocess_common(sdplrp_handle *h, int64_t n, int64_t m, int64_t nA, const int64_t *mat_off, const int64_t *I,
+                                 const int64_t *J, const double *V, const int64_t *gids, bool triplets_on_device) {
     REQUIRE_H(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
     free_state(h);
     free_problem(h);
     if (nA > 0 && (!mat_off || !gids)) return fail(h, SDPLRP_ERR_ARG, "preprocess: null arrays");
-    int32_t rc = pre_build(h, n, m, nA, mat_off, I, J, V, gids);
+    int32_t rc = pre_build(h, n, m, nA, mat_off, I, J, V, gids, triplets_on_device);
     if (rc != SDPLRP_OK && rc != SDPLRP_ERR_ASYMMETRIC) return rc;
     // vectors of SolverVars / SDPData
     SDP_CHECK(dev_alloc(h, &h->b, m)); SDP_CHECK(dev_alloc(h, &h->lambda, m)); SDP_CHECK(dev_alloc(h, &h->lambda_ub, m));

@@ -318,7 +318,7 @@ __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterp
 
 // host-visible kernels' launcher prototypes (one TU per subsystem) -----------
 int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off, const int64_t *I,
-                  const int64_t *J, const double *V, const int64_t *gids);
+                  const int64_t *J, const double *V, const int64_t *gids, bool triplets_on_device = false);
 int32_t pre_export(sdplrp_handle *h, int64_t *triu_colptr, int64_t *triu_rowval, int64_t *matptr,
                    int64_t *nzind, double *one, double *two, int64_t *full_colptr, int64_t *full_rowval,
                    int64_t *mapped);

@@ -579,7 +579,7 @@ void pre_free(sdplrp_handle *h) {
 }
 
 int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off, const int64_t *I,
-                  const int64_t *J, const double *V, const int64_t *gids) {
+                  const int64_t *J, const double *V, const int64_t *gids, bool triplets_on_device) {
     pre_free(h);
     if (n <= 0 || m < 0 || nA < 0) return fail(h, SDPLRP_ERR_ARG, "preprocess: bad sizes");
     if (n >= ((i64)1 << 31) - 1) return fail(h, SDPLRP_ERR_ARG, "preprocess: n must fit int32");
@@ -609,9 +609,11 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
     int *errw = tmp.get<int>(h, 1, &rc);
     if (rc) return rc;
     if (nnz > 0) {
-        CUDA_TRY(h, cudaMemcpyAsync(dI, I, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(h, cudaMemcpyAsync(dJ, J, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(h, cudaMemcpyAsync(dV, V, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+        // sdplrp_preprocess_device: the triplets were built on this GPU (a device-side problem generator); no host round trip
+        const cudaMemcpyKind kind = triplets_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        CUDA_TRY(h, cudaMemcpyAsync(dI, I, (size_t)nnz * 8, kind, st));
+        CUDA_TRY(h, cudaMemcpyAsync(dJ, J, (size_t)nnz * 8, kind, st));
+        CUDA_TRY(h, cudaMemcpyAsync(dV, V, (size_t)nnz * 8, kind, st));
     }
     if (nA > 0) {
         CUDA_TRY(h, cudaMemcpyAsync(dOff, mat_off, (size_t)(nA + 1) * 8, cudaMemcpyHostToDevice, st));

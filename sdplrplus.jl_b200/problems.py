@@ -198,7 +198,7 @@ def powerlaw_graph(n, target_edges, seed, exponent=2.3):
     return _sym_from_edges(n, perm[np.minimum(u, n - 1)], perm[np.minimum(v, n - 1)])
 
 
-def powerlaw_maxcut_assembled(n, target_edges, seed, device=None, exponent=2.3):
+def powerlaw_maxcut_assembled(n, target_edges, seed, device=None, exponent=2.3, keep_on_device=False):
     """MaxCut on a Chung-Lu power-law graph, assembled straight into the ABI's triplet form
     (n one-entry diagonal constraints, then C = -1/4 L in CSC `findnz` order) without scipy:
     torch does the sampling / sort / unique, on the GPU when `device` is a CUDA device
@@ -241,11 +241,18 @@ def powerlaw_maxcut_assembled(n, target_edges, seed, device=None, exponent=2.3):
     del ck
     V = torch.where(row == col, -0.25 * deg[row].to(torch.float64), torch.full((1,), 0.25, dtype=torch.float64, device=dev))
     normC = float(torch.sqrt(torch.sum(V * V)).item())
-    I = torch.cat([diag + 1, row + 1]).cpu().numpy()
-    J = torch.cat([diag + 1, col + 1]).cpu().numpy()
-    Vh = torch.cat([torch.ones(n, dtype=torch.float64, device=dev), V]).cpu().numpy()
+    I_t = torch.cat([diag + 1, row + 1])
+    J_t = torch.cat([diag + 1, col + 1])
+    V_t = torch.cat([torch.ones(n, dtype=torch.float64, device=dev), V])
     nnzC = int(V.numel())
     mat_off = np.concatenate([np.arange(n + 1, dtype=np.int64), [n + nnzC]]).astype(np.int64)
     gids = np.arange(1, n + 2, dtype=np.int64)
-    asm = AssembledSparse(n, n, mat_off, I, J, Vh, gids, [])
+    if keep_on_device and dev.type == "cuda":
+        # direct device construction: the triplets stay where they were built and go to
+        # sdplrp_preprocess_device; the host arrays of the ABI's other form are not materialised
+        empty_i, empty_f = np.empty(0, np.int64), np.empty(0, np.float64)
+        asm = AssembledSparse(n, n, mat_off, empty_i, empty_i, empty_f, gids, [])
+        asm.device_triplets = (I_t.contiguous(), J_t.contiguous(), V_t.contiguous())
+        return asm, np.ones(n), normC, E
+    asm = AssembledSparse(n, n, mat_off, I_t.cpu().numpy(), J_t.cpu().numpy(), V_t.cpu().numpy(), gids, [])
     return asm, np.ones(n), normC, E

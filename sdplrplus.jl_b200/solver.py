@@ -134,13 +134,20 @@ class B200Engine:
             asm = assemble_sparse(data)
         self.assemble_time = time.perf_counter() - t0
         t0 = time.perf_counter()
-        self.h.preprocess(asm.n, asm.m, asm.mat_off, asm.I, asm.J, asm.V, asm.gids)
+        dev = getattr(asm, "device_triplets", None)
+        if dev is not None:   # triplets built on the GPU (problems.powerlaw_maxcut_assembled(..., keep_on_device=True)): no host round trip
+            import torch
+            torch.cuda.synchronize()
+            self.h.preprocess_device(asm.n, asm.m, asm.mat_off, dev[0], dev[1], dev[2], asm.gids)
+        else:
+            self.h.preprocess(asm.n, asm.m, asm.mat_off, asm.I, asm.J, asm.V, asm.gids)
         self.preprocess_time = time.perf_counter() - t0
         for gid1, A in asm.lowrank:
             self.h.add_symlowrank(gid1, A.B, A.D)
         self.h.set_problem(data.b, data.constraint_types.astype(np.uint8) if data.has_inequalities else None)
         self.n, self.m = data.n, data.m
-        self.h2d_bytes = asm.I.nbytes + asm.J.nbytes + asm.V.nbytes + asm.mat_off.nbytes + asm.gids.nbytes + data.b.nbytes
+        trip = 0 if dev is not None else asm.I.nbytes + asm.J.nbytes + asm.V.nbytes
+        self.h2d_bytes = trip + asm.mat_off.nbytes + asm.gids.nbytes + data.b.nbytes
 
     # state -----------------------------------------------------------------
     def init_vars(self, r, Rt0, lambda0, sigma0, numlbfgsvecs):

@@ -32,6 +32,7 @@ PY
 line default
 line prefetch8 --option spmm_prefetch=1
 line prefetch4 --option spmm_prefetch=1 --option spmm_unroll=4
+line prefetch8_phases --option spmm_prefetch=1 --option spmm_phases=1
 line prefetch8_pad --option spmm_prefetch=1 --option spmm_pad=1
 line prefetch4_pad --option spmm_prefetch=1 --option spmm_unroll=4 --option spmm_pad=1
 line batched8 --option spmm_prefetch=3

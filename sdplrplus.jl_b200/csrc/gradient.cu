@@ -134,6 +134,7 @@ struct Acc<1> {
     __device__ __forceinline__ void ld(const double *p) { v = __ldg(p); }
     __device__ __forceinline__ void ld_hint(const double *p, unsigned long long pol) { v = ldg_f64_hint(p, pol); }
     __device__ __forceinline__ double dot_reg(const Acc &o) const { return v * o.v; }
+    __device__ __forceinline__ void add_reg_first(const Acc &o) { v = o.v + 1.0 * v; }   // accumulate_onto(1.0, .) on a preloaded value
 };
 template <>
 struct Acc<2> {
@@ -174,6 +175,7 @@ struct Acc<2> {
     __device__ __forceinline__ void ld(const double *p) { v = ldg2(p); }
     __device__ __forceinline__ void ld_hint(const double *p, unsigned long long pol) { v = ldg_f64x2_hint(p, pol); }
     __device__ __forceinline__ double dot_reg(const Acc &o) const { return v.x * o.v.x + v.y * o.v.y; }
+    __device__ __forceinline__ void add_reg_first(const Acc &o) { v.x = o.v.x + 1.0 * v.x; v.y = o.v.y + 1.0 * v.y; }
 };
 
 // EPI 0: Y_i = scale * acc                                   (seam-level At!)
@@ -485,7 +487,7 @@ __device__ __forceinline__ void owned_q_range(const int *__restrict__ list, i64 
     q_hi = hi;
 }
 
-template <int VEC, int NB>
+template <int VEC, int NB, int EPI>
 __global__ void __launch_bounds__(TPB, 2) k_rows_group_pf(RowArgs a) {
     const int nv = a.r / VEC;
     const int G = a.G0;
@@ -504,25 +506,32 @@ __global__ void __launch_bounds__(TPB, 2) k_rows_group_pf(RowArgs a) {
         // row index of list entry q; -2 = past the end
         // (row labels and list positions fit 32 bits: the pattern arrays are int32)
         auto row_at = [&](i64 q) -> int { return q < q_hi ? (a.rows ? __ldg(a.rows + q) : (int)q) : -2; };
+        // a row covers [beg_arr[i], end_arr[i]) when those are given (two-phase pass: hub | tail columns), else [ptr[i], ptr[i+1])
+        auto row_beg = [&](int i) -> int { return a.beg_arr ? __ldg(a.beg_arr + i) : __ldg(a.ptr + i); };
+        auto row_end = [&](int i) -> int { return a.end_arr ? __ldg(a.end_arr + i) : __ldg(a.ptr + i + 1); };
+        constexpr bool kDots = (EPI == 2 || EPI == 4);   // epilogues with the fused sums read X_i (and Z_i)
         i64 q = q_lo + (i64)blockIdx.x * gpb + gib;
         // prologue: fill the three stages (the only place where the chain is exposed)
         int iC = row_at(q);
         int k0 = 0, endC = 0;
-        if (iC >= 0) { k0 = __ldg(a.ptr + iC); endC = __ldg(a.ptr + iC + 1); }
+        if (iC >= 0) { k0 = row_beg(iC); endC = row_end(iC); }
         q += n_groups;
         int iB = row_at(q);
         int begB = 0, endB = 0;
-        if (iB >= 0) { begB = __ldg(a.ptr + iB); endB = __ldg(a.ptr + iB + 1); }
+        if (iB >= 0) { begB = row_beg(iB); endB = row_end(iB); }
         q += n_groups;
         int iA = row_at(q);
         int cc[NB];
 #pragma unroll
         for (int j = 0; j < NB; j++) cc[j] = k0 + j < endC ? ldg_i32_hint(a.idx + k0 + j, p_str) : 0;
-        Acc<VEC> xC, zC, acc;
-        xC.zero(); zC.zero(); acc.zero();
+        Acc<VEC> xC, zC, yC, acc;
+        xC.zero(); zC.zero(); yC.zero(); acc.zero();
         if (iC >= 0 && piece_ok) {
-            xC.ld(a.X + (size_t)iC * a.r + pc);
-            if (a.Z) zC.ld(a.Z + (size_t)iC * a.r + pc);
+            if (kDots) {
+                xC.ld(a.X + (size_t)iC * a.r + pc);
+                if (a.Z) zC.ld(a.Z + (size_t)iC * a.r + pc);
+            }
+            if (EPI == 4) yC.v = *reinterpret_cast<const decltype(yC.v) *>(a.Y + (size_t)iC * a.r + pc);   // phase one's part of the row
         }
         while (iC >= 0) {
             // 1. the gathers of the current block, and its values (their addresses need no index, so they travel with the
@@ -545,30 +554,38 @@ __global__ void __launch_bounds__(TPB, 2) k_rows_group_pf(RowArgs a) {
             //    epilogue operands of row B
             int iN = -2;
             int begA = 0, endA = 0;
-            Acc<VEC> xB, zB;
-            xB.zero(); zB.zero();
+            Acc<VEC> xB, zB, yB;
+            xB.zero(); zB.zero(); yB.zero();
             if (last) {
-                if (iA >= 0) { begA = __ldg(a.ptr + iA); endA = __ldg(a.ptr + iA + 1); }
+                if (iA >= 0) { begA = row_beg(iA); endA = row_end(iA); }
                 q += n_groups;
                 iN = row_at(q);
                 if (iB >= 0 && piece_ok) {
-                    xB.ld(a.X + (size_t)iB * a.r + pc);
-                    if (a.Z) zB.ld(a.Z + (size_t)iB * a.r + pc);
+                    if (kDots) {
+                        xB.ld(a.X + (size_t)iB * a.r + pc);
+                        if (a.Z) zB.ld(a.Z + (size_t)iB * a.r + pc);
+                    }
+                    if (EPI == 4) yB.v = *reinterpret_cast<const decltype(yB.v) *>(a.Y + (size_t)iB * a.r + pc);
                 }
             }
             // 4. consume the gathers, in stored order
 #pragma unroll
             for (int j = 0; j < NB; j++)
                 if (piece_ok && k0 + j < endC) acc.fma_reg(vv[j], g[j]);
-            // 5. row epilogue (EPI 2) and rotation
+            // 5. row epilogue and rotation.  EPI 0: Y_i = scale*acc;  EPI 2: Y_i = acc with the fused sums;
+            //    EPI 4: Y_i += acc (second phase of the two-phase pass), the sums on the total
             if (last) {
                 if (piece_ok) {
-                    s0 += acc.dot_reg(xC);
-                    if (a.Z) s1 += xC.dot_reg(zC);
+                    if (EPI == 0) acc.scale(a.scale);
+                    if (EPI == 4) acc.add_reg_first(yC);
+                    if (kDots) {
+                        s0 += acc.dot_reg(xC);
+                        if (a.Z) s1 += xC.dot_reg(zC);
+                    }
                     acc.store(a.Y + (size_t)iC * a.r + pc);
                 }
                 acc.zero();
-                iC = iB; k0 = begB; endC = endB; xC = xB; zC = zB;
+                iC = iB; k0 = begB; endC = endB; xC = xB; zC = zB; yC = yB;
                 iB = iA; begB = begA; endB = endA;
                 iA = iN;
             } else {
@@ -578,7 +595,7 @@ __global__ void __launch_bounds__(TPB, 2) k_rows_group_pf(RowArgs a) {
             for (int j = 0; j < NB; j++) cc[j] = cn[j];
         }
     }
-    finish_sums<2>(a, s0, s1);
+    finish_sums<EPI>(a, s0, s1);
 }
 
 // Class 0 by BUNDLES (option "spmm_prefetch" = 2): a warp takes 32/G0 CONSECUTIVE rows (6 at r = 10) whose nonzeros are one
@@ -701,7 +718,7 @@ __global__ void __launch_bounds__(TPB_B, NB <= 4 ? 6 : 4) k_rows_bundle(RowArgs 
 
 // class 1 (one warp per row) and the chunks of class 2 (one warp per chunk, CHUNK), pipelined the same way; a block is the
 // 4 nonzeros of each of the 32/G lane groups, the row pipeline is warp-uniform
-template <int VEC, bool CHUNK>
+template <int VEC, bool CHUNK, int EPI>
 __global__ void __launch_bounds__(TPB, 3) k_rows_warp_pf(RowArgs a) {
     const int nv = a.r / VEC;
     const int lane = threadIdx.x & 31;
@@ -718,8 +735,13 @@ __global__ void __launch_bounds__(TPB, 3) k_rows_warp_pf(RowArgs a) {
     // stage A loads: the row of work item q (CHUNK: and its nonzero range, which does not depend on the row)
     // (row labels fit 32 bits: the pattern arrays are int32)
     auto item_row = [&](i64 q) -> int { return q < q_hi ? (CHUNK ? __ldg(a.chunk_row + q) : (a.rows ? __ldg(a.rows + q) : (int)q)) : -2; };
-    auto item_beg = [&](i64 q, int i) -> int { return i < 0 ? 0 : (CHUNK ? __ldg(a.chunk_start + q) : __ldg(a.ptr + i)); };
-    auto item_end = [&](i64 q, int i) -> int { return i < 0 ? 0 : (CHUNK ? __ldg(a.chunk_end + q) : __ldg(a.ptr + i + 1)); };
+    auto item_beg = [&](i64 q, int i) -> int {
+        return i < 0 ? 0 : (CHUNK ? __ldg(a.chunk_start + q) : (a.beg_arr ? __ldg(a.beg_arr + i) : __ldg(a.ptr + i)));
+    };
+    auto item_end = [&](i64 q, int i) -> int {
+        return i < 0 ? 0 : (CHUNK ? __ldg(a.chunk_end + q) : (a.end_arr ? __ldg(a.end_arr + i) : __ldg(a.ptr + i + 1)));
+    };
+    constexpr bool kDots = !CHUNK && (EPI == 2 || EPI == 4);
     i64 q = q_lo + (i64)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
     i64 qC = q;
     int iC = item_row(q);
@@ -734,11 +756,14 @@ __global__ void __launch_bounds__(TPB, 3) k_rows_warp_pf(RowArgs a) {
     int cc[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) cc[j] = kb + go + j < endC ? ldg_i32_hint(a.idx + kb + go + j, p_str) : 0;
-    Acc<VEC> xC, zC, acc;
-    xC.zero(); zC.zero(); acc.zero();
+    Acc<VEC> xC, zC, yC, acc;
+    xC.zero(); zC.zero(); yC.zero(); acc.zero();
     if (!CHUNK && iC >= 0 && piece_ok && grp == 0) {
-        xC.ld(a.X + (size_t)iC * a.r + pc);
-        if (a.Z) zC.ld(a.Z + (size_t)iC * a.r + pc);
+        if (kDots) {
+            xC.ld(a.X + (size_t)iC * a.r + pc);
+            if (a.Z) zC.ld(a.Z + (size_t)iC * a.r + pc);
+        }
+        if (EPI == 4) yC.v = *reinterpret_cast<const decltype(yC.v) *>(a.Y + (size_t)iC * a.r + pc);
     }
     while (iC >= 0) {  // warp-uniform
         const int k0 = kb + go;
@@ -757,15 +782,18 @@ __global__ void __launch_bounds__(TPB, 3) k_rows_warp_pf(RowArgs a) {
         for (int j = 0; j < 4; j++) cn[j] = nkb + go + j < nend ? ldg_i32_hint(a.idx + nkb + go + j, p_str) : 0;
         int iN = -2;
         int begA = 0, endA = 0;
-        Acc<VEC> xB, zB;
-        xB.zero(); zB.zero();
+        Acc<VEC> xB, zB, yB;
+        xB.zero(); zB.zero(); yB.zero();
         if (last) {
             begA = item_beg(qA, iA); endA = item_end(qA, iA);
             q += n_warps;
             iN = item_row(q);
             if (!CHUNK && iB >= 0 && piece_ok && grp == 0) {
-                xB.ld(a.X + (size_t)iB * a.r + pc);
-                if (a.Z) zB.ld(a.Z + (size_t)iB * a.r + pc);
+                if (kDots) {
+                    xB.ld(a.X + (size_t)iB * a.r + pc);
+                    if (a.Z) zB.ld(a.Z + (size_t)iB * a.r + pc);
+                }
+                if (EPI == 4) yB.v = *reinterpret_cast<const decltype(yB.v) *>(a.Y + (size_t)iB * a.r + pc);
             }
         }
 #pragma unroll
@@ -777,13 +805,17 @@ __global__ void __launch_bounds__(TPB, 3) k_rows_warp_pf(RowArgs a) {
                 if (CHUNK) {
                     acc.store(a.scratch + (size_t)qC * a.r + pc);
                 } else {
-                    s0 += acc.dot_reg(xC);
-                    if (a.Z) s1 += xC.dot_reg(zC);
+                    if (EPI == 0) acc.scale(a.scale);
+                    if (EPI == 4) acc.add_reg_first(yC);
+                    if (kDots) {
+                        s0 += acc.dot_reg(xC);
+                        if (a.Z) s1 += xC.dot_reg(zC);
+                    }
                     acc.store(a.Y + (size_t)iC * a.r + pc);
                 }
             }
             acc.zero();
-            qC = qB; iC = iB; kb = begB; endC = endB; xC = xB; zC = zB;
+            qC = qB; iC = iB; kb = begB; endC = endB; xC = xB; zC = zB; yC = yB;
             qB = qA; iB = iA; begB = begA; endB = endA;
             qA = q; iA = iN;
         } else {
@@ -792,7 +824,7 @@ __global__ void __launch_bounds__(TPB, 3) k_rows_warp_pf(RowArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; j++) cc[j] = cn[j];
     }
-    if (!CHUNK) finish_sums<2>(a, s0, s1);
+    if (!CHUNK) finish_sums<EPI>(a, s0, s1);
 }
 
 // Y[j,:] += scale*coeff * sum_k XB[:,k] D[k] B[j,k]     (src/structs.jl:135-145)
@@ -991,7 +1023,9 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
     const int gpb0 = TPB / a.G0;
     // software-pipelined row loops: only the shape of the hot pass (one unit per lane, plain values, EPI 2, whole rows)
     bool pf = false;
-    if constexpr (MAXU == 1 && !IND && EPI == 2) pf = h->spmm_prefetch > 0 && sums && !a.beg_arr && !a.end_arr && !long_empty;
+    constexpr bool kPfShape = (MAXU == 1 && !IND && (EPI == 0 || EPI == 2 || EPI == 4));
+    if constexpr (kPfShape) pf = h->spmm_prefetch > 0 && (sums != nullptr) == (EPI != 0);
+    const bool whole_rows = !a.beg_arr && !a.end_arr;   // the bundle / batched kernels walk whole rows only
     for (int c = 0; c < 3; c++) {
         if (sums) a.out = sums + 2 * c;
         a.rows = cls.list[c];
@@ -1001,20 +1035,25 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
             continue;
         }
         if (pf) {
-            if constexpr (MAXU == 1 && !IND && EPI == 2) {
-                if (c == 0 && h->spmm_prefetch == 3) {
+            if constexpr (kPfShape) {
+                if (c == 0 && h->spmm_prefetch == 3 && whole_rows && EPI == 2) {
                     if (h->spmm_unroll >= 8) k_rows_group_b<VEC, 8><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
                     else k_rows_group_b<VEC, 4><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
-                } else if (c == 0 && h->spmm_prefetch >= 2 && 32 / a.G0 <= kBundleRows && class0_contiguous(h, cls, &a.c0_first)) {
+                } else if (c == 0 && h->spmm_prefetch == 2 && whole_rows && EPI == 2 && 32 / a.G0 <= kBundleRows &&
+                           class0_contiguous(h, cls, &a.c0_first)) {
                     const int rpw = 32 / a.G0;
                     const int grid = grid_for((a.n_rows + rpw - 1) / rpw, TPB_B / 32, 32 * kNumSM);
                     if (h->spmm_unroll >= 8) k_rows_bundle<VEC, 8><<<grid, TPB_B, 0, st>>>(a);
                     else k_rows_bundle<VEC, 4><<<grid, TPB_B, 0, st>>>(a);
                 } else if (c == 0) {
-                    if (h->spmm_unroll >= 8) k_rows_group_pf<VEC, 8><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
-                    else k_rows_group_pf<VEC, 4><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
+                    if (h->spmm_unroll >= 8) k_rows_group_pf<VEC, 8, EPI><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
+                    else k_rows_group_pf<VEC, 4, EPI><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
                 } else if (c == 1) {
-                    k_rows_warp_pf<VEC, false><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
+                    k_rows_warp_pf<VEC, false, EPI><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
+                } else if (long_empty) {   // second phase: the long rows were handled whole in the first; only their epilogue is left
+                    RowArgs b = a;
+                    b.beg_arr = a.ptr + 1; b.end_arr = a.ptr + 1;
+                    k_rows_warp_pf<VEC, false, EPI><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
                 } else {
                     const i64 need = longs.n_chunks * (i64)a.r;
                     if (h->tile_scratch_len < need) {
@@ -1025,7 +1064,7 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
                     b.chunk_start = longs.chunk_start; b.chunk_end = longs.chunk_end; b.chunk_row = longs.chunk_row;
                     b.long_rows = longs.long_rows; b.long_cptr = longs.long_cptr; b.scratch = h->tile_scratch;
                     b.n_rows = longs.n_chunks;
-                    k_rows_warp_pf<VEC, true><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
+                    k_rows_warp_pf<VEC, true, EPI><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
                     KLAUNCH(h);
                     b.n_rows = longs.n_long;
                     k_rows_combine<VEC, MAXU, EPI><<<grid_for(b.n_rows, gpb, 4 * kNumSM), TPB, 0, st>>>(b);

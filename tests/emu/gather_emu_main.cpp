@@ -87,28 +87,123 @@ Out run(const Problem &P, int variant, int NB, i64 own_lo, i64 own_hi, bool pad,
         if (a.n_rows == 0) continue;
         if (c == 0) {
             if (variant == 0) { if (NB == 8) emu::launch(k_rows_group<VEC, 1, false, 2, 8>, 3, TPB, a); else emu::launch(k_rows_group<VEC, 1, false, 2, 4>, 3, TPB, a); }
-            else if (variant == 1) { if (NB == 8) emu::launch(k_rows_group_pf<VEC, 8>, 3, TPB, a); else emu::launch(k_rows_group_pf<VEC, 4>, 3, TPB, a); }
+            else if (variant == 1) { if (NB == 8) emu::launch(k_rows_group_pf<VEC, 8, 2>, 3, TPB, a); else emu::launch(k_rows_group_pf<VEC, 4, 2>, 3, TPB, a); }
             else if (variant == 2 && contig && 32 / a.G0 <= kBundleRows) {
                 a.c0_first = P.cls[0].front();
                 if (NB == 8) emu::launch(k_rows_bundle<VEC, 8>, 3, TPB_B, a); else emu::launch(k_rows_bundle<VEC, 4>, 3, TPB_B, a);
-            } else if (variant == 2) { emu::launch(k_rows_group_pf<VEC, 8>, 2, TPB, a); }
+            } else if (variant == 2) { emu::launch(k_rows_group_pf<VEC, 8, 2>, 2, TPB, a); }
             else { if (NB == 8) emu::launch(k_rows_group_b<VEC, 8>, 3, TPB, a); else emu::launch(k_rows_group_b<VEC, 4>, 3, TPB, a); }
         } else if (c == 1) {
             if (variant == 0) emu::launch(k_rows_warp<VEC, 1, false, 2, false>, 2, TPB, a);
-            else emu::launch(k_rows_warp_pf<VEC, false>, 2, TPB, a);
+            else emu::launch(k_rows_warp_pf<VEC, false, 2>, 2, TPB, a);
         } else {
             RowArgs b = a;
             b.chunk_start = P.chunk_start.data(); b.chunk_end = P.chunk_end.data(); b.chunk_row = P.chunk_row.data();
             b.long_rows = P.long_rows.data(); b.long_cptr = P.long_cptr.data(); b.scratch = scratch.data();
             b.n_rows = (i64)P.chunk_row.size();
             if (variant == 0) emu::launch(k_rows_warp<VEC, 1, false, 2, true>, 1, TPB, b);
-            else emu::launch(k_rows_warp_pf<VEC, true>, 1, TPB, b);
+            else emu::launch(k_rows_warp_pf<VEC, true, 2>, 1, TPB, b);
             b.n_rows = (i64)P.long_rows.size();
             emu::launch(k_rows_combine<VEC, 1, 2>, 1, TPB, b);
         }
     }
     check(ticket[0] == 0, "ticket reset", n, r, variant);
     return o;
+}
+
+// The two-phase pass (hub | tail columns; grad_obj_spmm with "spmm_phases"): phase one takes the columns < hub of every
+// row with a plain store (EPI 0; the long rows whole, chunked), phase two the rest on top with the fused sums (EPI 4; the
+// long rows only their epilogue).  pipelined = the k_rows_*_pf kernels, else the default ones.
+template <int VEC>
+Out run_phases(const Problem &P, bool pipelined, int NB, i64 own_lo, i64 own_hi, int hub) {
+    const int n = P.n, r = P.r, nv = r / VEC;
+    Out o; o.Y.assign((size_t)n * r, std::nan(""));
+    std::vector<double> partials(1 << 16, 0.0), scratch(std::max<size_t>(1, P.chunk_row.size()) * r, std::nan(""));
+    unsigned ticket[4] = {0, 0, 0, 0};
+    for (double &s : o.sums) s = 0.0;
+    // columns ascending inside a row (the library's patterns are; make() draws them at random, so sort a copy)
+    std::vector<int> idx = P.idx; std::vector<double> val = P.val; std::vector<int> mid(n), ptr1(P.ptr.begin() + 1, P.ptr.end());
+    for (int i = 0; i < n; i++) {
+        std::vector<std::pair<int, double>> e;
+        for (int k = P.ptr[i]; k < P.ptr[i + 1]; k++) e.push_back({idx[k], val[k]});
+        std::stable_sort(e.begin(), e.end(), [](auto &x, auto &y) { return x.first < y.first; });
+        int m = P.ptr[i];
+        for (int k = P.ptr[i]; k < P.ptr[i + 1]; k++) { idx[k] = e[k - P.ptr[i]].first; val[k] = e[k - P.ptr[i]].second; if (idx[k] < hub) m = k + 1; }
+        mid[i] = m;
+    }
+    RowArgs a = {};
+    a.ptr = P.ptr.data(); a.idx = idx.data(); a.val = val.data();
+    a.X = P.X.data(); a.Xg = P.X.data(); a.ldx = r; a.Y = o.Y.data(); a.Z = P.Z.data(); a.scale = 1.0;
+    a.r = r; a.G = pick_group(nv); a.G0 = nv; a.hot_rows = hub;
+    a.partials = partials.data(); a.ticket = ticket; a.own_lo = own_lo; a.own_hi = own_hi;
+    for (int phase = 0; phase < 2; phase++) {
+        RowArgs p = a;
+        if (phase == 0) p.end_arr = mid.data(); else p.beg_arr = mid.data();
+        for (int c = 0; c < 3; c++) {
+            p.out = o.sums + 2 * c;
+            p.rows = P.cls[c].data(); p.n_rows = (i64)P.cls[c].size();
+            if (p.n_rows == 0) continue;
+            if (c == 0) {
+                if (phase == 0) {
+                    if (pipelined) { if (NB == 8) emu::launch(k_rows_group_pf<VEC, 8, 0>, 3, TPB, p); else emu::launch(k_rows_group_pf<VEC, 4, 0>, 3, TPB, p); }
+                    else emu::launch(k_rows_group<VEC, 1, false, 0, 8>, 3, TPB, p);
+                } else {
+                    if (pipelined) { if (NB == 8) emu::launch(k_rows_group_pf<VEC, 8, 4>, 3, TPB, p); else emu::launch(k_rows_group_pf<VEC, 4, 4>, 3, TPB, p); }
+                    else emu::launch(k_rows_group<VEC, 1, false, 4, 8>, 3, TPB, p);
+                }
+            } else if (c == 1) {
+                if (phase == 0) { if (pipelined) emu::launch(k_rows_warp_pf<VEC, false, 0>, 2, TPB, p); else emu::launch(k_rows_warp<VEC, 1, false, 0, false>, 2, TPB, p); }
+                else { if (pipelined) emu::launch(k_rows_warp_pf<VEC, false, 4>, 2, TPB, p); else emu::launch(k_rows_warp<VEC, 1, false, 4, false>, 2, TPB, p); }
+            } else if (phase == 0) {   // long rows whole, chunked, plain store
+                RowArgs b = p;
+                b.beg_arr = nullptr; b.end_arr = nullptr;
+                b.chunk_start = P.chunk_start.data(); b.chunk_end = P.chunk_end.data(); b.chunk_row = P.chunk_row.data();
+                b.long_rows = P.long_rows.data(); b.long_cptr = P.long_cptr.data(); b.scratch = scratch.data();
+                b.n_rows = (i64)P.chunk_row.size();
+                if (pipelined) emu::launch(k_rows_warp_pf<VEC, true, 0>, 1, TPB, b); else emu::launch(k_rows_warp<VEC, 1, false, 0, true>, 1, TPB, b);
+                b.n_rows = (i64)P.long_rows.size();
+                emu::launch(k_rows_combine<VEC, 1, 0>, 1, TPB, b);
+            } else {                   // long_empty: only the epilogue with the sums
+                RowArgs b = p;
+                b.beg_arr = ptr1.data(); b.end_arr = ptr1.data();
+                if (pipelined) emu::launch(k_rows_warp_pf<VEC, false, 4>, 1, TPB, b); else emu::launch(k_rows_warp<VEC, 1, false, 4, false>, 1, TPB, b);
+            }
+        }
+    }
+    return o;
+}
+
+template <int VEC>
+void suite_phases(int n, int r, unsigned seed) {
+    const Problem P = make(n, r, true, seed);
+    const i64 ranges[2][2] = {{0, n}, {n / 4, 3 * n / 4}};
+    for (int rg = 0; rg < 2; rg++) {
+        const i64 lo = ranges[rg][0], hi = ranges[rg][1];
+        const Out ref = run_phases<VEC>(P, false, 8, lo, hi, n / 5);
+        double s0 = 0.0, s1 = 0.0;
+        for (int i = 0; i < n; i++)
+            for (int c = 0; c < r; c++) {
+                const double got = ref.Y[(size_t)i * r + c];
+                if (i < lo || i >= hi) { check(std::isnan(got), "phases: row outside the owned range written", n, r, 0); continue; }
+                double acc = 0.0;
+                for (int k = P.ptr[i]; k < P.ptr[i + 1]; k++) acc += P.val[k] * P.X[(size_t)P.idx[k] * r + c];
+                check(std::fabs(got - acc) <= 1e-10 * (1.0 + std::fabs(acc)), "phases: default kernels vs CSR product", n, r, 0);
+                s0 += acc * P.X[(size_t)i * r + c]; s1 += P.X[(size_t)i * r + c] * P.Z[(size_t)i * r + c];
+            }
+        const double t0 = ref.sums[0] + ref.sums[2] + ref.sums[4], t1 = ref.sums[1] + ref.sums[3] + ref.sums[5];
+        check(std::fabs(t0 - s0) <= 1e-9 * (1.0 + std::fabs(s0)) && std::fabs(t1 - s1) <= 1e-9 * (1.0 + std::fabs(s1)), "phases: default sums", n, r, 0);
+        for (int NB : {8, 4}) {
+            const Out got = run_phases<VEC>(P, true, NB, lo, hi, n / 5);
+            bool same = true;
+            for (size_t e = 0; e < ref.Y.size(); e++) {
+                const double x = ref.Y[e], y = got.Y[e];
+                if (!((std::isnan(x) && std::isnan(y)) || x == y)) same = false;
+            }
+            check(same, "phases: pipelined rows differ from the default kernels (bitwise)", n, r, NB);
+            const double u0 = got.sums[0] + got.sums[2] + got.sums[4], u1 = got.sums[1] + got.sums[3] + got.sums[5];
+            check(std::fabs(u0 - t0) <= 1e-10 * (1.0 + std::fabs(t0)) && std::fabs(u1 - t1) <= 1e-10 * (1.0 + std::fabs(t1)), "phases: fused sums differ", n, r, NB);
+        }
+    }
 }
 
 template <int VEC>
@@ -161,6 +256,8 @@ int main() {
     suite<2>(400, 8, true, 3);     // 4 lanes per row, 8 rows per bundle
     suite<2>(300, 6, true, 4);     // 3 lanes per row: 10 rows per warp (> kBundleRows: fallback)
     suite<1>(300, 5, true, 5);     // odd rank: scalar pieces
+    suite_phases<2>(600, 10, 6);   // hub | tail two-phase pass: EPI 0 with row sub-ranges, then EPI 4 on top
+    suite_phases<1>(300, 5, 7);
     std::printf(g_fail ? "emulation: %d FAILED checks\n" : "emulation: all kernel variants agree with the default kernels\n", g_fail);
     return g_fail ? 1 : 0;
 }

@@ -256,11 +256,33 @@ __device__ __forceinline__ void finish_sums(const RowArgs &a, double s0, double 
 
 #define VAL_AT(k) (IND ? __ldg(a.val + __ldg(a.src + (k))) : __ldg(a.val + (k)))
 
+// Register budget handed to ptxas for the DEFAULT row kernels: the second __launch_bounds__ argument (minimum resident CTAs
+// per SM).  Without it ptxas aims at 48-64 registers and splits the gathers of a block into dependent batches (1 + 2 + 5 in
+// k_rows_group, 2 + 2 in k_rows_warp: profiles/r1_gather_size_sweep.md); with 3 (80 registers) it can keep them together.
+// 0 = no second argument = the configuration every measurement of round 1 was taken with.  A/B: scripts/r2_launch_bounds.sh
+// (make EXTRA="-DSDPLRP_LB_GROUP=3 -DSDPLRP_LB_WARP=3").
+#ifndef SDPLRP_LB_GROUP
+#define SDPLRP_LB_GROUP 0
+#endif
+#ifndef SDPLRP_LB_WARP
+#define SDPLRP_LB_WARP 0
+#endif
+#if SDPLRP_LB_GROUP > 0
+#define LB_GROUP __launch_bounds__(TPB, SDPLRP_LB_GROUP)
+#else
+#define LB_GROUP __launch_bounds__(TPB)
+#endif
+#if SDPLRP_LB_WARP > 0
+#define LB_WARP __launch_bounds__(TPB, SDPLRP_LB_WARP)
+#else
+#define LB_WARP __launch_bounds__(TPB)
+#endif
+
 // class 0: one group of G0 lanes per row (G0 = pieces per row when that fits a warp: 6 rows per warp at r = 10);
 // the row's nonzeros are taken NB at a time, fully predicated, so a row of <= NB nonzeros costs one round trip
 // ptr -> idx/val -> gathers with NB independent 128-bit gathers in flight per lane
 template <int VEC, int MAXU, bool IND, int EPI, int NB>
-__global__ void __launch_bounds__(TPB) k_rows_group(RowArgs a) {
+__global__ void LB_GROUP k_rows_group(RowArgs a) {
     const int nv = a.r / VEC;
     const int G = a.G0;
     const int gpb = TPB / G;                       // groups per CTA (lanes beyond gpb*G idle)
@@ -308,7 +330,7 @@ __global__ void __launch_bounds__(TPB) k_rows_group(RowArgs a) {
 // sums in a.scratch (combined per row, in chunk order, by k_rows_combine) -- a hub row of 30 k nonzeros is spread over
 // 60 warps instead of serialising one CTA, which is what lets the pass scale when the rows are divided among GPUs.
 template <int VEC, int MAXU, bool IND, int EPI, bool CHUNK>
-__global__ void __launch_bounds__(TPB) k_rows_warp(RowArgs a) {
+__global__ void LB_WARP k_rows_warp(RowArgs a) {
     const int nv = a.r / VEC;
     const int lane = threadIdx.x & 31;
     const int lg = lane & (a.G - 1), grp = lane / a.G, ng = 32 / a.G;
@@ -927,8 +949,16 @@ __global__ void __launch_bounds__(TPB) k_grad_diag(i64 lo, i64 hi, int r, double
 //   G_i = 2*(y_obj*CR_i + (sum_p val_p*y_p + S_dyn(i,i))*R_i) ;  ||G||^2 and ||max(raw,lb)||^2 fused.
 // 7N + ~9 doubles per constraint instead of the 9N + 3 m-vector passes of step / y / gradient / norm kernels.
 // raw is double-buffered (raw_in -> raw_out): every piece-thread of a row re-derives y_p from raw_in, only piece 0 writes.
+#ifndef SDPLRP_LB_TAIL   // as SDPLRP_LB_GROUP, for the fused tail: its seven m-vector loads per constraint are issued in four dependent batches at 40 registers
+#define SDPLRP_LB_TAIL 0
+#endif
+#if SDPLRP_LB_TAIL > 0
+#define LB_TAIL __launch_bounds__(TPB, SDPLRP_LB_TAIL)
+#else
+#define LB_TAIL __launch_bounds__(TPB)
+#endif
 template <int VEC>
-__global__ void __launch_bounds__(TPB) k_step_grad(i64 lo, i64 hi, int r, double a, double sigma, double yobj,
+__global__ void LB_TAIL k_step_grad(i64 lo, i64 hi, int r, double a, double sigma, double yobj,
                                                    const double *__restrict__ D, double *__restrict__ R,
                                                    const double *__restrict__ CD, double *__restrict__ CR,
                                                    const int *__restrict__ rowc_ptr, const double *__restrict__ rowc_val,

@@ -106,6 +106,8 @@ void *sdplrp_stream(sdplrp_handle *h);
  *   "spmm_pad"    with "spmm_prefetch" on one GPU: 1 = the gathers read a copy of the factor whose rows start on 128-byte
  *                 lines (an 80-byte row at an 80-byte stride crosses a line 5 times out of 8).  Confirmation experiment only:
  *                 no gain expected (profiles/r1_gather_size_sweep.md, addendum)
+ *   "lanczos_bundle" 1 = the short rows of the Lanczos operator are taken in bundles of 8 consecutive rows (pattern loaded
+ *                 coalesced, all gathers of a bundle in flight together); needs them to be one contiguous range.  Experimental
  *   "lanczos_dist" 0 = the q-step Lanczos operator is replicated on every rank (default); 1 = rows of S and of the Lanczos
  *                 vectors are divided among the ranks (one all-gather of n doubles + two scalar all-reduces per step).
  *                 Only with world > 1 and without re-orthogonalisation.  Experimental, as "spmm_prefetch"

@@ -51,6 +51,7 @@ line rank12 --rank 12
 line rank16 --rank 16
 line g0_pow2 --option spmm_g0=0
 line lanczos_default --lanczos 50
+line lanczos_bundle --lanczos 50 --option lanczos_bundle=1
 line device_triplets --device-triplets
 } | tee $out/summary.txt
 

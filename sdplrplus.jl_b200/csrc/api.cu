@@ -125,6 +125,7 @@ int32_t sdplrp_create(int32_t device, int32_t rank, int32_t world, const void *n
     if (const char *e = getenv("SDPLRP_SPMM_UNROLL")) h->spmm_unroll = atoi(e);
     if (const char *e = getenv("SDPLRP_SPMM_G0")) h->spmm_g0 = atoi(e);
     if (const char *e = getenv("SDPLRP_SPMM_PAD")) h->spmm_pad = atoi(e) > 0 ? 1 : 0;
+    if (const char *e = getenv("SDPLRP_LANCZOS_BUNDLE")) h->lanczos_bundle = atoi(e) > 0 ? 1 : 0;
     if (const char *e = getenv("SDPLRP_LANCZOS_DIST")) h->lanczos_dist = atoi(e) > 0 ? 1 : 0;
     if (const char *e = getenv("SDPLRP_SPMM_PREFETCH")) h->spmm_prefetch = atoi(e) > 0 ? atoi(e) : 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SDPLRP_ERR_CUDA; }
@@ -366,6 +367,7 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
     if (k == "spmm_kernel") { h->spmm_kernel = (int)value; return SDPLRP_OK; }
     if (k == "spmm_phases") { h->spmm_phases = value < 0 ? 0 : (int)value; return SDPLRP_OK; }
     if (k == "spmm_pad") { h->spmm_pad = value > 0 ? 1 : 0; return SDPLRP_OK; }
+    if (k == "lanczos_bundle") { h->lanczos_bundle = value > 0 ? 1 : 0; return SDPLRP_OK; }
     if (k == "lanczos_dist") { h->lanczos_dist = value > 0 ? 1 : 0; return SDPLRP_OK; }
     if (k == "spmm_prefetch") { h->spmm_prefetch = value > 0 ? (int)value : 0; return SDPLRP_OK; }
     if (k == "spmm_unroll") { h->spmm_unroll = (int)value; return SDPLRP_OK; }

@@ -109,6 +109,7 @@ struct sdplrp_handle {
     int spmm_pad = 0;                                    // 1 = the pipelined gather kernels read a 128-byte-aligned copy of the factor (experimental)
     double *gpad = nullptr;                              // that copy, n x pad_stride(r)
     i64 gpad_len = 0;
+    int lanczos_bundle = 0;                              // 1 = bundle SpMV kernel for the short rows of the Lanczos operator (experimental, lanczos.cu)
     int lanczos_dist = 0;                                // 1 = row-partitioned q-step Lanczos on world > 1 (experimental, lanczos.cu: lz_run_dist)
     int spmm_prefetch = 0;                               // 1 = software-pipelined row loops in the gather pass (experimental, gradient.cu:
                                                          // k_rows_group_pf / k_rows_warp_pf; same summation order as the default kernels)
@@ -334,6 +335,7 @@ int32_t lr_project(sdplrp_handle *h, const LowRank &L, const double *X, double *
 int32_t lr_scratch(sdplrp_handle *h);
 
 // gradient (gradient.cu)
+bool grad_class0_range(sdplrp_handle *h, i64 *first, i64 *count);  // class 0 of the full pattern as a contiguous row range (or false)
 int32_t grad_form_y(sdplrp_handle *h);                          // copy2y_lambda_sub_pvio!
 int32_t grad_assemble_S(sdplrp_handle *h);                      // At_preprocess! from device y
 int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bool want_norm);  // Y = scale*X*S (+low rank)

@@ -1206,6 +1206,15 @@ int32_t add_lowrank(sdplrp_handle *h, const double *X, double *Y, double scale) 
 
 }  // namespace
 
+// the short rows (class 0) of the full pattern as one contiguous row range, if they are one (hub-first order, or short rows only)
+bool grad_class0_range(sdplrp_handle *h, i64 *first, i64 *count) {
+    i64 f = 0;
+    if (!class0_contiguous(h, h->full_cls, &f)) return false;
+    *first = f;
+    *count = h->full_cls.cnt[0];
+    return true;
+}
+
 int32_t grad_form_y(sdplrp_handle *h) {
     k_form_y<<<grid_for(h->m + 1, TPB, kRedBlocks), TPB, 0, h->stream>>>(h->m, h->sigma, h->lambda, h->lambda_ub, h->pvio_raw, h->y);
     KLAUNCH(h);

@@ -39,8 +39,10 @@ GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "tile": {"relabel": 1, 
                "prefetch_pad": {"relabel": 1, "spmm_prefetch": 1, "spmm_pad": 1},
                "bundle": {"relabel": 1, "spmm_prefetch": 2}, "bundle4_pad": {"spmm_prefetch": 2, "spmm_unroll": 4, "spmm_pad": 1},
                "batched": {"relabel": 1, "spmm_prefetch": 3}, "batched4": {"spmm_prefetch": 3, "spmm_unroll": 4},
-               "prefetch_phases": {"relabel": 1, "spmm_prefetch": 1, "spmm_phases": 5}}
-EXPERIMENTAL_CONFIGS = ["prefetch", "prefetch4", "prefetch_pad", "bundle", "bundle4_pad", "batched", "batched4", "prefetch_phases"]
+               "prefetch_phases": {"relabel": 1, "spmm_prefetch": 1, "spmm_phases": 5},
+               "lanczos_bundle": {"relabel": 1, "lanczos_bundle": 1}}
+EXPERIMENTAL_CONFIGS = ["prefetch", "prefetch4", "prefetch_pad", "bundle", "bundle4_pad", "batched", "batched4", "prefetch_phases",
+                        "lanczos_bundle"]
 GPU_CONFIG_PARAMS = ["default", "relabel", "tile", "phases"] + (
     EXPERIMENTAL_CONFIGS if os.environ.get("SDPLRP_TEST_EXPERIMENTAL", "0") not in ("", "0") else [])
 

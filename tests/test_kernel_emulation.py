@@ -36,6 +36,30 @@ def extract(build_dir):
     open(os.path.join(build_dir, "extracted_gradient.inc"), "w").write(kernels)
 
 
+def extract_lanczos(build_dir):
+    common = open(os.path.join(CSRC, "common.cuh")).read()
+    lz = open(os.path.join(CSRC, "lanczos.cu")).read()
+    helpers = _between(common, "__device__ __forceinline__ double warp_sum", "// host-visible kernels' launcher prototypes")
+    kernels = _between(lz, "template <int LANES, bool WITH_ALPHA>", "}  // namespace")   # every kernel of the q-step path
+    assert "<<<" not in kernels
+    for name in ("k_lz_spmv", "k_lz_spmv_bundle", "k_lz_class_ranges", "k_lz_update_part", "k_lz_beta_finish", "k_lz_update"):
+        assert name in kernels, name
+    open(os.path.join(build_dir, "extracted_common.inc"), "w").write(helpers)
+    open(os.path.join(build_dir, "extracted_lanczos.inc"), "w").write(kernels)
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_lanczos_kernels_under_host_emulation(tmp_path):
+    """bundle SpMV (option "lanczos_bundle") and the kernels of the row-partitioned Lanczos (option "lanczos_dist")."""
+    extract_lanczos(str(tmp_path))
+    exe = os.path.join(str(tmp_path), "lanczos_emu")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I", EMU, "-I", str(tmp_path), "-o", exe,
+                           os.path.join(EMU, "lanczos_emu_main.cpp")])
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
+    assert "the Lanczos kernels agree" in res.stdout
+
+
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
 def test_gather_kernel_variants_under_host_emulation(tmp_path):
     extract(str(tmp_path))

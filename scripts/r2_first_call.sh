@@ -23,7 +23,9 @@ try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
     k = d["roofline"]["kernels"]
     print(sys.argv[2], "it/s", round(d["value"], 2), " ".join(f"{a}={b['ms_per_iter']:.3f}" for a, b in k.items()),
-          "L=%.15g obj=%.15g alpha=%.15g" % (d["last_iterate"]["L"], d["last_iterate"]["obj"], d["last_iterate"]["alpha"]))
+          "L=%.15g obj=%.15g alpha=%.15g" % (d["last_iterate"]["L"], d["last_iterate"]["obj"], d["last_iterate"]["alpha"]),
+          ("lanczos_ms_per_step=%.4f" % d["lanczos"]["ms_per_step"]) if d.get("lanczos") else "",
+          "setup=%s" % d.get("setup"))
 except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY

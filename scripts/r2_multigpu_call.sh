@@ -10,10 +10,11 @@ run2() { python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-
 timeout 300 python scripts/check_multigpu_solve.py > $out/solve_1gpu.json 2> $out/solve_1gpu.err
 timeout 300 bash -c "$(declare -f run2); run2 29561 scripts/check_multigpu_solve.py" > $out/solve_2gpu.json 2> $out/solve_2gpu.err
 SDPLRP_LANCZOS_DIST=1 timeout 300 bash -c "$(declare -f run2); run2 29562 scripts/check_multigpu_solve.py" > $out/solve_2gpu_lzdist.json 2> $out/solve_2gpu_lzdist.err
+SDPLRP_LANCZOS_DIST=1 SDPLRP_LANCZOS_BUNDLE=1 timeout 300 bash -c "$(declare -f run2); run2 29564 scripts/check_multigpu_solve.py" > $out/solve_2gpu_lzdist_bundle.json 2> $out/solve_2gpu_lzdist_bundle.err
 SDPLRP_LANCZOS_DIST=1 timeout 300 bash -c "$(declare -f run2); run2 29563 scripts/check_multigpu_parity.py" > $out/parity_2gpu_lzdist.log 2>&1
 python - <<'PY'
 import json
-for f in ("solve_1gpu", "solve_2gpu", "solve_2gpu_lzdist"):
+for f in ("solve_1gpu", "solve_2gpu", "solve_2gpu_lzdist", "solve_2gpu_lzdist_bundle"):
     try:
         d = json.loads(open(f"gpurun_out/r2_multigpu/{f}.json").read().strip().splitlines()[-1])
         print(f, "dual", d["dual"], "dual_s %.3f" % d["dual_s"], "it400", d["it400"])

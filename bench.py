@@ -163,34 +163,66 @@ def pinned_uniform(shape, seed):
     return t, a
 
 
-def cpu_oracle_run(sp, n_full, edges_full, r, sample_n, steps, warmup, seed, threads=None):
-    """The reference's CPU path (oracle port, OpenMP on the host cores) on a bounded sample:
-    the same graph family at sample_n vertices; iterations/s are scaled by sample_n/n_full
-    (per-iteration cost is linear in n and nnz) to the full workload's unit."""
+def host_threads():
+    """Host threads the CPU arm may use: the affinity mask, not OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_oracle_run(sp, n, edges, r, steps, warmup, seed, single_thread_steps=1, budget_s=150.0):
+    """The reference's CPU path (oracle port of src/*.jl) on the SAME workload as the GPU arm: the same graph
+    (same generator, same seed, same n and edge count), the same R0, the same loop body.  Timed twice:
+    with all host threads (OpenMP; the thread count is set here, whatever the launcher exported) and with ONE
+    thread, which is the reference's own benchmarking protocol (exps/README.md:23, exps/test.jl:46 -- no threading
+    anywhere in src/).  `steps` is clipped so that the whole run stays within `budget_s` of CPU time."""
     from oracle import pyoracle
     lib = pyoracle.load()
-    if threads:
-        lib.orc_set_threads(int(threads))
-    cores = lib.orc_max_threads()
-    sample_edges = int(edges_full * (sample_n / float(n_full)))
-    asm, b, normC, E, _ = generate(sp, sample_n, sample_edges, seed)
-    data = SimpleData(sample_n, sample_n, b)
+    cores = host_threads()
+    lib.orc_set_threads(cores)
+    asm, b, normC, E, gen_s = generate(sp, n, edges, seed)
+    data = SimpleData(n, n, b)
     t0 = time.perf_counter()
     eng = pyoracle.OracleEngine(data, asm=asm)
     prep = time.perf_counter() - t0
-    Rt0 = 2.0 * np.random.default_rng(0).random((sample_n, r)) - 1.0
-    eng.init_vars(r, Rt0, np.zeros(sample_n), 2.0, 4)
+    del asm
+    Rt0 = 2.0 * np.random.default_rng(0).random((n, r)) - 1.0
+    eng.init_vars(r, Rt0, np.zeros(n), 2.0, 4)
     eng.fg()
-    sp.solver.run_inner_iterations(eng, warmup)
+    # first (warm-up) iteration doubles as the probe that sizes the timed run
     t0 = time.perf_counter()
-    sp.solver.run_inner_iterations(eng, steps)
+    sp.solver.run_inner_iterations(eng, 1)
+    probe = time.perf_counter() - t0
+    warm_done = 1
+    while warm_done < warmup and probe * (warm_done + 2) < 0.25 * budget_s:
+        sp.solver.run_inner_iterations(eng, 1)
+        warm_done += 1
+    k = int(max(1, min(steps, (0.6 * budget_s) // max(probe, 1e-9))))
+    t0 = time.perf_counter()
+    last = sp.solver.run_inner_iterations(eng, k)
     dt = time.perf_counter() - t0
-    its = steps / dt
-    return {"value": its * sample_n / float(n_full), "unit": UNIT, "cores": int(cores), "kind": "port",
-            "sample": (f"CPU restatement of SDPLRPlus.jl (Julia unavailable in image), OpenMP x{cores}: {steps} inner iterations "
-                       f"(+{warmup} warm-up) on the same graph family at n={sample_n} ({E} edges, 1/{n_full // sample_n} of the workload); "
-                       f"{its:.3f} it/s there, scaled by n_sample/n"),
-            "sample_it_per_s": its, "sample_ms_per_iter": 1e3 * dt / steps, "cpu_preprocess_s": prep}
+    its = k / dt
+    single = None
+    if single_thread_steps > 0 and cores > 1:
+        lib.orc_set_threads(1)
+        k1 = int(single_thread_steps)
+        t0 = time.perf_counter()
+        sp.solver.run_inner_iterations(eng, k1)
+        dt1 = time.perf_counter() - t0
+        single = {"value": k1 / dt1, "unit": UNIT, "cores": 1, "steps": k1, "ms_per_iter": 1e3 * dt1 / k1,
+                  "protocol": "one thread, as in exps/README.md:23 / exps/test.jl:46"}
+        lib.orc_set_threads(cores)
+    return {"value": its, "unit": UNIT, "cores": int(cores), "kind": "port",
+            "sample": (f"CPU restatement of SDPLRPlus.jl (Julia unavailable in image), OpenMP x{cores}: {k} inner iterations "
+                       f"(+{warm_done} warm-up) of the full workload (n={n}, {E} edges, rank {r}); nothing is scaled"),
+            "steps": k, "warmup": warm_done, "ms_per_iter": 1e3 * dt / k, "single_thread": single, "cpu_preprocess_s": prep,
+            "graph_generation_s": gen_s, "edges": E,
+            "last_iterate": {"L": last[0], "obj": last[1], "gnorm2": last[2], "pnorm2": last[3], "alpha": last[4]}}
+
+
+def workload_string(n, E, r, h, seed):
+    return f"C5: MaxCut, Chung-Lu power-law graph n={n}, {E} edges, rank {r}, numlbfgsvecs {h}, seed {seed}"
 
 
 def main():
@@ -203,8 +235,9 @@ def main():
     ap.add_argument("--edges", type=int, default=80_000_000)
     ap.add_argument("--rank", type=int, default=10)
     ap.add_argument("--seed", type=int, default=42)
-    ap.add_argument("--cpu-sample-n", type=int, default=1_000_000)
-    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--cpu-steps", type=int, default=5, help="CPU arm: timed inner iterations with all host threads (clipped to the budget)")
+    ap.add_argument("--cpu-single-steps", type=int, default=1, help="CPU arm: timed inner iterations with one thread (reference protocol)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="CPU arm: seconds of CPU iterations allowed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--python-loop", action="store_true", help="drive the iterations from Python (one ctypes call per seam function) "
                     "instead of sdplrp_iterate")
@@ -225,15 +258,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sample_n = min(args.cpu_sample_n, args.n)
-        # keep the whole run within a few minutes whatever K is
-        steps = max(1, min(args.steps, 80))
-        res = cpu_oracle_run(sp, args.n, args.edges, args.rank, sample_n, steps, min(args.warmup, 2), args.seed)
-        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "strong",
+        res = cpu_oracle_run(sp, args.n, args.edges, args.rank, min(args.steps, args.cpu_steps), min(args.warmup, 2), args.seed,
+                             single_thread_steps=args.cpu_single_steps, budget_s=args.cpu_budget_s)
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": res["steps"],
+                "warmup": res["warmup"], "requested_steps": args.steps, "requested_warmup": args.warmup,
+                "ms_per_step": res["ms_per_iter"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"C5: MaxCut, Chung-Lu power-law graph n={args.n}, ~{args.edges} edges, rank {args.rank}, seed {args.seed}",
-                           "timed_steps_on_sample": steps},
+                "config": {"workload": workload_string(args.n, res["edges"], args.rank, 4, args.seed),
+                           "l2": "inputs (R 0.8 GB, pattern 2 GB per pass) far exceed the 126 MB L2",
+                           "parallelism": f"host cores only: OpenMP x{res['cores']} (headline) and 1 thread (reference protocol)"},
                 "cpu_baseline": res, "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return 0
@@ -355,7 +388,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_oracle_run(sp, n, args.edges, r, min(args.cpu_sample_n, n), args.cpu_steps, 1, args.seed)
+            cpu = cpu_oracle_run(sp, n, args.edges, r, args.cpu_steps, 1, args.seed, single_thread_steps=0, budget_s=30.0)
         except Exception as e:  # the baseline is a reported extra, never a reason to lose the GPU number
             cpu = {"error": repr(e)}
 
@@ -364,7 +397,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C5: MaxCut, Chung-Lu power-law graph n={n}, {E} edges, rank {r}, numlbfgsvecs {h}, seed {args.seed}",
+            "config": {"workload": workload_string(n, E, r, h, args.seed),
                        "nnzT": nnzT, "nnzF": nnzF, "E_c": Ec, "l2": "inputs (R 0.8 GB, pattern 2 GB per pass) far exceed the 126 MB L2",
                        "parallelism": f"rows 1-D partitioned over {world} GPU(s), nnz-balanced" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

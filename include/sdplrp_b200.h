@@ -113,6 +113,11 @@ void *sdplrp_stream(sdplrp_handle *h);
  *                 Only with world > 1 and without re-orthogonalisation.  Experimental, as "spmm_prefetch"
  *   "spmm_unroll" nonzeros per block of the short-row kernels: 8 (default) or 4
  *   "spmm_g0"     1 = lane groups of exactly r/2 lanes per short row (default: 6 rows per warp at r = 10), 0 = next power of two
+ *   "gather_mode" gather pass CD = C*D (gather.cu): 0 = row-binned register kernels, 1 = asynchronous tile pipeline with one
+ *                 cp.async.bulk per gathered row, 2 = the same pipeline with 16-byte cp.async row pieces (even ranks <= 64)
+ *   "gather_tile", "gather_stages", "gather_warps"  geometry of that pipeline (nonzeros per tile, stages of the
+ *                 gathered-rows ring, warps per CTA); 0 = automatic
+ *   "gather_hints" 1 = L2 evict_last / evict_first policies on the bulk row gathers of "gather_mode" 1
  *   "fused_tail"  1 = sdplrp_step_g uses the fused row pass (default), 0 = step and g separately
  *   "lbfgs_kernel" 1 = two-loop recursion on coefficients over directly computed dot products (default,
  *                 numlbfgsvecs <= 8), 0 = literal vector two-loop */

@@ -372,6 +372,11 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
     if (k == "spmm_prefetch") { h->spmm_prefetch = value > 0 ? (int)value : 0; return SDPLRP_OK; }
     if (k == "spmm_unroll") { h->spmm_unroll = (int)value; return SDPLRP_OK; }
     if (k == "spmm_g0") { h->spmm_g0 = (int)value; return SDPLRP_OK; }
+    if (k == "gather_mode") { h->gather_mode = value < 0 ? 0 : (int)value; return SDPLRP_OK; }
+    if (k == "gather_tile") { h->gather_tile = (int)value; return SDPLRP_OK; }
+    if (k == "gather_stages") { h->gather_stages = (int)value; return SDPLRP_OK; }
+    if (k == "gather_warps") { h->gather_warps = (int)value; return SDPLRP_OK; }
+    if (k == "gather_hints") { h->gather_hints = value > 0 ? 1 : 0; return SDPLRP_OK; }
     if (k == "fused_tail") { h->fused_tail = value != 0; return SDPLRP_OK; }
     if (k == "lbfgs_kernel") { h->lbfgs_kernel = (int)value; h->gram_pairs_valid = h->gram_g_valid = false; return SDPLRP_OK; }
     return fail(h, SDPLRP_ERR_ARG, "set_option: unknown key " + k);

@@ -38,6 +38,18 @@ struct TileLayout {
     int *chunk_start = nullptr, *chunk_end = nullptr, *chunk_row = nullptr;  // n_chunks
 };
 
+// tile plan of the asynchronous gather pass (gather.cu): the CSR of a row range cut into tiles of whole rows with at most T
+// nonzeros; rows longer than T become chunk tiles combined per row afterwards
+struct GatherPlan {
+    int4 *tiles = nullptr;       // {row0, nrows (< 0: chunk, slot = ~nrows), nz0, nnz}
+    long long ntiles = 0, n_long = 0, n_chunks = 0;
+    int *long_rows = nullptr;    // n_long
+    int *long_cptr = nullptr;    // n_long+1 chunk slots of each long row
+    const int *ptr_key = nullptr;
+    long long row_lo = 0, row_hi = 0;
+    int T = 0;
+};
+
 struct LowRank {
     i64 gid;     // 0-based global slot
     i64 s;
@@ -113,6 +125,12 @@ struct sdplrp_handle {
     int lanczos_dist = 0;                                // 1 = row-partitioned q-step Lanczos on world > 1 (experimental, lanczos.cu: lz_run_dist)
     int spmm_prefetch = 0;                               // 1 = software-pipelined row loops in the gather pass (experimental, gradient.cu:
                                                          // k_rows_group_pf / k_rows_warp_pf; same summation order as the default kernels)
+    // asynchronous tile pipeline of the gather pass (gather.cu)
+    int gather_mode = 0;                                 // 0 = register kernels of gradient.cu, 1 = cp.async.bulk row gathers, 2 = 16-byte cp.async row gathers
+    int gather_tile = 0, gather_stages = 0, gather_warps = 0;  // 0 = automatic (gather_geometry)
+    int gather_hints = 0;                                // 1 = L2 evict_last / evict_first policies on the row gathers (MODE 1)
+    bool gather_attr_set[2][5] = {{false}};
+    GatherPlan full_plan;                                // plan of the full pattern over the owned rows
     int *row_mid = nullptr;                              // n: first tail-column position of every row (two-phase pass)
     i64 row_mid_cols = -1;                               // hub prefix row_mid was built for
     // per-entry lists in reference order (E_c)
@@ -347,6 +365,14 @@ int32_t grad_step_fused(sdplrp_handle *h, double alpha);        // step + y + gr
 int32_t vec_tail_rest(sdplrp_handle *h, double alpha, const double *raw_in, double *raw_out, double *pn2_out);
 int32_t grad_spmv(sdplrp_handle *h, const double *x, double *y, i64 ncols);                     // y = S*x (+low rank), n x ncols col-major
 int32_t grad_triuS(sdplrp_handle *h, double *out_dev);          // materialise triu_sparse_S.nzval
+
+// asynchronous tile pipeline of the gather pass (gather.cu)
+bool gather_supported(const sdplrp_handle *h);
+int gather_tile_size(const sdplrp_handle *h);
+void gather_plan_free(GatherPlan &p);
+int32_t gather_plan_build(sdplrp_handle *h, GatherPlan &p, const int *ptr_dev, i64 row_lo, i64 row_hi, int T);
+int32_t gather_spmm(sdplrp_handle *h, const GatherPlan &plan, const int *ptr, const int *idx, const double *val, const double *Xg,
+                    const double *X, const double *Z, double *Y, int epi, double scale, double *sums4);
 
 // async-copy tile-stream SpMM (spmm.cu)
 bool tile_supported(const sdplrp_handle *h);

@@ -114,8 +114,10 @@ __global__ void __launch_bounds__(512) k_tile_gather(TileArgs a) {
         const int p0 = t.x & ~3, pcnt = t.y < 0 ? 0 : ((t.x + nrows + 1 - p0) + 3) & ~3;
         fence_proxy_async();
         mbar_expect_tx(bar_iv + s, (uint32_t)cnt * 12u + (uint32_t)pcnt * 4u);
-        bulk_g2s_hint(idx_s + s * TC, a.idx + a0, (uint32_t)cnt * 4u, bar_iv + s, p_str);
-        bulk_g2s_hint(val_s + s * TC, a.val + a0, (uint32_t)cnt * 8u, bar_iv + s, p_str);
+        if (cnt > 0) {
+            bulk_g2s_hint(idx_s + s * TC, a.idx + a0, (uint32_t)cnt * 4u, bar_iv + s, p_str);
+            bulk_g2s_hint(val_s + s * TC, a.val + a0, (uint32_t)cnt * 8u, bar_iv + s, p_str);
+        }
         if (pcnt > 0) bulk_g2s(ptr_s + s * TC, a.ptr + p0, (uint32_t)pcnt * 4u, bar_iv + s);
     };
     auto issue_gathers = [&](i64 k) {   // whole warp

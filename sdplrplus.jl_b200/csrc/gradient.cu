@@ -1272,7 +1272,10 @@ int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bo
 // the sparse part alone (DIMACS error 6 of the reference leaves the low-rank terms out, src/coreop.jl:448-451)
 int32_t grad_spmm_sparse(sdplrp_handle *h, const double *X, double *Y, double scale) {
     const int r = h->r;
-    if (h->nA > 0 && tile_supported(h)) {
+    if (h->nA > 0 && gather_supported(h) && h->nnzF > 0) {
+        SDP_CHECK(gather_plan_build(h, h->full_plan, h->full_ptr, h->row_lo, h->row_hi, gather_tile_size(h)));
+        SDP_CHECK(gather_spmm(h, h->full_plan, h->full_ptr, h->full_idx, h->S, X, nullptr, nullptr, Y, 0, scale, nullptr));
+    } else if (h->nA > 0 && tile_supported(h)) {
         SDP_CHECK(tile_spmm(h, h->full_tile, h->full_ptr, h->full_idx, h->S, nullptr, X, Y, 0, scale, 0.0, nullptr, nullptr, nullptr));
     } else if (h->nA > 0) {
         RowArgs a = {};
@@ -1305,6 +1308,11 @@ static int pad_stride(int r) {
 
 // Y = C*X over the owned rows with the fused sums  out0 = <X, Y>, out1 = <X, Z>  (Z may be null)
 int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double *Z, double *sums6) {
+    if (gather_supported(h) && h->nnzF > 0) {   // asynchronous tile pipeline (gather.cu)
+        SDP_CHECK(gather_plan_build(h, h->full_plan, h->full_ptr, h->row_lo, h->row_hi, gather_tile_size(h)));
+        CUDA_TRY(h, cudaMemsetAsync(sums6 + 4, 0, 2 * sizeof(double), h->stream));
+        return gather_spmm(h, h->full_plan, h->full_ptr, h->full_idx, h->Cfull, X, X, Z, Y, 2, 1.0, sums6);
+    }
     if (tile_supported(h)) {
         CUDA_TRY(h, cudaMemsetAsync(sums6, 0, 6 * sizeof(double), h->stream));
         return tile_spmm(h, h->full_tile, h->full_ptr, h->full_idx, h->Cfull, nullptr, X, Y, 2, 1.0, 0.0, X, Z, sums6);

@@ -552,6 +552,7 @@ int32_t tile_build(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, TileLayout
 }  // namespace
 
 void pre_free(sdplrp_handle *h) {
+    gather_plan_free(h->full_plan);
     tile_free(h->full_tile); tile_free(h->dyn_tile); tile_free(h->full_long); tile_free(h->dyn_long);
     dev_free(&h->tile_scratch); h->tile_scratch_len = 0;
     dev_free(&h->row_mid); h->row_mid_cols = -1;
@@ -667,8 +668,8 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
     h->nnzT = nnzT; h->nnzF = nnzF;
 
     SDP_CHECK(dev_alloc(h, &h->triu_colptr, n + 1)); SDP_CHECK(dev_alloc(h, &h->triu_rowval, nnzT));
-    SDP_CHECK(dev_alloc(h, &h->ref_full_ptr, n + 1)); SDP_CHECK(dev_alloc(h, &h->ref_full_idx, nnzF));
-    SDP_CHECK(dev_alloc(h, &h->mapped, nnzF)); SDP_CHECK(dev_alloc(h, &h->S, nnzF));
+    SDP_CHECK(dev_alloc(h, &h->ref_full_ptr, n + 1 + 8)); SDP_CHECK(dev_alloc(h, &h->ref_full_idx, nnzF + 8));  // slack: gather.cu copies 16-byte aligned spans
+    SDP_CHECK(dev_alloc(h, &h->mapped, nnzF)); SDP_CHECK(dev_alloc(h, &h->S, nnzF + 8));
     SDP_CHECK(dev_alloc(h, &h->triuS_static, nnzT));
     k_colptr<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, nnzT, UT, h->triu_colptr); KLAUNCH(h);
     k_colptr<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, nnzF, UF, h->ref_full_ptr); KLAUNCH(h);
@@ -738,7 +739,7 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
             }));
             k_scatter_inverse<<<GS, TPB, 0, st>>>(nnzF, h->i2r, h->r2i); KLAUNCH(h);
             h->full_ptr = nullptr; h->full_idx = nullptr;
-            SDP_CHECK(dev_alloc(h, &h->full_ptr, n + 1)); SDP_CHECK(dev_alloc(h, &h->full_idx, nnzF));
+            SDP_CHECK(dev_alloc(h, &h->full_ptr, n + 1 + 8)); SDP_CHECK(dev_alloc(h, &h->full_idx, nnzF + 8));
             k_colptr<<<grid_for(n + 1, TPB, GS), TPB, 0, st>>>(n, nnzF, keyF, h->full_ptr); KLAUNCH(h);
             k_low32<<<GS, TPB, 0, st>>>(nnzF, keyF, h->full_idx); KLAUNCH(h);
             h->relabeled = true;
@@ -864,7 +865,7 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
     }
 
     // ---- objective values on the full pattern + the dynamic pattern as CSR -------
-    SDP_CHECK(dev_alloc(h, &h->Cfull, nnzF));
+    SDP_CHECK(dev_alloc(h, &h->Cfull, nnzF + 8));
     SDP_CHECK(dev_alloc(h, &h->dynS, h->n_dyn));
     SDP_CHECK(dev_alloc(h, &h->dynrow_ptr, n + 1));
     SDP_CHECK(dev_alloc(h, &h->dyn_diag, n));

@@ -40,10 +40,15 @@ GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "tile": {"relabel": 1, 
                "bundle": {"relabel": 1, "spmm_prefetch": 2}, "bundle4_pad": {"spmm_prefetch": 2, "spmm_unroll": 4, "spmm_pad": 1},
                "batched": {"relabel": 1, "spmm_prefetch": 3}, "batched4": {"spmm_prefetch": 3, "spmm_unroll": 4},
                "prefetch_phases": {"relabel": 1, "spmm_prefetch": 1, "spmm_phases": 5},
-               "lanczos_bundle": {"relabel": 1, "lanczos_bundle": 1}}
+               "lanczos_bundle": {"relabel": 1, "lanczos_bundle": 1},
+               # asynchronous tile pipeline of the gather pass (gather.cu): bulk-copy and cp.async row gathers; small tiles so
+               # that chunked long rows, split rows and multi-pass tiles all occur on the small test graphs
+               "gather_bulk": {"relabel": 1, "gather_mode": 1, "gather_tile": 16},
+               "gather_async": {"gather_mode": 2},
+               "gather_async_small": {"relabel": 1, "gather_mode": 2, "gather_tile": 24, "gather_stages": 3, "gather_hints": 1}}
 EXPERIMENTAL_CONFIGS = ["prefetch", "prefetch4", "prefetch_pad", "bundle", "bundle4_pad", "batched", "batched4", "prefetch_phases",
                         "lanczos_bundle"]
-GPU_CONFIG_PARAMS = ["default", "relabel", "tile", "phases"] + (
+GPU_CONFIG_PARAMS = ["default", "relabel", "tile", "phases", "gather_bulk", "gather_async", "gather_async_small"] + (
     EXPERIMENTAL_CONFIGS if os.environ.get("SDPLRP_TEST_EXPERIMENTAL", "0") not in ("", "0") else [])
 
 

@@ -242,8 +242,10 @@ def main():
     ap.add_argument("--python-loop", action="store_true", help="drive the iterations from Python (one ctypes call per seam function) "
                     "instead of sdplrp_iterate")
     ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE",
-                    help="sdplrp_set_option before preprocessing (experiments: spmm_phases=1, spmm_kernel=1, ...)")
-    ap.add_argument("--lanczos", type=int, default=0, help="also time this many Lanczos steps (reported separately)")
+                    help="sdplrp_set_option before preprocessing (experiments: spmm_phases=1, gather_mode=2, ...)")
+    ap.add_argument("--lanczos", type=int, default=50, help="also time this many Lanczos steps (reported separately; 0 = skip)")
+    ap.add_argument("--no-solve", action="store_true", help="skip the time-to-tolerance leg (full solve with the native driver)")
+    ap.add_argument("--solve-maxtime", type=float, default=240.0, help="time limit of the time-to-tolerance solve in seconds")
     ap.add_argument("--device-triplets", action="store_true", help="one GPU: the generator's triplets stay on the device and go to "
                     "sdplrp_preprocess_device (no 4.4 GB D2H + H2D); affects the setup times only")
     args = ap.parse_args()
@@ -359,6 +361,33 @@ def main():
         ms = st["lanczos"][0] / args.lanczos
         lanczos = {"ms_per_step": ms, "achieved_gbs": (4.0 * (n + 1) + 12.0 * nnzF + 56.0 * n) / (ms * 1e-3) / 1e9}
 
+    # ---- time to tolerance (the other half of BASELINE.json's metric): the whole solve with the native driver
+    #      (sdplrp_solve = _sdplr of src/sdplr.jl:140-449 inside the library), reference defaults (src/options.jl:2-15:
+    #      ptol = objtol = 1e-2 relative, sigma_0 = 2, numlbfgsvecs = 4, fprec = 1e8, rank 10), prior_trace_bound = n
+    #      (exps protocol), R0 ~ U(-1,1) and the Lanczos start vectors from the device generator (seed 0: the same
+    #      start point for every GPU count)
+    time_to_tol = None
+    if not args.no_solve:
+        cfg = sp._lib.default_config()
+        cfg.prior_trace_bound = float(n)
+        cfg.printlevel = 0
+        cfg.maxtime = float(args.solve_maxtime)
+        cfg.seed = 0
+        spdist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res, _best = handle.solve(cfg, r, None, None, normb=math.sqrt(n), normC=normC)
+        torch.cuda.synchronize()
+        wall = spdist.max_over_ranks(time.perf_counter() - t0)
+        time_to_tol = {"totaltime_s": spdist.max_over_ranks(res.totaltime), "wall_s": wall, "primaltime_s": res.primaltime,
+                       "dual_time_s": res.dual_time, "iter": int(res.iter), "majoriter": int(res.majoriter),
+                       "lanczos_steps": int(res.lanczos_steps), "obj": res.obj, "max_dual_value": res.max_dual_value,
+                       "min_duality_gap": res.min_duality_gap, "primal_vio": res.primal_vio, "grad_norm": res.grad_norm,
+                       "status": int(res.status), "rank": int(res.r),
+                       "al_iters_per_s_over_the_solve": res.iter / max(res.primaltime, 1e-12),
+                       "plus_one_time_preprocess_s": preprocess_s,
+                       "what": "sdplrp_solve, reference default tolerances (ptol = objtol = 1e-2 relative), prior_trace_bound = n, "
+                               "device-generated R0 (seed 0); status 0 = tolerances met"}
+
     # ---- roofline per kernel class
     peak, peak_src = measured_peak()
     ab = algorithmic_bytes(n, n, r, nnzT, nnzF, Ec, h, hi - lo)
@@ -372,18 +401,37 @@ def main():
                          "achieved_gbs": nbytes / (per * 1e-3) / 1e9, "frac": nbytes / (per * 1e-3) / 1e9 / peak}
     comm_ms = sections.get("comm", (0.0, 0))[0]
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_iter"]) if kernels else None
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(dom)
-    except Exception:
-        pass
+    # DRAM traffic of the dominant kernel: a number from an ncu capture of THIS configuration on one GPU
+    # (profiles/ncu_traffic.json states which capture); never reported for N > 1 or for non-default options
+    traffic, traffic_src = None, None
+    if world == 1 and not args.option and n == 10_000_000 and r == 10:
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj.get(dom), tj.get("_source", "profiles/ncu_traffic.json (static, from an ncu --set full capture)")
+        except Exception:
+            pass
     roofline = None
     if dom:
+        rows_local = hi - lo
+        frac_rows = rows_local / float(n)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src, "kernels": kernels,
-                    "iteration_reference_equivalent_gbs": (63 * 8.0 * n * r + ab["ls_pass"] + ab["spmm"] + 32.0 * n + 12.0 * Ec + 16.0 * nnzT + 12.0 * nnzF)
-                    / (dev_ms / args.steps * 1e-3) / 1e9}
+                    "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "kernels": kernels}
+        if "spmm" in kernels:
+            # the same kernel against the other two bounds of SURVEY 8d / DESIGN section 4, so that progress is visible:
+            # (i) gather-inclusive bytes (every nonzero gathers its 8r-byte row once), (ii) the measured random-gather ceiling
+            # of this GPU (scripts/microbench/l2_probe.cu: 32.7 rows/ns for 80-byte rows from HBM, profiles/r2_l2_probe.txt)
+            ms = kernels["spmm"]["ms_per_iter"]
+            incl = 8.0 * rows_local * r + frac_rows * (4.0 * (n + 1) + (12.0 + 8.0 * r) * nnzF)
+            roofline["spmm_gather_inclusive"] = {"bytes": incl, "achieved_gbs": incl / (ms * 1e-3) / 1e9, "frac": incl / (ms * 1e-3) / 1e9 / peak}
+            roofline["spmm_gathered_rows_per_ns"] = frac_rows * nnzF / (ms * 1e6)
+        # the whole iteration: bytes the REFERENCE's unfused sequence would move divided by this repo's time.  A
+        # speed-up figure, NOT a bandwidth: fusion makes it exceed the HBM peak.
+        roofline["iteration_speedup_vs_unfused_reference_bytes"] = {
+            "reference_unfused_bytes": (63 * 8.0 * n * r + ab["ls_pass"] + ab["spmm"] + 32.0 * n + 12.0 * Ec + 16.0 * nnzT + 12.0 * nnzF),
+            "equivalent_gbs": (63 * 8.0 * n * r + ab["ls_pass"] + ab["spmm"] + 32.0 * n + 12.0 * Ec + 16.0 * nnzT + 12.0 * nnzF)
+            / (dev_ms / args.steps * 1e-3) / 1e9}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -404,7 +452,7 @@ def main():
             "host_wall_ms_per_step": 1e3 * t_wall / args.steps, "comm_ms_per_step": comm_ms / args.steps,
             "setup": {"graph_generation_s": gen_s, "preprocess_s": preprocess_s},
             "last_iterate": {"L": last[0], "obj": last[1], "gnorm2": last[2], "pnorm2": last[3], "alpha": last[4]},
-            "lanczos": lanczos, "options": args.option, "loop": "sdplrp_iterate (native)" if native else "python (one ABI call per seam function)",
+            "lanczos": lanczos, "time_to_tol": time_to_tol, "options": args.option, "loop": "sdplrp_iterate (native)" if native else "python (one ABI call per seam function)",
         }
         print(json.dumps(line), flush=True)
     handle.close()

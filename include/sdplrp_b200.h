@@ -57,6 +57,8 @@ enum {
     SDPLRP_MAT_D = 2,   /* dirt   */
     SDPLRP_MAT_W0 = 3,  /* scratch (operator tests) */
     SDPLRP_MAT_W1 = 4,
+    SDPLRP_MAT_CR = 5,  /* introspection (download only): C*R as kept by the recurrence CR += alpha*CD, and CD = C*dirt */
+    SDPLRP_MAT_CD = 6,
     SDPLRP_MAT_S0 = 16, /* L-BFGS s_j = S0 + j, j in [0,h) (0-based slot) */
     SDPLRP_MAT_Y0 = 48  /* L-BFGS y_j = Y0 + j */
 };
@@ -92,25 +94,11 @@ void *sdplrp_stream(sdplrp_handle *h);
  *   "relabel"     -1 auto (default) / 0 off / 1 on: internal hub-first vertex order, set BEFORE
  *                 sdplrp_preprocess.  Invisible at the ABI (every upload/download converts).
  *   "hot_rows"    leading rows of the gathered factor pinned in L2 (evict_last); -1 = sized from L2
- *   "spmm_kernel" 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel (experimental)
  *   "spmm_phases" 0 = one sweep per gather pass (default); 1 = two sweeps, hub columns (an L2-sized prefix of the
  *                 hub-first order) then tail columns; k > 1 = k hub columns.  One GPU, relabelled patterns only (experimental)
- *   "spmm_prefetch" 0 = default row loops; 1 = software-pipelined row loops of the gather pass (the next rows' index, ptr pair,
- *                 first idx/val block and epilogue operands are loaded while the current gathers are in flight; same
- *                 summation order, so results are those of the default kernels); 2 = in addition the short rows are taken in
- *                 bundles of 32/G consecutive rows whose CSR span is staged in shared memory with coalesced loads (needs the
- *                 short rows to be one contiguous range, else as 1); 3 = the default short-row loop with all gathers of a block
- *                 issued together (straight-line full blocks, unconditional gathers in the partial block, register
- *                 budget given to ptxas by the launch bounds).  Experimental: written at the end of round 1
- *                 without GPU time left, measured first thing in round 2 (profiles/r1_gather_size_sweep.md)
- *   "spmm_pad"    with "spmm_prefetch" on one GPU: 1 = the gathers read a copy of the factor whose rows start on 128-byte
- *                 lines (an 80-byte row at an 80-byte stride crosses a line 5 times out of 8).  Confirmation experiment only:
- *                 no gain expected (profiles/r1_gather_size_sweep.md, addendum)
- *   "lanczos_bundle" 1 = the short rows of the Lanczos operator are taken in bundles of 8 consecutive rows (pattern loaded
- *                 coalesced, all gathers of a bundle in flight together); needs them to be one contiguous range.  Experimental
  *   "lanczos_dist" 0 = the q-step Lanczos operator is replicated on every rank (default); 1 = rows of S and of the Lanczos
  *                 vectors are divided among the ranks (one all-gather of n doubles + two scalar all-reduces per step).
- *                 Only with world > 1 and without re-orthogonalisation.  Experimental, as "spmm_prefetch"
+ *                 Only with world > 1 and without re-orthogonalisation
  *   "spmm_unroll" nonzeros per block of the short-row kernels: 8 (default) or 4
  *   "spmm_g0"     1 = lane groups of exactly r/2 lanes per short row (default: 6 rows per warp at r = 10), 0 = next power of two
  *   "gather_mode" gather pass CD = C*D (gather.cu): 0 = row-binned register kernels, 1 = asynchronous tile pipeline with one

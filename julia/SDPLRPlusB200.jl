@@ -1,32 +1,44 @@
-# SDPLRPlusB200.jl -- thin `ccall` shim that plugs libsdplrp_b200.so into SDPLRPlus.jl.
+# SDPLRPlusB200.jl -- thin `ccall` shim that plugs libsdplrp_b200.so into an UNMODIFIED SDPLRPlus.jl.
 #
-# NOT EXECUTED IN THIS REPOSITORY'S CI: neither the build container nor the GPU box has a Julia
-# toolchain (DESIGN.md section 1).  The same control flow, through the same C entry points, is
-# exercised by sdplrplus.jl_b200/solver.py (ctypes) in tests/ and bench.py.
+# NOT EXECUTED IN THIS REPOSITORY'S CI: neither the build container nor the GPU box has a Julia toolchain (DESIGN.md
+# section 1), so this file has never been parsed by Julia.  It is written against the reference sources as they are
+# (signatures cited per method); the same control flow, through the same C entry points, is exercised by
+# sdplrplus.jl_b200/solver.py (ctypes) in tests/ and bench.py.  tests/test_julia_shim.py keeps the ccall signatures in
+# step with include/sdplrp_b200.h.
 #
-# What it does: `_sdplr` (src/sdplr.jl:140-449) is duck-typed over (data, var, aux) and reaches the
-# hot path through the functions listed in SURVEY.md 8b -- the same seam src/lowrankopt.jl:47-135
-# overloads for LowRankOpt models.  This file adds a device-backed `aux` (B200Auxiliary), a device
-# matrix wrapper usable as the `TR` type parameter of SolverVars / LBFGSVector (src/structs.jl:194,
-# src/lbfgs.jl:4), and methods of the seam functions for them.  The user-facing API is untouched:
+# How it works.  `_sdplr` (src/sdplr.jl:140-449) is duck-typed over (data, var, aux): `var.Rt` / `var.Gt` have the type
+# parameter TR of `SolverVars{Ti,Tv,TR<:AbstractArray{Tv}}` (src/structs.jl:194-196) and `aux` is untyped.  This module
+# supplies
+#   * `DevMat <: AbstractMatrix{Float64}`: a name for an r x n matrix that lives on the GPU (R, G, the direction, an L-BFGS
+#     slot), used as TR.  The generic calls `_sdplr` makes on such arrays -- `similar`, `zero`, `deepcopy`, `dot`, `norm`,
+#     `BLAS.scal!`, `copyto!`, `axpy!`, `.= 0` -- are methods that either do nothing (the fused entry point already did the
+#     work) or return the scalar the previous entry point produced;
+#   * `B200Auxiliary`: the opaque handle as `aux`;
+#   * methods of the seam functions (SURVEY.md 8b) `fg!`, `g!`, `lbfgs_dir!`, `lbfgs_update!`, `linesearch!`,
+#     `linesearch_armijo!`, `dual_obj`, `rank_update!`, `DIMACS_errors`, `SDP_S_eigval` for (`SolverVars{..,DevMat}`,
+#     `B200Auxiliary`), each a ccall or two.
+# The two places where `_sdplr` works on host vectors inline are served by mirrors, so NO patch of the reference is needed:
+#   * `norm(var.primal_vio, 2)` (src/sdplr.jl:230-234): `g!` / `fg!` leave a host vector whose 2-norm is the device value;
+#   * the dual update loop on `var.λ` / `var.primal_vio_raw` (src/sdplr.jl:358-362): `dual_obj` (which always precedes it,
+#     src/sdplr.jl:311-321) downloads both vectors, and the next `fg!` uploads `var.λ` and `var.σ[]`.
 #
 #     using SDPLRPlus, SDPLRPlusB200
 #     res = SDPLRPlusB200.sdplr(C, As, b, r; ptol = 1e-2, objtol = 1e-2, prior_trace_bound = n)
 #
-# (identical signature and result Dict to SDPLRPlus.sdplr, src/sdplr.jl:91-138, 426-448).
+# (same signature, keyword handling and result Dict as SDPLRPlus.sdplr, src/sdplr.jl:91-138, 426-448).
 module SDPLRPlusB200
 
 using LinearAlgebra, SparseArrays
 import SDPLRPlus
-import SDPLRPlus: SDPData, SolverVars, SolverStats, BurerMonteiroConfig, SymLowRankMatrix,
-    f!, g!, fg!, 𝒜!, 𝒜t!, 𝒜t_preprocess!, linesearch!, linesearch_armijo!, lbfgs_dir!, lbfgs_update!,
-    lbfgs_clear!, lbfgs_init, dual_obj, approx_mineigval_lanczos, side_dimension, b_vector, C_matrix,
-    LBFGSHistory, _sdplr
+import SDPLRPlus: SDPData, SolverVars, SolverStats, BurerMonteiroConfig, SymLowRankMatrix, LBFGSHistory,
+    fg!, g!, linesearch!, linesearch_armijo!, lbfgs_dir!, lbfgs_update!, dual_obj, rank_update!, side_dimension,
+    barvinok_pataki, set_rank!, _sdplr
 
 const LIB = get(ENV, "SDPLRP_B200_LIB", joinpath(@__DIR__, "..", "sdplrplus.jl_b200", "libsdplrp_b200.so"))
 
 # ids of include/sdplrp_b200.h
 const MAT_R, MAT_G, MAT_D = Cint(0), Cint(1), Cint(2)
+const MAT_HIST = Cint(-1)      # an L-BFGS slot: owned by the library, never addressed from Julia
 const VEC_LAMBDA, VEC_LAMBDA_UB, VEC_B, VEC_PVIO_RAW, VEC_Y, VEC_PVIO_LB, VEC_A_RD, VEC_A_DD = Cint.(0:7)
 
 struct B200Error <: Exception
@@ -34,13 +46,18 @@ struct B200Error <: Exception
     msg::String
 end
 
+# One handle per GPU.  The scalars the fused entry points return are kept here until `_sdplr` asks for them through
+# `dot` / `norm` (src/sdplr.jl:201, 224-234).
 mutable struct Handle
     ptr::Ptr{Cvoid}
+    gnorm2::Float64      # ||G||_F^2 of the last g! / fg!
+    descent::Float64     # dot(dirt, Gt) of the last lbfgs_dir!
+    stepped::Bool        # linesearch! already applied Rt += α dirt (the caller's axpy! is then a no-op)
     function Handle(device::Integer=0)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:sdplrp_create, LIB), Int32, (Int32, Int32, Int32, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), device, 0, 1, C_NULL, out)
         rc == 0 || throw(B200Error(rc, unsafe_string(ccall((:sdplrp_error_string, LIB), Cstring, (Int32,), rc))))
-        h = new(out[])
+        h = new(out[], 0.0, 0.0, false)
         finalizer(x -> ccall((:sdplrp_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
         return h
     end
@@ -67,10 +84,10 @@ Concatenate the sparse matrices in `findnz` order exactly as `SolverAuxiliary` w
 (src/structs.jl:303-332): sparse / Diagonal `A_i` in order of appearance, then `C` if sparse;
 `SymLowRankMatrix` constraints are registered separately.
 """
-function B200Auxiliary(data::SDPData{Ti,Tv}; device=0) where {Ti,Tv}
+function B200Auxiliary(data::SDPData; device=0)
     h = Handle(device)
     I, J, V, off, gids = Int64[], Int64[], Float64[], Int64[0], Int64[]
-    lowrank = Tuple{Int,SymLowRankMatrix{Tv}}[]
+    lowrank = Tuple{Int,Any}[]
     add!(A, gid) = begin
         A isa Diagonal && (A = sparse(A))
         if A isa SymLowRankMatrix
@@ -87,20 +104,21 @@ function B200Auxiliary(data::SDPData{Ti,Tv}; device=0) where {Ti,Tv}
         (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}),
         h.ptr, data.n, data.m, length(gids), off, I, J, V, gids))
     for (gid, A) in lowrank
-        B = Matrix(A.B); D = Vector(A.D.diag)
+        B = Matrix{Float64}(A.B); D = Vector{Float64}(A.D.diag)
         GC.@preserve B D check(h, ccall((:sdplrp_add_symlowrank, LIB), Int32,
             (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}), h.ptr, gid, size(B, 2), B, D))
     end
+    bvec = Vector{Float64}(data.b)
     ineq = UInt8.(data.constraint_types)
-    GC.@preserve ineq check(h, ccall((:sdplrp_set_problem, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}),
-        h.ptr, data.b, data.has_inequalities ? pointer(ineq) : Ptr{UInt8}(C_NULL)))
+    GC.@preserve bvec ineq check(h, ccall((:sdplrp_set_problem, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}),
+        h.ptr, bvec, data.has_inequalities ? pointer(ineq) : Ptr{UInt8}(C_NULL)))
     return B200Auxiliary(h, data.n, data.m)
 end
 
 """
-`DevMat` stands for an r x n matrix that lives on the device (`id` = SDPLRP_MAT_*).  It is the `TR` of
-`SolverVars{Ti,Tv,TR}` and the `Ts` of `LBFGSVector{T,Ts}`; the BLAS-1 calls `_sdplr` makes on such arrays
-(`dot`, `axpy!`, `norm`, `BLAS.scal!`, `copyto!`) never move data: the fused entry points below do the work.
+`DevMat` names an r x n matrix that lives on the device (`id` = SDPLRP_MAT_*, or MAT_HIST for an L-BFGS slot).  It is the
+`TR` of `SolverVars{Ti,Tv,TR}` and the array type `lbfgs_init` stores in its `LBFGSVector`s (src/lbfgs.jl:35-47 builds them
+with `zero(R)`).  No BLAS-1 call `_sdplr` makes on such arrays moves data.
 """
 struct DevMat <: AbstractMatrix{Float64}
     h::Handle
@@ -111,99 +129,207 @@ end
 Base.size(A::DevMat) = (A.r, A.n)
 Base.getindex(A::DevMat, i::Int, j::Int) = Array(A)[i, j]     # debugging only: downloads the matrix
 function Base.Array(A::DevMat)
+    A.id == MAT_HIST && error("L-BFGS slots are owned by the library")
     out = Matrix{Float64}(undef, A.r, A.n)
-    check(A.h, ccall((:sdplrp_download_mat, LIB), Int32, (Ptr{Cvoid}, Cint, Ptr{Float64}), A.h.ptr, A.id, out))
+    GC.@preserve out check(A.h, ccall((:sdplrp_download_mat, LIB), Int32, (Ptr{Cvoid}, Cint, Ptr{Float64}), A.h.ptr, A.id, out))
     return out
 end
+Base.Matrix(A::DevMat) = Array(A)
 upload!(A::DevMat, X::Matrix{Float64}) =
-    check(A.h, ccall((:sdplrp_upload_mat, LIB), Int32, (Ptr{Cvoid}, Cint, Ptr{Float64}), A.h.ptr, A.id, X))
+    GC.@preserve X check(A.h, ccall((:sdplrp_upload_mat, LIB), Int32, (Ptr{Cvoid}, Cint, Ptr{Float64}), A.h.ptr, A.id, X))
+
+# `dirt = similar(var.Rt)` (src/sdplr.jl:176, 381): the direction array of the library
+Base.similar(A::DevMat) = DevMat(A.h, MAT_D, A.r, A.n)
+Base.similar(A::DevMat, ::Type{Float64}) = similar(A)
+Base.similar(A::DevMat, ::Type{Float64}, dims::Dims{2}) = DevMat(A.h, MAT_D, dims[1], dims[2])
+# `zero(R)` inside lbfgs_init (src/lbfgs.jl:41): the history lives in the library (sdplrp_set_rank allocated it)
+Base.zero(A::DevMat) = DevMat(A.h, MAT_HIST, A.r, A.n)
+# `Rt0 = deepcopy(var.Rt)` (src/sdplr.jl:153-154): the start point as a host matrix, as the reference returns it
+Base.deepcopy_internal(A::DevMat, ::IdDict) = Array(A)
+# `lbfgshis.vecs[i].s .= 0` of lbfgs_clear! (src/lbfgs.jl:52-59): broadcasting a scalar into an array lowers to fill!
+function Base.fill!(A::DevMat, x)
+    (A.id == MAT_HIST && iszero(x)) || error("DevMat only supports zero-filling the L-BFGS history")
+    check(A.h, ccall((:sdplrp_lbfgs_clear, LIB), Int32, (Ptr{Cvoid},), A.h.ptr))   # idempotent: 2h calls per lbfgs_clear!, microseconds each
+    return A
+end
+
+# src/sdplr.jl:201  descent = dot(dirt, var.Gt)
+LinearAlgebra.dot(dirt::DevMat, Gt::DevMat) = dirt.h.descent
+# src/sdplr.jl:224-228  norm(var.Gt, 2)
+LinearAlgebra.norm(G::DevMat, p::Real=2) = (p == 2 || error("DevMat: only the Frobenius norm is kept"); sqrt(G.h.gnorm2))
+# src/sdplr.jl:202-205  BLAS.scal!(-1, var.Gt); copyto!(dirt, var.Gt)  -- one entry point does both
+LinearAlgebra.BLAS.scal!(a::Float64, G::DevMat) = (a == -1.0 || error("DevMat: scal! is only the sign flip of the fallback"); G)
+function Base.copyto!(dirt::DevMat, G::DevMat)
+    check(G.h, ccall((:sdplrp_use_gradient_direction, LIB), Int32, (Ptr{Cvoid},), G.h.ptr))
+    return dirt
+end
+# src/sdplr.jl:219  axpy!(α, dirt, var.Rt): sdplrp_step applied it together with the residual recurrence
+function LinearAlgebra.axpy!(α, dirt::DevMat, Rt::DevMat)
+    Rt.h.stepped || error("axpy!(α, dirt, Rt) on device matrices is only valid right after linesearch!")
+    Rt.h.stepped = false
+    return Rt
+end
 
 """
-SolverVars whose Rt/Gt are device matrices; the m-vectors stay host `Vector`s that mirror device state only
-when Julia needs them (λ for the result Dict, y for `best_λ`).
+SolverVars whose Rt/Gt are device matrices.  The m-vectors stay host `Vector`s; they mirror device state at the points
+where `_sdplr` reads them (see the header of this file).
 """
 function device_vars(data::SDPData, aux::B200Auxiliary, r, config::BurerMonteiroConfig)
-    host = SolverVars(data, r, config)                       # draws Rt0 / applies init_func exactly as the reference
+    host = SolverVars(data, r, config)                       # draws Rt0 / applies init_func exactly as the reference (src/structs.jl:225-240)
     h = aux.h
     check(h, ccall((:sdplrp_set_rank, LIB), Int32, (Ptr{Cvoid}, Int32, Int32), h.ptr, r, config.numlbfgsvecs))
     Rt, Gt = DevMat(h, MAT_R, r, data.n), DevMat(h, MAT_G, r, data.n)
-    upload!(Rt, Matrix(host.Rt))
-    check(h, ccall((:sdplrp_upload_vec, LIB), Int32, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), h.ptr, VEC_LAMBDA, host.λ, data.m))
-    check(h, ccall((:sdplrp_set_sigma, LIB), Int32, (Ptr{Cvoid}, Float64), h.ptr, config.σ_0))
-    var = SolverVars(Rt, Gt, host.λ, host.λ_ub, host.r, host.σ, host.obj, host.y, host.primal_vio_raw,
+    upload!(Rt, Matrix{Float64}(host.Rt))
+    upload_vec(h, VEC_LAMBDA, host.λ)
+    check(h, ccall((:sdplrp_set_sigma, LIB), Int32, (Ptr{Cvoid}, Float64), h.ptr, host.σ[]))
+    return SolverVars(Rt, Gt, host.λ, host.λ_ub, host.r, host.σ, host.obj, host.y, host.primal_vio_raw,
         host.primal_vio_lb, host.primal_vio, host.A_RD, host.A_DD)
-    return var, host.Rt
+end
+upload_vec(h::Handle, id::Cint, v::Vector{Float64}) =
+    GC.@preserve v check(h, ccall((:sdplrp_upload_vec, LIB), Int32, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), h.ptr, id, v, length(v)))
+download_vec!(h::Handle, id::Cint, v::Vector{Float64}) =
+    GC.@preserve v check(h, ccall((:sdplrp_download_vec, LIB), Int32, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), h.ptr, id, v, length(v)))
+
+# `norm(var.primal_vio, 2)` is evaluated on the host vector (src/sdplr.jl:230-234, src/coreop.jl:339-347): leave one with
+# the device's value as its 2-norm
+function mirror_pvio_norm!(var, pnorm2)
+    fill!(var.primal_vio, 0.0)
+    isempty(var.primal_vio) || (var.primal_vio[1] = sqrt(pnorm2))
+    return nothing
 end
 
 # ---- seam functions (SURVEY.md 8b) for the device types -------------------------------------------------
-sync_sigma(var, aux) = check(aux.h, ccall((:sdplrp_set_sigma, LIB), Int32, (Ptr{Cvoid}, Float64), aux.h.ptr, var.σ[]))
-
-function fg!(data, var::SolverVars{Ti,Tv,DevMat}, aux::B200Auxiliary, normC, normb) where {Ti,Tv}   # src/coreop.jl:323-349
-    sync_sigma(var, aux)
+# Every method below repeats the reference's own parametrisation with Tv = Float64 and the device types filled in, so that
+# it is strictly more specific than the generic method it shadows (no dispatch ambiguity).
+# src/coreop.jl:323-349  fg!(data, var, aux, normC, normb, config)
+function fg!(data, var::SolverVars{Ti,Float64,DevMat}, aux::B200Auxiliary, normC::Float64, normb::Float64, config) where {Ti<:Integer}
+    h = aux.h
+    # λ and σ may have been changed on the host by the dual / penalty update of the previous major iteration
+    # (src/sdplr.jl:358-368): the library's copies are refreshed here, once per major iteration
+    upload_vec(h, VEC_LAMBDA, var.λ)
+    check(h, ccall((:sdplrp_set_sigma, LIB), Int32, (Ptr{Cvoid}, Float64), h.ptr, var.σ[]))
     out = zeros(4)
-    check(aux.h, ccall((:sdplrp_fg, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), aux.h.ptr, out))
+    GC.@preserve out check(h, ccall((:sdplrp_fg, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), h.ptr, out))
     var.obj[] = out[2]
-    return out[1], sqrt(out[3]) / normC, sqrt(out[4]) / normb
+    h.gnorm2 = out[3]
+    mirror_pvio_norm!(var, out[4])
+    grad_norm = config.gtol_mode == :relative ? sqrt(out[3]) / normC : sqrt(out[3])
+    primal_vio_norm = config.ptol_mode == :relative ? sqrt(out[4]) / normb : sqrt(out[4])
+    return out[1], grad_norm, primal_vio_norm
 end
 
-function g!(var::SolverVars{Ti,Tv,DevMat}, aux::B200Auxiliary) where {Ti,Tv}                        # src/coreop.jl:305-317
+# src/coreop.jl:305-317  g!(var, aux); the two norms `_sdplr` takes right after it are returned by the same pass
+function g!(var::SolverVars{Ti,Float64,DevMat}, aux::B200Auxiliary) where {Ti<:Integer}
     gn2, pn2 = Ref(0.0), Ref(0.0)
     check(aux.h, ccall((:sdplrp_g, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), aux.h.ptr, gn2, pn2))
-    return gn2[], pn2[]
+    aux.h.gnorm2 = gn2[]
+    mirror_pvio_norm!(var, pn2[])
+    return 0
 end
-# `norm(var.Gt)` and the capped-residual norm of src/sdplr.jl:224-234 are the two values g! returned:
-LinearAlgebra.norm(G::DevMat, p::Real=2) = sqrt(last_gnorm2[])
-const last_gnorm2, last_pnorm2 = Ref(0.0), Ref(0.0)
 
-function lbfgs_dir!(dirt::DevMat, his, Gt::DevMat; negate::Bool=true)                               # src/lbfgs.jl:77-124
+# src/lbfgs.jl:77-124  lbfgs_dir!(dir, lbfgshis, grad; negate=true); the descent dot product comes back with it
+function lbfgs_dir!(dirt::DevMat, his::LBFGSHistory{Ti,Float64}, Gt::DevMat; negate::Bool=true) where {Ti<:Integer}
+    negate || error("the device two-loop returns the negated direction, as _sdplr asks for")
     d = Ref(0.0)
     check(dirt.h, ccall((:sdplrp_lbfgs_dir, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}), dirt.h.ptr, d))
-    last_descent[] = d[]
+    dirt.h.descent = d[]
     return nothing
 end
-const last_descent = Ref(0.0)
-LinearAlgebra.dot(dirt::DevMat, Gt::DevMat) = last_descent[]                                        # src/sdplr.jl:201
-# the non-descent fallback `Gt .*= -1; copyto!(dirt, Gt)` (src/sdplr.jl:202-205):
-use_gradient_direction!(aux) = check(aux.h, ccall((:sdplrp_use_gradient_direction, LIB), Int32, (Ptr{Cvoid},), aux.h.ptr))
 
-function linesearch!(var::SolverVars{Ti,Tv,DevMat}, aux::B200Auxiliary, dirt::DevMat; α_max=1.0) where {Ti,Tv}  # src/linesearch.jl:4-127
+# src/lbfgs.jl:129-149  lbfgs_update!(dir, lbfgshis, grad, stepsize)
+function lbfgs_update!(dirt::DevMat, his::LBFGSHistory{Ti,Float64}, Gt::DevMat, α::Float64) where {Ti<:Integer}
+    check(dirt.h, ccall((:sdplrp_lbfgs_update, LIB), Int32, (Ptr{Cvoid}, Float64), dirt.h.ptr, Float64(α)))
+    return nothing
+end
+
+# src/linesearch.jl:4-127  linesearch!(var, aux, Dt; α_max): the two 𝒜 passes and the quartic coefficients on the device,
+# the root selection of src/linesearch.jl:58-112 by sdplrp_pick_alpha (host code of the library, same candidate rule), the
+# commit `primal_vio_raw += α(α A_DD + A_RD)`, obj (src/linesearch.jl:118-124) and `Rt += α Dt` by sdplrp_step
+function linesearch!(var::SolverVars{Ti,Float64,DevMat}, aux::B200Auxiliary, dirt::DevMat; α_max=1.0) where {Ti<:Integer}
+    h = aux.h
     biquadratic = zeros(5)
-    check(aux.h, ccall((:sdplrp_linesearch_coeffs, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), aux.h.ptr, biquadratic))
-    α, 𝓛 = SDPLRPlus.cubic_linesearch_from_coeffs(biquadratic, α_max)   # root selection stays in Julia (src/linesearch.jl:58-112)
+    GC.@preserve biquadratic check(h, ccall((:sdplrp_linesearch_coeffs, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), h.ptr, biquadratic))
+    α, 𝓛 = Ref(0.0), Ref(0.0)
+    rc = GC.@preserve biquadratic ccall((:sdplrp_pick_alpha, LIB), Int32, (Ptr{Float64}, Float64, Ref{Float64}, Ref{Float64}), biquadratic, Float64(α_max), α, 𝓛)
+    rc == 0 || error("line search: the slope at 0 is positive (src/linesearch.jl:63-66)")
     obj = Ref(0.0)
-    # primal_vio_raw += α(α A_DD + A_RD), obj, and Rt += α*dirt (src/linesearch.jl:118-124, src/sdplr.jl:219)
-    check(aux.h, ccall((:sdplrp_step, LIB), Int32, (Ptr{Cvoid}, Float64, Ref{Float64}), aux.h.ptr, α, obj))
+    check(h, ccall((:sdplrp_step, LIB), Int32, (Ptr{Cvoid}, Float64, Ref{Float64}), h.ptr, α[], obj))
     var.obj[] = obj[]
+    h.stepped = true
+    return α[], 𝓛[]
+end
+
+# src/linesearch.jl:139-191  linesearch_armijo!(var, aux, Dt; α_max): eval_AL and the slope are evaluated on the device for a
+# batch of halvings at a time; the acceptance rule is the reference's
+function linesearch_armijo!(var::SolverVars{Ti,Float64,DevMat}, aux::B200Auxiliary, dirt::DevMat; α_max=1.0) where {Ti<:Integer}
+    h = aux.h
+    biquadratic = zeros(5)
+    GC.@preserve biquadratic check(h, ccall((:sdplrp_linesearch_coeffs, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), h.ptr, biquadratic))
+    evalAL(αs) = begin
+        L = zeros(length(αs)); slope = Ref(0.0)
+        GC.@preserve αs L check(h, ccall((:sdplrp_armijo_eval, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}, Ref{Float64}),
+            h.ptr, αs, length(αs), L, slope))
+        L, slope[]
+    end
+    L0v, slope = evalAL([0.0])
+    L0, c = L0v[1], 1e-4
+    αs = [Float64(α_max) / 2.0^k for k in 0:50]          # α_max and at most 50 halvings
+    α, 𝓛 = αs[end], NaN
+    found = false
+    for s in 1:15:51
+        blk = αs[s:min(s + 14, 51)]
+        Lb, _ = evalAL(blk)
+        k = findfirst(i -> Lb[i] <= L0 + c * blk[i] * slope, 1:length(blk))
+        if k !== nothing
+            α, 𝓛, found = blk[k], Lb[k], true
+            break
+        end
+        𝓛 = Lb[end]
+    end
+    obj = Ref(0.0)
+    check(h, ccall((:sdplrp_step, LIB), Int32, (Ptr{Cvoid}, Float64, Ref{Float64}), h.ptr, α, obj))
+    var.obj[] = obj[]
+    h.stepped = true
     return α, 𝓛
 end
-LinearAlgebra.axpy!(α, dirt::DevMat, Rt::DevMat) = Rt      # already applied by sdplrp_step
 
-lbfgs_update!(dirt::DevMat, his, Gt::DevMat, α) =                                                   # src/lbfgs.jl:129-149
-    check(dirt.h, ccall((:sdplrp_lbfgs_update, LIB), Int32, (Ptr{Cvoid}, Float64), dirt.h.ptr, α))
-lbfgs_clear!(his::LBFGSHistory{<:Any,<:Any,DevMat}) =                                               # src/lbfgs.jl:52-59
-    check(his.vecs[1].s.h, ccall((:sdplrp_lbfgs_clear, LIB), Int32, (Ptr{Cvoid},), his.vecs[1].s.h.ptr))
-
-function dual_obj(data, var::SolverVars{Ti,Tv,DevMat}, aux::B200Auxiliary, trace_bound, iter; highprecision=false) where {Ti,Tv}  # src/coreop.jl:376-415
-    v0 = randn(data.n)                                        # src/coreop.jl:473: the start vector stays Julia's
+# src/coreop.jl:376-415  dual_obj(data, var, aux, trace_bound, iter; highprecision)
+function dual_obj(data, var::SolverVars{Ti,Float64,DevMat}, aux::B200Auxiliary, trace_bound::Float64, iter::Ti; highprecision::Bool=false) where {Ti<:Integer}
+    h = aux.h
+    v0 = randn(aux.n)                                        # src/coreop.jl:473: the start vector stays Julia's
     dual, lam, steps = Ref(0.0), Ref(0.0), Ref{Int64}(0)
     if highprecision   # SDP_S_eigval (GenericArpack symeigs, src/coreop.jl:386-400) -> thick-restart Lanczos on the device
-        GC.@preserve v0 check(aux.h, ccall((:sdplrp_dual_obj_highprecision, LIB), Int32,
+        GC.@preserve v0 check(h, ccall((:sdplrp_dual_obj_highprecision, LIB), Int32,
             (Ptr{Cvoid}, Float64, Ptr{Float64}, UInt64, Ref{Float64}, Ref{Float64}, Ref{Int64}),
-            aux.h.ptr, trace_bound, v0, 0, dual, lam, steps))
+            h.ptr, Float64(trace_bound), v0, 0, dual, lam, steps))
     else
-        GC.@preserve v0 check(aux.h, ccall((:sdplrp_dual_obj, LIB), Int32,
+        GC.@preserve v0 check(h, ccall((:sdplrp_dual_obj, LIB), Int32,
             (Ptr{Cvoid}, Float64, Int64, Ptr{Float64}, UInt64, Ref{Float64}, Ref{Float64}, Ref{Int64}),
-            aux.h.ptr, trace_bound, iter, v0, 0, dual, lam, steps))
+            h.ptr, Float64(trace_bound), Int64(iter), v0, 0, dual, lam, steps))
     end
+    # what _sdplr reads on the host right after this call: var.y for best_λ (src/sdplr.jl:324), var.λ and
+    # var.primal_vio_raw for the dual update loop (src/sdplr.jl:358-362)
+    download_vec!(h, VEC_Y, var.y)
+    download_vec!(h, VEC_PVIO_RAW, var.primal_vio_raw)
+    download_vec!(h, VEC_LAMBDA, var.λ)
     return dual[], lam[]
 end
 
+# src/coreop.jl:518-526  rank_update!(data, var, config): a fresh point of the new rank on the device
+function rank_update!(data, var::SolverVars{Ti,Float64,DevMat}, config::BurerMonteiroConfig{Ti,Float64}) where {Ti<:Integer}
+    newr = min(barvinok_pataki(data), var.r[] * 2)
+    set_rank!(data, newr)
+    h = var.Rt.h
+    return device_vars(data, B200Auxiliary(h, size(var.Rt, 2), length(var.λ)), newr, config)
+end
+
 """
-`SDP_S_eigval(var, aux, nevs, true; which=:SA, ncv, tol, maxiter)` (src/coreop.jl:351-374) on the S last assembled.
+`SDP_S_eigval(var, aux, nevs, preprocessed; which=:SA, ncv, tol, maxiter)` (src/coreop.jl:351-374) on the S last assembled.
 """
-function SDPLRPlus.SDP_S_eigval(var::SolverVars{Ti,Tv,DevMat}, aux::B200Auxiliary, nevs, preprocessed::Bool=false;
-                                ncv=min(100, aux.n), tol=0.0, maxiter=1000000, kwargs...) where {Ti,Tv}
-    preprocessed || check(aux.h, ccall((:sdplrp_At_preprocess, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), aux.h.ptr, var.y))
+function SDPLRPlus.SDP_S_eigval(var::SolverVars{Ti,Float64,DevMat}, aux::B200Auxiliary, nevs::Integer, preprocessed::Bool=false;
+                                ncv=min(100, aux.n), tol=0.0, maxiter=1000000, kwargs...) where {Ti<:Integer}
+    y = var.y
+    preprocessed || GC.@preserve y check(aux.h, ccall((:sdplrp_At_preprocess, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), aux.h.ptr, y))
     ev = zeros(nevs); v0 = randn(aux.n)
     dt = @elapsed GC.@preserve ev v0 check(aux.h, ccall((:sdplrp_S_eigval, LIB), Int32,
         (Ptr{Cvoid}, Int64, Int64, Float64, Int64, Ptr{Float64}, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
@@ -214,35 +340,41 @@ end
 """
 `DIMACS_errors(data, var, aux)` (src/coreop.jl:426-453) in one call.
 """
-function SDPLRPlus.DIMACS_errors(data, var::SolverVars{Ti,Tv,DevMat}, aux::B200Auxiliary) where {Ti,Tv}
-    errs = zeros(6); v0 = randn(data.n)
+function SDPLRPlus.DIMACS_errors(data, var::SolverVars{Ti,Float64,DevMat}, aux::B200Auxiliary) where {Ti<:Integer}
+    errs = zeros(6); v0 = randn(aux.n)
     GC.@preserve errs v0 check(aux.h, ccall((:sdplrp_dimacs_errors, LIB), Int32,
         (Ptr{Cvoid}, Float64, Float64, Ptr{Float64}, UInt64, Ptr{Float64}),
         aux.h.ptr, norm(data.b, 2), norm(data.C, 2), v0, 0, errs))
     return errs
 end
 
-# λ_i <- min(ub_i, λ_i − σ v_i) (src/sdplr.jl:358-362) happens on the device; the host copy is refreshed for `best_λ`
-dual_update!(var, aux) = begin
-    check(aux.h, ccall((:sdplrp_dual_update, LIB), Int32, (Ptr{Cvoid},), aux.h.ptr))
-    check(aux.h, ccall((:sdplrp_download_vec, LIB), Int32, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), aux.h.ptr, VEC_LAMBDA, var.λ, length(var.λ)))
+function apply_kwargs!(config, kwargs)
+    for (k, v) in kwargs
+        hasfield(BurerMonteiroConfig, Symbol(k)) ? setfield!(config, Symbol(k), v) : @error "Unrecognized keyword argument $k"
+    end
+    return config
 end
+make_data(C, As, b, constraint_types) = constraint_types === nothing ? SDPData(C, As, b) : SDPData(C, As, b, constraint_types)
 
 """
-    sdplr(C, As, b, r; kwargs...)
+    sdplr(C, As, b, r; constraint_types = nothing, config = BurerMonteiroConfig{Int,Float64}(), kwargs...)
 
 Same contract as `SDPLRPlus.sdplr` (src/sdplr.jl:91-138); the hot path runs on the B200.
 """
-function sdplr(C, As, b, r; device=0, kwargs...)
-    config = BurerMonteiroConfig()
-    for (k, v) in kwargs
-        hasfield(BurerMonteiroConfig, k) ? setfield!(config, k, v) : @error "Unrecognized keyword argument $k"
+function sdplr(C::AbstractMatrix{Float64}, As::Vector, b::Vector{Float64}, r::Int;
+               constraint_types::Union{Nothing,AbstractVector{Bool}}=nothing,
+               config::BurerMonteiroConfig{Int,Float64}=BurerMonteiroConfig{Int,Float64}(), device=0, kwargs...)
+    apply_kwargs!(config, kwargs)
+    local data, aux, var
+    preprocess_dt = @elapsed begin
+        data = make_data(C, As, b, constraint_types)
+        aux = B200Auxiliary(data; device)
+        var = device_vars(data, aux, r, config)
     end
-    data = SDPData(C, As, b)
-    aux = B200Auxiliary(data; device)
-    var, Rt0 = device_vars(data, aux, r, config)
     ans = _sdplr(data, var, aux, SolverStats{Float64}(), config)
-    ans["Rt"] = Array(var.Rt); ans["Rt0"] = Rt0
+    ans["Rt"] = Array(ans["Rt"])                 # the reference returns host matrices
+    ans["preprocess_time"] = preprocess_dt
+    ans["totaltime"] += preprocess_dt
     return ans
 end
 
@@ -261,25 +393,26 @@ struct NativeResult
     DIMACS_errs::NTuple{6,Float64}
     iter::Int64; majoriter::Int64; lanczos_steps::Int64; r::Int64; status::Int64
 end
+# the *_mode fields of BurerMonteiroConfig are Symbols (src/options.jl:21-23)
 NativeConfig(c::BurerMonteiroConfig; seed=0) = NativeConfig(c.ptol, c.gtol, c.objtol, c.σ_0, c.σfac, c.maxtime, c.printfreq, c.fprec,
     c.prior_trace_bound, 1.0, c.maxmajoriter, c.maxiter, c.numlbfgsvecs, c.rankupd_tol, c.printlevel,
-    c.gtol_mode == "relative", c.ptol_mode == "relative", c.objtol_mode == "relative", c.eval_DIMACS_errs, c.eigval_highprecision, seed)
+    Int64(c.gtol_mode == :relative), Int64(c.ptol_mode == :relative), Int64(c.objtol_mode == :relative),
+    Int64(c.eval_DIMACS_errs), Int64(c.eigval_highprecision == true), UInt64(seed))
 
 """
-    sdplr_native(C, As, b, r; kwargs...)
+    sdplr_native(C, As, b, r; constraint_types = nothing, kwargs...)
 
 `sdplr` with the outer loop inside the library (`sdplrp_solve`).  Rt0 / λ0 come from `SolverVars(data, r, config)` as
 in the reference; the eigenvalue start vectors and the random point of a rank update come from the device generator.
 """
-function sdplr_native(C, As, b, r; device=0, seed=0, kwargs...)
-    config = BurerMonteiroConfig()
-    for (k, v) in kwargs
-        hasfield(BurerMonteiroConfig, k) ? setfield!(config, k, v) : @error "Unrecognized keyword argument $k"
-    end
-    data = SDPData(C, As, b)
+function sdplr_native(C::AbstractMatrix{Float64}, As::Vector, b::Vector{Float64}, r::Int;
+                      constraint_types::Union{Nothing,AbstractVector{Bool}}=nothing,
+                      config::BurerMonteiroConfig{Int,Float64}=BurerMonteiroConfig{Int,Float64}(), device=0, seed=0, kwargs...)
+    apply_kwargs!(config, kwargs)
+    data = make_data(C, As, b, constraint_types)
     aux = B200Auxiliary(data; device)
     host = SolverVars(data, r, config)
-    Rt0 = Matrix(host.Rt); λ0 = Vector(host.λ)
+    Rt0 = Matrix{Float64}(host.Rt); λ0 = Vector{Float64}(host.λ)
     cfg = Ref(NativeConfig(config; seed)); res = Ref{NativeResult}(); best = zeros(data.m + 1)
     GC.@preserve Rt0 λ0 best check(aux.h, ccall((:sdplrp_solve, LIB), Int32,
         (Ptr{Cvoid}, Ref{NativeConfig}, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ref{NativeResult}, Ptr{Float64}),

@@ -220,10 +220,17 @@ int orc_preprocess(orc_ctx *c, i64 nA, const i64 *mat_off, const i64 *I1, const 
     c->nzval_one = (double *)xcalloc(total_triu, sizeof(double));
     c->nzval_two = (double *)xcalloc(total_triu, sizeof(double));
     c->sparse_gid = (i64 *)xcalloc(nA, sizeof(i64));
-    i64 cumul = 0;
+    /* matptr first (counts of kept entries per matrix), then the entries of the matrices in parallel: each matrix fills
+     * its own span in stored order, so the result is the sequential loop's */
     for (i64 i = 0; i < nA; i++) {
-        c->matptr[i] = cumul;
+        i64 cnt = 0;
+        for (i64 k = mat_off[i]; k < mat_off[i + 1]; k++) cnt += (I1[k] <= J1[k]);
+        c->matptr[i + 1] = c->matptr[i] + cnt;
         c->sparse_gid[i] = sparse_gid1[i] - 1;
+    }
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (i64 i = 0; i < nA; i++) {
+        i64 cumul = c->matptr[i];
         for (i64 k = mat_off[i]; k < mat_off[i + 1]; k++) {
             i64 row = I1[k] - 1, col = J1[k] - 1;
             if (row > col) continue;

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdplrp_b200.so")
 
 # ids of include/sdplrp_b200.h
-MAT_R, MAT_G, MAT_D, MAT_W0, MAT_W1, MAT_S0, MAT_Y0 = 0, 1, 2, 3, 4, 16, 48
+MAT_R, MAT_G, MAT_D, MAT_W0, MAT_W1, MAT_CR, MAT_CD, MAT_S0, MAT_Y0 = 0, 1, 2, 3, 4, 5, 6, 16, 48
 (VEC_LAMBDA, VEC_LAMBDA_UB, VEC_B, VEC_PVIO_RAW, VEC_Y, VEC_PVIO_LB, VEC_A_RD, VEC_A_DD, VEC_S_NZVAL,
  VEC_TRIUS_NZVAL) = range(10)
 ERR_ASYMMETRIC = -4

@@ -53,6 +53,8 @@ static double *mat_ptr(sdplrp_handle *h, int id) {
     case SDPLRP_MAT_D: return h->D;
     case SDPLRP_MAT_W0: return h->W0;
     case SDPLRP_MAT_W1: return h->W1;
+    case SDPLRP_MAT_CR: return h->CR;   // introspection: the C*R recurrence of the objective split (null without a sparse C)
+    case SDPLRP_MAT_CD: return h->CD;
     default: break;
     }
     if (id >= SDPLRP_MAT_S0 && id < SDPLRP_MAT_S0 + h->hist) return h->Sh[id - SDPLRP_MAT_S0];
@@ -119,15 +121,11 @@ int32_t sdplrp_create(int32_t device, int32_t rank, int32_t world, const void *n
     sdplrp_handle *h = new sdplrp_handle();
     h->device = device; h->rank = rank; h->world = world;
     if (const char *e = getenv("SDPLRP_RELABEL")) h->relabel_mode = atoi(e) < 0 ? -1 : (atoi(e) > 0 ? 1 : 0);
-    if (const char *e = getenv("SDPLRP_SPMM_KERNEL")) h->spmm_kernel = atoi(e);
     if (const char *e = getenv("SDPLRP_HOT_ROWS")) h->hot_rows = atoll(e);
     if (const char *e = getenv("SDPLRP_LBFGS_KERNEL")) h->lbfgs_kernel = atoi(e);
     if (const char *e = getenv("SDPLRP_SPMM_UNROLL")) h->spmm_unroll = atoi(e);
     if (const char *e = getenv("SDPLRP_SPMM_G0")) h->spmm_g0 = atoi(e);
-    if (const char *e = getenv("SDPLRP_SPMM_PAD")) h->spmm_pad = atoi(e) > 0 ? 1 : 0;
-    if (const char *e = getenv("SDPLRP_LANCZOS_BUNDLE")) h->lanczos_bundle = atoi(e) > 0 ? 1 : 0;
     if (const char *e = getenv("SDPLRP_LANCZOS_DIST")) h->lanczos_dist = atoi(e) > 0 ? 1 : 0;
-    if (const char *e = getenv("SDPLRP_SPMM_PREFETCH")) h->spmm_prefetch = atoi(e) > 0 ? atoi(e) : 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SDPLRP_ERR_CUDA; }
     // L2 fetch granularity (cudaLimitMaxL2FetchGranularity: 32 / 64 / 128 bytes): the gather pass reads 80-byte rows at
     // random, so everything the memory system fetches beyond the touched sectors is waste
@@ -364,12 +362,8 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
     const std::string k(key);
     if (k == "relabel") { h->relabel_mode = value < 0 ? -1 : (value > 0 ? 1 : 0); return SDPLRP_OK; }  // before preprocess
     if (k == "hot_rows") { h->hot_rows = (i64)value; return SDPLRP_OK; }
-    if (k == "spmm_kernel") { h->spmm_kernel = (int)value; return SDPLRP_OK; }
     if (k == "spmm_phases") { h->spmm_phases = value < 0 ? 0 : (int)value; return SDPLRP_OK; }
-    if (k == "spmm_pad") { h->spmm_pad = value > 0 ? 1 : 0; return SDPLRP_OK; }
-    if (k == "lanczos_bundle") { h->lanczos_bundle = value > 0 ? 1 : 0; return SDPLRP_OK; }
     if (k == "lanczos_dist") { h->lanczos_dist = value > 0 ? 1 : 0; return SDPLRP_OK; }
-    if (k == "spmm_prefetch") { h->spmm_prefetch = value > 0 ? (int)value : 0; return SDPLRP_OK; }
     if (k == "spmm_unroll") { h->spmm_unroll = (int)value; return SDPLRP_OK; }
     if (k == "spmm_g0") { h->spmm_g0 = (int)value; return SDPLRP_OK; }
     if (k == "gather_mode") { h->gather_mode = value < 0 ? 0 : (int)value; return SDPLRP_OK; }
@@ -403,6 +397,7 @@ int32_t sdplrp_upload_mat(sdplrp_handle *h, int32_t id, const double *src) {
     REQUIRE_RANK(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
     SDP_CHECK(lazy_scratch(h, id));
+    if (id == SDPLRP_MAT_CR || id == SDPLRP_MAT_CD) return fail(h, SDPLRP_ERR_ARG, "upload_mat: CR / CD are download-only");
     double *p = mat_ptr(h, id);
     if (!p || !src) return fail(h, SDPLRP_ERR_ARG, "upload_mat: bad id");
     SDP_CHECK(perm_upload(h, p, src, h->r, true));

@@ -29,11 +29,10 @@ struct RowClasses {
     int *storage = nullptr;
 };
 
-// rows longer than one tile of the async-copy SpMM (spmm.cu) cut into chunks
-constexpr int kTileChunk = 64;          // == kTileNnz of spmm.cu
+// long rows cut into chunks (one warp each, gradient.cu)
 struct TileLayout {
     long long n_long = 0, n_chunks = 0;
-    int *long_rows = nullptr;    // n_long   rows with more than kTileChunk nonzeros (ascending)
+    int *long_rows = nullptr;    // n_long   rows with more than `chunk` nonzeros (ascending)
     int *long_cptr = nullptr;    // n_long+1 first chunk of each long row
     int *chunk_start = nullptr, *chunk_end = nullptr, *chunk_row = nullptr;  // n_chunks
 };
@@ -112,24 +111,14 @@ struct sdplrp_handle {
     i64 hot_rows = -1;                                   // leading (hub) rows of a gathered factor kept in L2; -1 = auto
     int spmm_unroll = 8;                                 // nonzeros per predicated block of the class-0 register kernel (4 or 8)
     int spmm_g0 = 1;                                     // class-0 lane groups of exactly r/2 lanes (0: next power of two)
-    int spmm_kernel = 0;                                 // 0 = row-binned register kernels (default), 1 = async-copy tile-stream kernel
     int spmm_phases = 0;                                 // 0 = one sweep per gather pass (default); 1 = hub | tail two-phase pass with an
                                                          // L2-sized hub prefix; > 1 = that many hub columns (gradient.cu, grad_obj_spmm)
-    const void *c0_checked = nullptr;                    // class-0 list the contiguity answer below belongs to (gradient.cu, k_rows_bundle)
-    i64 c0_first = 0;
-    bool c0_contig = false;
-    int spmm_pad = 0;                                    // 1 = the pipelined gather kernels read a 128-byte-aligned copy of the factor (experimental)
-    double *gpad = nullptr;                              // that copy, n x pad_stride(r)
-    i64 gpad_len = 0;
-    int lanczos_bundle = 0;                              // 1 = bundle SpMV kernel for the short rows of the Lanczos operator (experimental, lanczos.cu)
     int lanczos_dist = 0;                                // 1 = row-partitioned q-step Lanczos on world > 1 (experimental, lanczos.cu: lz_run_dist)
-    int spmm_prefetch = 0;                               // 1 = software-pipelined row loops in the gather pass (experimental, gradient.cu:
-                                                         // k_rows_group_pf / k_rows_warp_pf; same summation order as the default kernels)
     // asynchronous tile pipeline of the gather pass (gather.cu)
     int gather_mode = 0;                                 // 0 = register kernels of gradient.cu, 1 = cp.async.bulk row gathers, 2 = 16-byte cp.async row gathers
     int gather_tile = 0, gather_stages = 0, gather_warps = 0;  // 0 = automatic (gather_geometry)
     int gather_hints = 0;                                // 1 = L2 evict_last / evict_first policies on the row gathers (MODE 1)
-    bool gather_attr_set[2][5] = {{false}};
+    i64 gather_attr_smem[2][5] = {{0}};                 // dynamic shared memory the kernel variants were last sized for
     GatherPlan full_plan;                                // plan of the full pattern over the owned rows
     int *row_mid = nullptr;                              // n: first tail-column position of every row (two-phase pass)
     i64 row_mid_cols = -1;                               // hub prefix row_mid was built for
@@ -176,7 +165,6 @@ struct sdplrp_handle {
     i64 n_dyn_nsd = 0;             // their total number (0 for MaxCut-type problems: the hot loop then skips S_dyn)
     unsigned char *sd_flag = nullptr;  // nA: matrix handled by the row lists
     RowClasses full_cls, dyn_cls;  // row bins of the full / dynamic pattern
-    TileLayout full_tile, dyn_tile; // long-row chunk lists of both patterns (spmm.cu)
     TileLayout full_long, dyn_long; // rows of the third class cut into kRowWarpMax-nonzero chunks (gradient.cu)
     double *tile_scratch = nullptr; // chunk partial sums, max(n_chunks) x r
     i64 tile_scratch_len = 0;
@@ -353,7 +341,6 @@ int32_t lr_project(sdplrp_handle *h, const LowRank &L, const double *X, double *
 int32_t lr_scratch(sdplrp_handle *h);
 
 // gradient (gradient.cu)
-bool grad_class0_range(sdplrp_handle *h, i64 *first, i64 *count);  // class 0 of the full pattern as a contiguous row range (or false)
 int32_t grad_form_y(sdplrp_handle *h);                          // copy2y_lambda_sub_pvio!
 int32_t grad_assemble_S(sdplrp_handle *h);                      // At_preprocess! from device y
 int32_t grad_spmm(sdplrp_handle *h, const double *X, double *Y, double scale, bool want_norm);  // Y = scale*X*S (+low rank)
@@ -374,12 +361,7 @@ int32_t gather_plan_build(sdplrp_handle *h, GatherPlan &p, const int *ptr_dev, i
 int32_t gather_spmm(sdplrp_handle *h, const GatherPlan &plan, const int *ptr, const int *idx, const double *val, const double *Xg,
                     const double *X, const double *Z, double *Y, int epi, double scale, double *sums4);
 
-// async-copy tile-stream SpMM (spmm.cu)
-bool tile_supported(const sdplrp_handle *h);
-i64 tile_hot_rows(const sdplrp_handle *h);
-int32_t tile_spmm(sdplrp_handle *h, const TileLayout &lay, const int *ptr, const int *idx, const double *val, const int *src,
-                  const double *X, double *Y, int epi, double scale, double yobj, const double *E0, const double *E1,
-                  double *sums2);
+i64 tile_hot_rows(const sdplrp_handle *h);   // hub prefix of a gathered factor (gradient.cu)
 
 // m-vector kernels (vecops.cu)
 int32_t vec_f_finish(sdplrp_handle *h);      // raw -= b, obj, AL value -> SC_OBJ, SC_LVAL

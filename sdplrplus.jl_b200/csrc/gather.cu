@@ -350,7 +350,7 @@ static void gather_geometry(const sdplrp_handle *h, int r, int *T, int *niv, int
     t = std::max(16, std::min(256, t)) & ~7;
     const int NIV = 4, NRS = h->gather_stages > 0 ? h->gather_stages : 2;
     const size_t per_warp = ((size_t)NRS * t * r * 8 + (size_t)NIV * (t + 8) * 16 + (size_t)(NIV + 1) * 16 + (size_t)(NIV + NRS) * 8 + 127) & ~(size_t)127;
-    int w = (int)((size_t)(200 * 1024) / per_warp);
+    int w = (int)((size_t)(216 * 1024) / per_warp);
     if (h->gather_warps > 0) w = std::min(w, h->gather_warps);
     w = std::max(1, std::min(16, w));
     *T = t; *niv = NIV; *nrs = NRS; *warps = w; *smem = per_warp * w;
@@ -389,9 +389,9 @@ int32_t gather_spmm(sdplrp_handle *h, const GatherPlan &plan, const int *ptr, co
 #define TILE_LAUNCH(MODE, EPI)                                                                                           \
     do {                                                                                                                 \
         auto kern = k_tile_gather<MODE, EPI>;                                                                            \
-        if (!h->gather_attr_set[MODE - 1][EPI]) {                                                                        \
-            CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));            \
-            h->gather_attr_set[MODE - 1][EPI] = true;                                                                    \
+        if (h->gather_attr_smem[MODE - 1][EPI] < (i64)smem) {                                                            \
+            CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+            h->gather_attr_smem[MODE - 1][EPI] = (i64)smem;                                                              \
         }                                                                                                                \
         const i64 want = (plan.ntiles + warps - 1) / warps;                                                              \
         kern<<<(int)std::max<i64>(1, std::min<i64>(want, kNumSM)), warps * 32, smem, st>>>(a);                           \

@@ -191,9 +191,6 @@ struct RowArgs {
     const double *val;
     const int *src;    // IND: value = val[src[k]]
     const double *X;
-    i64 c0_first;      // k_rows_bundle: class 0 is the contiguous row range [c0_first, c0_first + n_rows)
-    const double *Xg;  // gathered operand of the pipelined kernels: X itself, or its line-aligned copy (option "spmm_pad")
-    int ldx;           // row stride of Xg in doubles
     double *Y;
     int r, G;
     int G0;            // lanes per row of the class-0 kernel (= pieces per row: no idle lanes, no shuffles there)
@@ -410,445 +407,6 @@ __global__ void __launch_bounds__(TPB) k_rows_combine(RowArgs a) {
     finish_sums<EPI>(a, s0, s1);
 }
 
-// Option "spmm_prefetch" = 3: the default class-0 row loop with ONE change -- full blocks are straight-line code and the last,
-// partial block gathers unconditionally (positions past the end repeat the row's last nonzero) with only its FMAs
-// predicated, so that all NB gathers of a block are in flight together.  In the default kernel ptxas issues the eight
-// predicated gathers as 1 + 2 + 5 with a dependent DFMA after each batch (source page of the round-1 capture,
-// profiles/r1_gather_size_sweep.md): three gather round trips per block.  EPI 2, one unit per lane, plain values.
-template <int VEC, int NB>
-__global__ void __launch_bounds__(TPB, NB >= 8 ? 2 : 4) k_rows_group_b(RowArgs a) {
-    const int nv = a.r / VEC;
-    const int G = a.G0;
-    const int gpb = TPB / G;
-    const int gib = threadIdx.x / G;
-    const int lg = threadIdx.x - gib * G;
-    const bool lane_ok = gib < gpb && lg < nv;
-    const size_t pc = (size_t)lg * VEC;
-    const i64 group = (i64)blockIdx.x * gpb + gib;
-    const i64 n_groups = (i64)gridDim.x * gpb;
-    const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
-    double s0 = 0.0, s1 = 0.0;
-    if (lane_ok)
-    for (i64 q = group; q < a.n_rows; q += n_groups) {
-        const i64 i = a.rows ? a.rows[q] : q;
-        if (i < a.own_lo || i >= a.own_hi) continue;
-        const int beg = a.ptr[i], end = a.ptr[i + 1];
-        Acc<VEC> x, z, acc;
-        acc.zero(); z.zero();
-        x.ld(a.X + (size_t)i * a.r + pc);              // epilogue operands: issued before the gathers, used after them
-        if (a.Z) z.ld(a.Z + (size_t)i * a.r + pc);
-        int k0 = beg;
-#pragma unroll 1
-        for (; k0 + NB <= end; k0 += NB) {
-            int c[NB];
-            double v[NB];
-            Acc<VEC> gq[NB];
-#pragma unroll
-            for (int j = 0; j < NB; j++) c[j] = ldg_i32_hint(a.idx + k0 + j, p_str);
-#pragma unroll
-            for (int j = 0; j < NB; j++) v[j] = ldg_f64_hint(a.val + k0 + j, p_str);
-#pragma unroll
-            for (int j = 0; j < NB; j++) gq[j].ld_hint(a.X + (size_t)c[j] * a.r + pc, c[j] < a.hot_rows ? p_hot : p_str);
-#pragma unroll
-            for (int j = 0; j < NB; j++) acc.fma_reg(v[j], gq[j]);
-        }
-        if (k0 < end) {
-            int c[NB];
-            double v[NB];
-            Acc<VEC> gq[NB];
-#pragma unroll
-            for (int j = 0; j < NB; j++) c[j] = ldg_i32_hint(a.idx + (k0 + j < end ? k0 + j : end - 1), p_str);
-#pragma unroll
-            for (int j = 0; j < NB; j++) v[j] = ldg_f64_hint(a.val + (k0 + j < end ? k0 + j : end - 1), p_str);
-#pragma unroll
-            for (int j = 0; j < NB; j++) gq[j].ld_hint(a.X + (size_t)c[j] * a.r + pc, c[j] < a.hot_rows ? p_hot : p_str);
-#pragma unroll
-            for (int j = 0; j < NB; j++)
-                if (k0 + j < end) acc.fma_reg(v[j], gq[j]);
-        }
-        s0 += acc.dot_reg(x);
-        if (a.Z) s1 += x.dot_reg(z);
-        acc.store(a.Y + (size_t)i * a.r + pc);
-    }
-    finish_sums<2>(a, s0, s1);
-}
-
-// ---- software-pipelined row loops (option "spmm_prefetch"; profiles/r1_gather_size_sweep.md) ----------------------------
-// The default kernels pay four to five DEPENDENT memory round trips per row: row list -> ptr pair -> idx/val block ->
-// gathers -> epilogue operands.  Measured: a nonzero costs the same 22-26 ps whether the gathered factor sits in L2 or not,
-// i.e. the pass is bound by that chain, not by its DRAM traffic.  Here the work of a lane group (class 0) or warp (class 1 /
-// chunks) is a sequence of BLOCKS of nonzeros walked by a three-stage row pipeline:
-//   stage A  row index of row q+2        (one load, issued two rows ahead)
-//   stage B  ptr pair of row q+1         (issued one row ahead)
-//   stage C  the current row: its next idx/val block -- or the first block of row q+1 when the current block is the row's
-//            last -- and the epilogue operands X_i, Z_i of row q+1 are loaded right after the current block's gathers were
-//            issued, so they travel together with those gathers.
-// One exposed latency per block instead of five per row.  The nonzeros of a row are still accumulated in stored order by the
-// same lane, rows are taken by the same group in the same order, and the sums go through the same grid reduction, so on one
-// GPU the results are those of the default kernels bit for bit.  Only one unit per lane (MAXU == 1: r <= 64 even / 32 odd),
-// the plain value stream and the epilogue of the hot pass (EPI 2: Y_i = acc, sum0 += <X_i, acc>, sum1 += <X_i, Z_i>).
-// Written at the end of round 1 with no GPU time left: off by default, first measurement is scripts/r2_first_call.sh.
-
-// [q_lo, q_hi) = the entries of the ascending row list whose row is owned by this rank (the whole list on one GPU)
-__device__ __forceinline__ void owned_q_range(const int *__restrict__ list, i64 n_list, i64 own_lo, i64 own_hi, i64 &q_lo, i64 &q_hi) {
-    if (!list) {
-        q_lo = own_lo < 0 ? 0 : (own_lo < n_list ? own_lo : n_list);
-        q_hi = own_hi < n_list ? (own_hi < q_lo ? q_lo : own_hi) : n_list;
-        return;
-    }
-    i64 lo = 0, hi = n_list;
-    if (own_lo > 0) {
-        while (lo < hi) { const i64 mid = lo + ((hi - lo) >> 1); if ((i64)__ldg(list + mid) < own_lo) lo = mid + 1; else hi = mid; }
-    }
-    q_lo = lo;
-    hi = n_list;
-    if (n_list > 0 && (i64)__ldg(list + n_list - 1) >= own_hi) {
-        while (lo < hi) { const i64 mid = lo + ((hi - lo) >> 1); if ((i64)__ldg(list + mid) < own_hi) lo = mid + 1; else hi = mid; }
-        hi = lo;
-    }
-    q_hi = hi;
-}
-
-template <int VEC, int NB, int EPI>
-__global__ void __launch_bounds__(TPB, 2) k_rows_group_pf(RowArgs a) {
-    const int nv = a.r / VEC;
-    const int G = a.G0;
-    const int gpb = TPB / G;
-    const int gib = threadIdx.x / G;
-    const int lg = threadIdx.x - gib * G;
-    const bool lane_ok = gib < gpb;
-    const bool piece_ok = lg < nv;
-    const size_t pc = (size_t)lg * VEC;             // this lane's slice of a factor row
-    const i64 n_groups = (i64)gridDim.x * gpb;
-    const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
-    double s0 = 0.0, s1 = 0.0;
-    if (lane_ok) {
-        i64 q_lo, q_hi;
-        owned_q_range(a.rows, a.n_rows, a.own_lo, a.own_hi, q_lo, q_hi);
-        // row index of list entry q; -2 = past the end
-        // (row labels and list positions fit 32 bits: the pattern arrays are int32)
-        auto row_at = [&](i64 q) -> int { return q < q_hi ? (a.rows ? __ldg(a.rows + q) : (int)q) : -2; };
-        // a row covers [beg_arr[i], end_arr[i]) when those are given (two-phase pass: hub | tail columns), else [ptr[i], ptr[i+1])
-        auto row_beg = [&](int i) -> int { return a.beg_arr ? __ldg(a.beg_arr + i) : __ldg(a.ptr + i); };
-        auto row_end = [&](int i) -> int { return a.end_arr ? __ldg(a.end_arr + i) : __ldg(a.ptr + i + 1); };
-        constexpr bool kDots = (EPI == 2 || EPI == 4);   // epilogues with the fused sums read X_i (and Z_i)
-        i64 q = q_lo + (i64)blockIdx.x * gpb + gib;
-        // prologue: fill the three stages (the only place where the chain is exposed)
-        int iC = row_at(q);
-        int k0 = 0, endC = 0;
-        if (iC >= 0) { k0 = row_beg(iC); endC = row_end(iC); }
-        q += n_groups;
-        int iB = row_at(q);
-        int begB = 0, endB = 0;
-        if (iB >= 0) { begB = row_beg(iB); endB = row_end(iB); }
-        q += n_groups;
-        int iA = row_at(q);
-        int cc[NB];
-#pragma unroll
-        for (int j = 0; j < NB; j++) cc[j] = k0 + j < endC ? ldg_i32_hint(a.idx + k0 + j, p_str) : 0;
-        Acc<VEC> xC, zC, yC, acc;
-        xC.zero(); zC.zero(); yC.zero(); acc.zero();
-        if (iC >= 0 && piece_ok) {
-            if (kDots) {
-                xC.ld(a.X + (size_t)iC * a.r + pc);
-                if (a.Z) zC.ld(a.Z + (size_t)iC * a.r + pc);
-            }
-            if (EPI == 4) yC.v = *reinterpret_cast<const decltype(yC.v) *>(a.Y + (size_t)iC * a.r + pc);   // phase one's part of the row
-        }
-        while (iC >= 0) {
-            // 1. the gathers of the current block, and its values (their addresses need no index, so they travel with the
-            //    gathers instead of occupying registers a block ahead)
-            Acc<VEC> g[NB];
-            double vv[NB];
-#pragma unroll
-            for (int j = 0; j < NB; j++)
-                if (piece_ok && k0 + j < endC) g[j].ld_hint(a.Xg + (size_t)cc[j] * a.ldx + pc, cc[j] < a.hot_rows ? p_hot : p_str);
-#pragma unroll
-            for (int j = 0; j < NB; j++) vv[j] = k0 + j < endC ? ldg_f64_hint(a.val + k0 + j, p_str) : 0.0;
-            // 2. the indices of the block after it: next block of this row, or the first block of row B
-            const bool last = k0 + NB >= endC;
-            const int nk0 = last ? begB : k0 + NB;
-            const int nend = last ? endB : endC;
-            int cn[NB];
-#pragma unroll
-            for (int j = 0; j < NB; j++) cn[j] = nk0 + j < nend ? ldg_i32_hint(a.idx + nk0 + j, p_str) : 0;
-            // 3. the row pipeline moves when this block ends its row: ptr pair of row A, index of the row after A,
-            //    epilogue operands of row B
-            int iN = -2;
-            int begA = 0, endA = 0;
-            Acc<VEC> xB, zB, yB;
-            xB.zero(); zB.zero(); yB.zero();
-            if (last) {
-                if (iA >= 0) { begA = row_beg(iA); endA = row_end(iA); }
-                q += n_groups;
-                iN = row_at(q);
-                if (iB >= 0 && piece_ok) {
-                    if (kDots) {
-                        xB.ld(a.X + (size_t)iB * a.r + pc);
-                        if (a.Z) zB.ld(a.Z + (size_t)iB * a.r + pc);
-                    }
-                    if (EPI == 4) yB.v = *reinterpret_cast<const decltype(yB.v) *>(a.Y + (size_t)iB * a.r + pc);
-                }
-            }
-            // 4. consume the gathers, in stored order
-#pragma unroll
-            for (int j = 0; j < NB; j++)
-                if (piece_ok && k0 + j < endC) acc.fma_reg(vv[j], g[j]);
-            // 5. row epilogue and rotation.  EPI 0: Y_i = scale*acc;  EPI 2: Y_i = acc with the fused sums;
-            //    EPI 4: Y_i += acc (second phase of the two-phase pass), the sums on the total
-            if (last) {
-                if (piece_ok) {
-                    if (EPI == 0) acc.scale(a.scale);
-                    if (EPI == 4) acc.add_reg_first(yC);
-                    if (kDots) {
-                        s0 += acc.dot_reg(xC);
-                        if (a.Z) s1 += xC.dot_reg(zC);
-                    }
-                    acc.store(a.Y + (size_t)iC * a.r + pc);
-                }
-                acc.zero();
-                iC = iB; k0 = begB; endC = endB; xC = xB; zC = zB; yC = yB;
-                iB = iA; begB = begA; endB = endA;
-                iA = iN;
-            } else {
-                k0 += NB;
-            }
-#pragma unroll
-            for (int j = 0; j < NB; j++) cc[j] = cn[j];
-        }
-    }
-    finish_sums<EPI>(a, s0, s1);
-}
-
-// Class 0 by BUNDLES (option "spmm_prefetch" = 2): a warp takes 32/G0 CONSECUTIVE rows (6 at r = 10) whose nonzeros are one
-// contiguous span of the CSR arrays (<= 32 per row in this class), stages that span into its own slice of shared memory with
-// fully coalesced loads, then every lane group walks its row out of shared memory and issues nothing but gathers.  The ptr
-// values of the next bundle are loaded one bundle ahead.  Two exposed round trips per bundle (staging, gathers) instead of
-// five per row, at 80 registers (24 warps per SM) where the register-pipelined kernels need 96-128.  Needs class 0 to be a
-// contiguous row range (hub-first order, or a pattern with short rows only) and 32/G0 <= kBundleRows.
-constexpr int TPB_B = 128;         // 4 warps: 4 x kBundleRows x 32 x 12 B = 12 KB of shared memory
-constexpr int kBundleRows = 8;
-template <int VEC, int NB>
-__global__ void __launch_bounds__(TPB_B, NB <= 4 ? 6 : 4) k_rows_bundle(RowArgs a) {
-    __shared__ double sv_all[(TPB_B / 32) * kBundleRows * 32];
-    __shared__ int si_all[(TPB_B / 32) * kBundleRows * 32];
-    const int nv = a.r / VEC;
-    const int G = a.G0;
-    const int RPW = 32 / G;                          // rows per bundle
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = lane / G, lg = lane - g * G;
-    const bool grp_ok = g < RPW;                     // lanes beyond RPW*G only help with the staging
-    const bool piece_ok = grp_ok && lg < nv;
-    const size_t pc = (size_t)lg * VEC;
-    double *sv = sv_all + wib * (kBundleRows * 32);
-    int *si = si_all + wib * (kBundleRows * 32);
-    const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
-    // the owned part of the contiguous class-0 range
-    i64 r_lo = a.c0_first, r_hi = a.c0_first + a.n_rows;
-    if (r_lo < a.own_lo) r_lo = a.own_lo;
-    if (r_hi > a.own_hi) r_hi = a.own_hi;
-    if (r_hi < r_lo) r_hi = r_lo;
-    const i64 n_bundles = (r_hi - r_lo + RPW - 1) / RPW;
-    const i64 n_warps = (i64)gridDim.x * (TPB_B / 32);
-    double s0 = 0.0, s1 = 0.0;
-    i64 b = (i64)blockIdx.x * (TPB_B / 32) + wib;
-    // lane l holds ptr[first row of the bundle + min(l, rows in the bundle)]: rows past the end come out empty
-    auto load_ptr = [&](i64 bb) -> int {
-        if (bb >= n_bundles) return 0;
-        const i64 i0 = r_lo + bb * RPW;
-        const i64 nrow = (r_hi - i0 < RPW) ? (r_hi - i0) : RPW;
-        return __ldg(a.ptr + i0 + (lane < nrow ? lane : nrow));
-    };
-    int myp = load_ptr(b);
-    while (b < n_bundles) {   // warp-uniform
-        const i64 i0 = r_lo + b * RPW;
-        const int nrow = (int)((r_hi - i0 < RPW) ? (r_hi - i0) : RPW);
-        const int p0 = __shfl_sync(0xffffffffu, myp, 0);
-        const int pR = __shfl_sync(0xffffffffu, myp, RPW);
-        const int o = __shfl_sync(0xffffffffu, myp, grp_ok ? g : RPW) - p0;        // this group's row inside the span
-        const int e = __shfl_sync(0xffffffffu, myp, grp_ok ? g + 1 : RPW) - p0;
-        // 1. stage the span (coalesced), prefetch the next bundle's ptr values and this row's epilogue operands
-        {
-            int ti[kBundleRows];
-            double tv[kBundleRows];
-#pragma unroll
-            for (int m = 0; m < kBundleRows; m++) {
-                const int k = p0 + lane + 32 * m;
-                if (k < pR) { ti[m] = ldg_i32_hint(a.idx + k, p_str); tv[m] = ldg_f64_hint(a.val + k, p_str); }
-            }
-#pragma unroll
-            for (int m = 0; m < kBundleRows; m++) {
-                const int k = p0 + lane + 32 * m;
-                if (k < pR) { si[lane + 32 * m] = ti[m]; sv[lane + 32 * m] = tv[m]; }
-            }
-        }
-        const int mypN = load_ptr(b + n_warps);
-        const bool row_ok = piece_ok && g < nrow;
-        const i64 i = i0 + g;
-        Acc<VEC> x, z, acc;
-        x.zero(); z.zero(); acc.zero();
-        if (row_ok) {
-            x.ld(a.X + (size_t)i * a.r + pc);
-            if (a.Z) z.ld(a.Z + (size_t)i * a.r + pc);
-        }
-        __syncwarp();
-        // 2. the row out of shared memory, NB gathers in flight per lane
-        if (row_ok) {
-            // Full blocks are straight-line code and the last, partial block gathers unconditionally (positions past the
-            // end repeat the row's last nonzero: an L1 hit) with only its FMAs predicated.  With a predicate on every
-            // gather ptxas schedules LDS -> LDG -> DFMA per nonzero (seen in the SASS of the first version, and as the
-            // 1 + 2 + 5 batches of the default kernel): one round trip per nonzero instead of one per block.
-            int k0 = o;
-#pragma unroll 1
-            for (; k0 + NB <= e; k0 += NB) {
-                int c[NB];
-                double v[NB];
-                Acc<VEC> gq[NB];
-#pragma unroll
-                for (int j = 0; j < NB; j++) c[j] = si[k0 + j];
-#pragma unroll
-                for (int j = 0; j < NB; j++) gq[j].ld_hint(a.Xg + (size_t)c[j] * a.ldx + pc, c[j] < a.hot_rows ? p_hot : p_str);
-#pragma unroll
-                for (int j = 0; j < NB; j++) v[j] = sv[k0 + j];
-#pragma unroll
-                for (int j = 0; j < NB; j++) acc.fma_reg(v[j], gq[j]);
-            }
-            if (k0 < e) {
-                int c[NB];
-                double v[NB];
-                Acc<VEC> gq[NB];
-#pragma unroll
-                for (int j = 0; j < NB; j++) c[j] = si[k0 + j < e ? k0 + j : e - 1];
-#pragma unroll
-                for (int j = 0; j < NB; j++) gq[j].ld_hint(a.Xg + (size_t)c[j] * a.ldx + pc, c[j] < a.hot_rows ? p_hot : p_str);
-#pragma unroll
-                for (int j = 0; j < NB; j++) v[j] = sv[k0 + j < e ? k0 + j : e - 1];
-#pragma unroll
-                for (int j = 0; j < NB; j++)
-                    if (k0 + j < e) acc.fma_reg(v[j], gq[j]);
-            }
-            s0 += acc.dot_reg(x);
-            if (a.Z) s1 += x.dot_reg(z);
-            acc.store(a.Y + (size_t)i * a.r + pc);
-        }
-        __syncwarp();   // every lane is done with the span before the next bundle overwrites it
-        myp = mypN;
-        b += n_warps;
-    }
-    finish_sums<2>(a, s0, s1);
-}
-
-// class 1 (one warp per row) and the chunks of class 2 (one warp per chunk, CHUNK), pipelined the same way; a block is the
-// 4 nonzeros of each of the 32/G lane groups, the row pipeline is warp-uniform
-template <int VEC, bool CHUNK, int EPI>
-__global__ void __launch_bounds__(TPB, 3) k_rows_warp_pf(RowArgs a) {
-    const int nv = a.r / VEC;
-    const int lane = threadIdx.x & 31;
-    const int lg = lane & (a.G - 1), grp = lane / a.G, ng = 32 / a.G;
-    const bool piece_ok = lg < nv;
-    const size_t pc = (size_t)lg * VEC;
-    const int step = ng * 4;
-    const int go = grp * 4;
-    const i64 n_warps = (i64)gridDim.x * (TPB / 32);
-    const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
-    double s0 = 0.0, s1 = 0.0;
-    i64 q_lo, q_hi;
-    owned_q_range(CHUNK ? a.chunk_row : a.rows, a.n_rows, a.own_lo, a.own_hi, q_lo, q_hi);
-    // stage A loads: the row of work item q (CHUNK: and its nonzero range, which does not depend on the row)
-    // (row labels fit 32 bits: the pattern arrays are int32)
-    auto item_row = [&](i64 q) -> int { return q < q_hi ? (CHUNK ? __ldg(a.chunk_row + q) : (a.rows ? __ldg(a.rows + q) : (int)q)) : -2; };
-    auto item_beg = [&](i64 q, int i) -> int {
-        return i < 0 ? 0 : (CHUNK ? __ldg(a.chunk_start + q) : (a.beg_arr ? __ldg(a.beg_arr + i) : __ldg(a.ptr + i)));
-    };
-    auto item_end = [&](i64 q, int i) -> int {
-        return i < 0 ? 0 : (CHUNK ? __ldg(a.chunk_end + q) : (a.end_arr ? __ldg(a.end_arr + i) : __ldg(a.ptr + i + 1)));
-    };
-    constexpr bool kDots = !CHUNK && (EPI == 2 || EPI == 4);
-    i64 q = q_lo + (i64)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
-    i64 qC = q;
-    int iC = item_row(q);
-    int kb = item_beg(q, iC), endC = item_end(q, iC);
-    q += n_warps;
-    i64 qB = q;
-    int iB = item_row(q);
-    int begB = item_beg(q, iB), endB = item_end(q, iB);
-    q += n_warps;
-    i64 qA = q;
-    int iA = item_row(q);
-    int cc[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) cc[j] = kb + go + j < endC ? ldg_i32_hint(a.idx + kb + go + j, p_str) : 0;
-    Acc<VEC> xC, zC, yC, acc;
-    xC.zero(); zC.zero(); yC.zero(); acc.zero();
-    if (!CHUNK && iC >= 0 && piece_ok && grp == 0) {
-        if (kDots) {
-            xC.ld(a.X + (size_t)iC * a.r + pc);
-            if (a.Z) zC.ld(a.Z + (size_t)iC * a.r + pc);
-        }
-        if (EPI == 4) yC.v = *reinterpret_cast<const decltype(yC.v) *>(a.Y + (size_t)iC * a.r + pc);
-    }
-    while (iC >= 0) {  // warp-uniform
-        const int k0 = kb + go;
-        Acc<VEC> g[4];
-        double vv[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (piece_ok && k0 + j < endC) g[j].ld_hint(a.Xg + (size_t)cc[j] * a.ldx + pc, cc[j] < a.hot_rows ? p_hot : p_str);
-#pragma unroll
-        for (int j = 0; j < 4; j++) vv[j] = k0 + j < endC ? ldg_f64_hint(a.val + k0 + j, p_str) : 0.0;
-        const bool last = kb + step >= endC;   // warp-uniform
-        const int nkb = last ? begB : kb + step;
-        const int nend = last ? endB : endC;
-        int cn[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) cn[j] = nkb + go + j < nend ? ldg_i32_hint(a.idx + nkb + go + j, p_str) : 0;
-        int iN = -2;
-        int begA = 0, endA = 0;
-        Acc<VEC> xB, zB, yB;
-        xB.zero(); zB.zero(); yB.zero();
-        if (last) {
-            begA = item_beg(qA, iA); endA = item_end(qA, iA);
-            q += n_warps;
-            iN = item_row(q);
-            if (!CHUNK && iB >= 0 && piece_ok && grp == 0) {
-                if (kDots) {
-                    xB.ld(a.X + (size_t)iB * a.r + pc);
-                    if (a.Z) zB.ld(a.Z + (size_t)iB * a.r + pc);
-                }
-                if (EPI == 4) yB.v = *reinterpret_cast<const decltype(yB.v) *>(a.Y + (size_t)iB * a.r + pc);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (piece_ok && k0 + j < endC) acc.fma_reg(vv[j], g[j]);
-        if (last) {
-            for (int o = a.G; o < 32; o <<= 1) acc.shfl_add(o);   // sum of the lane groups, fixed order
-            if (grp == 0 && piece_ok) {
-                if (CHUNK) {
-                    acc.store(a.scratch + (size_t)qC * a.r + pc);
-                } else {
-                    if (EPI == 0) acc.scale(a.scale);
-                    if (EPI == 4) acc.add_reg_first(yC);
-                    if (kDots) {
-                        s0 += acc.dot_reg(xC);
-                        if (a.Z) s1 += xC.dot_reg(zC);
-                    }
-                    acc.store(a.Y + (size_t)iC * a.r + pc);
-                }
-            }
-            acc.zero();
-            qC = qB; iC = iB; kb = begB; endC = endB; xC = xB; zC = zB; yC = yB;
-            qB = qA; iB = iA; begB = begA; endB = endA;
-            qA = q; iA = iN;
-        } else {
-            kb += step;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) cc[j] = cn[j];
-    }
-    if (!CHUNK) finish_sums<EPI>(a, s0, s1);
-}
-
 // Y[j,:] += scale*coeff * sum_k XB[:,k] D[k] B[j,k]     (src/structs.jl:135-145)
 __global__ void k_lr_apply(i64 lo, i64 hi, int r, int s, i64 n, const double *__restrict__ XB, const double *__restrict__ Dg,
                            const double *__restrict__ B, const double *__restrict__ y, int gid, double scale,
@@ -1010,6 +568,18 @@ __global__ void LB_TAIL k_step_grad(i64 lo, i64 hi, int r, double a, double sigm
     grid_sum_finalize<2>(acc, partials, ticket, [&](double (&s)[2]) { gn2_out[0] = s[0]; pn2_out[0] = s[1] + pn2_rest[0]; });
 }
 
+}  // namespace
+
+// leading (hub) rows of a gathered factor whose gathers carry the L2 evict_last policy (hub-first internal order)
+i64 tile_hot_rows(const sdplrp_handle *h) {
+    if (h->hot_rows >= 0) return std::min<i64>(h->hot_rows, h->n);
+    if (!h->relabeled) return 0;
+    if (h->dealt) return h->n;  // multi-GPU deal: hubs are spread over the rank blocks; one policy for every gather, streams evict_first
+    return std::min<i64>(h->n, (i64)(48.0 * 1024 * 1024) / (8 * (i64)std::max(1, h->r)));   // ~48 MB of leading factor rows
+}
+
+namespace {
+
 int pick_group(int nv) {
     int G = 1;
     while (G < nv && G < 32) G <<= 1;
@@ -1023,26 +593,6 @@ struct Csr {
     const RowClasses *cls;
 };
 
-// is class 0 of these row bins one contiguous row range?  (asked once per pattern; two 4-byte reads)
-static bool class0_contiguous(sdplrp_handle *h, const RowClasses &cls, i64 *first) {
-    if (cls.cnt[0] <= 0) return false;
-    if (!cls.list[0]) { *first = 0; return true; }   // identity list: every row is in class 0
-    if (h->c0_checked != (const void *)cls.list[0]) {
-        int ends[2] = {0, 0};
-        if (cudaMemcpyAsync(&ends[0], cls.list[0], sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-            cudaMemcpyAsync(&ends[1], cls.list[0] + (cls.cnt[0] - 1), sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-            cudaStreamSynchronize(h->stream) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        h->c0_checked = (const void *)cls.list[0];
-        h->c0_first = ends[0];
-        h->c0_contig = ((i64)ends[1] - (i64)ends[0] + 1 == cls.cnt[0]);   // the list is ascending and has no duplicates
-    }
-    *first = h->c0_first;
-    return h->c0_contig;
-}
-
 // long_empty: the long rows (class 2) take the warp-per-row kernel over an EMPTY range (second phase of the two-phase pass:
 // their nonzeros were all handled, chunked, in the first phase; only the epilogue is left)
 template <int VEC, int MAXU, bool IND, int EPI>
@@ -1051,56 +601,12 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
     cudaStream_t st = h->stream;
     const int gpb = TPB / a.G;
     const int gpb0 = TPB / a.G0;
-    // software-pipelined row loops: only the shape of the hot pass (one unit per lane, plain values, EPI 2, whole rows)
-    bool pf = false;
-    constexpr bool kPfShape = (MAXU == 1 && !IND && (EPI == 0 || EPI == 2 || EPI == 4));
-    if constexpr (kPfShape) pf = h->spmm_prefetch > 0 && (sums != nullptr) == (EPI != 0);
-    const bool whole_rows = !a.beg_arr && !a.end_arr;   // the bundle / batched kernels walk whole rows only
     for (int c = 0; c < 3; c++) {
         if (sums) a.out = sums + 2 * c;
         a.rows = cls.list[c];
         a.n_rows = cls.cnt[c];
         if (a.n_rows <= 0) {
             if (sums) CUDA_TRY(h, cudaMemsetAsync(sums + 2 * c, 0, 2 * sizeof(double), st));
-            continue;
-        }
-        if (pf) {
-            if constexpr (kPfShape) {
-                if (c == 0 && h->spmm_prefetch == 3 && whole_rows && EPI == 2) {
-                    if (h->spmm_unroll >= 8) k_rows_group_b<VEC, 8><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
-                    else k_rows_group_b<VEC, 4><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
-                } else if (c == 0 && h->spmm_prefetch == 2 && whole_rows && EPI == 2 && 32 / a.G0 <= kBundleRows &&
-                           class0_contiguous(h, cls, &a.c0_first)) {
-                    const int rpw = 32 / a.G0;
-                    const int grid = grid_for((a.n_rows + rpw - 1) / rpw, TPB_B / 32, 32 * kNumSM);
-                    if (h->spmm_unroll >= 8) k_rows_bundle<VEC, 8><<<grid, TPB_B, 0, st>>>(a);
-                    else k_rows_bundle<VEC, 4><<<grid, TPB_B, 0, st>>>(a);
-                } else if (c == 0) {
-                    if (h->spmm_unroll >= 8) k_rows_group_pf<VEC, 8, EPI><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
-                    else k_rows_group_pf<VEC, 4, EPI><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
-                } else if (c == 1) {
-                    k_rows_warp_pf<VEC, false, EPI><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
-                } else if (long_empty) {   // second phase: the long rows were handled whole in the first; only their epilogue is left
-                    RowArgs b = a;
-                    b.beg_arr = a.ptr + 1; b.end_arr = a.ptr + 1;
-                    k_rows_warp_pf<VEC, false, EPI><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
-                } else {
-                    const i64 need = longs.n_chunks * (i64)a.r;
-                    if (h->tile_scratch_len < need) {
-                        SDP_CHECK(dev_alloc(h, &h->tile_scratch, need));
-                        h->tile_scratch_len = need;
-                    }
-                    RowArgs b = a;
-                    b.chunk_start = longs.chunk_start; b.chunk_end = longs.chunk_end; b.chunk_row = longs.chunk_row;
-                    b.long_rows = longs.long_rows; b.long_cptr = longs.long_cptr; b.scratch = h->tile_scratch;
-                    b.n_rows = longs.n_chunks;
-                    k_rows_warp_pf<VEC, true, EPI><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
-                    KLAUNCH(h);
-                    b.n_rows = longs.n_long;
-                    k_rows_combine<VEC, MAXU, EPI><<<grid_for(b.n_rows, gpb, 4 * kNumSM), TPB, 0, st>>>(b);
-                }
-            }
-            KLAUNCH(h);
             continue;
         }
         if (c == 0) {
@@ -1141,7 +647,6 @@ int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const Til
     const bool vec2 = (r % 2 == 0);
     const int nv = vec2 ? r / 2 : r;
     a.r = r;
-    if (!a.Xg) { a.Xg = a.X; a.ldx = r; }
     a.G = pick_group(nv);
     a.partials = h->partials;
     a.ticket = h->ticket;
@@ -1206,15 +711,6 @@ int32_t add_lowrank(sdplrp_handle *h, const double *X, double *Y, double scale) 
 
 }  // namespace
 
-// the short rows (class 0) of the full pattern as one contiguous row range, if they are one (hub-first order, or short rows only)
-bool grad_class0_range(sdplrp_handle *h, i64 *first, i64 *count) {
-    i64 f = 0;
-    if (!class0_contiguous(h, h->full_cls, &f)) return false;
-    *first = f;
-    *count = h->full_cls.cnt[0];
-    return true;
-}
-
 int32_t grad_form_y(sdplrp_handle *h) {
     k_form_y<<<grid_for(h->m + 1, TPB, kRedBlocks), TPB, 0, h->stream>>>(h->m, h->sigma, h->lambda, h->lambda_ub, h->pvio_raw, h->y);
     KLAUNCH(h);
@@ -1275,8 +771,6 @@ int32_t grad_spmm_sparse(sdplrp_handle *h, const double *X, double *Y, double sc
     if (h->nA > 0 && gather_supported(h) && h->nnzF > 0) {
         SDP_CHECK(gather_plan_build(h, h->full_plan, h->full_ptr, h->row_lo, h->row_hi, gather_tile_size(h)));
         SDP_CHECK(gather_spmm(h, h->full_plan, h->full_ptr, h->full_idx, h->S, X, nullptr, nullptr, Y, 0, scale, nullptr));
-    } else if (h->nA > 0 && tile_supported(h)) {
-        SDP_CHECK(tile_spmm(h, h->full_tile, h->full_ptr, h->full_idx, h->S, nullptr, X, Y, 0, scale, 0.0, nullptr, nullptr, nullptr));
     } else if (h->nA > 0) {
         RowArgs a = {};
         a.ptr = h->full_ptr; a.idx = h->full_idx; a.val = h->S; a.src = nullptr;
@@ -1288,24 +782,6 @@ int32_t grad_spmm_sparse(sdplrp_handle *h, const double *X, double *Y, double sc
     return SDPLRP_OK;
 }
 
-// Option "spmm_pad" (with "spmm_prefetch", one GPU): the gathers read a copy of X whose rows start on 128-byte lines (an
-// 80-byte row at an 80-byte stride straddles a line 5 times out of 8).  Written for an L1-wavefront reading of the size sweep
-// that the ncu capture of the round does not support (L1 at 39 % of peak, long_scoreboard dominant; sectors and DRAM
-// granules per gather are the same with and without padding): kept as a cheap confirmation, not as a candidate.  The copy
-// is made by its own kernel inside the timed section.
-__global__ void k_pad_rows(i64 n, int r, int ld, const double *__restrict__ X, double *__restrict__ Xp) {
-    const i64 total = n * r;
-    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
-        const i64 i = e / r;
-        const int c = (int)(e - i * r);
-        Xp[i * ld + c] = X[e];
-    }
-}
-static int pad_stride(int r) {
-    if (r <= 16) { int p = 1; while (p < r) p <<= 1; return p; }  // 8r bytes divides 128: a row never crosses a line
-    return (r + 15) / 16 * 16;                                       // whole lines per row
-}
-
 // Y = C*X over the owned rows with the fused sums  out0 = <X, Y>, out1 = <X, Z>  (Z may be null)
 int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double *Z, double *sums6) {
     if (gather_supported(h) && h->nnzF > 0) {   // asynchronous tile pipeline (gather.cu)
@@ -1313,25 +789,9 @@ int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double
         CUDA_TRY(h, cudaMemsetAsync(sums6 + 4, 0, 2 * sizeof(double), h->stream));
         return gather_spmm(h, h->full_plan, h->full_ptr, h->full_idx, h->Cfull, X, X, Z, Y, 2, 1.0, sums6);
     }
-    if (tile_supported(h)) {
-        CUDA_TRY(h, cudaMemsetAsync(sums6, 0, 6 * sizeof(double), h->stream));
-        return tile_spmm(h, h->full_tile, h->full_ptr, h->full_idx, h->Cfull, nullptr, X, Y, 2, 1.0, 0.0, X, Z, sums6);
-    }
     RowArgs a = {};
     a.ptr = h->full_ptr; a.idx = h->full_idx; a.val = h->Cfull; a.src = nullptr;
     a.X = X; a.Y = Y; a.Z = Z; a.scale = 1.0;
-    if (h->spmm_pad > 0 && h->spmm_prefetch > 0 && h->world == 1 && pad_stride(h->r) != h->r) {
-        const int ld = pad_stride(h->r);
-        const i64 need = h->n * (i64)ld;
-        if (h->gpad_len < need) {
-            SDP_CHECK(dev_alloc(h, &h->gpad, need));
-            CUDA_TRY(h, cudaMemsetAsync(h->gpad, 0, (size_t)need * 8, h->stream));
-            h->gpad_len = need;
-        }
-        k_pad_rows<<<grid_for(h->n * (i64)h->r, TPB, 16 * kNumSM), TPB, 0, h->stream>>>(h->n, h->r, ld, X, h->gpad);
-        KLAUNCH(h);
-        a.Xg = h->gpad; a.ldx = ld;
-    }
     const i64 hub_cols = phase_hub_cols(h);
     if (hub_cols > 0 && hub_cols < h->n) {
         SDP_CHECK(ensure_row_mid(h, hub_cols));

@@ -64,74 +64,6 @@ __global__ void __launch_bounds__(TPB) k_lz_spmv(const int *__restrict__ rows, i
     if (WITH_ALPHA) grid_sum_finalize<1>(acc, partials, ticket, [&](double (&s)[1]) { alpha_part[0] = s[0]; });
 }
 
-// Class 0 by BUNDLES (option "lanczos_bundle"): the SpMV counterpart of k_rows_bundle (gradient.cu).  A warp takes 8
-// CONSECUTIVE short rows (<= 32 nonzeros each: a contiguous CSR span of <= 256 entries); every lane loads entries
-// p0 + lane + 32 m of idx and S (coalesced), issues its <= 8 gathers of v together, leaves the products in the warp's slice
-// of shared memory, and the 4 lanes of a row add them up in the order of k_lz_spmv (position p of a row goes to lane p % 4,
-// ascending; then the same xor shuffles).  Two exposed round trips per 8 rows (pattern, gathers) instead of four to six per
-// row; the ptr values of the next bundle are loaded one bundle ahead.  rows [r_lo, r_hi) = owned part of the class-0 range.
-constexpr int kLzBundleRows = 8;   // = 32 / 4 lanes per row
-template <bool WITH_ALPHA>
-__global__ void __launch_bounds__(TPB, 4) k_lz_spmv_bundle(i64 r_lo, i64 r_hi, const int *__restrict__ ptr, const int *__restrict__ idx,
-                                                           const double *__restrict__ S, const double *__restrict__ v,
-                                                           double *__restrict__ w, const double *__restrict__ stop, double *partials,
-                                                           unsigned *ticket, double *alpha_part) {
-    if (stop[0] != 0.0) return;
-    __shared__ double sp_all[(TPB / 32) * kLzBundleRows * 32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = lane >> 2, lg = lane & 3;
-    double *sp = sp_all + wib * (kLzBundleRows * 32);
-    const i64 n_bundles = (r_hi - r_lo + kLzBundleRows - 1) / kLzBundleRows;
-    const i64 n_warps = (i64)gridDim.x * (TPB / 32);
-    double acc[1] = {0.0};
-    auto load_ptr = [&](i64 bb) -> int {
-        if (bb >= n_bundles) return 0;
-        const i64 i0 = r_lo + bb * kLzBundleRows;
-        const i64 nrow = (r_hi - i0 < kLzBundleRows) ? (r_hi - i0) : kLzBundleRows;
-        return __ldg(ptr + i0 + (lane < nrow ? lane : nrow));
-    };
-    i64 b = (i64)blockIdx.x * (TPB / 32) + wib;
-    int myp = load_ptr(b);
-    while (b < n_bundles) {   // warp-uniform
-        const i64 i0 = r_lo + b * kLzBundleRows;
-        const int nrow = (int)((r_hi - i0 < kLzBundleRows) ? (r_hi - i0) : kLzBundleRows);
-        const int p0 = __shfl_sync(0xffffffffu, myp, 0);
-        const int pR = __shfl_sync(0xffffffffu, myp, kLzBundleRows);
-        const int o = __shfl_sync(0xffffffffu, myp, g) - p0;
-        const int e = __shfl_sync(0xffffffffu, myp, g + 1) - p0;
-        int c[kLzBundleRows];
-        double s[kLzBundleRows], x[kLzBundleRows];
-#pragma unroll
-        for (int m = 0; m < kLzBundleRows; m++) {
-            const int k = p0 + lane + 32 * m;
-            c[m] = k < pR ? __ldg(idx + k) : 0;
-            s[m] = k < pR ? __ldg(S + k) : 0.0;
-        }
-        const int mypN = load_ptr(b + n_warps);
-#pragma unroll
-        for (int m = 0; m < kLzBundleRows; m++) x[m] = __ldg(v + c[m]);   // positions past the span read v[0] (times 0, never stored)
-#pragma unroll
-        for (int m = 0; m < kLzBundleRows; m++) {
-            const int k = p0 + lane + 32 * m;
-            if (k < pR) sp[lane + 32 * m] = s[m] * x[m];
-        }
-        __syncwarp();
-        double t = 0.0;
-        for (int k = o + lg; k < e; k += 4) t += sp[k];
-        t += __shfl_xor_sync(0xffffffffu, t, 2);
-        t += __shfl_xor_sync(0xffffffffu, t, 1);
-        if (lg == 0 && g < nrow) {
-            const i64 i = i0 + g;
-            w[i] = t;
-            if (WITH_ALPHA) acc[0] += t * v[i];
-        }
-        __syncwarp();   // the products are consumed before the next bundle overwrites them
-        myp = mypN;
-        b += n_warps;
-    }
-    if (WITH_ALPHA) grid_sum_finalize<1>(acc, partials, ticket, [&](double (&sv)[1]) { alpha_part[0] = sv[0]; });
-}
-
 __global__ void k_lz_alpha_sum(const double *__restrict__ parts, int nparts, const double *__restrict__ stop, double *alpha_out) {
     if (stop[0] != 0.0) return;
     double a = 0.0;
@@ -352,13 +284,7 @@ static int32_t lz_apply(sdplrp_handle *h, const double *v, double *w, const doub
             if (nr <= 0) continue;
             const int *rows = cls.list[c];
 #define LZ_SPMV(L, A) k_lz_spmv<L, A><<<grid_for(nr, TPB / L, 16 * kNumSM), TPB, 0, st>>>(rows, nr, h->full_ptr, h->full_idx, h->S, v, w, stop, h->partials, h->ticket, parts + c)
-            i64 c0 = 0, n0 = 0;
-            if (c == 0 && h->lanczos_bundle && grad_class0_range(h, &c0, &n0)) {
-                const int gb = grid_for((n0 + kLzBundleRows - 1) / kLzBundleRows, TPB / 32, 16 * kNumSM);
-                if (has_lr) k_lz_spmv_bundle<false><<<gb, TPB, 0, st>>>(c0, c0 + n0, h->full_ptr, h->full_idx, h->S, v, w, stop, h->partials, h->ticket, parts);
-                else k_lz_spmv_bundle<true><<<gb, TPB, 0, st>>>(c0, c0 + n0, h->full_ptr, h->full_idx, h->S, v, w, stop, h->partials, h->ticket, parts);
-            }
-            else if (c == 0) { if (has_lr) LZ_SPMV(4, false); else LZ_SPMV(4, true); }
+            if (c == 0) { if (has_lr) LZ_SPMV(4, false); else LZ_SPMV(4, true); }
             else if (c == 1) { if (has_lr) LZ_SPMV(32, false); else LZ_SPMV(32, true); }
             else { if (has_lr) LZ_SPMV(256, false); else LZ_SPMV(256, true); }
 #undef LZ_SPMV
@@ -413,8 +339,6 @@ static int32_t lz_run_dist(sdplrp_handle *h, i64 q, const double *v0_host, uint6
         if (e != cudaSuccess) { cudaFree(d_rng); h->err = std::string("lanczos: ") + cudaGetErrorString(e); return SDPLRP_ERR_CUDA; }
     }
     cudaFree(d_rng);
-    i64 c0_first = 0, c0_count = 0;
-    const bool bundle0 = h->nA > 0 && h->lanczos_bundle && grad_class0_range(h, &c0_first, &c0_count);
     CUDA_TRY(h, cudaMemsetAsync(ab, 0, (size_t)(2 * q) * sizeof(double), st));
     CUDA_TRY(h, cudaMemsetAsync(stop, 0, sizeof(double), st));
     CUDA_TRY(h, cudaMemsetAsync(vp, 0, (size_t)n * sizeof(double), st));
@@ -438,13 +362,7 @@ static int32_t lz_run_dist(sdplrp_handle *h, i64 q, const double *v0_host, uint6
                 const int *rows = cls.list[c] ? cls.list[c] + rng[2 * c] : nullptr;
                 const i64 off = cls.list[c] ? 0 : rng[2 * c];
 #define LZ_SPMV(L, A) k_lz_spmv<L, A><<<grid_for(nr, TPB / L, 16 * kNumSM), TPB, 0, st>>>(rows, nr, h->full_ptr, h->full_idx, h->S, v, w, stop, h->partials, h->ticket, parts + c, off)
-                if (c == 0 && bundle0) {
-                    const i64 b_lo = std::max<i64>(c0_first, lo), b_hi = std::max<i64>(b_lo, std::min<i64>(c0_first + c0_count, hi));
-                    const int gb = grid_for(std::max<i64>(1, (b_hi - b_lo + kLzBundleRows - 1) / kLzBundleRows), TPB / 32, 16 * kNumSM);
-                    if (has_lr) k_lz_spmv_bundle<false><<<gb, TPB, 0, st>>>(b_lo, b_hi, h->full_ptr, h->full_idx, h->S, v, w, stop, h->partials, h->ticket, parts);
-                    else k_lz_spmv_bundle<true><<<gb, TPB, 0, st>>>(b_lo, b_hi, h->full_ptr, h->full_idx, h->S, v, w, stop, h->partials, h->ticket, parts);
-                }
-                else if (c == 0) { if (has_lr) LZ_SPMV(4, false); else LZ_SPMV(4, true); }
+                if (c == 0) { if (has_lr) LZ_SPMV(4, false); else LZ_SPMV(4, true); }
                 else if (c == 1) { if (has_lr) LZ_SPMV(32, false); else LZ_SPMV(32, true); }
                 else { if (has_lr) LZ_SPMV(256, false); else LZ_SPMV(256, true); }
 #undef LZ_SPMV

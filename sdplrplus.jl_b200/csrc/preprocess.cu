@@ -520,7 +520,7 @@ void tile_free(TileLayout &t) {
 }
 
 // chunk lists of the rows that do not fit one tile of the async-copy SpMM
-int32_t tile_build(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, TileLayout &t, int chunk = kTileChunk) {
+int32_t tile_build(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, TileLayout &t, int chunk) {
     cudaStream_t st = h->stream;
     const int GS = 8 * kNumSM;
     int32_t rc = SDPLRP_OK;
@@ -553,11 +553,9 @@ int32_t tile_build(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, TileLayout
 
 void pre_free(sdplrp_handle *h) {
     gather_plan_free(h->full_plan);
-    tile_free(h->full_tile); tile_free(h->dyn_tile); tile_free(h->full_long); tile_free(h->dyn_long);
+    tile_free(h->full_long); tile_free(h->dyn_long);
     dev_free(&h->tile_scratch); h->tile_scratch_len = 0;
     dev_free(&h->row_mid); h->row_mid_cols = -1;
-    dev_free(&h->gpad); h->gpad_len = 0;
-    h->c0_checked = nullptr; h->c0_contig = false;
     dev_free(&h->triu_colptr); dev_free(&h->triu_rowval);
     if (h->full_ptr == h->ref_full_ptr) { h->full_ptr = nullptr; h->full_idx = nullptr; }  // aliases when not relabeled
     dev_free(&h->full_ptr); dev_free(&h->full_idx); dev_free(&h->ref_full_ptr); dev_free(&h->ref_full_idx);
@@ -892,8 +890,6 @@ int32_t pre_build(sdplrp_handle *h, i64 n, i64 m, i64 nA, const int64_t *mat_off
     // ---- row bins of both patterns (sparse x dense kernels) -----------------------
     SDP_CHECK(build_classes(h, tmp, n, h->full_ptr, h->full_cls));
     SDP_CHECK(build_classes(h, tmp, n, h->dynrow_ptr, h->dyn_cls));
-    SDP_CHECK(tile_build(h, tmp, n, h->full_ptr, h->full_tile));
-    SDP_CHECK(tile_build(h, tmp, n, h->dynrow_ptr, h->dyn_tile));
     // rows of the third class (> kRowWarpMax nonzeros) cut into chunks of kRowWarpMax for the register kernels
     SDP_CHECK(tile_build(h, tmp, n, h->full_ptr, h->full_long, kRowWarpMax));
     SDP_CHECK(tile_build(h, tmp, n, h->dynrow_ptr, h->dyn_long, kRowWarpMax));

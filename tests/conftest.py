@@ -26,30 +26,17 @@ def oracle_mod():
     return pyoracle
 
 
-# kernel configurations every GPU parity test runs under: the product default (auto relabeling,
-# async-copy tile SpMM), forced hub-first relabeling (exercises every permuting copy on the small
-# regular test graphs too), and the alternative kernels (async-copy tile-stream SpMM, literal vector two-loop)
-# "phases": the two-phase (hub | tail columns) gather pass with a 5-column hub prefix, so that both phases and the
-# accumulate-with-dots epilogue are non-trivial on the small test graphs
-GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "tile": {"relabel": 1, "spmm_kernel": 1, "lbfgs_kernel": 0},
+# kernel configurations every GPU parity test runs under: the product default (auto relabeling), forced hub-first relabeling
+# (exercises every permuting copy on the small regular test graphs too), the literal vector two-loop, the two-phase (hub |
+# tail columns) gather pass with a 5-column hub prefix (both phases and the accumulate-with-dots epilogue are non-trivial on
+# the small graphs; the multi-GPU overlap runs on the same machinery), and the asynchronous tile pipeline of gather.cu
+# (cp.async.bulk and cp.async row gathers; small tiles so that chunked long rows, split rows and multi-pass tiles all occur)
+GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "literal": {"relabel": 1, "lbfgs_kernel": 0},
                "phases": {"relabel": 1, "spmm_phases": 5},
-               # experimental options: written without GPU time left, so they are NOT part of the default GPU run; they join it
-               # with SDPLRP_TEST_EXPERIMENTAL=1 (scripts/r2_first_call.sh) until they have been seen green on a B200
-               "prefetch": {"relabel": 1, "spmm_prefetch": 1}, "prefetch4": {"spmm_prefetch": 1, "spmm_unroll": 4},
-               "prefetch_pad": {"relabel": 1, "spmm_prefetch": 1, "spmm_pad": 1},
-               "bundle": {"relabel": 1, "spmm_prefetch": 2}, "bundle4_pad": {"spmm_prefetch": 2, "spmm_unroll": 4, "spmm_pad": 1},
-               "batched": {"relabel": 1, "spmm_prefetch": 3}, "batched4": {"spmm_prefetch": 3, "spmm_unroll": 4},
-               "prefetch_phases": {"relabel": 1, "spmm_prefetch": 1, "spmm_phases": 5},
-               "lanczos_bundle": {"relabel": 1, "lanczos_bundle": 1},
-               # asynchronous tile pipeline of the gather pass (gather.cu): bulk-copy and cp.async row gathers; small tiles so
-               # that chunked long rows, split rows and multi-pass tiles all occur on the small test graphs
                "gather_bulk": {"relabel": 1, "gather_mode": 1, "gather_tile": 16},
                "gather_async": {"gather_mode": 2},
                "gather_async_small": {"relabel": 1, "gather_mode": 2, "gather_tile": 24, "gather_stages": 3, "gather_hints": 1}}
-EXPERIMENTAL_CONFIGS = ["prefetch", "prefetch4", "prefetch_pad", "bundle", "bundle4_pad", "batched", "batched4", "prefetch_phases",
-                        "lanczos_bundle"]
-GPU_CONFIG_PARAMS = ["default", "relabel", "tile", "phases", "gather_bulk", "gather_async", "gather_async_small"] + (
-    EXPERIMENTAL_CONFIGS if os.environ.get("SDPLRP_TEST_EXPERIMENTAL", "0") not in ("", "0") else [])
+GPU_CONFIG_PARAMS = list(GPU_CONFIGS)
 
 
 @pytest.fixture(scope="session")

@@ -595,8 +595,79 @@ def test_c5_full_size_properties(sp, gpu_handle_factory):
         assert rel.max() <= 1e-9, (name, rel.max())
 
 
-@pytest.mark.skipif(os.environ.get("SDPLRP_TEST_EXPERIMENTAL", "0") in ("", "0"),
-                    reason="sdplrp_preprocess_device was written without GPU access: joins the default run once seen green on a B200")
+def test_c5_against_the_oracle(sp, oracle_mod, gpu_handle_factory):
+    """BASELINE config C5 at its FULL size against the CPU restatement of the reference (the bar of test/coreop.jl:58-72 at
+    n = 10^7): the nine preprocessing maps bit for bit, f!/g! (AL value, objective, both norms, the whole residual vector)
+    to 1e-10, then two FREE-RUNNING inner iterations (own direction, own step size on each side) to 1e-10."""
+    import torch
+    n, edges, r = 10_000_000, 80_000_000, 10
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~60 GB of device memory")
+    asm, b, normC, E = sp.problems.powerlaw_maxcut_assembled(n, edges, 42)
+    torch.cuda.synchronize(); torch.cuda.empty_cache()
+
+    class D:
+        pass
+    data = D(); data.n, data.m, data.b = n, n, b
+    data.constraint_types = np.zeros(n, dtype=bool); data.has_inequalities = False
+    oracle_mod.load().orc_set_threads(max(1, len(os.sched_getaffinity(0))))
+    oe = oracle_mod.OracleEngine(data, asm=asm)
+    ge = sp.B200Engine(data, handle=gpu_handle_factory("default"), asm=asm)
+    mo = oe.o.pattern_export()
+    mg = ge.h.pattern_export()
+    for k in MAP_KEYS:
+        assert np.array_equal(mg[k], mo[k]), f"preprocessing map {k} differs at n = 10^7"
+    del mo, mg, asm
+    Rt0 = 2.0 * np.random.default_rng(0).random((n, r)) - 1.0
+    lam0 = np.zeros(n)
+    for e in (ge, oe):
+        e.init_vars(r, Rt0, lam0, 2.0, 4)
+    del Rt0
+    tol = 1e-10
+    fg_g, fg_o = ge.fg(), oe.fg()          # (L, obj, ||G||^2, ||pvio||^2)
+    for a, c, what in zip(fg_g, fg_o, ("L", "obj", "gnorm2", "pnorm2")):
+        assert abs(a - c) <= tol * max(1.0, abs(c)), (what, a, c)
+    raw_g, raw_o = ge.get_pvio_raw(), oe.get_pvio_raw()
+    assert float(np.abs(raw_g - raw_o).max()) <= tol * max(1.0, float(np.abs(raw_o).max()))
+    for it in range(2):
+        out_g = sp.solver.run_inner_iterations(ge, 1)
+        out_o = sp.solver.run_inner_iterations(oe, 1)
+        for a, c, what in zip(out_g, out_o, ("L", "obj", "gnorm2", "pnorm2", "alpha")):
+            assert abs(a - c) <= tol * max(1.0, abs(c)), (it, what, a, c)
+    raw_g, raw_o = ge.get_pvio_raw(), oe.get_pvio_raw()
+    assert float(np.abs(raw_g - raw_o).max()) <= tol * max(1.0, float(np.abs(raw_o).max()))
+    ge.close()
+
+
+def test_cr_recurrence_drift_over_a_long_major_iteration(sp, gpu_handle_factory):
+    """The gradient of the hot loop uses CR = C*R advanced by the recurrence CR += alpha*CD, where the reference recomputes
+    R*S from scratch every iteration (src/coreop.jl:305-317).  After 1000 inner iterations WITHOUT a rebuild the recurrence
+    must still equal C*R computed from the current R: ||CR - C*R||_F <= 1e-11 ||C*R||_F (and the objective slot, which
+    rides on the same recurrence, 1e-11 relative)."""
+    n, edges, r = 200_000, 1_600_000, 10
+    asm, b, normC, E = sp.problems.powerlaw_maxcut_assembled(n, edges, 11)
+
+    class D:
+        pass
+    data = D(); data.n, data.m, data.b = n, n, b
+    data.constraint_types = np.zeros(n, dtype=bool); data.has_inequalities = False
+    h = gpu_handle_factory("default")
+    eng = sp.B200Engine(data, handle=h, asm=asm)
+    eng.init_vars(r, 2.0 * np.random.default_rng(3).random((n, r)) - 1.0, np.zeros(n), 2.0, 4)
+    eng.fg()
+    sp.solver.run_inner_iterations(eng, 1000, native=True)
+    CR_rec = h.download_mat(sp._lib.MAT_CR)
+    obj_rec = eng.get_pvio_raw()[-1]
+    eng.f()                                   # rebuilds CR = C*R from the current R
+    CR_new = h.download_mat(sp._lib.MAT_CR)
+    obj_new = eng.get_pvio_raw()[-1]
+    err = float(np.linalg.norm(CR_rec - CR_new)) / max(float(np.linalg.norm(CR_new)), 1e-300)
+    assert err <= 1e-11, err
+    assert abs(obj_rec - obj_new) <= 1e-11 * max(1.0, abs(obj_new))
+    h.close()
+
+
 def test_preprocess_device_gives_the_same_maps(sp, gpu_handle_factory):
     """f2 (direct device construction): triplets that stay on the GPU must preprocess to the maps of the host path, bit for bit."""
     n, edges = 20000, 160000

@@ -111,37 +111,52 @@ def algorithmic_bytes(n, m, r, nnzT, nnzF, Ec, h, rows_local):
 def generate(sp, n, edges, seed, keep_on_device=False):
     """The C5 problem in the ABI's triplet form.  With several ranks, rank 0 generates and broadcasts: torch's CUDA
     generator is reproducible per device index only (rank 1 draws a different graph from the same seed), and every rank
-    must preprocess the SAME problem -- the library replicates the pattern and partitions its rows."""
+    must be handed the SAME problem (SPMD contract of the library; it keeps the rows it owns).  keep_on_device: the triplets
+    stay in device memory (the broadcast lands there anyway) and go to sdplrp_preprocess_device on every rank -- no
+    4.4 GB D2H + H2D round trip per rank."""
     import torch
     import torch.distributed as dist
     t0 = time.perf_counter()
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     root = (not multi) or dist.get_rank() == 0
+    on_gpu = torch.cuda.is_available() and (not multi or dist.get_backend() == "nccl")
+    keep = bool(keep_on_device and on_gpu)
     if root:
-        asm, b, normC, E = sp.problems.powerlaw_maxcut_assembled(n, edges, seed, keep_on_device=keep_on_device and not multi)
+        asm, b, normC, E = sp.problems.powerlaw_maxcut_assembled(n, edges, seed, keep_on_device=keep)
     if multi:
         from sdplrplus.jl_b200.types import AssembledSparse
         dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
         meta = torch.zeros(3, dtype=torch.float64, device=dev)
         if root:
-            meta.copy_(torch.tensor([float(asm.I.size), float(normC), float(E)], dtype=torch.float64))
+            nnz_root = int(asm.device_triplets[0].numel()) if keep else int(asm.I.size)
+            meta.copy_(torch.tensor([float(nnz_root), float(normC), float(E)], dtype=torch.float64))
         dist.broadcast(meta, 0)
         nnz, normC, E = int(meta[0].item()), float(meta[1].item()), int(meta[2].item())
-        got = {}
-        for name, dt in (("I", torch.int64), ("J", torch.int64), ("V", torch.float64)):
-            t = torch.from_numpy(getattr(asm, name)).to(dev) if root else torch.empty(nnz, dtype=dt, device=dev)
+        got = []
+        for k, (name, dt) in enumerate((("I", torch.int64), ("J", torch.int64), ("V", torch.float64))):
+            if root:
+                t = asm.device_triplets[k] if keep else torch.from_numpy(getattr(asm, name)).to(dev)
+            else:
+                t = torch.empty(nnz, dtype=dt, device=dev)
             dist.broadcast(t, 0)
             if not root:
-                got[name] = t.cpu().numpy()
+                got.append(t if keep else t.cpu().numpy())
             del t
         if not root:
             nnzC = nnz - n   # n one-entry diagonal constraints, then C (problems.powerlaw_maxcut_assembled)
             mat_off = np.concatenate([np.arange(n + 1, dtype=np.int64), [n + nnzC]]).astype(np.int64)
-            asm = AssembledSparse(n, n, mat_off, got["I"], got["J"], got["V"], np.arange(1, n + 2, dtype=np.int64), [])
+            gids = np.arange(1, n + 2, dtype=np.int64)
+            if keep:
+                empty_i, empty_f = np.empty(0, np.int64), np.empty(0, np.float64)
+                asm = AssembledSparse(n, n, mat_off, empty_i, empty_i, empty_f, gids, [])
+                asm.device_triplets = tuple(got)
+            else:
+                asm = AssembledSparse(n, n, mat_off, got[0], got[1], got[2], gids, [])
             b = np.ones(n)
     if torch.cuda.is_available():
         torch.cuda.synchronize()
-        torch.cuda.empty_cache()
+        if not keep:
+            torch.cuda.empty_cache()
     return asm, b, normC, E, time.perf_counter() - t0
 
 
@@ -246,8 +261,8 @@ def main():
     ap.add_argument("--lanczos", type=int, default=50, help="also time this many Lanczos steps (reported separately; 0 = skip)")
     ap.add_argument("--no-solve", action="store_true", help="skip the time-to-tolerance leg (full solve with the native driver)")
     ap.add_argument("--solve-maxtime", type=float, default=240.0, help="time limit of the time-to-tolerance solve in seconds")
-    ap.add_argument("--device-triplets", action="store_true", help="one GPU: the generator's triplets stay on the device and go to "
-                    "sdplrp_preprocess_device (no 4.4 GB D2H + H2D); affects the setup times only")
+    ap.add_argument("--host-triplets", action="store_true", help="hand the problem to sdplrp_preprocess as HOST triplets (4.4 GB D2H + H2D per "
+                    "rank) instead of keeping the generator's triplets on the device (sdplrp_preprocess_device); affects the setup times only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -286,7 +301,7 @@ def main():
         handle.set_option(key, float(val))
     n, r, h = args.n, args.rank, 4
 
-    asm, b, normC, E, gen_s = generate(sp, n, args.edges, args.seed, keep_on_device=args.device_triplets)
+    asm, b, normC, E, gen_s = generate(sp, n, args.edges, args.seed, keep_on_device=not args.host_triplets)
     data = SimpleData(n, n, b)
     t0 = time.perf_counter()
     eng = sp.B200Engine(data, handle=handle, asm=asm)
@@ -294,6 +309,7 @@ def main():
     nnzT, nnzF, Ec = handle.pattern_sizes()
     pre_h2d = eng.h2d_bytes
     del asm
+    torch.cuda.empty_cache()
     lo, hi = handle.row_range()
 
     R0_t, R0 = pinned_uniform((n, r), 0)
@@ -341,14 +357,15 @@ def main():
     eng.init_vars(r, R0, lam0, 2.0, h)
     eng.fg()
     sp.solver.run_inner_iterations(eng, args.steps, native=native)
-    handle.lib.sdplrp_download_mat(handle._h, sp._lib.MAT_R, Rout_t.numpy().ctypes.data_as(sp._lib._p_f64))
+    handle.download_mat_owned(sp._lib.MAT_R, Rout_t.numpy())   # several GPUs: every rank fetches the rows it owns
     lam_out = eng.get_lambda()
     torch.cuda.synchronize(); spdist.barrier()
     e2e_s = spdist.max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": args.steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": (R0.nbytes + lam0.nbytes) / args.steps + 8.0,
-           "d2h_bytes_per_step": (R0.nbytes + lam0.nbytes) / args.steps + 8.0 * 9,
-           "what": "init_vars (H2D of R0, lambda0 from pinned host memory) + fg + K inner iterations + D2H of R, lambda; wall clock",
+           "h2d_bytes_per_step": (R0.nbytes * (hi - lo) / float(n) + lam0.nbytes) / args.steps + 8.0,
+           "d2h_bytes_per_step": (R0.nbytes * (hi - lo) / float(n) + lam0.nbytes) / args.steps + 8.0 * 9,
+           "what": "per rank: init_vars (H2D of the owned rows of R0 and of lambda0 from pinned host memory) + fg + K inner iterations "
+                   "(host scalars cross every iteration) + D2H of the owned rows of R and of lambda; wall clock, max over ranks",
            "one_time_preprocess_s": preprocess_s, "one_time_preprocess_h2d_bytes": pre_h2d}
 
     # ---- optional Lanczos timing (dual bound), reported beside the headline

@@ -96,11 +96,14 @@ void *sdplrp_stream(sdplrp_handle *h);
  *   "hot_rows"    leading rows of the gathered factor pinned in L2 (evict_last); -1 = sized from L2
  *   "spmm_phases" 0 = one sweep per gather pass (default); 1 = two sweeps, hub columns (an L2-sized prefix of the
  *                 hub-first order) then tail columns; k > 1 = k hub columns.  One GPU, relabelled patterns only (experimental)
- *   "lanczos_dist" 0 = the q-step Lanczos operator is replicated on every rank (default); 1 = rows of S and of the Lanczos
- *                 vectors are divided among the ranks (one all-gather of n doubles + two scalar all-reduces per step).
- *                 Only with world > 1 and without re-orthogonalisation
+ *   "lanczos_dist" several GPUs: 1 = rows of S and of the Lanczos vectors are divided among the ranks (one all-gather of n
+ *                 doubles + two scalar all-reduces per step; default), 0 = the q-step Lanczos operator is replicated on every
+ *                 rank.  Only without re-orthogonalisation
  *   "spmm_unroll" nonzeros per block of the short-row kernels: 8 (default) or 4
  *   "spmm_g0"     1 = lane groups of exactly r/2 lanes per short row (default: 6 rows per warp at r = 10), 0 = next power of two
+ *   "halo"        several GPUs: 1 = every rank keeps the objective pattern of its own rows and the gather pass exchanges only the
+ *                 factor rows that are actually gathered, hub class first, overlapped with the pass (default); 0 = one
+ *                 all-gather of the whole direction per iteration (round-1 path)
  *   "gather_mode" gather pass CD = C*D (gather.cu): 0 = row-binned register kernels, 1 = asynchronous tile pipeline with one
  *                 cp.async.bulk per gathered row, 2 = the same pipeline with 16-byte cp.async row pieces (even ranks <= 64)
  *   "gather_tile", "gather_stages", "gather_warps"  geometry of that pipeline (nonzeros per tile, stages of the
@@ -129,6 +132,26 @@ int32_t sdplrp_preprocess(sdplrp_handle *h, int64_t n, int64_t m, int64_t nA, co
 int32_t sdplrp_preprocess_device(sdplrp_handle *h, int64_t n, int64_t m, int64_t nA, const int64_t *mat_off,
                                  const int64_t *d_I, const int64_t *d_J, const double *d_V,
                                  const int64_t *sparse_global_inds);
+/* ---- structured problem blocks --------------------------------------------------------------------------
+ * The sparse list of sdplrp_preprocess described block by block, in order of appearance (A_1 ... A_m, then C if sparse), and
+ * expanded on the device into the `findnz`-order triplets -- what the reference's problem constructors build one
+ * SparseMatrixCOO at a time (test/problem.jl:16-30, 50-62, 80-92, 100-110).  A block of kind
+ *   TRIPLETS  one matrix, stored entries I, J (1-based), V in findnz order (nnz of them)
+ *   CSC       one matrix as SparseMatrixCSC fields: I = rowval (nnz), J = colptr (n+1), both 1-based, V = nzval
+ *   DIAG      `count` matrices with ONE entry each: matrix k = V[k] * e_p e_p', p = I[k] (I NULL: p = k+1; V NULL: 1.0)
+ *             -- Diag(X) = 1 of MaxCut / cut-norm / minimum bisection
+ *   EDGES     `count` matrices with the two stored entries (I[k], J[k]), (J[k], I[k]), both V[k] (V NULL: 1.0)
+ *             -- X_ij = 0 for every edge of Lovasz theta
+ *   IDENTITY  one matrix sparse(1.0I, n, n) -- the trace constraint
+ * takes the global ids first_gid, first_gid+1, ... (1-based; m+1 for C).  on_device != 0: the arrays are device memory of
+ * the handle's GPU.  Maps, error codes and everything downstream are those of sdplrp_preprocess on the expanded triplets. */
+enum { SDPLRP_BLOCK_TRIPLETS = 0, SDPLRP_BLOCK_CSC = 1, SDPLRP_BLOCK_DIAG = 2, SDPLRP_BLOCK_EDGES = 3, SDPLRP_BLOCK_IDENTITY = 4 };
+typedef struct {
+    int64_t kind, on_device, count, first_gid, nnz;
+    const int64_t *I, *J;
+    const double *V;
+} sdplrp_block;
+int32_t sdplrp_preprocess_blocks(sdplrp_handle *h, int64_t n, int64_t m, int64_t nblocks, const sdplrp_block *blocks);
 int32_t sdplrp_pattern_sizes(sdplrp_handle *h, int64_t *nnzT, int64_t *nnzF, int64_t *Ec);
 /* 1-based, exactly the seven outputs of preprocess_sparsecons */
 int32_t sdplrp_pattern_export(sdplrp_handle *h, int64_t *triu_colptr, int64_t *triu_rowval, int64_t *matptr,
@@ -151,6 +174,12 @@ int32_t sdplrp_get_sigma(sdplrp_handle *h, double *sigma);
 int32_t sdplrp_get_obj(sdplrp_handle *h, double *obj);
 int32_t sdplrp_upload_mat(sdplrp_handle *h, int32_t mat_id, const double *src /* r*n */);
 int32_t sdplrp_download_mat(sdplrp_handle *h, int32_t mat_id, double *dst /* r*n */);
+/* Several GPUs (one process per GPU): the same calls restricted to the rows this rank owns (sdplrp_row_range in the
+ * library's internal order; any vertex may be owned by any rank).  `src` / `dst` are full-size r x n buffers in the
+ * caller's vertex order; only the owned rows are read / written, so a rank moves n*r/world doubles over PCIe.  Rows of
+ * other ranks reach a rank over NVLink when a pass needs them.  One GPU: identical to the calls above. */
+int32_t sdplrp_upload_mat_owned(sdplrp_handle *h, int32_t mat_id, const double *src /* r*n */);
+int32_t sdplrp_download_mat_owned(sdplrp_handle *h, int32_t mat_id, double *dst /* r*n */);
 int32_t sdplrp_upload_vec(sdplrp_handle *h, int32_t vec_id, const double *src, int64_t len);
 int32_t sdplrp_download_vec(sdplrp_handle *h, int32_t vec_id, double *dst, int64_t len);
 

@@ -26,6 +26,15 @@ _p_f64 = C.POINTER(C.c_double)
 _p_u8 = C.POINTER(C.c_uint8)
 _H = C.c_void_p
 
+BLOCK_TRIPLETS, BLOCK_CSC, BLOCK_DIAG, BLOCK_EDGES, BLOCK_IDENTITY = range(5)
+
+
+class Block(C.Structure):
+    """sdplrp_block (include/sdplrp_b200.h): one structured block of the sparse list."""
+    _fields_ = [("kind", C.c_int64), ("on_device", C.c_int64), ("count", C.c_int64), ("first_gid", C.c_int64), ("nnz", C.c_int64),
+                ("I", C.c_void_p), ("J", C.c_void_p), ("V", C.c_void_p)]
+
+
 # name -> argtypes (restype is always int32 unless listed in _SPECIAL)
 _SIGNATURES = {
     "sdplrp_nccl_unique_id": [C.c_void_p],
@@ -35,6 +44,7 @@ _SIGNATURES = {
     "sdplrp_set_option": [_H, C.c_char_p, C.c_double],
     "sdplrp_preprocess": [_H, C.c_int64, C.c_int64, C.c_int64, _p_i64, _p_i64, _p_i64, _p_f64, _p_i64],
     "sdplrp_preprocess_device": [_H, C.c_int64, C.c_int64, C.c_int64, _p_i64, C.c_void_p, C.c_void_p, C.c_void_p, _p_i64],
+    "sdplrp_preprocess_blocks": [_H, C.c_int64, C.c_int64, C.c_int64, C.POINTER(Block)],
     "sdplrp_pattern_sizes": [_H, _p_i64, _p_i64, _p_i64],
     "sdplrp_pattern_export": [_H, _p_i64, _p_i64, _p_i64, _p_i64, _p_f64, _p_f64, _p_i64, _p_i64, _p_i64],
     "sdplrp_add_symlowrank": [_H, C.c_int64, C.c_int64, _p_f64, _p_f64],
@@ -45,6 +55,8 @@ _SIGNATURES = {
     "sdplrp_get_obj": [_H, _p_f64],
     "sdplrp_upload_mat": [_H, C.c_int32, _p_f64],
     "sdplrp_download_mat": [_H, C.c_int32, _p_f64],
+    "sdplrp_upload_mat_owned": [_H, C.c_int32, _p_f64],
+    "sdplrp_download_mat_owned": [_H, C.c_int32, _p_f64],
     "sdplrp_upload_vec": [_H, C.c_int32, _p_f64, C.c_int64],
     "sdplrp_download_vec": [_H, C.c_int32, _p_f64, C.c_int64],
     "sdplrp_A_uu": [_H, C.c_int32, _p_f64],
@@ -229,6 +241,44 @@ class Handle:
         self.n, self.m, self.nA = int(n), int(m), int(nA)
         return rc
 
+    def preprocess_blocks(self, n, m, blocks, allow_asymmetric=False):
+        """sdplrp_preprocess_blocks.  `blocks`: list of dicts {kind, first_gid, count=, I=, J=, V=}; the arrays are numpy arrays
+        (host) or objects with data_ptr() (device tensors: on_device is set).  For BLOCK_CSC: I = rowval, J = colptr."""
+        arr = (Block * len(blocks))()
+        keep = []   # the arrays must outlive the call
+        nA = 0
+        for k, b in enumerate(blocks):
+            kind = int(b["kind"])
+            dev = False
+            ptrs = {}
+            sizes = {}
+            for name, dt in (("I", np.int64), ("J", np.int64), ("V", np.float64)):
+                a = b.get(name)
+                if a is None:
+                    ptrs[name] = None
+                    continue
+                if hasattr(a, "data_ptr"):
+                    dev = True
+                    ptrs[name] = int(a.data_ptr()); sizes[name] = int(a.numel())
+                    keep.append(a)
+                else:
+                    a = np.ascontiguousarray(a, dtype=dt)
+                    keep.append(a)
+                    ptrs[name] = a.ctypes.data; sizes[name] = int(a.size)
+            if kind in (BLOCK_TRIPLETS, BLOCK_CSC):
+                count, nnz = 1, sizes.get("V", 0)
+            elif kind == BLOCK_IDENTITY:
+                count, nnz = 1, 0
+            else:
+                count = int(b["count"]) if "count" in b else sizes.get("I", 0)
+                nnz = 0
+            arr[k] = Block(kind, int(dev), count, int(b["first_gid"]), nnz, ptrs["I"], ptrs["J"], ptrs["V"])
+            nA += count
+        rc = self.lib.sdplrp_preprocess_blocks(self._h, n, m, len(blocks), arr)
+        self._check(rc, allow=(ERR_ASYMMETRIC,) if allow_asymmetric else ())
+        self.n, self.m, self.nA = int(n), int(m), int(nA)
+        return rc
+
     def pattern_sizes(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         self._check(self.lib.sdplrp_pattern_sizes(self._h, C.byref(a), C.byref(b), C.byref(c)))
@@ -291,6 +341,17 @@ class Handle:
         a = np.ascontiguousarray(Rt, dtype=np.float64)
         assert a.size == self.n * self.r, (a.shape, self.n, self.r)
         self._check(self.lib.sdplrp_upload_mat(self._h, mat_id, a.ctypes.data_as(_p_f64)))
+
+    def upload_mat_owned(self, mat_id, Rt):
+        """Several GPUs: only the rows this rank owns are read from the full-size (n, r) array and cross PCIe."""
+        a = np.ascontiguousarray(Rt, dtype=np.float64)
+        assert a.size == self.n * self.r, (a.shape, self.n, self.r)
+        self._check(self.lib.sdplrp_upload_mat_owned(self._h, mat_id, a.ctypes.data_as(_p_f64)))
+
+    def download_mat_owned(self, mat_id, out):
+        """Several GPUs: writes this rank's rows into the caller's full-size (n, r) array `out`."""
+        assert out.flags.c_contiguous and out.dtype == np.float64 and out.size == self.n * self.r
+        self._check(self.lib.sdplrp_download_mat_owned(self._h, mat_id, out.ctypes.data_as(_p_f64)))
 
     def download_mat(self, mat_id):
         """Returns the matrix as a numpy (n, r) C-order array (== Julia r x n column-major)."""

@@ -185,6 +185,8 @@ static void free_problem(sdplrp_handle *h) {
     dev_free(&h->lz_v); dev_free(&h->lz_w); dev_free(&h->lz_vp); dev_free(&h->lz_ab); dev_free(&h->lz_basis);
     h->lz_ab_len = 0; h->lz_basis_len = 0;
     dev_free(&h->stage); h->stage_len = 0;
+    if (h->host_stage) { cudaFreeHost(h->host_stage); h->host_stage = nullptr; h->host_stage_len = 0; }
+    h->own_ref_rows.clear(); h->own_ref_lo = -1;
 }
 
 int32_t sdplrp_destroy(sdplrp_handle *h) {
@@ -265,6 +267,7 @@ static int32_t preprocess_common(sdplrp_handle *h, int64_t n, int64_t m, int64_t
     CUDA_TRY(h, cudaStreamSynchronize(st));
     h->y_obj = 0.0;
     SDP_CHECK(comm_partition(h));
+    SDP_CHECK(halo_build(h));   // multi-GPU: local pattern + halo lists of the gather pass
     return rc;
 }
 
@@ -366,6 +369,7 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
     if (k == "lanczos_dist") { h->lanczos_dist = value > 0 ? 1 : 0; return SDPLRP_OK; }
     if (k == "spmm_unroll") { h->spmm_unroll = (int)value; return SDPLRP_OK; }
     if (k == "spmm_g0") { h->spmm_g0 = (int)value; return SDPLRP_OK; }
+    if (k == "halo") { h->halo_mode = value > 0 ? 1 : 0; return SDPLRP_OK; }
     if (k == "gather_mode") { h->gather_mode = value < 0 ? 0 : (int)value; return SDPLRP_OK; }
     if (k == "gather_tile") { h->gather_tile = (int)value; return SDPLRP_OK; }
     if (k == "gather_stages") { h->gather_stages = (int)value; return SDPLRP_OK; }
@@ -408,6 +412,38 @@ int32_t sdplrp_upload_mat(sdplrp_handle *h, int32_t id, const double *src) {
     if (id == SDPLRP_MAT_G) h->gram_g_valid = false;
     if (id >= SDPLRP_MAT_S0) { h->gram_pairs_valid = false; h->gram_prestored = -1; }
     return SDPLRP_OK;
+}
+
+// several GPUs: this rank's rows only (the other rows of `src` are not read); the matrix is then valid on its owners and the
+// passes that gather across the partition fetch the rest over NVLink.  One GPU: sdplrp_upload_mat.
+int32_t sdplrp_upload_mat_owned(sdplrp_handle *h, int32_t id, const double *src) {
+    REQUIRE_H(h);
+    REQUIRE_RANK(h);
+    if (h->world <= 1) return sdplrp_upload_mat(h, id, src);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(lazy_scratch(h, id));
+    if (id == SDPLRP_MAT_CR || id == SDPLRP_MAT_CD) return fail(h, SDPLRP_ERR_ARG, "upload_mat: CR / CD are download-only");
+    double *p = mat_ptr(h, id);
+    if (!p || !src) return fail(h, SDPLRP_ERR_ARG, "upload_mat_owned: bad id");
+    SDP_CHECK(perm_upload_owned(h, p, src, h->r));
+    comm_mark_partial(h, id);
+    if (id == SDPLRP_MAT_R) { h->CR_valid = false; h->ls_valid = false; }
+    if (id == SDPLRP_MAT_D) { h->CD_valid = false; h->ls_valid = false; }
+    if (id == SDPLRP_MAT_G) h->gram_g_valid = false;
+    if (id >= SDPLRP_MAT_S0) { h->gram_pairs_valid = false; h->gram_prestored = -1; }
+    return SDPLRP_OK;
+}
+
+// several GPUs: writes this rank's rows into `dst` (a full-size r x n buffer; the other rows are left alone)
+int32_t sdplrp_download_mat_owned(sdplrp_handle *h, int32_t id, double *dst) {
+    REQUIRE_H(h);
+    REQUIRE_RANK(h);
+    if (h->world <= 1) return sdplrp_download_mat(h, id, dst);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(lazy_scratch(h, id));
+    double *p = mat_ptr(h, id);
+    if (!p || !dst) return fail(h, SDPLRP_ERR_ARG, "download_mat_owned: bad id");
+    return perm_download_owned(h, p, dst, h->r);
 }
 
 int32_t sdplrp_download_mat(sdplrp_handle *h, int32_t id, double *dst) {
@@ -546,7 +582,8 @@ static bool needs_remote_R_rows(const sdplrp_handle *h) {
 
 // CR = C*R over the owned rows (from scratch); sums6[c][0] = <R,CR> per row class
 static int32_t rebuild_CR(sdplrp_handle *h) {
-    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
+    if (halo_active(h)) SDP_CHECK(halo_begin(h, h->R));   // only the ghost rows of R travel
+    else SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
     SectionScope sc(h, SDPLRP_SEC_SPMM);
     SDP_CHECK(grad_obj_spmm(h, h->R, h->CR, nullptr, h->dscal + SC_SUMS));
     h->CR_valid = true;
@@ -558,7 +595,7 @@ __global__ void k_store_sum3(const double *__restrict__ sums6, double *out) { *o
 // f! (src/coreop.jl:11-31).  With a sparse objective the slot m+1 is <R, C*R>, a by-product
 // of rebuilding CR = C*R (which resets the drift of the CR recurrence once per major iteration).
 static int32_t do_f(sdplrp_handle *h) {
-    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
+    if (!halo_active(h)) SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));   // halo plan: every constraint is a per-row list (own rows only)
     const bool split = h->obj_mat >= 0;
     {
         SectionScope sc(h, SDPLRP_SEC_A_UU);
@@ -650,10 +687,13 @@ int32_t sdplrp_use_gradient_direction(sdplrp_handle *h) {
 int32_t sdplrp_linesearch_coeffs(sdplrp_handle *h, double bq[5]) {
     REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
-    SDP_CHECK(comm_require_full(h, SDPLRP_MAT_D));
-    if (needs_remote_R_rows(h)) SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
     const bool split = h->obj_mat >= 0;
     if (split && !h->CR_valid) SDP_CHECK(rebuild_CR(h));
+    // several GPUs: the halo exchange of D starts here and runs on the comm stream under the constraint pass and the
+    // [own | hub] half of the gather pass; without a halo plan the whole of D is all-gathered first
+    if (halo_active(h)) SDP_CHECK(halo_begin(h, h->D));
+    else SDP_CHECK(comm_require_full(h, SDPLRP_MAT_D));
+    if (needs_remote_R_rows(h)) SDP_CHECK(comm_require_full(h, SDPLRP_MAT_R));
     {
         SectionScope sc(h, SDPLRP_SEC_LS_PASS);
         SDP_CHECK(aop_linesearch(h, split));  // constraints: sampled dots (A_RD already x2, A_DD)

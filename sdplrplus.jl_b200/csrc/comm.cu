@@ -25,6 +25,9 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, void *) = nullptr;   // optional (NCCL >= 2.18)
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -45,6 +48,9 @@ bool nccl_bind() {
     BIND(AllReduce, "ncclAllReduce");
     BIND(Broadcast, "ncclBroadcast");
     BIND(AllGather, "ncclAllGather");
+    BIND(Send, "ncclSend");
+    BIND(Recv, "ncclRecv");
+    *(void **)(&g_nccl.CommSplit) = dlsym(lib, "ncclCommSplit");
     BIND(GroupStart, "ncclGroupStart");
     BIND(GroupEnd, "ncclGroupEnd");
     BIND(GetErrorString, "ncclGetErrorString");
@@ -59,6 +65,8 @@ bool nccl_bind() {
 #define ncclAllReduce g_nccl.AllReduce
 #define ncclBroadcast g_nccl.Broadcast
 #define ncclAllGather g_nccl.AllGather
+#define ncclSend g_nccl.Send
+#define ncclRecv g_nccl.Recv
 #define ncclGroupStart g_nccl.GroupStart
 #define ncclGroupEnd g_nccl.GroupEnd
 #define ncclGetErrorString g_nccl.GetErrorString
@@ -91,10 +99,23 @@ int32_t comm_init(sdplrp_handle *h, const void *nccl_id) {
     ncclComm_t comm;
     NCCL_TRY(h, ncclCommInitRank(&comm, h->world, id, h->rank));
     h->nccl = (void *)comm;
+    // the halo exchange of the gather pass runs on its own stream, concurrently with kernels (and scalar all-reduces) of the
+    // compute stream: it gets its own communicator so that the two never serialise on one another
+    if (g_nccl.CommSplit) {
+        ncclComm_t c2 = nullptr;
+        if (g_nccl.CommSplit(comm, 0, h->rank, &c2, nullptr) == ncclSuccess && c2) h->nccl_halo = (void *)c2;
+    }
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_class[k], cudaEventDisableTiming));
     return SDPLRP_OK;
 }
 
 void comm_destroy(sdplrp_handle *h) {
+    if (h->nccl_halo) { ncclCommDestroy((ncclComm_t)h->nccl_halo); h->nccl_halo = nullptr; }
+    if (h->ev_pack) { cudaEventDestroy(h->ev_pack); h->ev_pack = nullptr; }
+    for (int k = 0; k < 2; k++) if (h->ev_class[k]) { cudaEventDestroy(h->ev_class[k]); h->ev_class[k] = nullptr; }
+    if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); h->comm_stream = nullptr; }
     if (h->nccl) {
         ncclCommDestroy((ncclComm_t)h->nccl);
         h->nccl = nullptr;
@@ -294,5 +315,71 @@ int32_t comm_step_R(sdplrp_handle *h, double alpha) {
     // owned rows only: the rows of other ranks are fetched lazily (comm_require_full) by the passes that need them
     SDP_CHECK(lb_axpy(h, alpha, h->D, h->R));
     comm_mark_partial(h, SDPLRP_MAT_R);
+    return SDPLRP_OK;
+}
+
+// every rank's `bytes` bytes to every rank (recv = world x bytes, rank order)
+int32_t comm_allgather_bytes(sdplrp_handle *h, const void *send, void *recv, size_t bytes) {
+    if (h->world <= 1) {
+        if (recv != send) CUDA_TRY(h, cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        return SDPLRP_OK;
+    }
+    NCCL_TRY(h, ncclAllGather(send, recv, bytes, ncclChar, (ncclComm_t)h->nccl, h->stream));
+    return SDPLRP_OK;
+}
+
+// ---- halo exchange of the gather pass ---------------------------------------------------------------------------------
+namespace {
+// out[e] = X[(lo + rows[e / r]) * r + e % r]: the rows the peers gather, in destination order
+__global__ void k_pack_rows(i64 n_rows, int r, const int *__restrict__ rows, const double *__restrict__ Xown, double *__restrict__ out) {
+    const i64 total = n_rows * r;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 q = e / r;
+        const int c = (int)(e - q * r);
+        out[e] = Xown[(size_t)rows[q] * r + c];
+    }
+}
+}  // namespace
+
+bool halo_active(const sdplrp_handle *h) { return h->world > 1 && h->halo.active && h->halo_mode != 0; }
+
+// pack both classes on the compute stream, then (comm stream) exchange the hub class and the tail class one after the other
+int32_t halo_begin(sdplrp_handle *h, const double *X) {
+    HaloPlan &p = h->halo;
+    const int r = h->r, P = h->world;
+    const i64 need_send = (p.n_send[0] + p.n_send[1]) * (i64)r, need_ghost = (p.n_ghost[0] + p.n_ghost[1]) * (i64)r;
+    if (p.sendbuf_len < need_send) { SDP_CHECK(dev_alloc(h, &p.sendbuf, need_send)); p.sendbuf_len = need_send; }
+    if (p.ghost_len < need_ghost) { SDP_CHECK(dev_alloc(h, &p.ghost, need_ghost)); p.ghost_len = need_ghost; }
+    const double *Xown = X + (size_t)h->row_lo * r;
+    for (int k = 0; k < 2; k++) {
+        if (p.n_send[k] <= 0) continue;
+        double *out = p.sendbuf + (size_t)(k == 0 ? 0 : p.n_send[0]) * r;
+        k_pack_rows<<<grid_for(p.n_send[k] * r, 256, 8 * kNumSM), 256, 0, h->stream>>>(p.n_send[k], r, p.send_rows[k], Xown, out);
+        KLAUNCH(h);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(h->ev_pack, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_pack, 0));
+    ncclComm_t comm = (ncclComm_t)(h->nccl_halo ? h->nccl_halo : h->nccl);
+    for (int k = 0; k < 2; k++) {
+        const double *sb = p.sendbuf + (size_t)(k == 0 ? 0 : p.n_send[0]) * r;
+        double *gb = p.ghost + (size_t)(k == 0 ? 0 : p.n_ghost[0]) * r;
+        NCCL_TRY(h, ncclGroupStart());
+        for (int q = 0; q < P; q++) {
+            if (q == h->rank) continue;
+            const i64 so = p.send_off[k][(size_t)q], sc = p.send_off[k][(size_t)q + 1] - so;
+            const i64 ro = p.recv_off[k][(size_t)q], rc = p.recv_off[k][(size_t)q + 1] - ro;
+            if (sc > 0) NCCL_TRY(h, ncclSend(sb + (size_t)so * r, (size_t)sc * r, ncclDouble, q, comm, h->comm_stream));
+            if (rc > 0) NCCL_TRY(h, ncclRecv(gb + (size_t)ro * r, (size_t)rc * r, ncclDouble, q, comm, h->comm_stream));
+        }
+        NCCL_TRY(h, ncclGroupEnd());
+        CUDA_TRY(h, cudaEventRecord(h->ev_class[k], h->comm_stream));
+    }
+    return SDPLRP_OK;
+}
+
+int32_t halo_wait(sdplrp_handle *h, int klass) {
+    SectionScope sc(h, SDPLRP_SEC_COMM);   // what the compute stream actually waits = the exposed part of the exchange
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_class[klass], 0));
     return SDPLRP_OK;
 }

@@ -49,6 +49,24 @@ struct GatherPlan {
     int T = 0;
 };
 
+// Multi-GPU gather pass (world > 1, dealt equal blocks, sparse objective, constraints in per-row lists): the LOCAL view of the
+// objective pattern -- only the owned rows, columns renumbered to [own rows | hub ghosts | tail ghosts] -- and the lists of
+// the halo exchange that replaces the all-gather of the gathered factor (preprocess.cu: halo_build, comm.cu: halo_*).
+struct HaloPlan {
+    bool active = false;
+    long long nloc = 0, lnnz = 0;
+    long long n_ghost[2] = {0, 0};       // ghost rows per class: 0 = hub part of the other ranks' blocks, 1 = tail part
+    long long n_send[2] = {0, 0};        // rows this rank packs per class (a row goes once to every peer that gathers it)
+    int *lptr = nullptr, *lmid = nullptr, *lidx = nullptr;   // nloc+1, nloc, lnnz: row i = [lptr[i], lmid[i]) own + hub-ghost columns,
+    double *lval = nullptr;                                   //                   [lmid[i], lptr[i+1]) tail-ghost columns
+    RowClasses cls;                      // row bins of the local rows
+    TileLayout longs;                    // their long rows in chunks
+    int *send_rows[2] = {nullptr, nullptr};                   // local row ids to pack, grouped by destination rank
+    std::vector<long long> send_off[2], recv_off[2];          // world+1 row offsets per class
+    double *sendbuf = nullptr, *ghost = nullptr;              // (n_send[0]+n_send[1]) x r and (n_ghost[0]+n_ghost[1]) x r
+    long long sendbuf_len = 0, ghost_len = 0;
+};
+
 struct LowRank {
     i64 gid;     // 0-based global slot
     i64 s;
@@ -105,6 +123,10 @@ struct sdplrp_handle {
     int *i2r = nullptr, *r2i = nullptr;                  // nnzF: internal full slot <-> reference full slot
     int *full_ptr = nullptr, *full_idx = nullptr;        // n+1, nnzF   the symmetric pattern as CSR in INTERNAL labels
     double *S = nullptr;                                 // nnzF  sparse_S.nzval (internal slot order)
+    std::vector<int> own_ref_rows;                       // host: reference vertex of every owned internal row (perm.cu, owned-row transfers)
+    i64 own_ref_lo = -1;
+    double *host_stage = nullptr;                        // pinned host staging of the owned-row transfers
+    i64 host_stage_len = 0;
     double *stage = nullptr;                             // n x r staging buffer of the permuting copies
     i64 stage_len = 0;
     i64 l2_persist_bytes = 0;                            // cudaLimitPersistingL2CacheSize set at creation
@@ -113,7 +135,14 @@ struct sdplrp_handle {
     int spmm_g0 = 1;                                     // class-0 lane groups of exactly r/2 lanes (0: next power of two)
     int spmm_phases = 0;                                 // 0 = one sweep per gather pass (default); 1 = hub | tail two-phase pass with an
                                                          // L2-sized hub prefix; > 1 = that many hub columns (gradient.cu, grad_obj_spmm)
-    int lanczos_dist = 0;                                // 1 = row-partitioned q-step Lanczos on world > 1 (experimental, lanczos.cu: lz_run_dist)
+    int lanczos_dist = 1;                                // world > 1: 1 = row-partitioned q-step Lanczos (default; measured identical to the replicated
+                                                         // recurrence on 2 GPUs and 2.5x faster), 0 = replicated operator (lanczos.cu: lz_run_dist)
+    // multi-GPU halo exchange of the gather pass (preprocess.cu: halo_build, comm.cu)
+    int halo_mode = 1;                                   // 0 = all-gather of the whole factor (round-1 path), 1 = halo exchange overlapped with the pass
+    HaloPlan halo;
+    void *nccl_halo = nullptr;                           // second communicator (ncclCommSplit) for the exchange on comm_stream
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_pack = nullptr, ev_class[2] = {nullptr, nullptr};
     // asynchronous tile pipeline of the gather pass (gather.cu)
     int gather_mode = 0;                                 // 0 = register kernels of gradient.cu, 1 = cp.async.bulk row gathers, 2 = 16-byte cp.async row gathers
     int gather_tile = 0, gather_stages = 0, gather_warps = 0;  // 0 = automatic (gather_geometry)
@@ -408,11 +437,22 @@ int32_t comm_reduce_scalars(sdplrp_handle *h, int slot, int count);
 int32_t comm_check_same(sdplrp_handle *h, unsigned long long value, const char *what);  // error unless all ranks pass the same value
 int32_t comm_reduce_ptr(sdplrp_handle *h, double *p, int count);
 int32_t comm_step_R(sdplrp_handle *h, double alpha);
+int32_t comm_allgather_bytes(sdplrp_handle *h, const void *send, void *recv, size_t bytes);       // recv = world x bytes
+// halo exchange (comm.cu): pack the rows the peers gather from X (n x r, internal labels, own block valid), start the two
+// class exchanges on the comm stream; halo_wait makes the compute stream wait for one class (its exposed time is the
+// "comm" section)
+int32_t halo_build(sdplrp_handle *h);       // preprocess.cu
+void halo_free(sdplrp_handle *h);
+bool halo_active(const sdplrp_handle *h);
+int32_t halo_begin(sdplrp_handle *h, const double *X);
+int32_t halo_wait(sdplrp_handle *h, int klass);
 
 // reference order <-> internal order (perm.cu)
 int32_t perm_stage(sdplrp_handle *h, i64 len);
 int32_t perm_upload(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 ncols, bool row_major);
 int32_t perm_download(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 ncols, bool row_major);
+int32_t perm_upload_owned(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 ncols);      // rows [row_lo, row_hi) only
+int32_t perm_download_owned(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 ncols);
 int32_t perm_device(sdplrp_handle *h, double *dst, const double *src, i64 ncols, bool row_major, bool to_internal);
 int32_t perm_slots_upload(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 len);
 int32_t perm_slots_download(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 len);

@@ -191,6 +191,8 @@ struct RowArgs {
     const double *val;
     const int *src;    // IND: value = val[src[k]]
     const double *X;
+    const double *Xgh; // multi-GPU local view: columns >= nown are ghosts and read from Xgh + c*r (Xgh = ghost buffer - nown*r)
+    int nown;          // INT_MAX on one GPU / replicated patterns: every column reads X
     double *Y;
     int r, G;
     int G0;            // lanes per row of the class-0 kernel (= pieces per row: no idle lanes, no shuffles there)
@@ -313,7 +315,7 @@ __global__ void LB_GROUP k_rows_group(RowArgs a) {
                 if (c < nv) {
 #pragma unroll
                     for (int j = 0; j < NB; j++)
-                        if (k0 + j < end) acc[u].fma_hint(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
+                        if (k0 + j < end) acc[u].fma_hint(vv[j], (cc[j] < a.nown ? a.X : a.Xgh) + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
                 }
             }
         }
@@ -358,7 +360,7 @@ __global__ void LB_WARP k_rows_warp(RowArgs a) {
                 if (c < nv) {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (k0 + j < end) acc[u].fma_hint(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
+                        if (k0 + j < end) acc[u].fma_hint(vv[j], (cc[j] < a.nown ? a.X : a.Xgh) + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
                 }
             }
         }
@@ -597,11 +599,12 @@ struct Csr {
 // their nonzeros were all handled, chunked, in the first phase; only the epilogue is left)
 template <int VEC, int MAXU, bool IND, int EPI>
 int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const TileLayout &longs, double *sums /* 3 x 2 or null */,
-                       bool long_empty = false) {
+                       bool long_empty = false, int class_mask = 7) {
     cudaStream_t st = h->stream;
     const int gpb = TPB / a.G;
     const int gpb0 = TPB / a.G0;
     for (int c = 0; c < 3; c++) {
+        if (!(class_mask & (1 << c))) continue;   // this class belongs to another launch of the pass
         if (sums) a.out = sums + 2 * c;
         a.rows = cls.list[c];
         a.n_rows = cls.cnt[c];
@@ -642,7 +645,7 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
 
 template <bool IND, int EPI>
 int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const TileLayout &longs, double *sums, bool long_empty = false,
-                   i64 hot_override = -1) {
+                   i64 hot_override = -1, int class_mask = 7) {
     const int r = h->r;
     const bool vec2 = (r % 2 == 0);
     const int nv = vec2 ? r / 2 : r;
@@ -650,18 +653,21 @@ int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const Til
     a.G = pick_group(nv);
     a.partials = h->partials;
     a.ticket = h->ticket;
-    a.own_lo = h->row_lo;
-    a.own_hi = h->row_hi;
+    if (a.own_hi <= 0) {   // (a local pattern sets its own row range)
+        a.own_lo = h->row_lo;
+        a.own_hi = h->row_hi;
+    }
+    if (!a.Xgh) { a.Xgh = a.X; a.nown = 0x7fffffff; }
     a.G0 = (nv <= 32 && h->spmm_g0) ? nv : a.G;   // class 0: exactly one lane per piece
     a.hot_rows = (int)(hot_override >= 0 ? hot_override : tile_hot_rows(h));
     const int units = (nv + a.G - 1) / a.G;
     if (units > 4) return fail(h, SDPLRP_ERR_ARG, "rank too large for the sparse kernels (r <= 256 even / 128 odd)");
     if (vec2) {
-        if (units == 1) return launch_classes<2, 1, IND, EPI>(h, a, cls, longs, sums, long_empty);
-        return launch_classes<2, 4, IND, EPI>(h, a, cls, longs, sums, long_empty);
+        if (units == 1) return launch_classes<2, 1, IND, EPI>(h, a, cls, longs, sums, long_empty, class_mask);
+        return launch_classes<2, 4, IND, EPI>(h, a, cls, longs, sums, long_empty, class_mask);
     }
-    if (units == 1) return launch_classes<1, 1, IND, EPI>(h, a, cls, longs, sums, long_empty);
-    return launch_classes<1, 4, IND, EPI>(h, a, cls, longs, sums, long_empty);
+    if (units == 1) return launch_classes<1, 1, IND, EPI>(h, a, cls, longs, sums, long_empty, class_mask);
+    return launch_classes<1, 4, IND, EPI>(h, a, cls, longs, sums, long_empty, class_mask);
 }
 
 // mid[i] = first position of row i whose column is >= hub_cols (columns are ascending inside a row, hubs first)
@@ -783,7 +789,32 @@ int32_t grad_spmm_sparse(sdplrp_handle *h, const double *X, double *Y, double sc
 }
 
 // Y = C*X over the owned rows with the fused sums  out0 = <X, Y>, out1 = <X, Z>  (Z may be null)
+// Several GPUs, halo plan active: Y = C*X over the own rows from the LOCAL pattern.  The caller started the exchange of the
+// ghost rows of X (halo_begin).  Phase A: the [own | hub-ghost] columns of the short and medium rows as soon as the (small)
+// hub class has arrived; phase B, once the tail class is in: their tail-ghost columns on top (with the fused dots of the
+// pass) and the long rows whole.
+static int32_t grad_obj_spmm_halo(sdplrp_handle *h, const double *X, double *Y, const double *Z, double *sums6) {
+    const HaloPlan &p = h->halo;
+    const size_t off = (size_t)h->row_lo * h->r;
+    RowArgs a = {};
+    a.ptr = p.lptr; a.idx = p.lidx; a.val = p.lval; a.src = nullptr;
+    a.X = X + off; a.Y = Y + off; a.Z = Z ? Z + off : nullptr; a.scale = 1.0;
+    a.Xgh = p.ghost - (size_t)p.nloc * h->r; a.nown = (int)p.nloc;
+    a.own_lo = 0; a.own_hi = p.nloc;
+    CUDA_TRY(h, cudaMemsetAsync(sums6, 0, 6 * sizeof(double), h->stream));
+    SDP_CHECK(halo_wait(h, 0));
+    RowArgs a1 = a;
+    a1.end_arr = p.lmid;                                   // phase A: plain store of the [own | hub] part
+    SDP_CHECK((launch_csr<false, 0>(h, a1, p.cls, p.longs, nullptr, false, -1, 3)));
+    SDP_CHECK(halo_wait(h, 1));
+    RowArgs a2 = a;
+    a2.beg_arr = p.lmid;                                   // phase B: tail part on top, dots on the total
+    SDP_CHECK((launch_csr<false, 4>(h, a2, p.cls, p.longs, sums6, false, -1, 3)));
+    return launch_csr<false, 2>(h, a, p.cls, p.longs, sums6, false, -1, 4);   // long rows: whole, chunked
+}
+
 int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double *Z, double *sums6) {
+    if (halo_active(h)) return grad_obj_spmm_halo(h, X, Y, Z, sums6);
     if (gather_supported(h) && h->nnzF > 0) {   // asynchronous tile pipeline (gather.cu)
         SDP_CHECK(gather_plan_build(h, h->full_plan, h->full_ptr, h->row_lo, h->row_hi, gather_tile_size(h)));
         CUDA_TRY(h, cudaMemsetAsync(sums6 + 4, 0, 2 * sizeof(double), h->stream));

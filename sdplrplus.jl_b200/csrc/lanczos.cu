@@ -306,12 +306,12 @@ static int32_t lz_apply(sdplrp_handle *h, const double *v, double *w, const doub
     return SDPLRP_OK;
 }
 
-// The same recurrence with the rows of S, w and the vector updates divided among the ranks (option "lanczos_dist"; the
-// default keeps the operator replicated, which does not scale: 8 s of a 55 s two-GPU solve of C5).  Per step: the SpMV over
+// The same recurrence with the rows of S, w and the vector updates divided among the ranks (option "lanczos_dist", the
+// default for world > 1; the replicated operator does not scale: 8 s of a 55 s two-GPU solve of C5).  Per step: the SpMV over
 // the owned rows of each class, alpha and ||w||^2 as partial sums + one scalar all-reduce each, and one all-gather of the
 // new Lanczos vector (n doubles), which the next SpMV gathers from.  Every rank ends with the same alpha / beta (the
 // all-reduced sums are identical on all ranks), so the decisions taken from the dual bound stay SPMD-consistent.
-// Written at the end of round 1 without GPU time left: off by default, first run is scripts/check_multigpu_solve.py.
+// Measured on 2 GPUs (profiles/r2_multigpu.md): the same alpha / beta as the replicated recurrence bit for bit, 0.59 -> 0.24 s per dual check.
 static int32_t lz_run_dist(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, double *alpha, double *beta, i64 *iters) {
     const i64 n = h->n;
     cudaStream_t st = h->stream;

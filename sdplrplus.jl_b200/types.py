@@ -235,3 +235,61 @@ def assemble_sparse(data: SDPData) -> AssembledSparse:
         mat_off = np.zeros(1, np.int64); I = np.zeros(0, np.int64); J = np.zeros(0, np.int64)
         V = np.zeros(0, np.float64); g = np.zeros(0, np.int64)
     return AssembledSparse(data.n, data.m, mat_off, I, J, V, g, lowrank)
+
+
+def structured_blocks(data: SDPData):
+    """The sparse list of `assemble_sparse` as structured blocks for sdplrp_preprocess_blocks: a ConstraintBatch
+    of one-entry diagonal matrices becomes ONE `DIAG` descriptor, a batch of {(i,j),(j,i)} pairs one `EDGES` descriptor, a CSC
+    matrix goes over as its three CSC arrays, the identity as a bare descriptor; anything else falls back to a TRIPLETS block.
+    Returns (blocks, lowrank) with lowrank = [(gid1, SymLowRankMatrix)]."""
+    from . import _lib
+    blocks, lowrank = [], []
+    gid = 0
+
+    def matrix_block(A, g, what):
+        if isinstance(A, SparseMatrixCOO):
+            blocks.append({"kind": _lib.BLOCK_TRIPLETS, "first_gid": g, "I": A.rows + 1, "J": A.cols + 1, "V": A.vals})
+        elif isinstance(A, Diagonal):
+            idx = np.arange(1, A.d.size + 1, dtype=np.int64)
+            blocks.append({"kind": _lib.BLOCK_TRIPLETS, "first_gid": g, "I": idx, "J": idx, "V": A.d})
+        elif isinstance(A, SymLowRankMatrix):
+            lowrank.append((g, A))
+        elif sp.issparse(A):
+            M = sp.csc_matrix(A)
+            M.sum_duplicates(); M.sort_indices()
+            n = M.shape[0]
+            if M.nnz == n and np.array_equal(M.indices, np.arange(n)) and np.all(M.data == 1.0) and np.array_equal(M.indptr, np.arange(n + 1)):
+                blocks.append({"kind": _lib.BLOCK_IDENTITY, "first_gid": g})
+            else:
+                blocks.append({"kind": _lib.BLOCK_CSC, "first_gid": g, "I": M.indices.astype(np.int64) + 1,
+                               "J": M.indptr.astype(np.int64) + 1, "V": M.data.astype(np.float64)})
+        else:
+            raise TypeError(f"Currently only sparse/symmetric low-rank/diagonal {what} are supported.")
+
+    for A in data.As:
+        if isinstance(A, ConstraintBatch):
+            k = len(A)
+            lens = np.diff(A.offsets)
+            if k > 0 and np.all(lens == 1) and np.array_equal(A.rows, A.cols):
+                pos = A.rows + 1
+                blk = {"kind": _lib.BLOCK_DIAG, "first_gid": gid + 1, "count": k}
+                if not np.array_equal(A.rows, np.arange(k)):
+                    blk["I"] = pos
+                if not np.all(A.vals == 1.0):
+                    blk["V"] = A.vals
+                blocks.append(blk)
+            elif k > 0 and np.all(lens == 2) and np.array_equal(A.rows[0::2], A.cols[1::2]) and np.array_equal(A.cols[0::2], A.rows[1::2]) \
+                    and np.array_equal(A.vals[0::2], A.vals[1::2]):
+                blk = {"kind": _lib.BLOCK_EDGES, "first_gid": gid + 1, "count": k, "I": A.rows[0::2] + 1, "J": A.cols[0::2] + 1}
+                if not np.all(A.vals == 1.0):
+                    blk["V"] = A.vals[0::2].copy()
+                blocks.append(blk)
+            else:   # mixed batch: matrix by matrix
+                for i in range(k):
+                    matrix_block(A[i], gid + 1 + i, "constraints")
+            gid += k
+        else:
+            gid += 1
+            matrix_block(A, gid, "constraints")
+    matrix_block(data.C, data.m + 1, "objectives")
+    return blocks, lowrank

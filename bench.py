@@ -469,6 +469,7 @@ def main():
             "host_wall_ms_per_step": 1e3 * t_wall / args.steps, "comm_ms_per_step": comm_ms / args.steps,
             "setup": {"graph_generation_s": gen_s, "preprocess_s": preprocess_s},
             "last_iterate": {"L": last[0], "obj": last[1], "gnorm2": last[2], "pnorm2": last[3], "alpha": last[4]},
+            "halo": handle.halo_stats() if world > 1 else None,
             "lanczos": lanczos, "time_to_tol": time_to_tol, "options": args.option, "loop": "sdplrp_iterate (native)" if native else "python (one ABI call per seam function)",
         }
         print(json.dumps(line), flush=True)

@@ -333,6 +333,9 @@ int32_t sdplrp_section_times(sdplrp_handle *h, double *ms, int64_t *counts);
 /* number of kernels this handle has launched since creation */
 int32_t sdplrp_launch_count(sdplrp_handle *h, int64_t *count);
 /* rows [lo,hi) of R/G/D owned by this rank (0-based) */
+/* several GPUs: the halo plan of the gather pass on this rank: {active, own rows, own nonzeros, hub ghost rows, tail ghost rows,
+ * hub rows packed per pass, tail rows packed per pass} (a packed row goes to one peer; a row needed by k peers counts k times) */
+int32_t sdplrp_halo_stats(sdplrp_handle *h, int64_t out[7]);
 int32_t sdplrp_row_range(sdplrp_handle *h, int64_t *lo, int64_t *hi);
 
 #ifdef __cplusplus

@@ -52,12 +52,13 @@ mutable struct Handle
     ptr::Ptr{Cvoid}
     gnorm2::Float64      # ||G||_F^2 of the last g! / fg!
     descent::Float64     # dot(dirt, Gt) of the last lbfgs_dir!
-    stepped::Bool        # linesearch! already applied Rt += α dirt (the caller's axpy! is then a no-op)
+    stepped::Bool        # a line search chose α: the caller's axpy!(α, dirt, Rt) is a no-op, the step runs fused with g!
+    pending_alpha::Float64   # that α, until g! issues sdplrp_step_g
     function Handle(device::Integer=0)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:sdplrp_create, LIB), Int32, (Int32, Int32, Int32, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), device, 0, 1, C_NULL, out)
         rc == 0 || throw(B200Error(rc, unsafe_string(ccall((:sdplrp_error_string, LIB), Cstring, (Int32,), rc))))
-        h = new(out[], 0.0, 0.0, false)
+        h = new(out[], 0.0, 0.0, false, NaN)
         finalizer(x -> ccall((:sdplrp_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
         return h
     end
@@ -163,9 +164,9 @@ function Base.copyto!(dirt::DevMat, G::DevMat)
     check(G.h, ccall((:sdplrp_use_gradient_direction, LIB), Int32, (Ptr{Cvoid},), G.h.ptr))
     return dirt
 end
-# src/sdplr.jl:219  axpy!(α, dirt, var.Rt): sdplrp_step applied it together with the residual recurrence
+# src/sdplr.jl:219  axpy!(α, dirt, var.Rt): applied by the fused step + gradient pass that the following g! issues
 function LinearAlgebra.axpy!(α, dirt::DevMat, Rt::DevMat)
-    Rt.h.stepped || error("axpy!(α, dirt, Rt) on device matrices is only valid right after linesearch!")
+    (Rt.h.stepped && α == Rt.h.pending_alpha) || error("axpy!(α, dirt, Rt) on device matrices is only valid right after a line search, with its α")
     Rt.h.stepped = false
     return Rt
 end
@@ -218,12 +219,22 @@ function fg!(data, var::SolverVars{Ti,Float64,DevMat}, aux::B200Auxiliary, normC
     return out[1], grad_norm, primal_vio_norm
 end
 
-# src/coreop.jl:305-317  g!(var, aux); the two norms `_sdplr` takes right after it are returned by the same pass
+# src/coreop.jl:305-317  g!(var, aux).  Right after a line search it is the fused pass sdplrp_step_g: Rt += α dirt, the
+# residual recurrence and obj (src/linesearch.jl:118-124), y, G and the two norms `_sdplr` takes next -- one row pass.
 function g!(var::SolverVars{Ti,Float64,DevMat}, aux::B200Auxiliary) where {Ti<:Integer}
-    gn2, pn2 = Ref(0.0), Ref(0.0)
-    check(aux.h, ccall((:sdplrp_g, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), aux.h.ptr, gn2, pn2))
-    aux.h.gnorm2 = gn2[]
-    mirror_pvio_norm!(var, pn2[])
+    h = aux.h
+    if !isnan(h.pending_alpha)
+        out = zeros(3)
+        GC.@preserve out check(h, ccall((:sdplrp_step_g, LIB), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}), h.ptr, h.pending_alpha, out))
+        h.pending_alpha = NaN
+        var.obj[] = out[1]; h.gnorm2 = out[2]
+        mirror_pvio_norm!(var, out[3])
+    else
+        gn2, pn2 = Ref(0.0), Ref(0.0)
+        check(h, ccall((:sdplrp_g, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h.ptr, gn2, pn2))
+        h.gnorm2 = gn2[]
+        mirror_pvio_norm!(var, pn2[])
+    end
     return 0
 end
 
@@ -243,8 +254,9 @@ function lbfgs_update!(dirt::DevMat, his::LBFGSHistory{Ti,Float64}, Gt::DevMat, 
 end
 
 # src/linesearch.jl:4-127  linesearch!(var, aux, Dt; α_max): the two 𝒜 passes and the quartic coefficients on the device,
-# the root selection of src/linesearch.jl:58-112 by sdplrp_pick_alpha (host code of the library, same candidate rule), the
-# commit `primal_vio_raw += α(α A_DD + A_RD)`, obj (src/linesearch.jl:118-124) and `Rt += α Dt` by sdplrp_step
+# the root selection of src/linesearch.jl:58-112 by sdplrp_pick_alpha (host code of the library, same candidate rule); the
+# commit `primal_vio_raw += α(α A_DD + A_RD)`, obj (src/linesearch.jl:118-124) and `Rt += α Dt` are deferred to the g! that
+# `_sdplr` calls next (src/sdplr.jl:219-221), where they run fused with the gradient (sdplrp_step_g)
 function linesearch!(var::SolverVars{Ti,Float64,DevMat}, aux::B200Auxiliary, dirt::DevMat; α_max=1.0) where {Ti<:Integer}
     h = aux.h
     biquadratic = zeros(5)
@@ -252,10 +264,7 @@ function linesearch!(var::SolverVars{Ti,Float64,DevMat}, aux::B200Auxiliary, dir
     α, 𝓛 = Ref(0.0), Ref(0.0)
     rc = GC.@preserve biquadratic ccall((:sdplrp_pick_alpha, LIB), Int32, (Ptr{Float64}, Float64, Ref{Float64}, Ref{Float64}), biquadratic, Float64(α_max), α, 𝓛)
     rc == 0 || error("line search: the slope at 0 is positive (src/linesearch.jl:63-66)")
-    obj = Ref(0.0)
-    check(h, ccall((:sdplrp_step, LIB), Int32, (Ptr{Cvoid}, Float64, Ref{Float64}), h.ptr, α[], obj))
-    var.obj[] = obj[]
-    h.stepped = true
+    h.pending_alpha = α[]; h.stepped = true       # the commit of src/linesearch.jl:118-124 runs fused with the next g!
     return α[], 𝓛[]
 end
 
@@ -286,10 +295,7 @@ function linesearch_armijo!(var::SolverVars{Ti,Float64,DevMat}, aux::B200Auxilia
         end
         𝓛 = Lb[end]
     end
-    obj = Ref(0.0)
-    check(h, ccall((:sdplrp_step, LIB), Int32, (Ptr{Cvoid}, Float64, Ref{Float64}), h.ptr, α, obj))
-    var.obj[] = obj[]
-    h.stepped = true
+    h.pending_alpha = α; h.stepped = true
     return α, 𝓛
 end
 

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "sdplrp_preprocess": [_H, C.c_int64, C.c_int64, C.c_int64, _p_i64, _p_i64, _p_i64, _p_f64, _p_i64],
     "sdplrp_preprocess_device": [_H, C.c_int64, C.c_int64, C.c_int64, _p_i64, C.c_void_p, C.c_void_p, C.c_void_p, _p_i64],
     "sdplrp_preprocess_blocks": [_H, C.c_int64, C.c_int64, C.c_int64, C.POINTER(Block)],
+    "sdplrp_halo_stats": [_H, _p_i64],
     "sdplrp_pattern_sizes": [_H, _p_i64, _p_i64, _p_i64],
     "sdplrp_pattern_export": [_H, _p_i64, _p_i64, _p_i64, _p_i64, _p_f64, _p_f64, _p_i64, _p_i64, _p_i64],
     "sdplrp_add_symlowrank": [_H, C.c_int64, C.c_int64, _p_f64, _p_f64],
@@ -552,6 +553,11 @@ class Handle:
         c = C.c_int64()
         self._check(self.lib.sdplrp_launch_count(self._h, C.byref(c)))
         return c.value
+
+    def halo_stats(self):
+        a = np.zeros(7, np.int64)
+        self._check(self.lib.sdplrp_halo_stats(self._h, a.ctypes.data_as(_p_i64)))
+        return dict(zip(("active", "own_rows", "own_nnz", "hub_ghosts", "tail_ghosts", "hub_rows_sent", "tail_rows_sent"), (int(x) for x in a)))
 
     def row_range(self):
         lo, hi = C.c_int64(), C.c_int64()

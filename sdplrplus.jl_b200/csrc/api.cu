@@ -127,6 +127,16 @@ int32_t sdplrp_create(int32_t device, int32_t rank, int32_t world, const void *n
     if (const char *e = getenv("SDPLRP_SPMM_G0")) h->spmm_g0 = atoi(e);
     if (const char *e = getenv("SDPLRP_LANCZOS_DIST")) h->lanczos_dist = atoi(e) > 0 ? 1 : 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SDPLRP_ERR_CUDA; }
+    {   // side streams of the row classes of a gather pass (SDPLRP_CLASS_STREAMS=0: everything on the one stream)
+        const char *e = getenv("SDPLRP_CLASS_STREAMS");
+        if (!e || atoi(e) != 0) {
+            bool ok = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+            for (int c = 0; c < 2 && ok; c++)
+                ok = cudaStreamCreateWithFlags(&h->class_streams[c], cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) { cudaGetLastError(); h->class_streams[0] = nullptr; }
+        }
+    }
     // L2 fetch granularity (cudaLimitMaxL2FetchGranularity: 32 / 64 / 128 bytes): the gather pass reads 80-byte rows at
     // random, so everything the memory system fetches beyond the touched sectors is waste
     if (const char *e = getenv("SDPLRP_L2_FETCH")) {
@@ -201,6 +211,11 @@ int32_t sdplrp_destroy(sdplrp_handle *h) {
     free_problem(h);
     dev_free(&h->dscal); dev_free(&h->partials); dev_free(&h->ticket);
     if (h->hscal) cudaFreeHost(h->hscal);
+    for (int c = 0; c < 2; c++) {
+        if (h->class_streams[c]) cudaStreamDestroy(h->class_streams[c]);
+        if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return SDPLRP_OK;
@@ -269,6 +284,16 @@ static int32_t preprocess_common(sdplrp_handle *h, int64_t n, int64_t m, int64_t
     SDP_CHECK(comm_partition(h));
     SDP_CHECK(halo_build(h));   // multi-GPU: local pattern + halo lists of the gather pass
     return rc;
+}
+
+// multi-GPU introspection: {active, own rows, own nonzeros, hub ghosts, tail ghosts, hub rows sent, tail rows sent}
+int32_t sdplrp_halo_stats(sdplrp_handle *h, int64_t out[7]) {
+    REQUIRE_H(h);
+    REQUIRE_PRE(h);
+    const HaloPlan &p = h->halo;
+    out[0] = halo_active(h) ? 1 : 0; out[1] = p.nloc; out[2] = p.lnnz; out[3] = p.n_ghost[0]; out[4] = p.n_ghost[1];
+    out[5] = p.n_send[0]; out[6] = p.n_send[1];
+    return SDPLRP_OK;
 }
 
 int32_t sdplrp_pattern_sizes(sdplrp_handle *h, int64_t *nnzT, int64_t *nnzF, int64_t *Ec) {

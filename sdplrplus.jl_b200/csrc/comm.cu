@@ -343,7 +343,7 @@ __global__ void k_pack_rows(i64 n_rows, int r, const int *__restrict__ rows, con
 
 bool halo_active(const sdplrp_handle *h) { return h->world > 1 && h->halo.active && h->halo_mode != 0; }
 
-// pack both classes on the compute stream, then (comm stream) exchange the hub class and the tail class one after the other
+// (comm stream) pack and exchange the hub class, then the tail class
 int32_t halo_begin(sdplrp_handle *h, const double *X) {
     HaloPlan &p = h->halo;
     const int r = h->r, P = h->world;
@@ -351,19 +351,19 @@ int32_t halo_begin(sdplrp_handle *h, const double *X) {
     if (p.sendbuf_len < need_send) { SDP_CHECK(dev_alloc(h, &p.sendbuf, need_send)); p.sendbuf_len = need_send; }
     if (p.ghost_len < need_ghost) { SDP_CHECK(dev_alloc(h, &p.ghost, need_ghost)); p.ghost_len = need_ghost; }
     const double *Xown = X + (size_t)h->row_lo * r;
-    for (int k = 0; k < 2; k++) {
-        if (p.n_send[k] <= 0) continue;
-        double *out = p.sendbuf + (size_t)(k == 0 ? 0 : p.n_send[0]) * r;
-        k_pack_rows<<<grid_for(p.n_send[k] * r, 256, 8 * kNumSM), 256, 0, h->stream>>>(p.n_send[k], r, p.send_rows[k], Xown, out);
-        KLAUNCH(h);
-    }
-    CUDA_TRY(h, cudaGetLastError());
+    // everything on the comm stream, behind what produced X: pack hub rows -> exchange them -> pack tail rows -> exchange them.
+    // The compute stream is free for the constraint pass and (from the hub event on) the [own | hub] half of the pass.
     CUDA_TRY(h, cudaEventRecord(h->ev_pack, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_pack, 0));
     ncclComm_t comm = (ncclComm_t)(h->nccl_halo ? h->nccl_halo : h->nccl);
     for (int k = 0; k < 2; k++) {
-        const double *sb = p.sendbuf + (size_t)(k == 0 ? 0 : p.n_send[0]) * r;
+        double *sb = p.sendbuf + (size_t)(k == 0 ? 0 : p.n_send[0]) * r;
         double *gb = p.ghost + (size_t)(k == 0 ? 0 : p.n_ghost[0]) * r;
+        if (p.n_send[k] > 0) {
+            k_pack_rows<<<grid_for(p.n_send[k] * r, 256, 8 * kNumSM), 256, 0, h->comm_stream>>>(p.n_send[k], r, p.send_rows[k], Xown, sb);
+            KLAUNCH(h);
+            CUDA_TRY(h, cudaGetLastError());
+        }
         NCCL_TRY(h, ncclGroupStart());
         for (int q = 0; q < P; q++) {
             if (q == h->rank) continue;

@@ -137,6 +137,9 @@ struct sdplrp_handle {
                                                          // L2-sized hub prefix; > 1 = that many hub columns (gradient.cu, grad_obj_spmm)
     int lanczos_dist = 1;                                // world > 1: 1 = row-partitioned q-step Lanczos (default; measured identical to the replicated
                                                          // recurrence on 2 GPUs and 2.5x faster), 0 = replicated operator (lanczos.cu: lz_run_dist)
+    cudaStream_t class_streams[2] = {nullptr, nullptr};  // side streams of the medium / long row classes of a gather pass (gradient.cu)
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    bool fork_open = false;                              // a caller forked the side streams around several launches of one pass
     // multi-GPU halo exchange of the gather pass (preprocess.cu: halo_build, comm.cu)
     int halo_mode = 1;                                   // 0 = all-gather of the whole factor (round-1 path), 1 = halo exchange overlapped with the pass
     HaloPlan halo;

@@ -292,6 +292,10 @@ int32_t sdplrp_solve(sdplrp_handle *h, const sdplrp_config *cfgp, int64_t r0, co
             const double rel_delta = (lastval - L_val) / std::max(1.0, std::max(fabs(L_val), fabs(lastval)));
             if (rel_delta < cfg.fprec * kEps) break;  // src/sdplr.jl:238-241
             if (hist > 0) SDP_CHECK(sdplrp_lbfgs_update(h, alpha));
+            // the iteration budget is the same number on every rank: tested every iteration, as the reference does
+            // (src/sdplr.jl:271-276).  Only the WALL-CLOCK decision needs an agreement among the ranks (an all-reduce),
+            // which is taken every 16th iteration when there are several.
+            if (it > cfg.maxiter) { out_of_budget = true; break; }
             if ((it & 15) == 0 || h->world <= 1) {
                 const double now = now_s();
                 if (now - lastprint >= cfg.printfreq) {
@@ -300,7 +304,7 @@ int32_t sdplrp_solve(sdplrp_handle *h, const sdplrp_config *cfgp, int64_t r0, co
                         print_row(cfg, majoriter, localiter, it, L_val, obj, h->sigma, cur_gtol, cur_ptol, grad_norm, pvio_norm, min_gap, max_dual);
                 }
                 bool over = false;
-                SDP_CHECK(agree(h, now - t_start > cfg.maxtime || it > cfg.maxiter, &over));
+                SDP_CHECK(agree(h, now - t_start > cfg.maxtime, &over));
                 if (over) { out_of_budget = true; break; }
             }
         }

@@ -597,15 +597,42 @@ struct Csr {
 
 // long_empty: the long rows (class 2) take the warp-per-row kernel over an EMPTY range (second phase of the two-phase pass:
 // their nonzeros were all handled, chunked, in the first phase; only the epilogue is left)
+// side streams of the row classes: everything enqueued on the main stream so far happens before them / they before what follows
+static int32_t classes_fork(sdplrp_handle *h) {
+    if (!h->class_streams[0]) return SDPLRP_OK;
+    CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
+    for (int c = 0; c < 2; c++) CUDA_TRY(h, cudaStreamWaitEvent(h->class_streams[c], h->ev_fork, 0));
+    h->fork_open = true;
+    return SDPLRP_OK;
+}
+static int32_t classes_join(sdplrp_handle *h) {
+    if (!h->class_streams[0]) return SDPLRP_OK;
+    for (int c = 0; c < 2; c++) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_join[c], h->class_streams[c]));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join[c], 0));
+    }
+    h->fork_open = false;
+    return SDPLRP_OK;
+}
+
 template <int VEC, int MAXU, bool IND, int EPI>
 int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const TileLayout &longs, double *sums /* 3 x 2 or null */,
                        bool long_empty = false, int class_mask = 7) {
-    cudaStream_t st = h->stream;
     const int gpb = TPB / a.G;
     const int gpb0 = TPB / a.G0;
+    // The three row classes are independent (disjoint rows, their own sums, their own reduction scratch): the medium and the
+    // long rows run on side streams next to the short rows.  On one GPU each kernel fills the machine anyway; with the rows
+    // divided among 8 GPUs the medium / long kernels are a few hundred CTAs each and would otherwise run one after the other
+    // at a fraction of the occupancy this latency-bound pass needs.
+    const bool fork = h->class_streams[0] != nullptr;
+    const bool own_fork = fork && !h->fork_open;   // a caller that issues several launches of one pass forks / joins around them
+    if (own_fork) SDP_CHECK(classes_fork(h));
     for (int c = 0; c < 3; c++) {
         if (!(class_mask & (1 << c))) continue;   // this class belongs to another launch of the pass
+        cudaStream_t st = (fork && c > 0) ? h->class_streams[c - 1] : h->stream;
         if (sums) a.out = sums + 2 * c;
+        a.partials = h->partials + (size_t)c * 16384;   // <= 16 * kNumSM CTAs x 2 sums per class
+        a.ticket = h->ticket + c;
         a.rows = cls.list[c];
         a.n_rows = cls.cnt[c];
         if (a.n_rows <= 0) {
@@ -625,6 +652,7 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
             // long rows: one warp per chunk, then the per-row combination with the epilogue
             const i64 need = longs.n_chunks * (i64)a.r;
             if (h->tile_scratch_len < need) {
+                if (fork) CUDA_TRY(h, cudaDeviceSynchronize());   // (re)allocation under concurrent streams: rare, first call per rank
                 SDP_CHECK(dev_alloc(h, &h->tile_scratch, need));
                 h->tile_scratch_len = need;
             }
@@ -639,6 +667,7 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
         }
         KLAUNCH(h);
     }
+    if (own_fork) SDP_CHECK(classes_join(h));
     CUDA_TRY(h, cudaGetLastError());
     return SDPLRP_OK;
 }
@@ -651,8 +680,6 @@ int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const Til
     const int nv = vec2 ? r / 2 : r;
     a.r = r;
     a.G = pick_group(nv);
-    a.partials = h->partials;
-    a.ticket = h->ticket;
     if (a.own_hi <= 0) {   // (a local pattern sets its own row range)
         a.own_lo = h->row_lo;
         a.own_hi = h->row_hi;
@@ -808,9 +835,12 @@ static int32_t grad_obj_spmm_halo(sdplrp_handle *h, const double *X, double *Y, 
     SDP_CHECK((launch_csr<false, 0>(h, a1, p.cls, p.longs, nullptr, false, -1, 3)));
     SDP_CHECK(halo_wait(h, 1));
     RowArgs a2 = a;
-    a2.beg_arr = p.lmid;                                   // phase B: tail part on top, dots on the total
-    SDP_CHECK((launch_csr<false, 4>(h, a2, p.cls, p.longs, sums6, false, -1, 3)));
-    return launch_csr<false, 2>(h, a, p.cls, p.longs, sums6, false, -1, 4);   // long rows: whole, chunked
+    a2.beg_arr = p.lmid;                                   // phase B: tail part on top, dots on the total ...
+    SDP_CHECK(classes_fork(h));
+    int32_t rc = launch_csr<false, 4>(h, a2, p.cls, p.longs, sums6, false, -1, 3);
+    if (rc == SDPLRP_OK) rc = launch_csr<false, 2>(h, a, p.cls, p.longs, sums6, false, -1, 4);   // ... next to the long rows: whole, chunked
+    const int32_t rj = classes_join(h);
+    return rc != SDPLRP_OK ? rc : rj;
 }
 
 int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double *Z, double *sums6) {

@@ -36,6 +36,20 @@ __global__ void __launch_bounds__(TPB) k_lz_spmv(const int *__restrict__ rows, i
         double t = 0.0;
         if (live) {
             const int beg = ptr[i], end = ptr[i + 1];
+            if (LANES <= 8) {
+                // short rows: blocks of 2*LANES nonzeros, fully predicated, so that a row of <= 2*LANES nonzeros costs ONE
+                // round trip for its indices / values and ONE for its gathers (the scalar tail loop below paid a dependent
+                // idx -> v pair per LANES nonzeros: ncu long_scoreboard, profiles/r2_lanczos.md)
+                for (int k0 = beg; k0 < end; k0 += 2 * LANES) {
+                    const int ka = k0 + lg, kb = ka + LANES;
+                    const bool oa = ka < end, ob = kb < end;
+                    const int ca = oa ? __ldg(idx + ka) : 0, cb = ob ? __ldg(idx + kb) : 0;
+                    const double sa = oa ? __ldg(S + ka) : 0.0, sb = ob ? __ldg(S + kb) : 0.0;
+                    const double va = __ldg(v + ca), vb = __ldg(v + cb);
+                    t += sa * va;
+                    t += sb * vb;
+                }
+            } else {
             int k = beg + lg;
             for (; k + 3 * LANES < end; k += 4 * LANES) {  // four independent index -> value chains per lane
                 const int c0 = __ldg(idx + k), c1 = __ldg(idx + k + LANES), c2 = __ldg(idx + k + 2 * LANES), c3 = __ldg(idx + k + 3 * LANES);
@@ -43,6 +57,7 @@ __global__ void __launch_bounds__(TPB) k_lz_spmv(const int *__restrict__ rows, i
                 t += s0 * __ldg(v + c0) + s1 * __ldg(v + c1) + s2 * __ldg(v + c2) + s3 * __ldg(v + c3);
             }
             for (; k < end; k += LANES) t += __ldg(S + k) * __ldg(v + __ldg(idx + k));
+            }
         }
         if (LANES <= 32) {
 #pragma unroll

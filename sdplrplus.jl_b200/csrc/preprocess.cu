@@ -275,8 +275,17 @@ int32_t with_cub_temp(sdplrp_handle *h, F f) {
     return SDPLRP_OK;
 }
 
+// The CUB primitives below take 32-bit item counts and the device patterns are int32: inputs beyond 2^31 - 1 entries are
+// refused with an error instead of being truncated.
+constexpr i64 kMaxItems = 0x7fffffffLL;
+#define REQUIRE_32BIT(h, count, what)                                                                                    \
+    do {                                                                                                                 \
+        if ((count) > kMaxItems) return fail((h), SDPLRP_ERR_ARG, std::string(what) + ": more than 2^31 - 1 entries per GPU"); \
+    } while (0)
+
 int32_t exclusive_scan(sdplrp_handle *h, const int *in, int *out, i64 count) {
     if (count <= 0) return SDPLRP_OK;
+    REQUIRE_32BIT(h, count, "preprocess (scan)");
     h->launches += 2;
     return with_cub_temp(h, [&](void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum(t, b, in, out, (int)count, h->stream); });
 }
@@ -285,6 +294,7 @@ int32_t exclusive_scan(sdplrp_handle *h, const int *in, int *out, i64 count) {
 int32_t sort_unique(sdplrp_handle *h, unsigned long long *keys, unsigned long long *scratch, i64 count, int end_bit,
                     unsigned long long *out, i64 *n_out) {
     if (count <= 0) { *n_out = 0; return SDPLRP_OK; }
+    REQUIRE_32BIT(h, count, "preprocess (sort)");
     h->launches += 8;
     SDP_CHECK(with_cub_temp(h, [&](void *t, size_t &b) {
         return cub::DeviceRadixSort::SortKeys(t, b, keys, scratch, (int)count, 0, end_bit, h->stream);

@@ -301,6 +301,12 @@ def main():
         handle.set_option(key, float(val))
     n, r, h = args.n, args.rank, 4
 
+    # library warm-up outside every timed region: the first launches of a process pay the CUDA module load of the .so
+    # (tens of MB of SASS), which is not preprocessing work
+    warm = sp.Handle(device=local)
+    Cw, Aw, bw = sp.problems.maxcut(sp.problems.gnm_graph(64, 256, 0))
+    sp.B200Engine(sp.SDPData(Cw, Aw, bw), handle=warm).close()
+    del warm
     asm, b, normC, E, gen_s = generate(sp, n, args.edges, args.seed, keep_on_device=not args.host_triplets)
     data = SimpleData(n, n, b)
     t0 = time.perf_counter()
@@ -357,15 +363,16 @@ def main():
     eng.init_vars(r, R0, lam0, 2.0, h)
     eng.fg()
     sp.solver.run_inner_iterations(eng, args.steps, native=native)
-    handle.download_mat_owned(sp._lib.MAT_R, Rout_t.numpy())   # several GPUs: every rank fetches the rows it owns
+    handle.download_mat_slice(sp._lib.MAT_R, Rout_t.numpy())   # several GPUs: every rank fetches its contiguous slice of the result
     lam_out = eng.get_lambda()
     torch.cuda.synchronize(); spdist.barrier()
     e2e_s = spdist.max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": args.steps / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": (R0.nbytes * (hi - lo) / float(n) + lam0.nbytes) / args.steps + 8.0,
            "d2h_bytes_per_step": (R0.nbytes * (hi - lo) / float(n) + lam0.nbytes) / args.steps + 8.0 * 9,
-           "what": "per rank: init_vars (H2D of the owned rows of R0 and of lambda0 from pinned host memory) + fg + K inner iterations "
-                   "(host scalars cross every iteration) + D2H of the owned rows of R and of lambda; wall clock, max over ranks",
+           "what": "per rank: init_vars (H2D of this rank's 1/world slice of R0 and of lambda0 from pinned host memory; the slices are "
+                   "exchanged over NVLink) + fg + K inner iterations (host scalars cross every iteration) + D2H of this rank's slice of R "
+                   "and of lambda; wall clock, max over ranks",
            "one_time_preprocess_s": preprocess_s, "one_time_preprocess_h2d_bytes": pre_h2d}
 
     # ---- optional Lanczos timing (dual bound), reported beside the headline

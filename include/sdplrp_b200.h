@@ -99,6 +99,8 @@ void *sdplrp_stream(sdplrp_handle *h);
  *   "lanczos_dist" several GPUs: 1 = rows of S and of the Lanczos vectors are divided among the ranks (one all-gather of n
  *                 doubles + two scalar all-reduces per step; default), 0 = the q-step Lanczos operator is replicated on every
  *                 rank.  Only without re-orthogonalisation
+ *   "row_group_max" rows with at most this many nonzeros are taken by one lane group each (default 64: measured 24 / 32 / 48 / 64 -> 4.27 / 4.14 / 4.06 / 4.02 ms for the C5 pass), longer ones by one
+ *                 warp each; set BEFORE sdplrp_preprocess
  *   "spmm_unroll" nonzeros per block of the short-row kernels: 8 (default) or 4
  *   "spmm_g0"     1 = lane groups of exactly r/2 lanes per short row (default: 6 rows per warp at r = 10), 0 = next power of two
  *   "halo"        several GPUs: 1 = every rank keeps the objective pattern of its own rows and the gather pass exchanges only the
@@ -180,6 +182,11 @@ int32_t sdplrp_download_mat(sdplrp_handle *h, int32_t mat_id, double *dst /* r*n
  * other ranks reach a rank over NVLink when a pass needs them.  One GPU: identical to the calls above. */
 int32_t sdplrp_upload_mat_owned(sdplrp_handle *h, int32_t mat_id, const double *src /* r*n */);
 int32_t sdplrp_download_mat_owned(sdplrp_handle *h, int32_t mat_id, double *dst /* r*n */);
+/* The same with CONTIGUOUS slices: rank q reads / writes rows [q*S, min(n, (q+1)*S)) of the caller's matrix, S = ceil(n / world).
+ * Upload: the slices are exchanged over NVLink, every rank ends up with the whole matrix.  Download: the matrix is completed
+ * over NVLink and each rank writes its slice; the union over the ranks is the result. */
+int32_t sdplrp_upload_mat_slice(sdplrp_handle *h, int32_t mat_id, const double *src /* r*n */);
+int32_t sdplrp_download_mat_slice(sdplrp_handle *h, int32_t mat_id, double *dst /* r*n */);
 int32_t sdplrp_upload_vec(sdplrp_handle *h, int32_t vec_id, const double *src, int64_t len);
 int32_t sdplrp_download_vec(sdplrp_handle *h, int32_t vec_id, double *dst, int64_t len);
 

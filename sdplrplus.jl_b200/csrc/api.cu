@@ -392,6 +392,7 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
     if (k == "hot_rows") { h->hot_rows = (i64)value; return SDPLRP_OK; }
     if (k == "spmm_phases") { h->spmm_phases = value < 0 ? 0 : (int)value; return SDPLRP_OK; }
     if (k == "lanczos_dist") { h->lanczos_dist = value > 0 ? 1 : 0; return SDPLRP_OK; }
+    if (k == "row_group_max") { h->row_group_max = std::max(1, std::min((int)value, kRowWarpMax)); return SDPLRP_OK; }   // before preprocess
     if (k == "spmm_unroll") { h->spmm_unroll = (int)value; return SDPLRP_OK; }
     if (k == "spmm_g0") { h->spmm_g0 = (int)value; return SDPLRP_OK; }
     if (k == "halo") { h->halo_mode = value > 0 ? 1 : 0; return SDPLRP_OK; }
@@ -469,6 +470,39 @@ int32_t sdplrp_download_mat_owned(sdplrp_handle *h, int32_t id, double *dst) {
     double *p = mat_ptr(h, id);
     if (!p || !dst) return fail(h, SDPLRP_ERR_ARG, "download_mat_owned: bad id");
     return perm_download_owned(h, p, dst, h->r);
+}
+
+// several GPUs: rank q reads rows [q*S, (q+1)*S) of `src` (the caller's vertex order, S = ceil(n / world)); the slices are
+// exchanged over NVLink, so every rank ends up with the WHOLE matrix while n*r/world doubles crossed its PCIe link
+int32_t sdplrp_upload_mat_slice(sdplrp_handle *h, int32_t id, const double *src) {
+    REQUIRE_H(h);
+    REQUIRE_RANK(h);
+    if (h->world <= 1) return sdplrp_upload_mat(h, id, src);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(lazy_scratch(h, id));
+    if (id == SDPLRP_MAT_CR || id == SDPLRP_MAT_CD) return fail(h, SDPLRP_ERR_ARG, "upload_mat: CR / CD are download-only");
+    double *p = mat_ptr(h, id);
+    if (!p || !src) return fail(h, SDPLRP_ERR_ARG, "upload_mat_slice: bad id");
+    SDP_CHECK(perm_upload_slice(h, p, src, h->r));
+    comm_mark_full(h, id);
+    if (id == SDPLRP_MAT_R) { h->CR_valid = false; h->ls_valid = false; }
+    if (id == SDPLRP_MAT_D) { h->CD_valid = false; h->ls_valid = false; }
+    if (id == SDPLRP_MAT_G) h->gram_g_valid = false;
+    if (id >= SDPLRP_MAT_S0) { h->gram_pairs_valid = false; h->gram_prestored = -1; }
+    return SDPLRP_OK;
+}
+
+// several GPUs: rank q writes rows [q*S, (q+1)*S) of `dst`; the union over the ranks is the matrix
+int32_t sdplrp_download_mat_slice(sdplrp_handle *h, int32_t id, double *dst) {
+    REQUIRE_H(h);
+    REQUIRE_RANK(h);
+    if (h->world <= 1) return sdplrp_download_mat(h, id, dst);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    SDP_CHECK(lazy_scratch(h, id));
+    double *p = mat_ptr(h, id);
+    if (!p || !dst) return fail(h, SDPLRP_ERR_ARG, "download_mat_slice: bad id");
+    SDP_CHECK(comm_gather_rows(h, p, id));   // the rows of the other ranks over NVLink
+    return perm_download_slice(h, p, dst, h->r);
 }
 
 int32_t sdplrp_download_mat(sdplrp_handle *h, int32_t id, double *dst) {
@@ -685,7 +719,9 @@ int32_t sdplrp_fg(sdplrp_handle *h, double out[4]) {
     return SDPLRP_OK;
 }
 
-int32_t sdplrp_lbfgs_dir(sdplrp_handle *h, double *descent) {
+// the direction without the host round trip for `descent` (native loop: the value comes back with the line-search
+// coefficients, api_linesearch_coeffs_descent)
+int32_t api_lbfgs_dir_async(sdplrp_handle *h) {
     REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
     {
@@ -694,6 +730,11 @@ int32_t sdplrp_lbfgs_dir(sdplrp_handle *h, double *descent) {
     }
     h->CD_valid = false; h->ls_valid = false;
     comm_mark_partial(h, SDPLRP_MAT_D);
+    return SDPLRP_OK;
+}
+
+int32_t sdplrp_lbfgs_dir(sdplrp_handle *h, double *descent) {
+    SDP_CHECK(api_lbfgs_dir_async(h));
     SDP_CHECK(fetch_scalars(h, SC_DESCENT, 1));
     if (descent) *descent = h->hscal[SC_DESCENT];
     return SDPLRP_OK;
@@ -709,7 +750,8 @@ int32_t sdplrp_use_gradient_direction(sdplrp_handle *h) {
     return SDPLRP_OK;
 }
 
-int32_t sdplrp_linesearch_coeffs(sdplrp_handle *h, double bq[5]) {
+// linesearch_coeffs; `descent` (may be null) receives dot(dirt, Gt) of the preceding direction call in the same host round trip
+int32_t api_linesearch_coeffs_descent(sdplrp_handle *h, double bq[5], double *descent) {
     REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
     const bool split = h->obj_mat >= 0;
@@ -736,10 +778,15 @@ int32_t sdplrp_linesearch_coeffs(sdplrp_handle *h, double bq[5]) {
         SDP_CHECK(vec_biquadratic(h));
     }
     h->ls_valid = true;
-    SDP_CHECK(fetch_scalars(h, SC_BQ, 5));
+    static_assert(SC_DESCENT < SC_BQ, "one contiguous fetch covers descent and the coefficients");
+    SDP_CHECK(fetch_scalars(h, SC_DESCENT, SC_BQ + 5 - SC_DESCENT));
     for (int k = 0; k < 5; k++) bq[k] = h->hscal[SC_BQ + k];
+    if (descent) *descent = h->hscal[SC_DESCENT];
     return SDPLRP_OK;
 }
+
+int32_t sdplrp_linesearch_coeffs(sdplrp_handle *h, double bq[5]) { return api_linesearch_coeffs_descent(h, bq, nullptr); }
+
 
 int32_t sdplrp_step(sdplrp_handle *h, double alpha, double *obj) {
     REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);

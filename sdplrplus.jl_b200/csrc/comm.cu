@@ -328,6 +328,13 @@ int32_t comm_allgather_bytes(sdplrp_handle *h, const void *send, void *recv, siz
     return SDPLRP_OK;
 }
 
+// in-place all-gather of equal blocks: rank q's cnt doubles sit at buf + q*cnt
+int32_t comm_allgather_inplace(sdplrp_handle *h, double *buf, size_t cnt) {
+    if (h->world <= 1) return SDPLRP_OK;
+    NCCL_TRY(h, ncclAllGather(buf + (size_t)h->rank * cnt, buf, cnt, ncclDouble, (ncclComm_t)h->nccl, h->stream));
+    return SDPLRP_OK;
+}
+
 // ---- halo exchange of the gather pass ---------------------------------------------------------------------------------
 namespace {
 // out[e] = X[(lo + rows[e / r]) * r + e % r]: the rows the peers gather, in destination order

@@ -18,7 +18,7 @@ constexpr int kLbSmallLen = 17 * 17 + 3 * 17 + 17 + 7;  // Gram (17x17) + three 
 constexpr long long kPartialsLen = (long long)kRedBlocks * kMaxRedK * 8;  // doubles in h->partials
 constexpr int kLongMatThreshold = 64;   // matrices with more triu entries go to the chunked path
 constexpr int kChunkEntries = 2048;     // entries per chunk (one CTA) of a long matrix
-constexpr int kRowGroupMax = 32;        // rows with <= this many nonzeros: one sub-warp lane group per row
+constexpr int kRowGroupMax = 64;        // rows with <= this many nonzeros: one sub-warp lane group per row
 constexpr int kRowWarpMax = 512;        // rows with <= this many: one warp per row; longer: chunks of this size, one warp each
 
 // rows of a CSR pattern binned by length (compacted lists, natural order inside a bin);
@@ -131,6 +131,7 @@ struct sdplrp_handle {
     i64 stage_len = 0;
     i64 l2_persist_bytes = 0;                            // cudaLimitPersistingL2CacheSize set at creation
     i64 hot_rows = -1;                                   // leading (hub) rows of a gathered factor kept in L2; -1 = auto
+    int row_group_max = kRowGroupMax;                    // rows with <= this many nonzeros go to the lane-group-per-row kernels (set before preprocessing)
     int spmm_unroll = 8;                                 // nonzeros per predicated block of the class-0 register kernel (4 or 8)
     int spmm_g0 = 1;                                     // class-0 lane groups of exactly r/2 lanes (0: next power of two)
     int spmm_phases = 0;                                 // 0 = one sweep per gather pass (default); 1 = hub | tail two-phase pass with an
@@ -456,6 +457,9 @@ int32_t perm_upload(sdplrp_handle *h, double *dst_dev, const double *src_host, i
 int32_t perm_download(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 ncols, bool row_major);
 int32_t perm_upload_owned(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 ncols);      // rows [row_lo, row_hi) only
 int32_t perm_download_owned(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 ncols);
+int32_t perm_upload_slice(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 ncols);      // reference rows [rank*S, (rank+1)*S), S = ceil(n/world)
+int32_t perm_download_slice(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 ncols);
+int32_t comm_allgather_inplace(sdplrp_handle *h, double *buf, size_t cnt);
 int32_t perm_device(sdplrp_handle *h, double *dst, const double *src, i64 ncols, bool row_major, bool to_internal);
 int32_t perm_slots_upload(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 len);
 int32_t perm_slots_download(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 len);

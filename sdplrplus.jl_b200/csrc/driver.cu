@@ -19,6 +19,11 @@
 #include <vector>
 #include "common.cuh"
 
+extern "C" {   // internal entry points of api.cu (not part of the public header)
+int32_t api_lbfgs_dir_async(sdplrp_handle *h);
+int32_t api_linesearch_coeffs_descent(sdplrp_handle *h, double bq[5], double *descent);
+}
+
 namespace {
 
 constexpr double kEps = 2.220446049250313e-16;
@@ -154,11 +159,17 @@ void print_row(const sdplrp_config &cfg, i64 T, i64 localiter, i64 it, double L,
 // fallback, line search (exact quartic, or Armijo backtracking for inequality problems), step + gradient + norms.
 // L_val <- the line search's AL value, alpha <- the step, sg <- {obj, ||G||^2, ||pvio||^2}.
 int32_t inner_iteration(sdplrp_handle *h, bool use_armijo, double alpha_max, double *L_val, double *alpha_out, double sg[3]) {
-    double descent = 0.0;
-    SDP_CHECK(sdplrp_lbfgs_dir(h, &descent));
-    if (std::isnan(descent) || descent >= 0.0) SDP_CHECK(sdplrp_use_gradient_direction(h));  // src/sdplr.jl:202-205
-    double alpha = 0.0, bq[5];
-    SDP_CHECK(sdplrp_linesearch_coeffs(h, bq));
+    // The descent test (src/sdplr.jl:201-205) is taken SPECULATIVELY: the line-search pass is enqueued for the L-BFGS direction
+    // right away and `descent` comes back in the same host round trip as the five coefficients; only when the direction turns
+    // out not to be a descent direction (rare) the pass is redone for the gradient direction.  One synchronisation less per
+    // iteration, same decisions and results.
+    double descent = 0.0, alpha = 0.0, bq[5];
+    SDP_CHECK(api_lbfgs_dir_async(h));
+    SDP_CHECK(api_linesearch_coeffs_descent(h, bq, &descent));
+    if (std::isnan(descent) || descent >= 0.0) {
+        SDP_CHECK(sdplrp_use_gradient_direction(h));
+        SDP_CHECK(sdplrp_linesearch_coeffs(h, bq));
+    }
     if (!use_armijo) {
         if (pick_alpha(bq, alpha_max, &alpha, L_val) != SDPLRP_OK)
             return fail(h, SDPLRP_ERR_LINESEARCH, "Error: cubic[1] = " + std::to_string(bq[1]) + " should be less than 0.");

@@ -123,6 +123,7 @@ struct Acc<1> {
     __device__ __forceinline__ void fma(double s, const double *p) { v += s * __ldg(p); }
     __device__ __forceinline__ void fma_hint(double s, const double *p, unsigned long long pol) { v += s * ldg_f64_hint(p, pol); }
     __device__ __forceinline__ void shfl_add(int o) { v += __shfl_xor_sync(0xffffffffu, v, o); }
+    __device__ __forceinline__ void add_from_lane(const Acc &o, int src) { v += __shfl_sync(0xffffffffu, o.v, src & 31); }
     __device__ __forceinline__ void scale_add(double sc, double a, const double *p) { v = sc * (v + a * __ldg(p)); }
     __device__ __forceinline__ void accumulate_onto(double sc, const double *p) { v = p[0] + sc * v; }
     __device__ __forceinline__ void fma_reg(double s, const Acc &o) { v += s * o.v; }
@@ -151,6 +152,10 @@ struct Acc<2> {
     __device__ __forceinline__ void shfl_add(int o) {
         v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
         v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    __device__ __forceinline__ void add_from_lane(const Acc &o, int src) {
+        v.x += __shfl_sync(0xffffffffu, o.v.x, src & 31);
+        v.y += __shfl_sync(0xffffffffu, o.v.y, src & 31);
     }
     __device__ __forceinline__ void scale_add(double sc, double a, const double *p) {
         const double2 x = ldg2(p);
@@ -195,6 +200,7 @@ struct RowArgs {
     int nown;          // INT_MAX on one GPU / replicated patterns: every column reads X
     double *Y;
     int r, G;
+    int Gw;            // lanes per group of the warp-per-row kernels (= pieces per row when <= 16, else G)
     int G0;            // lanes per row of the class-0 kernel (= pieces per row: no idle lanes, no shuffles there)
     int hot_rows;      // gathers of columns < hot_rows are L2 evict_last
     double scale, yobj;
@@ -280,7 +286,9 @@ __device__ __forceinline__ void finish_sums(const RowArgs &a, double s0, double 
 // class 0: one group of G0 lanes per row (G0 = pieces per row when that fits a warp: 6 rows per warp at r = 10);
 // the row's nonzeros are taken NB at a time, fully predicated, so a row of <= NB nonzeros costs one round trip
 // ptr -> idx/val -> gathers with NB independent 128-bit gathers in flight per lane
-template <int VEC, int MAXU, bool IND, int EPI, int NB>
+// GH: multi-GPU local view (columns >= a.nown are ghost rows read from a.Xgh); false: every column reads a.X -- a separate
+// instantiation, because the pointer select costs the single-GPU kernel 20 % (2.30 -> 2.85 ms, profiles/r2_ncu_launches.csv)
+template <int VEC, int MAXU, bool IND, int EPI, int NB, bool GH>
 __global__ void LB_GROUP k_rows_group(RowArgs a) {
     const int nv = a.r / VEC;
     const int G = a.G0;
@@ -315,7 +323,7 @@ __global__ void LB_GROUP k_rows_group(RowArgs a) {
                 if (c < nv) {
 #pragma unroll
                     for (int j = 0; j < NB; j++)
-                        if (k0 + j < end) acc[u].fma_hint(vv[j], (cc[j] < a.nown ? a.X : a.Xgh) + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
+                        if (k0 + j < end) acc[u].fma_hint(vv[j], ((!GH || cc[j] < a.nown) ? a.X : a.Xgh) + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
                 }
             }
         }
@@ -328,11 +336,16 @@ __global__ void LB_GROUP k_rows_group(RowArgs a) {
 // CHUNK: the work items are the kRowWarpMax-nonzero chunks of the long rows (class 2) and the warp leaves its partial
 // sums in a.scratch (combined per row, in chunk order, by k_rows_combine) -- a hub row of 30 k nonzeros is spread over
 // 60 warps instead of serialising one CTA, which is what lets the pass scale when the rows are divided among GPUs.
-template <int VEC, int MAXU, bool IND, int EPI, bool CHUNK>
+template <int VEC, int MAXU, bool IND, int EPI, bool CHUNK, bool GH>
 __global__ void LB_WARP k_rows_warp(RowArgs a) {
     const int nv = a.r / VEC;
     const int lane = threadIdx.x & 31;
-    const int lg = lane & (a.G - 1), grp = lane / a.G, ng = 32 / a.G;
+    // lane groups of Gw lanes split the nonzeros of the row.  Gw = the number of 16-byte pieces of a factor row when that is
+    // <= 16 (5 at r = 10: six groups, 24 gathers in flight per warp step, lanes 30-31 idle) -- with the next power of two
+    // (8) three lanes of every group idled: 16 gathers per step.  Wider rows keep power-of-two groups with several units.
+    const int Gw = a.Gw, ng = 32 / Gw;
+    const int grp = lane / Gw, lg = lane - grp * Gw;
+    const bool lane_ok = grp < ng;
     const i64 warp = (i64)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
     const i64 n_warps = (i64)gridDim.x * (TPB / 32);
     const unsigned long long p_hot = pol_evict_last(), p_str = pol_evict_first();
@@ -345,7 +358,7 @@ __global__ void LB_WARP k_rows_warp(RowArgs a) {
         Acc<VEC> acc[MAXU];
 #pragma unroll
         for (int u = 0; u < MAXU; u++) acc[u].zero();
-        for (int k0 = beg + grp * 4; k0 < end; k0 += ng * 4) {
+        for (int k0 = beg + grp * 4; lane_ok && k0 < end; k0 += ng * 4) {
             int cc[4];
             double vv[4];
 #pragma unroll
@@ -356,27 +369,36 @@ __global__ void LB_WARP k_rows_warp(RowArgs a) {
             }
 #pragma unroll
             for (int u = 0; u < MAXU; u++) {
-                const int c = lg + u * a.G;
+                const int c = lg + u * Gw;
                 if (c < nv) {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (k0 + j < end) acc[u].fma_hint(vv[j], (cc[j] < a.nown ? a.X : a.Xgh) + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
+                        if (k0 + j < end) acc[u].fma_hint(vv[j], ((!GH || cc[j] < a.nown) ? a.X : a.Xgh) + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
                 }
             }
         }
-        // sum the lane groups (xor offsets G, 2G, ... < 32)
+        // sum the lane groups: xor offsets Gw, 2Gw, ... < 32 for power-of-two groups; otherwise group 0 adds the groups
+        // 1, 2, ... in that order (every lane takes part in the shuffles, only group 0's totals are used)
+        if ((Gw & (Gw - 1)) == 0) {
 #pragma unroll
-        for (int u = 0; u < MAXU; u++)
-            for (int o = a.G; o < 32; o <<= 1) acc[u].shfl_add(o);
+            for (int u = 0; u < MAXU; u++)
+                for (int o = Gw; o < 32; o <<= 1) acc[u].shfl_add(o);
+        } else {
+#pragma unroll
+            for (int u = 0; u < MAXU; u++) {
+                const Acc<VEC> own = acc[u];
+                for (int o = 1; o < ng; o++) acc[u].add_from_lane(own, (((lane_ok ? grp : 0) + o) % ng) * Gw + lg);
+            }
+        }
         if (grp == 0) {
             if (CHUNK) {
 #pragma unroll
                 for (int u = 0; u < MAXU; u++) {
-                    const int c = lg + u * a.G;
+                    const int c = lg + u * Gw;
                     if (c < nv) acc[u].store(a.scratch + (size_t)q * a.r + c * VEC);
                 }
             } else {
-                row_epilogue<VEC, MAXU, EPI>(a, i, acc, lg, nv, s0, s1, a.G);
+                row_epilogue<VEC, MAXU, EPI>(a, i, acc, lg, nv, s0, s1, Gw);
             }
         }
     }
@@ -615,7 +637,7 @@ static int32_t classes_join(sdplrp_handle *h) {
     return SDPLRP_OK;
 }
 
-template <int VEC, int MAXU, bool IND, int EPI>
+template <int VEC, int MAXU, bool IND, int EPI, bool GH>
 int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const TileLayout &longs, double *sums /* 3 x 2 or null */,
                        bool long_empty = false, int class_mask = 7) {
     const int gpb = TPB / a.G;
@@ -640,14 +662,14 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
             continue;
         }
         if (c == 0) {
-            if (h->spmm_unroll >= 8) k_rows_group<VEC, MAXU, IND, EPI, 8><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
-            else k_rows_group<VEC, MAXU, IND, EPI, 4><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
+            if (h->spmm_unroll >= 8) k_rows_group<VEC, MAXU, IND, EPI, 8, GH><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
+            else k_rows_group<VEC, MAXU, IND, EPI, 4, GH><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
         } else if (c == 1) {
-            k_rows_warp<VEC, MAXU, IND, EPI, false><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
+            k_rows_warp<VEC, MAXU, IND, EPI, false, GH><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
         } else if (long_empty) {
             RowArgs b = a;
             b.beg_arr = a.ptr + 1; b.end_arr = a.ptr + 1;
-            k_rows_warp<VEC, MAXU, IND, EPI, false><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
+            k_rows_warp<VEC, MAXU, IND, EPI, false, GH><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
         } else {
             // long rows: one warp per chunk, then the per-row combination with the epilogue
             const i64 need = longs.n_chunks * (i64)a.r;
@@ -660,7 +682,7 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
             b.chunk_start = longs.chunk_start; b.chunk_end = longs.chunk_end; b.chunk_row = longs.chunk_row;
             b.long_rows = longs.long_rows; b.long_cptr = longs.long_cptr; b.scratch = h->tile_scratch;
             b.n_rows = longs.n_chunks;
-            k_rows_warp<VEC, MAXU, IND, EPI, true><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
+            k_rows_warp<VEC, MAXU, IND, EPI, true, GH><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
             KLAUNCH(h);
             b.n_rows = longs.n_long;
             k_rows_combine<VEC, MAXU, EPI><<<grid_for(b.n_rows, gpb, 4 * kNumSM), TPB, 0, st>>>(b);
@@ -688,13 +710,26 @@ int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const Til
     a.G0 = (nv <= 32 && h->spmm_g0) ? nv : a.G;   // class 0: exactly one lane per piece
     a.hot_rows = (int)(hot_override >= 0 ? hot_override : tile_hot_rows(h));
     const int units = (nv + a.G - 1) / a.G;
+    a.Gw = (h->spmm_g0 && nv <= 16 && units == 1) ? nv : a.G;
     if (units > 4) return fail(h, SDPLRP_ERR_ARG, "rank too large for the sparse kernels (r <= 256 even / 128 odd)");
+    // the ghost-aware instantiations exist only for the shapes of the multi-GPU gather pass (plain values, EPI 0 / 2 / 4)
+    constexpr bool kGhostShape = !IND && (EPI == 0 || EPI == 2 || EPI == 4);
+    const bool gh = a.nown != 0x7fffffff;
+    if (gh && !kGhostShape) return fail(h, SDPLRP_ERR_STATE, "ghost columns are only supported by the objective gather pass");
+#define LAUNCH_CLS(V, U)                                                                                      \
+    do {                                                                                                      \
+        if constexpr (kGhostShape) {                                                                          \
+            if (gh) return launch_classes<V, U, IND, EPI, true>(h, a, cls, longs, sums, long_empty, class_mask); \
+        }                                                                                                     \
+        return launch_classes<V, U, IND, EPI, false>(h, a, cls, longs, sums, long_empty, class_mask);          \
+    } while (0)
     if (vec2) {
-        if (units == 1) return launch_classes<2, 1, IND, EPI>(h, a, cls, longs, sums, long_empty, class_mask);
-        return launch_classes<2, 4, IND, EPI>(h, a, cls, longs, sums, long_empty, class_mask);
+        if (units == 1) LAUNCH_CLS(2, 1);
+        LAUNCH_CLS(2, 4);
     }
-    if (units == 1) return launch_classes<1, 1, IND, EPI>(h, a, cls, longs, sums, long_empty, class_mask);
-    return launch_classes<1, 4, IND, EPI>(h, a, cls, longs, sums, long_empty, class_mask);
+    if (units == 1) LAUNCH_CLS(1, 1);
+    LAUNCH_CLS(1, 4);
+#undef LAUNCH_CLS
 }
 
 // mid[i] = first position of row i whose column is >= hub_cols (columns are ascending inside a row, hubs first)

@@ -24,6 +24,16 @@ __global__ void k_perm_copy(i64 n, i64 ncols, i64 rs, i64 cs, const int *__restr
     }
 }
 
+// stage[(i - lo)*ncols + c] = src[perm[i]*ncols + c] for the reference rows i in [lo, hi)
+__global__ void k_perm_rows_range(i64 lo, i64 hi, i64 ncols, const int *__restrict__ perm, const double *__restrict__ src,
+                                  double *__restrict__ dst) {
+    const i64 total = (hi - lo) * ncols;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 i = e / ncols, c = e - i * ncols;
+        dst[e] = src[(size_t)(perm ? perm[lo + i] : lo + i) * ncols + c];
+    }
+}
+
 __global__ void k_perm_slots(i64 len, const int *__restrict__ map, const double *__restrict__ src, double *__restrict__ dst,
                              bool scatter) {
     for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < len; k += (i64)gridDim.x * blockDim.x) {
@@ -203,5 +213,47 @@ int32_t perm_download_owned(sdplrp_handle *h, const double *src_dev, double *dst
     const int *ref = h->own_ref_rows.data();
     const double *st = h->host_stage;
     parallel_rows(nloc, [=](i64 a, i64 b) { for (i64 i = a; i < b; i++) memcpy(dst_host + (size_t)ref[i] * ncols, st + i * ncols, (size_t)ncols * 8); });
+    return SDPLRP_OK;
+}
+
+// ---- several GPUs: contiguous slices of the caller's matrix ------------------------------------------------------------------
+// Rank q moves rows [q*S, (q+1)*S) of the caller's (reference-order) matrix over PCIe, S = ceil(n / world); the slices are
+// all-gathered over NVLink into the staging array and permuted on the device (upload), or the matrix is completed over
+// NVLink and the rank's slice permuted out (download).  n*r/world doubles per rank cross PCIe, contiguous on both sides.
+static void slice_range(const sdplrp_handle *h, i64 *S, i64 *lo, i64 *hi) {
+    *S = (h->n + h->world - 1) / h->world;
+    *lo = std::min<i64>(h->n, (i64)h->rank * *S);
+    *hi = std::min<i64>(h->n, *lo + *S);
+}
+
+int32_t perm_upload_slice(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 ncols) {
+    i64 S, lo, hi;
+    slice_range(h, &S, &lo, &hi);
+    SDP_CHECK(perm_stage(h, (i64)h->world * S * ncols));
+    if (hi > lo) CUDA_TRY(h, cudaMemcpyAsync(h->stage + (size_t)lo * ncols, src_host + (size_t)lo * ncols, (size_t)((hi - lo) * ncols) * 8, cudaMemcpyHostToDevice, h->stream));
+    SDP_CHECK(comm_allgather_inplace(h, h->stage, (size_t)(S * ncols)));
+    const i64 len = h->n * ncols;
+    if (h->relabeled) {
+        k_perm_copy<true><<<grid_for(len, TPB, kRedBlocks * 4), TPB, 0, h->stream>>>(h->n, ncols, ncols, 1, h->perm, h->stage, dst_dev);
+        KLAUNCH(h);
+        CUDA_TRY(h, cudaGetLastError());
+    } else {
+        CUDA_TRY(h, cudaMemcpyAsync(dst_dev, h->stage, (size_t)len * 8, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SDPLRP_OK;
+}
+
+// src_dev must hold every row (the caller completes it over NVLink first)
+int32_t perm_download_slice(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 ncols) {
+    i64 S, lo, hi;
+    slice_range(h, &S, &lo, &hi);
+    if (hi <= lo) return SDPLRP_OK;
+    SDP_CHECK(perm_stage(h, (i64)h->world * S * ncols));
+    k_perm_rows_range<<<grid_for((hi - lo) * ncols, TPB, kRedBlocks * 4), TPB, 0, h->stream>>>(lo, hi, ncols, h->relabeled ? h->perm : nullptr, src_dev, h->stage);
+    KLAUNCH(h);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(dst_host + (size_t)lo * ncols, h->stage, (size_t)((hi - lo) * ncols) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return SDPLRP_OK;
 }

@@ -390,10 +390,10 @@ __global__ void k_dyn_rows(i64 nnzF, const int *__restrict__ flag, const int *__
 __global__ void k_gather_ptr(i64 n, const int *__restrict__ full_ptr, const int *__restrict__ pos, int *__restrict__ out) {
     for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i <= n; i += (i64)gridDim.x * blockDim.x) out[i] = pos[full_ptr[i]];
 }
-__global__ void k_class_flags(i64 n, const int *__restrict__ ptr, int *__restrict__ f0, int *__restrict__ f1, int *__restrict__ f2) {
+__global__ void k_class_flags(i64 n, int gmax, const int *__restrict__ ptr, int *__restrict__ f0, int *__restrict__ f1, int *__restrict__ f2) {
     for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
         const int len = ptr[i + 1] - ptr[i];
-        const int c = len <= kRowGroupMax ? 0 : (len <= kRowWarpMax ? 1 : 2);
+        const int c = len <= gmax ? 0 : (len <= kRowWarpMax ? 1 : 2);
         f0[i] = c == 0; f1[i] = c == 1; f2[i] = c == 2;
     }
 }
@@ -454,7 +454,7 @@ int32_t build_classes(sdplrp_handle *h, Tmp &tmp, i64 n, const int *ptr, RowClas
     for (int c = 0; c < 3; c++) { f[c] = tmp.get<int>(h, n + 1, &rc); p[c] = tmp.get<int>(h, n + 1, &rc); }
     if (rc) return rc;
     for (int c = 0; c < 3; c++) CUDA_TRY(h, cudaMemsetAsync(f[c], 0, (size_t)(n + 1) * sizeof(int), st));
-    k_class_flags<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, ptr, f[0], f[1], f[2]); KLAUNCH(h);
+    k_class_flags<<<grid_for(n, TPB, GS), TPB, 0, st>>>(n, h->row_group_max, ptr, f[0], f[1], f[2]); KLAUNCH(h);
     int cnt[3];
     for (int c = 0; c < 3; c++) {
         SDP_CHECK(exclusive_scan(h, f[c], p[c], n + 1));

@@ -153,7 +153,7 @@ class B200Engine:
     def init_vars(self, r, Rt0, lambda0, sigma0, numlbfgsvecs):
         """SolverVars(Rt0, lambda0, lambda_ub, r, sigma_0) + lbfgs_init."""
         self.h.set_rank(r, numlbfgsvecs)
-        self.h.upload_mat_owned(_lib.MAT_R, np.ascontiguousarray(Rt0, dtype=np.float64))   # several GPUs: own rows only over PCIe
+        self.h.upload_mat_slice(_lib.MAT_R, np.ascontiguousarray(Rt0, dtype=np.float64))   # several GPUs: 1/world of the matrix per PCIe link, the rest over NVLink
         lam = np.ascontiguousarray(lambda0, dtype=np.float64)
         ct = self.data.constraint_types
         if ct is not None and np.any(ct):  # lambda_ub = 0 on inequalities (src/structs.jl:225-268); equalities: min(x, inf) = x,

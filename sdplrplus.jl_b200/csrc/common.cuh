@@ -63,8 +63,9 @@ struct HaloPlan {
     TileLayout longs;                    // their long rows in chunks
     int *send_rows[2] = {nullptr, nullptr};                   // local row ids to pack, grouped by destination rank
     std::vector<long long> send_off[2], recv_off[2];          // world+1 row offsets per class
-    double *sendbuf = nullptr, *ghost = nullptr;              // (n_send[0]+n_send[1]) x r and (n_ghost[0]+n_ghost[1]) x r
-    long long sendbuf_len = 0, ghost_len = 0;
+    double *sendbuf = nullptr;                                // (n_send[0] + n_send[1]) x r
+    double *xc = nullptr;                                     // the gathered operand of a pass, compact: [own rows | hub ghosts | tail ghosts] x r
+    long long sendbuf_len = 0, xc_len = 0;
 };
 
 struct LowRank {

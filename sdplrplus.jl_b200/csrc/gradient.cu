@@ -196,8 +196,6 @@ struct RowArgs {
     const double *val;
     const int *src;    // IND: value = val[src[k]]
     const double *X;
-    const double *Xgh; // multi-GPU local view: columns >= nown are ghosts and read from Xgh + c*r (Xgh = ghost buffer - nown*r)
-    int nown;          // INT_MAX on one GPU / replicated patterns: every column reads X
     double *Y;
     int r, G;
     int Gw;            // lanes per group of the warp-per-row kernels (= pieces per row when <= 16, else G)
@@ -286,9 +284,7 @@ __device__ __forceinline__ void finish_sums(const RowArgs &a, double s0, double 
 // class 0: one group of G0 lanes per row (G0 = pieces per row when that fits a warp: 6 rows per warp at r = 10);
 // the row's nonzeros are taken NB at a time, fully predicated, so a row of <= NB nonzeros costs one round trip
 // ptr -> idx/val -> gathers with NB independent 128-bit gathers in flight per lane
-// GH: multi-GPU local view (columns >= a.nown are ghost rows read from a.Xgh); false: every column reads a.X -- a separate
-// instantiation, because the pointer select costs the single-GPU kernel 20 % (2.30 -> 2.85 ms, profiles/r2_ncu_launches.csv)
-template <int VEC, int MAXU, bool IND, int EPI, int NB, bool GH>
+template <int VEC, int MAXU, bool IND, int EPI, int NB>
 __global__ void LB_GROUP k_rows_group(RowArgs a) {
     const int nv = a.r / VEC;
     const int G = a.G0;
@@ -323,7 +319,7 @@ __global__ void LB_GROUP k_rows_group(RowArgs a) {
                 if (c < nv) {
 #pragma unroll
                     for (int j = 0; j < NB; j++)
-                        if (k0 + j < end) acc[u].fma_hint(vv[j], ((!GH || cc[j] < a.nown) ? a.X : a.Xgh) + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
+                        if (k0 + j < end) acc[u].fma_hint(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
                 }
             }
         }
@@ -336,7 +332,7 @@ __global__ void LB_GROUP k_rows_group(RowArgs a) {
 // CHUNK: the work items are the kRowWarpMax-nonzero chunks of the long rows (class 2) and the warp leaves its partial
 // sums in a.scratch (combined per row, in chunk order, by k_rows_combine) -- a hub row of 30 k nonzeros is spread over
 // 60 warps instead of serialising one CTA, which is what lets the pass scale when the rows are divided among GPUs.
-template <int VEC, int MAXU, bool IND, int EPI, bool CHUNK, bool GH>
+template <int VEC, int MAXU, bool IND, int EPI, bool CHUNK>
 __global__ void LB_WARP k_rows_warp(RowArgs a) {
     const int nv = a.r / VEC;
     const int lane = threadIdx.x & 31;
@@ -373,7 +369,7 @@ __global__ void LB_WARP k_rows_warp(RowArgs a) {
                 if (c < nv) {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (k0 + j < end) acc[u].fma_hint(vv[j], ((!GH || cc[j] < a.nown) ? a.X : a.Xgh) + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
+                        if (k0 + j < end) acc[u].fma_hint(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
                 }
             }
         }
@@ -637,7 +633,7 @@ static int32_t classes_join(sdplrp_handle *h) {
     return SDPLRP_OK;
 }
 
-template <int VEC, int MAXU, bool IND, int EPI, bool GH>
+template <int VEC, int MAXU, bool IND, int EPI>
 int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const TileLayout &longs, double *sums /* 3 x 2 or null */,
                        bool long_empty = false, int class_mask = 7) {
     const int gpb = TPB / a.G;
@@ -662,14 +658,14 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
             continue;
         }
         if (c == 0) {
-            if (h->spmm_unroll >= 8) k_rows_group<VEC, MAXU, IND, EPI, 8, GH><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
-            else k_rows_group<VEC, MAXU, IND, EPI, 4, GH><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
+            if (h->spmm_unroll >= 8) k_rows_group<VEC, MAXU, IND, EPI, 8><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
+            else k_rows_group<VEC, MAXU, IND, EPI, 4><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
         } else if (c == 1) {
-            k_rows_warp<VEC, MAXU, IND, EPI, false, GH><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
+            k_rows_warp<VEC, MAXU, IND, EPI, false><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
         } else if (long_empty) {
             RowArgs b = a;
             b.beg_arr = a.ptr + 1; b.end_arr = a.ptr + 1;
-            k_rows_warp<VEC, MAXU, IND, EPI, false, GH><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
+            k_rows_warp<VEC, MAXU, IND, EPI, false><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
         } else {
             // long rows: one warp per chunk, then the per-row combination with the epilogue
             const i64 need = longs.n_chunks * (i64)a.r;
@@ -682,7 +678,7 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
             b.chunk_start = longs.chunk_start; b.chunk_end = longs.chunk_end; b.chunk_row = longs.chunk_row;
             b.long_rows = longs.long_rows; b.long_cptr = longs.long_cptr; b.scratch = h->tile_scratch;
             b.n_rows = longs.n_chunks;
-            k_rows_warp<VEC, MAXU, IND, EPI, true, GH><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
+            k_rows_warp<VEC, MAXU, IND, EPI, true><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
             KLAUNCH(h);
             b.n_rows = longs.n_long;
             k_rows_combine<VEC, MAXU, EPI><<<grid_for(b.n_rows, gpb, 4 * kNumSM), TPB, 0, st>>>(b);
@@ -706,30 +702,17 @@ int32_t launch_csr(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const Til
         a.own_lo = h->row_lo;
         a.own_hi = h->row_hi;
     }
-    if (!a.Xgh) { a.Xgh = a.X; a.nown = 0x7fffffff; }
     a.G0 = (nv <= 32 && h->spmm_g0) ? nv : a.G;   // class 0: exactly one lane per piece
     a.hot_rows = (int)(hot_override >= 0 ? hot_override : tile_hot_rows(h));
     const int units = (nv + a.G - 1) / a.G;
     a.Gw = (h->spmm_g0 && nv <= 16 && units == 1) ? nv : a.G;
     if (units > 4) return fail(h, SDPLRP_ERR_ARG, "rank too large for the sparse kernels (r <= 256 even / 128 odd)");
-    // the ghost-aware instantiations exist only for the shapes of the multi-GPU gather pass (plain values, EPI 0 / 2 / 4)
-    constexpr bool kGhostShape = !IND && (EPI == 0 || EPI == 2 || EPI == 4);
-    const bool gh = a.nown != 0x7fffffff;
-    if (gh && !kGhostShape) return fail(h, SDPLRP_ERR_STATE, "ghost columns are only supported by the objective gather pass");
-#define LAUNCH_CLS(V, U)                                                                                      \
-    do {                                                                                                      \
-        if constexpr (kGhostShape) {                                                                          \
-            if (gh) return launch_classes<V, U, IND, EPI, true>(h, a, cls, longs, sums, long_empty, class_mask); \
-        }                                                                                                     \
-        return launch_classes<V, U, IND, EPI, false>(h, a, cls, longs, sums, long_empty, class_mask);          \
-    } while (0)
     if (vec2) {
-        if (units == 1) LAUNCH_CLS(2, 1);
-        LAUNCH_CLS(2, 4);
+        if (units == 1) return launch_classes<2, 1, IND, EPI>(h, a, cls, longs, sums, long_empty, class_mask);
+        return launch_classes<2, 4, IND, EPI>(h, a, cls, longs, sums, long_empty, class_mask);
     }
-    if (units == 1) LAUNCH_CLS(1, 1);
-    LAUNCH_CLS(1, 4);
-#undef LAUNCH_CLS
+    if (units == 1) return launch_classes<1, 1, IND, EPI>(h, a, cls, longs, sums, long_empty, class_mask);
+    return launch_classes<1, 4, IND, EPI>(h, a, cls, longs, sums, long_empty, class_mask);
 }
 
 // mid[i] = first position of row i whose column is >= hub_cols (columns are ascending inside a row, hubs first)
@@ -860,10 +843,18 @@ static int32_t grad_obj_spmm_halo(sdplrp_handle *h, const double *X, double *Y, 
     const size_t off = (size_t)h->row_lo * h->r;
     RowArgs a = {};
     a.ptr = p.lptr; a.idx = p.lidx; a.val = p.lval; a.src = nullptr;
-    a.X = X + off; a.Y = Y + off; a.Z = Z ? Z + off : nullptr; a.scale = 1.0;
-    a.Xgh = p.ghost - (size_t)p.nloc * h->r; a.nown = (int)p.nloc;
+    // the gathered operand is the compact array [own rows | hub ghosts | tail ghosts] that halo_begin filled (own rows copied,
+    // ghosts received in place): one base pointer for every column, as on one GPU (a two-base select in the gather address
+    // cost the row kernels 20-25 %: 2.30 -> 2.85 ms for the short-row kernel of C5)
+    (void)X;
+    a.X = p.xc; a.Y = Y + off; a.Z = Z ? Z + off : nullptr; a.scale = 1.0;
     a.own_lo = 0; a.own_hi = p.nloc;
     CUDA_TRY(h, cudaMemsetAsync(sums6, 0, 6 * sizeof(double), h->stream));
+    if (h->halo_mode == 2) {   // one sweep over whole rows once both classes are in (no second visit of the rows, exchange exposed)
+        SDP_CHECK(halo_wait(h, 0));
+        SDP_CHECK(halo_wait(h, 1));
+        return launch_csr<false, 2>(h, a, p.cls, p.longs, sums6);
+    }
     SDP_CHECK(halo_wait(h, 0));
     RowArgs a1 = a;
     a1.end_arr = p.lmid;                                   // phase A: plain store of the [own | hub] part

@@ -621,7 +621,7 @@ __global__ void k_local_rows(i64 nloc, i64 lo, i64 B, int rank, i64 Hq, int ngh0
 void halo_free(sdplrp_handle *h) {
     HaloPlan &p = h->halo;
     dev_free(&p.lptr); dev_free(&p.lmid); dev_free(&p.lidx); dev_free(&p.lval);
-    dev_free(&p.send_rows[0]); dev_free(&p.send_rows[1]); dev_free(&p.sendbuf); dev_free(&p.ghost);
+    dev_free(&p.send_rows[0]); dev_free(&p.send_rows[1]); dev_free(&p.sendbuf); dev_free(&p.xc);
     dev_free(&p.cls.storage);
     tile_free(p.longs);
     p = HaloPlan();

@@ -186,20 +186,32 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_oracle_run(sp, n, edges, r, steps, warmup, seed, single_thread_steps=1, budget_s=150.0):
+def cpu_oracle_run(sp, n, edges, r, steps, warmup, seed, single_thread_steps=1, budget_s=150.0, adopt=None):
     """The reference's CPU path (oracle port of src/*.jl) on the SAME workload as the GPU arm: the same graph
     (same generator, same seed, same n and edge count), the same R0, the same loop body.  Timed twice:
     with all host threads (OpenMP; the thread count is set here, whatever the launcher exported) and with ONE
     thread, which is the reference's own benchmarking protocol (exps/README.md:23, exps/test.jl:46 -- no threading
-    anywhere in src/).  `steps` is clipped so that the whole run stays within `budget_s` of CPU time."""
+    anywhere in src/).  `steps` is clipped so that the whole run stays within `budget_s` of CPU time.
+    adopt = (asm, maps, E): the cpu_baseline leg of the B200 arm hands over the index maps it exported from the library
+    (they are bit-identical to the oracle's own, tests/test_gpu_parity.py) so that this leg does not spend a minute on the
+    oracle's single-threaded sort of 1.8e8 triplets -- the SETUP only; every timed iteration is the oracle's.  The reference
+    arm (--impl reference) never does this: it preprocesses by itself."""
     from oracle import pyoracle
     lib = pyoracle.load()
     cores = host_threads()
     lib.orc_set_threads(cores)
-    asm, b, normC, E, gen_s = generate(sp, n, edges, seed)
-    data = SimpleData(n, n, b)
     t0 = time.perf_counter()
-    eng = pyoracle.OracleEngine(data, asm=asm)
+    if adopt is not None:
+        asm, maps, E = adopt
+        gen_s = 0.0
+        data = SimpleData(n, n, np.ones(n))
+        eng = pyoracle.OracleEngine(data, asm=asm, maps=maps)
+        del maps
+    else:
+        asm, b, normC, E, gen_s = generate(sp, n, edges, seed)
+        data = SimpleData(n, n, b)
+        t0 = time.perf_counter()
+        eng = pyoracle.OracleEngine(data, asm=asm)
     prep = time.perf_counter() - t0
     del asm
     Rt0 = 2.0 * np.random.default_rng(0).random((n, r)) - 1.0
@@ -314,7 +326,8 @@ def main():
     preprocess_s = time.perf_counter() - t0
     nnzT, nnzF, Ec = handle.pattern_sizes()
     pre_h2d = eng.h2d_bytes
-    del asm
+    if getattr(asm, "device_triplets", None) is not None:
+        asm.device_triplets = None      # the triplets are consumed; the (light) descriptor stays for the cpu_baseline leg
     torch.cuda.empty_cache()
     lo, hi = handle.row_range()
 
@@ -460,7 +473,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_oracle_run(sp, n, args.edges, r, args.cpu_steps, 1, args.seed, single_thread_steps=0, budget_s=30.0)
+            adopt = (asm, handle.pattern_export(), E) if asm.I.size == 0 else None
+            cpu = cpu_oracle_run(sp, n, args.edges, r, args.cpu_steps, 1, args.seed, single_thread_steps=0, budget_s=25.0, adopt=adopt)
+            if adopt is not None:
+                cpu["sample"] += "; setup: index maps adopted from the library's bit-identical export (untimed)"
         except Exception as e:  # the baseline is a reported extra, never a reason to lose the GPU number
             cpu = {"error": repr(e)}
 

@@ -103,10 +103,11 @@ void *sdplrp_stream(sdplrp_handle *h);
  *                 warp each; set BEFORE sdplrp_preprocess
  *   "spmm_unroll" nonzeros per block of the short-row kernels: 8 (default) or 4
  *   "spmm_g0"     1 = lane groups of exactly r/2 lanes per short row (default: 6 rows per warp at r = 10), 0 = next power of two
- *   "halo"        several GPUs: 1 = every rank keeps the objective pattern of its own rows and the gather pass exchanges only the
- *                 factor rows that are actually gathered, hub class first, overlapped with a two-phase pass (default);
+ *   "halo"        several GPUs: every rank keeps the objective pattern of its own rows and the gather pass exchanges only the
+ *                 factor rows that are actually gathered, hub class first.  1 = the tail class travels under a two-phase pass;
  *                 2 = the same exchange, then ONE sweep over whole rows (nothing overlaps the tail class, no second visit of
- *                 the rows); 0 = one all-gather of the whole direction per iteration (round-1 path)
+ *                 the rows); 3 = auto: 1 or 2 from the sizes of the plan (default); 0 = one all-gather of the whole
+ *                 direction per iteration (round-1 path)
  *   "gather_mode" gather pass CD = C*D (gather.cu): 0 = row-binned register kernels, 1 = asynchronous tile pipeline with one
  *                 cp.async.bulk per gathered row, 2 = the same pipeline with 16-byte cp.async row pieces (even ranks <= 64)
  *   "gather_tile", "gather_stages", "gather_warps"  geometry of that pipeline (nonzeros per tile, stages of the

@@ -143,7 +143,8 @@ struct sdplrp_handle {
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     bool fork_open = false;                              // a caller forked the side streams around several launches of one pass
     // multi-GPU halo exchange of the gather pass (preprocess.cu: halo_build, comm.cu)
-    int halo_mode = 1;                                   // 0 = all-gather of the whole factor (round-1 path), 1 = halo exchange overlapped with the pass
+    int halo_mode = 3;                                   // 0 = all-gather of the whole factor (round-1 path), 1 = halo exchange under a two-phase pass,
+                                                         // 2 = halo exchange, then one sweep, 3 = auto (1 or 2 from the plan's sizes; default)
     HaloPlan halo;
     void *nccl_halo = nullptr;                           // second communicator (ncclCommSplit) for the exchange on comm_stream
     cudaStream_t comm_stream = nullptr;

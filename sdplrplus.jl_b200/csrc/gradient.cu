@@ -850,7 +850,20 @@ static int32_t grad_obj_spmm_halo(sdplrp_handle *h, const double *X, double *Y, 
     a.X = p.xc; a.Y = Y + off; a.Z = Z ? Z + off : nullptr; a.scale = 1.0;
     a.own_lo = 0; a.own_hi = p.nloc;
     CUDA_TRY(h, cudaMemsetAsync(sums6, 0, 6 * sizeof(double), h->stream));
-    if (h->halo_mode == 2) {   // one sweep over whole rows once both classes are in (no second visit of the rows, exchange exposed)
+    // Two-phase (the tail exchange runs under phase A) or one sweep over whole rows once both classes are in?  The phases cost a
+    // second visit of every short / medium row (measured: 1.27-1.33x the sweep) and can only hide what phase A lasts.  "auto"
+    // compares the two with rates measured on B200 / NVLink 5 (profiles/r2_multigpu.md): exchange at 450 GB/s, sweep at 39
+    // gathered rows/ns, constraint pass 0.1 ms + 3 TB/s under the exchange.  C5: one sweep at 2 and 8 GPUs, two phases at 4.
+    bool single_sweep = h->halo_mode == 2;
+    if (h->halo_mode == 3) {
+        const double exch = (double)(p.n_ghost[0] + p.n_ghost[1]) * h->r * 8.0 / 450e9 * 1e3;      // ms
+        const double sweep = (double)p.lnnz / 39e9 * 1e3;
+        const double ls = 0.1 + 2.0 * (double)p.nloc * h->r * 8.0 / 3e12 * 1e3;
+        const double hidden = std::min(std::max(0.0, exch - ls - 0.1), 0.58 * 1.27 * sweep);
+        const double extra = 0.33 * sweep + 0.1;
+        single_sweep = hidden < extra + 0.15;
+    }
+    if (single_sweep) {   // one sweep over whole rows once both classes are in (no second visit of the rows, exchange exposed)
         SDP_CHECK(halo_wait(h, 0));
         SDP_CHECK(halo_wait(h, 1));
         return launch_csr<false, 2>(h, a, p.cls, p.longs, sums6);

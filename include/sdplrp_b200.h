@@ -178,13 +178,7 @@ int32_t sdplrp_get_sigma(sdplrp_handle *h, double *sigma);
 int32_t sdplrp_get_obj(sdplrp_handle *h, double *obj);
 int32_t sdplrp_upload_mat(sdplrp_handle *h, int32_t mat_id, const double *src /* r*n */);
 int32_t sdplrp_download_mat(sdplrp_handle *h, int32_t mat_id, double *dst /* r*n */);
-/* Several GPUs (one process per GPU): the same calls restricted to the rows this rank owns (sdplrp_row_range in the
- * library's internal order; any vertex may be owned by any rank).  `src` / `dst` are full-size r x n buffers in the
- * caller's vertex order; only the owned rows are read / written, so a rank moves n*r/world doubles over PCIe.  Rows of
- * other ranks reach a rank over NVLink when a pass needs them.  One GPU: identical to the calls above. */
-int32_t sdplrp_upload_mat_owned(sdplrp_handle *h, int32_t mat_id, const double *src /* r*n */);
-int32_t sdplrp_download_mat_owned(sdplrp_handle *h, int32_t mat_id, double *dst /* r*n */);
-/* The same with CONTIGUOUS slices: rank q reads / writes rows [q*S, min(n, (q+1)*S)) of the caller's matrix, S = ceil(n / world).
+/* Several GPUs (one process per GPU), CONTIGUOUS slices: rank q reads / writes rows [q*S, min(n, (q+1)*S)) of the caller's matrix, S = ceil(n / world).
  * Upload: the slices are exchanged over NVLink, every rank ends up with the whole matrix.  Download: the matrix is completed
  * over NVLink and each rank writes its slice; the union over the ranks is the result. */
 int32_t sdplrp_upload_mat_slice(sdplrp_handle *h, int32_t mat_id, const double *src /* r*n */);

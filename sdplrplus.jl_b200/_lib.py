@@ -58,8 +58,6 @@ _SIGNATURES = {
     "sdplrp_download_mat": [_H, C.c_int32, _p_f64],
     "sdplrp_upload_mat_slice": [_H, C.c_int32, _p_f64],
     "sdplrp_download_mat_slice": [_H, C.c_int32, _p_f64],
-    "sdplrp_upload_mat_owned": [_H, C.c_int32, _p_f64],
-    "sdplrp_download_mat_owned": [_H, C.c_int32, _p_f64],
     "sdplrp_upload_vec": [_H, C.c_int32, _p_f64, C.c_int64],
     "sdplrp_download_vec": [_H, C.c_int32, _p_f64, C.c_int64],
     "sdplrp_A_uu": [_H, C.c_int32, _p_f64],
@@ -355,17 +353,6 @@ class Handle:
         """Several GPUs: rank q writes rows [q*S, (q+1)*S) of the caller's full-size (n, r) array `out`."""
         assert out.flags.c_contiguous and out.dtype == np.float64 and out.size == self.n * self.r
         self._check(self.lib.sdplrp_download_mat_slice(self._h, mat_id, out.ctypes.data_as(_p_f64)))
-
-    def upload_mat_owned(self, mat_id, Rt):
-        """Several GPUs: only the rows this rank owns are read from the full-size (n, r) array and cross PCIe."""
-        a = np.ascontiguousarray(Rt, dtype=np.float64)
-        assert a.size == self.n * self.r, (a.shape, self.n, self.r)
-        self._check(self.lib.sdplrp_upload_mat_owned(self._h, mat_id, a.ctypes.data_as(_p_f64)))
-
-    def download_mat_owned(self, mat_id, out):
-        """Several GPUs: writes this rank's rows into the caller's full-size (n, r) array `out`."""
-        assert out.flags.c_contiguous and out.dtype == np.float64 and out.size == self.n * self.r
-        self._check(self.lib.sdplrp_download_mat_owned(self._h, mat_id, out.ctypes.data_as(_p_f64)))
 
     def download_mat(self, mat_id):
         """Returns the matrix as a numpy (n, r) C-order array (== Julia r x n column-major)."""

@@ -195,8 +195,6 @@ static void free_problem(sdplrp_handle *h) {
     dev_free(&h->lz_v); dev_free(&h->lz_w); dev_free(&h->lz_vp); dev_free(&h->lz_ab); dev_free(&h->lz_basis);
     h->lz_ab_len = 0; h->lz_basis_len = 0;
     dev_free(&h->stage); h->stage_len = 0;
-    if (h->host_stage) { cudaFreeHost(h->host_stage); h->host_stage = nullptr; h->host_stage_len = 0; }
-    h->own_ref_rows.clear(); h->own_ref_lo = -1;
 }
 
 int32_t sdplrp_destroy(sdplrp_handle *h) {
@@ -438,38 +436,6 @@ int32_t sdplrp_upload_mat(sdplrp_handle *h, int32_t id, const double *src) {
     if (id == SDPLRP_MAT_G) h->gram_g_valid = false;
     if (id >= SDPLRP_MAT_S0) { h->gram_pairs_valid = false; h->gram_prestored = -1; }
     return SDPLRP_OK;
-}
-
-// several GPUs: this rank's rows only (the other rows of `src` are not read); the matrix is then valid on its owners and the
-// passes that gather across the partition fetch the rest over NVLink.  One GPU: sdplrp_upload_mat.
-int32_t sdplrp_upload_mat_owned(sdplrp_handle *h, int32_t id, const double *src) {
-    REQUIRE_H(h);
-    REQUIRE_RANK(h);
-    if (h->world <= 1) return sdplrp_upload_mat(h, id, src);
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    SDP_CHECK(lazy_scratch(h, id));
-    if (id == SDPLRP_MAT_CR || id == SDPLRP_MAT_CD) return fail(h, SDPLRP_ERR_ARG, "upload_mat: CR / CD are download-only");
-    double *p = mat_ptr(h, id);
-    if (!p || !src) return fail(h, SDPLRP_ERR_ARG, "upload_mat_owned: bad id");
-    SDP_CHECK(perm_upload_owned(h, p, src, h->r));
-    comm_mark_partial(h, id);
-    if (id == SDPLRP_MAT_R) { h->CR_valid = false; h->ls_valid = false; }
-    if (id == SDPLRP_MAT_D) { h->CD_valid = false; h->ls_valid = false; }
-    if (id == SDPLRP_MAT_G) h->gram_g_valid = false;
-    if (id >= SDPLRP_MAT_S0) { h->gram_pairs_valid = false; h->gram_prestored = -1; }
-    return SDPLRP_OK;
-}
-
-// several GPUs: writes this rank's rows into `dst` (a full-size r x n buffer; the other rows are left alone)
-int32_t sdplrp_download_mat_owned(sdplrp_handle *h, int32_t id, double *dst) {
-    REQUIRE_H(h);
-    REQUIRE_RANK(h);
-    if (h->world <= 1) return sdplrp_download_mat(h, id, dst);
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    SDP_CHECK(lazy_scratch(h, id));
-    double *p = mat_ptr(h, id);
-    if (!p || !dst) return fail(h, SDPLRP_ERR_ARG, "download_mat_owned: bad id");
-    return perm_download_owned(h, p, dst, h->r);
 }
 
 // several GPUs: rank q reads rows [q*S, (q+1)*S) of `src` (the caller's vertex order, S = ceil(n / world)); the slices are

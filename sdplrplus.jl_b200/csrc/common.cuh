@@ -124,10 +124,6 @@ struct sdplrp_handle {
     int *i2r = nullptr, *r2i = nullptr;                  // nnzF: internal full slot <-> reference full slot
     int *full_ptr = nullptr, *full_idx = nullptr;        // n+1, nnzF   the symmetric pattern as CSR in INTERNAL labels
     double *S = nullptr;                                 // nnzF  sparse_S.nzval (internal slot order)
-    std::vector<int> own_ref_rows;                       // host: reference vertex of every owned internal row (perm.cu, owned-row transfers)
-    i64 own_ref_lo = -1;
-    double *host_stage = nullptr;                        // pinned host staging of the owned-row transfers
-    i64 host_stage_len = 0;
     double *stage = nullptr;                             // n x r staging buffer of the permuting copies
     i64 stage_len = 0;
     i64 l2_persist_bytes = 0;                            // cudaLimitPersistingL2CacheSize set at creation
@@ -457,8 +453,6 @@ int32_t halo_wait(sdplrp_handle *h, int klass);
 int32_t perm_stage(sdplrp_handle *h, i64 len);
 int32_t perm_upload(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 ncols, bool row_major);
 int32_t perm_download(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 ncols, bool row_major);
-int32_t perm_upload_owned(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 ncols);      // rows [row_lo, row_hi) only
-int32_t perm_download_owned(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 ncols);
 int32_t perm_upload_slice(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 ncols);      // reference rows [rank*S, (rank+1)*S), S = ceil(n/world)
 int32_t perm_download_slice(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 ncols);
 int32_t comm_allgather_inplace(sdplrp_handle *h, double *buf, size_t cnt);

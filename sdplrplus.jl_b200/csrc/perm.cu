@@ -1,8 +1,6 @@
 // perm.cu -- permuting copies between the reference vertex order (everything that
 // crosses the ABI) and the internal hub-first order the kernels work in
 // (preprocess.cu, "internal vertex order").  With relabeling off they are plain copies.
-#include <string.h>
-#include <thread>
 #include "common.cuh"
 
 namespace {
@@ -154,65 +152,6 @@ int32_t perm_cvec_download(sdplrp_handle *h, const double *src_dev, double *dst_
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemcpyAsync(dst_host, h->stage, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return SDPLRP_OK;
-}
-
-// ---- several GPUs: only the rows this rank owns cross PCIe ------------------------------------------------------------
-// The reference order <-> internal order permutation of the owned rows is applied on the host (iperm[lo..hi) is kept there),
-// so that a rank moves nloc*r doubles instead of n*r: the end-to-end cost of a start point / a result then shrinks with the
-// number of GPUs instead of being paid in full by every rank.
-static int32_t owned_rows_setup(sdplrp_handle *h, i64 len) {
-    const i64 nloc = h->row_hi - h->row_lo;
-    if ((i64)h->own_ref_rows.size() != nloc || h->own_ref_lo != h->row_lo) {
-        h->own_ref_rows.resize((size_t)nloc);
-        if (h->relabeled) {
-            CUDA_TRY(h, cudaMemcpyAsync(h->own_ref_rows.data(), h->iperm + h->row_lo, (size_t)nloc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        } else {
-            for (i64 i = 0; i < nloc; i++) h->own_ref_rows[(size_t)i] = (int)(h->row_lo + i);
-        }
-        h->own_ref_lo = h->row_lo;
-    }
-    if (h->host_stage_len < len) {
-        if (h->host_stage) cudaFreeHost(h->host_stage);
-        h->host_stage = nullptr; h->host_stage_len = 0;
-        CUDA_TRY(h, cudaMallocHost((void **)&h->host_stage, (size_t)len * 8));
-        h->host_stage_len = len;
-    }
-    return SDPLRP_OK;
-}
-
-template <typename F>
-static void parallel_rows(i64 nloc, F f) {
-    const unsigned hw = std::thread::hardware_concurrency();
-    const int T = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(8, hw ? hw : 1), nloc / 65536 + 1));
-    if (T == 1) { f(0, nloc); return; }
-    std::vector<std::thread> th;
-    for (int t = 0; t < T; t++) th.emplace_back([=] { f(nloc * t / T, nloc * (t + 1) / T); });
-    for (auto &x : th) x.join();
-}
-
-int32_t perm_upload_owned(sdplrp_handle *h, double *dst_dev, const double *src_host, i64 ncols) {
-    const i64 nloc = h->row_hi - h->row_lo;
-    if (nloc <= 0) return SDPLRP_OK;
-    SDP_CHECK(owned_rows_setup(h, nloc * ncols));
-    const int *ref = h->own_ref_rows.data();
-    double *st = h->host_stage;
-    parallel_rows(nloc, [=](i64 a, i64 b) { for (i64 i = a; i < b; i++) memcpy(st + i * ncols, src_host + (size_t)ref[i] * ncols, (size_t)ncols * 8); });
-    CUDA_TRY(h, cudaMemcpyAsync(dst_dev + (size_t)h->row_lo * ncols, st, (size_t)(nloc * ncols) * 8, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return SDPLRP_OK;
-}
-
-int32_t perm_download_owned(sdplrp_handle *h, const double *src_dev, double *dst_host, i64 ncols) {
-    const i64 nloc = h->row_hi - h->row_lo;
-    if (nloc <= 0) return SDPLRP_OK;
-    SDP_CHECK(owned_rows_setup(h, nloc * ncols));
-    CUDA_TRY(h, cudaMemcpyAsync(h->host_stage, src_dev + (size_t)h->row_lo * ncols, (size_t)(nloc * ncols) * 8, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    const int *ref = h->own_ref_rows.data();
-    const double *st = h->host_stage;
-    parallel_rows(nloc, [=](i64 a, i64 b) { for (i64 i = a; i < b; i++) memcpy(dst_host + (size_t)ref[i] * ncols, st + i * ncols, (size_t)ncols * 8); });
     return SDPLRP_OK;
 }
 

@@ -79,3 +79,46 @@ def test_blocks_from_device_arrays(sp, gpu_handle_factory):
     for k in MAP_KEYS:
         assert np.array_equal(ma[k], mb[k]), k
     h_host.close(); h_dev.close()
+
+
+def _expand_blocks_numpy(n, blocks, L):
+    """numpy restatement of the device expansion of csrc/blocks.cu (findnz order per matrix)."""
+    Is, Js, Vs, lens, gids = [], [], [], [], []
+    for b in blocks:
+        kind, g0 = b["kind"], b["first_gid"]
+        if kind == L.BLOCK_TRIPLETS:
+            Is.append(b["I"]); Js.append(b["J"]); Vs.append(b["V"]); lens.append([len(b["V"])]); gids.append([g0])
+        elif kind == L.BLOCK_CSC:
+            colptr = np.asarray(b["J"]) - 1
+            cols = np.repeat(np.arange(1, n + 1), np.diff(colptr))
+            Is.append(b["I"]); Js.append(cols); Vs.append(b["V"]); lens.append([len(b["V"])]); gids.append([g0])
+        elif kind == L.BLOCK_DIAG:
+            k = b["count"]
+            pos = np.asarray(b["I"]) if b.get("I") is not None else np.arange(1, k + 1)
+            val = np.asarray(b["V"]) if b.get("V") is not None else np.ones(k)
+            Is.append(pos); Js.append(pos); Vs.append(val); lens.append(np.ones(k, np.int64)); gids.append(np.arange(g0, g0 + k))
+        elif kind == L.BLOCK_EDGES:
+            k = b["count"]
+            u, v = np.asarray(b["I"]), np.asarray(b["J"])
+            w = np.asarray(b["V"]) if b.get("V") is not None else np.ones(k)
+            Is.append(np.stack([u, v], 1).reshape(-1)); Js.append(np.stack([v, u], 1).reshape(-1)); Vs.append(np.repeat(w, 2))
+            lens.append(np.full(k, 2, np.int64)); gids.append(np.arange(g0, g0 + k))
+        else:
+            idx = np.arange(1, n + 1)
+            Is.append(idx); Js.append(idx); Vs.append(np.ones(n)); lens.append([n]); gids.append([g0])
+    cat = lambda xs, dt: np.concatenate([np.asarray(x, dt) for x in xs]) if xs else np.zeros(0, dt)
+    return cat(Is, np.int64), cat(Js, np.int64), cat(Vs, np.float64), np.concatenate([[0], np.cumsum(cat(lens, np.int64))]), cat(gids, np.int64)
+
+
+def test_block_expansion_spec_equals_the_triplet_assembly():
+    """CPU: the expansion rule of the structured blocks (restated in numpy) reproduces assemble_sparse's triplet stream --
+    entry order inside every matrix, matrix offsets and global ids -- for the four families."""
+    import sdplrplus.jl_b200 as sp
+    from sdplrplus.jl_b200.types import structured_blocks, assemble_sparse
+    for name, (C, As, bs) in _cases(sp):
+        data = sp.SDPData(C, As, bs)
+        asm = assemble_sparse(data)
+        blocks, _ = structured_blocks(data)
+        I, J, V, off, gids = _expand_blocks_numpy(data.n, blocks, sp._lib)
+        assert np.array_equal(I, asm.I) and np.array_equal(J, asm.J) and np.array_equal(V, asm.V), name
+        assert np.array_equal(off, asm.mat_off) and np.array_equal(gids, asm.gids), name

@@ -244,7 +244,7 @@ def cpu_oracle_run(sp, n, edges, r, steps, warmup, seed, single_thread_steps=1, 
             "sample": (f"CPU restatement of SDPLRPlus.jl (Julia unavailable in image), OpenMP x{cores}: {k} inner iterations "
                        f"(+{warm_done} warm-up) of the full workload (n={n}, {E} edges, rank {r}); nothing is scaled"),
             "steps": k, "warmup": warm_done, "ms_per_iter": 1e3 * dt / k, "single_thread": single, "cpu_preprocess_s": prep,
-            "graph_generation_s": gen_s, "edges": E,
+            "graph_generation_s": gen_s, "edges": E, "pattern_sizes": [int(x) for x in eng.o.pattern_sizes()],
             "last_iterate": {"L": last[0], "obj": last[1], "gnorm2": last[2], "pnorm2": last[3], "alpha": last[4]}}
 
 
@@ -294,6 +294,7 @@ def main():
                 "ms_per_step": res["ms_per_iter"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_string(args.n, res["edges"], args.rank, 4, args.seed),
+                           "nnzT": res["pattern_sizes"][0], "nnzF": res["pattern_sizes"][1], "E_c": res["pattern_sizes"][2],
                            "l2": "inputs (R 0.8 GB, pattern 2 GB per pass) far exceed the 126 MB L2",
                            "parallelism": f"host cores only: OpenMP x{res['cores']} (headline) and 1 thread (reference protocol)"},
                 "cpu_baseline": res, "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

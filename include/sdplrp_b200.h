@@ -103,6 +103,8 @@ void *sdplrp_stream(sdplrp_handle *h);
  *                 warp each; set BEFORE sdplrp_preprocess
  *   "spmm_unroll" nonzeros per block of the short-row kernels: 8 (default) or 4
  *   "spmm_g0"     1 = lane groups of exactly r/2 lanes per short row (default: 6 rows per warp at r = 10), 0 = next power of two
+ *   "rowc_kernel" pass over the per-row (single-diagonal-entry) constraints: 1 = barrier-free warp kernel, 32/(r/2) whole rows per
+ *                 warp step (default; rows of at most 32 pieces), 0 = shared-memory tile kernel.  Same bits either way
  *   "halo"        several GPUs: every rank keeps the objective pattern of its own rows and the gather pass exchanges only the
  *                 factor rows that are actually gathered, hub class first.  1 = the tail class travels under a two-phase pass;
  *                 2 = the same exchange, then ONE sweep over whole rows (nothing overlaps the tail class, no second visit of

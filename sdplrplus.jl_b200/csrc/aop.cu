@@ -172,6 +172,73 @@ __global__ void __launch_bounds__(TPB) k_A_rowc(long long lo, long long hi, cons
     }
 }
 
+// The same pass without a CTA barrier (nv <= 32; default): a warp takes 32/nv whole rows per step (6 at r = 10: 30 lanes,
+// 480 contiguous bytes per factor), kRowcUnroll steps per trip with every factor load of the trip issued before the first
+// use; the pieces of a row are combined by shuffles in the order of the shared-memory kernel above (piece 0, 1, 2, ...:
+// the two kernels give the same bits), and the lane of piece 0 serves the row's constraints.  The tile kernel above
+// serialises factor loads -> barrier -> (ptr -> val -> stores) -> barrier per CTA (0.68 of the copy peak on C5); here the
+// warps of an SM are at different stages, so the dependent ptr -> val -> store tail of one warp runs under the loads of
+// the others.  Minimum 4 CTAs per SM = a 64-register budget: with __launch_bounds__(TPB) alone ptxas targets 48 registers
+// and interleaves the load pairs with their DMUL/DFMA (one round trip per step); at 64 all 2 x kRowcUnroll 128-bit loads of
+// a trip are issued back to back (checked in the SASS).
+constexpr int kRowcUnroll = 4;
+template <int MODE, int VEC>
+__global__ void __launch_bounds__(TPB, 4) k_A_rowc_warp(long long lo, long long hi, const int *__restrict__ rowc_ptr,
+                                                     const double *__restrict__ rowc_val,
+                                                     const double *__restrict__ U, const double *__restrict__ V, int r,
+                                                     double *__restrict__ out1, double *__restrict__ out2) {
+    typedef Ld<VEC> L;
+    const int nv = r / VEC;
+    const int rpw = 32 / nv;                       // whole rows per warp step
+    const int lane = threadIdx.x & 31;
+    const int rl = lane / nv, c = lane - rl * nv;
+    const bool act = rl < rpw;
+    const long long n_rows = hi - lo;
+    const long long per_trip = (long long)rpw * kRowcUnroll;
+    const long long warp = (long long)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (TPB / 32);
+    for (long long t0 = warp * per_trip; t0 < n_rows; t0 += n_warps * per_trip) {   // warp-uniform
+        double d1[kRowcUnroll], d2[kRowcUnroll];
+        int beg[kRowcUnroll], end[kRowcUnroll];
+        typename L::T a[kRowcUnroll], b[kRowcUnroll];
+        // every load of the trip before the first use: lanes without a live row read (and discard) piece c of the last
+        // row, so that no load sits behind a branch
+#pragma unroll
+        for (int u = 0; u < kRowcUnroll; u++) {
+            const long long i = lo + t0 + (long long)u * rpw + rl;
+            const bool live = act && i < hi;
+            const long long is = live ? i : hi - 1;
+            beg[u] = 0; end[u] = 0;
+            if (live && c == 0) { beg[u] = rowc_ptr[i]; end[u] = rowc_ptr[i + 1]; }
+            a[u] = L::ld(U + (size_t)is * r + c * VEC);
+            if (MODE != 0) b[u] = L::ld(V + (size_t)is * r + c * VEC);
+        }
+#pragma unroll
+        for (int u = 0; u < kRowcUnroll; u++) {
+            d2[u] = 0.0;
+            if (MODE == 0) {
+                d1[u] = L::dot(a[u], a[u]);
+            } else {
+                d1[u] = L::dot(a[u], b[u]);
+                if (MODE == 2) d2[u] = L::dot(b[u], b[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kRowcUnroll; u++) {
+            double s1 = 0.0 + d1[u], s2 = 0.0 + d2[u];   // (0 + piece 0) + piece 1 + ...: the order of k_A_rowc
+            for (int k = 1; k < nv; k++) {               // lanes of a row are lane .. lane + nv - 1 < 32 for c == 0
+                s1 += __shfl_down_sync(0xffffffffu, d1[u], k);
+                if (MODE == 2) s2 += __shfl_down_sync(0xffffffffu, d2[u], k);
+            }
+            for (int k = beg[u]; k < end[u]; k++) {      // empty unless this lane holds piece 0 of a live row
+                const double val = rowc_val[k];
+                out1[k] = (MODE == 2 ? 2.0 : 1.0) * val * s1;  // MODE 2: A_RD is kept already doubled
+                if (MODE == 2) out2[k] = val * s2;
+            }
+        }
+    }
+}
+
 // one CTA per chunk of a long matrix
 template <int MODE, int VEC>
 __global__ void __launch_bounds__(TPB) k_A_long(const int *__restrict__ chunk_mat, const int *__restrict__ long_mat,
@@ -301,7 +368,12 @@ int32_t run_sparse(sdplrp_handle *h, const double *U, const double *V, double *o
         else k_A_short<MODE, 1><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi, skip_mat, sdf);
         KLAUNCH(h);
     }
-    if (h->n_sd > 0) {
+    if (h->n_sd > 0 && nv <= 32 && h->rowc_kernel == 1) {   // barrier-free warp-per-rows pass
+        const int grid_rows = grid_for(h->row_hi - h->row_lo, (TPB / 32) * (32 / nv) * kRowcUnroll, 16 * kNumSM);
+        if (vec2) k_A_rowc_warp<MODE, 2><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, out1, out2);
+        else k_A_rowc_warp<MODE, 1><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, out1, out2);
+        KLAUNCH(h);
+    } else if (h->n_sd > 0) {                               // rows of more than 32 pieces (r > 64 even, r > 32 odd)
         const int grid_rows = grid_for(h->row_hi - h->row_lo, TPB / nv, 16 * kNumSM);
         if (vec2) k_A_rowc<MODE, 2><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, G, out1, out2);
         else k_A_rowc<MODE, 1><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, G, out1, out2);
@@ -388,8 +460,12 @@ int32_t aop_uv(sdplrp_handle *h, const double *U, const double *V, double *out) 
 }
 
 int32_t aop_linesearch(sdplrp_handle *h, bool skip_objective) {
-    CUDA_TRY(h, cudaMemsetAsync(h->A_RD, 0, (size_t)(h->m + 1) * sizeof(double), h->stream));
-    CUDA_TRY(h, cudaMemsetAsync(h->A_DD, 0, (size_t)(h->m + 1) * sizeof(double), h->stream));
+    // One GPU: the row-list pass stores every slot [0, n_sd) on every call (each of those constraints belongs to exactly one
+    // row), so only the slots after them start from zero (2 x 80 MB of stores per iteration saved on C5).  Several GPUs: a
+    // rank stores the slots of its own rows only; everything is zeroed as before.
+    const i64 z0 = h->world == 1 ? h->n_sd : 0;
+    CUDA_TRY(h, cudaMemsetAsync(h->A_RD + z0, 0, (size_t)(h->m + 1 - z0) * sizeof(double), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->A_DD + z0, 0, (size_t)(h->m + 1 - z0) * sizeof(double), h->stream));
     SDP_CHECK(run_sparse<2>(h, h->R, h->D, h->A_RD, h->A_DD, skip_objective ? h->obj_mat : -1));
     return run_lowrank(h, 2, h->R, h->D, h->A_RD, h->A_DD);
 }

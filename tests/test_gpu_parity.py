@@ -219,6 +219,40 @@ def test_A_uv_seam(sp, oracle_mod, handle, fam):
     _relclose(handle.A_uv(sp._lib.MAT_W1, sp._lib.MAT_W1), oe.o.A_uu(V), 1e-13, "A_uv(V,V) == A_uu(V)")
 
 
+@pytest.mark.parametrize("r", [1, 2, 3, 5, 7, 10, 11, 32, 33, 64])
+def test_rowc_kernels_give_the_same_bits(sp, oracle_mod, handle, r):
+    """The barrier-free warp kernel of the per-row constraint pass ("rowc_kernel" 1, default) combines the pieces of a row
+    in the order of the shared-memory tile kernel ("rowc_kernel" 0): A(UU'), A((UV'+VU')/2) and the line-search vectors
+    A_RD / A_DD must agree bit for bit, on a row count (131) that leaves partial warps and partial trips, for every piece
+    count per row (r/2 or r pieces: 1 ... 32 lanes per row; r = 33 takes the tile kernel either way)."""
+    P = sp.problems
+    C, As, bs = P.maxcut(P.erdos_renyi(131, 0.06, 5))
+    data = sp.SDPData(C, As, bs)
+    rng = np.random.default_rng(100 + r)
+    Rt0 = 2 * rng.random((data.n, r)) - 1
+    V = rng.standard_normal(Rt0.shape)
+    got = {}
+    try:
+        for mode in (0, 1):
+            handle.set_option("rowc_kernel", mode)
+            ge, oe = _pair(sp, oracle_mod, handle, data, Rt0, r)
+            handle.upload_mat(sp._lib.MAT_W1, V)
+            ge.fg()
+            ge.set_D(V)
+            bq = ge.linesearch_coeffs()
+            got[mode] = (handle.A_uu(sp._lib.MAT_R), handle.A_uv(sp._lib.MAT_R, sp._lib.MAT_W1),
+                         handle.download_vec(sp._lib.VEC_A_RD, data.m + 1), handle.download_vec(sp._lib.VEC_A_DD, data.m + 1), np.asarray(bq))
+            if mode == 1:
+                _relclose(got[1][0], oe.o.A_uu(Rt0), 1e-13, "A_uu")
+                _relclose(got[1][1], oe.o.A_uv(Rt0, V), 1e-13, "A_uv")
+                oe.fg(); oe.set_D(V)
+                _relclose(bq, oe.linesearch_coeffs(), 1e-11, "bq")
+    finally:
+        handle.set_option("rowc_kernel", 1)
+    for a, b, what in zip(got[0], got[1], ("A_uu", "A_uv", "A_RD", "A_DD", "bq")):
+        np.testing.assert_array_equal(a, b, err_msg=what)
+
+
 @pytest.mark.parametrize("r", [1, 2, 3, 5, 8, 10, 12, 16, 20, 33, 40, 70])
 def test_rank_sweep(sp, oracle_mod, handle, r):
     """runtime rank (dynamic rank doubling, src/sdplr.jl:373-382): odd/even, small/large r"""

@@ -99,6 +99,9 @@ void *sdplrp_stream(sdplrp_handle *h);
  *   "lanczos_dist" several GPUs: 1 = rows of S and of the Lanczos vectors are divided among the ranks (one all-gather of n
  *                 doubles + two scalar all-reduces per step; default), 0 = the q-step Lanczos operator is replicated on every
  *                 rank.  Only without re-orthogonalisation
+ *   "lanczos_l2_mb" one GPU, q-step Lanczos without re-orthogonalisation: for the duration of a run, set aside this many MB of L2
+ *                 for persisting lines and put a stream access-policy window over the leading bytes of the vector the SpMV
+ *                 gathers from (the set-aside is returned when the run ends: it slows every streaming kernel).  0 = off
  *   "row_group_max" rows with at most this many nonzeros are taken by one lane group each (default 64: measured 24 / 32 / 48 / 64 -> 4.27 / 4.14 / 4.06 / 4.02 ms for the C5 pass), longer ones by one
  *                 warp each; set BEFORE sdplrp_preprocess
  *   "spmm_unroll" nonzeros per block of the short-row kernels: 8 (default) or 4

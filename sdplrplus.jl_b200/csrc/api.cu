@@ -390,6 +390,7 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
     if (k == "hot_rows") { h->hot_rows = (i64)value; return SDPLRP_OK; }
     if (k == "spmm_phases") { h->spmm_phases = value < 0 ? 0 : (int)value; return SDPLRP_OK; }
     if (k == "lanczos_dist") { h->lanczos_dist = value > 0 ? 1 : 0; return SDPLRP_OK; }
+    if (k == "lanczos_l2_mb") { h->lanczos_l2_mb = value > 0 ? (int)value : 0; return SDPLRP_OK; }
     if (k == "row_group_max") { h->row_group_max = std::max(1, std::min((int)value, kRowWarpMax)); return SDPLRP_OK; }   // before preprocess
     if (k == "spmm_unroll") { h->spmm_unroll = (int)value; return SDPLRP_OK; }
     if (k == "spmm_g0") { h->spmm_g0 = (int)value; return SDPLRP_OK; }

@@ -134,6 +134,8 @@ struct sdplrp_handle {
     int spmm_g0 = 1;                                     // class-0 lane groups of exactly r/2 lanes (0: next power of two)
     int spmm_phases = 0;                                 // 0 = one sweep per gather pass (default); 1 = hub | tail two-phase pass with an
                                                          // L2-sized hub prefix; > 1 = that many hub columns (gradient.cu, grad_obj_spmm)
+    int lanczos_l2_mb = 0;                               // one GPU, q-step Lanczos: persisting-L2 set-aside (MB) + access-policy window over the gathered vector for the
+                                                         // duration of a run (lanczos.cu, lz_window_*); 0 = off
     int lanczos_dist = 1;                                // world > 1: 1 = row-partitioned q-step Lanczos (default; measured identical to the replicated
                                                          // recurrence on 2 GPUs and 2.5x faster), 0 = replicated operator (lanczos.cu: lz_run_dist)
     cudaStream_t class_streams[2] = {nullptr, nullptr};  // side streams of the medium / long row classes of a gather pass (gradient.cu)

@@ -99,15 +99,16 @@ void *sdplrp_stream(sdplrp_handle *h);
  *   "lanczos_dist" several GPUs: 1 = rows of S and of the Lanczos vectors are divided among the ranks (one all-gather of n
  *                 doubles + two scalar all-reduces per step; default), 0 = the q-step Lanczos operator is replicated on every
  *                 rank.  Only without re-orthogonalisation
- *   "lanczos_l2_mb" one GPU, q-step Lanczos without re-orthogonalisation: for the duration of a run, set aside this many MB of L2
- *                 for persisting lines and put a stream access-policy window over the leading bytes of the vector the SpMV
- *                 gathers from (the set-aside is returned when the run ends: it slows every streaming kernel).  0 = off
  *   "row_group_max" rows with at most this many nonzeros are taken by one lane group each (default 64: measured 24 / 32 / 48 / 64 -> 4.27 / 4.14 / 4.06 / 4.02 ms for the C5 pass), longer ones by one
  *                 warp each; set BEFORE sdplrp_preprocess
  *   "spmm_unroll" nonzeros per block of the short-row kernels: 8 (default) or 4
  *   "spmm_g0"     1 = lane groups of exactly r/2 lanes per short row (default: 6 rows per warp at r = 10), 0 = next power of two
  *   "rowc_kernel" pass over the per-row (single-diagonal-entry) constraints: 1 = barrier-free warp kernel, 32/(r/2) whole rows per
  *                 warp step (default; rows of at most 32 pieces), 0 = shared-memory tile kernel.  Same bits either way
+ *   "dir_ls_fuse" native loop (sdplrp_iterate / sdplrp_solve), one GPU: 1 = the L-BFGS direction kernel also leaves A_RD / A_DD of
+ *                 the per-row constraints, computed from the direction rows while they are in registers (default: the line
+ *                 search does not read D again for them), 0 = separate constraint pass.  Same bits either way
+ *   "tail_ctas"   CTAs per SM of the fused step + gradient pass (1..8, default 4)
  *   "halo"        several GPUs: every rank keeps the objective pattern of its own rows and the gather pass exchanges only the
  *                 factor rows that are actually gathered, hub class first.  1 = the tail class travels under a two-phase pass;
  *                 2 = the same exchange, then ONE sweep over whole rows (nothing overlaps the tail class, no second visit of

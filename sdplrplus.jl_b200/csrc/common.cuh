@@ -130,12 +130,14 @@ struct sdplrp_handle {
     i64 hot_rows = -1;                                   // leading (hub) rows of a gathered factor kept in L2; -1 = auto
     int row_group_max = kRowGroupMax;                    // rows with <= this many nonzeros go to the lane-group-per-row kernels (set before preprocessing)
     int spmm_unroll = 8;                                 // nonzeros per predicated block of the class-0 register kernel (4 or 8)
+    int dir_ls_fuse = 1;                                 // native loop, one GPU: the direction kernel also evaluates the row-list constraints of the line search (lbfgs.cu, k_gram_form_rowc)
+    bool fuse_rowc_request = false;                      // set by the native loop right before the direction whose line search follows at once
+    bool rowc_fused_valid = false;                       // A_RD / A_DD slots [0, n_sd) hold the values of the current direction (consumed by the next line-search pass)
+    int tail_ctas = 4;                                   // CTAs per SM of the fused tail kernel k_step_grad (gradient.cu)
     int rowc_kernel = 1;                                 // row-list constraint pass: 1 = barrier-free warp kernel (r/2 <= 32 pieces), 0 = shared-memory tile kernel (aop.cu)
     int spmm_g0 = 1;                                     // class-0 lane groups of exactly r/2 lanes (0: next power of two)
     int spmm_phases = 0;                                 // 0 = one sweep per gather pass (default); 1 = hub | tail two-phase pass with an
                                                          // L2-sized hub prefix; > 1 = that many hub columns (gradient.cu, grad_obj_spmm)
-    int lanczos_l2_mb = 0;                               // one GPU, q-step Lanczos: persisting-L2 set-aside (MB) + access-policy window over the gathered vector for the
-                                                         // duration of a run (lanczos.cu, lz_window_*); 0 = off
     int lanczos_dist = 1;                                // world > 1: 1 = row-partitioned q-step Lanczos (default; measured identical to the replicated
                                                          // recurrence on 2 GPUs and 2.5x faster), 0 = replicated operator (lanczos.cu: lz_run_dist)
     cudaStream_t class_streams[2] = {nullptr, nullptr};  // side streams of the medium / long row classes of a gather pass (gradient.cu)

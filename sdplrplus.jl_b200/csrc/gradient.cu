@@ -963,7 +963,7 @@ int32_t grad_step_fused(sdplrp_handle *h, double alpha) {
     const bool vec2 = (r % 2 == 0);
     const int nv = vec2 ? r / 2 : r;
     const i64 total = (h->row_hi - h->row_lo) * nv;
-    const int grid = grid_for(total, TPB * 2, kRedBlocks);
+    const int grid = grid_for(total, TPB * 2, h->tail_ctas * kNumSM);   // K = 2 sums: h->partials holds up to 8 CTAs per SM
     const double *CD = split ? h->CD : nullptr;
     double *CR = split ? h->CR : nullptr;
 #define SG_ARGS h->row_lo, h->row_hi, r, alpha, h->sigma, h->y_obj, h->D, h->R, CD, CR, h->rowc_ptr, h->rowc_val, h->lambda, h->lambda_ub, \

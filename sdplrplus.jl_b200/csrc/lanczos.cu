@@ -417,53 +417,11 @@ static int32_t lz_run_dist(sdplrp_handle *h, i64 q, const double *v0_host, uint6
     return SDPLRP_OK;
 }
 
-// Option "lanczos_l2_mb" (one GPU): the SpMV of a step gathers 174.5 M entries of an 80 MB vector on C5 while 2.1 GB of pattern
-// stream through the L2, and LRU keeps only the hub entries (L2 hit 44 %, 4.7 GB of DRAM reads for 2.1 GB of pattern,
-// profiles/r2_ncu_lanczos.csv).  For the duration of a run a persisting set-aside plus a stream access-policy window over the
-// leading bytes of the gathered vector (hubs first = the most gathered entries first) keeps that vector resident; the
-// set-aside is returned afterwards because it slows every streaming kernel of the iteration.
-namespace {
-struct LzWindow {
-    sdplrp_handle *h = nullptr;
-    size_t bytes = 0;
-    bool begin(sdplrp_handle *hh) {
-        if (hh->lanczos_l2_mb <= 0 || hh->world > 1) return false;
-        int maxp = 0, maxw = 0;
-        if (cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, hh->device) != cudaSuccess ||
-            cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, hh->device) != cudaSuccess) { cudaGetLastError(); return false; }
-        size_t want = std::min<size_t>((size_t)maxp, (size_t)hh->lanczos_l2_mb << 20);
-        if (want == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); return false; }
-        h = hh;
-        bytes = std::min<size_t>(want, (size_t)maxw);
-        return true;
-    }
-    void point_at(const double *v, i64 n) {   // launches enqueued after this call gather `v` through the window
-        if (!h) return;
-        cudaStreamAttrValue av = {};
-        av.accessPolicyWindow.base_ptr = const_cast<double *>(v);
-        av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)n * sizeof(double));
-        av.accessPolicyWindow.hitRatio = 1.0f;
-        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
-    }
-    void end() {
-        if (!h) return;
-        cudaStreamAttrValue av = {};
-        av.accessPolicyWindow.num_bytes = 0;
-        if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
-        if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)h->l2_persist_bytes) != cudaSuccess) cudaGetLastError();
-        h = nullptr;
-    }
-    ~LzWindow() { end(); }
-};
-}  // namespace
-
+// Measured and NOT built in (profiles/r2_call9_lanczos_l2_window.md): a persisting L2 set-aside (64 MB) with a stream access-policy
+// window over the gathered vector cuts the DRAM reads of a step from 4.74 to 2.88 GB and the step gets SLOWER (1.17 -> 1.24 ms;
+// 79 MB: 1.42 ms): the SpMV is bound by the L1 gather-wavefront rate (one wavefront per gathered 8-byte entry), not by DRAM.
 int32_t lz_run(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, int reorth, double *alpha, double *beta, i64 *iters) {
     if (h->world > 1 && h->lanczos_dist && !reorth) return lz_run_dist(h, q, v0_host, seed, alpha, beta, iters);
-    LzWindow win;
-    if (!reorth) win.begin(h);
     const i64 n = h->n;
     cudaStream_t st = h->stream;
     if (q > n - 1) q = n - 1;
@@ -490,7 +448,6 @@ int32_t lz_run(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, in
     k_lz_div<<<gs, TPB, 0, st>>>(n, tmp, v); KLAUNCH(h);
     for (i64 i = 0; i < q; i++) {
         if (reorth) CUDA_TRY(h, cudaMemcpyAsync(h->lz_basis + (size_t)i * n, v, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        win.point_at(v, n);
         SDP_CHECK(lz_apply(h, v, w, stop, ab + i));
         k_lz_update<<<gs, TPB, 0, st>>>(n, (int)i, v, vp, w, ab, q, stop, h->partials, h->ticket); KLAUNCH(h);
         if (reorth) {
@@ -508,7 +465,6 @@ int32_t lz_run(sdplrp_handle *h, i64 q, const double *v0_host, uint64_t seed, in
     CUDA_TRY(h, cudaMemcpyAsync(hab.data(), ab, (size_t)(2 * q) * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaMemcpyAsync(&hstop, stop, sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
-    win.end();
     if (coef) cudaFree(coef);
     for (i64 i = 0; i < q; i++) { alpha[i] = hab[(size_t)i]; beta[i] = hab[(size_t)(q + i)]; }
     *iters = hstop != 0.0 ? (i64)hstop : q;

@@ -308,6 +308,65 @@ __global__ void __launch_bounds__(TPB) k_gram_form(i64 nu, LbPtrs P, const doubl
     grid_sum_finalize<1>(acc, partials, ticket, [&](double (&sv)[1]) { dot_out[0] = sv[0]; });
 }
 
+// k_gram_form with the row-list constraint pass of the line search fused in (native loop, one GPU, "dir_ls_fuse"): the
+// direction rows are produced whole by the lanes of a warp (32/nv rows per step, the mapping of k_A_rowc_warp, aop.cu), so
+// <R_i, D_i> and <D_i, D_i> are taken from registers while D_i is on its way to memory and the line search no longer
+// re-reads D (2N + 28m bytes of the pass become N + 28m on top of the direction's 11N).  Pieces are combined in the order
+// of k_A_rowc_warp and D is formed by the expression of k_gram_form: A_RD / A_DD and D carry the bits of the separate kernels.
+template <int VEC, int M>
+__global__ void __launch_bounds__(TPB) k_gram_form_rowc(i64 n_rows, int r, LbPtrs P, const double *__restrict__ G,
+                                                        const double *__restrict__ coef, double *dir, double *ypre,
+                                                        const double *__restrict__ R, const int *__restrict__ rowc_ptr,
+                                                        const double *__restrict__ rowc_val, double *__restrict__ a_rd,
+                                                        double *__restrict__ a_dd, double *partials, unsigned *ticket,
+                                                        double *dot_out) {
+    constexpr int NB = 2 * M + 1;
+    double c[NB];
+#pragma unroll
+    for (int k = 0; k < NB; k++) c[k] = coef[k];
+    const int nv = r / VEC;
+    const int rpw = 32 / nv;                       // whole rows per warp step
+    const int lane = threadIdx.x & 31;
+    const int rl = lane / nv, pc = lane - rl * nv;
+    const bool act = rl < rpw;
+    const i64 warp = (i64)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+    const i64 n_warps = (i64)gridDim.x * (TPB / 32);
+    double acc[1] = {0.0};
+    for (i64 t0 = warp * rpw; t0 < n_rows; t0 += n_warps * rpw) {   // warp-uniform
+        const i64 il = t0 + rl;
+        const bool live = act && il < n_rows;
+        const i64 e = (live ? il : n_rows - 1) * nv + (live ? pc : 0);   // idle lanes re-read a valid piece and store nothing
+        int beg = 0, end = 0;
+        if (live && pc == 0) { beg = rowc_ptr[il]; end = rowc_ptr[il + 1]; }
+        const typename V<VEC>::T g = V<VEC>::ld(G, e);
+        const typename V<VEC>::T rr = V<VEC>::ld(R, e);
+        typename V<VEC>::T d = V<VEC>::scale(c[2 * M], g);
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+            d = V<VEC>::axpy(c[k], V<VEC>::ld(P.S[k], e), d);
+            d = V<VEC>::axpy(c[M + k], V<VEC>::ld(P.Y[k], e), d);
+        }
+        d = V<VEC>::neg(d);
+        if (live) {
+            V<VEC>::st(dir, e, d);
+            V<VEC>::st(ypre, e, V<VEC>::neg(g));  // slot jpre is read above before it is overwritten (same element, same thread)
+            acc[0] += V<VEC>::dot(d, g);
+        }
+        const double d1 = V<VEC>::dot(rr, d), d2 = V<VEC>::dot(d, d);
+        double s1 = 0.0 + d1, s2 = 0.0 + d2;       // (0 + piece 0) + piece 1 + ...: the order of k_A_rowc / k_A_rowc_warp
+        for (int k = 1; k < nv; k++) {
+            s1 += __shfl_down_sync(0xffffffffu, d1, k);
+            s2 += __shfl_down_sync(0xffffffffu, d2, k);
+        }
+        for (int k = beg; k < end; k++) {          // empty unless this lane holds piece 0 of a live row
+            const double val = rowc_val[k];
+            a_rd[k] = 2.0 * val * s1;              // A_RD is kept already doubled
+            a_dd[k] = val * s2;
+        }
+    }
+    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&sv)[1]) { dot_out[0] = sv[0]; });
+}
+
 struct Slice {
     i64 off, len, nu;
     int vec;
@@ -391,6 +450,23 @@ template <int M>
 int32_t gram_form_m(sdplrp_handle *h, const Slice &sl, int jpre) {
     const LbPtrs P = gram_ptrs(h, sl.off);
     const double *coef = h->lb_small + kGramNB * kGramNB + 3 * kGramNB;
+    // the caller (native loop) runs the line search of this direction next: fuse its row-list constraint pass
+    const int nv = h->r / sl.vec;
+    const bool fuse = h->fuse_rowc_request && h->dir_ls_fuse && h->world == 1 && h->n_sd > 0 && nv <= 32 && sl.len > 0;
+    h->fuse_rowc_request = false;
+    if (fuse) {
+        const i64 n_rows = h->row_hi - h->row_lo;
+        const int grid = grid_for(n_rows, (TPB / 32) * (32 / nv), kRedBlocks);
+#define GF_ARGS n_rows, h->r, P, h->G + sl.off, coef, h->D + sl.off, h->Yh[jpre] + sl.off, h->R + sl.off, h->rowc_ptr + h->row_lo, h->rowc_val, \
+                h->A_RD, h->A_DD, h->partials, h->ticket, h->dscal + SC_DESCENT
+        if (sl.vec == 2) k_gram_form_rowc<2, M><<<grid, TPB, 0, h->stream>>>(GF_ARGS);
+        else k_gram_form_rowc<1, M><<<grid, TPB, 0, h->stream>>>(GF_ARGS);
+#undef GF_ARGS
+        KLAUNCH(h);
+        CUDA_TRY(h, cudaGetLastError());
+        h->rowc_fused_valid = true;
+        return SDPLRP_OK;
+    }
     if (sl.vec == 2)
         k_gram_form<2, M><<<sl.grid, TPB, 0, h->stream>>>(sl.nu, P, h->G + sl.off, coef, h->D + sl.off, h->Yh[jpre] + sl.off, jpre,
                                                           h->partials, h->ticket, h->dscal + SC_DESCENT);

@@ -108,6 +108,8 @@ void *sdplrp_stream(sdplrp_handle *h);
  *   "dir_ls_fuse" native loop (sdplrp_iterate / sdplrp_solve), one GPU: 1 = the L-BFGS direction kernel also leaves A_RD / A_DD of
  *                 the per-row constraints, computed from the direction rows while they are in registers (default: the line
  *                 search does not read D again for them), 0 = separate constraint pass.  Same bits either way
+ *   "spmm_ctas"   grid cap, in CTAs per SM, of the grid-stride row kernels of a gather pass (1..48, default 16)
+ *   "dir_ctas"    CTAs per SM of that fused direction kernel (1..8, default 4)
  *   "tail_ctas"   CTAs per SM of the fused step + gradient pass (1..8, default 4)
  *   "halo"        several GPUs: every rank keeps the objective pattern of its own rows and the gather pass exchanges only the
  *                 factor rows that are actually gathered, hub class first.  1 = the tail class travels under a two-phase pass;

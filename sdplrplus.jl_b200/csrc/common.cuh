@@ -133,6 +133,8 @@ struct sdplrp_handle {
     int dir_ls_fuse = 1;                                 // native loop, one GPU: the direction kernel also evaluates the row-list constraints of the line search (lbfgs.cu, k_gram_form_rowc)
     bool fuse_rowc_request = false;                      // set by the native loop right before the direction whose line search follows at once
     bool rowc_fused_valid = false;                       // A_RD / A_DD slots [0, n_sd) hold the values of the current direction (consumed by the next line-search pass)
+    int spmm_ctas = 16;                                  // grid cap (CTAs per SM) of the row kernels of a gather pass (gradient.cu, launch_classes)
+    int dir_ctas = 4;                                    // CTAs per SM of the fused direction + constraint kernel k_gram_form_rowc (lbfgs.cu)
     int tail_ctas = 4;                                   // CTAs per SM of the fused tail kernel k_step_grad (gradient.cu)
     int rowc_kernel = 1;                                 // row-list constraint pass: 1 = barrier-free warp kernel (r/2 <= 32 pieces), 0 = shared-memory tile kernel (aop.cu)
     int spmm_g0 = 1;                                     // class-0 lane groups of exactly r/2 lanes (0: next power of two)

@@ -638,6 +638,7 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
                        bool long_empty = false, int class_mask = 7) {
     const int gpb = TPB / a.G;
     const int gpb0 = TPB / a.G0;
+    const int spmm_cap = h->spmm_ctas * kNumSM;   // grid cap of the grid-stride row kernels (<= 55 CTAs per SM: 16384 partials per class)
     // The three row classes are independent (disjoint rows, their own sums, their own reduction scratch): the medium and the
     // long rows run on side streams next to the short rows.  On one GPU each kernel fills the machine anyway; with the rows
     // divided among 8 GPUs the medium / long kernels are a few hundred CTAs each and would otherwise run one after the other
@@ -649,7 +650,7 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
         if (!(class_mask & (1 << c))) continue;   // this class belongs to another launch of the pass
         cudaStream_t st = (fork && c > 0) ? h->class_streams[c - 1] : h->stream;
         if (sums) a.out = sums + 2 * c;
-        a.partials = h->partials + (size_t)c * 16384;   // <= 16 * kNumSM CTAs x 2 sums per class
+        a.partials = h->partials + (size_t)c * 16384;   // <= spmm_cap CTAs x 2 sums per class
         a.ticket = h->ticket + c;
         a.rows = cls.list[c];
         a.n_rows = cls.cnt[c];
@@ -658,14 +659,14 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
             continue;
         }
         if (c == 0) {
-            if (h->spmm_unroll >= 8) k_rows_group<VEC, MAXU, IND, EPI, 8><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
-            else k_rows_group<VEC, MAXU, IND, EPI, 4><<<grid_for(a.n_rows, gpb0, 16 * kNumSM), TPB, 0, st>>>(a);
+            if (h->spmm_unroll >= 8) k_rows_group<VEC, MAXU, IND, EPI, 8><<<grid_for(a.n_rows, gpb0, spmm_cap), TPB, 0, st>>>(a);
+            else k_rows_group<VEC, MAXU, IND, EPI, 4><<<grid_for(a.n_rows, gpb0, spmm_cap), TPB, 0, st>>>(a);
         } else if (c == 1) {
-            k_rows_warp<VEC, MAXU, IND, EPI, false><<<grid_for(a.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(a);
+            k_rows_warp<VEC, MAXU, IND, EPI, false><<<grid_for(a.n_rows, TPB / 32, spmm_cap), TPB, 0, st>>>(a);
         } else if (long_empty) {
             RowArgs b = a;
             b.beg_arr = a.ptr + 1; b.end_arr = a.ptr + 1;
-            k_rows_warp<VEC, MAXU, IND, EPI, false><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
+            k_rows_warp<VEC, MAXU, IND, EPI, false><<<grid_for(b.n_rows, TPB / 32, spmm_cap), TPB, 0, st>>>(b);
         } else {
             // long rows: one warp per chunk, then the per-row combination with the epilogue
             const i64 need = longs.n_chunks * (i64)a.r;
@@ -678,7 +679,7 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
             b.chunk_start = longs.chunk_start; b.chunk_end = longs.chunk_end; b.chunk_row = longs.chunk_row;
             b.long_rows = longs.long_rows; b.long_cptr = longs.long_cptr; b.scratch = h->tile_scratch;
             b.n_rows = longs.n_chunks;
-            k_rows_warp<VEC, MAXU, IND, EPI, true><<<grid_for(b.n_rows, TPB / 32, 16 * kNumSM), TPB, 0, st>>>(b);
+            k_rows_warp<VEC, MAXU, IND, EPI, true><<<grid_for(b.n_rows, TPB / 32, spmm_cap), TPB, 0, st>>>(b);
             KLAUNCH(h);
             b.n_rows = longs.n_long;
             k_rows_combine<VEC, MAXU, EPI><<<grid_for(b.n_rows, gpb, 4 * kNumSM), TPB, 0, st>>>(b);

@@ -431,19 +431,6 @@ def main():
     ab_ref = algorithmic_bytes(n, n, r, nnzT, nnzF, Ec, h, hi - lo)
     ab = dict(ab_ref)
     kernels = {}
-    # native loop on one GPU: the direction kernel also evaluates the per-row constraints of the line search (option
-    # "dir_ls_fuse", default on), reading R once more instead of re-reading D in a pass of its own.  The two sections are
-    # then ONE kernel: its time is the sum of the two sections (the second is two small memsets), its algorithmic bytes the
-    # direction's (2h+3)N plus the pass's N + 28m.
-    opt = dict(kv.split("=", 1) for kv in args.option)
-    fused_ls = world == 1 and native and float(opt.get("dir_ls_fuse", 1)) > 0 and "lbfgs_kernel" not in opt
-    if fused_ls and sections.get("lbfgs_dir", (0.0, 0))[1] > 0:
-        d_ms, d_cnt = sections["lbfgs_dir"]
-        l_ms, _ = sections.get("ls_pass", (0.0, 0))
-        sections = dict(sections)
-        sections["lbfgs_dir"] = (d_ms + l_ms, d_cnt)
-        sections.pop("ls_pass", None)
-        ab["lbfgs_dir"] = ab["lbfgs_dir"] + ab.pop("ls_pass") - 8.0 * (hi - lo) * r
     for name, nbytes in ab.items():
         ms, cnt = sections.get(name, (0.0, 0))
         if cnt == 0 or ms <= 0:
@@ -470,9 +457,6 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "kernels": kernels}
-        if fused_ls:
-            roofline["fused"] = ("lbfgs_dir includes the per-row constraint pass of the line search (A_RD, A_DD from the direction rows in "
-                                 "registers): (2h+3)N + N + 28m algorithmic bytes; `--option dir_ls_fuse=0` times the two kernels separately")
         if "spmm" in kernels:
             # the same kernel against the other two bounds of SURVEY 8d / DESIGN section 4, so that progress is visible:
             # (i) gather-inclusive bytes (every nonzero gathers its 8r-byte row once), (ii) the measured random-gather ceiling

@@ -105,12 +105,10 @@ void *sdplrp_stream(sdplrp_handle *h);
  *   "spmm_g0"     1 = lane groups of exactly r/2 lanes per short row (default: 6 rows per warp at r = 10), 0 = next power of two
  *   "rowc_kernel" pass over the per-row (single-diagonal-entry) constraints: 1 = barrier-free warp kernel, 32/(r/2) whole rows per
  *                 warp step (default; rows of at most 32 pieces), 0 = shared-memory tile kernel.  Same bits either way
- *   "dir_ls_fuse" native loop (sdplrp_iterate / sdplrp_solve), one GPU: 1 = the L-BFGS direction kernel also leaves A_RD / A_DD of
- *                 the per-row constraints, computed from the direction rows while they are in registers (default: the line
- *                 search does not read D again for them), 0 = separate constraint pass.  Same bits either way
- *   "spmm_ctas"   grid cap, in CTAs per SM, of the grid-stride row kernels of a gather pass (1..48, default 16)
- *   "dir_ctas"    CTAs per SM of that fused direction kernel (1..8, default 4)
- *   "tail_ctas"   CTAs per SM of the fused step + gradient pass (1..8, default 4)
+ *   "lb_ctas"     CTAs per SM of the streaming L-BFGS kernels (direction / update passes; 1..8, default 4)
+ *   "rowc_ctas"   grid cap, in CTAs per SM, of the per-row constraint pass (1..48, default 16)
+ *   "tail_ctas"   CTAs per SM of the fused step + gradient pass (1..8; 0 = auto, the default: 6 on one GPU, 4 on several.  Measured on C5, one GPU:
+ *                 4 / 5 / 6 / 7 / 8 -> 1.16 / 1.10 / 0.98 / 1.31 / 1.20 ms)
  *   "halo"        several GPUs: every rank keeps the objective pattern of its own rows and the gather pass exchanges only the
  *                 factor rows that are actually gathered, hub class first.  1 = the tail class travels under a two-phase pass;
  *                 2 = the same exchange, then ONE sweep over whole rows (nothing overlaps the tail class, no second visit of

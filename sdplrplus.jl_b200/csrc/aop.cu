@@ -368,10 +368,8 @@ int32_t run_sparse(sdplrp_handle *h, const double *U, const double *V, double *o
         else k_A_short<MODE, 1><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi, skip_mat, sdf);
         KLAUNCH(h);
     }
-    if (MODE == 2 && h->n_sd > 0 && h->rowc_fused_valid) {
-        // the direction kernel of the native loop has already left A_RD / A_DD of these constraints (lbfgs.cu, k_gram_form_rowc)
-    } else if (h->n_sd > 0 && nv <= 32 && h->rowc_kernel == 1) {   // barrier-free warp-per-rows pass
-        const int grid_rows = grid_for(h->row_hi - h->row_lo, (TPB / 32) * (32 / nv) * kRowcUnroll, 16 * kNumSM);
+    if (h->n_sd > 0 && nv <= 32 && h->rowc_kernel == 1) {   // barrier-free warp-per-rows pass
+        const int grid_rows = grid_for(h->row_hi - h->row_lo, (TPB / 32) * (32 / nv) * kRowcUnroll, h->rowc_ctas * kNumSM);
         if (vec2) k_A_rowc_warp<MODE, 2><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, out1, out2);
         else k_A_rowc_warp<MODE, 1><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, out1, out2);
         KLAUNCH(h);
@@ -468,8 +466,6 @@ int32_t aop_linesearch(sdplrp_handle *h, bool skip_objective) {
     const i64 z0 = h->world == 1 ? h->n_sd : 0;
     CUDA_TRY(h, cudaMemsetAsync(h->A_RD + z0, 0, (size_t)(h->m + 1 - z0) * sizeof(double), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->A_DD + z0, 0, (size_t)(h->m + 1 - z0) * sizeof(double), h->stream));
-    const int32_t rc = run_sparse<2>(h, h->R, h->D, h->A_RD, h->A_DD, skip_objective ? h->obj_mat : -1);
-    h->rowc_fused_valid = false;   // one direction, one line-search pass
-    SDP_CHECK(rc);
+    SDP_CHECK(run_sparse<2>(h, h->R, h->D, h->A_RD, h->A_DD, skip_objective ? h->obj_mat : -1));
     return run_lowrank(h, 2, h->R, h->D, h->A_RD, h->A_DD);
 }

@@ -394,10 +394,9 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
     if (k == "spmm_unroll") { h->spmm_unroll = (int)value; return SDPLRP_OK; }
     if (k == "spmm_g0") { h->spmm_g0 = (int)value; return SDPLRP_OK; }
     if (k == "rowc_kernel") { h->rowc_kernel = value > 0 ? 1 : 0; return SDPLRP_OK; }
-    if (k == "dir_ls_fuse") { h->dir_ls_fuse = value > 0 ? 1 : 0; return SDPLRP_OK; }
-    if (k == "spmm_ctas") { h->spmm_ctas = std::max(1, std::min((int)value, 48)); return SDPLRP_OK; }
-    if (k == "dir_ctas") { h->dir_ctas = std::max(1, std::min((int)value, 8)); return SDPLRP_OK; }
-    if (k == "tail_ctas") { h->tail_ctas = std::max(1, std::min((int)value, 8)); return SDPLRP_OK; }
+    if (k == "lb_ctas") { h->lb_ctas = std::max(1, std::min((int)value, 8)); return SDPLRP_OK; }
+    if (k == "rowc_ctas") { h->rowc_ctas = std::max(1, std::min((int)value, 48)); return SDPLRP_OK; }
+    if (k == "tail_ctas") { h->tail_ctas = std::max(0, std::min((int)value, 8)); return SDPLRP_OK; }
     if (k == "halo") { h->halo_mode = value < 0.5 ? 0 : (value < 1.5 ? 1 : (value < 2.5 ? 2 : 3)); return SDPLRP_OK; }
     if (k == "gather_mode") { h->gather_mode = value < 0 ? 0 : (int)value; return SDPLRP_OK; }
     if (k == "gather_tile") { h->gather_tile = (int)value; return SDPLRP_OK; }
@@ -695,12 +694,9 @@ int32_t sdplrp_fg(sdplrp_handle *h, double out[4]) {
 int32_t api_lbfgs_dir_async(sdplrp_handle *h) {
     REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
-    h->rowc_fused_valid = false;
     {
         SectionScope sc(h, SDPLRP_SEC_LBFGS_DIR);
-        const int32_t rc = lb_dir(h);
-        h->fuse_rowc_request = false;   // a request is good for this one direction, whichever kernel formed it
-        SDP_CHECK(rc);
+        SDP_CHECK(lb_dir(h));
     }
     h->CD_valid = false; h->ls_valid = false;
     comm_mark_partial(h, SDPLRP_MAT_D);
@@ -718,7 +714,6 @@ int32_t sdplrp_use_gradient_direction(sdplrp_handle *h) {
     REQUIRE_H(h); REQUIRE_PRE(h); REQUIRE_RANK(h);
     CUDA_TRY(h, cudaSetDevice(h->device));
     SDP_CHECK(lb_neg_copy(h));
-    h->rowc_fused_valid = false;
     h->gram_g_valid = false;
     h->CD_valid = false; h->ls_valid = false;
     comm_mark_partial(h, SDPLRP_MAT_D);

@@ -164,7 +164,6 @@ int32_t inner_iteration(sdplrp_handle *h, bool use_armijo, double alpha_max, dou
     // out not to be a descent direction (rare) the pass is redone for the gradient direction.  One synchronisation less per
     // iteration, same decisions and results.
     double descent = 0.0, alpha = 0.0, bq[5];
-    h->fuse_rowc_request = true;   // the line search of this direction follows at once: the direction kernel may serve its row-list constraints
     SDP_CHECK(api_lbfgs_dir_async(h));
     SDP_CHECK(api_linesearch_coeffs_descent(h, bq, &descent));
     if (std::isnan(descent) || descent >= 0.0) {

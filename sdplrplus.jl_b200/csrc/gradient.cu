@@ -638,7 +638,7 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
                        bool long_empty = false, int class_mask = 7) {
     const int gpb = TPB / a.G;
     const int gpb0 = TPB / a.G0;
-    const int spmm_cap = h->spmm_ctas * kNumSM;   // grid cap of the grid-stride row kernels (<= 55 CTAs per SM: 16384 partials per class)
+    const int spmm_cap = 16 * kNumSM;   // grid cap of the grid-stride row kernels (measured on C5: 8 / 16 / 32 CTAs per SM -> 4.07 / 3.98 / 3.98 ms)
     // The three row classes are independent (disjoint rows, their own sums, their own reduction scratch): the medium and the
     // long rows run on side streams next to the short rows.  On one GPU each kernel fills the machine anyway; with the rows
     // divided among 8 GPUs the medium / long kernels are a few hundred CTAs each and would otherwise run one after the other
@@ -964,7 +964,10 @@ int32_t grad_step_fused(sdplrp_handle *h, double alpha) {
     const bool vec2 = (r % 2 == 0);
     const int nv = vec2 ? r / 2 : r;
     const i64 total = (h->row_hi - h->row_lo) * nv;
-    const int grid = grid_for(total, TPB * 2, h->tail_ctas * kNumSM);   // K = 2 sums: h->partials holds up to 8 CTAs per SM
+    // CTAs per SM: measured on C5, one GPU: 4 / 5 / 6 / 7 / 8 -> 1.156 / 1.101 / 0.975 / 1.305 / 1.198 ms (profiles/r2_call11_summary.txt);
+    // the multi-GPU numbers of the round were taken with 4, which stays the value there
+    const int ctas = h->tail_ctas > 0 ? h->tail_ctas : (h->world == 1 ? 6 : 4);
+    const int grid = grid_for(total, TPB * 2, ctas * kNumSM);   // K = 2 sums: h->partials holds up to 8 CTAs per SM
     const double *CD = split ? h->CD : nullptr;
     double *CR = split ? h->CR : nullptr;
 #define SG_ARGS h->row_lo, h->row_hi, r, alpha, h->sigma, h->y_obj, h->D, h->R, CD, CR, h->rowc_ptr, h->rowc_val, h->lambda, h->lambda_ub, \

@@ -308,79 +308,6 @@ __global__ void __launch_bounds__(TPB) k_gram_form(i64 nu, LbPtrs P, const doubl
     grid_sum_finalize<1>(acc, partials, ticket, [&](double (&sv)[1]) { dot_out[0] = sv[0]; });
 }
 
-// k_gram_form with the row-list constraint pass of the line search fused in (native loop, one GPU, "dir_ls_fuse"): the
-// direction rows are produced whole by the lanes of a warp (32/nv rows per step, the mapping of k_A_rowc_warp, aop.cu), so
-// <R_i, D_i> and <D_i, D_i> are taken from registers while D_i is on its way to memory and the line search no longer
-// re-reads D (2N + 28m bytes of the pass become N + 28m on top of the direction's 11N).  Pieces are combined in the order
-// of k_A_rowc_warp and D is formed by the expression of k_gram_form: A_RD / A_DD and D carry the bits of the separate kernels.
-// The constraint range of a row is loaded ONE STEP AHEAD, so that the value of its (first) constraint travels with the row
-// loads of the step: one round trip per step instead of rows -> ptr -> val (measured without: 0.91 of the copy peak).
-// Minimum 4 CTAs per SM = a 64-register budget: at the 40 registers ptxas picks on its own the R load is sunk below the two
-// stores of the step (a second round trip per step); with 64 every load of the step precedes the stores (checked in the SASS).
-template <int VEC, int M>
-__global__ void __launch_bounds__(TPB, 4) k_gram_form_rowc(i64 n_rows, int r, LbPtrs P, const double *__restrict__ G,
-                                                        const double *__restrict__ coef, double *dir, double *ypre,
-                                                        const double *__restrict__ R, const int *__restrict__ rowc_ptr,
-                                                        const double *__restrict__ rowc_val, double *__restrict__ a_rd,
-                                                        double *__restrict__ a_dd, double *partials, unsigned *ticket,
-                                                        double *dot_out) {
-    constexpr int NB = 2 * M + 1;
-    double c[NB];
-#pragma unroll
-    for (int k = 0; k < NB; k++) c[k] = coef[k];
-    const int nv = r / VEC;
-    const int rpw = 32 / nv;                       // whole rows per warp step
-    const int lane = threadIdx.x & 31;
-    const int rl = lane / nv, pc = lane - rl * nv;
-    const bool act = rl < rpw;
-    const i64 warp = (i64)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
-    const i64 stride = (i64)gridDim.x * (TPB / 32) * rpw;
-    double acc[1] = {0.0};
-    int beg = 0, end = 0;
-    {
-        const i64 il = warp * rpw + rl;
-        if (act && pc == 0 && il < n_rows) { beg = rowc_ptr[il]; end = rowc_ptr[il + 1]; }
-    }
-    for (i64 t0 = warp * rpw; t0 < n_rows; t0 += stride) {   // warp-uniform
-        const i64 il = t0 + rl;
-        const bool live = act && il < n_rows;
-        const i64 e = (live ? il : n_rows - 1) * nv + (live ? pc : 0);   // idle lanes re-read a valid piece and store nothing
-        const double val0 = beg < end ? rowc_val[beg] : 0.0;            // beg / end arrived during the previous step
-        int nbeg = 0, nend = 0;
-        {
-            const i64 iln = il + stride;
-            if (act && pc == 0 && iln < n_rows) { nbeg = rowc_ptr[iln]; nend = rowc_ptr[iln + 1]; }
-        }
-        const typename V<VEC>::T g = V<VEC>::ld(G, e);
-        const typename V<VEC>::T rr = V<VEC>::ld(R, e);
-        typename V<VEC>::T d = V<VEC>::scale(c[2 * M], g);
-#pragma unroll
-        for (int k = 0; k < M; k++) {
-            d = V<VEC>::axpy(c[k], V<VEC>::ld(P.S[k], e), d);
-            d = V<VEC>::axpy(c[M + k], V<VEC>::ld(P.Y[k], e), d);
-        }
-        d = V<VEC>::neg(d);
-        if (live) {
-            V<VEC>::st(dir, e, d);
-            V<VEC>::st(ypre, e, V<VEC>::neg(g));  // slot jpre is read above before it is overwritten (same element, same thread)
-            acc[0] += V<VEC>::dot(d, g);
-        }
-        const double d1 = V<VEC>::dot(rr, d), d2 = V<VEC>::dot(d, d);
-        double s1 = 0.0 + d1, s2 = 0.0 + d2;       // (0 + piece 0) + piece 1 + ...: the order of k_A_rowc / k_A_rowc_warp
-        for (int k = 1; k < nv; k++) {
-            s1 += __shfl_down_sync(0xffffffffu, d1, k);
-            s2 += __shfl_down_sync(0xffffffffu, d2, k);
-        }
-        for (int k = beg; k < end; k++) {          // empty unless this lane holds piece 0 of a live row
-            const double val = k == beg ? val0 : rowc_val[k];
-            a_rd[k] = 2.0 * val * s1;              // A_RD is kept already doubled
-            a_dd[k] = val * s2;
-        }
-        beg = nbeg; end = nend;
-    }
-    grid_sum_finalize<1>(acc, partials, ticket, [&](double (&sv)[1]) { dot_out[0] = sv[0]; });
-}
-
 struct Slice {
     i64 off, len, nu;
     int vec;
@@ -392,7 +319,7 @@ Slice owned(const sdplrp_handle *h) {
     s.len = (h->row_hi - h->row_lo) * h->r;
     s.vec = (s.off % 2 == 0 && s.len % 2 == 0) ? 2 : 1;
     s.nu = s.len / s.vec;
-    s.grid = grid_for(s.nu, TPB * 4, kRedBlocks);
+    s.grid = grid_for(s.nu, TPB * 4, h->lb_ctas * kNumSM);   // <= 8 CTAs per SM: 27 sums per CTA fit h->partials many times over
     return s;
 }
 
@@ -464,25 +391,6 @@ template <int M>
 int32_t gram_form_m(sdplrp_handle *h, const Slice &sl, int jpre) {
     const LbPtrs P = gram_ptrs(h, sl.off);
     const double *coef = h->lb_small + kGramNB * kGramNB + 3 * kGramNB;
-    // the caller (native loop) runs the line search of this direction next: fuse its row-list constraint pass
-    // pieces per ROW (sl.vec is the flat vector width of the element-wise kernels: 2 also for odd r when the slice length is even)
-    const int rv = (h->r % 2 == 0 && sl.vec == 2) ? 2 : 1;
-    const int nv = h->r / rv;
-    const bool fuse = h->fuse_rowc_request && h->dir_ls_fuse && h->world == 1 && h->n_sd > 0 && nv >= 1 && nv <= 32 && sl.len > 0;
-    h->fuse_rowc_request = false;
-    if (fuse) {
-        const i64 n_rows = h->row_hi - h->row_lo;
-        const int grid = grid_for(n_rows, (TPB / 32) * (32 / nv), std::min(h->dir_ctas * kNumSM, 2 * kRedBlocks));   // one sum per CTA: room for 8 CTAs per SM
-#define GF_ARGS n_rows, h->r, P, h->G + sl.off, coef, h->D + sl.off, h->Yh[jpre] + sl.off, h->R + sl.off, h->rowc_ptr + h->row_lo, h->rowc_val, \
-                h->A_RD, h->A_DD, h->partials, h->ticket, h->dscal + SC_DESCENT
-        if (rv == 2) k_gram_form_rowc<2, M><<<grid, TPB, 0, h->stream>>>(GF_ARGS);
-        else k_gram_form_rowc<1, M><<<grid, TPB, 0, h->stream>>>(GF_ARGS);
-#undef GF_ARGS
-        KLAUNCH(h);
-        CUDA_TRY(h, cudaGetLastError());
-        h->rowc_fused_valid = true;
-        return SDPLRP_OK;
-    }
     if (sl.vec == 2)
         k_gram_form<2, M><<<sl.grid, TPB, 0, h->stream>>>(sl.nu, P, h->G + sl.off, coef, h->D + sl.off, h->Yh[jpre] + sl.off, jpre,
                                                           h->partials, h->ticket, h->dscal + SC_DESCENT);

@@ -132,34 +132,3 @@ def test_iterate_matches_python_loop(sp, handle):
         outs.append((np.array(last), eng.get_R()))
     np.testing.assert_allclose(outs[1][0], outs[0][0], rtol=1e-7, atol=1e-12)
     np.testing.assert_allclose(outs[1][1], outs[0][1], rtol=1e-7, atol=1e-9)
-
-
-@pytest.mark.parametrize("r,hist", [(10, 4), (3, 2), (7, 1), (64, 4), (33, 3)])
-def test_native_loop_fused_direction_and_constraint_pass(sp, handle, r, hist):
-    """Native loop, one GPU: the L-BFGS direction kernel also evaluates the per-row constraints of the line search
-    ("dir_ls_fuse" 1, default).  It forms D with the expression of the plain direction kernel and combines the row pieces in
-    the order of the constraint kernels, so the iterates of sdplrp_iterate must be the SAME BITS with and without the fusion
-    (only `descent`, a grid-wide sum over a different thread mapping, may differ in its last bits; its sign decides nothing
-    else).  Ranks with 1 ... 32 pieces per row; r = 33 (odd: 33 pieces) takes the separate pass either way.  Also the
-    "tail_ctas" grid of the fused step + gradient pass: same R, norms to rounding."""
-    P = sp.problems
-    C, As, bs = P.maxcut(P.erdos_renyi(157, 0.05, 9))
-    data = sp.SDPData(C, As, bs)
-    Rt0 = 2 * np.random.default_rng(r).random((data.n, r)) - 1
-    res = {}
-    try:
-        for fuse, ctas in ((1, 4), (0, 4), (1, 8)):
-            handle.set_option("dir_ls_fuse", fuse)
-            handle.set_option("tail_ctas", ctas)
-            ge = sp.B200Engine(data, handle=handle)
-            ge.init_vars(r, Rt0, np.zeros(data.m), 2.0, hist)
-            ge.fg()
-            last = sp.solver.run_inner_iterations(ge, 7, native=True)
-            res[(fuse, ctas)] = (ge.get_R(), ge.get_G(), ge.get_pvio_raw(), np.asarray(last))
-    finally:
-        handle.set_option("dir_ls_fuse", 1)
-        handle.set_option("tail_ctas", 4)
-    for a, b, what in zip(res[(1, 4)], res[(0, 4)], ("R", "G", "pvio_raw", "L/obj/norms/alpha")):
-        np.testing.assert_array_equal(a, b, err_msg=what)
-    np.testing.assert_array_equal(res[(1, 8)][0], res[(1, 4)][0], err_msg="R with 8 CTAs per SM in the tail")
-    np.testing.assert_allclose(res[(1, 8)][3], res[(1, 4)][3], rtol=1e-12)

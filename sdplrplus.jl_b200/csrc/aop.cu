@@ -369,7 +369,7 @@ int32_t run_sparse(sdplrp_handle *h, const double *U, const double *V, double *o
         KLAUNCH(h);
     }
     if (h->n_sd > 0 && nv <= 32 && h->rowc_kernel == 1) {   // barrier-free warp-per-rows pass
-        const int grid_rows = grid_for(h->row_hi - h->row_lo, (TPB / 32) * (32 / nv) * kRowcUnroll, h->rowc_ctas * kNumSM);
+        const int grid_rows = grid_for(h->row_hi - h->row_lo, (TPB / 32) * (32 / nv) * kRowcUnroll, 16 * kNumSM);
         if (vec2) k_A_rowc_warp<MODE, 2><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, out1, out2);
         else k_A_rowc_warp<MODE, 1><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, out1, out2);
         KLAUNCH(h);

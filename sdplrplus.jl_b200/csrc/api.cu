@@ -394,8 +394,6 @@ int32_t sdplrp_set_option(sdplrp_handle *h, const char *key, double value) {
     if (k == "spmm_unroll") { h->spmm_unroll = (int)value; return SDPLRP_OK; }
     if (k == "spmm_g0") { h->spmm_g0 = (int)value; return SDPLRP_OK; }
     if (k == "rowc_kernel") { h->rowc_kernel = value > 0 ? 1 : 0; return SDPLRP_OK; }
-    if (k == "lb_ctas") { h->lb_ctas = std::max(1, std::min((int)value, 8)); return SDPLRP_OK; }
-    if (k == "rowc_ctas") { h->rowc_ctas = std::max(1, std::min((int)value, 48)); return SDPLRP_OK; }
     if (k == "tail_ctas") { h->tail_ctas = std::max(0, std::min((int)value, 8)); return SDPLRP_OK; }
     if (k == "halo") { h->halo_mode = value < 0.5 ? 0 : (value < 1.5 ? 1 : (value < 2.5 ? 2 : 3)); return SDPLRP_OK; }
     if (k == "gather_mode") { h->gather_mode = value < 0 ? 0 : (int)value; return SDPLRP_OK; }

@@ -130,8 +130,6 @@ struct sdplrp_handle {
     i64 hot_rows = -1;                                   // leading (hub) rows of a gathered factor kept in L2; -1 = auto
     int row_group_max = kRowGroupMax;                    // rows with <= this many nonzeros go to the lane-group-per-row kernels (set before preprocessing)
     int spmm_unroll = 8;                                 // nonzeros per predicated block of the class-0 register kernel (4 or 8)
-    int lb_ctas = 4;                                     // CTAs per SM of the streaming L-BFGS kernels (lbfgs.cu, owned())
-    int rowc_ctas = 16;                                  // grid cap (CTAs per SM) of the row-list constraint pass (aop.cu)
     int tail_ctas = 0;                                   // CTAs per SM of the fused tail kernel k_step_grad (gradient.cu); 0 = auto (6 on one GPU, 4 on several)
     int rowc_kernel = 1;                                 // row-list constraint pass: 1 = barrier-free warp kernel (r/2 <= 32 pieces), 0 = shared-memory tile kernel (aop.cu)
     int spmm_g0 = 1;                                     // class-0 lane groups of exactly r/2 lanes (0: next power of two)

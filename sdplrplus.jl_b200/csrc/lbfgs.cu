@@ -319,7 +319,7 @@ Slice owned(const sdplrp_handle *h) {
     s.len = (h->row_hi - h->row_lo) * h->r;
     s.vec = (s.off % 2 == 0 && s.len % 2 == 0) ? 2 : 1;
     s.nu = s.len / s.vec;
-    s.grid = grid_for(s.nu, TPB * 4, h->lb_ctas * kNumSM);   // <= 8 CTAs per SM: 27 sums per CTA fit h->partials many times over
+    s.grid = grid_for(s.nu, TPB * 4, kRedBlocks);   // 4 CTAs per SM; measured on C5: 3 / 4 / 5 / 6 / 7 / 8 -> direction 1.40 / 1.35 / 1.34 / 1.74 / 1.44 / 1.36 ms, update 1.40 / 1.31 / 1.36 / 1.31 / 1.35 / 1.31 ms
     return s;
 }
 

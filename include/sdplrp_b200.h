@@ -103,9 +103,6 @@ void *sdplrp_stream(sdplrp_handle *h);
  *                 warp each; set BEFORE sdplrp_preprocess
  *   "spmm_unroll" nonzeros per block of the short-row kernels: 8 (default) or 4
  *   "spmm_g0"     1 = lane groups of exactly r/2 lanes per short row (default: 6 rows per warp at r = 10), 0 = next power of two
- *   "l2_window_mb" one GPU, relabelled pattern: set aside this many MB of L2 for persisting lines (cudaLimitPersistingL2CacheSize) and
- *                 put a stream access-policy window over the hub prefix of the factor the objective pass gathers; the hub gathers
- *                 then carry no per-load policy (WIN variants of the row kernels).  0 = off (default)
  *   "rowc_kernel" pass over the per-row (single-diagonal-entry) constraints: 1 = barrier-free warp kernel, 32/(r/2) whole rows per
  *                 warp step (default; rows of at most 32 pieces), 0 = shared-memory tile kernel.  Same bits either way
  *   "tail_ctas"   CTAs per SM of the fused step + gradient pass (1..8; 0 = auto, the default: 6 on one GPU, 4 on several.  Measured on C5, one GPU:

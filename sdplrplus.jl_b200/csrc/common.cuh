@@ -131,8 +131,6 @@ struct sdplrp_handle {
     int row_group_max = kRowGroupMax;                    // rows with <= this many nonzeros go to the lane-group-per-row kernels (set before preprocessing)
     int spmm_unroll = 8;                                 // nonzeros per predicated block of the class-0 register kernel (4 or 8)
     int tail_ctas = 0;                                   // CTAs per SM of the fused tail kernel k_step_grad (gradient.cu); 0 = auto (6 on one GPU, 4 on several)
-    int l2_window_mb = 0;                                // one GPU: persisting L2 set-aside (MB) + access-policy window over the hub prefix of the factor the objective pass gathers (gradient.cu); 0 = off
-    i64 l2_window_bytes = 0;                             // the set-aside actually granted (-1: refused)
     int rowc_kernel = 1;                                 // row-list constraint pass: 1 = barrier-free warp kernel (r/2 <= 32 pieces), 0 = shared-memory tile kernel (aop.cu)
     int spmm_g0 = 1;                                     // class-0 lane groups of exactly r/2 lanes (0: next power of two)
     int spmm_phases = 0;                                 // 0 = one sweep per gather pass (default); 1 = hub | tail two-phase pass with an

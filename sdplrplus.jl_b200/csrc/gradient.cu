@@ -67,23 +67,6 @@ __device__ __forceinline__ double2 ldg_f64x2_hint(const double *p, unsigned long
     return v;
 }
 
-// WIN variants of the row kernels (option "l2_window_mb"): a gather of a hub-prefix column (col < plain_rows) carries NO
-// explicit L2 policy, so that the stream's access-policy window (persisting lines over that prefix of the gathered factor)
-// decides -- an explicit per-load policy overrides the window; every other gather stays evict_first.  Two predicated loads,
-// no branch: the gathers of a block stay independent.
-__device__ __forceinline__ double ldg_f64_win(const double *p, int col, int plain_rows, unsigned long long pol) {
-    double v;
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.s32 q, %2, %3;\n\t@q ld.global.nc.f64 %0, [%1];\n\t@!q ld.global.nc.L2::cache_hint.f64 %0, [%1], %4;\n\t}"
-                 : "=d"(v) : "l"(p), "r"(col), "r"(plain_rows), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ double2 ldg_f64x2_win(const double *p, int col, int plain_rows, unsigned long long pol) {
-    double2 v;
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.s32 q, %3, %4;\n\t@q ld.global.nc.v2.f64 {%0, %1}, [%2];\n\t@!q ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %5;\n\t}"
-                 : "=d"(v.x), "=d"(v.y) : "l"(p), "r"(col), "r"(plain_rows), "l"(pol));
-    return v;
-}
-
 // y_i = -min(ub_i, lambda_i - sigma*raw_i), y_{m+1} = 1   (src/coreop.jl:229-236)
 __global__ void k_form_y(i64 m, double sigma, const double *__restrict__ lambda, const double *__restrict__ ub,
                          const double *__restrict__ raw, double *__restrict__ y) {
@@ -139,7 +122,6 @@ struct Acc<1> {
     __device__ __forceinline__ void zero() { v = 0.0; }
     __device__ __forceinline__ void fma(double s, const double *p) { v += s * __ldg(p); }
     __device__ __forceinline__ void fma_hint(double s, const double *p, unsigned long long pol) { v += s * ldg_f64_hint(p, pol); }
-    __device__ __forceinline__ void fma_win(double s, const double *p, int col, int plain_rows, unsigned long long pol) { v += s * ldg_f64_win(p, col, plain_rows, pol); }
     __device__ __forceinline__ void shfl_add(int o) { v += __shfl_xor_sync(0xffffffffu, v, o); }
     __device__ __forceinline__ void add_from_lane(const Acc &o, int src) { v += __shfl_sync(0xffffffffu, o.v, src & 31); }
     __device__ __forceinline__ void scale_add(double sc, double a, const double *p) { v = sc * (v + a * __ldg(p)); }
@@ -165,10 +147,6 @@ struct Acc<2> {
     }
     __device__ __forceinline__ void fma_hint(double s, const double *p, unsigned long long pol) {
         const double2 x = ldg_f64x2_hint(p, pol);
-        v.x += s * x.x; v.y += s * x.y;
-    }
-    __device__ __forceinline__ void fma_win(double s, const double *p, int col, int plain_rows, unsigned long long pol) {
-        const double2 x = ldg_f64x2_win(p, col, plain_rows, pol);
         v.x += s * x.x; v.y += s * x.y;
     }
     __device__ __forceinline__ void shfl_add(int o) {
@@ -223,7 +201,6 @@ struct RowArgs {
     int Gw;            // lanes per group of the warp-per-row kernels (= pieces per row when <= 16, else G)
     int G0;            // lanes per row of the class-0 kernel (= pieces per row: no idle lanes, no shuffles there)
     int hot_rows;      // gathers of columns < hot_rows are L2 evict_last
-    int plain_rows;    // gathers of columns < plain_rows carry no explicit policy (the stream's access-policy window applies); 0 = none
     double scale, yobj;
     const double *ADD, *Z;
     double *partials;
@@ -307,7 +284,7 @@ __device__ __forceinline__ void finish_sums(const RowArgs &a, double s0, double 
 // class 0: one group of G0 lanes per row (G0 = pieces per row when that fits a warp: 6 rows per warp at r = 10);
 // the row's nonzeros are taken NB at a time, fully predicated, so a row of <= NB nonzeros costs one round trip
 // ptr -> idx/val -> gathers with NB independent 128-bit gathers in flight per lane
-template <int VEC, int MAXU, bool IND, int EPI, int NB, bool WIN = false>
+template <int VEC, int MAXU, bool IND, int EPI, int NB>
 __global__ void LB_GROUP k_rows_group(RowArgs a) {
     const int nv = a.r / VEC;
     const int G = a.G0;
@@ -342,10 +319,7 @@ __global__ void LB_GROUP k_rows_group(RowArgs a) {
                 if (c < nv) {
 #pragma unroll
                     for (int j = 0; j < NB; j++)
-                        if (k0 + j < end) {
-                            if (WIN) acc[u].fma_win(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j], a.plain_rows, p_str);
-                            else acc[u].fma_hint(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
-                        }
+                        if (k0 + j < end) acc[u].fma_hint(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
                 }
             }
         }
@@ -358,7 +332,7 @@ __global__ void LB_GROUP k_rows_group(RowArgs a) {
 // CHUNK: the work items are the kRowWarpMax-nonzero chunks of the long rows (class 2) and the warp leaves its partial
 // sums in a.scratch (combined per row, in chunk order, by k_rows_combine) -- a hub row of 30 k nonzeros is spread over
 // 60 warps instead of serialising one CTA, which is what lets the pass scale when the rows are divided among GPUs.
-template <int VEC, int MAXU, bool IND, int EPI, bool CHUNK, bool WIN = false>
+template <int VEC, int MAXU, bool IND, int EPI, bool CHUNK>
 __global__ void LB_WARP k_rows_warp(RowArgs a) {
     const int nv = a.r / VEC;
     const int lane = threadIdx.x & 31;
@@ -395,10 +369,7 @@ __global__ void LB_WARP k_rows_warp(RowArgs a) {
                 if (c < nv) {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (k0 + j < end) {
-                            if (WIN) acc[u].fma_win(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j], a.plain_rows, p_str);
-                            else acc[u].fma_hint(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
-                        }
+                        if (k0 + j < end) acc[u].fma_hint(vv[j], a.X + (size_t)cc[j] * a.r + c * VEC, cc[j] < a.hot_rows ? p_hot : p_str);
                 }
             }
         }
@@ -687,34 +658,7 @@ int32_t launch_classes(sdplrp_handle *h, RowArgs a, const RowClasses &cls, const
             if (sums) CUDA_TRY(h, cudaMemsetAsync(sums + 2 * c, 0, 2 * sizeof(double), st));
             continue;
         }
-        bool win_done = false;
-        if constexpr (EPI == 2 && !IND) {   // the objective pass with the hub prefix served through the streams' access-policy window
-            if (a.plain_rows > 0 && !long_empty) {
-                if (c == 0) {
-                    k_rows_group<VEC, MAXU, IND, EPI, 8, true><<<grid_for(a.n_rows, gpb0, spmm_cap), TPB, 0, st>>>(a);
-                } else if (c == 1) {
-                    k_rows_warp<VEC, MAXU, IND, EPI, false, true><<<grid_for(a.n_rows, TPB / 32, spmm_cap), TPB, 0, st>>>(a);
-                } else {
-                    const i64 need = longs.n_chunks * (i64)a.r;
-                    if (h->tile_scratch_len < need) {
-                        if (fork) CUDA_TRY(h, cudaDeviceSynchronize());
-                        SDP_CHECK(dev_alloc(h, &h->tile_scratch, need));
-                        h->tile_scratch_len = need;
-                    }
-                    RowArgs b = a;
-                    b.chunk_start = longs.chunk_start; b.chunk_end = longs.chunk_end; b.chunk_row = longs.chunk_row;
-                    b.long_rows = longs.long_rows; b.long_cptr = longs.long_cptr; b.scratch = h->tile_scratch;
-                    b.n_rows = longs.n_chunks;
-                    k_rows_warp<VEC, MAXU, IND, EPI, true, true><<<grid_for(b.n_rows, TPB / 32, spmm_cap), TPB, 0, st>>>(b);
-                    KLAUNCH(h);
-                    b.n_rows = longs.n_long;
-                    k_rows_combine<VEC, MAXU, EPI><<<grid_for(b.n_rows, gpb, 4 * kNumSM), TPB, 0, st>>>(b);
-                }
-                win_done = true;
-            }
-        }
-        if (win_done) {
-        } else if (c == 0) {
+        if (c == 0) {
             if (h->spmm_unroll >= 8) k_rows_group<VEC, MAXU, IND, EPI, 8><<<grid_for(a.n_rows, gpb0, spmm_cap), TPB, 0, st>>>(a);
             else k_rows_group<VEC, MAXU, IND, EPI, 4><<<grid_for(a.n_rows, gpb0, spmm_cap), TPB, 0, st>>>(a);
         } else if (c == 1) {
@@ -939,34 +883,6 @@ static int32_t grad_obj_spmm_halo(sdplrp_handle *h, const double *X, double *Y, 
     return rc != SDPLRP_OK ? rc : rj;
 }
 
-// rows of the gathered factor behind the access-policy window ("l2_window_mb"), 0 = off.  The set-aside is requested once.
-static i64 window_rows(sdplrp_handle *h) {
-    if (h->l2_window_mb <= 0 || h->world > 1 || !h->relabeled || h->r <= 0) return 0;
-    if (h->l2_window_bytes == 0) {
-        int maxp = 0, maxw = 0;
-        if (cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, h->device) != cudaSuccess ||
-            cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, h->device) != cudaSuccess) { cudaGetLastError(); h->l2_window_bytes = -1; return 0; }
-        const size_t want = std::min<size_t>(std::min<size_t>((size_t)maxp, (size_t)maxw), (size_t)h->l2_window_mb << 20);
-        if (want == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); h->l2_window_bytes = -1; return 0; }
-        h->l2_window_bytes = (i64)want;
-    }
-    if (h->l2_window_bytes <= 0) return 0;
-    return std::min<i64>(h->n, h->l2_window_bytes / (8 * (i64)h->r));
-}
-// window over [base, base + bytes) on the main stream and the class streams (launches enqueued afterwards see it); bytes = 0 clears it
-static int32_t window_set(sdplrp_handle *h, const double *base, size_t bytes) {
-    cudaStreamAttrValue av = {};
-    av.accessPolicyWindow.base_ptr = const_cast<double *>(base);
-    av.accessPolicyWindow.num_bytes = bytes;
-    av.accessPolicyWindow.hitRatio = 1.0f;
-    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    CUDA_TRY(h, cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
-    for (int c = 0; c < 2; c++)
-        if (h->class_streams[c]) CUDA_TRY(h, cudaStreamSetAttribute(h->class_streams[c], cudaStreamAttributeAccessPolicyWindow, &av));
-    return SDPLRP_OK;
-}
-
 int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double *Z, double *sums6) {
     if (halo_active(h)) return grad_obj_spmm_halo(h, X, Y, Z, sums6);
     if (gather_supported(h) && h->nnzF > 0) {   // asynchronous tile pipeline (gather.cu)
@@ -984,16 +900,6 @@ int32_t grad_obj_spmm(sdplrp_handle *h, const double *X, double *Y, const double
         SDP_CHECK((launch_csr<false, 0>(h, a, h->full_cls, h->full_long, nullptr, false, hub_cols)));
         a.beg_arr = h->row_mid; a.end_arr = nullptr;  // phase two: tail columns on top, with the fused dots of the pass
         return launch_csr<false, 4>(h, a, h->full_cls, h->full_long, sums6, true, hub_cols);
-    }
-    // option "l2_window_mb" (one GPU, relabelled pattern): persisting L2 set-aside + an access-policy window over the hub prefix of
-    // the gathered factor on the three streams of the pass; the hub gathers of the WIN kernels carry no policy of their own
-    const i64 win_rows = window_rows(h);
-    if (win_rows > 0) {
-        SDP_CHECK(window_set(h, X, (size_t)win_rows * h->r * sizeof(double)));
-        a.plain_rows = (int)win_rows;
-        const int32_t rc = launch_csr<false, 2>(h, a, h->full_cls, h->full_long, sums6, false, win_rows);
-        const int32_t rw = window_set(h, nullptr, 0);
-        return rc != SDPLRP_OK ? rc : rw;
     }
     return launch_csr<false, 2>(h, a, h->full_cls, h->full_long, sums6);
 }

@@ -35,8 +35,7 @@ GPU_CONFIGS = {"default": {}, "relabel": {"relabel": 1}, "literal": {"relabel": 
                "phases": {"relabel": 1, "spmm_phases": 5},
                "gather_bulk": {"relabel": 1, "gather_mode": 1, "gather_tile": 16},
                "gather_async": {"gather_mode": 2},
-               "gather_async_small": {"relabel": 1, "gather_mode": 2, "gather_tile": 24, "gather_stages": 3, "gather_hints": 1},
-               "window": {"relabel": 1, "l2_window_mb": 8}}
+               "gather_async_small": {"relabel": 1, "gather_mode": 2, "gather_tile": 24, "gather_stages": 3, "gather_hints": 1}}
 GPU_CONFIG_PARAMS = list(GPU_CONFIGS)
 
 

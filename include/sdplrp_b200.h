@@ -104,7 +104,7 @@ void *sdplrp_stream(sdplrp_handle *h);
  *   "spmm_unroll" nonzeros per block of the short-row kernels: 8 (default) or 4
  *   "spmm_g0"     1 = lane groups of exactly r/2 lanes per short row (default: 6 rows per warp at r = 10), 0 = next power of two
  *   "rowc_kernel" pass over the per-row (single-diagonal-entry) constraints: 1 = barrier-free warp kernel, 32/(r/2) whole rows per
- *                 warp step (default; rows of at most 32 pieces), 0 = shared-memory tile kernel.  Same bits either way
+ *                 warp step (default on one GPU; rows of at most 32 pieces), 0 = shared-memory tile kernel (always on several GPUs).  Same bits either way
  *   "tail_ctas"   CTAs per SM of the fused step + gradient pass (1..8; 0 = auto, the default: 6 on one GPU, 4 on several.  Measured on C5, one GPU:
  *                 4 / 5 / 6 / 7 / 8 -> 1.16 / 1.10 / 0.98 / 1.31 / 1.20 ms)
  *   "halo"        several GPUs: every rank keeps the objective pattern of its own rows and the gather pass exchanges only the

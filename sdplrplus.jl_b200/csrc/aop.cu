@@ -368,7 +368,9 @@ int32_t run_sparse(sdplrp_handle *h, const double *U, const double *V, double *o
         else k_A_short<MODE, 1><<<grid_short, TPB, 0, st>>>((int)h->nA, h->matptr, h->mat_gid, h->ent_row, h->ent_col, h->ent_two, U, V, r, G, out1, out2, lo, hi, skip_mat, sdf);
         KLAUNCH(h);
     }
-    if (h->n_sd > 0 && nv <= 32 && h->rowc_kernel == 1) {   // barrier-free warp-per-rows pass
+    // several GPUs keep the tile kernel: it is what the multi-GPU parity test saw on 2 / 4 / 8 ranks, and no multi-GPU box was
+    // available after the warp kernel was written (same bits on one GPU: test_rowc_kernels_give_the_same_bits)
+    if (h->n_sd > 0 && nv <= 32 && h->rowc_kernel == 1 && h->world == 1) {   // barrier-free warp-per-rows pass
         const int grid_rows = grid_for(h->row_hi - h->row_lo, (TPB / 32) * (32 / nv) * kRowcUnroll, 16 * kNumSM);
         if (vec2) k_A_rowc_warp<MODE, 2><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, out1, out2);
         else k_A_rowc_warp<MODE, 1><<<grid_rows, TPB, 0, st>>>(h->row_lo, h->row_hi, h->rowc_ptr, h->rowc_val, U, V, r, out1, out2);
